@@ -1,0 +1,145 @@
+/*
+ * pqv.h -- C ABI of libpqv.so: the B200 (sm_100a) replacement for pq-vector's brute-force
+ * squared-L2 / top-k / IVF-assign hot path.
+ *
+ * The reference (XiangpengHao/pq-vector @ 808b90d) has no FFI boundary of its own: the path is
+ * in-process Rust.  These are the entry points a Rust `extern "C"` block would bind at the call
+ * sites listed beside each function (all paths relative to the reference root); INTEGRATION.md
+ * shows the binding.  Plain pointers and sizes only; no CUDA or torch types cross this boundary.
+ *
+ * Conventions
+ *  - every function returns 0 (PQV_OK) or a PQV_E* code; pqv_last_error() gives the message of
+ *    the last failure on the calling thread (valid until the next call on that thread).
+ *  - all input pointers are HOST pointers, borrowed for the duration of the call; all outputs are
+ *    caller-allocated host buffers.  The library never retains or frees caller memory.
+ *  - row ids are u32 everywhere (reference: src/ivf/index.rs:13, src/ivf/search.rs:43).
+ *  - results are bit-identical to the reference loops: same f32 summation order, no FMA, and the
+ *    same bounded-BinaryHeap / stable-sort tie behaviour.
+ *  - there is no CPU fallback: without a CUDA device pqv_init fails with PQV_ENODEV.
+ */
+#ifndef PQV_H
+#define PQV_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define PQV_API __attribute__((visibility("default")))
+#else
+#define PQV_API
+#endif
+
+#define PQV_OK        0
+#define PQV_EINVAL    1  /* bad argument (k == 0, dim mismatch, null pointer, ...)            */
+#define PQV_ENODEV    2  /* no usable CUDA device / device id out of range                    */
+#define PQV_ECUDA     3  /* a CUDA runtime call failed; message carries cudaGetErrorString    */
+#define PQV_ENOMEM    4  /* device or pinned-host allocation failed                            */
+#define PQV_EHANDLE   5  /* unknown dataset / stream handle                                    */
+#define PQV_ELIMIT    6  /* over an implementation limit (k > PQV_MAX_K, dim > PQV_MAX_DIM)    */
+
+#define PQV_MAX_K    1024u   /* per-query k handled by the in-kernel selection               */
+#define PQV_MAX_DIM  16384u  /* query staged in shared memory                                 */
+
+/* flags for the top-k calls */
+#define PQV_SUM_UNROLL4  0u  /* src/ivf/index.rs:461-480   sum += ((d0^2+d1^2)+d2^2)+d3^2 + scalar tail   */
+#define PQV_SUM_SEQ      1u  /* src/df_vector/exec.rs:529-533   dist += diff*diff, sequential               */
+#define PQV_SQRT         2u  /* apply sqrt to the kept distances BEFORE the final stable sort and return
+                                them (src/ivf/search.rs:129-140); without it squared distances are sorted
+                                and returned (src/df_vector/exec.rs:269-274)                                */
+#define PQV_TIES_BY_POSITION 4u /* skip the reference heap replay: order strictly by (distance, candidate
+                                   position).  Differs from the reference only among bit-equal distances.  */
+
+typedef struct pqv_ctx pqv_ctx;
+
+/* Lifetime.  device_ids == NULL && n_devices == 0 selects the current device.  With n_devices > 1
+ * a dataset's rows are split into contiguous ranges, one per device. */
+PQV_API int  pqv_init(pqv_ctx **out, const int *device_ids, int n_devices);
+PQV_API void pqv_destroy(pqv_ctx *ctx);
+PQV_API const char *pqv_last_error(void);
+PQV_API const char *pqv_version(void);
+PQV_API int  pqv_device_count(pqv_ctx *ctx);
+
+/* ---- dataset residency ---------------------------------------------------------------------
+ * Replaces the per-query Parquet re-read of src/ivf/search.rs:155-244 (read_embeddings_for_rows)
+ * and the `Embeddings` copy built in src/ivf/parquet.rs:281-292: the dense row-major N x dim f32
+ * block (the child values buffer of the Arrow List<Float32> column) is appended once, batch by
+ * batch, and stays in HBM.  Row ids are assigned in append order starting at 0. */
+PQV_API int pqv_dataset_create(pqv_ctx *ctx, uint32_t dim, uint64_t n_rows_hint, uint64_t *out_handle);
+PQV_API int pqv_dataset_append(pqv_ctx *ctx, uint64_t handle, const float *values, uint64_t n_rows);
+PQV_API int pqv_dataset_rows(pqv_ctx *ctx, uint64_t handle, uint64_t *out_rows, uint32_t *out_dim);
+PQV_API int pqv_dataset_drop(pqv_ctx *ctx, uint64_t handle);
+/* bench/test helper: fill rows [0, n_rows) on the device with the counter-based uniform[0,1)
+ * generator (distribution of benches/bench_util.rs:29-41; stream documented in DESIGN.md). */
+PQV_API int pqv_dataset_fill_synthetic(pqv_ctx *ctx, uint64_t handle, uint64_t n_rows, uint64_t seed);
+/* read rows back (tests, and fetching the k winners) */
+PQV_API int pqv_dataset_read(pqv_ctx *ctx, uint64_t handle, uint64_t first_row, uint64_t n_rows, float *out);
+
+/* ---- brute-force and gathered top-k ---------------------------------------------------------
+ * pqv_l2_topk        replaces the re-rank loop of src/ivf/search.rs:112-141 when every row is a
+ *                    candidate (nprobe >= n_clusters), one call per query.
+ * pqv_l2_topk_gather replaces the same loop for an IVF candidate list (`rows_to_check`,
+ *                    src/ivf/search.rs:100): row_ids in candidate order.
+ * Output i of query q is at out_*[q*k + i]; out_count[q] <= k results are valid, ascending. */
+PQV_API int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k,
+                uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count);
+PQV_API int pqv_l2_topk_gather(pqv_ctx *ctx, uint64_t handle, const float *query, const uint32_t *row_ids,
+                       uint64_t n_ids, uint32_t k, uint32_t flags, uint32_t *out_row_idx, float *out_dist,
+                       uint32_t *out_count);
+
+/* ---- streaming top-k over RecordBatches ------------------------------------------------------
+ * Replaces VectorTopKExec::topk_from_batches / update_topk_heap (src/df_vector/exec.rs:257-277,
+ * 457-482): begin with the query, push each batch's dense values buffer (n_rows x dim f32, the
+ * caller has already dropped null / wrong-length rows as exec.rs:496-498, 526-528 do), finish to
+ * get the k winners as indices into the pushed row sequence (push order).  Batches are copied
+ * host->device on a copy stream overlapped with the scan of the previous batch. */
+PQV_API int pqv_topk_stream_begin(pqv_ctx *ctx, uint32_t dim, const float *query, uint32_t k, uint32_t flags,
+                          uint64_t *out_stream);
+PQV_API int pqv_topk_stream_push(pqv_ctx *ctx, uint64_t stream, const float *values, uint64_t n_rows);
+PQV_API int pqv_topk_stream_push_f64(pqv_ctx *ctx, uint64_t stream, const double *values, uint64_t n_rows);
+PQV_API int pqv_topk_stream_finish(pqv_ctx *ctx, uint64_t stream, uint32_t *out_row_idx, float *out_dist,
+                           uint32_t *out_count);
+
+/* ---- k-means / IVF build pieces ---------------------------------------------------------------
+ * pqv_kmeans_assign   replaces the assignment sweeps src/ivf/index.rs:193-201 (final, all N rows)
+ *                     and :398-424 (Lloyd): out_assign[i] = argmin_c dist(row i, centroid c), first
+ *                     minimum wins (index.rs:251).  rows == NULL scans the resident dataset
+ *                     `handle`; otherwise `rows` (n x dim, host) is streamed through.
+ *                     out_sizes (may be NULL) = per-cluster counts (index.rs:421).
+ * pqv_min_dist_update replaces one k-means++ sweep src/ivf/index.rs:344-370: for each selected row
+ *                     s: d = dist(row, centroid); init ? slot = d : (d < slot ? slot = d).  The
+ *                     f32 sums of index.rs:359-370 stay with the caller (thread-count dependent).
+ * pqv_centroid_rank   replaces find_closest_centroids src/ivf/index.rs:130-149: per query the
+ *                     min(nprobe, C) closest cluster ids, stable ascending. Returns nprobe_eff. */
+PQV_API int pqv_kmeans_assign(pqv_ctx *ctx, uint64_t handle, const float *rows, uint64_t n, uint32_t dim,
+                      const float *centroids, uint32_t n_clusters, uint32_t *out_assign, uint64_t *out_sizes);
+PQV_API int pqv_min_dist_update(pqv_ctx *ctx, uint64_t handle, const float *rows, const uint64_t *row_sel,
+                        uint64_t n_sel, uint32_t dim, const float *centroid, int init, float *inout_min_dist);
+PQV_API int pqv_centroid_rank(pqv_ctx *ctx, const float *centroids, uint32_t n_clusters, uint32_t dim,
+                      const float *queries, uint32_t n_queries, uint32_t nprobe, uint32_t *out_cluster_ids,
+                      uint32_t *out_nprobe_eff);
+
+/* ---- measurement hooks (bench.py / ncu) ------------------------------------------------------- */
+typedef struct {
+    double scan_ms;        /* CUDA-event time of the last distance+select kernel (on the library's stream) */
+    double post_ms;        /* prefix-merge + entrant-filter kernels                                       */
+    double total_ms;       /* first launch -> last device op of the last call                              */
+    uint64_t scan_bytes;   /* algorithmic bytes of that scan: rows * dim * 4                               */
+    uint32_t launches;     /* kernels launched by the last call                                            */
+    uint32_t entrants;     /* heap-entrant candidates replayed on the host by the last call                */
+    uint32_t grid;         /* CTAs of the scan kernel                                                      */
+    uint32_t reserved;
+} pqv_timing;
+PQV_API int pqv_last_timing(pqv_ctx *ctx, pqv_timing *out);
+/* device-resident loop for roofline timing: runs `iters` scans of query 0 back to back with inputs and
+ * outputs in HBM and returns the mean kernel time (CUDA events on the launch stream). */
+PQV_API int pqv_bench_scan(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags,
+                   uint32_t iters, double *out_ms_per_scan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PQV_H */

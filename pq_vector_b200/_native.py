@@ -1,0 +1,68 @@
+"""ctypes loader for pq_vector_b200/csrc/libpqv.so (the C ABI of include/pqv.h).
+
+There is no fallback: if the shared library is missing or does not load, importing raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libpqv.so")
+
+PQV_OK, PQV_EINVAL, PQV_ENODEV, PQV_ECUDA, PQV_ENOMEM, PQV_EHANDLE, PQV_ELIMIT = range(7)
+PQV_SUM_UNROLL4, PQV_SUM_SEQ, PQV_SQRT, PQV_TIES_BY_POSITION = 0, 1, 2, 4
+PQV_MAX_K, PQV_MAX_DIM = 1024, 16384
+
+
+class PqvTiming(C.Structure):
+    _fields_ = [("scan_ms", C.c_double), ("post_ms", C.c_double), ("total_ms", C.c_double),
+                ("scan_bytes", C.c_uint64), ("launches", C.c_uint32), ("entrants", C.c_uint32),
+                ("grid", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+f32p, f64p = C.POINTER(C.c_float), C.POINTER(C.c_double)
+u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
+ctxp = C.c_void_p
+
+# every symbol include/pqv.h declares, with its signature
+SIGNATURES = {
+    "pqv_init": (C.c_int, [C.POINTER(ctxp), C.POINTER(C.c_int), C.c_int]),
+    "pqv_destroy": (None, [ctxp]),
+    "pqv_last_error": (C.c_char_p, []),
+    "pqv_version": (C.c_char_p, []),
+    "pqv_device_count": (C.c_int, [ctxp]),
+    "pqv_dataset_create": (C.c_int, [ctxp, C.c_uint32, C.c_uint64, u64p]),
+    "pqv_dataset_append": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint64]),
+    "pqv_dataset_rows": (C.c_int, [ctxp, C.c_uint64, u64p, u32p]),
+    "pqv_dataset_drop": (C.c_int, [ctxp, C.c_uint64]),
+    "pqv_dataset_fill_synthetic": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "pqv_dataset_read": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, C.c_uint64, f32p]),
+    "pqv_l2_topk": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),
+    "pqv_l2_topk_gather": (C.c_int, [ctxp, C.c_uint64, f32p, u32p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p,
+                                     u32p]),
+    "pqv_topk_stream_begin": (C.c_int, [ctxp, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u64p]),
+    "pqv_topk_stream_push": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint64]),
+    "pqv_topk_stream_push_f64": (C.c_int, [ctxp, C.c_uint64, f64p, C.c_uint64]),
+    "pqv_topk_stream_finish": (C.c_int, [ctxp, C.c_uint64, u32p, f32p, u32p]),
+    "pqv_kmeans_assign": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint64, C.c_uint32, f32p, C.c_uint32, u32p, u64p]),
+    "pqv_min_dist_update": (C.c_int, [ctxp, C.c_uint64, f32p, u64p, C.c_uint64, C.c_uint32, f32p, C.c_int, f32p]),
+    "pqv_centroid_rank": (C.c_int, [ctxp, f32p, C.c_uint32, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u32p, u32p]),
+    "pqv_last_timing": (C.c_int, [ctxp, C.POINTER(PqvTiming)]),
+    "pqv_bench_scan": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, f64p]),
+}
+
+
+def load():
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(make -C pq_vector_b200/csrc).  pq_vector_b200 has no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    return lib
+
+
+lib = load()

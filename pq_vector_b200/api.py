@@ -1,0 +1,233 @@
+"""Thin numpy-facing wrappers over the C ABI.  Every distance is computed by libpqv.so on the GPU."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from . import _native as N
+
+_lib = N.lib
+
+
+class PqvError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"pqv error {code}: {msg}")
+        self.code = code
+        self.message = msg
+
+
+def _check(rc: int):
+    if rc != N.PQV_OK:
+        raise PqvError(rc, (_lib.pqv_last_error() or b"").decode())
+
+
+def _f32(a):
+    return np.ascontiguousarray(a, dtype=np.float32)
+
+
+def _ptr(a, ct):
+    return None if a is None else a.ctypes.data_as(C.POINTER(ct))
+
+
+class Context:
+    """Owns devices, streams and scratch (pqv_ctx)."""
+
+    def __init__(self, devices=None):
+        self._h = N.ctxp()
+        if devices is None:
+            _check(_lib.pqv_init(C.byref(self._h), None, 0))
+        else:
+            arr = (C.c_int * len(devices))(*devices)
+            _check(_lib.pqv_init(C.byref(self._h), arr, len(devices)))
+
+    def close(self):
+        if self._h:
+            _lib.pqv_destroy(self._h)
+            self._h = N.ctxp()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def device_count(self) -> int:
+        return _lib.pqv_device_count(self._h)
+
+    # ---- datasets
+    def dataset(self, dim: int, n_rows_hint: int = 0) -> "Dataset":
+        h = C.c_uint64()
+        _check(_lib.pqv_dataset_create(self._h, dim, n_rows_hint, C.byref(h)))
+        return Dataset(self, h.value, dim)
+
+    def dataset_from(self, rows) -> "Dataset":
+        rows = _f32(rows)
+        ds = self.dataset(rows.shape[1], rows.shape[0])
+        ds.append(rows)
+        return ds
+
+    # ---- k-means pieces
+    def kmeans_assign(self, rows_or_dataset, centroids, n=None, want_sizes=False):
+        centroids = _f32(centroids)
+        c, dim = centroids.shape
+        if isinstance(rows_or_dataset, Dataset):
+            handle, rows = rows_or_dataset.handle, None
+            n = rows_or_dataset.rows if n is None else n
+        else:
+            rows = _f32(rows_or_dataset)
+            handle, n = 0, rows.shape[0]
+        out = np.empty(n, dtype=np.uint32)
+        sizes = np.empty(c, dtype=np.uint64) if want_sizes else None
+        _check(_lib.pqv_kmeans_assign(self._h, handle, _ptr(rows, C.c_float), n, dim, _ptr(centroids, C.c_float), c,
+                                      _ptr(out, C.c_uint32), _ptr(sizes, C.c_uint64)))
+        return (out, sizes) if want_sizes else out
+
+    def min_dist_update(self, rows_or_dataset, row_sel, centroid, min_dist=None):
+        """init (min_dist None) -> returns new array; else updates min_dist in place (index.rs:344-370)."""
+        centroid = _f32(centroid)
+        dim = centroid.size
+        if isinstance(rows_or_dataset, Dataset):
+            handle, rows, n_rows = rows_or_dataset.handle, None, rows_or_dataset.rows
+        else:
+            rows = _f32(rows_or_dataset)
+            handle, n_rows = 0, rows.shape[0]
+        sel = None if row_sel is None else np.ascontiguousarray(row_sel, dtype=np.uint64)
+        n_sel = n_rows if sel is None else sel.size
+        init = min_dist is None
+        if init:
+            min_dist = np.empty(n_sel, dtype=np.float32)
+        assert min_dist.dtype == np.float32 and min_dist.flags.c_contiguous and min_dist.size == n_sel
+        _check(_lib.pqv_min_dist_update(self._h, handle, _ptr(rows, C.c_float), _ptr(sel, C.c_uint64), n_sel, dim,
+                                        _ptr(centroid, C.c_float), int(init), _ptr(min_dist, C.c_float)))
+        return min_dist
+
+    def centroid_rank(self, centroids, queries, nprobe):
+        centroids = _f32(centroids)
+        queries = np.atleast_2d(_f32(queries))
+        c, dim = centroids.shape
+        if queries.shape[1] != dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {dim}, got {queries.shape[1]}")
+        nq = queries.shape[0]
+        out = np.empty((nq, min(max(nprobe, 1), c)), dtype=np.uint32)
+        eff = C.c_uint32()
+        _check(_lib.pqv_centroid_rank(self._h, _ptr(centroids, C.c_float), c, dim, _ptr(queries, C.c_float), nq,
+                                      nprobe, _ptr(out, C.c_uint32), C.byref(eff)))
+        return out[:, :eff.value]
+
+    def topk_stream(self, query, k, flags=N.PQV_SUM_SEQ) -> "TopkStream":
+        return TopkStream(self, query, k, flags)
+
+    def last_timing(self) -> dict:
+        t = N.PqvTiming()
+        _check(_lib.pqv_last_timing(self._h, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in N.PqvTiming._fields_ if f != "reserved"}
+
+
+class Dataset:
+    """HBM-resident dense N x dim f32 embedding block (pqv_dataset_*)."""
+
+    def __init__(self, ctx: Context, handle: int, dim: int):
+        self.ctx, self.handle, self.dim = ctx, handle, dim
+
+    def append(self, rows):
+        rows = _f32(rows)
+        if rows.ndim != 2 or rows.shape[1] != self.dim:
+            raise PqvError(N.PQV_EINVAL, "Embedding data length must be a multiple of dimension")
+        _check(_lib.pqv_dataset_append(self.ctx._h, self.handle, _ptr(rows, C.c_float), rows.shape[0]))
+
+    def fill_synthetic(self, n_rows: int, seed: int):
+        _check(_lib.pqv_dataset_fill_synthetic(self.ctx._h, self.handle, n_rows, seed))
+
+    @property
+    def rows(self) -> int:
+        n = C.c_uint64()
+        _check(_lib.pqv_dataset_rows(self.ctx._h, self.handle, C.byref(n), None))
+        return n.value
+
+    def read(self, first_row: int, n_rows: int) -> np.ndarray:
+        out = np.empty((n_rows, self.dim), dtype=np.float32)
+        _check(_lib.pqv_dataset_read(self.ctx._h, self.handle, first_row, n_rows, _ptr(out, C.c_float)))
+        return out
+
+    def drop(self):
+        if self.handle:
+            _check(_lib.pqv_dataset_drop(self.ctx._h, self.handle))
+            self.handle = 0
+
+    def l2_topk(self, queries, k: int, flags: int = N.PQV_SQRT):
+        """Brute-force top-k (src/ivf/search.rs:112-141 with every row a candidate).
+        Returns (row_idx [nq,k] u32, dist [nq,k] f32, count [nq]); 1-D query -> 1-D results trimmed to count."""
+        q = _f32(queries)
+        single = q.ndim == 1
+        q2 = np.atleast_2d(q)
+        if q2.shape[1] != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q2.shape[1]}")
+        nq = q2.shape[0]
+        kk = max(k, 1)
+        rows = np.zeros((nq, kk), dtype=np.uint32)
+        dist = np.zeros((nq, kk), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        _check(_lib.pqv_l2_topk(self.ctx._h, self.handle, _ptr(q2, C.c_float), nq, k, flags, _ptr(rows, C.c_uint32),
+                                _ptr(dist, C.c_float), _ptr(cnt, C.c_uint32)))
+        if single:
+            return rows[0, :cnt[0]].copy(), dist[0, :cnt[0]].copy()
+        return rows, dist, cnt
+
+    def l2_topk_gather(self, query, row_ids, k: int, flags: int = N.PQV_SQRT):
+        q = _f32(query)
+        if q.size != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.size}")
+        ids = np.ascontiguousarray(row_ids, dtype=np.uint32)
+        kk = max(k, 1)
+        rows = np.zeros(kk, dtype=np.uint32)
+        dist = np.zeros(kk, dtype=np.float32)
+        cnt = C.c_uint32()
+        _check(_lib.pqv_l2_topk_gather(self.ctx._h, self.handle, _ptr(q, C.c_float), _ptr(ids, C.c_uint32), ids.size,
+                                       k, flags, _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), C.byref(cnt)))
+        return rows[:cnt.value].copy(), dist[:cnt.value].copy()
+
+    def bench_scan(self, query, k: int, flags: int, iters: int) -> float:
+        q = _f32(query)
+        ms = C.c_double()
+        _check(_lib.pqv_bench_scan(self.ctx._h, self.handle, _ptr(q, C.c_float), k, flags, iters, C.byref(ms)))
+        return ms.value
+
+
+class TopkStream:
+    """VectorTopKExec::topk_from_batches replacement (src/df_vector/exec.rs:257-277)."""
+
+    def __init__(self, ctx: Context, query, k: int, flags: int):
+        q = _f32(query)
+        self.ctx, self.k, self.dim = ctx, k, q.size
+        h = C.c_uint64()
+        _check(_lib.pqv_topk_stream_begin(ctx._h, q.size, _ptr(q, C.c_float), k, flags, C.byref(h)))
+        self.handle = h.value
+
+    def push(self, values):
+        v = np.asarray(values)
+        if v.dtype == np.float64:
+            v = np.ascontiguousarray(v)
+            fn, ct = _lib.pqv_topk_stream_push_f64, C.c_double
+        else:
+            v = _f32(v)
+            fn, ct = _lib.pqv_topk_stream_push, C.c_float
+        if v.size % self.dim:
+            raise PqvError(N.PQV_EINVAL, "Embedding data length must be a multiple of dimension")
+        _check(fn(self.ctx._h, self.handle, _ptr(v, ct), v.size // self.dim))
+
+    def finish(self):
+        rows = np.zeros(self.k, dtype=np.uint32)
+        dist = np.zeros(self.k, dtype=np.float32)
+        cnt = C.c_uint32()
+        _check(_lib.pqv_topk_stream_finish(self.ctx._h, self.handle, _ptr(rows, C.c_uint32), _ptr(dist, C.c_float),
+                                           C.byref(cnt)))
+        self.handle = 0
+        return rows[:cnt.value].copy(), dist[:cnt.value].copy()

@@ -1,0 +1,1162 @@
+// pqv_capi.cu -- the C ABI of include/pqv.h on top of the sm_100a kernels in pqv_kernels.cuh.
+//
+// Host-side responsibilities: device scratch management, dataset residency (row-range shards over the
+// context's devices), launch sequencing on a per-device stream, and the final exact replay of the
+// reference's bounded BinaryHeap over the (small) heap-entrant superset the kernels emit
+// (DESIGN.md section 4.3).  No CPU fallback exists: every distance is computed on the GPU.
+#include "../../include/pqv.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "pqv_kernels.cuh"
+
+using pqv::u64;
+
+// ------------------------------------------------------------------------------------------------
+// errors
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+
+static int fail(int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                                   \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            int code__ = (e__ == cudaErrorMemoryAllocation) ? PQV_ENOMEM : PQV_ECUDA;                 \
+            return fail(code__, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+        }                                                                                              \
+    } while (0)
+
+#define PQV_TRY(expr)          \
+    do {                       \
+        int rc__ = (expr);     \
+        if (rc__) return rc__; \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// Rust std::collections::BinaryHeap<HeapItem> (max-heap on distance, NaN -> Equal), written against
+// the published std source: push = sift_up(0, old_len); pop = swap last into root +
+// sift_down_to_bottom(0) (+ sift_up); into_iter = backing-vector order.  Used to replay the
+// reference loop src/ivf/search.rs:115-127 / src/df_vector/exec.rs:467-482 over the entrant set.
+// ------------------------------------------------------------------------------------------------
+namespace {
+
+struct HeapItem {
+    float distance;
+    uint32_t row_idx;
+};
+
+struct RustMaxHeap {
+    std::vector<HeapItem> data;
+    static bool le(const HeapItem &a, const HeapItem &b) { return !(a.distance > b.distance); }
+    void sift_up(size_t start, size_t pos) {
+        HeapItem elt = data[pos];
+        while (pos > start) {
+            size_t parent = (pos - 1) / 2;
+            if (le(elt, data[parent])) break;
+            data[pos] = data[parent];
+            pos = parent;
+        }
+        data[pos] = elt;
+    }
+    void sift_down_to_bottom(size_t pos) {
+        const size_t end = data.size(), start = pos;
+        HeapItem elt = data[pos];
+        size_t child = 2 * pos + 1;
+        while (end >= 2 && child <= end - 2) {
+            child += le(data[child], data[child + 1]) ? 1 : 0;
+            data[pos] = data[child];
+            pos = child;
+            child = 2 * pos + 1;
+        }
+        if (child == end - 1) {
+            data[pos] = data[child];
+            pos = child;
+        }
+        data[pos] = elt;
+        sift_up(start, pos);
+    }
+    void push(HeapItem it) {
+        data.push_back(it);
+        sift_up(0, data.size() - 1);
+    }
+    void pop() {
+        HeapItem last = data.back();
+        data.pop_back();
+        if (!data.empty()) {
+            data[0] = last;
+            sift_down_to_bottom(0);
+        }
+    }
+};
+
+inline float key_dist(u64 key) {
+    uint32_t b = (uint32_t)(key >> 32);
+    float f;
+    memcpy(&f, &b, 4);
+    return f;
+}
+inline uint32_t key_pos(u64 key) { return (uint32_t)(key & 0xFFFFFFFFull); }
+
+// entrants: keys (bits(d) << 32 | position) in any order; a superset of every candidate the
+// reference heap admits.  Replays the reference loop in position order, then (sqrt), stable sort.
+size_t replay_reference_heap(std::vector<u64> &entrants, const uint32_t *row_ids, uint32_t k, uint32_t flags,
+                             uint32_t *out_rows, float *out_dist) {
+    std::sort(entrants.begin(), entrants.end(),
+              [](u64 a, u64 b) { return key_pos(a) < key_pos(b); });
+    RustMaxHeap h;
+    h.data.reserve((size_t)k + 1);
+    for (u64 key : entrants) {
+        const float d = key_dist(key);
+        const uint32_t pos = key_pos(key);
+        HeapItem it{d, row_ids ? row_ids[pos] : pos};
+        if (h.data.size() < k) {
+            h.push(it);
+        } else if (d < h.data[0].distance) {
+            h.pop();
+            h.push(it);
+        }
+    }
+    std::vector<HeapItem> &r = h.data;
+    if (flags & PQV_SQRT)
+        for (auto &it : r) it.distance = sqrtf(it.distance);
+    std::stable_sort(r.begin(), r.end(), [](const HeapItem &a, const HeapItem &b) { return a.distance < b.distance; });
+    for (size_t i = 0; i < r.size(); ++i) {
+        out_rows[i] = r[i].row_idx;
+        out_dist[i] = r[i].distance;
+    }
+    return r.size();
+}
+
+uint32_t pow2ceil(uint32_t v) {
+    uint32_t p = 1;
+    while (p < v) p <<= 1;
+    return p;
+}
+
+// ------------------------------------------------------------------------------------------------
+// per-device state
+// ------------------------------------------------------------------------------------------------
+template <typename T>
+struct DevBuf {
+    T *p = nullptr;
+    size_t cap = 0;  // elements
+    int ensure(size_t n) {
+        if (n <= cap) return PQV_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        size_t want = n + n / 8 + 64;
+        cudaError_t e = cudaMalloc((void **)&p, want * sizeof(T));
+        if (e != cudaSuccess) return fail(PQV_ENOMEM, "cudaMalloc(%zu bytes) failed: %s", want * sizeof(T), cudaGetErrorString(e));
+        cap = want;
+        return PQV_OK;
+    }
+    void release() {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+template <typename T>
+struct PinBuf {
+    T *p = nullptr;
+    size_t cap = 0;
+    int ensure(size_t n) {
+        if (n <= cap) return PQV_OK;
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+        cudaError_t e = cudaMallocHost((void **)&p, n * sizeof(T));
+        if (e != cudaSuccess) return fail(PQV_ENOMEM, "cudaMallocHost(%zu bytes) failed: %s", n * sizeof(T), cudaGetErrorString(e));
+        cap = n;
+        return PQV_OK;
+    }
+    void release() {
+        if (p) cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+constexpr uint32_t ENT_FIRST_CHUNK = 8192;  // entrant keys fetched with the first D2H (64 KiB)
+
+struct DeviceState {
+    int dev = 0;
+    int sm_count = 0;
+    cudaStream_t stream = nullptr, copy_stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    DevBuf<float> d_query;
+    DevBuf<u64> cta_topk, ent, final_topk, ent_out;
+    DevBuf<uint32_t> ent_count, gthr, d_row_ids, d_assign;
+    DevBuf<float> d_vec, d_tmp_rows, d_centroids, d_dist;
+    PinBuf<u64> h_ent_out, h_final;
+    PinBuf<float> h_query;
+};
+
+struct Shard {
+    int di = 0;  // index into ctx->devs
+    float *d_data = nullptr;
+    u64 cap_rows = 0, n_rows = 0, first_row = 0;
+};
+
+struct Dataset {
+    uint32_t dim = 0;
+    u64 n_rows = 0;
+    std::vector<Shard> shards;
+};
+
+struct StreamState {
+    uint32_t dim = 0, k = 0, flags = 0;
+    u64 rows_pushed = 0;
+    u64 ent_rows_bound = 0;  // rows pushed since the device entrant accumulator was last drained
+    int cur = 0;
+    DevBuf<float> staging[2];
+    DevBuf<double> staging64;
+    cudaEvent_t scan_done[2] = {nullptr, nullptr};
+    cudaEvent_t copy_done = nullptr;
+    DevBuf<u64> carry[2];
+    int carry_cur = 0;
+    DevBuf<float> d_query;
+    DevBuf<u64> ent_acc;  // [0] = count, then keys
+    std::vector<u64> host_entrants;
+    bool any = false;
+};
+
+}  // namespace
+
+struct pqv_ctx {
+    std::vector<DeviceState> devs;
+    std::map<u64, Dataset> datasets;
+    std::map<u64, StreamState *> streams;
+    u64 next_handle = 1;
+    std::mutex mu;
+    pqv_timing last{};
+    int occ_override = 0;
+};
+
+namespace {
+
+struct DevGuard {
+    int prev = -1;
+    explicit DevGuard(int dev) {
+        cudaGetDevice(&prev);
+        if (prev != dev) cudaSetDevice(dev);
+    }
+    ~DevGuard() {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------
+// scan launch
+// ------------------------------------------------------------------------------------------------
+constexpr int SCAN_WARPS = 8;
+
+struct ScanGeom {
+    uint32_t kcap, sort_n, flush_at, grid;
+    size_t smem;
+    bool vec4;
+};
+
+template <int ORDER, bool VEC4, bool GATHER>
+int scan_launch_t(const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStream_t st) {
+    auto kern = pqv::l2_scan_topk_kernel<ORDER, VEC4, GATHER, SCAN_WARPS>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    kern<<<grid, SCAN_WARPS * 32, smem, st>>>(p);
+    CU_TRY(cudaGetLastError());
+    return PQV_OK;
+}
+
+template <int ORDER, bool VEC4, bool GATHER>
+int scan_occupancy_t(size_t smem, int *occ) {
+    auto kern = pqv::l2_scan_topk_kernel<ORDER, VEC4, GATHER, SCAN_WARPS>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, SCAN_WARPS * 32, smem));
+    return PQV_OK;
+}
+
+#define SCAN_DISPATCH(FN, order, vec4, gather, ...)                                                 \
+    ((order) == 0 ? ((vec4) ? ((gather) ? FN<0, true, true>(__VA_ARGS__) : FN<0, true, false>(__VA_ARGS__))      \
+                            : ((gather) ? FN<0, false, true>(__VA_ARGS__) : FN<0, false, false>(__VA_ARGS__)))   \
+                  : ((vec4) ? ((gather) ? FN<1, true, true>(__VA_ARGS__) : FN<1, true, false>(__VA_ARGS__))      \
+                            : ((gather) ? FN<1, false, true>(__VA_ARGS__) : FN<1, false, false>(__VA_ARGS__))))
+
+size_t scan_smem_bytes(int order, bool vec4, uint32_t dim, uint32_t sort_n) {
+    const size_t tile = (order == 1 && vec4) ? pqv::TileCfg<1, true>::TILE_FLOATS : pqv::TileCfg<0, true>::TILE_FLOATS;
+    const size_t dim_pad = (dim + 3u) & ~3u;
+    return dim_pad * 4 + (size_t)SCAN_WARPS * tile * 4 + (size_t)sort_n * 8;
+}
+
+int scan_geometry(pqv_ctx *ctx, DeviceState &D, const float *d_data, u64 n, uint32_t dim, uint32_t k, int order,
+                  bool gather, ScanGeom *g) {
+    g->vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_data) & 15) == 0);
+    g->kcap = std::max<uint32_t>(32, pow2ceil(k));
+    g->flush_at = std::max<uint32_t>(1, g->kcap / 2);
+    g->sort_n = pow2ceil(g->kcap + g->flush_at + SCAN_WARPS * 32);
+    g->smem = scan_smem_bytes(order, g->vec4, dim, g->sort_n);
+    if (g->smem > 227 * 1024) return fail(PQV_ELIMIT, "scan needs %zu bytes of shared memory (dim=%u k=%u)", g->smem, dim, k);
+    int occ = 0;
+    PQV_TRY(SCAN_DISPATCH(scan_occupancy_t, order, g->vec4, gather, g->smem, &occ));
+    if (occ < 1) return fail(PQV_ELIMIT, "scan kernel does not fit on an SM (smem %zu)", g->smem);
+    int want = ctx->occ_override > 0 ? ctx->occ_override : 2;
+    occ = std::min(occ, want);
+    const u64 NG = (n + 31) / 32;
+    g->grid = (uint32_t)std::min<u64>((u64)D.sm_count * occ, std::max<u64>(NG, 1));
+    return PQV_OK;
+}
+
+// Enqueue scan + prefix merge + entrant filter on D.stream.  Device outputs: D.final_topk (kcap keys) or
+// `final_out` if given, and entrant keys appended to `ent_out` ([0] = running count).
+int enqueue_scan(pqv_ctx *ctx, DeviceState &D, const float *d_data, const uint32_t *d_row_ids, u64 n, uint32_t dim,
+                 const float *d_query, uint32_t k, int order, uint32_t pos_base, const u64 *d_carry, u64 *final_out,
+                 u64 *ent_out, uint32_t ent_out_cap, bool time_it, ScanGeom *geom_out) {
+    ScanGeom g;
+    PQV_TRY(scan_geometry(ctx, D, d_data, n, dim, k, order, d_row_ids != nullptr, &g));
+    PQV_TRY(D.cta_topk.ensure((size_t)g.grid * g.kcap));
+    PQV_TRY(D.ent.ensure((size_t)n + 64));
+    PQV_TRY(D.ent_count.ensure(g.grid));
+    PQV_TRY(D.gthr.ensure(g.grid));
+    pqv::ScanParams p{};
+    p.data = d_data;
+    p.query = d_query;
+    p.row_ids = d_row_ids;
+    p.n = n;
+    p.dim = dim;
+    p.k = k;
+    p.kcap = g.kcap;
+    p.sort_n = g.sort_n;
+    p.flush_at = g.flush_at;
+    p.cap_bits = 0xFFFFFFFFu;
+    p.carry = d_carry;
+    p.pos_base = pos_base;
+    p.cta_topk = D.cta_topk.p;
+    p.ent = D.ent.p;
+    p.ent_count = D.ent_count.p;
+    if (time_it) CU_TRY(cudaEventRecord(D.ev[0], D.stream));
+    PQV_TRY(SCAN_DISPATCH(scan_launch_t, order, g.vec4, d_row_ids != nullptr, p, g.grid, g.smem, D.stream));
+    if (time_it) CU_TRY(cudaEventRecord(D.ev[1], D.stream));
+    const uint32_t mt = std::min<uint32_t>(g.kcap, 1024);
+    pqv::topk_prefix_merge_kernel<<<1, mt, (size_t)2 * g.kcap * 8, D.stream>>>(D.cta_topk.p, g.grid, k, g.kcap, d_carry,
+                                                                              D.gthr.p, final_out);
+    CU_TRY(cudaGetLastError());
+    pqv::entrant_filter_kernel<<<g.grid, 256, 0, D.stream>>>(D.ent.p, D.ent_count.p, D.gthr.p, n, ent_out, ent_out_cap);
+    CU_TRY(cudaGetLastError());
+    if (time_it) CU_TRY(cudaEventRecord(D.ev[2], D.stream));
+    if (geom_out) *geom_out = g;
+    return PQV_OK;
+}
+
+// Fetch the entrant keys accumulated in ent_out (device) into `out` (appends).  Requires the stream
+// to be idle on return.  Returns PQV_ELIMIT via *overflow when the device buffer was too small.
+int fetch_entrants(DeviceState &D, u64 *d_ent_out, uint32_t ent_out_cap, std::vector<u64> &out, bool *overflow) {
+    PQV_TRY(D.h_ent_out.ensure((size_t)ENT_FIRST_CHUNK + 1));
+    const uint32_t first = std::min<uint32_t>(ENT_FIRST_CHUNK, ent_out_cap);
+    CU_TRY(cudaMemcpyAsync(D.h_ent_out.p, d_ent_out, ((size_t)first + 1) * 8, cudaMemcpyDeviceToHost, D.stream));
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    const u64 count = D.h_ent_out.p[0];
+    *overflow = count > ent_out_cap;
+    if (*overflow) return PQV_OK;
+    const size_t base = out.size();
+    out.resize(base + count);
+    const u64 got = std::min<u64>(count, first);
+    memcpy(out.data() + base, D.h_ent_out.p + 1, got * 8);
+    if (count > got) {
+        CU_TRY(cudaMemcpyAsync(out.data() + base + got, d_ent_out + 1 + got, (count - got) * 8, cudaMemcpyDeviceToHost,
+                               D.stream));
+        CU_TRY(cudaStreamSynchronize(D.stream));
+    }
+    return PQV_OK;
+}
+
+Dataset *find_dataset(pqv_ctx *ctx, u64 h) {
+    auto it = ctx->datasets.find(h);
+    return it == ctx->datasets.end() ? nullptr : &it->second;
+}
+
+int check_topk_args(uint32_t k, uint32_t dim, uint32_t flags) {
+    if (k == 0) return fail(PQV_EINVAL, "k must be > 0");  // src/ivf/search.rs:67
+    if (k > PQV_MAX_K) return fail(PQV_ELIMIT, "k = %u exceeds PQV_MAX_K = %u", k, PQV_MAX_K);
+    if (dim == 0) return fail(PQV_EINVAL, "Embedding dimension must be > 0");  // src/ivf/mod.rs:61
+    if (dim > PQV_MAX_DIM) return fail(PQV_ELIMIT, "dim = %u exceeds PQV_MAX_DIM = %u", dim, PQV_MAX_DIM);
+    if (flags & ~(PQV_SUM_SEQ | PQV_SQRT | PQV_TIES_BY_POSITION)) return fail(PQV_EINVAL, "unknown flags 0x%x", flags);
+    return PQV_OK;
+}
+
+// final (distance, position)-ordered keys -> outputs (PQV_TIES_BY_POSITION mode)
+size_t emit_by_position(std::vector<u64> &keys, const uint32_t *row_ids, uint32_t k, uint32_t flags,
+                        uint32_t *out_rows, float *out_dist) {
+    std::sort(keys.begin(), keys.end());
+    size_t n = 0;
+    for (u64 key : keys) {
+        if (key == pqv::KEY_MAX || n >= k) break;
+        float d = key_dist(key);
+        out_rows[n] = row_ids ? row_ids[key_pos(key)] : key_pos(key);
+        out_dist[n] = (flags & PQV_SQRT) ? sqrtf(d) : d;
+        ++n;
+    }
+    return n;
+}
+
+// One query over a resident dataset (all shards), brute force or gathered.  Host inputs/outputs.
+int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_ids, u64 n_ids, uint32_t k,
+             uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count) {
+    const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
+    const bool gather = row_ids != nullptr;
+    std::vector<u64> entrants;
+    std::vector<u64> finals;
+    pqv_timing tm{};
+    struct Launched {
+        DeviceState *D;
+        ScanGeom g;
+        uint32_t cap;
+        u64 n;
+    };
+    std::vector<Launched> launched;
+
+    // gathered search runs on the shard that owns the table; multi-shard gather splits ids by owner
+    for (size_t si = 0; si < ds.shards.size(); ++si) {
+        Shard &sh = ds.shards[si];
+        DeviceState &D = ctx->devs[sh.di];
+        DevGuard guard(D.dev);
+        u64 n = 0;
+        const uint32_t *d_ids = nullptr;
+        if (gather) {
+            if (ds.shards.size() != 1)
+                return fail(PQV_EINVAL, "pqv_l2_topk_gather needs a single-device dataset (got %zu shards)", ds.shards.size());
+            n = n_ids;
+            if (n) {
+                PQV_TRY(D.d_row_ids.ensure(n));
+                CU_TRY(cudaMemcpyAsync(D.d_row_ids.p, row_ids, n * 4, cudaMemcpyHostToDevice, D.stream));
+                d_ids = D.d_row_ids.p;
+            }
+        } else {
+            n = sh.n_rows;
+        }
+        if (n == 0) continue;
+        PQV_TRY(D.d_query.ensure(ds.dim));
+        PQV_TRY(D.h_query.ensure(ds.dim));
+        memcpy(D.h_query.p, query, (size_t)ds.dim * 4);
+        CU_TRY(cudaMemcpyAsync(D.d_query.p, D.h_query.p, (size_t)ds.dim * 4, cudaMemcpyHostToDevice, D.stream));
+        PQV_TRY(D.final_topk.ensure(PQV_MAX_K));
+        PQV_TRY(D.ent_out.ensure((size_t)(1u << 16) + 1));
+        const uint32_t cap = (uint32_t)std::min<size_t>(D.ent_out.cap - 1, 0xFFFFFFF0u);
+        CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
+        ScanGeom g;
+        PQV_TRY(enqueue_scan(ctx, D, sh.d_data, d_ids, n, ds.dim, D.d_query.p, k, order,
+                             gather ? 0u : (uint32_t)sh.first_row, nullptr, D.final_topk.p, D.ent_out.p, cap, si == 0, &g));
+        launched.push_back({&D, g, cap, n});
+    }
+    // collect
+    for (auto &L : launched) {
+        DeviceState &D = *L.D;
+        DevGuard guard(D.dev);
+        if (flags & PQV_TIES_BY_POSITION) {
+            PQV_TRY(D.h_final.ensure(PQV_MAX_K));
+            CU_TRY(cudaMemcpyAsync(D.h_final.p, D.final_topk.p, (size_t)L.g.kcap * 8, cudaMemcpyDeviceToHost, D.stream));
+            CU_TRY(cudaStreamSynchronize(D.stream));
+            finals.insert(finals.end(), D.h_final.p, D.h_final.p + L.g.kcap);
+        } else {
+            bool overflow = false;
+            PQV_TRY(fetch_entrants(D, D.ent_out.p, L.cap, entrants, &overflow));
+            if (overflow) {
+                // adversarial ordering (most rows enter the heap): rerun the filter with a buffer that can
+                // hold every row; the scan outputs are still valid in D.ent / D.gthr.
+                const u64 need = D.h_ent_out.p[0];
+                PQV_TRY(D.ent_out.ensure((size_t)need + 1));
+                const uint32_t cap2 = (uint32_t)std::min<size_t>(D.ent_out.cap - 1, 0xFFFFFFF0u);
+                CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
+                pqv::entrant_filter_kernel<<<L.g.grid, 256, 0, D.stream>>>(D.ent.p, D.ent_count.p, D.gthr.p, L.n,
+                                                                           D.ent_out.p, cap2);
+                CU_TRY(cudaGetLastError());
+                PQV_TRY(fetch_entrants(D, D.ent_out.p, cap2, entrants, &overflow));
+                if (overflow) return fail(PQV_ECUDA, "entrant buffer overflow after regrow");
+            }
+        }
+    }
+    if (!launched.empty()) {
+        DeviceState &D = *launched[0].D;
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, D.ev[0], D.ev[1]);
+        cudaEventElapsedTime(&b, D.ev[1], D.ev[2]);
+        tm.scan_ms = a;
+        tm.post_ms = b;
+        tm.total_ms = a + b;
+        tm.scan_bytes = launched[0].n * (u64)ds.dim * 4;
+        tm.launches = 3 * (uint32_t)launched.size();
+        tm.grid = launched[0].g.grid;
+    }
+    size_t cnt;
+    if (flags & PQV_TIES_BY_POSITION) {
+        cnt = emit_by_position(finals, row_ids, k, flags, out_rows, out_dist);
+    } else {
+        tm.entrants = (uint32_t)entrants.size();
+        cnt = replay_reference_heap(entrants, row_ids, k, flags, out_rows, out_dist);
+    }
+    *out_count = (uint32_t)cnt;
+    ctx->last = tm;
+    return PQV_OK;
+}
+
+}  // namespace
+
+// ================================================================================================
+// C ABI
+// ================================================================================================
+extern "C" {
+
+const char *pqv_last_error(void) { return g_err.c_str(); }
+const char *pqv_version(void) { return "pq-vector-b200 0.1.0 (sm_100a)"; }
+
+int pqv_init(pqv_ctx **out, const int *device_ids, int n_devices) {
+    if (!out) return fail(PQV_EINVAL, "out is null");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return fail(PQV_ENODEV, "no CUDA device available (%s); libpqv has no CPU fallback",
+                    e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    std::vector<int> ids;
+    if (device_ids == nullptr || n_devices == 0) {
+        int cur = 0;
+        cudaGetDevice(&cur);
+        ids.push_back(cur);
+    } else {
+        for (int i = 0; i < n_devices; ++i) {
+            if (device_ids[i] < 0 || device_ids[i] >= count) return fail(PQV_ENODEV, "device id %d out of range [0,%d)", device_ids[i], count);
+            ids.push_back(device_ids[i]);
+        }
+    }
+    pqv_ctx *ctx = new pqv_ctx();
+    if (const char *s = getenv("PQV_SCAN_CTAS_PER_SM")) ctx->occ_override = atoi(s);
+    for (int id : ids) {
+        DeviceState D;
+        D.dev = id;
+        DevGuard guard(id);
+        cudaDeviceProp prop;
+        CU_TRY(cudaGetDeviceProperties(&prop, id));
+        if (prop.major < 10) {
+            delete ctx;
+            return fail(PQV_ENODEV, "device %d is sm_%d%d; libpqv is built for sm_100a only", id, prop.major, prop.minor);
+        }
+        D.sm_count = prop.multiProcessorCount;
+        CU_TRY(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
+        CU_TRY(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
+        for (auto &ev : D.ev) CU_TRY(cudaEventCreate(&ev));
+        ctx->devs.push_back(D);
+    }
+    *out = ctx;
+    return PQV_OK;
+}
+
+void pqv_destroy(pqv_ctx *ctx) {
+    if (!ctx) return;
+    for (auto &kv : ctx->streams) {
+        StreamState *s = kv.second;
+        DevGuard guard(ctx->devs[0].dev);
+        s->staging[0].release();
+        s->staging[1].release();
+        s->staging64.release();
+        s->carry[0].release();
+        s->carry[1].release();
+        s->d_query.release();
+        s->ent_acc.release();
+        for (auto &ev : s->scan_done)
+            if (ev) cudaEventDestroy(ev);
+        if (s->copy_done) cudaEventDestroy(s->copy_done);
+        delete s;
+    }
+    for (auto &kv : ctx->datasets)
+        for (auto &sh : kv.second.shards) {
+            DevGuard guard(ctx->devs[sh.di].dev);
+            if (sh.d_data) cudaFree(sh.d_data);
+        }
+    for (auto &D : ctx->devs) {
+        DevGuard guard(D.dev);
+        cudaStreamSynchronize(D.stream);
+        D.d_query.release();
+        D.cta_topk.release();
+        D.ent.release();
+        D.final_topk.release();
+        D.ent_out.release();
+        D.ent_count.release();
+        D.gthr.release();
+        D.d_row_ids.release();
+        D.d_assign.release();
+        D.d_vec.release();
+        D.d_tmp_rows.release();
+        D.d_centroids.release();
+        D.d_dist.release();
+        D.h_ent_out.release();
+        D.h_final.release();
+        D.h_query.release();
+        for (auto &ev : D.ev)
+            if (ev) cudaEventDestroy(ev);
+        cudaStreamDestroy(D.stream);
+        cudaStreamDestroy(D.copy_stream);
+    }
+    delete ctx;
+}
+
+int pqv_device_count(pqv_ctx *ctx) { return ctx ? (int)ctx->devs.size() : 0; }
+
+// ---- datasets ----------------------------------------------------------------------------------
+int pqv_dataset_create(pqv_ctx *ctx, uint32_t dim, uint64_t n_rows_hint, uint64_t *out_handle) {
+    if (!ctx || !out_handle) return fail(PQV_EINVAL, "null argument");
+    if (dim == 0) return fail(PQV_EINVAL, "Embedding dimension must be > 0");
+    if (n_rows_hint > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "row ids are u32: %llu rows do not fit", (unsigned long long)n_rows_hint);
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset ds;
+    ds.dim = dim;
+    const size_t nd = ctx->devs.size();
+    const u64 hint = std::max<u64>(n_rows_hint, 1);
+    const u64 per = (hint + nd - 1) / nd;
+    for (size_t i = 0; i < nd; ++i) {
+        Shard sh;
+        sh.di = (int)i;
+        sh.cap_rows = per;
+        sh.first_row = per * i;
+        DevGuard guard(ctx->devs[i].dev);
+        cudaError_t e = cudaMalloc((void **)&sh.d_data, (size_t)per * dim * sizeof(float));
+        if (e != cudaSuccess) {
+            for (auto &s2 : ds.shards) cudaFree(s2.d_data);
+            return fail(PQV_ENOMEM, "cudaMalloc of %.2f GB for a dataset shard failed: %s", per * (double)dim * 4 / 1e9,
+                        cudaGetErrorString(e));
+        }
+        ds.shards.push_back(sh);
+    }
+    const u64 h = ctx->next_handle++;
+    ctx->datasets[h] = ds;
+    *out_handle = h;
+    return PQV_OK;
+}
+
+// grow the last shard (single-device datasets only) so appends past the hint keep working
+static int grow_shard(pqv_ctx *ctx, Dataset &ds, Shard &sh, u64 need_rows) {
+    DeviceState &D = ctx->devs[sh.di];
+    DevGuard guard(D.dev);
+    u64 new_cap = std::max<u64>(need_rows, sh.cap_rows + sh.cap_rows / 2 + 1024);
+    float *nd = nullptr;
+    cudaError_t e = cudaMalloc((void **)&nd, (size_t)new_cap * ds.dim * sizeof(float));
+    if (e != cudaSuccess) return fail(PQV_ENOMEM, "growing a dataset shard to %llu rows failed: %s", (unsigned long long)new_cap, cudaGetErrorString(e));
+    CU_TRY(cudaMemcpyAsync(nd, sh.d_data, (size_t)sh.n_rows * ds.dim * 4, cudaMemcpyDeviceToDevice, D.stream));
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    cudaFree(sh.d_data);
+    sh.d_data = nd;
+    sh.cap_rows = new_cap;
+    return PQV_OK;
+}
+
+int pqv_dataset_append(pqv_ctx *ctx, uint64_t handle, const float *values, uint64_t n_rows) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    if (n_rows == 0) return PQV_OK;
+    if (!values) return fail(PQV_EINVAL, "values is null");
+    if (ds->n_rows + n_rows > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "row ids are u32");
+    u64 done = 0;
+    while (done < n_rows) {
+        // the shard that owns global row ds->n_rows
+        Shard *sh = nullptr;
+        for (auto &s : ds->shards)
+            if (s.n_rows < s.cap_rows && s.first_row + s.n_rows == ds->n_rows) {
+                sh = &s;
+                break;
+            }
+        if (!sh) {
+            Shard &last = ds->shards.back();
+            if (last.first_row + last.n_rows != ds->n_rows) return fail(PQV_ECUDA, "dataset shard bookkeeping is inconsistent");
+            PQV_TRY(grow_shard(ctx, *ds, last, last.n_rows + (n_rows - done)));
+            sh = &last;
+        }
+        const u64 take = std::min<u64>(n_rows - done, sh->cap_rows - sh->n_rows);
+        DeviceState &D = ctx->devs[sh->di];
+        DevGuard guard(D.dev);
+        CU_TRY(cudaMemcpyAsync(sh->d_data + sh->n_rows * ds->dim, values + done * ds->dim, (size_t)take * ds->dim * 4,
+                               cudaMemcpyHostToDevice, D.stream));
+        CU_TRY(cudaStreamSynchronize(D.stream));  // values is only borrowed for the call
+        sh->n_rows += take;
+        ds->n_rows += take;
+        done += take;
+    }
+    return PQV_OK;
+}
+
+int pqv_dataset_rows(pqv_ctx *ctx, uint64_t handle, uint64_t *out_rows, uint32_t *out_dim) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    if (out_rows) *out_rows = ds->n_rows;
+    if (out_dim) *out_dim = ds->dim;
+    return PQV_OK;
+}
+
+int pqv_dataset_drop(pqv_ctx *ctx, uint64_t handle) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    for (auto &sh : ds->shards) {
+        DevGuard guard(ctx->devs[sh.di].dev);
+        cudaStreamSynchronize(ctx->devs[sh.di].stream);
+        if (sh.d_data) cudaFree(sh.d_data);
+    }
+    ctx->datasets.erase(handle);
+    return PQV_OK;
+}
+
+int pqv_dataset_fill_synthetic(pqv_ctx *ctx, uint64_t handle, uint64_t n_rows, uint64_t seed) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    u64 total_cap = 0;
+    for (auto &sh : ds->shards) total_cap += sh.cap_rows;
+    if (n_rows > total_cap) return fail(PQV_EINVAL, "n_rows %llu exceeds the dataset capacity %llu", (unsigned long long)n_rows, (unsigned long long)total_cap);
+    u64 left = n_rows;
+    ds->n_rows = 0;
+    for (auto &sh : ds->shards) {
+        const u64 take = std::min<u64>(left, sh.cap_rows);
+        sh.n_rows = take;
+        left -= take;
+        ds->n_rows += take;
+        if (!take) continue;
+        DeviceState &D = ctx->devs[sh.di];
+        DevGuard guard(D.dev);
+        pqv::synth_fill_kernel<<<D.sm_count * 8, 256, 0, D.stream>>>(sh.d_data, sh.first_row * ds->dim, take * ds->dim, seed);
+        CU_TRY(cudaGetLastError());
+    }
+    for (auto &sh : ds->shards) {
+        DevGuard guard(ctx->devs[sh.di].dev);
+        CU_TRY(cudaStreamSynchronize(ctx->devs[sh.di].stream));
+    }
+    return PQV_OK;
+}
+
+int pqv_dataset_read(pqv_ctx *ctx, uint64_t handle, uint64_t first_row, uint64_t n_rows, float *out) {
+    if (!ctx || (!out && n_rows)) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    if (first_row + n_rows > ds->n_rows) return fail(PQV_EINVAL, "rows [%llu,%llu) out of range (%llu rows)", (unsigned long long)first_row, (unsigned long long)(first_row + n_rows), (unsigned long long)ds->n_rows);
+    for (auto &sh : ds->shards) {
+        const u64 lo = std::max<u64>(first_row, sh.first_row), hi = std::min<u64>(first_row + n_rows, sh.first_row + sh.n_rows);
+        if (lo >= hi) continue;
+        DeviceState &D = ctx->devs[sh.di];
+        DevGuard guard(D.dev);
+        CU_TRY(cudaMemcpyAsync(out + (lo - first_row) * ds->dim, sh.d_data + (lo - sh.first_row) * ds->dim,
+                               (size_t)(hi - lo) * ds->dim * 4, cudaMemcpyDeviceToHost, D.stream));
+        CU_TRY(cudaStreamSynchronize(D.stream));
+    }
+    return PQV_OK;
+}
+
+// ---- top-k -------------------------------------------------------------------------------------
+int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k, uint32_t flags,
+                uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    if (n_queries && (!queries || !out_row_idx || !out_dist || !out_count)) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    for (uint32_t q = 0; q < n_queries; ++q)
+        PQV_TRY(topk_one(ctx, *ds, queries + (size_t)q * ds->dim, nullptr, 0, k, flags, out_row_idx + (size_t)q * k,
+                         out_dist + (size_t)q * k, out_count + q));
+    return PQV_OK;
+}
+
+int pqv_l2_topk_gather(pqv_ctx *ctx, uint64_t handle, const float *query, const uint32_t *row_ids, uint64_t n_ids,
+                       uint32_t k, uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
+    if (!ctx || !query || !out_row_idx || !out_dist || !out_count) return fail(PQV_EINVAL, "null argument");
+    if (n_ids && !row_ids) return fail(PQV_EINVAL, "row_ids is null");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (n_ids > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "candidate positions are u32");
+    for (u64 i = 0; i < n_ids; ++i)
+        if (row_ids[i] >= ds->n_rows) return fail(PQV_EINVAL, "row id %u at position %llu is out of range (%llu rows)", row_ids[i], (unsigned long long)i, (unsigned long long)ds->n_rows);
+    if (n_ids == 0) {
+        *out_count = 0;
+        return PQV_OK;
+    }
+    static const uint32_t dummy = 0;
+    return topk_one(ctx, *ds, query, row_ids ? row_ids : &dummy, n_ids, k, flags, out_row_idx, out_dist, out_count);
+}
+
+int pqv_last_timing(pqv_ctx *ctx, pqv_timing *out) {
+    if (!ctx || !out) return fail(PQV_EINVAL, "null argument");
+    *out = ctx->last;
+    return PQV_OK;
+}
+
+int pqv_bench_scan(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t iters,
+                   double *out_ms_per_scan) {
+    if (!ctx || !query || !out_ms_per_scan || iters == 0) return fail(PQV_EINVAL, "bad argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (ds->shards.size() != 1 || ds->shards[0].n_rows == 0) return fail(PQV_EINVAL, "pqv_bench_scan needs a non-empty single-device dataset");
+    Shard &sh = ds->shards[0];
+    DeviceState &D = ctx->devs[sh.di];
+    DevGuard guard(D.dev);
+    const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
+    PQV_TRY(D.d_query.ensure(ds->dim));
+    CU_TRY(cudaMemcpyAsync(D.d_query.p, query, (size_t)ds->dim * 4, cudaMemcpyHostToDevice, D.stream));
+    PQV_TRY(D.final_topk.ensure(PQV_MAX_K));
+    PQV_TRY(D.ent_out.ensure((size_t)(1u << 20) + 1));
+    const uint32_t cap = (uint32_t)(D.ent_out.cap - 1);
+    std::vector<cudaEvent_t> evs((size_t)iters * 3);
+    for (auto &e : evs) CU_TRY(cudaEventCreate(&e));
+    ScanGeom g{};
+    for (uint32_t it = 0; it < iters; ++it) {
+        CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
+        // same launch sequence as topk_one, with our own event triplet per iteration
+        cudaEvent_t keep[3] = {D.ev[0], D.ev[1], D.ev[2]};
+        D.ev[0] = evs[it * 3 + 0];
+        D.ev[1] = evs[it * 3 + 1];
+        D.ev[2] = evs[it * 3 + 2];
+        int rc = enqueue_scan(ctx, D, sh.d_data, nullptr, sh.n_rows, ds->dim, D.d_query.p, k, order, 0, nullptr,
+                              D.final_topk.p, D.ent_out.p, cap, true, &g);
+        D.ev[0] = keep[0];
+        D.ev[1] = keep[1];
+        D.ev[2] = keep[2];
+        if (rc) return rc;
+    }
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    double scan = 0, post = 0;
+    for (uint32_t it = 0; it < iters; ++it) {
+        float a = 0, b = 0;
+        cudaEventElapsedTime(&a, evs[it * 3], evs[it * 3 + 1]);
+        cudaEventElapsedTime(&b, evs[it * 3 + 1], evs[it * 3 + 2]);
+        scan += a;
+        post += b;
+    }
+    float whole = 0;
+    cudaEventElapsedTime(&whole, evs[0], evs[(size_t)iters * 3 - 1]);
+    for (auto &e : evs) cudaEventDestroy(e);
+    pqv_timing tm{};
+    tm.scan_ms = scan / iters;
+    tm.post_ms = post / iters;
+    tm.total_ms = whole / iters;
+    tm.scan_bytes = sh.n_rows * (u64)ds->dim * 4;
+    tm.launches = 3;
+    tm.grid = g.grid;
+    ctx->last = tm;
+    *out_ms_per_scan = tm.scan_ms;
+    return PQV_OK;
+}
+
+// ---- k-means pieces ------------------------------------------------------------------------------
+static int dist_launch(DeviceState &D, const float *d_data, const uint32_t *d_ids, u64 n, uint32_t dim, const float *d_vec,
+                       float *d_out, int min_update) {
+    const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_data) & 15) == 0);
+    const size_t smem = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)SCAN_WARPS * pqv::TileCfg<0, true>::TILE_FLOATS * 4;
+    const u64 NG = (n + 31) / 32;
+    const uint32_t grid = (uint32_t)std::min<u64>((NG + SCAN_WARPS - 1) / SCAN_WARPS, (u64)D.sm_count * 4);
+#define DIST_GO(V, G)                                                                                        \
+    do {                                                                                                     \
+        auto kern = pqv::l2_dist_kernel<V, G, SCAN_WARPS>;                                                   \
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        kern<<<grid, SCAN_WARPS * 32, smem, D.stream>>>(d_data, d_ids, n, dim, d_vec, d_out, min_update);    \
+    } while (0)
+    if (vec4) {
+        if (d_ids) DIST_GO(true, true);
+        else DIST_GO(true, false);
+    } else {
+        if (d_ids) DIST_GO(false, true);
+        else DIST_GO(false, false);
+    }
+#undef DIST_GO
+    CU_TRY(cudaGetLastError());
+    return PQV_OK;
+}
+
+// resolve (handle, rows) to a device pointer for the first `n` rows; streams host rows into scratch
+static int resolve_rows(pqv_ctx *ctx, uint64_t handle, const float *rows, u64 n, uint32_t dim, DeviceState **Dout,
+                        const float **d_rows) {
+    if (rows) {
+        DeviceState &D = ctx->devs[0];
+        DevGuard guard(D.dev);
+        PQV_TRY(D.d_tmp_rows.ensure((size_t)n * dim));
+        CU_TRY(cudaMemcpyAsync(D.d_tmp_rows.p, rows, (size_t)n * dim * 4, cudaMemcpyHostToDevice, D.stream));
+        *Dout = &D;
+        *d_rows = D.d_tmp_rows.p;
+        return PQV_OK;
+    }
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu (and rows is null)", (unsigned long long)handle);
+    if (ds->dim != dim) return fail(PQV_EINVAL, "dimension mismatch: dataset has %u, call has %u", ds->dim, dim);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "k-means entry points need a single-device dataset");
+    if (n > ds->n_rows) return fail(PQV_EINVAL, "n = %llu exceeds the dataset's %llu rows", (unsigned long long)n, (unsigned long long)ds->n_rows);
+    *Dout = &ctx->devs[ds->shards[0].di];
+    *d_rows = ds->shards[0].d_data;
+    return PQV_OK;
+}
+
+int pqv_kmeans_assign(pqv_ctx *ctx, uint64_t handle, const float *rows, uint64_t n, uint32_t dim, const float *centroids,
+                      uint32_t n_clusters, uint32_t *out_assign, uint64_t *out_sizes) {
+    if (!ctx || !centroids || (!out_assign && n)) return fail(PQV_EINVAL, "null argument");
+    if (dim == 0) return fail(PQV_EINVAL, "Embedding dimension must be > 0");
+    if (n_clusters == 0) return fail(PQV_EINVAL, "Cluster count must be > 0");  // src/ivf/index.rs:24
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (out_sizes) memset(out_sizes, 0, sizeof(uint64_t) * n_clusters);
+    if (n == 0) return PQV_OK;
+    // host rows are streamed in bounded pieces so scratch stays small
+    const u64 piece = rows ? std::max<u64>(1, (u64)(256u << 20) / ((u64)dim * 4)) : n;
+    for (u64 off = 0; off < n; off += piece) {
+        const u64 cnt = std::min<u64>(piece, n - off);
+        DeviceState *D = nullptr;
+        const float *d_rows = nullptr;
+        PQV_TRY(resolve_rows(ctx, handle, rows ? rows + off * dim : nullptr, rows ? cnt : n, dim, &D, &d_rows));
+        DevGuard guard(D->dev);
+        if (!rows) d_rows += off * dim;
+        PQV_TRY(D->d_centroids.ensure((size_t)n_clusters * dim));
+        if (off == 0)
+            CU_TRY(cudaMemcpyAsync(D->d_centroids.p, centroids, (size_t)n_clusters * dim * 4, cudaMemcpyHostToDevice, D->stream));
+        PQV_TRY(D->d_assign.ensure(cnt));
+        const uint32_t grid = (uint32_t)((cnt + pqv::AS_BM - 1) / pqv::AS_BM);
+        const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rows) & 15) == 0);
+        if (vec4) pqv::kmeans_assign_kernel<true><<<grid, 256, 0, D->stream>>>(d_rows, cnt, dim, D->d_centroids.p, n_clusters, D->d_assign.p);
+        else pqv::kmeans_assign_kernel<false><<<grid, 256, 0, D->stream>>>(d_rows, cnt, dim, D->d_centroids.p, n_clusters, D->d_assign.p);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(out_assign + off, D->d_assign.p, cnt * 4, cudaMemcpyDeviceToHost, D->stream));
+        CU_TRY(cudaStreamSynchronize(D->stream));
+    }
+    if (out_sizes)
+        for (u64 i = 0; i < n; ++i) out_sizes[out_assign[i]]++;
+    return PQV_OK;
+}
+
+int pqv_min_dist_update(pqv_ctx *ctx, uint64_t handle, const float *rows, const uint64_t *row_sel, uint64_t n_sel,
+                        uint32_t dim, const float *centroid, int init, float *inout_min_dist) {
+    if (!ctx || !centroid || (!inout_min_dist && n_sel)) return fail(PQV_EINVAL, "null argument");
+    if (dim == 0) return fail(PQV_EINVAL, "Embedding dimension must be > 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    if (n_sel == 0) return PQV_OK;
+    u64 n_table = n_sel;
+    if (row_sel) {
+        n_table = 0;
+        for (u64 i = 0; i < n_sel; ++i) n_table = std::max<u64>(n_table, row_sel[i] + 1);
+        if (n_table > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "row ids are u32");
+    }
+    DeviceState *D = nullptr;
+    const float *d_rows = nullptr;
+    PQV_TRY(resolve_rows(ctx, handle, rows, n_table, dim, &D, &d_rows));
+    DevGuard guard(D->dev);
+    const uint32_t *d_ids = nullptr;
+    if (row_sel) {
+        std::vector<uint32_t> ids32(n_sel);
+        for (u64 i = 0; i < n_sel; ++i) ids32[i] = (uint32_t)row_sel[i];
+        PQV_TRY(D->d_row_ids.ensure(n_sel));
+        CU_TRY(cudaMemcpyAsync(D->d_row_ids.p, ids32.data(), n_sel * 4, cudaMemcpyHostToDevice, D->stream));
+        CU_TRY(cudaStreamSynchronize(D->stream));  // ids32 is a local
+        d_ids = D->d_row_ids.p;
+    }
+    PQV_TRY(D->d_vec.ensure(dim));
+    PQV_TRY(D->d_dist.ensure(n_sel));
+    CU_TRY(cudaMemcpyAsync(D->d_vec.p, centroid, (size_t)dim * 4, cudaMemcpyHostToDevice, D->stream));
+    if (!init) CU_TRY(cudaMemcpyAsync(D->d_dist.p, inout_min_dist, n_sel * 4, cudaMemcpyHostToDevice, D->stream));
+    PQV_TRY(dist_launch(*D, d_rows, d_ids, n_sel, dim, D->d_vec.p, D->d_dist.p, init ? 0 : 1));
+    CU_TRY(cudaMemcpyAsync(inout_min_dist, D->d_dist.p, n_sel * 4, cudaMemcpyDeviceToHost, D->stream));
+    CU_TRY(cudaStreamSynchronize(D->stream));
+    return PQV_OK;
+}
+
+int pqv_centroid_rank(pqv_ctx *ctx, const float *centroids, uint32_t n_clusters, uint32_t dim, const float *queries,
+                      uint32_t n_queries, uint32_t nprobe, uint32_t *out_cluster_ids, uint32_t *out_nprobe_eff) {
+    if (!ctx || !centroids || (n_queries && (!queries || !out_cluster_ids))) return fail(PQV_EINVAL, "null argument");
+    if (dim == 0) return fail(PQV_EINVAL, "Embedding dimension must be > 0");
+    if (n_clusters == 0) return fail(PQV_EINVAL, "Cluster count must be > 0");
+    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");  // src/ivf/search.rs:72
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const uint32_t np = std::min(nprobe, n_clusters);  // src/ivf/index.rs:131
+    if (out_nprobe_eff) *out_nprobe_eff = np;
+    DeviceState &D = ctx->devs[0];
+    DevGuard guard(D.dev);
+    PQV_TRY(D.d_centroids.ensure((size_t)n_clusters * dim));
+    PQV_TRY(D.d_vec.ensure(dim));
+    PQV_TRY(D.d_dist.ensure(n_clusters));
+    CU_TRY(cudaMemcpyAsync(D.d_centroids.p, centroids, (size_t)n_clusters * dim * 4, cudaMemcpyHostToDevice, D.stream));
+    std::vector<float> dist(n_clusters);
+    std::vector<uint32_t> idx(n_clusters);
+    for (uint32_t q = 0; q < n_queries; ++q) {
+        CU_TRY(cudaMemcpyAsync(D.d_vec.p, queries + (size_t)q * dim, (size_t)dim * 4, cudaMemcpyHostToDevice, D.stream));
+        // index.rs:138 squared_l2_distance(query, centroid); (q-c)^2 == (c-q)^2 bit for bit
+        PQV_TRY(dist_launch(D, D.d_centroids.p, nullptr, n_clusters, dim, D.d_vec.p, D.d_dist.p, 0));
+        CU_TRY(cudaMemcpyAsync(dist.data(), D.d_dist.p, (size_t)n_clusters * 4, cudaMemcpyDeviceToHost, D.stream));
+        CU_TRY(cudaStreamSynchronize(D.stream));
+        for (uint32_t i = 0; i < n_clusters; ++i) idx[i] = i;
+        // index.rs:143 stable sort, partial_cmp -> Equal for NaN
+        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return dist[a] < dist[b]; });
+        memcpy(out_cluster_ids + (size_t)q * np, idx.data(), (size_t)np * 4);
+    }
+    return PQV_OK;
+}
+
+// ---- streaming top-k (VectorTopKExec) --------------------------------------------------------------
+int pqv_topk_stream_begin(pqv_ctx *ctx, uint32_t dim, const float *query, uint32_t k, uint32_t flags, uint64_t *out_stream) {
+    if (!ctx || !query || !out_stream) return fail(PQV_EINVAL, "null argument");
+    PQV_TRY(check_topk_args(k, dim, flags));
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    DeviceState &D = ctx->devs[0];
+    DevGuard guard(D.dev);
+    StreamState *s = new StreamState();
+    s->dim = dim;
+    s->k = k;
+    s->flags = flags;
+    int rc = s->d_query.ensure(dim);
+    if (!rc) rc = s->carry[0].ensure(PQV_MAX_K);
+    if (!rc) rc = s->carry[1].ensure(PQV_MAX_K);
+    if (!rc) rc = s->ent_acc.ensure((size_t)(1u << 22) + 1);
+    if (rc) {
+        delete s;
+        return rc;
+    }
+    CU_TRY(cudaMemcpyAsync(s->d_query.p, query, (size_t)dim * 4, cudaMemcpyHostToDevice, D.stream));
+    CU_TRY(cudaMemsetAsync(s->carry[0].p, 0xFF, (size_t)PQV_MAX_K * 8, D.stream));
+    CU_TRY(cudaMemsetAsync(s->ent_acc.p, 0, 8, D.stream));
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    for (auto &ev : s->scan_done) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming));
+    const u64 h = ctx->next_handle++;
+    ctx->streams[h] = s;
+    *out_stream = h;
+    return PQV_OK;
+}
+
+static int stream_drain(DeviceState &D, StreamState *s) {
+    bool overflow = false;
+    PQV_TRY(fetch_entrants(D, s->ent_acc.p, (uint32_t)(s->ent_acc.cap - 1), s->host_entrants, &overflow));
+    if (overflow) return fail(PQV_ECUDA, "stream entrant accumulator overflow (internal bound violated)");
+    CU_TRY(cudaMemsetAsync(s->ent_acc.p, 0, 8, D.stream));
+    s->ent_rows_bound = 0;
+    return PQV_OK;
+}
+
+static int stream_push_impl(pqv_ctx *ctx, uint64_t stream, const void *values, uint64_t n_rows, bool f64) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->streams.find(stream);
+    if (it == ctx->streams.end()) return fail(PQV_EHANDLE, "unknown stream handle %llu", (unsigned long long)stream);
+    StreamState *s = it->second;
+    if (n_rows == 0) return PQV_OK;
+    if (!values) return fail(PQV_EINVAL, "values is null");
+    if (s->rows_pushed + n_rows > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "row positions are u32");
+    DeviceState &D = ctx->devs[0];
+    DevGuard guard(D.dev);
+    const int cur = s->cur;
+    const size_t elems = (size_t)n_rows * s->dim;
+    // every row could be an entrant in the worst case: drain the accumulator before it can overflow
+    if (s->ent_rows_bound + n_rows > s->ent_acc.cap - 1) {
+        PQV_TRY(stream_drain(D, s));
+        if (n_rows > s->ent_acc.cap - 1) {
+            CU_TRY(cudaStreamSynchronize(D.stream));
+            PQV_TRY(s->ent_acc.ensure((size_t)n_rows + 1));
+            CU_TRY(cudaMemsetAsync(s->ent_acc.p, 0, 8, D.stream));
+        }
+    }
+    // staging[cur] was last read by the scan two pushes ago
+    if (s->any) CU_TRY(cudaStreamWaitEvent(D.copy_stream, s->scan_done[cur], 0));
+    if (elems > s->staging[cur].cap) {
+        CU_TRY(cudaEventSynchronize(s->scan_done[cur]));
+        PQV_TRY(s->staging[cur].ensure(elems));
+    }
+    if (f64) {
+        CU_TRY(cudaStreamSynchronize(D.copy_stream));
+        CU_TRY(cudaStreamSynchronize(D.stream));
+        PQV_TRY(s->staging64.ensure(elems));
+        CU_TRY(cudaMemcpyAsync(s->staging64.p, values, elems * 8, cudaMemcpyHostToDevice, D.copy_stream));
+        pqv::narrow_f64_kernel<<<D.sm_count * 4, 256, 0, D.copy_stream>>>(s->staging64.p, s->staging[cur].p, elems);
+        CU_TRY(cudaGetLastError());
+    } else {
+        CU_TRY(cudaMemcpyAsync(s->staging[cur].p, values, elems * 4, cudaMemcpyHostToDevice, D.copy_stream));
+    }
+    CU_TRY(cudaEventRecord(s->copy_done, D.copy_stream));
+    CU_TRY(cudaStreamWaitEvent(D.stream, s->copy_done, 0));
+    const int order = (s->flags & PQV_SUM_SEQ) ? 1 : 0;
+    const int cc = s->carry_cur;
+    PQV_TRY(enqueue_scan(ctx, D, s->staging[cur].p, nullptr, n_rows, s->dim, s->d_query.p, s->k, order,
+                         (uint32_t)s->rows_pushed, s->carry[cc].p, s->carry[cc ^ 1].p, s->ent_acc.p,
+                         (uint32_t)(s->ent_acc.cap - 1), false, nullptr));
+    CU_TRY(cudaEventRecord(s->scan_done[cur], D.stream));
+    s->carry_cur ^= 1;
+    s->cur ^= 1;
+    s->any = true;
+    s->rows_pushed += n_rows;
+    s->ent_rows_bound += n_rows;
+    // the caller's buffer is only borrowed for this call: wait for the H2D copy (not for the scan)
+    CU_TRY(cudaEventSynchronize(s->copy_done));
+    return PQV_OK;
+}
+
+int pqv_topk_stream_push(pqv_ctx *ctx, uint64_t stream, const float *values, uint64_t n_rows) {
+    return stream_push_impl(ctx, stream, values, n_rows, false);
+}
+int pqv_topk_stream_push_f64(pqv_ctx *ctx, uint64_t stream, const double *values, uint64_t n_rows) {
+    return stream_push_impl(ctx, stream, values, n_rows, true);
+}
+
+int pqv_topk_stream_finish(pqv_ctx *ctx, uint64_t stream, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
+    if (!ctx || !out_row_idx || !out_dist || !out_count) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    auto it = ctx->streams.find(stream);
+    if (it == ctx->streams.end()) return fail(PQV_EHANDLE, "unknown stream handle %llu", (unsigned long long)stream);
+    StreamState *s = it->second;
+    DeviceState &D = ctx->devs[0];
+    DevGuard guard(D.dev);
+    int rc = PQV_OK;
+    size_t cnt = 0;
+    if (s->flags & PQV_TIES_BY_POSITION) {
+        std::vector<u64> keys(PQV_MAX_K);
+        cudaError_t e = cudaMemcpyAsync(keys.data(), s->carry[s->carry_cur].p, (size_t)PQV_MAX_K * 8, cudaMemcpyDeviceToHost, D.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+        if (e != cudaSuccess) rc = fail(PQV_ECUDA, "stream finish copy failed: %s", cudaGetErrorString(e));
+        else cnt = emit_by_position(keys, nullptr, s->k, s->flags, out_row_idx, out_dist);
+    } else {
+        rc = stream_drain(D, s);
+        if (!rc) cnt = replay_reference_heap(s->host_entrants, nullptr, s->k, s->flags, out_row_idx, out_dist);
+    }
+    cudaStreamSynchronize(D.stream);
+    cudaStreamSynchronize(D.copy_stream);
+    s->staging[0].release();
+    s->staging[1].release();
+    s->staging64.release();
+    s->carry[0].release();
+    s->carry[1].release();
+    s->d_query.release();
+    s->ent_acc.release();
+    for (auto &ev : s->scan_done)
+        if (ev) cudaEventDestroy(ev);
+    if (s->copy_done) cudaEventDestroy(s->copy_done);
+    delete s;
+    ctx->streams.erase(it);
+    if (rc) return rc;
+    *out_count = (uint32_t)cnt;
+    return PQV_OK;
+}
+
+}  // extern "C"

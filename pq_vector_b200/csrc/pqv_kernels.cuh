@@ -1,0 +1,611 @@
+// pqv_kernels.cuh -- sm_100a device code for the pq-vector squared-L2 / top-k / IVF-assign hot path.
+//
+// Design: every distance is produced with the reference's exact f32 operation
+// order (no FMA: __fsub_rn/__fmul_rn/__fadd_rn), so results are bit-identical to the Rust loops:
+//   PQV_SUM_UNROLL4  src/ivf/index.rs:461-480      sum += ((d0^2+d1^2)+d2^2)+d3^2, scalar tail
+//   PQV_SUM_SEQ      src/df_vector/exec.rs:529-533  dist += diff*diff
+// The per-row sum is a serial chain, so one warp works on a group of 32 rows: all lanes load each
+// row with coalesced 128-bit loads and compute the (independent) chain terms in parallel, the
+// terms are transposed through a padded shared-memory tile, and then lane r runs row r's serial
+// chain in the reference order.  HBM is read exactly once; the chain costs one FADD per term.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pqv {
+
+typedef unsigned long long u64;
+constexpr u64 KEY_MAX = 0xFFFFFFFFFFFFFFFFull;
+
+// ------------------------------------------------------------------------------------------------
+// small helpers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 ld_stream_v4(const float *p) {
+    // read-only, streaming: do not allocate in L1 (each byte is used once)
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ld_stream_f32(const float *p) {
+    float r;
+    asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+
+// one chain term of src/ivf/index.rs:467-471: ((d0*d0 + d1*d1) + d2*d2) + d3*d3, d = a - b
+__device__ __forceinline__ float chunk4(const float4 a, const float4 b) {
+    const float d0 = __fsub_rn(a.x, b.x), d1 = __fsub_rn(a.y, b.y);
+    const float d2 = __fsub_rn(a.z, b.z), d3 = __fsub_rn(a.w, b.w);
+    return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(d0, d0), __fmul_rn(d1, d1)), __fmul_rn(d2, d2)),
+                     __fmul_rn(d3, d3));
+}
+__device__ __forceinline__ float sq1(const float a, const float b) {
+    const float d = __fsub_rn(a, b);
+    return __fmul_rn(d, d);
+}
+
+// ------------------------------------------------------------------------------------------------
+// group_distance: squared-L2 of the 32 rows of group g against the vector staged in s_vec.
+// Returns in lane r the distance of row (g*32 + r) (rows past n are clamped to n-1; callers mask).
+//   ORDER 0: unroll-4 order, a = s_vec (query), b = row     (search.rs:117  squared_l2_distance(query, vec))
+//   ORDER 1: sequential,     diff = row - s_vec             (exec.rs:531    value - q)
+//   VEC4   : dim % 4 == 0 and 16-byte aligned rows -> 128-bit loads; otherwise scalar loads.
+//   GATHER : row index taken from row_ids[position].
+// tile: per-warp shared memory, 32 rows x TSTRIDE floats (TSTRIDE = 36, or 132 for ORDER 1 + VEC4).
+// ------------------------------------------------------------------------------------------------
+template <int ORDER, bool VEC4>
+struct TileCfg {
+    static constexpr int TERMS = (ORDER == 1 && VEC4) ? 4 : 1;  // chain terms per lane per column block
+    static constexpr int TSTRIDE = 32 * TERMS + 4;              // floats; /4 is odd -> LDS.128 conflict-free
+    static constexpr int TILE_FLOATS = 32 * TSTRIDE;
+};
+
+template <int ORDER, bool VEC4, bool GATHER>
+__device__ __forceinline__ float group_distance(const float *__restrict__ data,
+                                                const uint32_t *__restrict__ row_ids, const u64 n,
+                                                const uint32_t dim, const u64 g, const float *s_vec,
+                                                float *tile, const uint32_t lane) {
+    constexpr int TSTRIDE = TileCfg<ORDER, VEC4>::TSTRIDE;
+    const u64 pos = g * 32 + lane;
+    const u64 posc = pos < n ? pos : n - 1;
+    const u64 my_row = GATHER ? (u64)row_ids[posc] : posc;
+    // dense groups are contiguous: row r of the group starts at gbase + r*dim (clamped at the table end)
+    const u64 g_first = g * 32;
+    float sum = 0.0f;
+    float *trow = tile + lane * TSTRIDE;
+
+    if constexpr (VEC4) {
+        const uint32_t ncb = (dim + 127u) >> 7;
+        for (uint32_t cb = 0; cb < ncb; ++cb) {
+            const uint32_t col = (cb << 7) + (lane << 2);
+            const bool inb = col < dim;
+            float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (inb) q4 = *reinterpret_cast<const float4 *>(s_vec + col);
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                float4 v[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    u64 row;
+                    if constexpr (GATHER) {
+                        row = (u64)__shfl_sync(0xffffffffu, (uint32_t)my_row, r0 + j);
+                    } else {
+                        row = g_first + (r0 + j);
+                        row = row < n ? row : n - 1;
+                    }
+                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (inb) v[j] = ld_stream_v4(data + row * dim + col);
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if constexpr (ORDER == 0) {
+                        tile[(r0 + j) * TSTRIDE + lane] = chunk4(q4, v[j]);
+                    } else {
+                        float4 p;
+                        p.x = sq1(v[j].x, q4.x);
+                        p.y = sq1(v[j].y, q4.y);
+                        p.z = sq1(v[j].z, q4.z);
+                        p.w = sq1(v[j].w, q4.w);
+                        *reinterpret_cast<float4 *>(tile + (r0 + j) * TSTRIDE + (lane << 2)) = p;
+                    }
+                }
+            }
+            __syncwarp();
+            // serial chain, lane = row
+            const uint32_t rem = dim - (cb << 7);  // elements left in this block (multiple of 4)
+            if constexpr (ORDER == 0) {
+                if (rem >= 128u) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const float4 t = *reinterpret_cast<const float4 *>(trow + 4 * j);
+                        sum = __fadd_rn(sum, t.x);
+                        sum = __fadd_rn(sum, t.y);
+                        sum = __fadd_rn(sum, t.z);
+                        sum = __fadd_rn(sum, t.w);
+                    }
+                } else {
+                    const uint32_t nt = rem >> 2;
+                    for (uint32_t j = 0; j < nt; ++j) sum = __fadd_rn(sum, trow[j]);
+                }
+            } else {
+                if (rem >= 128u) {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float4 t = *reinterpret_cast<const float4 *>(trow + 4 * j);
+                        sum = __fadd_rn(sum, t.x);
+                        sum = __fadd_rn(sum, t.y);
+                        sum = __fadd_rn(sum, t.z);
+                        sum = __fadd_rn(sum, t.w);
+                    }
+                } else {
+                    for (uint32_t j = 0; j < rem; ++j) sum = __fadd_rn(sum, trow[j]);
+                }
+            }
+            __syncwarp();
+        }
+    } else {
+        // scalar-load path (dim % 4 != 0 or unaligned base).  ORDER 0: lane handles chunk j of 4
+        // consecutive elements; ORDER 1: lane handles one element.
+        constexpr uint32_t EPL = (ORDER == 0) ? 4u : 1u;       // elements per lane per block
+        const uint32_t n_terms = (ORDER == 0) ? (dim >> 2) : dim;
+        const uint32_t nblk = (n_terms + 31u) >> 5;
+        for (uint32_t cb = 0; cb < nblk; ++cb) {
+            const uint32_t term = (cb << 5) + lane;
+            const bool inb = term < n_terms;
+            const uint32_t col = term * EPL;
+            float q[EPL];
+#pragma unroll
+            for (uint32_t e = 0; e < EPL; ++e) q[e] = inb ? s_vec[col + e] : 0.f;
+#pragma unroll 4
+            for (int r = 0; r < 32; ++r) {
+                u64 row;
+                if constexpr (GATHER) {
+                    row = (u64)__shfl_sync(0xffffffffu, (uint32_t)my_row, r);
+                } else {
+                    row = g_first + r;
+                    row = row < n ? row : n - 1;
+                }
+                float t = 0.f;
+                if (inb) {
+                    const float *rp = data + row * dim + col;
+                    if constexpr (ORDER == 0) {
+                        const float4 v = make_float4(ld_stream_f32(rp), ld_stream_f32(rp + 1),
+                                                     ld_stream_f32(rp + 2), ld_stream_f32(rp + 3));
+                        t = chunk4(make_float4(q[0], q[1], q[2], q[3]), v);
+                    } else {
+                        t = sq1(ld_stream_f32(rp), q[0]);
+                    }
+                }
+                tile[r * TSTRIDE + lane] = t;
+            }
+            __syncwarp();
+            const uint32_t left = n_terms - (cb << 5);
+            const uint32_t nt = left < 32u ? left : 32u;
+            for (uint32_t j = 0; j < nt; ++j) sum = __fadd_rn(sum, trow[j]);
+            __syncwarp();
+        }
+        if constexpr (ORDER == 0) {
+            // scalar tail of src/ivf/index.rs:474-478: each leftover element is its own chain term
+            const float *rp = data + my_row * dim;
+            for (uint32_t i = (dim >> 2) << 2; i < dim; ++i) sum = __fadd_rn(sum, sq1(s_vec[i], rp[i]));
+        }
+    }
+    return sum;
+}
+
+// ------------------------------------------------------------------------------------------------
+// l2_scan_topk_kernel: distance scan + per-CTA exact top-k + heap-entrant candidate emission.
+//
+// CTA b owns the contiguous groups [NG*b/G, NG*(b+1)/G) and walks them in position order, WARPS
+// groups per lock-step iteration.  A row passes the filter iff bits(d) < tau, where tau is the
+// k-th smallest distance among the rows this CTA finished in EARLIER iterations (0xFFFFFFFF while
+// it holds fewer than k), optionally capped by cap_bits (a bound carried in from rows that precede
+// the whole launch).  Because tau only ever summarises rows at smaller positions, it is an upper
+// bound of the reference heap's root at that position, so the rows that pass are a superset of the
+// rows the reference's BinaryHeap would ever admit.  Passing keys go to
+//   (a) the CTA's sorted top-k list  -> cta_topk[b][0..kcap)   key = bits(d) << 32 | position
+//   (b) the entrant list             -> ent[first_pos_of_cta ...], ent_count[b]
+// ------------------------------------------------------------------------------------------------
+struct ScanParams {
+    const float *data;
+    const float *query;       // device
+    const uint32_t *row_ids;  // device, GATHER only
+    u64 n;                    // candidates to scan
+    uint32_t dim;
+    uint32_t k;
+    uint32_t kcap;     // pow2 >= max(k, 32)
+    uint32_t sort_n;   // pow2 >= kcap + flush_at + WARPS*32
+    uint32_t flush_at;
+    uint32_t cap_bits;  // static cap on tau (0xFFFFFFFF = none)
+    const u64 *carry;   // device, may be null: ascending top-k keys of all rows that precede this launch;
+                        // its k-th distance caps tau (streaming pushes)
+    uint32_t pos_base;  // added to positions in emitted keys
+    u64 *cta_topk;      // [grid][kcap]
+    u64 *ent;           // [n]
+    uint32_t *ent_count;  // [grid]
+};
+
+__device__ __forceinline__ void bitonic_sort_smem(u64 *s, const uint32_t n, const uint32_t tid,
+                                                  const uint32_t nthreads) {
+    for (uint32_t size = 2; size <= n; size <<= 1) {
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t t = tid; t < (n >> 1); t += nthreads) {
+                const uint32_t i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                const uint32_t j = i + stride;
+                const bool up = (i & size) == 0;
+                const u64 a = s[i], b = s[j];
+                if ((a > b) == up) {
+                    s[i] = b;
+                    s[j] = a;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+template <int ORDER, bool VEC4, bool GATHER, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) l2_scan_topk_kernel(const ScanParams p) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TILE_FLOATS = TileCfg<ORDER, VEC4>::TILE_FLOATS;
+    constexpr uint32_t NT = WARPS * 32;
+    const uint32_t dim_pad = (p.dim + 3u) & ~3u;
+    float *s_query = reinterpret_cast<float *>(smem_raw);
+    float *s_tiles = s_query + dim_pad;
+    u64 *s_keys = reinterpret_cast<u64 *>(s_tiles + WARPS * TILE_FLOATS);
+    __shared__ uint32_t s_buf_count;
+    __shared__ uint32_t s_tau;
+
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u64 NG = (p.n + 31) >> 5;
+    const u64 g_begin = NG * blockIdx.x / gridDim.x;
+    const u64 g_end = NG * (blockIdx.x + 1) / gridDim.x;
+
+    uint32_t cap_bits = p.cap_bits;
+    if (p.carry) {
+        const u64 kth = p.carry[p.k - 1];
+        const uint32_t t = (kth == KEY_MAX) ? 0xFFFFFFFFu : (uint32_t)(kth >> 32);
+        cap_bits = t < cap_bits ? t : cap_bits;
+    }
+    for (uint32_t i = tid; i < p.dim; i += NT) s_query[i] = p.query[i];
+    for (uint32_t i = tid; i < p.sort_n; i += NT) s_keys[i] = KEY_MAX;
+    if (tid == 0) {
+        s_buf_count = 0;
+        s_tau = cap_bits;
+    }
+    __syncthreads();
+
+    float *tile = s_tiles + warp * TILE_FLOATS;
+    u64 *s_buf = s_keys + p.kcap;
+    const u64 ent_base = g_begin * 32;
+    uint32_t ent_written = 0;
+
+    auto flush = [&]() {
+        const uint32_t n_new = s_buf_count;
+        __syncthreads();
+        for (uint32_t i = tid; i < n_new; i += NT) p.ent[ent_base + ent_written + i] = s_buf[i];
+        ent_written += n_new;
+        for (uint32_t i = p.kcap + n_new + tid; i < p.sort_n; i += NT) s_keys[i] = KEY_MAX;
+        __syncthreads();
+        bitonic_sort_smem(s_keys, p.sort_n, tid, NT);
+        for (uint32_t i = p.k + tid; i < p.kcap; i += NT) s_keys[i] = KEY_MAX;
+        if (tid == 0) {
+            s_buf_count = 0;
+            const u64 kth = s_keys[p.k - 1];
+            const uint32_t t = (kth == KEY_MAX) ? 0xFFFFFFFFu : (uint32_t)(kth >> 32);
+            s_tau = t < cap_bits ? t : cap_bits;
+        }
+        __syncthreads();
+    };
+
+    for (u64 g0 = g_begin; g0 < g_end; g0 += WARPS) {
+        const u64 g = g0 + warp;
+        const bool active = g < g_end;  // warp-uniform
+        float d = 0.f;
+        if (active) d = group_distance<ORDER, VEC4, GATHER>(p.data, p.row_ids, p.n, p.dim, g, s_query, tile, lane);
+        const u64 pos = g * 32 + lane;
+        const uint32_t bits = __float_as_uint(d);
+        const bool pass = active && pos < p.n && bits < s_tau;
+        const uint32_t m = __ballot_sync(0xffffffffu, pass);
+        bool crossed = false;
+        if (m) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(&s_buf_count, __popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (pass) s_buf[base + __popc(m & ((1u << lane) - 1u))] = ((u64)bits << 32) | (u64)(uint32_t)(pos + p.pos_base);
+            // the count only grows inside an iteration, so the warp whose append ends at the final
+            // count sees whether the flush mark was reached; OR-reduce that across the CTA.
+            crossed = base + __popc(m) >= p.flush_at;
+        }
+        if (__syncthreads_or(crossed)) flush();  // one barrier, CTA-uniform decision
+    }
+    if (s_buf_count > 0) flush();
+
+    u64 *out = p.cta_topk + (u64)blockIdx.x * p.kcap;
+    for (uint32_t i = tid; i < p.kcap; i += NT) out[i] = s_keys[i];
+    if (tid == 0) p.ent_count[blockIdx.x] = ent_written;
+}
+
+// ------------------------------------------------------------------------------------------------
+// topk_prefix_merge_kernel (1 CTA): walks the per-CTA lists in CTA (= position) order keeping the
+// running exact top-k P.  gthr[b] = distance bits of the k-th smallest key among all CTAs < b (the
+// reference heap's root when the scan reaches CTA b's first row; P starts from `carry`).  The final
+// P (ascending by (distance, position)) is written to final_topk[0..kcap).
+// `carry` (may be null): kcap keys of an earlier launch's final_topk to start P from.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) topk_prefix_merge_kernel(const u64 *__restrict__ cta_topk,
+                                                                 const uint32_t n_lists, const uint32_t k,
+                                                                 const uint32_t kcap,
+                                                                 const u64 *__restrict__ carry,
+                                                                 uint32_t *__restrict__ gthr,
+                                                                 u64 *__restrict__ final_topk) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *s = reinterpret_cast<u64 *>(smem_raw);  // 2*kcap keys: [P ascending | next list descending]
+    const uint32_t tid = threadIdx.x, nt = blockDim.x;
+    for (uint32_t i = tid; i < kcap; i += nt) s[i] = carry ? carry[i] : KEY_MAX;
+    __syncthreads();
+    for (uint32_t b = 0; b < n_lists; ++b) {
+        if (tid == 0) {
+            const u64 kth = s[k - 1];
+            const uint32_t t = (kth == KEY_MAX) ? 0xFFFFFFFFu : (uint32_t)(kth >> 32);
+            gthr[b] = t;
+        }
+        const u64 *L = cta_topk + (u64)b * kcap;
+        for (uint32_t i = tid; i < kcap; i += nt) s[kcap + i] = L[kcap - 1 - i];
+        __syncthreads();
+        // bitonic merge of the 2*kcap bitonic sequence, ascending
+        for (uint32_t stride = kcap; stride > 0; stride >>= 1) {
+            for (uint32_t t = tid; t < kcap; t += nt) {
+                const uint32_t i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
+                const uint32_t j = i + stride;
+                const u64 a = s[i], c = s[j];
+                if (a > c) {
+                    s[i] = c;
+                    s[j] = a;
+                }
+            }
+            __syncthreads();
+        }
+        for (uint32_t i = k + tid; i < kcap; i += nt) s[i] = KEY_MAX;
+        __syncthreads();
+    }
+    for (uint32_t i = tid; i < kcap; i += nt) final_topk[i] = s[i];
+}
+
+// ------------------------------------------------------------------------------------------------
+// entrant_filter_kernel: CTA b keeps the entrant keys of scan-CTA b whose distance is below gthr[b]
+// and appends them (order irrelevant, the host sorts by position) to out[1..]; out[0] = count.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) entrant_filter_kernel(const u64 *__restrict__ ent,
+                                                             const uint32_t *__restrict__ ent_count,
+                                                             const uint32_t *__restrict__ gthr, const u64 n,
+                                                             u64 *__restrict__ out, const uint32_t out_cap) {
+    const uint32_t b = blockIdx.x, G = gridDim.x;
+    const u64 NG = (n + 31) >> 5;
+    const u64 base = (NG * b / G) * 32;
+    const uint32_t cnt = ent_count[b];
+    const uint32_t thr = gthr[b];
+    const uint32_t lane = threadIdx.x & 31;
+    for (uint32_t i0 = 0; i0 < cnt; i0 += blockDim.x) {
+        const uint32_t i = i0 + threadIdx.x;
+        u64 key = 0;
+        bool keep = false;
+        if (i < cnt) {
+            key = ent[base + i];
+            keep = (uint32_t)(key >> 32) < thr;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, keep);
+        if (m) {
+            u64 slot = 0;
+            if (lane == 0) slot = atomicAdd(out, (u64)__popc(m));
+            slot = __shfl_sync(0xffffffffu, slot, 0);
+            const u64 idx = slot + __popc(m & ((1u << lane) - 1u));
+            if (keep && idx < out_cap) out[1 + idx] = key;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// l2_dist_kernel: plain distance sweep in index.rs order (a = row, b = vec as in index.rs:350/362
+// `squared_l2_distance(vec, centroid)`), optional row selection, store or k-means++ min-update
+// (index.rs:363-365: if dist < slot { slot = dist }).
+// ------------------------------------------------------------------------------------------------
+template <bool VEC4, bool GATHER, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) l2_dist_kernel(const float *__restrict__ data,
+                                                             const uint32_t *__restrict__ row_ids, const u64 n,
+                                                             const uint32_t dim, const float *__restrict__ vec,
+                                                             float *__restrict__ out, const int min_update) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TILE_FLOATS = TileCfg<0, VEC4>::TILE_FLOATS;
+    const uint32_t dim_pad = (dim + 3u) & ~3u;
+    float *s_vec = reinterpret_cast<float *>(smem_raw);
+    float *s_tiles = s_vec + dim_pad;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (uint32_t i = tid; i < dim; i += WARPS * 32) s_vec[i] = vec[i];
+    __syncthreads();
+    float *tile = s_tiles + warp * TILE_FLOATS;
+    const u64 NG = (n + 31) >> 5;
+    for (u64 g = (u64)blockIdx.x * WARPS + warp; g < NG; g += (u64)gridDim.x * WARPS) {
+        const float d = group_distance<0, VEC4, GATHER>(data, row_ids, n, dim, g, s_vec, tile, lane);
+        const u64 pos = g * 32 + lane;
+        if (pos < n) {
+            if (min_update) {
+                if (d < out[pos]) out[pos] = d;
+            } else {
+                out[pos] = d;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// kmeans_assign_kernel: exact f32 argmin over all centroids for a tile of 64 rows
+// (src/ivf/index.rs:244-257 / 405-415).  Register-tiled SIMT: 256 threads = 16 (centroid dir) x 16
+// (row dir), each thread owns 4 rows x 4 centroids; every (row, centroid) pair keeps its own serial
+// chain in the reference order, operands staged through shared memory in blocks of 32 columns.
+// Ties: lowest centroid index (strict '<' while scanning centroids upwards); NaN/inf never win.
+// ------------------------------------------------------------------------------------------------
+constexpr int AS_BM = 64, AS_BN = 64, AS_BK = 32, AS_LD = AS_BK + 4;
+
+template <bool VEC4>
+__global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__restrict__ rows, const u64 n,
+                                                               const uint32_t dim,
+                                                               const float *__restrict__ centroids,
+                                                               const uint32_t n_clusters,
+                                                               uint32_t *__restrict__ out_assign) {
+    __shared__ __align__(16) float As[2][AS_BM * AS_LD];
+    __shared__ __align__(16) float Bs[2][AS_BN * AS_LD];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t tx = tid & 15, ty = tid >> 4;
+    const u64 row0 = (u64)blockIdx.x * AS_BM;
+    const uint32_t n4 = dim >> 2;                       // full 4-chunks (chain terms)
+    const uint32_t nkb = (n4 + 7) >> 3;                 // blocks of 8 chunks = 32 columns
+    const uint32_t tail0 = n4 << 2, ntail = dim - tail0;  // scalar tail terms (dim % 4)
+
+    // loader mapping: 64 rows x 8 chunks = 512 float4 per tile -> 2 per thread
+    auto load_tile = [&](float *dst, const float *src, const u64 first, const u64 limit, const uint32_t kb) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+            const uint32_t idx = tid + it * 256;
+            const uint32_t r = idx >> 3, c = idx & 7;
+            const uint32_t chunk = kb * 8 + c;
+            u64 row = first + r;
+            row = row < limit ? row : limit - 1;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (chunk < n4) {
+                const float *sp = src + row * dim + (chunk << 2);
+                if constexpr (VEC4) v = *reinterpret_cast<const float4 *>(sp);
+                else v = make_float4(sp[0], sp[1], sp[2], sp[3]);
+            }
+            *reinterpret_cast<float4 *>(dst + r * AS_LD + (c << 2)) = v;
+        }
+    };
+
+    float run_d[4];
+    uint32_t run_i[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        run_d[i] = __int_as_float(0x7f800000);
+        run_i[i] = 0;
+    }
+
+    for (uint32_t cn = 0; cn < n_clusters; cn += AS_BN) {
+        float acc[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+        int buf = 0;
+        if (nkb > 0) {
+            load_tile(As[0], rows, row0, n, 0);
+            load_tile(Bs[0], centroids, cn, n_clusters, 0);
+        }
+        __syncthreads();
+        for (uint32_t kb = 0; kb < nkb; ++kb) {
+            if (kb + 1 < nkb) {
+                load_tile(As[buf ^ 1], rows, row0, n, kb + 1);
+                load_tile(Bs[buf ^ 1], centroids, cn, n_clusters, kb + 1);
+            }
+            const float *A = As[buf] + (ty * 4) * AS_LD;
+            const float *B = Bs[buf] + tx * AS_LD;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                float4 a[4], b[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) a[i] = *reinterpret_cast<const float4 *>(A + i * AS_LD + (c << 2));
+#pragma unroll
+                for (int j = 0; j < 4; ++j) b[j] = *reinterpret_cast<const float4 *>(B + (16 * j) * AS_LD + (c << 2));
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) acc[i][j] = __fadd_rn(acc[i][j], chunk4(a[i], b[j]));
+            }
+            __syncthreads();
+            buf ^= 1;
+        }
+        // scalar tail (dim % 4 != 0): each leftover column is its own chain term (index.rs:474-478)
+        for (uint32_t t = 0; t < ntail; ++t) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                u64 row = row0 + ty * 4 + i;
+                row = row < n ? row : n - 1;
+                const float av = rows[row * dim + tail0 + t];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t c = cn + tx + 16 * j;
+                    c = c < n_clusters ? c : n_clusters - 1;
+                    acc[i][j] = __fadd_rn(acc[i][j], sq1(av, centroids[(u64)c * dim + tail0 + t]));
+                }
+            }
+        }
+        // argmin over this centroid tile, first-min on ties
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            float bd = __int_as_float(0x7f800000);
+            uint32_t bi = 0xFFFFFFFFu;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const uint32_t c = cn + tx + 16 * j;
+                const float d = acc[i][j];
+                if (c < n_clusters && d < bd) {  // NaN fails '<'; inf fails '<' against inf
+                    bd = d;
+                    bi = c;
+                }
+            }
+#pragma unroll
+            for (int off = 8; off > 0; off >>= 1) {
+                const float od = __shfl_xor_sync(0xffffffffu, bd, off);
+                const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, off);
+                if (od < bd || (od == bd && oi < bi)) {
+                    bd = od;
+                    bi = oi;
+                }
+            }
+            if (bd < run_d[i]) {
+                run_d[i] = bd;
+                run_i[i] = bi;
+            }
+        }
+        __syncthreads();
+    }
+    if (tx == 0) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const u64 row = row0 + ty * 4 + i;
+            if (row < n) out_assign[row] = run_i[i];
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// synthetic data: uniform [0,1) on the 24-bit grid ((u32 >> 8) * 2^-24, the distribution of
+// rand's gen::<f32>() used by benches/bench_util.rs:29-41), counter-based and keyed by
+// (seed, absolute element index) so any row can be regenerated anywhere (stream defined in
+// DESIGN.md section 6; the test-side checker regenerates the same stream on the CPU).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t synth_u32(const u64 seed, const u64 idx) {
+    u64 z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z = z ^ (z >> 31);
+    return (uint32_t)(z >> 32);
+}
+
+__global__ void __launch_bounds__(256) synth_fill_kernel(float *__restrict__ out, const u64 first_elem,
+                                                         const u64 n_elems, const u64 seed) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n_elems; i += stride)
+        out[i] = (float)(synth_u32(seed, first_elem + i) >> 8) * (1.0f / 16777216.0f);
+}
+
+// f64 -> f32 narrowing of a pushed batch (src/df_vector/exec.rs:542 `value as f32`)
+__global__ void __launch_bounds__(256) narrow_f64_kernel(const double *__restrict__ in, float *__restrict__ out,
+                                                         const u64 n) {
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)in[i];
+}
+
+}  // namespace pqv

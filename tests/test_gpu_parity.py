@@ -1,0 +1,333 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle, bit for bit."""
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SQRT, SEQ, BYPOS = 2, 1, 4
+
+
+@pytest.fixture(scope="module")
+def P():
+    import pq_vector_b200 as P
+    return P
+
+
+@pytest.fixture(scope="module")
+def ctx(P):
+    c = P.Context()
+    yield c
+    c.close()
+
+
+def bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def check_topk(ds, data, q, k, flags, row_ids=None):
+    order = 1 if flags & SEQ else 0
+    do_sqrt = bool(flags & SQRT)
+    if row_ids is None:
+        r, d = ds.l2_topk(q, k, flags)
+        er, ed = O.topk_rerank(q, data, None, k, order, do_sqrt)
+    else:
+        r, d = ds.l2_topk_gather(q, row_ids, k, flags)
+        er, ed = O.topk_rerank_gather(q, data, row_ids, k, order, do_sqrt)
+    assert r.tolist() == er.tolist()
+    assert bits(d).tolist() == bits(ed).tolist()
+
+
+# ---- C1: the reference's own dataset ---------------------------------------------------------------
+VLDB_IDS = {0: [0, 126, 81, 265, 315, 464, 322, 269, 169, 140], 1: [1, 177, 57, 19, 36, 16, 450, 179, 9, 140],
+            100: [100, 181, 400, 352, 448, 476, 36, 198, 370, 213]}
+
+
+def test_c1_vldb_top10(ctx, vldb):
+    ds = ctx.dataset_from(vldb)
+    for qrow, ids in VLDB_IDS.items():
+        r, d = ds.l2_topk(vldb[qrow], 10, SQRT)
+        assert r.tolist() == ids
+        check_topk(ds, vldb, vldb[qrow], 10, SQRT)
+        check_topk(ds, vldb, vldb[qrow], 10, SEQ)          # VectorTopKExec order, squared distances
+    for qrow in range(0, 496, 37):                         # duplicates in the data included
+        check_topk(ds, vldb, vldb[qrow], 10, SQRT)
+        check_topk(ds, vldb, vldb[qrow], 496, SQRT)        # k == n
+        check_topk(ds, vldb, vldb[qrow], 600, SEQ)         # k > n -> 496 results
+    ds.drop()
+
+
+def test_reference_kats_through_the_abi(ctx):
+    # src/df_vector/tests.rs:31-39,99 and :166-174,235 (filter applied by the caller: ids >= min_id)
+    for rows, min_id, expect in [([(0, 0), (1, 0), (0, 2), (5, 5), (2, 2), (0.1, 0.1)], 2, [5, 2]),
+                                 ([(0, 0), (.05, .05), (.2, .2), (1, 1), (1.1, 1.1), (1.4, 1.4)], 3, [3, 4])]:
+        rows = np.array(rows, np.float32)
+        ds = ctx.dataset_from(rows)
+        r, _ = ds.l2_topk_gather(np.zeros(2, np.float32), np.arange(min_id, 6, dtype=np.uint32), 2, SEQ)
+        assert r.tolist() == expect
+        st = ctx.topk_stream(np.zeros(2, np.float32), 2, SEQ)
+        st.push(rows[min_id:])
+        r, _ = st.finish()
+        assert (r + min_id).tolist() == expect
+        ds.drop()
+    # src/ivf/index.rs:487-493
+    ds = ctx.dataset_from(np.array([[4, 5, 6]], np.float32))
+    _, d = ds.l2_topk(np.array([1, 2, 3], np.float32), 1, 0)
+    assert d.tolist() == [27.0]
+    ds.drop()
+
+
+# ---- seeded random inputs vs oracle ------------------------------------------------------------------
+@pytest.mark.parametrize("n,dim", [(1, 4), (31, 8), (32, 3), (33, 5), (257, 1), (1000, 7), (4096, 128), (5000, 130),
+                                   (3000, 768), (2000, 1000), (1500, 1536), (700, 4096), (50_000, 64)])
+def test_bruteforce_matches_oracle(ctx, n, dim):
+    rng = np.random.default_rng(n * 31 + dim)
+    data = rng.random((n, dim), dtype=np.float32)
+    ds = ctx.dataset_from(data)
+    for k in (1, 10, 100, 1024):
+        q = rng.random(dim, dtype=np.float32)
+        for flags in (SQRT, SEQ, 0, SEQ | SQRT):
+            check_topk(ds, data, q, k, flags)
+    ds.drop()
+
+
+def test_heavy_ties_follow_the_reference_heap(ctx):
+    # quantised coordinates -> thousands of bit-equal distances; order must equal the BinaryHeap replay
+    rng = np.random.default_rng(99)
+    for n, dim, levels in [(20_000, 4, 3), (5000, 8, 2), (70_000, 2, 5)]:
+        data = rng.integers(0, levels, (n, dim)).astype(np.float32)
+        ds = ctx.dataset_from(data)
+        q = np.zeros(dim, np.float32)
+        for k in (1, 7, 100, 1000):
+            check_topk(ds, data, q, k, SQRT)
+            check_topk(ds, data, q, k, SEQ)
+        ds.drop()
+
+
+def test_adversarial_descending_order(ctx):
+    # every row improves on all earlier ones: every row enters the reference heap -> entrant buffer regrow path
+    n, dim = 200_000, 4
+    data = np.zeros((n, dim), np.float32)
+    data[:, 0] = np.linspace(1000, 1, n, dtype=np.float32)
+    ds = ctx.dataset_from(data)
+    q = np.zeros(dim, np.float32)
+    check_topk(ds, data, q, 10, SQRT)
+    assert ctx.last_timing()["entrants"] == n
+    check_topk(ds, data, q, 100, SEQ)
+    ds.drop()
+
+
+def test_non_finite_distances(ctx):
+    rng = np.random.default_rng(5)
+    data = rng.random((1000, 8), dtype=np.float32)
+    data[500:, 3] = np.inf            # distance +inf: only admitted while the heap is not full (search.rs:119)
+    ds = ctx.dataset_from(data)
+    q = rng.random(8, dtype=np.float32)
+    for k in (10, 600):
+        check_topk(ds, data, q, k, SQRT)
+    ds.drop()
+
+
+def test_gather_matches_oracle(ctx):
+    rng = np.random.default_rng(11)
+    data = rng.random((20_000, 96), dtype=np.float32)
+    ds = ctx.dataset_from(data)
+    q = rng.random(96, dtype=np.float32)
+    for m in (1, 33, 5000, 20_000):
+        ids = rng.permutation(20_000)[:m].astype(np.uint32)
+        for k in (1, 10, 100):
+            check_topk(ds, data, q, k, SQRT, ids)
+            check_topk(ds, data, q, k, SEQ, ids)
+    ids = rng.integers(0, 20_000, 3000).astype(np.uint32)     # duplicates allowed
+    check_topk(ds, data, q, 50, SQRT, ids)
+    r, d = ds.l2_topk_gather(q, np.zeros(0, np.uint32), 5, SQRT)
+    assert r.size == 0
+    ds.drop()
+
+
+def test_ties_by_position_mode(ctx):
+    rng = np.random.default_rng(12)
+    data = rng.integers(0, 3, (10_000, 4)).astype(np.float32)
+    ds = ctx.dataset_from(data)
+    q = np.zeros(4, np.float32)
+    r, d = ds.l2_topk(q, 100, BYPOS)
+    dist = O.distances(data, q, 0)
+    order = np.lexsort((np.arange(10_000), dist))[:100]
+    assert r.tolist() == order.tolist()
+    assert bits(d).tolist() == bits(dist[order]).tolist()
+    ds.drop()
+
+
+def test_synthetic_fill_matches_oracle_stream(ctx):
+    ds = ctx.dataset(48, 5000)
+    ds.fill_synthetic(5000, 1234)
+    got = ds.read(0, 5000)
+    assert np.array_equal(got, O.synth(5000, 48, 1234))
+    assert np.array_equal(ds.read(1234, 10), O.synth(10, 48, 1234, first_row=1234))
+    ds.drop()
+
+
+# ---- streaming (VectorTopKExec) ----------------------------------------------------------------------
+def test_stream_matches_oracle(ctx):
+    rng = np.random.default_rng(21)
+    dim = 64
+    batches = [rng.random((m, dim), dtype=np.float32) for m in (100, 8192, 1, 33, 8192, 5000)]
+    allrows = np.vstack(batches)
+    q = rng.random(dim, dtype=np.float32)
+    for k, flags in [(10, SEQ), (100, SEQ), (5, SQRT), (1000, SEQ)]:
+        st = ctx.topk_stream(q, k, flags)
+        for b in batches:
+            st.push(b)
+        r, d = st.finish()
+        er, ed = O.topk_rerank(q, allrows, None, k, 1 if flags & SEQ else 0, bool(flags & SQRT))
+        assert r.tolist() == er.tolist() and bits(d).tolist() == bits(ed).tolist()
+    # ties across batches + f64 batches narrowed to f32 first (exec.rs:542)
+    tb = [rng.integers(0, 3, (m, 4)).astype(np.float64) for m in (3000, 3000, 10)]
+    st = ctx.topk_stream(np.zeros(4, np.float32), 50, SEQ)
+    for b in tb:
+        st.push(b)
+    r, d = st.finish()
+    er, ed = O.topk_rerank(np.zeros(4, np.float32), np.vstack(tb).astype(np.float32), None, 50, 1, False)
+    assert r.tolist() == er.tolist() and bits(d).tolist() == bits(ed).tolist()
+    st = ctx.topk_stream(q, 3, SEQ)          # nothing pushed -> empty result (exec.rs:553-555)
+    r, d = st.finish()
+    assert r.size == 0
+
+
+# ---- k-means pieces ------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n,dim,c", [(1, 4, 1), (100, 3, 5), (1000, 8, 64), (777, 130, 100), (3000, 768, 256),
+                                     (500, 7, 3), (2048, 64, 1024)])
+def test_kmeans_assign_matches_oracle(ctx, n, dim, c):
+    rng = np.random.default_rng(n + dim + c)
+    data = rng.random((n, dim), dtype=np.float32)
+    cent = data[rng.integers(0, n, c)].copy()        # duplicates likely -> first-min tie rule exercised
+    got, sizes = ctx.kmeans_assign(data, cent, want_sizes=True)
+    exp = O.assign(data, cent, workers=8)
+    assert np.array_equal(got, exp)
+    assert np.array_equal(sizes, np.bincount(exp, minlength=c).astype(np.uint64))
+    ds = ctx.dataset_from(data)                      # resident-dataset form
+    assert np.array_equal(ctx.kmeans_assign(ds, cent), exp)
+    ds.drop()
+
+
+def test_kmeans_assign_ties_and_nan(ctx):
+    cent = np.array([[1, 1, 0, 0], [0, 0, 0, 0], [0, 0, 0, 0], [5, 5, 0, 0]], np.float32)
+    data = np.array([[0, 0, 0, 0], [np.nan, 0, 0, 0], [np.inf, 0, 0, 0], [4, 4, 0, 0], [1, 1, 0, 0]], np.float32)
+    got = ctx.kmeans_assign(data, cent)
+    assert got.tolist() == [1, 0, 0, 3, 0] == O.assign(data, cent).tolist()
+
+
+def test_min_dist_update_matches_oracle(ctx):
+    rng = np.random.default_rng(31)
+    data = rng.random((5000, 100), dtype=np.float32)
+    sel = rng.permutation(5000)[:1777].astype(np.uint64)
+    md = ctx.min_dist_update(data, sel, data[3])
+    emd = O.min_dist_init(data, sel, data[3])
+    assert bits(md).tolist() == bits(emd).tolist()
+    for c in (10, 20, 30):
+        ctx.min_dist_update(data, sel, data[c], md)
+        O.min_dist_update(data, sel, data[c], emd, workers=4)
+        assert bits(md).tolist() == bits(emd).tolist()
+    ds = ctx.dataset_from(data)                      # resident form, no selection
+    md2 = ctx.min_dist_update(ds, None, data[3])
+    assert bits(md2).tolist() == bits(O.min_dist_init(data, None, data[3])).tolist()
+    ds.drop()
+
+
+def test_centroid_rank_matches_oracle(ctx):
+    rng = np.random.default_rng(41)
+    cent = rng.random((300, 72), dtype=np.float32)
+    cent[50] = cent[10]
+    cent[200] = cent[10]                              # exact ties -> stable order by index
+    qs = rng.random((5, 72), dtype=np.float32)
+    for nprobe in (1, 16, 300, 1000):
+        got = ctx.centroid_rank(cent, qs, nprobe)
+        for i in range(5):
+            assert got[i].tolist() == O.find_closest_centroids(qs[i], cent, nprobe).tolist()
+    assert ctx.centroid_rank(cent, cent[10], 3)[0].tolist() == [10, 50, 200]
+
+
+def test_ivf_search_pipeline_matches_oracle(ctx, vldb):
+    # C1 through the IVF path: rank centroids -> candidate rows in rank order -> gathered re-rank
+    n, dim = vldb.shape
+    c = O.build_sizes(n)[0]
+    rng = np.random.default_rng(0)
+    cent = vldb[rng.choice(n, c, replace=False)].copy()
+    assign = ctx.kmeans_assign(vldb, cent)
+    assert np.array_equal(assign, O.assign(vldb, cent))
+    offsets, ids = O.inverted_lists(assign, c)
+    ds = ctx.dataset_from(vldb)
+    for nprobe in (1, 5, 32):
+        for qrow in (0, 1, 100, 333):
+            q = vldb[qrow]
+            cl = ctx.centroid_rank(cent, q, nprobe)[0]
+            cand = np.concatenate([ids[int(offsets[j]):int(offsets[j + 1])] for j in cl]).astype(np.uint32)
+            assert cand.tolist() == O.candidate_rows(q, cent, offsets, ids, nprobe).tolist()
+            check_topk(ds, vldb, q, 10, SQRT, cand)
+    ds.drop()
+
+
+# ---- error behaviour ---------------------------------------------------------------------------------
+def test_errors(ctx, P):
+    ds = ctx.dataset_from(np.zeros((10, 4), np.float32))
+    with pytest.raises(P.PqvError, match="k must be > 0"):
+        ds.l2_topk(np.zeros(4, np.float32), 0)
+    with pytest.raises(P.PqvError, match="Query dimension mismatch: expected 4, got 5"):
+        ds.l2_topk(np.zeros(5, np.float32), 1)
+    with pytest.raises(P.PqvError) as ei:
+        ds.l2_topk(np.zeros(4, np.float32), 5000)
+    assert ei.value.code == 6
+    with pytest.raises(P.PqvError, match="out of range"):
+        ds.l2_topk_gather(np.zeros(4, np.float32), np.array([10], np.uint32), 1)
+    with pytest.raises(P.PqvError, match="nprobe must be > 0"):
+        ctx.centroid_rank(np.zeros((3, 4), np.float32), np.zeros(4, np.float32), 0)
+    ds.drop()
+    with pytest.raises(P.PqvError) as ei:
+        ds2 = P.Dataset(ctx, 12345, 4)
+        ds2.l2_topk(np.zeros(4, np.float32), 1)
+    assert ei.value.code == 5
+    empty = ctx.dataset(4, 0)
+    r, d = empty.l2_topk(np.zeros(4, np.float32), 3)
+    assert r.size == 0
+    empty.drop()
+
+
+# ---- BASELINE sizes: size-independent properties ---------------------------------------------------------
+def test_c2_scale_properties(ctx):
+    """1M x 768 vs the full oracle, then 10M x 768 (config C2) through properties the oracle can check from a
+    sample: returned distances are bit-exact for the returned rows, ascending, and no sampled row beats the k-th."""
+    dim, seed, k = 768, 1234, 100
+    q = O.synth(1, dim, 7)[0]
+    n1 = 1_000_000
+    ds = ctx.dataset(dim, n1)
+    ds.fill_synthetic(n1, seed)
+    r, d = ds.l2_topk(q, k, SQRT)
+    host = O.synth(n1, dim, seed)
+    er, ed = O.scan_topk_mt(host, q, k, 0, workers=1)
+    assert r.tolist() == er.tolist()
+    assert bits(d).tolist() == bits(np.sqrt(ed)).tolist()
+    del host
+    ds.drop()
+
+    n2 = 10_000_000
+    ds = ctx.dataset(dim, n2)
+    ds.fill_synthetic(n2, seed)
+    r, d = ds.l2_topk(q, k, 0)
+    assert r.size == k and np.all(np.diff(d) >= 0) and len(set(r.tolist())) == k
+    for i, row in enumerate(r.tolist()):
+        v = O.synth(1, dim, seed, first_row=row)[0]
+        assert O.squared_l2_unroll4(q, v).view(np.uint32) == d[i].view(np.uint32)
+    rng = np.random.default_rng(3)
+    kth = d[-1]
+    rset = set(r.tolist())
+    for start in rng.integers(0, n2 - 20_000, 8):
+        blk = O.synth(20_000, dim, seed, first_row=int(start))
+        dd = O.distances(blk, q, 0)
+        better = np.nonzero(dd < kth)[0]
+        assert all(int(start + b) in rset for b in better)
+    # the block that holds the winner must reproduce it
+    blk0 = int(r[0]) - int(r[0]) % 1000
+    dd = O.distances(O.synth(1000, dim, seed, first_row=blk0), q, 0)
+    assert int(np.argmin(dd)) + blk0 == int(r[0])
+    ds.drop()
