@@ -73,8 +73,10 @@ PQV_API int pqv_dataset_append(pqv_ctx *ctx, uint64_t handle, const float *value
 PQV_API int pqv_dataset_rows(pqv_ctx *ctx, uint64_t handle, uint64_t *out_rows, uint32_t *out_dim);
 PQV_API int pqv_dataset_drop(pqv_ctx *ctx, uint64_t handle);
 /* bench/test helper: fill rows [0, n_rows) on the device with the counter-based uniform[0,1)
- * generator (distribution of benches/bench_util.rs:29-41; stream documented in DESIGN.md). */
-PQV_API int pqv_dataset_fill_synthetic(pqv_ctx *ctx, uint64_t handle, uint64_t n_rows, uint64_t seed);
+ * generator (distribution of benches/bench_util.rs:29-41; stream documented in DESIGN.md); local row r
+ * gets row (stream_first_row + r) of the seed's stream, so ranks can hold slices of one global table. */
+PQV_API int pqv_dataset_fill_synthetic(pqv_ctx *ctx, uint64_t handle, uint64_t n_rows, uint64_t seed,
+                                       uint64_t stream_first_row);
 /* read rows back (tests, and fetching the k winners) */
 PQV_API int pqv_dataset_read(pqv_ctx *ctx, uint64_t handle, uint64_t first_row, uint64_t n_rows, float *out);
 
@@ -121,6 +123,20 @@ PQV_API int pqv_min_dist_update(pqv_ctx *ctx, uint64_t handle, const float *rows
 PQV_API int pqv_centroid_rank(pqv_ctx *ctx, const float *centroids, uint32_t n_clusters, uint32_t dim,
                       const float *queries, uint32_t n_queries, uint32_t nprobe, uint32_t *out_cluster_ids,
                       uint32_t *out_nprobe_eff);
+
+
+/* ---- one process per GPU -----------------------------------------------------
+ * Each rank owns a contiguous slice of the rows.  pqv_l2_topk_candidates scans the rank's resident
+ * slice and returns the heap-entrant candidate keys (bits(squared distance) << 32 | global position,
+ * global position = pos_base + local row): a superset of every row the reference's BinaryHeap
+ * (src/ivf/search.rs:115-127) would admit while walking this slice.  The ranks exchange these few KB
+ * with ONE all-gather and each calls pqv_replay_candidates on the union, which replays the reference
+ * loop in global position order -> the same bit-exact result on every rank.
+ * If more than `cap` keys exist the call returns PQV_ELIMIT with *out_count = the number needed. */
+PQV_API int pqv_l2_topk_candidates(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags,
+                                   uint32_t pos_base, uint64_t *out_keys, uint64_t cap, uint64_t *out_count);
+PQV_API int pqv_replay_candidates(const uint64_t *keys, uint64_t n_keys, const uint32_t *row_ids, uint32_t k,
+                                  uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count);
 
 /* ---- measurement hooks (bench.py / ncu) ------------------------------------------------------- */
 typedef struct {

@@ -35,7 +35,7 @@ SIGNATURES = {
     "pqv_dataset_append": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint64]),
     "pqv_dataset_rows": (C.c_int, [ctxp, C.c_uint64, u64p, u32p]),
     "pqv_dataset_drop": (C.c_int, [ctxp, C.c_uint64]),
-    "pqv_dataset_fill_synthetic": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, C.c_uint64]),
+    "pqv_dataset_fill_synthetic": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "pqv_dataset_read": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, C.c_uint64, f32p]),
     "pqv_l2_topk": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),
     "pqv_l2_topk_gather": (C.c_int, [ctxp, C.c_uint64, f32p, u32p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p,
@@ -47,6 +47,9 @@ SIGNATURES = {
     "pqv_kmeans_assign": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint64, C.c_uint32, f32p, C.c_uint32, u32p, u64p]),
     "pqv_min_dist_update": (C.c_int, [ctxp, C.c_uint64, f32p, u64p, C.c_uint64, C.c_uint32, f32p, C.c_int, f32p]),
     "pqv_centroid_rank": (C.c_int, [ctxp, f32p, C.c_uint32, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u32p, u32p]),
+    "pqv_l2_topk_candidates": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_uint64,
+                                         u64p]),
+    "pqv_replay_candidates": (C.c_int, [u64p, C.c_uint64, u32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),
     "pqv_last_timing": (C.c_int, [ctxp, C.POINTER(PqvTiming)]),
     "pqv_bench_scan": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, f64p]),
 }

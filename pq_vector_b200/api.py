@@ -143,8 +143,8 @@ class Dataset:
             raise PqvError(N.PQV_EINVAL, "Embedding data length must be a multiple of dimension")
         _check(_lib.pqv_dataset_append(self.ctx._h, self.handle, _ptr(rows, C.c_float), rows.shape[0]))
 
-    def fill_synthetic(self, n_rows: int, seed: int):
-        _check(_lib.pqv_dataset_fill_synthetic(self.ctx._h, self.handle, n_rows, seed))
+    def fill_synthetic(self, n_rows: int, seed: int, stream_first_row: int = 0):
+        _check(_lib.pqv_dataset_fill_synthetic(self.ctx._h, self.handle, n_rows, seed, stream_first_row))
 
     @property
     def rows(self) -> int:
@@ -194,11 +194,39 @@ class Dataset:
                                        k, flags, _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), C.byref(cnt)))
         return rows[:cnt.value].copy(), dist[:cnt.value].copy()
 
+    def l2_topk_candidates(self, query, k: int, flags: int = N.PQV_SQRT, pos_base: int = 0, cap: int = 4096):
+        """Heap-entrant candidate keys of this (rank-local) slice; see pqv_l2_topk_candidates."""
+        q = _f32(query)
+        if q.size != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.size}")
+        while True:
+            keys = np.empty(cap, dtype=np.uint64)
+            cnt = C.c_uint64()
+            rc = _lib.pqv_l2_topk_candidates(self.ctx._h, self.handle, _ptr(q, C.c_float), k, flags, pos_base,
+                                             _ptr(keys, C.c_uint64), cap, C.byref(cnt))
+            if rc == N.PQV_ELIMIT and cnt.value > cap:
+                cap = int(cnt.value)
+                continue
+            _check(rc)
+            return keys[:cnt.value]
+
     def bench_scan(self, query, k: int, flags: int, iters: int) -> float:
         q = _f32(query)
         ms = C.c_double()
         _check(_lib.pqv_bench_scan(self.ctx._h, self.handle, _ptr(q, C.c_float), k, flags, iters, C.byref(ms)))
         return ms.value
+
+
+def replay_candidates(keys, k: int, flags: int = N.PQV_SQRT, row_ids=None):
+    """Replay the reference's bounded BinaryHeap over candidate keys (union over ranks)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    ids = None if row_ids is None else np.ascontiguousarray(row_ids, dtype=np.uint32)
+    rows = np.zeros(max(k, 1), dtype=np.uint32)
+    dist = np.zeros(max(k, 1), dtype=np.float32)
+    cnt = C.c_uint32()
+    _check(_lib.pqv_replay_candidates(_ptr(keys, C.c_uint64), keys.size, _ptr(ids, C.c_uint32), k, flags,
+                                      _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), C.byref(cnt)))
+    return rows[:cnt.value].copy(), dist[:cnt.value].copy()
 
 
 class TopkStream:

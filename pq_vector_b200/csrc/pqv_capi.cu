@@ -419,7 +419,8 @@ size_t emit_by_position(std::vector<u64> &keys, const uint32_t *row_ids, uint32_
 
 // One query over a resident dataset (all shards), brute force or gathered.  Host inputs/outputs.
 int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_ids, u64 n_ids, uint32_t k,
-             uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count) {
+             uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
+             std::vector<u64> *entrants_out = nullptr, uint32_t pos_offset = 0) {
     const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
     const bool gather = row_ids != nullptr;
     std::vector<u64> entrants;
@@ -463,7 +464,8 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
         CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
         ScanGeom g;
         PQV_TRY(enqueue_scan(ctx, D, sh.d_data, d_ids, n, ds.dim, D.d_query.p, k, order,
-                             gather ? 0u : (uint32_t)sh.first_row, nullptr, D.final_topk.p, D.ent_out.p, cap, si == 0, &g));
+                             gather ? 0u : (uint32_t)sh.first_row + pos_offset, nullptr, D.final_topk.p, D.ent_out.p, cap,
+                             si == 0, &g));
         launched.push_back({&D, g, cap, n});
     }
     // collect
@@ -506,6 +508,12 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
         tm.grid = launched[0].g.grid;
     }
     size_t cnt;
+    if (entrants_out) {
+        tm.entrants = (uint32_t)entrants.size();
+        entrants_out->swap(entrants);
+        ctx->last = tm;
+        return PQV_OK;
+    }
     if (flags & PQV_TIES_BY_POSITION) {
         cnt = emit_by_position(finals, row_ids, k, flags, out_rows, out_dist);
     } else {
@@ -726,7 +734,7 @@ int pqv_dataset_drop(pqv_ctx *ctx, uint64_t handle) {
     return PQV_OK;
 }
 
-int pqv_dataset_fill_synthetic(pqv_ctx *ctx, uint64_t handle, uint64_t n_rows, uint64_t seed) {
+int pqv_dataset_fill_synthetic(pqv_ctx *ctx, uint64_t handle, uint64_t n_rows, uint64_t seed, uint64_t stream_first_row) {
     if (!ctx) return fail(PQV_EINVAL, "null ctx");
     std::lock_guard<std::mutex> lk(ctx->mu);
     Dataset *ds = find_dataset(ctx, handle);
@@ -744,7 +752,7 @@ int pqv_dataset_fill_synthetic(pqv_ctx *ctx, uint64_t handle, uint64_t n_rows, u
         if (!take) continue;
         DeviceState &D = ctx->devs[sh.di];
         DevGuard guard(D.dev);
-        pqv::synth_fill_kernel<<<D.sm_count * 8, 256, 0, D.stream>>>(sh.d_data, sh.first_row * ds->dim, take * ds->dim, seed);
+        pqv::synth_fill_kernel<<<D.sm_count * 8, 256, 0, D.stream>>>(sh.d_data, (stream_first_row + sh.first_row) * ds->dim, take * ds->dim, seed);
         CU_TRY(cudaGetLastError());
     }
     for (auto &sh : ds->shards) {
@@ -804,6 +812,33 @@ int pqv_l2_topk_gather(pqv_ctx *ctx, uint64_t handle, const float *query, const 
     }
     static const uint32_t dummy = 0;
     return topk_one(ctx, *ds, query, row_ids ? row_ids : &dummy, n_ids, k, flags, out_row_idx, out_dist, out_count);
+}
+
+
+int pqv_l2_topk_candidates(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags,
+                           uint32_t pos_base, uint64_t *out_keys, uint64_t cap, uint64_t *out_count) {
+    if (!ctx || !query || !out_count || (cap && !out_keys)) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (flags & PQV_TIES_BY_POSITION) return fail(PQV_EINVAL, "candidates are only defined for the reference tie order");
+    if ((u64)pos_base + ds->n_rows > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "global row ids are u32");
+    std::vector<u64> ent;
+    PQV_TRY(topk_one(ctx, *ds, query, nullptr, 0, k, flags, nullptr, nullptr, nullptr, &ent, pos_base));
+    *out_count = ent.size();
+    if (ent.size() > cap) return fail(PQV_ELIMIT, "%zu candidate keys do not fit the caller's buffer of %llu", ent.size(), (unsigned long long)cap);
+    if (!ent.empty()) memcpy(out_keys, ent.data(), ent.size() * 8);
+    return PQV_OK;
+}
+
+int pqv_replay_candidates(const uint64_t *keys, uint64_t n_keys, const uint32_t *row_ids, uint32_t k, uint32_t flags,
+                          uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
+    if ((n_keys && !keys) || !out_row_idx || !out_dist || !out_count) return fail(PQV_EINVAL, "null argument");
+    if (k == 0) return fail(PQV_EINVAL, "k must be > 0");
+    std::vector<u64> ent(keys, keys + n_keys);
+    *out_count = (uint32_t)replay_reference_heap(ent, row_ids, k, flags, out_row_idx, out_dist);
+    return PQV_OK;
 }
 
 int pqv_last_timing(pqv_ctx *ctx, pqv_timing *out) {

@@ -1,0 +1,48 @@
+"""CPU, world_size 2, gloo: the N>1 host logic (candidate exchange + replay) gives the single-process answer.
+The per-rank 'scan' here is the oracle's distance sweep turned into candidate keys (every row of the slice is
+a trivially valid candidate superset); on the GPU box the same class is driven by Dataset.l2_topk_candidates."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _worker(rank, world, port, n, dim, k, flags, cap, seed, out_dir):
+    sys.path.insert(0, ROOT)
+    import oracle as O
+    from pq_vector_b200.sharded import ShardedTopk
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    data = rng.integers(0, 4, (n, dim)).astype(np.float32) if seed % 2 else rng.random((n, dim), dtype=np.float32)
+    q = np.zeros(dim, np.float32) if seed % 2 else rng.random(dim, dtype=np.float32)
+    per = (n + world - 1) // world
+    lo, hi = rank * per, min(n, (rank + 1) * per)
+
+    def scan(query, k_, flags_, pos_base):
+        d = O.distances(data[lo:hi], query, 1 if flags_ & 1 else 0)
+        return (d.view(np.uint32).astype(np.uint64) << np.uint64(32)) | (np.arange(lo, hi, dtype=np.uint64))
+
+    st = ShardedTopk(scan, lo, "cpu", cap=cap)
+    rows, dd = st.search(q, k, flags)
+    er, ed = O.topk_rerank(q, data, None, k, 1 if flags & 1 else 0, bool(flags & 2))
+    ok = rows.tolist() == er.tolist() and dd.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,dim,k,flags,cap,seed", [(1000, 8, 10, 2, 4096, 2), (3000, 4, 100, 1, 64, 3),
+                                                     (5, 3, 10, 2, 16, 4), (2000, 6, 50, 3, 4096, 5)])
+def test_two_rank_exchange_matches_single_process(tmp_path, n, dim, k, flags, cap, seed):
+    port = 29500 + (os.getpid() + seed) % 2000
+    mp.spawn(_worker, args=(2, port, n, dim, k, flags, cap, seed, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
