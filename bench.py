@@ -312,7 +312,7 @@ def run_ours(args):
             "e2e": {"value": world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_s * 1e3,
                     "path": "pqv_l2_topk_candidates (host query in, host candidate keys out) + all-gather + pqv_replay_candidates"},
-            "gpu_launches": 3 * args.steps,
+            "gpu_launches": 4 * args.steps,
             "clocks": clocks,
             "aggregate_gbs": world * scan_bytes / (step_ms * 1e-3) / 1e9,
             "host_wall_ms_per_step_device_loop": wall_dev * 1e3,

@@ -206,7 +206,7 @@ struct DeviceState {
     cudaStream_t stream = nullptr, copy_stream = nullptr;
     cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
     DevBuf<float> d_query;
-    DevBuf<u64> cta_topk, ent, final_topk, ent_out;
+    DevBuf<u64> cta_topk, ent, final_topk, ent_out, within_prefix, group_total, group_prefix;
     DevBuf<uint32_t> ent_count, gthr, d_row_ids, d_assign;
     DevBuf<float> d_vec, d_tmp_rows, d_centroids, d_dist;
     PinBuf<u64> h_ent_out, h_final;
@@ -355,11 +355,21 @@ int enqueue_scan(pqv_ctx *ctx, DeviceState &D, const float *d_data, const uint32
     if (time_it) CU_TRY(cudaEventRecord(D.ev[0], D.stream));
     PQV_TRY(SCAN_DISPATCH(scan_launch_t, order, g.vec4, d_row_ids != nullptr, p, g.grid, g.smem, D.stream));
     if (time_it) CU_TRY(cudaEventRecord(D.ev[1], D.stream));
-    const uint32_t mt = std::min<uint32_t>(g.kcap, 1024);
-    pqv::topk_prefix_merge_kernel<<<1, mt, (size_t)2 * g.kcap * 8, D.stream>>>(D.cta_topk.p, g.grid, k, g.kcap, d_carry,
-                                                                              D.gthr.p, final_out);
+    // two-level exclusive "top-k scan" over the per-CTA lists, then per-CTA threshold + entrant filter
+    const uint32_t n_groups = (g.grid + pqv::MERGE_GROUP - 1) / pqv::MERGE_GROUP;
+    PQV_TRY(D.within_prefix.ensure((size_t)g.grid * g.kcap));
+    PQV_TRY(D.group_total.ensure((size_t)n_groups * g.kcap));
+    PQV_TRY(D.group_prefix.ensure((size_t)n_groups * g.kcap));
+    const size_t msmem = (size_t)2 * g.kcap * 8;
+    pqv::topk_seq_merge_kernel<<<n_groups, g.kcap, msmem, D.stream>>>(D.cta_topk.p, g.grid, pqv::MERGE_GROUP, k, g.kcap,
+                                                                      nullptr, D.within_prefix.p, D.group_total.p);
     CU_TRY(cudaGetLastError());
-    pqv::entrant_filter_kernel<<<g.grid, 256, 0, D.stream>>>(D.ent.p, D.ent_count.p, D.gthr.p, n, ent_out, ent_out_cap);
+    pqv::topk_seq_merge_kernel<<<1, g.kcap, msmem, D.stream>>>(D.group_total.p, n_groups, n_groups, k, g.kcap, d_carry,
+                                                               D.group_prefix.p, final_out);
+    CU_TRY(cudaGetLastError());
+    pqv::entrant_filter_kernel<<<g.grid, 256, msmem, D.stream>>>(D.ent.p, D.ent_count.p, D.group_prefix.p,
+                                                                 D.within_prefix.p, k, g.kcap, D.gthr.p, n, ent_out,
+                                                                 ent_out_cap);
     CU_TRY(cudaGetLastError());
     if (time_it) CU_TRY(cudaEventRecord(D.ev[2], D.stream));
     if (geom_out) *geom_out = g;
@@ -487,8 +497,8 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
                 PQV_TRY(D.ent_out.ensure((size_t)need + 1));
                 const uint32_t cap2 = (uint32_t)std::min<size_t>(D.ent_out.cap - 1, 0xFFFFFFF0u);
                 CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
-                pqv::entrant_filter_kernel<<<L.g.grid, 256, 0, D.stream>>>(D.ent.p, D.ent_count.p, D.gthr.p, L.n,
-                                                                           D.ent_out.p, cap2);
+                pqv::entrant_filter_kernel<<<L.g.grid, 256, (size_t)2 * L.g.kcap * 8, D.stream>>>(
+                    D.ent.p, D.ent_count.p, D.group_prefix.p, D.within_prefix.p, k, L.g.kcap, D.gthr.p, L.n, D.ent_out.p, cap2);
                 CU_TRY(cudaGetLastError());
                 PQV_TRY(fetch_entrants(D, D.ent_out.p, cap2, entrants, &overflow));
                 if (overflow) return fail(PQV_ECUDA, "entrant buffer overflow after regrow");
@@ -504,7 +514,7 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
         tm.post_ms = b;
         tm.total_ms = a + b;
         tm.scan_bytes = launched[0].n * (u64)ds.dim * 4;
-        tm.launches = 3 * (uint32_t)launched.size();
+        tm.launches = 4 * (uint32_t)launched.size();
         tm.grid = launched[0].g.grid;
     }
     size_t cnt;
@@ -606,6 +616,9 @@ void pqv_destroy(pqv_ctx *ctx) {
         D.ent.release();
         D.final_topk.release();
         D.ent_out.release();
+        D.within_prefix.release();
+        D.group_total.release();
+        D.group_prefix.release();
         D.ent_count.release();
         D.gthr.release();
         D.d_row_ids.release();
@@ -898,7 +911,7 @@ int pqv_bench_scan(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k
     tm.post_ms = post / iters;
     tm.total_ms = whole / iters;
     tm.scan_bytes = sh.n_rows * (u64)ds->dim * 4;
-    tm.launches = 3;
+    tm.launches = 4;
     tm.grid = g.grid;
     ctx->last = tm;
     *out_ms_per_scan = tm.scan_ms;

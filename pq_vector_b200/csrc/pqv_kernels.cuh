@@ -329,64 +329,114 @@ __global__ void __launch_bounds__(WARPS * 32, 2) l2_scan_topk_kernel(const ScanP
 }
 
 // ------------------------------------------------------------------------------------------------
-// topk_prefix_merge_kernel (1 CTA): walks the per-CTA lists in CTA (= position) order keeping the
-// running exact top-k P.  gthr[b] = distance bits of the k-th smallest key among all CTAs < b (the
-// reference heap's root when the scan reaches CTA b's first row; P starts from `carry`).  The final
-// P (ascending by (distance, position)) is written to final_topk[0..kcap).
-// `carry` (may be null): kcap keys of an earlier launch's final_topk to start P from.
+// topk_seq_merge_kernel: CTA j walks the sorted lists [j*lists_per_cta, min(n_lists,(j+1)*lists_per_cta))
+// in order, keeping the running exact top-k P (ascending by (distance, position)); blockDim.x == kcap.
+//   excl_prefix_out[b] (kcap keys) = P BEFORE list b is merged (this CTA's exclusive prefix)
+//   total_out[j]       (kcap keys) = P after the CTA's last list
+// P starts from `carry` (kcap keys, may be null = empty).  The next lists are prefetched into registers
+// (depth PF) so the sequential chain is not exposed to global-memory latency.
+// Used twice (two-level scan): level 1 with lists_per_cta = MERGE_GROUP over the scan CTAs' lists
+// (-> W[b], T[j]); level 2 with one CTA over the group totals T (-> GP[j], final top-k).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024) topk_prefix_merge_kernel(const u64 *__restrict__ cta_topk,
-                                                                 const uint32_t n_lists, const uint32_t k,
-                                                                 const uint32_t kcap,
-                                                                 const u64 *__restrict__ carry,
-                                                                 uint32_t *__restrict__ gthr,
-                                                                 u64 *__restrict__ final_topk) {
+constexpr uint32_t MERGE_GROUP = 16;
+
+__global__ void __launch_bounds__(1024) topk_seq_merge_kernel(const u64 *__restrict__ lists, const uint32_t n_lists,
+                                                              const uint32_t lists_per_cta, const uint32_t k,
+                                                              const uint32_t kcap, const u64 *__restrict__ carry,
+                                                              u64 *__restrict__ excl_prefix_out,
+                                                              u64 *__restrict__ total_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *s = reinterpret_cast<u64 *>(smem_raw);  // 2*kcap keys: [P ascending | next list descending]
-    const uint32_t tid = threadIdx.x, nt = blockDim.x;
-    for (uint32_t i = tid; i < kcap; i += nt) s[i] = carry ? carry[i] : KEY_MAX;
+    u64 *s = reinterpret_cast<u64 *>(smem_raw);  // 2*kcap keys: [P ascending | incoming list descending]
+    constexpr int PF = 4;
+    const uint32_t tid = threadIdx.x;  // blockDim.x == kcap
+    const uint32_t b0 = blockIdx.x * lists_per_cta;
+    const uint32_t b1 = min(n_lists, b0 + lists_per_cta);
+    s[tid] = carry ? carry[tid] : KEY_MAX;
+    u64 nxt[PF];
+#pragma unroll
+    for (int i = 0; i < PF; ++i) nxt[i] = (b0 + i < b1) ? lists[(u64)(b0 + i) * kcap + (kcap - 1 - tid)] : KEY_MAX;
     __syncthreads();
-    for (uint32_t b = 0; b < n_lists; ++b) {
-        if (tid == 0) {
-            const u64 kth = s[k - 1];
-            const uint32_t t = (kth == KEY_MAX) ? 0xFFFFFFFFu : (uint32_t)(kth >> 32);
-            gthr[b] = t;
-        }
-        const u64 *L = cta_topk + (u64)b * kcap;
-        for (uint32_t i = tid; i < kcap; i += nt) s[kcap + i] = L[kcap - 1 - i];
-        __syncthreads();
-        // bitonic merge of the 2*kcap bitonic sequence, ascending
-        for (uint32_t stride = kcap; stride > 0; stride >>= 1) {
-            for (uint32_t t = tid; t < kcap; t += nt) {
-                const uint32_t i = ((t & ~(stride - 1)) << 1) | (t & (stride - 1));
-                const uint32_t j = i + stride;
-                const u64 a = s[i], c = s[j];
+    for (uint32_t b = b0; b < b1; b += PF) {
+#pragma unroll
+        for (int i = 0; i < PF; ++i) {
+            if (b + i >= b1) break;  // uniform
+            if (excl_prefix_out) excl_prefix_out[(u64)(b + i) * kcap + tid] = s[tid];
+            s[kcap + tid] = nxt[i];
+            const uint32_t bn = b + i + PF;
+            nxt[i] = (bn < b1) ? lists[(u64)bn * kcap + (kcap - 1 - tid)] : KEY_MAX;
+            __syncthreads();
+            // bitonic merge of the 2*kcap bitonic sequence, ascending; one compare-exchange per thread per step
+            for (uint32_t stride = kcap; stride > 0; stride >>= 1) {
+                const uint32_t lo = ((tid & ~(stride - 1)) << 1) | (tid & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const u64 a = s[lo], c = s[hi];
                 if (a > c) {
-                    s[i] = c;
-                    s[j] = a;
+                    s[lo] = c;
+                    s[hi] = a;
                 }
+                __syncthreads();
             }
+            if (tid >= k) s[tid] = KEY_MAX;
             __syncthreads();
         }
-        for (uint32_t i = k + tid; i < kcap; i += nt) s[i] = KEY_MAX;
-        __syncthreads();
     }
-    for (uint32_t i = tid; i < kcap; i += nt) final_topk[i] = s[i];
+    total_out[(u64)blockIdx.x * kcap + tid] = s[tid];
 }
 
 // ------------------------------------------------------------------------------------------------
-// entrant_filter_kernel: CTA b keeps the entrant keys of scan-CTA b whose distance is below gthr[b]
-// and appends them (order irrelevant, the host sorts by position) to out[1..]; out[0] = count.
+// entrant_filter_kernel: CTA b first derives gthr[b] = distance bits of the k-th smallest key among all
+// scan CTAs < b (and the carry) = k-th smallest of GP[b / MERGE_GROUP] U W[b] (two sorted lists, merge
+// path by rank), i.e. the reference heap's root when the scan reaches CTA b's first row.  It then keeps
+// the entrant keys of scan-CTA b whose distance is below it and appends them (order irrelevant, the host
+// sorts by position) to out[1..]; out[0] = running count.
 // ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t lower_bound_keys(const u64 *a, const uint32_t n, const u64 x) {
+    uint32_t lo = 0, hi = n;  // first index with a[idx] >= x
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] < x) lo = mid + 1;
+        else hi = mid;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(256) entrant_filter_kernel(const u64 *__restrict__ ent,
                                                              const uint32_t *__restrict__ ent_count,
-                                                             const uint32_t *__restrict__ gthr, const u64 n,
-                                                             u64 *__restrict__ out, const uint32_t out_cap) {
+                                                             const u64 *__restrict__ group_prefix,
+                                                             const u64 *__restrict__ within_prefix, const uint32_t k,
+                                                             const uint32_t kcap, uint32_t *__restrict__ gthr,
+                                                             const u64 n, u64 *__restrict__ out,
+                                                             const uint32_t out_cap) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *sA = reinterpret_cast<u64 *>(smem_raw);  // GP list
+    u64 *sB = sA + kcap;                           // W list
+    __shared__ uint32_t s_thr;
     const uint32_t b = blockIdx.x, G = gridDim.x;
+    const u64 *A = group_prefix + (u64)(b / MERGE_GROUP) * kcap;
+    const u64 *B = within_prefix + (u64)b * kcap;
+    for (uint32_t i = threadIdx.x; i < kcap; i += blockDim.x) {
+        sA[i] = A[i];
+        sB[i] = B[i];
+    }
+    if (threadIdx.x == 0) s_thr = 0xFFFFFFFFu;
+    __syncthreads();
+    // keys are unique (position field), so exactly one real key has merged rank k-1 when >= k keys exist
+    for (uint32_t i = threadIdx.x; i < 2 * kcap; i += blockDim.x) {
+        const bool inA = i < kcap;
+        const uint32_t idx = inA ? i : i - kcap;
+        const u64 key = inA ? sA[idx] : sB[idx];
+        if (key != KEY_MAX) {
+            const uint32_t rank = idx + lower_bound_keys(inA ? sB : sA, kcap, key);
+            if (rank == k - 1) s_thr = (uint32_t)(key >> 32);
+        }
+    }
+    __syncthreads();
+    const uint32_t thr = s_thr;
+    if (threadIdx.x == 0) gthr[b] = thr;
+
     const u64 NG = (n + 31) >> 5;
     const u64 base = (NG * b / G) * 32;
     const uint32_t cnt = ent_count[b];
-    const uint32_t thr = gthr[b];
     const uint32_t lane = threadIdx.x & 31;
     for (uint32_t i0 = 0; i0 < cnt; i0 += blockDim.x) {
         const uint32_t i = i0 + threadIdx.x;

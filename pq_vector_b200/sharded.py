@@ -55,6 +55,9 @@ class ShardedTopk:
 
     def search(self, query, k: int, flags: int):
         keys = np.ascontiguousarray(self.scan_fn(query, k, flags, self.pos_base), dtype=np.uint64)
+        if self.world == 1:  # nothing to exchange
+            self.last_gather_bytes = 0
+            return replay_candidates(keys, k, flags)
         out, ok = self._exchange(keys, self.cap)
         if not ok:  # some rank had more candidates than the default payload: one more round, sized to fit
             out, ok = self._exchange(keys, int(out.max()))
