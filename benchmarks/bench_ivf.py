@@ -1,0 +1,62 @@
+#!/usr/bin/env python
+"""Config C3 of BASELINE.json: 10M x 768 synthetic f32, IVF build with n_clusters=1024 (k-means assign kernel)
++ nprobe=32 search, 1 B200.  Prints one JSON object (build seconds, final-assign GB/s and f32 op rate, search
+QPS, recall@k against the brute-force scan).  Secondary bench; bench.py carries the headline metric."""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import pq_vector_b200 as P  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--rows", type=int, default=10_000_000)
+ap.add_argument("--dim", type=int, default=768)
+ap.add_argument("--clusters", type=int, default=1024)
+ap.add_argument("--max-iters", type=int, default=20)
+ap.add_argument("--nprobe", type=int, default=32)
+ap.add_argument("--k", type=int, default=100)
+ap.add_argument("--queries", type=int, default=50)
+a = ap.parse_args()
+
+ctx = P.Context([0])
+ds = ctx.dataset(a.dim, a.rows)
+ds.fill_synthetic(a.rows, 1234)
+qd = ctx.dataset(a.dim, a.queries)
+qd.fill_synthetic(a.queries, 7)
+queries = qd.read(0, a.queries)
+
+t0 = time.perf_counter()
+ix = ctx.ivf_build(ds, n_clusters=a.clusters, max_iters=a.max_iters, seed=42)
+build_s = time.perf_counter() - t0
+st = ix.build_stats()
+fa_s = st["final_assign_ms"] * 1e-3
+out = {
+    "config": f"{a.rows} x {a.dim} f32, IVF C={a.clusters}, max_iters={a.max_iters}, seed=42; search nprobe={a.nprobe} k={a.k}",
+    "build_seconds": build_s, "build_breakdown_ms": st,
+    "final_assign": {"seconds_incl_d2h_and_list_build": fa_s, "rows_gbs": a.rows * a.dim * 4 / fa_s / 1e9,
+                     "f32_ops_per_s": 3.0 * a.rows * a.clusters * a.dim / fa_s,
+                     "note": "3*N*C*dim non-fusable f32 ops (sub, mul, add), exact reference order"},
+}
+# search
+for q in queries[:3]:
+    ix.search(ds, q, a.k, a.nprobe)
+lat, cands, recall = [], [], []
+for q in queries:
+    t0 = time.perf_counter()
+    r, d = ix.search(ds, q, a.k, a.nprobe)
+    lat.append(time.perf_counter() - t0)
+    cands.append(ctx.last_timing()["scan_bytes"] // (a.dim * 4))
+for q in queries[:10]:
+    r, _ = ix.search(ds, q, a.k, a.nprobe)
+    br, _ = ds.l2_topk(q, a.k)
+    recall.append(len(set(r.tolist()) & set(br.tolist())) / max(len(br), 1))
+t = ctx.last_timing()
+out["search"] = {"qps_e2e": 1.0 / float(np.mean(lat)), "ms_per_query_e2e": float(np.mean(lat)) * 1e3,
+                 "mean_candidates": float(np.mean(cands)), "recall_at_k_vs_bruteforce": float(np.mean(recall)),
+                 "gather_gbs_e2e": float(np.mean(cands)) * (a.dim * 4 + 4) / float(np.mean(lat)) / 1e9}
+print(json.dumps(out))

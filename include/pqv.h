@@ -125,6 +125,30 @@ PQV_API int pqv_centroid_rank(pqv_ctx *ctx, const float *centroids, uint32_t n_c
                       uint32_t *out_nprobe_eff);
 
 
+/* ---- IVF index: build / blob / search ------------------------------------------------------------
+ * Host-side mirror of the reference's IVF layer with every distance on the GPU.
+ * pqv_ivf_build      build_ivf_index + k_means, src/ivf/index.rs:152-214, 323-457, over a resident dataset:
+ *                    sizing rules (:161-174, :332), k-means++ (sweeps = pqv_min_dist_update's kernel; the f32
+ *                    partial sums use `sum_workers` chunks, 0 = hardware threads, as :259-265, :356-370),
+ *                    Lloyd (assign kernel + exact-order centroid update :436-453), final assignment of all rows
+ *                    (:189-206).  The RNG stream is not rand's StdRng.
+ * pqv_ivf_to_bytes / pqv_ivf_from_bytes   IvfIndex::to_bytes / from_bytes, src/ivf/index.rs:65-128 (same bytes).
+ * pqv_ivf_candidate_rows  IvfIndex::candidate_rows, src/ivf/index.rs:57-63.
+ * pqv_ivf_search     TopkBuilder::topk, src/ivf/search.rs:83-142, with the index and the table resident in HBM
+ *                    (replaces read_index_from_parquet + read_embeddings_for_rows + the re-rank loop). */
+PQV_API int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint32_t max_iters, uint64_t seed,
+                          uint32_t sum_workers, uint64_t *out_index);
+PQV_API int pqv_ivf_build_stats(pqv_ctx *ctx, uint64_t index, uint32_t *out_lloyd_iters, double *out_ms4);
+PQV_API int pqv_ivf_from_bytes(pqv_ctx *ctx, const uint8_t *bytes, uint64_t len, uint64_t *out_index);
+PQV_API int pqv_ivf_to_bytes(pqv_ctx *ctx, uint64_t index, uint8_t *out, uint64_t cap, uint64_t *out_len);
+PQV_API int pqv_ivf_info(pqv_ctx *ctx, uint64_t index, uint32_t *out_dim, uint32_t *out_clusters, uint64_t *out_ids);
+PQV_API int pqv_ivf_drop(pqv_ctx *ctx, uint64_t index);
+PQV_API int pqv_ivf_candidate_rows(pqv_ctx *ctx, uint64_t index, const float *query, uint32_t nprobe,
+                                   uint32_t *out_rows, uint64_t cap, uint64_t *out_n);
+PQV_API int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k,
+                           uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist,
+                           uint32_t *out_count);
+
 /* ---- one process per GPU -----------------------------------------------------
  * Each rank owns a contiguous slice of the rows.  pqv_l2_topk_candidates scans the rank's resident
  * slice and returns the heap-entrant candidate keys (bits(squared distance) << 32 | global position,

@@ -122,6 +122,22 @@ class Context:
                                       nprobe, _ptr(out, C.c_uint32), C.byref(eff)))
         return out[:, :eff.value]
 
+    # ---- IVF index
+    def ivf_build(self, dataset: "Dataset", n_clusters=None, max_iters: int = 20, seed: int = 42,
+                  sum_workers: int = 0) -> "IvfIndex":
+        """build_ivf_index (src/ivf/index.rs:152-214); defaults as IndexBuilder (src/ivf/parquet.rs:32-40)."""
+        if n_clusters is not None and n_clusters <= 0:
+            raise PqvError(N.PQV_EINVAL, "n_clusters must be > 0")
+        h = C.c_uint64()
+        _check(_lib.pqv_ivf_build(self._h, dataset.handle, n_clusters or 0, max_iters, seed, sum_workers, C.byref(h)))
+        return IvfIndex(self, h.value)
+
+    def ivf_from_bytes(self, blob: bytes) -> "IvfIndex":
+        buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob if blob else b"\0")
+        h = C.c_uint64()
+        _check(_lib.pqv_ivf_from_bytes(self._h, buf, len(blob), C.byref(h)))
+        return IvfIndex(self, h.value)
+
     def topk_stream(self, query, k, flags=N.PQV_SUM_SEQ) -> "TopkStream":
         return TopkStream(self, query, k, flags)
 
@@ -215,6 +231,57 @@ class Dataset:
         ms = C.c_double()
         _check(_lib.pqv_bench_scan(self.ctx._h, self.handle, _ptr(q, C.c_float), k, flags, iters, C.byref(ms)))
         return ms.value
+
+
+class IvfIndex:
+    """IVF index (centroids + inverted lists), host + HBM resident (pqv_ivf_*)."""
+
+    def __init__(self, ctx: Context, handle: int):
+        self.ctx, self.handle = ctx, handle
+        d, c, n = C.c_uint32(), C.c_uint32(), C.c_uint64()
+        _check(_lib.pqv_ivf_info(ctx._h, handle, C.byref(d), C.byref(c), C.byref(n)))
+        self.dim, self.n_clusters, self.n_ids = d.value, c.value, n.value
+
+    def to_bytes(self) -> bytes:
+        need = C.c_uint64()
+        _check(_lib.pqv_ivf_to_bytes(self.ctx._h, self.handle, None, 0, C.byref(need)))
+        buf = (C.c_uint8 * need.value)()
+        _check(_lib.pqv_ivf_to_bytes(self.ctx._h, self.handle, buf, need.value, C.byref(need)))
+        return bytes(buf)
+
+    def build_stats(self) -> dict:
+        it = C.c_uint32()
+        ms = (C.c_double * 4)()
+        _check(_lib.pqv_ivf_build_stats(self.ctx._h, self.handle, C.byref(it), ms))
+        return {"lloyd_iters": it.value, "init_ms": ms[0], "lloyd_ms": ms[1], "final_assign_ms": ms[2],
+                "total_ms": ms[3]}
+
+    def candidate_rows(self, query, nprobe: int) -> np.ndarray:
+        q = _f32(query)
+        if q.size != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.size}")
+        out = np.empty(max(self.n_ids, 1), dtype=np.uint32)
+        n = C.c_uint64()
+        _check(_lib.pqv_ivf_candidate_rows(self.ctx._h, self.handle, _ptr(q, C.c_float), nprobe,
+                                           _ptr(out, C.c_uint32), out.size, C.byref(n)))
+        return out[:n.value].copy()
+
+    def search(self, dataset: "Dataset", query, k: int, nprobe: int, flags: int = N.PQV_SQRT):
+        """TopkBuilder::search (src/ivf/search.rs:76-142) over a resident table."""
+        q = _f32(query)
+        if q.size != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.size}")
+        rows = np.zeros(max(k, 1), dtype=np.uint32)
+        dist = np.zeros(max(k, 1), dtype=np.float32)
+        cnt = C.c_uint32()
+        _check(_lib.pqv_ivf_search(self.ctx._h, dataset.handle, self.handle, _ptr(q, C.c_float), k, nprobe, flags,
+                                   _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), C.byref(cnt)))
+        return rows[:cnt.value].copy(), dist[:cnt.value].copy()
+
+    def drop(self):
+        if self.handle:
+            _check(_lib.pqv_ivf_drop(self.ctx._h, self.handle))
+            self.handle = 0
 
 
 def replay_candidates(keys, k: int, flags: int = N.PQV_SQRT, row_ids=None):

@@ -12,9 +12,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <functional>
 #include <map>
 #include <mutex>
 #include <string>
+#include <thread>
+#include <time.h>
 #include <vector>
 
 #include "pqv_kernels.cuh"
@@ -118,7 +121,14 @@ inline uint32_t key_pos(u64 key) { return (uint32_t)(key & 0xFFFFFFFFull); }
 
 // entrants: keys (bits(d) << 32 | position) in any order; a superset of every candidate the
 // reference heap admits.  Replays the reference loop in position order, then (sqrt), stable sort.
-size_t replay_reference_heap(std::vector<u64> &entrants, const uint32_t *row_ids, uint32_t k, uint32_t flags,
+// maps a candidate position to its row id: identity, a host array (gather API) or a functor (IVF lists)
+struct RowMap {
+    const uint32_t *ids = nullptr;
+    const std::function<uint32_t(uint32_t)> *fn = nullptr;
+    uint32_t operator()(uint32_t pos) const { return fn ? (*fn)(pos) : (ids ? ids[pos] : pos); }
+};
+
+size_t replay_reference_heap(std::vector<u64> &entrants, const RowMap &row_of, uint32_t k, uint32_t flags,
                              uint32_t *out_rows, float *out_dist) {
     std::sort(entrants.begin(), entrants.end(),
               [](u64 a, u64 b) { return key_pos(a) < key_pos(b); });
@@ -127,7 +137,7 @@ size_t replay_reference_heap(std::vector<u64> &entrants, const uint32_t *row_ids
     for (u64 key : entrants) {
         const float d = key_dist(key);
         const uint32_t pos = key_pos(key);
-        HeapItem it{d, row_ids ? row_ids[pos] : pos};
+        HeapItem it{d, row_of(pos)};
         if (h.data.size() < k) {
             h.push(it);
         } else if (d < h.data[0].distance) {
@@ -248,6 +258,7 @@ struct pqv_ctx {
     std::vector<DeviceState> devs;
     std::map<u64, Dataset> datasets;
     std::map<u64, StreamState *> streams;
+    std::map<u64, void *> indexes;  // IvfIndex*, see pqv_ivf_impl.cuh
     u64 next_handle = 1;
     std::mutex mu;
     pqv_timing last{};
@@ -413,14 +424,14 @@ int check_topk_args(uint32_t k, uint32_t dim, uint32_t flags) {
 }
 
 // final (distance, position)-ordered keys -> outputs (PQV_TIES_BY_POSITION mode)
-size_t emit_by_position(std::vector<u64> &keys, const uint32_t *row_ids, uint32_t k, uint32_t flags,
+size_t emit_by_position(std::vector<u64> &keys, const RowMap &row_of, uint32_t k, uint32_t flags,
                         uint32_t *out_rows, float *out_dist) {
     std::sort(keys.begin(), keys.end());
     size_t n = 0;
     for (u64 key : keys) {
         if (key == pqv::KEY_MAX || n >= k) break;
         float d = key_dist(key);
-        out_rows[n] = row_ids ? row_ids[key_pos(key)] : key_pos(key);
+        out_rows[n] = row_of(key_pos(key));
         out_dist[n] = (flags & PQV_SQRT) ? sqrtf(d) : d;
         ++n;
     }
@@ -428,11 +439,17 @@ size_t emit_by_position(std::vector<u64> &keys, const uint32_t *row_ids, uint32_
 }
 
 // One query over a resident dataset (all shards), brute force or gathered.  Host inputs/outputs.
+// row_ids: host candidate list (gather API) or null.  d_cand: candidate list already on the device (IVF path;
+// then row_fn maps positions to row ids on the host).  Neither => brute force over every resident row.
 int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_ids, u64 n_ids, uint32_t k,
              uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
-             std::vector<u64> *entrants_out = nullptr, uint32_t pos_offset = 0) {
+             std::vector<u64> *entrants_out = nullptr, uint32_t pos_offset = 0, const uint32_t *d_cand = nullptr,
+             const std::function<uint32_t(uint32_t)> *row_fn = nullptr) {
     const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
-    const bool gather = row_ids != nullptr;
+    const bool gather = row_ids != nullptr || d_cand != nullptr;
+    RowMap row_of;
+    row_of.ids = row_ids;
+    row_of.fn = row_fn;
     std::vector<u64> entrants;
     std::vector<u64> finals;
     pqv_timing tm{};
@@ -455,7 +472,9 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
             if (ds.shards.size() != 1)
                 return fail(PQV_EINVAL, "pqv_l2_topk_gather needs a single-device dataset (got %zu shards)", ds.shards.size());
             n = n_ids;
-            if (n) {
+            if (n && d_cand) {
+                d_ids = d_cand;
+            } else if (n) {
                 PQV_TRY(D.d_row_ids.ensure(n));
                 CU_TRY(cudaMemcpyAsync(D.d_row_ids.p, row_ids, n * 4, cudaMemcpyHostToDevice, D.stream));
                 d_ids = D.d_row_ids.p;
@@ -525,10 +544,10 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
         return PQV_OK;
     }
     if (flags & PQV_TIES_BY_POSITION) {
-        cnt = emit_by_position(finals, row_ids, k, flags, out_rows, out_dist);
+        cnt = emit_by_position(finals, row_of, k, flags, out_rows, out_dist);
     } else {
         tm.entrants = (uint32_t)entrants.size();
-        cnt = replay_reference_heap(entrants, row_ids, k, flags, out_rows, out_dist);
+        cnt = replay_reference_heap(entrants, row_of, k, flags, out_rows, out_dist);
     }
     *out_count = (uint32_t)cnt;
     ctx->last = tm;
@@ -536,6 +555,8 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
 }
 
 }  // namespace
+
+static void pqv_free_all_indexes(pqv_ctx *ctx);
 
 // ================================================================================================
 // C ABI
@@ -603,6 +624,7 @@ void pqv_destroy(pqv_ctx *ctx) {
         if (s->copy_done) cudaEventDestroy(s->copy_done);
         delete s;
     }
+    pqv_free_all_indexes(ctx);
     for (auto &kv : ctx->datasets)
         for (auto &sh : kv.second.shards) {
             DevGuard guard(ctx->devs[sh.di].dev);
@@ -850,7 +872,9 @@ int pqv_replay_candidates(const uint64_t *keys, uint64_t n_keys, const uint32_t 
     if ((n_keys && !keys) || !out_row_idx || !out_dist || !out_count) return fail(PQV_EINVAL, "null argument");
     if (k == 0) return fail(PQV_EINVAL, "k must be > 0");
     std::vector<u64> ent(keys, keys + n_keys);
-    *out_count = (uint32_t)replay_reference_heap(ent, row_ids, k, flags, out_row_idx, out_dist);
+    RowMap row_of;
+    row_of.ids = row_ids;
+    *out_count = (uint32_t)replay_reference_heap(ent, row_of, k, flags, out_row_idx, out_dist);
     return PQV_OK;
 }
 
@@ -1183,10 +1207,10 @@ int pqv_topk_stream_finish(pqv_ctx *ctx, uint64_t stream, uint32_t *out_row_idx,
         cudaError_t e = cudaMemcpyAsync(keys.data(), s->carry[s->carry_cur].p, (size_t)PQV_MAX_K * 8, cudaMemcpyDeviceToHost, D.stream);
         if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
         if (e != cudaSuccess) rc = fail(PQV_ECUDA, "stream finish copy failed: %s", cudaGetErrorString(e));
-        else cnt = emit_by_position(keys, nullptr, s->k, s->flags, out_row_idx, out_dist);
+        else cnt = emit_by_position(keys, RowMap{}, s->k, s->flags, out_row_idx, out_dist);
     } else {
         rc = stream_drain(D, s);
-        if (!rc) cnt = replay_reference_heap(s->host_entrants, nullptr, s->k, s->flags, out_row_idx, out_dist);
+        if (!rc) cnt = replay_reference_heap(s->host_entrants, RowMap{}, s->k, s->flags, out_row_idx, out_dist);
     }
     cudaStreamSynchronize(D.stream);
     cudaStreamSynchronize(D.copy_stream);
@@ -1208,3 +1232,5 @@ int pqv_topk_stream_finish(pqv_ctx *ctx, uint64_t stream, uint32_t *out_row_idx,
 }
 
 }  // extern "C"
+
+#include "pqv_ivf_impl.cuh"

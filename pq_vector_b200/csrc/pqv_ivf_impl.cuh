@@ -1,0 +1,528 @@
+// pqv_ivf_impl.cuh -- host-side mirror of the reference's IVF layer on top of the kernels (included at the
+// end of pqv_capi.cu; same translation unit so it shares pqv_ctx / DeviceState).
+//
+//   build    : build_ivf_index + k_means                    src/ivf/index.rs:152-214, 323-457
+//   blob     : IvfIndex::to_bytes / from_bytes              src/ivf/index.rs:65-128   (byte-identical format)
+//   search   : TopkBuilder::topk minus the Parquet I/O      src/ivf/search.rs:83-142
+//   candidates: IvfIndex::candidate_rows                    src/ivf/index.rs:57-63
+//
+// Every distance, argmin, centroid mean and top-k comes from the GPU kernels; the host keeps what the
+// reference keeps serial: RNG draws, the f32 running sums of the k-means++ pick (index.rs:356-383, whose
+// chunking depends on the worker count), list bookkeeping.  The RNG stream is NOT rand 0.8.5's
+// ChaCha12 (unverifiable here): the sampled rows differ from a Rust build, every step after the
+// draws is bit-identical given the same draws (tests pin sweeps/assignments/updates against the oracle).
+#pragma once
+
+namespace {
+
+struct SplitMix64 {
+    u64 s;
+    explicit SplitMix64(u64 seed) : s(seed) {}
+    u64 next() {
+        u64 z = (s += 0x9E3779B97F4A7C15ull);
+        z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+        z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+        return z ^ (z >> 31);
+    }
+    u64 below(u64 n) {  // uniform in [0, n), rejection sampling
+        const u64 lim = ~0ull - (~0ull % n);
+        u64 v;
+        do v = next();
+        while (v >= lim);
+        return v % n;
+    }
+    float unit_f32() { return (float)(next() >> 40) * (1.0f / 16777216.0f); }  // [0,1), 24 bits
+};
+
+// `amount` distinct indices from [0, n) in random order (role of rand::seq::index::sample)
+std::vector<uint32_t> sample_indices(SplitMix64 &rng, u64 n, u64 amount) {
+    std::vector<uint32_t> out;
+    out.reserve(amount);
+    if (amount * 2 >= n) {  // partial Fisher-Yates
+        std::vector<uint32_t> all(n);
+        for (u64 i = 0; i < n; ++i) all[i] = (uint32_t)i;
+        for (u64 i = 0; i < amount; ++i) {
+            const u64 j = i + rng.below(n - i);
+            std::swap(all[i], all[j]);
+        }
+        out.assign(all.begin(), all.begin() + amount);
+    } else {  // Floyd's algorithm, then shuffle
+        std::map<uint32_t, bool> seen;
+        for (u64 j = n - amount; j < n; ++j) {
+            const uint32_t t = (uint32_t)rng.below(j + 1);
+            if (seen.count(t)) {
+                seen[(uint32_t)j] = true;
+                out.push_back((uint32_t)j);
+            } else {
+                seen[t] = true;
+                out.push_back(t);
+            }
+        }
+        for (u64 i = amount; i > 1; --i) std::swap(out[i - 1], out[rng.below(i)]);
+    }
+    return out;
+}
+
+struct IvfIndex {
+    uint32_t dim = 0, n_clusters = 0;
+    std::vector<float> centroids;
+    std::vector<u64> offsets;  // n_clusters + 1
+    std::vector<uint32_t> ids;
+    // device mirror (device 0 of the context), created on first search
+    bool resident = false;
+    DevBuf<float> d_centroids, d_cdist;
+    DevBuf<u64> d_offsets, d_probe_prefix;
+    DevBuf<uint32_t> d_ids, d_probe_cluster, d_cand;
+    uint32_t build_iters = 0;   // Lloyd iterations the build ran
+    double build_ms[4] = {0, 0, 0, 0};  // sample+init, lloyd, final assign, total
+};
+
+void csr_from_assign(const uint32_t *assign, u64 n, uint32_t n_clusters, std::vector<u64> &offsets,
+                     std::vector<uint32_t> &ids) {
+    // src/ivf/index.rs:202-206: per-cluster row ids ascending
+    offsets.assign((size_t)n_clusters + 1, 0);
+    for (u64 i = 0; i < n; ++i) offsets[assign[i] + 1]++;
+    for (uint32_t c = 0; c < n_clusters; ++c) offsets[c + 1] += offsets[c];
+    ids.resize(n);
+    std::vector<u64> cur(offsets.begin(), offsets.end() - 1);
+    for (u64 i = 0; i < n; ++i) ids[cur[assign[i]]++] = (uint32_t)i;
+}
+
+int assign_device(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const float *d_centroids, uint32_t C,
+                  uint32_t *d_out) {
+    const uint32_t grid = (uint32_t)((n + pqv::AS_BM - 1) / pqv::AS_BM);
+    const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rows) & 15) == 0) &&
+                      ((reinterpret_cast<uintptr_t>(d_centroids) & 15) == 0);
+    if (vec4) pqv::kmeans_assign_kernel<true><<<grid, 256, 0, D.stream>>>(d_rows, n, dim, d_centroids, C, d_out);
+    else pqv::kmeans_assign_kernel<false><<<grid, 256, 0, D.stream>>>(d_rows, n, dim, d_centroids, C, d_out);
+    CU_TRY(cudaGetLastError());
+    return PQV_OK;
+}
+
+double now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+IvfIndex *find_index(pqv_ctx *ctx, u64 h) {
+    auto it = ctx->indexes.find(h);
+    return it == ctx->indexes.end() ? nullptr : static_cast<IvfIndex *>(it->second);
+}
+
+int index_make_resident(DeviceState &D, IvfIndex &ix) {
+    if (ix.resident) return PQV_OK;
+    PQV_TRY(ix.d_centroids.ensure(ix.centroids.size()));
+    PQV_TRY(ix.d_offsets.ensure(ix.offsets.size()));
+    PQV_TRY(ix.d_ids.ensure(std::max<size_t>(ix.ids.size(), 1)));
+    PQV_TRY(ix.d_cdist.ensure(ix.n_clusters));
+    PQV_TRY(ix.d_probe_cluster.ensure(ix.n_clusters));
+    PQV_TRY(ix.d_probe_prefix.ensure((size_t)ix.n_clusters + 1));
+    PQV_TRY(ix.d_cand.ensure(std::max<size_t>(ix.ids.size(), 1)));
+    CU_TRY(cudaMemcpyAsync(ix.d_centroids.p, ix.centroids.data(), ix.centroids.size() * 4, cudaMemcpyHostToDevice, D.stream));
+    CU_TRY(cudaMemcpyAsync(ix.d_offsets.p, ix.offsets.data(), ix.offsets.size() * 8, cudaMemcpyHostToDevice, D.stream));
+    if (!ix.ids.empty())
+        CU_TRY(cudaMemcpyAsync(ix.d_ids.p, ix.ids.data(), ix.ids.size() * 4, cudaMemcpyHostToDevice, D.stream));
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    ix.resident = true;
+    return PQV_OK;
+}
+
+void index_free(IvfIndex *ix) {
+    ix->d_centroids.release();
+    ix->d_cdist.release();
+    ix->d_offsets.release();
+    ix->d_probe_prefix.release();
+    ix->d_ids.release();
+    ix->d_probe_cluster.release();
+    ix->d_cand.release();
+    delete ix;
+}
+
+// find_closest_centroids (index.rs:130-149) on a resident index; host gets the ranked cluster ids
+int rank_clusters(DeviceState &D, IvfIndex &ix, const float *query, uint32_t nprobe, std::vector<uint32_t> &ranked) {
+    PQV_TRY(D.d_query.ensure(ix.dim));
+    PQV_TRY(D.h_query.ensure(ix.dim));
+    memcpy(D.h_query.p, query, (size_t)ix.dim * 4);
+    CU_TRY(cudaMemcpyAsync(D.d_query.p, D.h_query.p, (size_t)ix.dim * 4, cudaMemcpyHostToDevice, D.stream));
+    PQV_TRY(dist_launch(D, ix.d_centroids.p, nullptr, ix.n_clusters, ix.dim, D.d_query.p, ix.d_cdist.p, 0));
+    std::vector<float> dist(ix.n_clusters);
+    CU_TRY(cudaMemcpyAsync(dist.data(), ix.d_cdist.p, (size_t)ix.n_clusters * 4, cudaMemcpyDeviceToHost, D.stream));
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    std::vector<uint32_t> idx(ix.n_clusters);
+    for (uint32_t i = 0; i < ix.n_clusters; ++i) idx[i] = i;
+    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return dist[a] < dist[b]; });
+    const uint32_t np = std::min(nprobe, ix.n_clusters);
+    ranked.assign(idx.begin(), idx.begin() + np);
+    return PQV_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint32_t max_iters, uint64_t seed,
+                  uint32_t sum_workers, uint64_t *out_index) {
+    if (!ctx || !out_index) return fail(PQV_EINVAL, "null argument");
+    if (max_iters == 0) return fail(PQV_EINVAL, "max_iters must be > 0");  // src/ivf/parquet.rs:89-91
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_build needs a single-device dataset");
+    const u64 n = ds->n_rows;
+    const uint32_t dim = ds->dim;
+    if (n == 0) return fail(PQV_EINVAL, "Cannot build IVF index with zero vectors");  // index.rs:157-159
+    const u64 C64 = n_clusters_or_0 ? n_clusters_or_0 : (u64)std::ceil(std::sqrt((double)n));  // index.rs:161-167
+    if (C64 > n) return fail(PQV_EINVAL, "n_clusters cannot exceed number of vectors");          // index.rs:168-170
+    const uint32_t C = (uint32_t)C64;
+    u64 sample_size = std::max<u64>(n / 20, 1);                                                   // index.rs:172-174
+    sample_size = std::min<u64>(sample_size, 100000);
+    sample_size = std::min<u64>(std::max<u64>(sample_size, C), n);
+
+    Shard &sh = ds->shards[0];
+    DeviceState &D = ctx->devs[sh.di];
+    DevGuard guard(D.dev);
+    const double t_begin = now_ms();
+    IvfIndex *ix = new IvfIndex();
+    ix->dim = dim;
+    ix->n_clusters = C;
+    auto bail = [&](int rc) {
+        index_free(ix);
+        return rc;
+    };
+#define IVF_TRY(expr)                 \
+    do {                              \
+        int rc__ = (expr);            \
+        if (rc__) return bail(rc__);  \
+    } while (0)
+#define IVF_CU(expr)                                                                                              \
+    do {                                                                                                          \
+        cudaError_t e__ = (expr);                                                                                 \
+        if (e__ != cudaSuccess) return bail(fail(PQV_ECUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)));    \
+    } while (0)
+
+    // ---- training sample (index.rs:182-187, 222-242)
+    const float *d_sample = sh.d_data;
+    const u64 ns = sample_size;
+    if (sample_size != n) {
+        SplitMix64 rng_s(seed);
+        std::vector<uint32_t> sidx = sample_indices(rng_s, n, sample_size);
+        IVF_TRY(D.d_row_ids.ensure(ns));
+        IVF_TRY(D.d_tmp_rows.ensure((size_t)ns * dim));
+        IVF_CU(cudaMemcpyAsync(D.d_row_ids.p, sidx.data(), ns * 4, cudaMemcpyHostToDevice, D.stream));
+        pqv::gather_rows_kernel<<<D.sm_count * 8, 256, 0, D.stream>>>(sh.d_data, D.d_row_ids.p, ns, dim, D.d_tmp_rows.p);
+        IVF_CU(cudaGetLastError());
+        IVF_CU(cudaStreamSynchronize(D.stream));
+        d_sample = D.d_tmp_rows.p;
+    }
+
+    // ---- k_means (index.rs:323-457)
+    SplitMix64 rng(seed);  // the reference re-seeds StdRng with the same seed inside k_means (index.rs:327)
+    const u64 init_n = std::max<u64>(std::min<u64>(ns, 50000), C);  // index.rs:332
+    std::vector<uint32_t> init_idx;
+    if (init_n == ns) {
+        init_idx.resize(ns);
+        for (u64 i = 0; i < ns; ++i) init_idx[i] = (uint32_t)i;
+    } else {
+        init_idx = sample_indices(rng, ns, init_n);
+    }
+    IVF_TRY(D.d_centroids.ensure((size_t)C * dim));
+    IVF_CU(cudaMemsetAsync(D.d_centroids.p, 0, (size_t)C * dim * 4, D.stream));  // vec![0.0; C*dim] (index.rs:330)
+    DevBuf<uint32_t> d_init;
+    DevBuf<float> d_md;
+    IVF_TRY(d_init.ensure(init_n));
+    IVF_TRY(d_md.ensure(init_n));
+    auto free_tmp = [&]() {
+        d_init.release();
+        d_md.release();
+    };
+    cudaError_t ce = cudaMemcpyAsync(d_init.p, init_idx.data(), init_n * 4, cudaMemcpyHostToDevice, D.stream);
+    const u64 first_choice = rng.below(init_n);  // index.rs:340
+    auto set_centroid = [&](uint32_t i, uint32_t sample_row) {
+        return cudaMemcpyAsync(D.d_centroids.p + (size_t)i * dim, d_sample + (size_t)sample_row * dim, (size_t)dim * 4,
+                               cudaMemcpyDeviceToDevice, D.stream);
+    };
+    if (ce == cudaSuccess) ce = set_centroid(0, init_idx[first_choice]);
+    if (ce != cudaSuccess) {
+        free_tmp();
+        return bail(fail(PQV_ECUDA, "k-means init failed: %s", cudaGetErrorString(ce)));
+    }
+    int rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p, d_md.p, 0);  // index.rs:344-352
+    std::vector<float> md(init_n);
+    unsigned hw = std::thread::hardware_concurrency();
+    const u64 workers = std::max<u64>(1, std::min<u64>(sum_workers ? sum_workers : (hw ? hw : 1), init_n));  // index.rs:259-265
+    const u64 chunk = (init_n + workers - 1) / workers;
+    for (uint32_t i = 1; i < C && !rc; ++i) {
+        rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p + (size_t)(i - 1) * dim, d_md.p, 1);
+        if (rc) break;
+        ce = cudaMemcpyAsync(md.data(), d_md.p, init_n * 4, cudaMemcpyDeviceToHost, D.stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);
+        if (ce != cudaSuccess) {
+            rc = fail(PQV_ECUDA, "k-means++ sweep failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+        float total = 0.0f;  // index.rs:356-370: per-chunk f32 sums, summed in chunk order
+        for (u64 s0 = 0; s0 < init_n; s0 += chunk) {
+            float local = 0.0f;
+            const u64 s1 = std::min<u64>(s0 + chunk, init_n);
+            for (u64 s = s0; s < s1; ++s) local += md[s];
+            total += local;
+        }
+        if (total > 0.0f) {  // index.rs:372-383
+            const float threshold = rng.unit_f32() * total;
+            float cumsum = 0.0f;
+            for (u64 s = 0; s < init_n; ++s) {
+                cumsum += md[s];
+                if (cumsum >= threshold) {
+                    ce = set_centroid(i, init_idx[s]);
+                    break;
+                }
+            }
+        } else {  // index.rs:384-389
+            ce = set_centroid(i, init_idx[rng.below(init_n)]);
+        }
+        if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "k-means++ pick failed: %s", cudaGetErrorString(ce));
+    }
+    free_tmp();
+    if (rc) return bail(rc);
+    const double t_init = now_ms();
+
+    // ---- Lloyd (index.rs:392-454)
+    std::vector<uint32_t> assign(ns, 0), next(ns);
+    std::vector<u64> sizes(C, 0), moff;
+    std::vector<uint32_t> mids;
+    IVF_TRY(D.d_assign.ensure(ns));
+    DevBuf<uint32_t> d_mids;
+    DevBuf<u64> d_moff;
+    for (uint32_t iter = 0; iter < max_iters; ++iter) {
+        ix->build_iters = iter + 1;
+        rc = assign_device(D, d_sample, ns, dim, D.d_centroids.p, C, D.d_assign.p);
+        if (!rc) {
+            ce = cudaMemcpyAsync(next.data(), D.d_assign.p, ns * 4, cudaMemcpyDeviceToHost, D.stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);
+            if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "Lloyd assignment failed: %s", cudaGetErrorString(ce));
+        }
+        if (rc) break;
+        u64 changed = 0;
+        for (u64 i = 0; i < ns; ++i) changed += assign[i] != next[i];
+        assign.swap(next);
+        if (changed == 0) break;  // index.rs:432-434
+        csr_from_assign(assign.data(), ns, C, moff, mids);
+        rc = d_mids.ensure(ns);
+        if (!rc) rc = d_moff.ensure((size_t)C + 1);
+        if (rc) break;
+        ce = cudaMemcpyAsync(d_mids.p, mids.data(), ns * 4, cudaMemcpyHostToDevice, D.stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_moff.p, moff.data(), ((size_t)C + 1) * 8, cudaMemcpyHostToDevice, D.stream);
+        if (ce != cudaSuccess) {
+            rc = fail(PQV_ECUDA, "Lloyd update upload failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+        pqv::centroid_update_kernel<<<C, 256, 0, D.stream>>>(d_sample, dim, d_mids.p, d_moff.p, D.d_centroids.p);
+        ce = cudaGetLastError();
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);  // mids/moff are reused next iteration
+        if (ce != cudaSuccess) {
+            rc = fail(PQV_ECUDA, "centroid update failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+    }
+    d_mids.release();
+    d_moff.release();
+    if (rc) return bail(rc);
+    const double t_lloyd = now_ms();
+
+    // ---- final assignment of all N rows (index.rs:189-206)
+    ix->centroids.resize((size_t)C * dim);
+    IVF_CU(cudaMemcpyAsync(ix->centroids.data(), D.d_centroids.p, (size_t)C * dim * 4, cudaMemcpyDeviceToHost, D.stream));
+    IVF_TRY(D.d_assign.ensure(n));
+    IVF_TRY(assign_device(D, sh.d_data, n, dim, D.d_centroids.p, C, D.d_assign.p));
+    std::vector<uint32_t> full(n);
+    IVF_CU(cudaMemcpyAsync(full.data(), D.d_assign.p, n * 4, cudaMemcpyDeviceToHost, D.stream));
+    IVF_CU(cudaStreamSynchronize(D.stream));
+    csr_from_assign(full.data(), n, C, ix->offsets, ix->ids);
+    const double t_end = now_ms();
+    ix->build_ms[0] = t_init - t_begin;
+    ix->build_ms[1] = t_lloyd - t_init;
+    ix->build_ms[2] = t_end - t_lloyd;
+    ix->build_ms[3] = t_end - t_begin;
+#undef IVF_TRY
+#undef IVF_CU
+    const u64 h = ctx->next_handle++;
+    ctx->indexes[h] = ix;
+    *out_index = h;
+    return PQV_OK;
+}
+
+int pqv_ivf_build_stats(pqv_ctx *ctx, uint64_t index, uint32_t *out_lloyd_iters, double *out_ms4) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    if (out_lloyd_iters) *out_lloyd_iters = ix->build_iters;
+    if (out_ms4) memcpy(out_ms4, ix->build_ms, sizeof ix->build_ms);
+    return PQV_OK;
+}
+
+int pqv_ivf_from_bytes(pqv_ctx *ctx, const uint8_t *bytes, uint64_t len, uint64_t *out_index) {
+    if (!ctx || !out_index || (!bytes && len)) return fail(PQV_EINVAL, "null argument");
+    if (len < 8) return fail(PQV_EINVAL, "IVF index buffer too small");  // index.rs:88-90
+    uint32_t dim, C;
+    memcpy(&dim, bytes, 4);
+    memcpy(&C, bytes + 4, 4);
+    if (dim == 0) return fail(PQV_EINVAL, "Embedding dimension must be > 0");
+    if (C == 0) return fail(PQV_EINVAL, "Cluster count must be > 0");
+    u64 off = 8;
+    const u64 cbytes = (u64)dim * C * 4;
+    if (off + cbytes > len) return fail(PQV_EINVAL, "IVF index buffer truncated in centroids");
+    IvfIndex *ix = new IvfIndex();
+    ix->dim = dim;
+    ix->n_clusters = C;
+    ix->centroids.resize((size_t)dim * C);
+    memcpy(ix->centroids.data(), bytes + off, cbytes);
+    off += cbytes;
+    ix->offsets.assign((size_t)C + 1, 0);
+    for (uint32_t c = 0; c < C; ++c) {
+        uint32_t l;
+        if (off + 4 > len) {
+            delete ix;
+            return fail(PQV_EINVAL, "IVF index buffer truncated in list %u", c);
+        }
+        memcpy(&l, bytes + off, 4);
+        off += 4;
+        if (off + (u64)l * 4 > len) {
+            delete ix;
+            return fail(PQV_EINVAL, "IVF index buffer truncated in list %u", c);
+        }
+        const size_t base = ix->ids.size();
+        ix->ids.resize(base + l);
+        if (l) memcpy(ix->ids.data() + base, bytes + off, (size_t)l * 4);
+        off += (u64)l * 4;
+        ix->offsets[c + 1] = ix->offsets[c] + l;
+    }
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    const u64 h = ctx->next_handle++;
+    ctx->indexes[h] = ix;
+    *out_index = h;
+    return PQV_OK;
+}
+
+int pqv_ivf_to_bytes(pqv_ctx *ctx, uint64_t index, uint8_t *out, uint64_t cap, uint64_t *out_len) {
+    if (!ctx || !out_len) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    const u64 need = 8 + (u64)ix->centroids.size() * 4 + (u64)ix->n_clusters * 4 + (u64)ix->ids.size() * 4;
+    *out_len = need;
+    if (!out || cap < need) return out ? fail(PQV_ELIMIT, "blob needs %llu bytes", (unsigned long long)need) : PQV_OK;
+    uint8_t *p = out;  // index.rs:65-83
+    memcpy(p, &ix->dim, 4);
+    p += 4;
+    memcpy(p, &ix->n_clusters, 4);
+    p += 4;
+    memcpy(p, ix->centroids.data(), ix->centroids.size() * 4);
+    p += ix->centroids.size() * 4;
+    for (uint32_t c = 0; c < ix->n_clusters; ++c) {
+        const uint32_t l = (uint32_t)(ix->offsets[c + 1] - ix->offsets[c]);
+        memcpy(p, &l, 4);
+        p += 4;
+        if (l) memcpy(p, ix->ids.data() + ix->offsets[c], (size_t)l * 4);
+        p += (size_t)l * 4;
+    }
+    return PQV_OK;
+}
+
+int pqv_ivf_info(pqv_ctx *ctx, uint64_t index, uint32_t *out_dim, uint32_t *out_clusters, uint64_t *out_ids) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    if (out_dim) *out_dim = ix->dim;
+    if (out_clusters) *out_clusters = ix->n_clusters;
+    if (out_ids) *out_ids = ix->ids.size();
+    return PQV_OK;
+}
+
+int pqv_ivf_drop(pqv_ctx *ctx, uint64_t index) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    DevGuard guard(ctx->devs[0].dev);
+    cudaStreamSynchronize(ctx->devs[0].stream);
+    index_free(ix);
+    ctx->indexes.erase(index);
+    return PQV_OK;
+}
+
+int pqv_ivf_candidate_rows(pqv_ctx *ctx, uint64_t index, const float *query, uint32_t nprobe, uint32_t *out_rows,
+                           uint64_t cap, uint64_t *out_n) {
+    if (!ctx || !query || !out_n) return fail(PQV_EINVAL, "null argument");
+    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    DeviceState &D = ctx->devs[0];
+    DevGuard guard(D.dev);
+    PQV_TRY(index_make_resident(D, *ix));
+    std::vector<uint32_t> ranked;
+    PQV_TRY(rank_clusters(D, *ix, query, nprobe, ranked));
+    u64 total = 0;
+    for (uint32_t c : ranked) total += ix->offsets[c + 1] - ix->offsets[c];
+    *out_n = total;
+    if (total > cap || (total && !out_rows)) return fail(PQV_ELIMIT, "%llu candidate rows do not fit the caller's buffer", (unsigned long long)total);
+    u64 o = 0;
+    for (uint32_t c : ranked) {  // index.rs:57-63
+        const u64 l = ix->offsets[c + 1] - ix->offsets[c];
+        if (l) memcpy(out_rows + o, ix->ids.data() + ix->offsets[c], l * 4);
+        o += l;
+    }
+    return PQV_OK;
+}
+
+int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k, uint32_t nprobe,
+                   uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
+    if (!ctx || !query || !out_row_idx || !out_dist || !out_count) return fail(PQV_EINVAL, "null argument");
+    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");  // src/ivf/search.rs:72
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search needs a single-device dataset");
+    if (!ix->ids.empty() && ix->ids.size() > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %zu rows, dataset has %llu", ix->ids.size(), (unsigned long long)ds->n_rows);
+    DeviceState &D = ctx->devs[ds->shards[0].di];
+    DevGuard guard(D.dev);
+    PQV_TRY(index_make_resident(D, *ix));
+    std::vector<uint32_t> ranked;
+    PQV_TRY(rank_clusters(D, *ix, query, nprobe, ranked));
+    const uint32_t np = (uint32_t)ranked.size();
+    std::vector<u64> prefix((size_t)np + 1, 0);
+    for (uint32_t r = 0; r < np; ++r) prefix[r + 1] = prefix[r] + (ix->offsets[ranked[r] + 1] - ix->offsets[ranked[r]]);
+    const u64 n_cand = prefix[np];
+    if (n_cand == 0) {
+        *out_count = 0;
+        return PQV_OK;
+    }
+    CU_TRY(cudaMemcpyAsync(ix->d_probe_cluster.p, ranked.data(), (size_t)np * 4, cudaMemcpyHostToDevice, D.stream));
+    CU_TRY(cudaMemcpyAsync(ix->d_probe_prefix.p, prefix.data(), ((size_t)np + 1) * 8, cudaMemcpyHostToDevice, D.stream));
+    pqv::ivf_expand_kernel<<<np, 256, 0, D.stream>>>(ix->d_ids.p, ix->d_offsets.p, ix->d_probe_cluster.p,
+                                                     ix->d_probe_prefix.p, ix->d_cand.p);
+    CU_TRY(cudaGetLastError());
+    // candidate position -> row id on the host, from the host copy of the lists
+    const std::function<uint32_t(uint32_t)> row_fn = [&](uint32_t pos) -> uint32_t {
+        const uint32_t r = (uint32_t)(std::upper_bound(prefix.begin(), prefix.end(), (u64)pos) - prefix.begin()) - 1;
+        return ix->ids[ix->offsets[ranked[r]] + (pos - prefix[r])];
+    };
+    return topk_one(ctx, *ds, query, nullptr, n_cand, k, flags, out_row_idx, out_dist, out_count, nullptr, 0,
+                    ix->d_cand.p, &row_fn);
+}
+
+}  // extern "C"
+
+static void pqv_free_all_indexes(pqv_ctx *ctx) {
+    if (ctx->indexes.empty()) return;
+    DevGuard guard(ctx->devs[0].dev);
+    for (auto &kv : ctx->indexes) index_free(static_cast<IvfIndex *>(kv.second));
+    ctx->indexes.clear();
+}

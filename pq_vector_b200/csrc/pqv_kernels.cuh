@@ -658,4 +658,52 @@ __global__ void __launch_bounds__(256) narrow_f64_kernel(const double *__restric
     for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) out[i] = (float)in[i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// IVF support kernels
+// ------------------------------------------------------------------------------------------------
+// dense copy of selected rows (k-means sample, src/ivf/index.rs:234-239): out[i] = data[ids[i]]
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restrict__ data,
+                                                          const uint32_t *__restrict__ ids, const u64 n_ids,
+                                                          const uint32_t dim, float *__restrict__ out) {
+    const u64 total = n_ids * dim;
+    const u64 stride = (u64)gridDim.x * blockDim.x;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+        const u64 r = i / dim;
+        const uint32_t c = (uint32_t)(i - r * dim);
+        out[i] = data[(u64)ids[r] * dim + c];
+    }
+}
+
+// candidate_rows (src/ivf/index.rs:57-63): concatenate the inverted lists of the probed clusters in
+// rank order.  probe_cluster[r] = cluster id of rank r, probe_prefix[r] = first candidate position of
+// rank r (probe_prefix[nprobe] = n_cand).  One CTA per probed cluster.
+__global__ void __launch_bounds__(256) ivf_expand_kernel(const uint32_t *__restrict__ list_ids,
+                                                         const u64 *__restrict__ list_offsets,
+                                                         const uint32_t *__restrict__ probe_cluster,
+                                                         const u64 *__restrict__ probe_prefix,
+                                                         uint32_t *__restrict__ out_rows) {
+    const uint32_t r = blockIdx.x;
+    const uint32_t c = probe_cluster[r];
+    const u64 src = list_offsets[c], len = list_offsets[c + 1] - src, dst = probe_prefix[r];
+    for (u64 i = threadIdx.x; i < len; i += blockDim.x) out_rows[dst + i] = list_ids[src + i];
+}
+
+// centroid update (src/ivf/index.rs:436-453): per cluster, column-wise serial f32 sums over the member
+// rows in ascending row order (the order the reference's `for i in 0..n` visits them), then `/= size`
+// when size > 0; an empty cluster becomes the origin.  One CTA per cluster, a thread per
+// column: the per-(cluster, column) chain is identical to the reference's.
+__global__ void __launch_bounds__(256) centroid_update_kernel(const float *__restrict__ data, const uint32_t dim,
+                                                              const uint32_t *__restrict__ member_ids,
+                                                              const u64 *__restrict__ member_offsets,
+                                                              float *__restrict__ centroids) {
+    const uint32_t j = blockIdx.x;
+    const u64 b = member_offsets[j], e = member_offsets[j + 1];
+    for (uint32_t d = threadIdx.x; d < dim; d += blockDim.x) {
+        float acc = 0.f;
+        for (u64 m = b; m < e; ++m) acc = __fadd_rn(acc, data[(u64)member_ids[m] * dim + d]);
+        if (e > b) acc = __fdiv_rn(acc, (float)(e - b));
+        centroids[(u64)j * dim + d] = acc;
+    }
+}
+
 }  // namespace pqv
