@@ -292,7 +292,11 @@ struct ScanGeom {
 template <int ORDER, bool VEC4, bool GATHER>
 int scan_launch_t(const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStream_t st) {
     auto kern = pqv::l2_scan_topk_kernel<ORDER, VEC4, GATHER, SCAN_WARPS>;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    static size_t attr_smem = 0;  // raised (never lowered) per variant; scan_occupancy_t already set it for `smem`
+    if (smem > attr_smem) {
+        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_smem = smem;
+    }
     kern<<<grid, SCAN_WARPS * 32, smem, st>>>(p);
     CU_TRY(cudaGetLastError());
     return PQV_OK;
@@ -300,9 +304,19 @@ int scan_launch_t(const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStre
 
 template <int ORDER, bool VEC4, bool GATHER>
 int scan_occupancy_t(size_t smem, int *occ) {
+    // the occupancy query and the attribute call cost ~10 us each: remember the answer per (variant, smem)
+    static std::mutex mu;
+    static std::map<size_t, int> cache;
+    std::lock_guard<std::mutex> lk(mu);
+    auto it = cache.find(smem);
+    if (it != cache.end()) {
+        *occ = it->second;
+        return PQV_OK;
+    }
     auto kern = pqv::l2_scan_topk_kernel<ORDER, VEC4, GATHER, SCAN_WARPS>;
     CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, SCAN_WARPS * 32, smem));
+    cache[smem] = *occ;
     return PQV_OK;
 }
 
