@@ -337,7 +337,7 @@ def run_ours(args):
                 "sharding": "contiguous row ranges, one all-gather of per-rank heap-entrant candidates" if world > 1 else "single GPU",
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "l2_scan_topk_kernel<0,true,false,8>",
+                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "l2_scan_topk_kernel<ORDER=0,VEC4,dense,WARPS=8,RB=8,CBV=2,MINB=2>",
                          "algorithmic_bytes_per_launch": scan_bytes, "kernel_ms": scan_ms, "post_kernels_ms": post_ms},
             "e2e": {"value": world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_s * 1e3,

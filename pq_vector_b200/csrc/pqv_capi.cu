@@ -263,6 +263,7 @@ struct pqv_ctx {
     std::mutex mu;
     pqv_timing last{};
     int occ_override = 0;
+    int scan_variant = 0;
 };
 
 namespace {
@@ -284,6 +285,7 @@ struct DevGuard {
 constexpr int SCAN_WARPS = 8;
 
 struct ScanGeom {
+    int variant = 0;
     uint32_t kcap, sort_n, flush_at, grid;
     size_t smem;
     bool vec4;
@@ -320,6 +322,45 @@ int scan_occupancy_t(size_t smem, int *occ) {
     return PQV_OK;
 }
 
+// Tuning variants of the dense unroll-4 vector kernel (PQV_SCAN_VARIANT=n; 0 = the shipped default, which is
+// the <8,2,2> configuration = entry 4 of this table).
+struct ScanVariant {
+    int rb, cbv, minb;
+};
+static const ScanVariant kVariants[] = {{8, 1, 2}, {16, 1, 2}, {4, 1, 3}, {4, 2, 2}, {8, 2, 2}, {4, 1, 4}, {2, 2, 3}, {8, 1, 1}, {16, 1, 1},
+                                       {16, 2, 2}, {8, 3, 2}, {4, 3, 2}, {16, 2, 1}};
+
+template <int RB, int CBV, int MINB>
+int scan_variant_go(const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStream_t st, int *occ_out) {
+    auto kern = pqv::l2_scan_topk_kernel<0, true, false, SCAN_WARPS, RB, CBV, MINB>;
+    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if (occ_out) {
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, SCAN_WARPS * 32, smem));
+        return PQV_OK;
+    }
+    kern<<<grid, SCAN_WARPS * 32, smem, st>>>(p);
+    CU_TRY(cudaGetLastError());
+    return PQV_OK;
+}
+
+static int scan_variant_dispatch(int v, const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStream_t st, int *occ_out) {
+    switch (v) {
+        case 1: return scan_variant_go<16, 1, 2>(p, grid, smem, st, occ_out);
+        case 2: return scan_variant_go<4, 1, 3>(p, grid, smem, st, occ_out);
+        case 3: return scan_variant_go<4, 2, 2>(p, grid, smem, st, occ_out);
+        case 4: return scan_variant_go<8, 2, 2>(p, grid, smem, st, occ_out);
+        case 5: return scan_variant_go<4, 1, 4>(p, grid, smem, st, occ_out);
+        case 6: return scan_variant_go<2, 2, 3>(p, grid, smem, st, occ_out);
+        case 7: return scan_variant_go<8, 1, 1>(p, grid, smem, st, occ_out);
+        case 8: return scan_variant_go<16, 1, 1>(p, grid, smem, st, occ_out);
+        case 9: return scan_variant_go<16, 2, 2>(p, grid, smem, st, occ_out);
+        case 10: return scan_variant_go<8, 3, 2>(p, grid, smem, st, occ_out);
+        case 11: return scan_variant_go<4, 3, 2>(p, grid, smem, st, occ_out);
+        case 12: return scan_variant_go<16, 2, 1>(p, grid, smem, st, occ_out);
+        default: return fail(PQV_EINVAL, "unknown PQV_SCAN_VARIANT %d", v);
+    }
+}
+
 #define SCAN_DISPATCH(FN, order, vec4, gather, ...)                                                 \
     ((order) == 0 ? ((vec4) ? ((gather) ? FN<0, true, true>(__VA_ARGS__) : FN<0, true, false>(__VA_ARGS__))      \
                             : ((gather) ? FN<0, false, true>(__VA_ARGS__) : FN<0, false, false>(__VA_ARGS__)))   \
@@ -327,7 +368,9 @@ int scan_occupancy_t(size_t smem, int *occ) {
                             : ((gather) ? FN<1, false, true>(__VA_ARGS__) : FN<1, false, false>(__VA_ARGS__))))
 
 size_t scan_smem_bytes(int order, bool vec4, uint32_t dim, uint32_t sort_n) {
-    const size_t tile = (order == 1 && vec4) ? pqv::TileCfg<1, true>::TILE_FLOATS : pqv::TileCfg<0, true>::TILE_FLOATS;
+    const size_t tile = (order == 1 && vec4) ? pqv::TileCfg<1, true>::TILE_FLOATS
+                        : (order == 0 && vec4) ? pqv::TileCfg<0, true, pqv::ScanDefaults<0, true>::CBV>::TILE_FLOATS
+                                               : pqv::TileCfg<0, false>::TILE_FLOATS;
     const size_t dim_pad = (dim + 3u) & ~3u;
     return dim_pad * 4 + (size_t)SCAN_WARPS * tile * 4 + (size_t)sort_n * 8;
 }
@@ -339,6 +382,19 @@ int scan_geometry(pqv_ctx *ctx, DeviceState &D, const float *d_data, u64 n, uint
     g->flush_at = std::max<uint32_t>(1, g->kcap / 2);
     g->sort_n = pow2ceil(g->kcap + g->flush_at + SCAN_WARPS * 32);
     g->smem = scan_smem_bytes(order, g->vec4, dim, g->sort_n);
+    g->variant = (order == 0 && g->vec4 && !gather) ? ctx->scan_variant : 0;
+    if (g->variant > 0) {
+        const ScanVariant &sv = kVariants[g->variant];
+        g->smem = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)SCAN_WARPS * 32 * (32 * sv.cbv + 4) * 4 + (size_t)g->sort_n * 8;
+        int occ = 0;
+        pqv::ScanParams dummy{};
+        PQV_TRY(scan_variant_dispatch(g->variant, dummy, 0, g->smem, nullptr, &occ));
+        if (occ < 1) return fail(PQV_ELIMIT, "scan variant does not fit");
+        occ = std::min(occ, ctx->occ_override > 0 ? ctx->occ_override : sv.minb);
+        const u64 NGv = (n + 31) / 32;
+        g->grid = (uint32_t)std::min<u64>((u64)D.sm_count * occ, std::max<u64>(NGv, 1));
+        return PQV_OK;
+    }
     if (g->smem > 227 * 1024) return fail(PQV_ELIMIT, "scan needs %zu bytes of shared memory (dim=%u k=%u)", g->smem, dim, k);
     int occ = 0;
     PQV_TRY(SCAN_DISPATCH(scan_occupancy_t, order, g->vec4, gather, g->smem, &occ));
@@ -378,7 +434,8 @@ int enqueue_scan(pqv_ctx *ctx, DeviceState &D, const float *d_data, const uint32
     p.ent = D.ent.p;
     p.ent_count = D.ent_count.p;
     if (time_it) CU_TRY(cudaEventRecord(D.ev[0], D.stream));
-    PQV_TRY(SCAN_DISPATCH(scan_launch_t, order, g.vec4, d_row_ids != nullptr, p, g.grid, g.smem, D.stream));
+    if (g.variant > 0) PQV_TRY(scan_variant_dispatch(g.variant, p, g.grid, g.smem, D.stream, nullptr));
+    else PQV_TRY(SCAN_DISPATCH(scan_launch_t, order, g.vec4, d_row_ids != nullptr, p, g.grid, g.smem, D.stream));
     if (time_it) CU_TRY(cudaEventRecord(D.ev[1], D.stream));
     // two-level exclusive "top-k scan" over the per-CTA lists, then per-CTA threshold + entrant filter
     const uint32_t n_groups = (g.grid + pqv::MERGE_GROUP - 1) / pqv::MERGE_GROUP;
@@ -601,6 +658,7 @@ int pqv_init(pqv_ctx **out, const int *device_ids, int n_devices) {
     }
     pqv_ctx *ctx = new pqv_ctx();
     if (const char *s = getenv("PQV_SCAN_CTAS_PER_SM")) ctx->occ_override = atoi(s);
+    if (const char *s = getenv("PQV_SCAN_VARIANT")) ctx->scan_variant = std::max(0, std::min(12, atoi(s)));
     for (int id : ids) {
         DeviceState D;
         D.dev = id;

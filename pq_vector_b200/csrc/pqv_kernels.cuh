@@ -55,19 +55,30 @@ __device__ __forceinline__ float sq1(const float a, const float b) {
 //   GATHER : row index taken from row_ids[position].
 // tile: per-warp shared memory, 32 rows x TSTRIDE floats (TSTRIDE = 36, or 132 for ORDER 1 + VEC4).
 // ------------------------------------------------------------------------------------------------
-template <int ORDER, bool VEC4>
+// CBV = float4 loads per lane per row per column block (ORDER 0 + VEC4 only): a warp then reads CBV*512
+// contiguous bytes of a row per block.
+template <int ORDER, bool VEC4, int CBV = 1>
 struct TileCfg {
-    static constexpr int TERMS = (ORDER == 1 && VEC4) ? 4 : 1;  // chain terms per lane per column block
-    static constexpr int TSTRIDE = 32 * TERMS + 4;              // floats; /4 is odd -> LDS.128 conflict-free
+    static constexpr int TERMS = (ORDER == 1 && VEC4) ? 4 : CBV;  // chain terms per lane per column block
+    static constexpr int TSTRIDE = 32 * TERMS + 4;                // floats; /4 is odd -> LDS.128 conflict-free
     static constexpr int TILE_FLOATS = 32 * TSTRIDE;
 };
 
-template <int ORDER, bool VEC4, bool GATHER>
+// Tuned on B200 (profiles/r01_sweep_scan.jsonl): 8 rows x 2 float4 per lane in flight (1 KB contiguous per
+// row per request pair) gives 7.2 TB/s; 8 x 1 gives 6.0-6.6, 16 x 1 7.1, 4 CTAs/SM x 4 x 1 7.1.
+template <int ORDER, bool VEC4, bool GATHER = false>
+struct ScanDefaults {
+    static constexpr int CBV = (ORDER == 0 && VEC4) ? 2 : 1;
+    static constexpr int RB = (GATHER && CBV == 2) ? 4 : 8;  // the gather variant spills at 8 x 2 under 128 regs
+};
+
+template <int ORDER, bool VEC4, bool GATHER, int RB = 8, int CBV = 1>
 __device__ __forceinline__ float group_distance(const float *__restrict__ data,
                                                 const uint32_t *__restrict__ row_ids, const u64 n,
                                                 const uint32_t dim, const u64 g, const float *s_vec,
                                                 float *tile, const uint32_t lane) {
-    constexpr int TSTRIDE = TileCfg<ORDER, VEC4>::TSTRIDE;
+    constexpr int TSTRIDE = TileCfg<ORDER, VEC4, CBV>::TSTRIDE;
+    static_assert(CBV == 1 || (ORDER == 0 && VEC4), "CBV > 1 only for the unroll-4 vector path");
     const u64 pos = g * 32 + lane;
     const u64 posc = pos < n ? pos : n - 1;
     const u64 my_row = GATHER ? (u64)row_ids[posc] : posc;
@@ -77,17 +88,23 @@ __device__ __forceinline__ float group_distance(const float *__restrict__ data,
     float *trow = tile + lane * TSTRIDE;
 
     if constexpr (VEC4) {
-        const uint32_t ncb = (dim + 127u) >> 7;
+        constexpr uint32_t BLK = 128u * CBV;  // columns per block
+        const uint32_t ncb = (dim + BLK - 1) / BLK;
         for (uint32_t cb = 0; cb < ncb; ++cb) {
-            const uint32_t col = (cb << 7) + (lane << 2);
-            const bool inb = col < dim;
-            float4 q4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (inb) q4 = *reinterpret_cast<const float4 *>(s_vec + col);
+            const uint32_t col0 = cb * BLK + (lane << 2);
+            float4 q4[CBV];
+            bool inb[CBV];
 #pragma unroll
-            for (int r0 = 0; r0 < 32; r0 += 8) {
-                float4 v[8];
+            for (int v = 0; v < CBV; ++v) {
+                inb[v] = col0 + 128u * v < dim;
+                q4[v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (inb[v]) q4[v] = *reinterpret_cast<const float4 *>(s_vec + col0 + 128u * v);
+            }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+            for (int r0 = 0; r0 < 32; r0 += RB) {
+                float4 v4[RB][CBV];
+#pragma unroll
+                for (int j = 0; j < RB; ++j) {
                     u64 row;
                     if constexpr (GATHER) {
                         row = (u64)__shfl_sync(0xffffffffu, (uint32_t)my_row, r0 + j);
@@ -95,30 +112,35 @@ __device__ __forceinline__ float group_distance(const float *__restrict__ data,
                         row = g_first + (r0 + j);
                         row = row < n ? row : n - 1;
                     }
-                    v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (inb) v[j] = ld_stream_v4(data + row * dim + col);
+                    const float *rp = data + row * dim + col0;
+#pragma unroll
+                    for (int v = 0; v < CBV; ++v) {
+                        v4[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (inb[v]) v4[j][v] = ld_stream_v4(rp + 128 * v);
+                    }
                 }
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
+                for (int j = 0; j < RB; ++j) {
                     if constexpr (ORDER == 0) {
-                        tile[(r0 + j) * TSTRIDE + lane] = chunk4(q4, v[j]);
+#pragma unroll
+                        for (int v = 0; v < CBV; ++v) tile[(r0 + j) * TSTRIDE + 32 * v + lane] = chunk4(q4[v], v4[j][v]);
                     } else {
                         float4 p;
-                        p.x = sq1(v[j].x, q4.x);
-                        p.y = sq1(v[j].y, q4.y);
-                        p.z = sq1(v[j].z, q4.z);
-                        p.w = sq1(v[j].w, q4.w);
+                        p.x = sq1(v4[j][0].x, q4[0].x);
+                        p.y = sq1(v4[j][0].y, q4[0].y);
+                        p.z = sq1(v4[j][0].z, q4[0].z);
+                        p.w = sq1(v4[j][0].w, q4[0].w);
                         *reinterpret_cast<float4 *>(tile + (r0 + j) * TSTRIDE + (lane << 2)) = p;
                     }
                 }
             }
             __syncwarp();
             // serial chain, lane = row
-            const uint32_t rem = dim - (cb << 7);  // elements left in this block (multiple of 4)
+            const uint32_t rem = dim - cb * BLK;  // elements left in this block (multiple of 4)
             if constexpr (ORDER == 0) {
-                if (rem >= 128u) {
+                if (rem >= BLK) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
+                    for (int j = 0; j < 8 * CBV; ++j) {
                         const float4 t = *reinterpret_cast<const float4 *>(trow + 4 * j);
                         sum = __fadd_rn(sum, t.x);
                         sum = __fadd_rn(sum, t.y);
@@ -246,10 +268,11 @@ __device__ __forceinline__ void bitonic_sort_smem(u64 *s, const uint32_t n, cons
     }
 }
 
-template <int ORDER, bool VEC4, bool GATHER, int WARPS>
-__global__ void __launch_bounds__(WARPS * 32, 2) l2_scan_topk_kernel(const ScanParams p) {
+template <int ORDER, bool VEC4, bool GATHER, int WARPS, int RB = ScanDefaults<ORDER, VEC4, GATHER>::RB,
+          int CBV = ScanDefaults<ORDER, VEC4, GATHER>::CBV, int MINB = 2>
+__global__ void __launch_bounds__(WARPS * 32, MINB) l2_scan_topk_kernel(const ScanParams p) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int TILE_FLOATS = TileCfg<ORDER, VEC4>::TILE_FLOATS;
+    constexpr int TILE_FLOATS = TileCfg<ORDER, VEC4, CBV>::TILE_FLOATS;
     constexpr uint32_t NT = WARPS * 32;
     const uint32_t dim_pad = (p.dim + 3u) & ~3u;
     float *s_query = reinterpret_cast<float *>(smem_raw);
@@ -304,7 +327,7 @@ __global__ void __launch_bounds__(WARPS * 32, 2) l2_scan_topk_kernel(const ScanP
         const u64 g = g0 + warp;
         const bool active = g < g_end;  // warp-uniform
         float d = 0.f;
-        if (active) d = group_distance<ORDER, VEC4, GATHER>(p.data, p.row_ids, p.n, p.dim, g, s_query, tile, lane);
+        if (active) d = group_distance<ORDER, VEC4, GATHER, RB, CBV>(p.data, p.row_ids, p.n, p.dim, g, s_query, tile, lane);
         const u64 pos = g * 32 + lane;
         const uint32_t bits = __float_as_uint(d);
         const bool pass = active && pos < p.n && bits < s_tau;
