@@ -291,22 +291,31 @@ struct ScanGeom {
     bool vec4;
 };
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is sticky per kernel: only ever raise it
 template <int ORDER, bool VEC4, bool GATHER>
-int scan_launch_t(const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStream_t st) {
-    auto kern = pqv::l2_scan_topk_kernel<ORDER, VEC4, GATHER, SCAN_WARPS>;
-    static size_t attr_smem = 0;  // raised (never lowered) per variant; scan_occupancy_t already set it for `smem`
+int scan_ensure_smem_attr(size_t smem) {
+    static std::mutex mu;
+    static size_t attr_smem = 0;
+    std::lock_guard<std::mutex> lk(mu);
     if (smem > attr_smem) {
+        auto kern = pqv::l2_scan_topk_kernel<ORDER, VEC4, GATHER, SCAN_WARPS>;
         CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         attr_smem = smem;
     }
-    kern<<<grid, SCAN_WARPS * 32, smem, st>>>(p);
+    return PQV_OK;
+}
+
+template <int ORDER, bool VEC4, bool GATHER>
+int scan_launch_t(const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStream_t st) {
+    PQV_TRY((scan_ensure_smem_attr<ORDER, VEC4, GATHER>(smem)));
+    pqv::l2_scan_topk_kernel<ORDER, VEC4, GATHER, SCAN_WARPS><<<grid, SCAN_WARPS * 32, smem, st>>>(p);
     CU_TRY(cudaGetLastError());
     return PQV_OK;
 }
 
 template <int ORDER, bool VEC4, bool GATHER>
 int scan_occupancy_t(size_t smem, int *occ) {
-    // the occupancy query and the attribute call cost ~10 us each: remember the answer per (variant, smem)
+    // the occupancy query costs ~10 us: remember the answer per (variant, smem)
     static std::mutex mu;
     static std::map<size_t, int> cache;
     std::lock_guard<std::mutex> lk(mu);
@@ -315,8 +324,8 @@ int scan_occupancy_t(size_t smem, int *occ) {
         *occ = it->second;
         return PQV_OK;
     }
+    PQV_TRY((scan_ensure_smem_attr<ORDER, VEC4, GATHER>(smem)));
     auto kern = pqv::l2_scan_topk_kernel<ORDER, VEC4, GATHER, SCAN_WARPS>;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ, kern, SCAN_WARPS * 32, smem));
     cache[smem] = *occ;
     return PQV_OK;
