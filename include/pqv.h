@@ -174,6 +174,27 @@ typedef struct {
     uint32_t reserved;
 } pqv_timing;
 PQV_API int pqv_last_timing(pqv_ctx *ctx, pqv_timing *out);
+/* what the last pqv_kmeans_assign / pqv_bench_assign did.  path 1 = tcgen05 tf32 filter
+ * (tensor cores decide every row whose candidate window holds one centroid; the rest are re-evaluated in the
+ * reference's exact f32 order), path 0 = exact SIMT kernel for every (row, centroid) pair. */
+typedef struct {
+    uint32_t path;            /* 0 = exact SIMT, 1 = tcgen05 filter + exact re-check                        */
+    uint32_t reserved;
+    uint64_t rows;
+    uint64_t ambiguous_rows;  /* rows with 2..4 candidates after the filter (exact chain over those only)  */
+    uint64_t overflow_rows;   /* rows sent to the full exact scan (non-finite norms, > 4 candidates)       */
+    double prep_ms;           /* centroid centring/rounding + row norms                                    */
+    double filter_ms;         /* the tcgen05 kernel (path 1) or the SIMT kernel (path 0), CUDA events      */
+    double recheck_ms;        /* exact re-evaluation kernels                                               */
+    double total_ms;
+} pqv_assign_timing;
+PQV_API int pqv_last_assign_timing(pqv_ctx *ctx, pqv_assign_timing *out);
+/* device-resident loop for roofline timing of the assignment sweep (src/ivf/index.rs:189-206): `iters` sweeps of
+ * the first n rows of the resident dataset against `centroids` with inputs and outputs in HBM; the mean times
+ * land in *out (path as pqv_kmeans_assign would pick it, or forced by the PQV_ASSIGN=simt|tc environment variable).
+ * out_assign (may be NULL) receives the assignments of the last sweep. */
+PQV_API int pqv_bench_assign(pqv_ctx *ctx, uint64_t handle, uint64_t n, const float *centroids, uint32_t n_clusters,
+                             uint32_t iters, pqv_assign_timing *out, uint32_t *out_assign);
 /* device-resident loop for roofline timing: runs `iters` scans of query 0 back to back with inputs and
  * outputs in HBM and returns the mean kernel time (CUDA events on the launch stream). */
 PQV_API int pqv_bench_scan(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags,

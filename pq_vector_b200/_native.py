@@ -20,6 +20,12 @@ class PqvTiming(C.Structure):
                 ("grid", C.c_uint32), ("reserved", C.c_uint32)]
 
 
+class PqvAssignTiming(C.Structure):
+    _fields_ = [("path", C.c_uint32), ("reserved", C.c_uint32), ("rows", C.c_uint64),
+                ("ambiguous_rows", C.c_uint64), ("overflow_rows", C.c_uint64), ("prep_ms", C.c_double),
+                ("filter_ms", C.c_double), ("recheck_ms", C.c_double), ("total_ms", C.c_double)]
+
+
 f32p, f64p = C.POINTER(C.c_float), C.POINTER(C.c_double)
 u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
 ctxp = C.c_void_p
@@ -60,6 +66,9 @@ SIGNATURES = {
                                          u64p]),
     "pqv_replay_candidates": (C.c_int, [u64p, C.c_uint64, u32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),
     "pqv_last_timing": (C.c_int, [ctxp, C.POINTER(PqvTiming)]),
+    "pqv_last_assign_timing": (C.c_int, [ctxp, C.POINTER(PqvAssignTiming)]),
+    "pqv_bench_assign": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32,
+                                   C.POINTER(PqvAssignTiming), u32p]),
     "pqv_bench_scan": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, f64p]),
 }
 

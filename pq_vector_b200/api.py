@@ -141,6 +141,26 @@ class Context:
     def topk_stream(self, query, k, flags=N.PQV_SUM_SEQ) -> "TopkStream":
         return TopkStream(self, query, k, flags)
 
+    def last_assign_timing(self) -> dict:
+        """What the last kmeans_assign / bench_assign did: path (1 = tcgen05 filter), ambiguous/overflow rows, ms."""
+        t = N.PqvAssignTiming()
+        _check(_lib.pqv_last_assign_timing(self._h, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in N.PqvAssignTiming._fields_ if f != "reserved"}
+
+    def bench_assign(self, dataset: "Dataset", centroids, iters: int = 3, n=None, want_assign=False):
+        """Device-resident assignment sweeps (inputs and outputs stay in HBM); mean CUDA-event times."""
+        centroids = _f32(centroids)
+        c, dim = centroids.shape
+        if dim != dataset.dim:
+            raise PqvError(N.PQV_EINVAL, f"dimension mismatch: dataset has {dataset.dim}, centroids have {dim}")
+        n = dataset.rows if n is None else n
+        out = np.empty(n, dtype=np.uint32) if want_assign else None
+        t = N.PqvAssignTiming()
+        _check(_lib.pqv_bench_assign(self._h, dataset.handle, n, _ptr(centroids, C.c_float), c, iters, C.byref(t),
+                                     _ptr(out, C.c_uint32)))
+        d = {f: getattr(t, f) for f, _ in N.PqvAssignTiming._fields_ if f != "reserved"}
+        return (d, out) if want_assign else d
+
     def last_timing(self) -> dict:
         t = N.PqvTiming()
         _check(_lib.pqv_last_timing(self._h, C.byref(t)))

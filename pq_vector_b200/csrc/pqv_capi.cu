@@ -219,6 +219,9 @@ struct DeviceState {
     DevBuf<u64> cta_topk, ent, final_topk, ent_out, within_prefix, group_total, group_prefix;
     DevBuf<uint32_t> ent_count, gthr, d_row_ids, d_assign;
     DevBuf<float> d_vec, d_tmp_rows, d_centroids, d_dist;
+    // tcgen05 assignment filter scratch (pqv_tc_host.cuh)
+    DevBuf<float> tc_bp, tc_mu, tc_cn, tc_x2;
+    DevBuf<uint32_t> tc_u32, tc_amb_rows, tc_amb_cand, tc_ovf_rows;
     PinBuf<u64> h_ent_out, h_final;
     PinBuf<float> h_query;
 };
@@ -262,6 +265,7 @@ struct pqv_ctx {
     u64 next_handle = 1;
     std::mutex mu;
     pqv_timing last{};
+    pqv_assign_timing last_assign{};
     int occ_override = 0;
     int scan_variant = 0;
 };
@@ -636,6 +640,8 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
 
 }  // namespace
 
+#include "pqv_tc_host.cuh"
+
 static void pqv_free_all_indexes(pqv_ctx *ctx);
 
 // ================================================================================================
@@ -730,6 +736,14 @@ void pqv_destroy(pqv_ctx *ctx) {
         D.d_tmp_rows.release();
         D.d_centroids.release();
         D.d_dist.release();
+        D.tc_bp.release();
+        D.tc_mu.release();
+        D.tc_cn.release();
+        D.tc_x2.release();
+        D.tc_u32.release();
+        D.tc_amb_rows.release();
+        D.tc_amb_cand.release();
+        D.tc_ovf_rows.release();
         D.h_ent_out.release();
         D.h_final.release();
         D.h_query.release();
@@ -1091,16 +1105,67 @@ int pqv_kmeans_assign(pqv_ctx *ctx, uint64_t handle, const float *rows, uint64_t
         if (off == 0)
             CU_TRY(cudaMemcpyAsync(D->d_centroids.p, centroids, (size_t)n_clusters * dim * 4, cudaMemcpyHostToDevice, D->stream));
         PQV_TRY(D->d_assign.ensure(cnt));
-        const uint32_t grid = (uint32_t)((cnt + pqv::AS_BM - 1) / pqv::AS_BM);
-        const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rows) & 15) == 0);
-        if (vec4) pqv::kmeans_assign_kernel<true><<<grid, 256, 0, D->stream>>>(d_rows, cnt, dim, D->d_centroids.p, n_clusters, D->d_assign.p);
-        else pqv::kmeans_assign_kernel<false><<<grid, 256, 0, D->stream>>>(d_rows, cnt, dim, D->d_centroids.p, n_clusters, D->d_assign.p);
-        CU_TRY(cudaGetLastError());
+        int path = 0;
+        PQV_TRY(assign_dispatch(*D, d_rows, cnt, dim, D->d_centroids.p, n_clusters, D->d_assign.p, &path, true));
+        uint32_t h_counts[2] = {0, 0};
+        if (path == ASSIGN_TC)
+            CU_TRY(cudaMemcpyAsync(h_counts, D->tc_u32.p + 4, sizeof h_counts, cudaMemcpyDeviceToHost, D->stream));
         CU_TRY(cudaMemcpyAsync(out_assign + off, D->d_assign.p, cnt * 4, cudaMemcpyDeviceToHost, D->stream));
         CU_TRY(cudaStreamSynchronize(D->stream));
+        record_assign_timing(ctx, *D, path, cnt, h_counts, off == 0);
     }
     if (out_sizes)
         for (u64 i = 0; i < n; ++i) out_sizes[out_assign[i]]++;
+    return PQV_OK;
+}
+
+int pqv_last_assign_timing(pqv_ctx *ctx, pqv_assign_timing *out) {
+    if (!ctx || !out) return fail(PQV_EINVAL, "null argument");
+    *out = ctx->last_assign;
+    return PQV_OK;
+}
+
+int pqv_bench_assign(pqv_ctx *ctx, uint64_t handle, uint64_t n, const float *centroids, uint32_t n_clusters, uint32_t iters,
+                     pqv_assign_timing *out, uint32_t *out_assign) {
+    if (!ctx || !centroids || !out) return fail(PQV_EINVAL, "null argument");
+    if (n_clusters == 0) return fail(PQV_EINVAL, "Cluster count must be > 0");
+    if (iters == 0 || n == 0) return fail(PQV_EINVAL, "iters and n must be > 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    DeviceState *D = nullptr;
+    const float *d_rows = nullptr;
+    PQV_TRY(resolve_rows(ctx, handle, nullptr, n, ds->dim, &D, &d_rows));
+    DevGuard guard(D->dev);
+    const uint32_t dim = ds->dim;
+    PQV_TRY(D->d_centroids.ensure((size_t)n_clusters * dim));
+    PQV_TRY(D->d_assign.ensure(n));
+    CU_TRY(cudaMemcpyAsync(D->d_centroids.p, centroids, (size_t)n_clusters * dim * 4, cudaMemcpyHostToDevice, D->stream));
+    pqv_assign_timing acc{};
+    for (uint32_t it = 0; it < iters; ++it) {
+        int path = 0;
+        PQV_TRY(assign_dispatch(*D, d_rows, n, dim, D->d_centroids.p, n_clusters, D->d_assign.p, &path, true));
+        uint32_t h_counts[2] = {0, 0};
+        if (path == ASSIGN_TC)
+            CU_TRY(cudaMemcpyAsync(h_counts, D->tc_u32.p + 4, sizeof h_counts, cudaMemcpyDeviceToHost, D->stream));
+        CU_TRY(cudaStreamSynchronize(D->stream));
+        record_assign_timing(ctx, *D, path, n, h_counts, true);
+        const pqv_assign_timing &t = ctx->last_assign;
+        acc.path = t.path;
+        acc.rows = t.rows;
+        acc.ambiguous_rows = t.ambiguous_rows;
+        acc.overflow_rows = t.overflow_rows;
+        acc.prep_ms += t.prep_ms / iters;
+        acc.filter_ms += t.filter_ms / iters;
+        acc.recheck_ms += t.recheck_ms / iters;
+        acc.total_ms += t.total_ms / iters;
+    }
+    if (out_assign) {
+        CU_TRY(cudaMemcpyAsync(out_assign, D->d_assign.p, n * 4, cudaMemcpyDeviceToHost, D->stream));
+        CU_TRY(cudaStreamSynchronize(D->stream));
+    }
+    ctx->last_assign = acc;
+    *out = acc;
     return PQV_OK;
 }
 

@@ -90,13 +90,7 @@ void csr_from_assign(const uint32_t *assign, u64 n, uint32_t n_clusters, std::ve
 
 int assign_device(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const float *d_centroids, uint32_t C,
                   uint32_t *d_out) {
-    const uint32_t grid = (uint32_t)((n + pqv::AS_BM - 1) / pqv::AS_BM);
-    const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_rows) & 15) == 0) &&
-                      ((reinterpret_cast<uintptr_t>(d_centroids) & 15) == 0);
-    if (vec4) pqv::kmeans_assign_kernel<true><<<grid, 256, 0, D.stream>>>(d_rows, n, dim, d_centroids, C, d_out);
-    else pqv::kmeans_assign_kernel<false><<<grid, 256, 0, D.stream>>>(d_rows, n, dim, d_centroids, C, d_out);
-    CU_TRY(cudaGetLastError());
-    return PQV_OK;
+    return assign_dispatch(D, d_rows, n, dim, d_centroids, C, d_out);  // tcgen05 filter or exact SIMT, pqv_tc_host.cuh
 }
 
 double now_ms() {
