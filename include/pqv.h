@@ -185,7 +185,8 @@ typedef struct {
     uint64_t overflow_rows;   /* rows sent to the full exact scan (non-finite norms, > 4 candidates)       */
     double prep_ms;           /* centroid centring/rounding + row norms                                    */
     double filter_ms;         /* the tcgen05 kernel (path 1) or the SIMT kernel (path 0), CUDA events      */
-    double recheck_ms;        /* exact re-evaluation kernels                                               */
+    double recheck_ms;        /* exact re-evaluation kernels (pairs + overflow scan + finalize)            */
+    double pair_ms;           /* of which: the (row, candidate) pair kernel                                */
     double total_ms;
 } pqv_assign_timing;
 PQV_API int pqv_last_assign_timing(pqv_ctx *ctx, pqv_assign_timing *out);

@@ -269,6 +269,12 @@ class IvfIndex:
         _check(_lib.pqv_ivf_to_bytes(self.ctx._h, self.handle, buf, need.value, C.byref(need)))
         return bytes(buf)
 
+    def centroids(self) -> np.ndarray:
+        """C x dim f32 centroid table, parsed from the blob header (src/ivf/index.rs:65-83: u32 dim, u32 C, f32[C*dim])."""
+        b = self.to_bytes()
+        dim, c = np.frombuffer(b, dtype="<u4", count=2)
+        return np.frombuffer(b, dtype="<f4", count=int(dim) * int(c), offset=8).reshape(int(c), int(dim)).copy()
+
     def build_stats(self) -> dict:
         it = C.c_uint32()
         ms = (C.c_double * 4)()

@@ -214,14 +214,17 @@ struct DeviceState {
     int dev = 0;
     int sm_count = 0;
     cudaStream_t stream = nullptr, copy_stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
     DevBuf<float> d_query;
     DevBuf<u64> cta_topk, ent, final_topk, ent_out, within_prefix, group_total, group_prefix;
     DevBuf<uint32_t> ent_count, gthr, d_row_ids, d_assign;
     DevBuf<float> d_vec, d_tmp_rows, d_centroids, d_dist;
     // tcgen05 assignment filter scratch (pqv_tc_host.cuh)
-    DevBuf<float> tc_bp, tc_mu, tc_cn, tc_x2;
-    DevBuf<uint32_t> tc_u32, tc_amb_rows, tc_amb_cand, tc_ovf_rows;
+    DevBuf<float> tc_bp, tc_mu, tc_cn;
+    DevBuf<float2> tc_stats;
+    DevBuf<uint2> tc_pairs;
+    DevBuf<u64> tc_best;
+    DevBuf<uint32_t> tc_u32, tc_amb_rows, tc_ovf_rows;
     PinBuf<u64> h_ent_out, h_final;
     PinBuf<float> h_query;
 };
@@ -739,10 +742,11 @@ void pqv_destroy(pqv_ctx *ctx) {
         D.tc_bp.release();
         D.tc_mu.release();
         D.tc_cn.release();
-        D.tc_x2.release();
+        D.tc_stats.release();
+        D.tc_pairs.release();
+        D.tc_best.release();
         D.tc_u32.release();
         D.tc_amb_rows.release();
-        D.tc_amb_cand.release();
         D.tc_ovf_rows.release();
         D.h_ent_out.release();
         D.h_final.release();
@@ -1158,6 +1162,7 @@ int pqv_bench_assign(pqv_ctx *ctx, uint64_t handle, uint64_t n, const float *cen
         acc.prep_ms += t.prep_ms / iters;
         acc.filter_ms += t.filter_ms / iters;
         acc.recheck_ms += t.recheck_ms / iters;
+        acc.pair_ms += t.pair_ms / iters;
         acc.total_ms += t.total_ms / iters;
     }
     if (out_assign) {

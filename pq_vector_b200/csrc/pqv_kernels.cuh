@@ -522,23 +522,35 @@ __global__ void __launch_bounds__(WARPS * 32, 2) l2_dist_kernel(const float *__r
 // ------------------------------------------------------------------------------------------------
 constexpr int AS_BM = 64, AS_BN = 64, AS_BK = 32, AS_LD = AS_BK + 4;
 
-template <bool VEC4>
-__global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__restrict__ rows, const u64 n,
+// GATHER: the tile's rows are row_ids[0 .. *n_dev) (a device-side list: the rows the tensor-core filter could not
+// decide).  The grid covers the worst case in x and surplus CTAs exit at once; blockIdx.y selects a slice of slice_len
+// centroids (a multiple of AS_BN) so that a handful of rows does not serialise behind one CTA's walk over the whole table.
+// Each slice folds its winner into best[row] = min(bits(distance) << 32 | centroid): distances that can win are finite and
+// >= 0, so the u64 order is (distance, index) -- the strict-'<' ascending scan; best[row] stays KEY_MAX if nothing wins.
+template <bool VEC4, bool GATHER = false>
+__global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__restrict__ rows, const u64 n_arg,
                                                                const uint32_t dim,
                                                                const float *__restrict__ centroids,
                                                                const uint32_t n_clusters,
-                                                               uint32_t *__restrict__ out_assign) {
+                                                               uint32_t *__restrict__ out_assign,
+                                                               const uint32_t *__restrict__ row_ids = nullptr,
+                                                               const uint32_t *__restrict__ n_dev = nullptr,
+                                                               u64 *__restrict__ best = nullptr,
+                                                               const uint32_t slice_len = 0) {
     __shared__ __align__(16) float As[2][AS_BM * AS_LD];
     __shared__ __align__(16) float Bs[2][AS_BN * AS_LD];
     const uint32_t tid = threadIdx.x;
     const uint32_t tx = tid & 15, ty = tid >> 4;
     const u64 row0 = (u64)blockIdx.x * AS_BM;
+    const u64 n = GATHER ? (u64)*n_dev : n_arg;
+    if (GATHER && row0 >= n) return;
     const uint32_t n4 = dim >> 2;                       // full 4-chunks (chain terms)
     const uint32_t nkb = (n4 + 7) >> 3;                 // blocks of 8 chunks = 32 columns
     const uint32_t tail0 = n4 << 2, ntail = dim - tail0;  // scalar tail terms (dim % 4)
 
     // loader mapping: 64 rows x 8 chunks = 512 float4 per tile -> 2 per thread
-    auto load_tile = [&](float *dst, const float *src, const u64 first, const u64 limit, const uint32_t kb) {
+    auto load_tile = [&](float *dst, const float *src, const u64 first, const u64 limit, const uint32_t kb,
+                         const bool via_ids = false) {
 #pragma unroll
         for (int it = 0; it < 2; ++it) {
             const uint32_t idx = tid + it * 256;
@@ -546,6 +558,7 @@ __global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__re
             const uint32_t chunk = kb * 8 + c;
             u64 row = first + r;
             row = row < limit ? row : limit - 1;
+            if (GATHER && via_ids) row = row_ids[row];
             float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
             if (chunk < n4) {
                 const float *sp = src + row * dim + (chunk << 2);
@@ -564,7 +577,9 @@ __global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__re
         run_i[i] = 0;
     }
 
-    for (uint32_t cn = 0; cn < n_clusters; cn += AS_BN) {
+    const uint32_t c_begin = GATHER ? blockIdx.y * slice_len : 0u;
+    const uint32_t c_end = GATHER ? min(n_clusters, c_begin + slice_len) : n_clusters;
+    for (uint32_t cn = c_begin; cn < c_end; cn += AS_BN) {
         float acc[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i)
@@ -573,13 +588,13 @@ __global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__re
 
         int buf = 0;
         if (nkb > 0) {
-            load_tile(As[0], rows, row0, n, 0);
+            load_tile(As[0], rows, row0, n, 0, true);
             load_tile(Bs[0], centroids, cn, n_clusters, 0);
         }
         __syncthreads();
         for (uint32_t kb = 0; kb < nkb; ++kb) {
             if (kb + 1 < nkb) {
-                load_tile(As[buf ^ 1], rows, row0, n, kb + 1);
+                load_tile(As[buf ^ 1], rows, row0, n, kb + 1, true);
                 load_tile(Bs[buf ^ 1], centroids, cn, n_clusters, kb + 1);
             }
             const float *A = As[buf] + (ty * 4) * AS_LD;
@@ -605,6 +620,7 @@ __global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__re
             for (int i = 0; i < 4; ++i) {
                 u64 row = row0 + ty * 4 + i;
                 row = row < n ? row : n - 1;
+                if (GATHER) row = row_ids[row];
                 const float av = rows[row * dim + tail0 + t];
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
@@ -648,7 +664,15 @@ __global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__re
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const u64 row = row0 + ty * 4 + i;
-            if (row < n) out_assign[row] = run_i[i];
+            if (row < n) {
+                if constexpr (GATHER) {
+                    if (run_d[i] < __int_as_float(0x7f800000))
+                        atomicMin(reinterpret_cast<unsigned long long *>(&best[row_ids[row]]),
+                                  ((u64)__float_as_uint(run_d[i]) << 32) | (u64)run_i[i]);
+                } else {
+                    out_assign[row] = run_i[i];
+                }
+            }
         }
     }
 }

@@ -14,7 +14,7 @@
 //
 // so the reference argmin lies in  { j : ŝ_j <= min_j ŝ_j + 2E + G },  G >= 2.1 delta max_j d_true_j.  Rows whose
 // set has one element are final; the others (and rows with non-finite norms or a full candidate FIFO) are
-// re-evaluated with the exact serial-order f32 chain (assign_recheck_kernel / assign_overflow_kernel).
+// re-evaluated with the exact serial-order f32 chain (pair_exact_kernel / the sliced kmeans_assign_kernel<.., GATHER>).
 //
 // Kernel shape (one persistent CTA per SM, 192 threads):
 //   warp 0   : TMA producer      rows tile 128 x 32 f32 + centroid tile 256 x 32 f32 per stage (SWIZZLE_128B), 4 stages
@@ -45,7 +45,7 @@ constexpr int EPI_WARP0 = 2;
 constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
 constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr int FIFO = 4;      // candidate slots per row
+constexpr int FIFO = 8;      // candidate slots per row (unordered; a slot is free once its score left the window)
 
 constexpr uint64_t HINT_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
@@ -149,15 +149,17 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // ------------------------------------------------------------------------------------------------
 // preparation kernels (tiny): column mean of the centroid table, centred + tf32-rounded table, norms, bounds
 // ------------------------------------------------------------------------------------------------
-// bounds[0] = max_j 2 (eps_mma bn_j + rn_j)   bounds[1] = max_j |c_j|^2   bounds[2] = max_j bn_j     (f32 bit patterns, >= 0)
+// bounds[0] = max_j 2 (eps_mma bn_j + rn_j)   bounds[1] = max_j |c_j|^2   bounds[2] = max_j bn_j   bounds[3] = |mu|^2
+// (f32 bit patterns, >= 0; zeroed by the caller before centroid_mean_kernel)
 __global__ void centroid_mean_kernel(const float *__restrict__ cent, uint32_t C, uint32_t dim, float *__restrict__ mu,
                                      uint32_t *__restrict__ bounds) {
     const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
-    if (blockIdx.x == 0 && threadIdx.x < 4) bounds[threadIdx.x] = 0u;
     if (col >= dim) return;
     float s = 0.f;
     for (uint32_t j = 0; j < C; ++j) s += cent[(size_t)j * dim + col];
-    mu[col] = s / (float)C;  // any vector is valid here; the mean just keeps |c - mu| small
+    const float m = s / (float)C;  // any vector is valid here; the mean just keeps |c - mu| small
+    mu[col] = m;
+    atomicAdd(reinterpret_cast<float *>(&bounds[3]), m * m);  // |mu|^2 (order-dependent rounding: only feeds an inflated bound)
 }
 
 __device__ __forceinline__ float tf32_rn(float v) {
@@ -168,12 +170,15 @@ __device__ __forceinline__ float tf32_rn(float v) {
 
 __global__ void __launch_bounds__(128) centroid_prep_kernel(const float *__restrict__ cent, uint32_t C, uint32_t dim,
                                                             const float *__restrict__ mu, float *__restrict__ Bp,
-                                                            float *__restrict__ cn, uint32_t cn_len,
+                                                            float *__restrict__ cn, float *__restrict__ wv, uint32_t cn_len,
                                                             uint32_t *__restrict__ bounds) {
     const uint32_t j = blockIdx.x;
     __shared__ double red[3][4];
     if (j >= C) {  // padding entries of cn: +inf never passes "ŝ <= thr"
-        if (threadIdx.x == 0 && j < cn_len) cn[j] = __int_as_float(0x7f800000);
+        if (threadIdx.x == 0 && j < cn_len) {
+            cn[j] = __int_as_float(0x7f800000);
+            wv[j] = 0.f;
+        }
         return;
     }
     double r2 = 0.0, b2 = 0.0, c2 = 0.0;
@@ -212,36 +217,47 @@ __global__ void __launch_bounds__(128) centroid_prep_kernel(const float *__restr
         const float wj = (float)(2.0 * (eps * bn + rn) * up);
         const float cnj = (float)c2;
         cn[j] = cnj;
+        wv[j] = wj;  // |ŝ_j - s_j| <= |x| wv[j] + rounding slack
         atomicMax(&bounds[0], __float_as_uint(wj));   // non-negative floats (and NaN/inf above them) order as unsigned
         atomicMax(&bounds[1], __float_as_uint(cnj));
         atomicMax(&bounds[2], __float_as_uint((float)bn));
     }
 }
 
-// |x_i|^2 in f32 (any order: it only feeds the error bound, inflated by the caller)
-__global__ void __launch_bounds__(256) row_norm_kernel(const float *__restrict__ rows, u64 n, uint32_t dim, float *__restrict__ x2) {
+// per row: (|x|^2, x.mu) in f32 (any order: they only feed the error bounds, inflated by the consumer)
+__global__ void __launch_bounds__(256) row_stats_kernel(const float *__restrict__ rows, u64 n, uint32_t dim,
+                                                        const float *__restrict__ mu, float2 *__restrict__ stats) {
     const uint32_t lane = threadIdx.x & 31;
     const u64 warp = ((u64)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const u64 nwarps = ((u64)gridDim.x * blockDim.x) >> 5;
     const uint32_t n4 = dim >> 2;
+    const float4 *m4 = reinterpret_cast<const float4 *>(mu);
     for (u64 r = warp; r < n; r += nwarps) {
         const float4 *p = reinterpret_cast<const float4 *>(rows + r * dim);
-        float s0 = 0.f, s1 = 0.f;
+        float s0 = 0.f, s1 = 0.f, t0 = 0.f, t1 = 0.f;
         uint32_t c = lane;
         for (; c + 32 < n4; c += 64) {
             const float4 a = ld_stream_v4(reinterpret_cast<const float *>(p + c));
             const float4 b = ld_stream_v4(reinterpret_cast<const float *>(p + c + 32));
+            const float4 ma = __ldg(m4 + c), mb = __ldg(m4 + c + 32);
             s0 = __fmaf_rn(a.x, a.x, s0); s0 = __fmaf_rn(a.y, a.y, s0); s0 = __fmaf_rn(a.z, a.z, s0); s0 = __fmaf_rn(a.w, a.w, s0);
             s1 = __fmaf_rn(b.x, b.x, s1); s1 = __fmaf_rn(b.y, b.y, s1); s1 = __fmaf_rn(b.z, b.z, s1); s1 = __fmaf_rn(b.w, b.w, s1);
+            t0 = __fmaf_rn(a.x, ma.x, t0); t0 = __fmaf_rn(a.y, ma.y, t0); t0 = __fmaf_rn(a.z, ma.z, t0); t0 = __fmaf_rn(a.w, ma.w, t0);
+            t1 = __fmaf_rn(b.x, mb.x, t1); t1 = __fmaf_rn(b.y, mb.y, t1); t1 = __fmaf_rn(b.z, mb.z, t1); t1 = __fmaf_rn(b.w, mb.w, t1);
         }
         for (; c < n4; c += 32) {
             const float4 a = ld_stream_v4(reinterpret_cast<const float *>(p + c));
+            const float4 ma = __ldg(m4 + c);
             s0 = __fmaf_rn(a.x, a.x, s0); s0 = __fmaf_rn(a.y, a.y, s0); s0 = __fmaf_rn(a.z, a.z, s0); s0 = __fmaf_rn(a.w, a.w, s0);
+            t0 = __fmaf_rn(a.x, ma.x, t0); t0 = __fmaf_rn(a.y, ma.y, t0); t0 = __fmaf_rn(a.z, ma.z, t0); t0 = __fmaf_rn(a.w, ma.w, t0);
         }
-        float s = s0 + s1;
+        float s = s0 + s1, t = t0 + t1;
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (lane == 0) x2[r] = s;
+        for (int o = 16; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            t += __shfl_xor_sync(0xffffffffu, t, o);
+        }
+        if (lane == 0) stats[r] = make_float2(s, t);
     }
 }
 
@@ -249,15 +265,18 @@ __global__ void __launch_bounds__(256) row_norm_kernel(const float *__restrict__
 // the tensor-core filter
 // ------------------------------------------------------------------------------------------------
 struct AssignTcParams {
-    const float *x2;        // [n] row squared norms (row_norm_kernel)
+    const float2 *stats;    // [n] (|x|^2, x.mu) per row (row_stats_kernel)
     const float *cn;        // [num_nb * BN] centroid squared norms, +inf padded
+    const float *wv;        // [num_nb * BN] per-centroid error weight w_j (0 padded): |ŝ_j - s_j| <= |x| w_j + slack
     const uint32_t *bounds; // [4] see centroid_prep_kernel
-    uint32_t *assign;       // [n] out: final for unambiguous rows
-    uint32_t *counts;       // [0] ambiguous rows, [1] overflow rows (zeroed by the caller)
+    uint32_t *assign;       // [n] out: final for rows the filter decides
+    uint32_t *counts;       // [0] ambiguous rows, [1] overflow rows, [2] (row, candidate) pairs; zeroed by the caller
     uint32_t *amb_rows;     // [n]
-    uint32_t *amb_cand;     // [n * FIFO]
-    uint32_t *ovf_rows;     // [n]
+    uint2 *pairs;           // [pair_cap] (row, candidate): one exact distance each (pair_exact_kernel)
+    u64 *best;              // [n] per ambiguous row: min over its pairs of bits(distance) << 32 | candidate
+    uint32_t *ovf_rows;     // [n] rows for the full exact scan
     u64 n;
+    uint32_t pair_cap;
     uint32_t dim, C;
     uint32_t num_mb, num_nb, num_kb;
 };
@@ -343,29 +362,35 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===== epilogue: one row per thread; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
         const uint32_t q = warp & 3u;
         const uint32_t row_in_tile = q * 32u + lane;
-        const float cnmax = __uint_as_float(p.bounds[1]), bnmax = __uint_as_float(p.bounds[2]);
-        const float wmax = __uint_as_float(p.bounds[0]);
-        const float delta = (float)(p.dim / 4 + 12) * 5.9604645e-08f;  // 2^-24
-        const float cmaxn = sqrtf(cnmax) * 1.000001f;
-        const bool table_ok = (cnmax < 1e30f) && (wmax < 1e30f);
+        const float wmax = __uint_as_float(p.bounds[0]), cnmax = __uint_as_float(p.bounds[1]);
+        const float bnmax = __uint_as_float(p.bounds[2]);
+        const float mun = sqrtf(__uint_as_float(p.bounds[3])) * 1.000001f;
+        const float delta = (float)(p.dim / 4 + 12) * 5.9604645e-08f;   // 2^-24: reference's serial f32 chain, terms >= 0
+        const float gamma = (float)(p.dim + 32) * 5.9604645e-08f;       // row_stats_kernel's f32 sums
+        const float c2 = 2.2f * delta;
+        const bool table_ok = (cnmax < 1e30f) && (wmax < 1e30f) && (mun < 1e30f);
+        const float inf = __int_as_float(0x7f800000);
         uint32_t tile = 0;
         for (uint32_t mb = blockIdx.x; mb < p.num_mb; mb += gridDim.x) {
             const u64 row = (u64)mb * BM + row_in_tile;
             const bool valid = row < p.n;
-            float x2 = valid ? p.x2[row] : 0.f;
-            x2 = x2 * (1.f + (float)(p.dim + 32) * 1.1920929e-07f);  // f32 summation error of row_norm_kernel
+            const float2 st = valid ? p.stats[row] : make_float2(0.f, 0.f);
+            const float x2 = st.x * (1.f + gamma) + 1e-37f;
             const float a = sqrtf(x2) * 1.000001f;
-            // E: bound on |ŝ_j - s_j|;  T: width of the candidate window above the running minimum
-            const float mag = cnmax + 2.f * a * bnmax;              // bound on |ŝ|
-            const float E = a * wmax * 1.000001f + mag * 4.7683716e-07f + 1e-37f;  // + cn rounding, fma rounding (2^-21 |ŝ|)
-            const float G = 2.1f * delta * (a + cmaxn) * (a + cmaxn);
-            const float T = (2.f * E + G) * 1.000001f + mag * 2.3841858e-07f;      // + rounding of (m + T) itself
-            float m = __int_as_float(0x7f800000);
+            // per centroid:  L_j = ŝ_j - a w_j <= s_j <= U_j = ŝ_j + a w_j  (up to the rounding slack folded into T2).  With
+            // m = min_j U_j the reference argmin satisfies  L_j <= thr(m) = m + T2 + 2.2 delta max(m + K2, 0):  m + K2 bounds
+            // |x - c_j'|^2 for the j' attaining m, because s_j and d_j differ by exactly |x|^2 - 2 x.mu <= K2.
+            const float na = -a;
+            const float mag = cnmax + 2.f * a * bnmax + a * wmax;                        // bound on |ŝ|, |L|, |U|
+            const float kmag = x2 + 2.f * fabsf(st.y);
+            const float T2 = mag * 9.5367432e-07f + 1e-37f;                              // 2^-20: cn/fma/thr roundings
+            const float K2 = (x2 - 2.f * st.y) + 2.02f * gamma * a * mun + (kmag + mag) * 9.5367432e-07f;
+            float m = inf;
             float fs[FIFO];
             uint32_t fi[FIFO];
 #pragma unroll
             for (int e = 0; e < FIFO; ++e) {
-                fs[e] = __int_as_float(0x7f800000);
+                fs[e] = inf;
                 fi[e] = NONE;
             }
             bool ovf = false;
@@ -375,40 +400,49 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BN;
                 const float4 *cn4 = reinterpret_cast<const float4 *>(p.cn + (size_t)nb * BN);
+                const float4 *wv4 = reinterpret_cast<const float4 *>(p.wv + (size_t)nb * BN);
 #pragma unroll 1
                 for (uint32_t ch = 0; ch < BN / 32; ++ch) {
-                    float v[32];
+                    float v[32], w[32];
                     tmem_ld32(taddr + ch * 32u, v);
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
                         const float4 c = __ldg(cn4 + ch * 8 + i4);
+                        const float4 ww = __ldg(wv4 + ch * 8 + i4);
                         v[4 * i4 + 0] = __fmaf_rn(-2.f, v[4 * i4 + 0], c.x);
                         v[4 * i4 + 1] = __fmaf_rn(-2.f, v[4 * i4 + 1], c.y);
                         v[4 * i4 + 2] = __fmaf_rn(-2.f, v[4 * i4 + 2], c.z);
                         v[4 * i4 + 3] = __fmaf_rn(-2.f, v[4 * i4 + 3], c.w);
+                        w[4 * i4 + 0] = ww.x;
+                        w[4 * i4 + 1] = ww.y;
+                        w[4 * i4 + 2] = ww.z;
+                        w[4 * i4 + 3] = ww.w;
                     }
-                    float cm = v[0];
+                    float cm = inf;
 #pragma unroll
-                    for (int i = 1; i < 32; ++i) cm = fminf(cm, v[i]);
+                    for (int i = 0; i < 32; ++i) cm = fminf(cm, __fmaf_rn(a, w[i], v[i]));   // min U_j
                     m = fminf(m, cm);
-                    const float thr = m + T;
+                    const float thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
                     bool any = false;
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) any |= (v[i] <= thr);
+                    for (int i = 0; i < 32; ++i) {
+                        v[i] = __fmaf_rn(na, w[i], v[i]);                                    // L_j
+                        any |= (v[i] <= thr);
+                    }
                     if (any) {
                         const uint32_t j0 = nb * BN + ch * 32u;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
                             if (v[i] <= thr) {
-                                // push; the slot that falls off must already be outside the window, else give up on the filter
-                                if (fs[FIFO - 1] <= thr) ovf = true;
+                                bool placed = false;  // take any slot whose lower bound has left the window
 #pragma unroll
-                                for (int e = FIFO - 1; e > 0; --e) {
-                                    fs[e] = fs[e - 1];
-                                    fi[e] = fi[e - 1];
+                                for (int e = 0; e < FIFO; ++e) {
+                                    const bool take = !placed && !(fs[e] <= thr);
+                                    fs[e] = take ? v[i] : fs[e];
+                                    fi[e] = take ? j0 + i : fi[e];
+                                    placed |= take;
                                 }
-                                fs[0] = v[i];
-                                fi[0] = j0 + i;
+                                ovf |= !placed;
                             }
                         }
                     }
@@ -417,23 +451,48 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 mbar_arrive(BAR_TEMPTY(as));
             }
             // ---- finalize the row
-            const float thr = m + T;
+            const float thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
             uint32_t nv = 0;
-            uint32_t cand[FIFO];
+            uint32_t only = NONE;
 #pragma unroll
             for (int e = 0; e < FIFO; ++e) {
                 const bool ok = fs[e] <= thr;
-                cand[e] = ok ? fi[e] : NONE;
+                fi[e] = ok ? fi[e] : NONE;
+                only = ok ? fi[e] : only;
                 nv += ok ? 1u : 0u;
             }
-            const bool finite = table_ok && (x2 < 1e30f) && (m < 1e30f) && (m > -1e30f);
-            const bool is_ovf = valid && (ovf || !finite || nv == 0u);
-            const bool is_amb = valid && !is_ovf && nv > 1u;
-            if (valid && !is_ovf && nv == 1u) {
-                uint32_t only = NONE;
+            const bool finite = table_ok && (x2 < 1e30f) && (m < 1e30f) && (m > -1e30f) && (kmag < 1e30f);
+            bool is_ovf = valid && (ovf || !finite || nv == 0u);
+            bool is_amb = valid && !is_ovf && nv > 1u;
+            if (valid && !is_ovf && nv == 1u) p.assign[row] = only;
+            // (row, candidate) pairs of the ambiguous rows: warp-aggregated reservation
+            const uint32_t cnt = is_amb ? nv : 0u;
+            uint32_t incl = cnt;
 #pragma unroll
-                for (int e = 0; e < FIFO; ++e) only = (cand[e] != NONE) ? cand[e] : only;
-                p.assign[row] = only;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((int)lane >= o) incl += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+            uint32_t pbase = 0;
+            if (total) {
+                if (lane == 0) pbase = atomicAdd(&p.counts[2], total);
+                pbase = __shfl_sync(0xffffffffu, pbase, 0);
+            }
+            const bool fits = (u64)pbase + total <= (u64)p.pair_cap;
+            if (is_amb) {
+                uint32_t slot = pbase + incl - cnt;
+#pragma unroll
+                for (int e = 0; e < FIFO; ++e)
+                    if (fi[e] != NONE) {
+                        // a reservation that does not fit leaves sentinels behind and the row takes the full scan
+                        if (slot < p.pair_cap) p.pairs[slot] = fits ? make_uint2((uint32_t)row, fi[e]) : make_uint2(NONE, NONE);
+                        ++slot;
+                    }
+                if (!fits) {
+                    is_amb = false;
+                    is_ovf = true;
+                }
             }
             const uint32_t amb_mask = __ballot_sync(0xffffffffu, is_amb);
             const uint32_t ovf_mask = __ballot_sync(0xffffffffu, is_ovf);
@@ -446,11 +505,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             ovf_base = __shfl_sync(0xffffffffu, ovf_base, 0);
             const uint32_t below = (1u << lane) - 1u;
             if (is_amb) {
-                const uint32_t slot = amb_base + (uint32_t)__popc(amb_mask & below);
-                p.amb_rows[slot] = (uint32_t)row;
-                *reinterpret_cast<uint4 *>(p.amb_cand + (size_t)slot * FIFO) = make_uint4(cand[0], cand[1], cand[2], cand[3]);
+                p.amb_rows[amb_base + (uint32_t)__popc(amb_mask & below)] = (uint32_t)row;
+                p.best[row] = KEY_MAX;
             }
-            if (is_ovf) p.ovf_rows[ovf_base + (uint32_t)__popc(ovf_mask & below)] = (uint32_t)row;
+            if (is_ovf) {
+                p.ovf_rows[ovf_base + (uint32_t)__popc(ovf_mask & below)] = (uint32_t)row;
+                p.best[row] = KEY_MAX;
+            }
         }
     }
     // ---- teardown
@@ -467,83 +528,81 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------
-// exact re-evaluation in the reference order (src/ivf/index.rs:461-480), dim % 4 == 0 on this path
+// exact re-evaluation in the reference order (src/ivf/index.rs:461-480); dim % 4 == 0 on this path.
+// One warp per 32 (row, candidate) pairs, same scheme as group_distance: all lanes load a pair's row and centroid with
+// coalesced 128-bit loads and compute the independent chain terms, the terms are transposed through a padded
+// shared-memory tile, and lane p runs pair p's serial chain.  The per-row winner is an atomicMin over
+// bits(distance) << 32 | candidate: squared distances are >= 0 and finite here, so the u64 order is (distance, index) --
+// the reference's strict-'<' ascending scan (index.rs:251).
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ float4 ldg4(const float *p) { return __ldg(reinterpret_cast<const float4 *>(p)); }
 
-// one thread per ambiguous row: up to FIFO candidates evaluated side by side
-__global__ void __launch_bounds__(128) assign_recheck_kernel(const float *__restrict__ rows, uint32_t dim,
-                                                             const float *__restrict__ cent,
-                                                             const uint32_t *__restrict__ counts,
-                                                             const uint32_t *__restrict__ amb_rows,
-                                                             const uint32_t *__restrict__ amb_cand,
-                                                             uint32_t *__restrict__ assign) {
-    const uint32_t total = counts[0];
-    const uint32_t n4 = dim >> 2;
-    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-        const uint32_t row = amb_rows[i];
-        const uint4 cq = *reinterpret_cast<const uint4 *>(amb_cand + (size_t)i * FIFO);
-        const uint32_t cand[FIFO] = {cq.x, cq.y, cq.z, cq.w};
-        const float *xp = rows + (u64)row * dim;
-        const float *cp[FIFO];
-        float sum[FIFO];
+constexpr int PAIR_WARPS = 8, PAIR_TS = 36;
+
+__global__ void __launch_bounds__(PAIR_WARPS * 32) pair_exact_kernel(const float *__restrict__ rows, uint32_t dim,
+                                                                     const float *__restrict__ cent,
+                                                                     const uint32_t *__restrict__ counts, uint32_t pair_cap,
+                                                                     const uint2 *__restrict__ pairs, u64 *__restrict__ best) {
+    __shared__ __align__(16) float tiles[PAIR_WARPS][32 * PAIR_TS];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float *tile = tiles[wib];
+    const uint32_t npairs = min(counts[2], pair_cap);
+    const uint32_t ngroups = (npairs + 31u) / 32u;
+    const uint32_t ncb = (dim + 127u) / 128u;
+    for (uint32_t g = blockIdx.x * PAIR_WARPS + wib; g < ngroups; g += gridDim.x * PAIR_WARPS) {
+        const uint32_t idx = g * 32u + lane;
+        const uint2 pr = idx < npairs ? pairs[idx] : make_uint2(NONE, NONE);
+        const bool valid = pr.x != NONE;
+        const uint32_t row_l = valid ? pr.x : 0u, cand_l = valid ? pr.y : 0u;
+        float sum = 0.f;
+        for (uint32_t cb = 0; cb < ncb; ++cb) {
+            const uint32_t col = cb * 128u + (lane << 2);
+            const bool inb = col < dim;
 #pragma unroll
-        for (int e = 0; e < FIFO; ++e) {
-            cp[e] = cent + (size_t)(cand[e] == NONE ? 0u : cand[e]) * dim;
-            sum[e] = 0.f;
-        }
-        for (uint32_t c = 0; c < n4; ++c) {
-            const float4 xv = ldg4(xp + 4 * c);
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                float4 xv[8], cv[8];
 #pragma unroll
-            for (int e = 0; e < FIFO; ++e)
-                if (cand[e] != NONE) sum[e] = __fadd_rn(sum[e], chunk4(xv, ldg4(cp[e] + 4 * c)));
-        }
-        float bd = __int_as_float(0x7f800000);
-        uint32_t bi = NONE;
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t rr = __shfl_sync(0xffffffffu, row_l, r0 + j);
+                    const uint32_t cc = __shfl_sync(0xffffffffu, cand_l, r0 + j);
+                    xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    cv[j] = xv[j];
+                    if (inb) {
+                        xv[j] = ldg4(rows + (u64)rr * dim + col);
+                        cv[j] = ldg4(cent + (size_t)cc * dim + col);
+                    }
+                }
 #pragma unroll
-        for (int e = 0; e < FIFO; ++e)
-            if (cand[e] != NONE && (sum[e] < bd || (sum[e] == bd && cand[e] < bi))) {
-                bd = sum[e];
-                bi = cand[e];
+                for (int j = 0; j < 8; ++j) tile[(r0 + j) * PAIR_TS + lane] = chunk4(xv[j], cv[j]);
             }
-        assign[row] = (bi == NONE) ? 0u : bi;  // unreachable NONE: candidate distances are finite on this path
+            __syncwarp();
+            // columns past dim contribute +0.0 terms: x + (+0.0) == x bit for bit for the non-negative partial sums
+            const float4 *tr = reinterpret_cast<const float4 *>(tile + lane * PAIR_TS);
+#pragma unroll
+            for (int t4 = 0; t4 < 8; ++t4) {
+                const float4 t = tr[t4];
+                sum = __fadd_rn(sum, t.x);
+                sum = __fadd_rn(sum, t.y);
+                sum = __fadd_rn(sum, t.z);
+                sum = __fadd_rn(sum, t.w);
+            }
+            __syncwarp();
+        }
+        if (valid) atomicMin(reinterpret_cast<unsigned long long *>(&best[row_l]), ((u64)__float_as_uint(sum) << 32) | (u64)cand_l);
     }
 }
 
-// one warp per overflow row: the full reference scan over all centroids (strict '<' from +inf, default 0)
-__global__ void __launch_bounds__(128) assign_overflow_kernel(const float *__restrict__ rows, uint32_t dim,
-                                                              const float *__restrict__ cent, uint32_t C,
-                                                              const uint32_t *__restrict__ counts,
-                                                              const uint32_t *__restrict__ ovf_rows,
-                                                              uint32_t *__restrict__ assign) {
-    const uint32_t total = counts[1];
-    const uint32_t lane = threadIdx.x & 31;
-    const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = (gridDim.x * blockDim.x) >> 5;
-    const uint32_t n4 = dim >> 2;
-    for (uint32_t i = warp; i < total; i += nwarps) {
-        const uint32_t row = ovf_rows[i];
-        const float *xp = rows + (u64)row * dim;
-        float bd = __int_as_float(0x7f800000);
-        uint32_t bi = NONE;
-        for (uint32_t j = lane; j < C; j += 32) {
-            const float *cp = cent + (size_t)j * dim;
-            float sum = 0.f;
-            for (uint32_t c = 0; c < n4; ++c) sum = __fadd_rn(sum, chunk4(ldg4(xp + 4 * c), ldg4(cp + 4 * c)));
-            if (sum < bd) {
-                bd = sum;
-                bi = j;
-            }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-            const float od = __shfl_xor_sync(0xffffffffu, bd, o);
-            const uint32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
-            if (od < bd || (od == bd && oi < bi)) {
-                bd = od;
-                bi = oi;
-            }
-        }
-        if (lane == 0) assign[row] = (bi == NONE) ? 0u : bi;
+// assign[row] = low word of best[row] for the rows of both lists (ambiguous: pair_exact_kernel; overflow: the sliced exact
+// scan).  KEY_MAX means no finite distance won: the reference's default, cluster 0 (index.rs:245).
+__global__ void __launch_bounds__(256) best_finalize_kernel(const uint32_t *__restrict__ counts,
+                                                            const uint32_t *__restrict__ amb_rows,
+                                                            const uint32_t *__restrict__ ovf_rows,
+                                                            const u64 *__restrict__ best, uint32_t *__restrict__ assign) {
+    const uint32_t na = counts[0], total = na + counts[1];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t row = i < na ? amb_rows[i] : ovf_rows[i - na];
+        const uint32_t c = (uint32_t)(best[row] & 0xFFFFFFFFull);
+        assign[row] = (c == NONE) ? 0u : c;
     }
 }
 

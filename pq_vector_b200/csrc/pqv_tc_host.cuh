@@ -71,13 +71,15 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     const uint32_t num_nb = (C + T::BN - 1) / T::BN;
     const uint32_t num_kb = (dim + T::BK - 1) / T::BK;
     const uint32_t cn_len = num_nb * T::BN;
+    const u64 pair_cap64 = std::min<u64>(4 * n + 1024, 0xFFFFFFF0ull);
     PQV_TRY(D.tc_bp.ensure((size_t)C * dim));
     PQV_TRY(D.tc_mu.ensure(dim));
-    PQV_TRY(D.tc_cn.ensure(cn_len));
-    PQV_TRY(D.tc_x2.ensure(n));
+    PQV_TRY(D.tc_cn.ensure(2 * (size_t)cn_len));
+    PQV_TRY(D.tc_stats.ensure(n));
     PQV_TRY(D.tc_u32.ensure(8));
     PQV_TRY(D.tc_amb_rows.ensure(n));
-    PQV_TRY(D.tc_amb_cand.ensure((size_t)n * T::FIFO));
+    PQV_TRY(D.tc_pairs.ensure(pair_cap64));
+    PQV_TRY(D.tc_best.ensure(n));
     PQV_TRY(D.tc_ovf_rows.ensure(n));
     uint32_t *bounds = D.tc_u32.p, *counts = D.tc_u32.p + 4;
 
@@ -93,22 +95,26 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     PQV_TRY(make_row_tmap(&tmB, D.tc_bp.p, C, dim, T::BN));
 
     if (time_it) CU_TRY(cudaEventRecord(D.ev[0], D.stream));
+    CU_TRY(cudaMemsetAsync(D.tc_u32.p, 0, 8 * sizeof(uint32_t), D.stream));
     T::centroid_mean_kernel<<<(dim + 127) / 128, 128, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, bounds);
-    T::centroid_prep_kernel<<<cn_len, 128, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, D.tc_bp.p, D.tc_cn.p, cn_len, bounds);
-    T::row_norm_kernel<<<(uint32_t)D.sm_count * 8, 256, 0, D.stream>>>(d_rows, n, dim, D.tc_x2.p);
-    CU_TRY(cudaMemsetAsync(counts, 0, 4 * sizeof(uint32_t), D.stream));
+    T::centroid_prep_kernel<<<cn_len, 128, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, D.tc_bp.p, D.tc_cn.p, D.tc_cn.p + cn_len,
+                                                              cn_len, bounds);
+    T::row_stats_kernel<<<(uint32_t)D.sm_count * 8, 256, 0, D.stream>>>(d_rows, n, dim, D.tc_mu.p, D.tc_stats.p);
     CU_TRY(cudaGetLastError());
 
     T::AssignTcParams p;
-    p.x2 = D.tc_x2.p;
+    p.stats = D.tc_stats.p;
     p.cn = D.tc_cn.p;
+    p.wv = D.tc_cn.p + cn_len;
     p.bounds = bounds;
     p.assign = d_out;
     p.counts = counts;
     p.amb_rows = D.tc_amb_rows.p;
-    p.amb_cand = D.tc_amb_cand.p;
+    p.pairs = D.tc_pairs.p;
+    p.best = D.tc_best.p;
     p.ovf_rows = D.tc_ovf_rows.p;
     p.n = n;
+    p.pair_cap = (uint32_t)pair_cap64;
     p.dim = dim;
     p.C = C;
     p.num_mb = num_mb;
@@ -119,9 +125,17 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     T::assign_tc_kernel<<<grid, T::THREADS, T::SMEM_BYTES, D.stream>>>(tmA, tmB, p);
     CU_TRY(cudaGetLastError());
     if (time_it) CU_TRY(cudaEventRecord(D.ev[2], D.stream));
-    T::assign_recheck_kernel<<<(uint32_t)D.sm_count * 8, 128, 0, D.stream>>>(d_rows, dim, d_cent, counts, D.tc_amb_rows.p,
-                                                                           D.tc_amb_cand.p, d_out);
-    T::assign_overflow_kernel<<<(uint32_t)D.sm_count * 4, 128, 0, D.stream>>>(d_rows, dim, d_cent, C, counts, D.tc_ovf_rows.p,
+    // exact f32 chains: one per (row, candidate) pair of the ambiguous rows; the full scan for the overflow rows
+    T::pair_exact_kernel<<<(uint32_t)D.sm_count * 4, T::PAIR_WARPS * 32, 0, D.stream>>>(d_rows, dim, d_cent, counts, p.pair_cap,
+                                                                                     D.tc_pairs.p, D.tc_best.p);
+    if (time_it) CU_TRY(cudaEventRecord(D.ev[4], D.stream));
+    {
+        const uint32_t slice_len = 2 * pqv::AS_BN;
+        dim3 grid_ovf((uint32_t)((n + pqv::AS_BM - 1) / pqv::AS_BM), (C + slice_len - 1) / slice_len);
+        pqv::kmeans_assign_kernel<true, true><<<grid_ovf, 256, 0, D.stream>>>(d_rows, 0, dim, d_cent, C, nullptr, D.tc_ovf_rows.p,
+                                                                              counts + 1, D.tc_best.p, slice_len);
+    }
+    T::best_finalize_kernel<<<(uint32_t)D.sm_count * 2, 256, 0, D.stream>>>(counts, D.tc_amb_rows.p, D.tc_ovf_rows.p, D.tc_best.p,
                                                                             d_out);
     CU_TRY(cudaGetLastError());
     if (time_it) CU_TRY(cudaEventRecord(D.ev[3], D.stream));
@@ -138,6 +152,7 @@ int assign_dispatch(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, co
     if (time_it) CU_TRY(cudaEventRecord(D.ev[1], D.stream));
     PQV_TRY(assign_simt(D, d_rows, n, dim, d_cent, C, d_out));
     if (time_it) CU_TRY(cudaEventRecord(D.ev[2], D.stream));
+    if (time_it) CU_TRY(cudaEventRecord(D.ev[4], D.stream));
     if (time_it) CU_TRY(cudaEventRecord(D.ev[3], D.stream));
     return PQV_OK;
 }
@@ -148,6 +163,8 @@ void record_assign_timing(pqv_ctx *ctx, DeviceState &D, int path, u64 rows, cons
     cudaEventElapsedTime(&prep, D.ev[0], D.ev[1]);
     cudaEventElapsedTime(&filt, D.ev[1], D.ev[2]);
     cudaEventElapsedTime(&post, D.ev[2], D.ev[3]);
+    float pair_ms = 0.f;
+    cudaEventElapsedTime(&pair_ms, D.ev[2], D.ev[4]);
     pqv_assign_timing &t = ctx->last_assign;
     if (first_piece) t = pqv_assign_timing{};
     t.path = (uint32_t)path;
@@ -157,6 +174,7 @@ void record_assign_timing(pqv_ctx *ctx, DeviceState &D, int path, u64 rows, cons
     t.prep_ms += prep;
     t.filter_ms += filt;
     t.recheck_ms += post;
+    t.pair_ms += pair_ms;
     t.total_ms += (double)prep + filt + post;
 }
 
