@@ -88,6 +88,24 @@ PQV_API int pqv_dataset_read(pqv_ctx *ctx, uint64_t handle, uint64_t first_row, 
  * Output i of query q is at out_*[q*k + i]; out_count[q] <= k results are valid, ascending. */
 PQV_API int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k,
                 uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count);
+/* With n_queries >= 4 (single-device dataset, dim % 4 == 0) pqv_l2_topk answers the whole batch in one tensor-core pass
+ * over the table (tcgen05 tf32 filter + exact re-rank of the survivors); every query's output is
+ * still identical to its own single-query call.  PQV_BATCH=off in the environment disables the batched pass. */
+typedef struct {
+    uint32_t queries;      /* batch size of the last pqv_l2_topk call (0: batched pass not used)                        */
+    uint32_t declined;     /* 1: batch abandoned (non-finite inputs, candidate buffers full) -> single-query scans      */
+    uint32_t tie_queries;  /* queries re-run through the single-query path (order hinges on the reference heap layout) */
+    uint32_t reserved;
+    uint64_t rows;
+    uint64_t sample_rows;  /* rows of the threshold pass                                                               */
+    uint64_t candidates;   /* (row, query) pairs re-evaluated exactly                                                  */
+    double prep_ms;        /* query rounding + row norms                                                               */
+    double sample_ms;      /* tcgen05 pass over the sample rows + per-query threshold selection                        */
+    double filter_ms;      /* tcgen05 pass over all rows                                                               */
+    double rerank_ms;      /* exact distances of the candidates + per-query top-k selection                            */
+    double total_ms;
+} pqv_batch_timing;
+PQV_API int pqv_last_batch_timing(pqv_ctx *ctx, pqv_batch_timing *out);
 PQV_API int pqv_l2_topk_gather(pqv_ctx *ctx, uint64_t handle, const float *query, const uint32_t *row_ids,
                        uint64_t n_ids, uint32_t k, uint32_t flags, uint32_t *out_row_idx, float *out_dist,
                        uint32_t *out_count);

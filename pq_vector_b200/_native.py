@@ -27,6 +27,12 @@ class PqvAssignTiming(C.Structure):
                 ("total_ms", C.c_double)]
 
 
+class PqvBatchTiming(C.Structure):
+    _fields_ = [("queries", C.c_uint32), ("declined", C.c_uint32), ("tie_queries", C.c_uint32), ("reserved", C.c_uint32),
+                ("rows", C.c_uint64), ("sample_rows", C.c_uint64), ("candidates", C.c_uint64), ("prep_ms", C.c_double),
+                ("sample_ms", C.c_double), ("filter_ms", C.c_double), ("rerank_ms", C.c_double), ("total_ms", C.c_double)]
+
+
 f32p, f64p = C.POINTER(C.c_float), C.POINTER(C.c_double)
 u32p, u64p = C.POINTER(C.c_uint32), C.POINTER(C.c_uint64)
 ctxp = C.c_void_p
@@ -67,6 +73,7 @@ SIGNATURES = {
                                          u64p]),
     "pqv_replay_candidates": (C.c_int, [u64p, C.c_uint64, u32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),
     "pqv_last_timing": (C.c_int, [ctxp, C.POINTER(PqvTiming)]),
+    "pqv_last_batch_timing": (C.c_int, [ctxp, C.POINTER(PqvBatchTiming)]),
     "pqv_last_assign_timing": (C.c_int, [ctxp, C.POINTER(PqvAssignTiming)]),
     "pqv_bench_assign": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32,
                                    C.POINTER(PqvAssignTiming), u32p]),

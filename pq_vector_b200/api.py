@@ -141,6 +141,12 @@ class Context:
     def topk_stream(self, query, k, flags=N.PQV_SUM_SEQ) -> "TopkStream":
         return TopkStream(self, query, k, flags)
 
+    def last_batch_timing(self) -> dict:
+        """What the batched pass of the last l2_topk_batch / pqv_l2_topk call did (queries == 0: not used)."""
+        t = N.PqvBatchTiming()
+        _check(_lib.pqv_last_batch_timing(self._h, C.byref(t)))
+        return {f: getattr(t, f) for f, _ in N.PqvBatchTiming._fields_ if f != "reserved"}
+
     def last_assign_timing(self) -> dict:
         """What the last kmeans_assign / bench_assign did: path (1 = tcgen05 filter), ambiguous/overflow rows, ms."""
         t = N.PqvAssignTiming()

@@ -225,6 +225,12 @@ struct DeviceState {
     DevBuf<uint2> tc_pairs;
     DevBuf<u64> tc_best;
     DevBuf<uint32_t> tc_u32, tc_amb_rows, tc_ovf_rows;
+    // batched top-k scratch
+    DevBuf<float> tb_Q, tb_Qp, tb_qf, tb_U;
+    DevBuf<uint32_t> tb_u32, tb_info;
+    DevBuf<uint2> tb_cand;
+    DevBuf<u64> tb_seg, tb_keys;
+    PinBuf<u64> h_batch_keys;
     PinBuf<u64> h_ent_out, h_final;
     PinBuf<float> h_query;
 };
@@ -269,6 +275,7 @@ struct pqv_ctx {
     std::mutex mu;
     pqv_timing last{};
     pqv_assign_timing last_assign{};
+    pqv_batch_timing last_batch{};
     int occ_override = 0;
     int scan_variant = 0;
 };
@@ -748,6 +755,16 @@ void pqv_destroy(pqv_ctx *ctx) {
         D.tc_u32.release();
         D.tc_amb_rows.release();
         D.tc_ovf_rows.release();
+        D.tb_Q.release();
+        D.tb_Qp.release();
+        D.tb_qf.release();
+        D.tb_U.release();
+        D.tb_u32.release();
+        D.tb_info.release();
+        D.tb_cand.release();
+        D.tb_seg.release();
+        D.tb_keys.release();
+        D.h_batch_keys.release();
         D.h_ent_out.release();
         D.h_final.release();
         D.h_query.release();
@@ -923,9 +940,26 @@ int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_
     Dataset *ds = find_dataset(ctx, handle);
     if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
     PQV_TRY(check_topk_args(k, ds->dim, flags));
+    // several queries: one tensor-core pass over the table answers every query whose result does not hinge on the
+    // reference heap's layout (pqv_tc.cuh); the rest -- and small batches -- take the single-query scan
+    std::vector<uint8_t> handled(n_queries, 0);
+    ctx->last_batch = pqv_batch_timing{};
+    if (n_queries && ds->n_rows && batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k)) {
+        DeviceState &D = ctx->devs[ds->shards[0].di];
+        DevGuard guard(D.dev);
+        PQV_TRY(batch_topk(ctx, D, ds->shards[0].d_data, ds->n_rows, ds->dim, queries, n_queries, k, flags, out_row_idx, out_dist,
+                           out_count, handled));
+    }
     for (uint32_t q = 0; q < n_queries; ++q)
-        PQV_TRY(topk_one(ctx, *ds, queries + (size_t)q * ds->dim, nullptr, 0, k, flags, out_row_idx + (size_t)q * k,
-                         out_dist + (size_t)q * k, out_count + q));
+        if (!handled[q])
+            PQV_TRY(topk_one(ctx, *ds, queries + (size_t)q * ds->dim, nullptr, 0, k, flags, out_row_idx + (size_t)q * k,
+                             out_dist + (size_t)q * k, out_count + q));
+    return PQV_OK;
+}
+
+int pqv_last_batch_timing(pqv_ctx *ctx, pqv_batch_timing *out) {
+    if (!ctx || !out) return fail(PQV_EINVAL, "null argument");
+    *out = ctx->last_batch;
     return PQV_OK;
 }
 

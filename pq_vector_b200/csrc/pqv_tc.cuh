@@ -278,22 +278,49 @@ struct AssignTcParams {
     u64 n;
     uint32_t pair_cap;
     uint32_t dim, C;
-    uint32_t num_mb, num_nb, num_kb;
 };
 
+// barrier i at bar0 + 8 i: full[STAGES], empty[STAGES], tfull[2], tempty[2]; then the TMEM base-address slot and a u32
+// scratch counter for the epilogue
+#define BAR_FULL(s) (bar0 + 8u * (uint32_t)(s))
+#define BAR_EMPTY(s) (bar0 + 8u * (uint32_t)(STAGES + (s)))
+#define BAR_TFULL(a) (bar0 + 8u * (uint32_t)(2 * STAGES + (a)))
+#define BAR_TEMPTY(a) (bar0 + 8u * (uint32_t)(2 * STAGES + 2 + (a)))
+
+struct GemmShape {
+    uint32_t num_mb, num_nb, num_kb;  // 128-row tiles of A, 256-row tiles of B, 32-column k blocks
+};
+
+// what an epilogue warp needs: barrier base, TMEM base, its TMEM lane quarter, and the CTA's scratch counter
+struct EpiCtx {
+    uint32_t bar0, tmem_base, q, lane;
+    uint32_t *counter;  // shared memory, zeroed before the roles start
+    // wait for accumulator `tile` of this CTA; returns the TMEM address of this warp's 32 lanes x BN columns
+    __device__ __forceinline__ uint32_t acquire(uint32_t tile) const {
+        const uint32_t as = tile & 1u, aph = (tile >> 1) & 1u;
+        mbar_wait(BAR_TFULL(as), aph);
+        tc_fence_after();
+        return tmem_base + ((q * 32u) << 16) + as * BN;
+    }
+    __device__ __forceinline__ void release(uint32_t tile) const {
+        tc_fence_before();
+        mbar_arrive(BAR_TEMPTY(tile & 1u));
+    }
+};
+
+// D[128 x 256 per tile] = A[rows x dim] . B[table x dim]^T in tf32 on the tensor cores, persistent over the row tiles of A;
+// Epi::run consumes every accumulator tile straight from TMEM (nothing of D is ever written to memory as a matrix).
+template <class Epi>
 __global__ void __launch_bounds__(THREADS, 1)
-assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const AssignTcParams p) {
+tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
+                       const typename Epi::Params p) {
     extern __shared__ uint8_t smem_raw[];
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t bar0 = base + STAGES * STAGE_BYTES;
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    // barrier i at bar0 + 8 i: full[STAGES], empty[STAGES], tfull[2], tempty[2]; then the TMEM base-address slot
-#define BAR_FULL(s) (bar0 + 8u * (uint32_t)(s))
-#define BAR_EMPTY(s) (bar0 + 8u * (uint32_t)(STAGES + (s)))
-#define BAR_TFULL(a) (bar0 + 8u * (uint32_t)(2 * STAGES + (a)))
-#define BAR_TEMPTY(a) (bar0 + 8u * (uint32_t)(2 * STAGES + 2 + (a)))
     const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
+    uint32_t *const counter = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot + 8u - raw));
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -306,6 +333,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_init(BAR_TFULL(a), 1);
             mbar_init(BAR_TEMPTY(a), 128);
         }
+        *counter = 0u;
         fence_barrier_init();
     }
     if (warp == 1) {
@@ -321,9 +349,9 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===== TMA producer =====
         if (lane == 0) {
             uint32_t it = 0;
-            for (uint32_t mb = blockIdx.x; mb < p.num_mb; mb += gridDim.x)
-                for (uint32_t nb = 0; nb < p.num_nb; ++nb)
-                    for (uint32_t kb = 0; kb < p.num_kb; ++kb, ++it) {
+            for (uint32_t mb = blockIdx.x; mb < g.num_mb; mb += gridDim.x)
+                for (uint32_t nb = 0; nb < g.num_nb; ++nb)
+                    for (uint32_t kb = 0; kb < g.num_kb; ++kb, ++it) {
                         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                         mbar_wait(BAR_EMPTY(s), ph ^ 1u);
                         mbar_expect_tx(BAR_FULL(s), STAGE_BYTES);
@@ -337,13 +365,13 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // ===== MMA issuer (one thread) =====
         if (lane == 0) {
             uint32_t it = 0, tile = 0;
-            for (uint32_t mb = blockIdx.x; mb < p.num_mb; mb += gridDim.x)
-                for (uint32_t nb = 0; nb < p.num_nb; ++nb, ++tile) {
+            for (uint32_t mb = blockIdx.x; mb < g.num_mb; mb += gridDim.x)
+                for (uint32_t nb = 0; nb < g.num_nb; ++nb, ++tile) {
                     const uint32_t as = tile & 1u, aph = (tile >> 1) & 1u;
                     mbar_wait(BAR_TEMPTY(as), aph ^ 1u);  // epilogue has drained this accumulator stage
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + as * BN;
-                    for (uint32_t kb = 0; kb < p.num_kb; ++kb, ++it) {
+                    for (uint32_t kb = 0; kb < g.num_kb; ++kb, ++it) {
                         const uint32_t s = it % STAGES, ph = (it / STAGES) & 1u;
                         mbar_wait(BAR_FULL(s), ph);
                         tc_fence_after();
@@ -359,8 +387,25 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
         __syncwarp();
     } else {
-        // ===== epilogue: one row per thread; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
-        const uint32_t q = warp & 3u;
+        // ===== epilogue warps: one row per thread; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
+        Epi::run(EpiCtx{bar0, tmem_base, warp & 3u, lane, counter}, g, p);
+    }
+    // ---- teardown
+    tc_fence_before();
+    __syncthreads();
+    if (threadIdx.x == 0) Epi::finish(counter, p);
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, TMEM_COLS);
+    }
+}
+
+// epilogue of the k-means assignment filter (see the header of this file)
+struct AssignEpi {
+    typedef AssignTcParams Params;
+    static __device__ __forceinline__ void finish(uint32_t *, const Params &) {}
+    static __device__ void run(const EpiCtx c, const GemmShape g, const Params &p) {
+        const uint32_t q = c.q, lane = c.lane;
         const uint32_t row_in_tile = q * 32u + lane;
         const float wmax = __uint_as_float(p.bounds[0]), cnmax = __uint_as_float(p.bounds[1]);
         const float bnmax = __uint_as_float(p.bounds[2]);
@@ -371,7 +416,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool table_ok = (cnmax < 1e30f) && (wmax < 1e30f) && (mun < 1e30f);
         const float inf = __int_as_float(0x7f800000);
         uint32_t tile = 0;
-        for (uint32_t mb = blockIdx.x; mb < p.num_mb; mb += gridDim.x) {
+        for (uint32_t mb = blockIdx.x; mb < g.num_mb; mb += gridDim.x) {
             const u64 row = (u64)mb * BM + row_in_tile;
             const bool valid = row < p.n;
             const float2 st = valid ? p.stats[row] : make_float2(0.f, 0.f);
@@ -394,11 +439,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 fi[e] = NONE;
             }
             bool ovf = false;
-            for (uint32_t nb = 0; nb < p.num_nb; ++nb, ++tile) {
-                const uint32_t as = tile & 1u, aph = (tile >> 1) & 1u;
-                mbar_wait(BAR_TFULL(as), aph);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + ((q * 32u) << 16) + as * BN;
+            for (uint32_t nb = 0; nb < g.num_nb; ++nb, ++tile) {
+                const uint32_t taddr = c.acquire(tile);
                 const float4 *cn4 = reinterpret_cast<const float4 *>(p.cn + (size_t)nb * BN);
                 const float4 *wv4 = reinterpret_cast<const float4 *>(p.wv + (size_t)nb * BN);
 #pragma unroll 1
@@ -447,8 +489,7 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                         }
                     }
                 }
-                tc_fence_before();
-                mbar_arrive(BAR_TEMPTY(as));
+                c.release(tile);
             }
             // ---- finalize the row
             const float thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
@@ -514,18 +555,8 @@ assign_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
         }
     }
-    // ---- teardown
-    tc_fence_before();
-    __syncthreads();
-    if (warp == 1) {
-        tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
-    }
-#undef BAR_FULL
-#undef BAR_EMPTY
-#undef BAR_TFULL
-#undef BAR_TEMPTY
-}
+};
+
 
 // ------------------------------------------------------------------------------------------------
 // exact re-evaluation in the reference order (src/ivf/index.rs:461-480); dim % 4 == 0 on this path.
@@ -605,6 +636,418 @@ __global__ void __launch_bounds__(256) best_finalize_kernel(const uint32_t *__re
         assign[row] = (c == NONE) ? 0u : c;
     }
 }
+
+
+// ================================================================================================
+// Batched brute-force top-k: nq independent single-query searches (src/ivf/search.rs:112-141, src/df_vector/exec.rs:
+// 257-277) answered in ONE pass over the table.  The reference has no batched entry point; every query's
+// result must equal the single-query loop's.  The row tile x query tile contraction runs on the tensor cores as a filter:
+//
+//   s_rq := |x_r|^2 - 2 x_r.q            = d_true(r, q) - |q|^2   (per-query constant shift)
+//   ŝ_rq := x2c_r - 2 tf32_mma(x_r, Q'_q)                         Q'_q = tf32_rn(q)
+//   |ŝ - s| <= a_r w_q + rho_r            a_r >= |x_r|, w_q = 2 (eps_mma |Q'_q| + |q - Q'_q|), rho_r: norm/rounding slack
+//
+//   phase A (BATCH_SAMPLE): U_rq = ŝ + a_r w_q + rho_r >= s_rq for the first S rows; theta_q = k-th smallest U over them
+//                           (+ the reference's own f32 rounding, 2.2 delta d): no row outside {s_rq <= theta_q} can be
+//                           among the reference's k smallest distances, ties at the boundary included.
+//   phase B (BATCH_FILTER): every (row, query) with  ŝ - a_r w_q - rho_r <= theta_q  is appended to the CTA's candidate
+//                           region; pair_dist_kernel then evaluates the exact serial-order f32 distance of each candidate
+//                           and topk_select_kernel keeps the k + 1 smallest (distance, row) keys per query.
+// A query whose k + 1 smallest keys hold a boundary tie (d_k == d_k+1) or whose k returned values are not pairwise
+// distinct is re-run through the single-query path: only there does the order depend on the reference heap's layout.
+// ================================================================================================
+enum { BATCH_SAMPLE = 0, BATCH_FILTER = 1 };
+constexpr uint32_t FLAG_NONFINITE_ROW = 1u, FLAG_REGION_FULL = 2u;
+
+// per query: Q' = tf32_rn(q), w_q, q2 = |q|^2 rounded up; qbounds[0] = max_q |Q'_q|
+__global__ void __launch_bounds__(128) query_prep_kernel(const float *__restrict__ Q, uint32_t nq, uint32_t dim,
+                                                         float *__restrict__ Qp, float *__restrict__ qw,
+                                                         float *__restrict__ q2, uint32_t nq_pad,
+                                                         uint32_t *__restrict__ qbounds) {
+    const uint32_t j = blockIdx.x;
+    __shared__ double red[3][4];
+    if (j >= nq) {
+        if (threadIdx.x == 0 && j < nq_pad) {
+            qw[j] = 0.f;
+            q2[j] = 0.f;
+        }
+        return;
+    }
+    double r2 = 0.0, b2 = 0.0, c2 = 0.0;
+    for (uint32_t col = threadIdx.x; col < dim; col += blockDim.x) {
+        const float c = Q[(size_t)j * dim + col];
+        const float b = tf32_rn(c);
+        Qp[(size_t)j * dim + col] = b;
+        const double r = (double)c - (double)b;
+        r2 += r * r;
+        b2 += (double)b * (double)b;
+        c2 += (double)c * (double)c;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+        b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+        c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    }
+    const uint32_t w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    if (l == 0) {
+        red[0][w] = r2;
+        red[1][w] = b2;
+        red[2][w] = c2;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        r2 = red[0][0] + red[0][1] + red[0][2] + red[0][3];
+        b2 = red[1][0] + red[1][1] + red[1][2] + red[1][3];
+        c2 = red[2][0] + red[2][1] + red[2][2] + red[2][3];
+        const double up = 1.0 + 1e-6;
+        const double bn = sqrt(b2) * up, rn = sqrt(r2) * up + 1e-300;
+        const double eps = ldexp(1.0, -10) + ((double)(dim / 8 + 4)) * ldexp(1.0, -19);  // as centroid_prep_kernel
+        qw[j] = (float)(2.0 * (eps * bn + rn) * up);
+        q2[j] = (float)(c2 * up);
+        atomicMax(&qbounds[0], __float_as_uint((float)bn));
+    }
+}
+
+struct BatchParams {
+    const float2 *stats;     // [n] (.x = |x|^2 in f32, row_stats_kernel)
+    const float *qw;         // [nq_pad] w_q, 0 padded
+    const float *qtheta;     // [nq_pad] theta_q (-inf padded)                       BATCH_FILTER
+    const uint32_t *qbounds; // [0] = max_q |Q'_q| (f32 bits)
+    float *U;                // [nq_pad][ldU] upper bounds of s over the sample rows   BATCH_SAMPLE
+    uint32_t ldU;
+    uint2 *cand;             // [gridDim.x][region_cap] (row, query)                   BATCH_FILTER
+    uint32_t region_cap;
+    uint32_t *region_count;  // [gridDim.x]
+    uint32_t *flags;         // FLAG_*
+    u64 n;                   // rows covered by this launch
+    uint32_t dim;
+};
+
+template <int MODE>
+struct BatchEpi {
+    typedef BatchParams Params;
+    static __device__ __forceinline__ void finish(uint32_t *counter, const Params &p) {
+        if (MODE == BATCH_FILTER) p.region_count[blockIdx.x] = min(*counter, p.region_cap);
+    }
+    static __device__ void run(const EpiCtx c, const GemmShape g, const Params &p) {
+        const uint32_t lane = c.lane;
+        const uint32_t row_in_tile = c.q * 32u + lane;
+        const float bnmax = __uint_as_float(p.qbounds[0]);
+        const float gamma = (float)(p.dim + 32) * 5.9604645e-08f;  // f32 summation error of row_stats_kernel
+        uint2 *const region = (MODE == BATCH_FILTER) ? p.cand + (size_t)blockIdx.x * p.region_cap : nullptr;
+        uint32_t tile = 0;
+        for (uint32_t mb = blockIdx.x; mb < g.num_mb; mb += gridDim.x) {
+            const u64 row = (u64)mb * BM + row_in_tile;
+            const bool valid = row < p.n;
+            const float x2c = valid ? p.stats[row].x : 0.f;
+            if (MODE == BATCH_FILTER && valid && !(x2c < 1e30f)) atomicOr(p.flags, FLAG_NONFINITE_ROW);
+            const float x2hi = x2c * (1.f + 2.f * gamma) + 1e-37f;
+            const float a = sqrtf(x2hi) * 1.000001f;
+            const float rho = 1.5f * gamma * x2hi + (x2hi + 2.f * a * bnmax) * 9.5367432e-07f + 1e-37f;
+            const float x2s = (MODE == BATCH_SAMPLE) ? x2c + rho : x2c - rho;
+            for (uint32_t nb = 0; nb < g.num_nb; ++nb, ++tile) {
+                const uint32_t taddr = c.acquire(tile);
+                const float4 *w4 = reinterpret_cast<const float4 *>(p.qw + (size_t)nb * BN);
+                const float4 *t4 = reinterpret_cast<const float4 *>(p.qtheta + (size_t)nb * BN);
+#pragma unroll 1
+                for (uint32_t ch = 0; ch < BN / 32; ++ch) {
+                    float v[32];
+                    tmem_ld32(taddr + ch * 32u, v);
+                    const uint32_t q0 = nb * BN + ch * 32u;
+                    if (MODE == BATCH_SAMPLE) {
+#pragma unroll
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 ww = __ldg(w4 + ch * 8 + i4);
+                            const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const float u = __fmaf_rn(a, wv[e], __fmaf_rn(-2.f, v[4 * i4 + e], x2s));
+                                if (valid) p.U[(size_t)(q0 + 4 * i4 + e) * p.ldU + row] = u;  // lanes = consecutive rows: coalesced
+                            }
+                        }
+                    } else {
+                        uint32_t mask = 0;
+#pragma unroll
+                        for (int i4 = 0; i4 < 8; ++i4) {
+                            const float4 ww = __ldg(w4 + ch * 8 + i4);
+                            const float4 tt = __ldg(t4 + ch * 8 + i4);
+                            const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+                            const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                const bool hit = __fmaf_rn(-2.f, v[4 * i4 + e], x2s) <= __fmaf_rn(a, wv[e], tv[e]);
+                                mask |= hit ? (1u << (4 * i4 + e)) : 0u;
+                            }
+                        }
+                        if (!valid) mask = 0;
+                        if (__any_sync(0xffffffffu, mask != 0u)) {
+                            const uint32_t cnt = (uint32_t)__popc(mask);
+                            uint32_t incl = cnt;
+#pragma unroll
+                            for (int o = 1; o < 32; o <<= 1) {
+                                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                                if ((int)lane >= o) incl += t;
+                            }
+                            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                            uint32_t base = 0;
+                            if (lane == 0) base = atomicAdd(c.counter, total);
+                            base = __shfl_sync(0xffffffffu, base, 0);
+                            uint32_t slot = base + incl - cnt;
+                            while (mask) {
+                                const uint32_t i = (uint32_t)__ffs(mask) - 1u;
+                                mask &= mask - 1u;
+                                if (slot < p.region_cap) region[slot] = make_uint2((uint32_t)row, q0 + i);
+                                else atomicOr(p.flags, FLAG_REGION_FULL);
+                                ++slot;
+                            }
+                        }
+                    }
+                }
+                c.release(tile);
+            }
+        }
+    }
+};
+
+// order-preserving map of f32 bit patterns onto u32 (negative values below positive ones)
+__device__ __forceinline__ uint32_t f32_ordered(float f) {
+    const uint32_t u = __float_as_uint(f);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float f32_unordered(uint32_t o) {
+    return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
+}
+
+// one CTA per query: theta_q from the k-th smallest of U[q][0..S) (MSB-first radix select, 4 passes of 8 bits), then
+//   theta_q = th + (2^-20 + 2.2 delta) max(th + q2_q, 0) + rounding slack      (header of this section)
+// queries >= nq (padding) get -inf so that they never produce candidates.  S < k: +inf (every row is a candidate).
+__global__ void __launch_bounds__(256) theta_select_kernel(const float *__restrict__ U, uint32_t ldU, uint32_t S, uint32_t k,
+                                                           uint32_t nq, const float *__restrict__ q2, float delta,
+                                                           float *__restrict__ qtheta) {
+    const uint32_t q = blockIdx.x;
+    if (q >= nq) {
+        if (threadIdx.x == 0) qtheta[q] = __int_as_float(0xff800000);
+        return;
+    }
+    if (S < k) {
+        if (threadIdx.x == 0) qtheta[q] = __int_as_float(0x7f800000);
+        return;
+    }
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_remaining;
+    const float *u = U + (size_t)q * ldU;
+    if (threadIdx.x == 0) {
+        s_prefix = 0u;
+        s_remaining = k;  // rank (1-based) of the wanted element among those matching the prefix
+    }
+    for (int pass = 3; pass >= 0; --pass) {
+        hist[threadIdx.x] = 0u;
+        __syncthreads();
+        const uint32_t prefix = s_prefix;
+        const uint32_t shift = 8u * (uint32_t)pass;
+        const uint32_t himask = (pass == 3) ? 0u : (0xFFFFFFFFu << (shift + 8u));
+        for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
+            const uint32_t o = f32_ordered(u[i]);
+            if ((o & himask) == prefix) atomicAdd(&hist[(o >> shift) & 0xFFu], 1u);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            uint32_t rem = s_remaining, b = 0;
+            for (; b < 256; ++b) {
+                if (hist[b] >= rem) break;
+                rem -= hist[b];
+            }
+            b = b < 256 ? b : 255;
+            s_prefix = prefix | (b << shift);
+            s_remaining = rem;
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const float th = f32_unordered(s_prefix);
+        const float qq = q2[q];
+        const float d = fmaxf(th + qq, 0.f);
+        qtheta[q] = th + (9.5367432e-07f + 2.2f * delta) * d + (fabsf(th) + qq) * 9.5367432e-07f + 1e-37f;
+    }
+}
+
+// Exact squared distance of every candidate (row, query) pair in the reference's operation order; the result goes to the
+// query's key segment as bits(distance) << 32 | row.  One warp per 32 pairs, transposed through a padded shared tile
+// exactly like group_distance / pair_exact_kernel.
+//   ORDER 0: src/ivf/index.rs:461-480      sum += ((d0^2 + d1^2) + d2^2) + d3^2   (one chain term per 4 columns)
+//   ORDER 1: src/df_vector/exec.rs:529-533 dist += diff * diff                    (one chain term per column)
+template <int ORDER>
+struct PairCfg {
+    static constexpr int TERMS = ORDER == 1 ? 4 : 1;       // chain terms per lane per 128-column block
+    static constexpr int TS = 32 * TERMS + 4;              // tile row stride (floats); TS/4 odd -> conflict-free LDS.128
+    static constexpr int WARPS = ORDER == 1 ? 2 : 8;       // static shared memory <= 48 KB
+};
+
+template <int ORDER>
+__global__ void __launch_bounds__(PairCfg<ORDER>::WARPS * 32)
+pair_dist_kernel(const float *__restrict__ rows, uint32_t dim, const float *__restrict__ Q,
+                 const uint2 *__restrict__ cand, uint32_t region_cap, const uint32_t *__restrict__ region_count,
+                 u64 *__restrict__ seg, uint32_t cap_q, uint32_t *__restrict__ cntq) {
+    constexpr int TS = PairCfg<ORDER>::TS, WARPS = PairCfg<ORDER>::WARPS, TERMS = PairCfg<ORDER>::TERMS;
+    __shared__ __align__(16) float tiles[WARPS][32 * TS];
+    const uint32_t lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    float *tile = tiles[wib];
+    const uint32_t npairs = region_count[blockIdx.y];
+    const uint2 *pairs = cand + (size_t)blockIdx.y * region_cap;
+    const uint32_t ngroups = (npairs + 31u) / 32u;
+    const uint32_t ncb = (dim + 127u) / 128u;
+    for (uint32_t g = blockIdx.x * WARPS + wib; g < ngroups; g += gridDim.x * WARPS) {
+        const uint32_t idx = g * 32u + lane;
+        const bool valid = idx < npairs;
+        const uint2 pr = valid ? pairs[idx] : make_uint2(0u, 0u);
+        float sum = 0.f;
+        for (uint32_t cb = 0; cb < ncb; ++cb) {
+            const uint32_t col = cb * 128u + (lane << 2);
+            const bool inb = col < dim;
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 8) {
+                float4 xv[8], qv[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const uint32_t rr = __shfl_sync(0xffffffffu, pr.x, r0 + j);
+                    const uint32_t qq = __shfl_sync(0xffffffffu, pr.y, r0 + j);
+                    xv[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    qv[j] = xv[j];
+                    if (inb) {
+                        xv[j] = ldg4(rows + (u64)rr * dim + col);
+                        qv[j] = ldg4(Q + (size_t)qq * dim + col);
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    if (ORDER == 0) {
+                        tile[(r0 + j) * TS + lane] = chunk4(qv[j], xv[j]);   // squared_l2_distance(query, vec), search.rs:117
+                    } else {
+                        float4 t;                                            // diff = value - q, exec.rs:531
+                        t.x = sq1(xv[j].x, qv[j].x);
+                        t.y = sq1(xv[j].y, qv[j].y);
+                        t.z = sq1(xv[j].z, qv[j].z);
+                        t.w = sq1(xv[j].w, qv[j].w);
+                        *reinterpret_cast<float4 *>(tile + (r0 + j) * TS + (lane << 2)) = t;
+                    }
+                }
+            }
+            __syncwarp();
+            // columns past dim contribute +0.0 terms: x + (+0.0) == x bit for bit for the non-negative partial sums
+            const float4 *tr = reinterpret_cast<const float4 *>(tile + lane * TS);
+#pragma unroll
+            for (int t4 = 0; t4 < 8 * TERMS; ++t4) {
+                const float4 t = tr[t4];
+                sum = __fadd_rn(sum, t.x);
+                sum = __fadd_rn(sum, t.y);
+                sum = __fadd_rn(sum, t.z);
+                sum = __fadd_rn(sum, t.w);
+            }
+            __syncwarp();
+        }
+        if (valid) {
+            const uint32_t slot = atomicAdd(&cntq[pr.y], 1u);
+            if (slot < cap_q) seg[(size_t)pr.y * cap_q + slot] = ((u64)__float_as_uint(sum) << 32) | (u64)pr.x;
+        }
+    }
+}
+
+// one CTA per query: the kk = min(k + 1, cnt) smallest keys of the query's segment (8-pass MSB-first radix select on the
+// u64 keys, then a bitonic sort of the survivors in shared memory).  out_keys[q][0..k) ascending; out_info[q] =
+// count | TIE << 30 | OVERFLOW << 31 where TIE means the caller must re-run the query through the single-query path.
+constexpr uint32_t SEL_TIE = 1u << 30, SEL_OVERFLOW = 1u << 31;
+constexpr int SEL_MAX = 2048;  // >= PQV_MAX_K + 1, power of two
+
+__global__ void __launch_bounds__(256) topk_select_kernel(const u64 *__restrict__ seg, uint32_t cap_q,
+                                                          const uint32_t *__restrict__ cntq, uint32_t k, int apply_sqrt,
+                                                          u64 *__restrict__ out_keys, uint32_t *__restrict__ out_info) {
+    const uint32_t q = blockIdx.x;
+    const uint32_t raw_cnt = cntq[q];
+    const uint32_t cnt = min(raw_cnt, cap_q);
+    const u64 *keys = seg + (size_t)q * cap_q;
+    const uint32_t kk = min(k + 1u, cnt);
+    __shared__ uint32_t hist[256];
+    __shared__ u64 s_prefix;
+    __shared__ uint32_t s_remaining, s_fill, s_tie;
+    __shared__ u64 buf[SEL_MAX];
+    if (threadIdx.x == 0) {
+        s_prefix = 0ull;
+        s_remaining = kk;
+        s_fill = 0u;
+        s_tie = 0u;
+    }
+    __syncthreads();
+    if (kk > 0) {
+        for (int pass = 7; pass >= 0; --pass) {
+            hist[threadIdx.x] = 0u;
+            __syncthreads();
+            const u64 prefix = s_prefix;
+            const uint32_t shift = 8u * (uint32_t)pass;
+            const u64 himask = (pass == 7) ? 0ull : (~0ull << (shift + 8u));
+            for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+                const u64 key = keys[i];
+                if ((key & himask) == prefix) atomicAdd(&hist[(uint32_t)(key >> shift) & 0xFFu], 1u);
+            }
+            __syncthreads();
+            if (threadIdx.x == 0) {
+                uint32_t rem = s_remaining, b = 0;
+                for (; b < 256; ++b) {
+                    if (hist[b] >= rem) break;
+                    rem -= hist[b];
+                }
+                b = b < 256 ? b : 255;
+                s_prefix = prefix | ((u64)b << shift);
+                s_remaining = rem;
+            }
+            __syncthreads();
+        }
+    }
+    const u64 kth = s_prefix;  // the kk-th smallest key (keys are unique: one per row)
+    for (uint32_t i = threadIdx.x; i < SEL_MAX; i += blockDim.x) buf[i] = KEY_MAX;
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < cnt; i += blockDim.x) {
+        const u64 key = keys[i];
+        if (kk > 0 && key <= kth) {
+            const uint32_t slot = atomicAdd(&s_fill, 1u);
+            if (slot < (uint32_t)SEL_MAX) buf[slot] = key;
+        }
+    }
+    __syncthreads();
+    for (uint32_t size = 2; size <= (uint32_t)SEL_MAX; size <<= 1)
+        for (uint32_t stride = size >> 1; stride > 0; stride >>= 1) {
+            for (uint32_t i = threadIdx.x; i < (uint32_t)SEL_MAX / 2; i += blockDim.x) {
+                const uint32_t lo = 2 * i - (i & (stride - 1));
+                const uint32_t hi = lo + stride;
+                const bool up = ((lo & size) == 0);
+                const u64 x = buf[lo], y = buf[hi];
+                if ((x > y) == up) {
+                    buf[lo] = y;
+                    buf[hi] = x;
+                }
+            }
+            __syncthreads();
+        }
+    const uint32_t nout = min(k, cnt);
+    for (uint32_t i = threadIdx.x; i < nout; i += blockDim.x) {
+        out_keys[(size_t)q * k + i] = buf[i];
+        if (i + 1 < nout) {  // returned values must be pairwise distinct, else their order is the heap layout's
+            const float d0 = __uint_as_float((uint32_t)(buf[i] >> 32)), d1 = __uint_as_float((uint32_t)(buf[i + 1] >> 32));
+            const bool same = apply_sqrt ? (__fsqrt_rn(d0) == __fsqrt_rn(d1)) : (d0 == d1);
+            if (same) atomicOr(&s_tie, 1u);
+        }
+    }
+    // boundary: the k-th and (k+1)-th smallest squared distances must differ, else the kept set is the heap layout's
+    if (threadIdx.x == 0 && cnt > k && (uint32_t)(buf[k - 1] >> 32) == (uint32_t)(buf[k] >> 32)) atomicOr(&s_tie, 1u);
+    __syncthreads();
+    if (threadIdx.x == 0)
+        out_info[q] = nout | (s_tie ? SEL_TIE : 0u) | ((raw_cnt > cap_q || s_fill > (uint32_t)SEL_MAX) ? SEL_OVERFLOW : 0u);
+}
+
+#undef BAR_FULL
+#undef BAR_EMPTY
+#undef BAR_TFULL
+#undef BAR_TEMPTY
 
 }  // namespace tc
 }  // namespace pqv

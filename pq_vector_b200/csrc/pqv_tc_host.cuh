@@ -86,7 +86,8 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
     std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(T::assign_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES);
+        attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_kernel<T::AssignEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)T::SMEM_BYTES);
     });
     CU_TRY(attr_err);
 
@@ -117,12 +118,10 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     p.pair_cap = (uint32_t)pair_cap64;
     p.dim = dim;
     p.C = C;
-    p.num_mb = num_mb;
-    p.num_nb = num_nb;
-    p.num_kb = num_kb;
+    const T::GemmShape shape{num_mb, num_nb, num_kb};
     const uint32_t grid = std::min<uint32_t>(num_mb, (uint32_t)D.sm_count);
     if (time_it) CU_TRY(cudaEventRecord(D.ev[1], D.stream));
-    T::assign_tc_kernel<<<grid, T::THREADS, T::SMEM_BYTES, D.stream>>>(tmA, tmB, p);
+    T::tc_rows_x_table_kernel<T::AssignEpi><<<grid, T::THREADS, T::SMEM_BYTES, D.stream>>>(tmA, tmB, shape, p);
     CU_TRY(cudaGetLastError());
     if (time_it) CU_TRY(cudaEventRecord(D.ev[2], D.stream));
     // exact f32 chains: one per (row, candidate) pair of the ambiguous rows; the full scan for the overflow rows
@@ -176,6 +175,170 @@ void record_assign_timing(pqv_ctx *ctx, DeviceState &D, int path, u64 rows, cons
     t.recheck_ms += post;
     t.pair_ms += pair_ms;
     t.total_ms += (double)prep + filt + post;
+}
+
+// ------------------------------------------------------------------------------------------------
+// batched brute-force top-k (pqv_tc.cuh, "Batched brute-force top-k")
+// ------------------------------------------------------------------------------------------------
+constexpr uint32_t BATCH_MIN_QUERIES = 4;          // below this the single-query scans are cheaper than the prep
+constexpr u64 BATCH_TOTAL_CAND = 64ull << 20;      // candidate (row, query) records kept per batch (8 B each)
+
+// PQV_BATCH=off disables the path (every query then takes the single-query scan)
+bool batch_path_applies(const Dataset &ds, const float *d_rows, uint32_t nq, uint32_t k) {
+    const char *e = getenv("PQV_BATCH");
+    if (e && !strcmp(e, "off")) return false;
+    return ds.shards.size() == 1 && nq >= BATCH_MIN_QUERIES && (ds.dim % 4 == 0) && ds.dim >= (uint32_t)pqv::tc::BK &&
+           ((reinterpret_cast<uintptr_t>(d_rows) & 15) == 0) && ds.n_rows < 0xFFFFFFFFull && ds.n_rows >= 1 &&
+           k + 1 <= (uint32_t)pqv::tc::SEL_MAX && tmap_encoder() != nullptr;
+}
+
+// Answers every query it can decide exactly; handled[q] = 0 marks the queries the caller must run through the
+// single-query path (ties whose order depends on the reference heap's layout, or a declined batch).
+int batch_topk(pqv_ctx *ctx, DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const float *queries, uint32_t nq,
+               uint32_t k, uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
+               std::vector<uint8_t> &handled) {
+    namespace T = pqv::tc;
+    handled.assign(nq, 0);
+    pqv_batch_timing &bt = ctx->last_batch;
+    bt = pqv_batch_timing{};
+    bt.queries = nq;
+    bt.rows = n;
+    // non-finite or huge queries: the reference's NaN/inf heap behaviour is reproduced by the single-query path only
+    for (size_t i = 0; i < (size_t)nq * dim; ++i)
+        if (!(fabsf(queries[i]) < 1e15f)) {
+            bt.declined = 1;
+            return PQV_OK;
+        }
+    const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
+    const bool by_pos = (flags & PQV_TIES_BY_POSITION) != 0;
+    const uint32_t nq_pad = (nq + T::BN - 1) / T::BN * T::BN;
+    const uint32_t num_nb = nq_pad / T::BN, num_kb = (dim + T::BK - 1) / T::BK;
+    const uint32_t num_mb = (uint32_t)((n + T::BM - 1) / T::BM);
+    const u64 S = std::min<u64>(n, std::min<u64>(std::max<u64>(n / 16, 65536), 524288));
+    const uint32_t num_mb_s = (uint32_t)((S + T::BM - 1) / T::BM);
+    const uint32_t ldU = num_mb_s * T::BM;
+    const uint32_t grid = std::min<uint32_t>(num_mb, (uint32_t)D.sm_count);
+    const uint32_t grid_s = std::min<uint32_t>(num_mb_s, (uint32_t)D.sm_count);
+    const u64 rows_per_cta = (u64)((num_mb + grid - 1) / grid) * T::BM;
+    const uint32_t region_cap = (uint32_t)std::min<u64>(rows_per_cta * nq, std::max<u64>(BATCH_TOTAL_CAND / grid, 1024));
+    const uint32_t cap_q = (uint32_t)std::min<u64>(n, std::max<u64>(BATCH_TOTAL_CAND / nq, 4096));
+
+    PQV_TRY(D.tb_Q.ensure((size_t)nq * dim));
+    PQV_TRY(D.tb_Qp.ensure((size_t)nq * dim));
+    PQV_TRY(D.tb_qf.ensure(3 * (size_t)nq_pad));
+    PQV_TRY(D.tb_u32.ensure(4 + (size_t)nq + grid));
+    PQV_TRY(D.tb_U.ensure((size_t)nq_pad * ldU));
+    PQV_TRY(D.tb_cand.ensure((size_t)grid * region_cap));
+    PQV_TRY(D.tb_seg.ensure((size_t)nq * cap_q));
+    PQV_TRY(D.tb_keys.ensure((size_t)nq * k));
+    PQV_TRY(D.tc_stats.ensure(n));
+    PQV_TRY(D.tc_mu.ensure(dim));
+    PQV_TRY(D.h_batch_keys.ensure((size_t)nq * k + nq + 2));
+    float *qw = D.tb_qf.p, *q2 = D.tb_qf.p + nq_pad, *qtheta = D.tb_qf.p + 2 * (size_t)nq_pad;
+    uint32_t *qbounds = D.tb_u32.p, *dflags = D.tb_u32.p + 1, *cntq = D.tb_u32.p + 4, *region_count = D.tb_u32.p + 4 + nq;
+    PQV_TRY(D.tb_info.ensure(nq));
+
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_SAMPLE>>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_FILTER>>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES);
+    });
+    CU_TRY(attr_err);
+
+    CUtensorMap tmAs, tmA, tmB;
+    PQV_TRY(make_row_tmap(&tmAs, d_rows, S, dim, T::BM));
+    PQV_TRY(make_row_tmap(&tmA, d_rows, n, dim, T::BM));
+    PQV_TRY(make_row_tmap(&tmB, D.tb_Qp.p, nq, dim, T::BN));
+
+    cudaStream_t st = D.stream;
+    CU_TRY(cudaEventRecord(D.ev[0], st));
+    CU_TRY(cudaMemsetAsync(D.tb_u32.p, 0, (4 + (size_t)nq + grid) * sizeof(uint32_t), st));
+    CU_TRY(cudaMemsetAsync(D.tc_mu.p, 0, (size_t)dim * sizeof(float), st));
+    CU_TRY(cudaMemcpyAsync(D.tb_Q.p, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, st));
+    T::query_prep_kernel<<<nq_pad, 128, 0, st>>>(D.tb_Q.p, nq, dim, D.tb_Qp.p, qw, q2, nq_pad, qbounds);
+    T::row_stats_kernel<<<(uint32_t)D.sm_count * 8, 256, 0, st>>>(d_rows, n, dim, D.tc_mu.p, D.tc_stats.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(D.ev[1], st));
+
+    T::BatchParams p;
+    p.stats = D.tc_stats.p;
+    p.qw = qw;
+    p.qtheta = qtheta;
+    p.qbounds = qbounds;
+    p.U = D.tb_U.p;
+    p.ldU = ldU;
+    p.cand = D.tb_cand.p;
+    p.region_cap = region_cap;
+    p.region_count = region_count;
+    p.flags = dflags;
+    p.dim = dim;
+    // phase A: upper bounds over the first S rows -> theta_q
+    p.n = S;
+    T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_SAMPLE>><<<grid_s, T::THREADS, T::SMEM_BYTES, st>>>(
+        tmAs, tmB, T::GemmShape{num_mb_s, num_nb, num_kb}, p);
+    const float delta = (float)(order == 1 ? dim + 8 : dim / 4 + 12) * 5.9604645e-08f;
+    T::theta_select_kernel<<<nq_pad, 256, 0, st>>>(D.tb_U.p, ldU, (uint32_t)S, k, nq, q2, delta, qtheta);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(D.ev[2], st));
+    // phase B: candidates over all rows
+    p.n = n;
+    T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_FILTER>><<<grid, T::THREADS, T::SMEM_BYTES, st>>>(
+        tmA, tmB, T::GemmShape{num_mb, num_nb, num_kb}, p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(D.ev[3], st));
+    // exact distances of the candidates, per-query selection
+    if (order == 0)
+        T::pair_dist_kernel<0><<<dim3(8, grid), T::PairCfg<0>::WARPS * 32, 0, st>>>(d_rows, dim, D.tb_Q.p, D.tb_cand.p, region_cap,
+                                                                                   region_count, D.tb_seg.p, cap_q, cntq);
+    else
+        T::pair_dist_kernel<1><<<dim3(32, grid), T::PairCfg<1>::WARPS * 32, 0, st>>>(d_rows, dim, D.tb_Q.p, D.tb_cand.p, region_cap,
+                                                                                    region_count, D.tb_seg.p, cap_q, cntq);
+    T::topk_select_kernel<<<nq, 256, 0, st>>>(D.tb_seg.p, cap_q, cntq, k, (flags & PQV_SQRT) ? 1 : 0, D.tb_keys.p, D.tb_info.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaEventRecord(D.ev[4], st));
+    u64 *h_keys = D.h_batch_keys.p;
+    uint32_t *h_info = reinterpret_cast<uint32_t *>(h_keys + (size_t)nq * k);
+    uint32_t *h_flags = h_info + nq;  // + region counts are not needed on the host
+    CU_TRY(cudaMemcpyAsync(h_keys, D.tb_keys.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_info, D.tb_info.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_flags, dflags, 4, cudaMemcpyDeviceToHost, st));
+    std::vector<uint32_t> h_cnt(nq);
+    CU_TRY(cudaMemcpyAsync(h_cnt.data(), cntq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    float ms[4] = {0, 0, 0, 0};
+    for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], D.ev[i], D.ev[i + 1]);
+    bt.prep_ms = ms[0];
+    bt.sample_ms = ms[1];
+    bt.filter_ms = ms[2];
+    bt.rerank_ms = ms[3];
+    bt.total_ms = (double)ms[0] + ms[1] + ms[2] + ms[3];
+    bt.sample_rows = S;
+    for (uint32_t q = 0; q < nq; ++q) bt.candidates += h_cnt[q];
+    if (*h_flags) {  // non-finite rows or a full candidate region: nothing of this batch is trusted
+        bt.declined = 1;
+        return PQV_OK;
+    }
+    for (uint32_t q = 0; q < nq; ++q) {
+        const uint32_t info = h_info[q];
+        if ((info & T::SEL_OVERFLOW) || ((info & T::SEL_TIE) && !by_pos)) {
+            bt.tie_queries++;
+            continue;
+        }
+        const uint32_t cnt = info & 0xFFFFu;
+        for (uint32_t i = 0; i < cnt; ++i) {
+            const u64 key = h_keys[(size_t)q * k + i];
+            const float d = key_dist(key);
+            out_rows[(size_t)q * k + i] = key_pos(key);
+            out_dist[(size_t)q * k + i] = (flags & PQV_SQRT) ? sqrtf(d) : d;
+        }
+        out_count[q] = cnt;
+        handled[q] = 1;
+    }
+    return PQV_OK;
 }
 
 }  // namespace

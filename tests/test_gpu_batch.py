@@ -1,0 +1,153 @@
+"""GPU parity tests for the batched brute-force top-k (tcgen05 filter + exact re-rank, pqv_tc.cuh): every query of a batch
+must return exactly what its own single-query reference loop returns (src/ivf/search.rs:112-141 with PQV_SQRT,
+src/df_vector/exec.rs:257-277 with PQV_SUM_SEQ) -- row ids, order and distance bits."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SQRT, SEQ, BYPOS = 2, 1, 4
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    import pq_vector_b200 as P
+    c = P.Context()
+    yield c
+    c.close()
+
+
+class batch_off:
+    def __enter__(self):
+        self.old = os.environ.get("PQV_BATCH")
+        os.environ["PQV_BATCH"] = "off"
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            os.environ.pop("PQV_BATCH", None)
+        else:
+            os.environ["PQV_BATCH"] = self.old
+
+
+def bits(a):
+    return np.asarray(a, np.float32).view(np.uint32)
+
+
+def check_batch(ctx, data, queries, k, flags, expect_used=True, nan_payload_free=False):
+    ds = ctx.dataset_from(data)
+    rows, dist, cnt = ds.l2_topk(queries, k, flags)
+    t = ctx.last_batch_timing()
+    order = 1 if flags & SEQ else 0
+    for i, q in enumerate(queries):
+        er, ed = O.topk_rerank(q, data, None, k, order, bool(flags & SQRT))
+        assert cnt[i] == er.size, (i, cnt[i], er.size, t)
+        assert rows[i, :cnt[i]].tolist() == er.tolist(), (i, t)
+        if nan_payload_free and np.isnan(ed).any():   # a NaN query: every distance is NaN, payload bits are not pinned
+            assert np.isnan(dist[i, :cnt[i]]).all()
+            continue
+        assert bits(dist[i, :cnt[i]]).tolist() == bits(ed).tolist(), (i, t)
+    if expect_used:
+        assert t["queries"] == len(queries) and t["declined"] == 0, t
+    ds.drop()
+    return t
+
+
+@pytest.mark.parametrize("n,dim,nq,k,flags", [
+    (20000, 768, 24, 10, SQRT), (20000, 768, 24, 100, SQRT), (30000, 128, 300, 10, SEQ), (5001, 100, 7, 33, SQRT),
+    (4096, 32, 4, 1, SEQ | 0), (3000, 1536, 40, 100, SEQ), (700, 64, 9, 1024, SQRT), (50, 64, 5, 100, SQRT),
+])
+def test_batch_matches_the_single_query_reference(ctx, n, dim, nq, k, flags):
+    rng = np.random.default_rng(n + dim + nq + k)
+    data = rng.random((n, dim), dtype=np.float32)
+    queries = rng.random((nq, dim), dtype=np.float32)
+    queries[0] = data[n // 2]          # an exact hit (distance 0)
+    t = check_batch(ctx, data, queries, k, flags)
+    assert t["tie_queries"] <= nq
+
+
+def test_clustered_and_unit_norm_data(ctx):
+    rng = np.random.default_rng(3)
+    cent = rng.standard_normal((50, 256)).astype(np.float32)
+    data = (cent[rng.integers(0, 50, 40000)] + 0.05 * rng.standard_normal((40000, 256))).astype(np.float32)
+    data /= np.linalg.norm(data, axis=1, keepdims=True)
+    queries = data[rng.integers(0, 40000, 64)] + 0.01 * rng.standard_normal((64, 256)).astype(np.float32)
+    check_batch(ctx, data, queries.astype(np.float32), 20, SQRT)
+    check_batch(ctx, data, queries.astype(np.float32), 20, SEQ)
+
+
+def test_duplicate_rows_fall_back_to_the_heap_replay(ctx):
+    """bit-equal distances inside the top-k: the order is the reference heap's layout -> those queries are re-run exactly"""
+    rng = np.random.default_rng(4)
+    base = rng.random((3000, 64), dtype=np.float32)
+    data = np.concatenate([base, base[:1500], base[:700]])
+    queries = rng.random((12, 64), dtype=np.float32)
+    t = check_batch(ctx, data, queries, 50, SQRT)
+    assert t["tie_queries"] >= 1
+    # grid data: many exactly equal distances
+    grid = rng.integers(0, 3, (20000, 32)).astype(np.float32)
+    tq = check_batch(ctx, grid, rng.integers(0, 3, (8, 32)).astype(np.float32), 10, SEQ)
+    assert tq["tie_queries"] >= 1
+
+
+def test_ties_by_position_flag_needs_no_fallback(ctx):
+    rng = np.random.default_rng(5)
+    grid = rng.integers(0, 3, (20000, 32)).astype(np.float32)
+    queries = rng.integers(0, 3, (8, 32)).astype(np.float32)
+    ds = ctx.dataset_from(grid)
+    rows, dist, cnt = ds.l2_topk(queries, 10, SEQ | BYPOS)
+    t = ctx.last_batch_timing()
+    assert t["queries"] == 8 and t["tie_queries"] == 0 and t["declined"] == 0
+    with batch_off():
+        r1, d1, c1 = ds.l2_topk(queries, 10, SEQ | BYPOS)
+    assert np.array_equal(rows, r1) and np.array_equal(bits(dist), bits(d1)) and np.array_equal(cnt, c1)
+    ds.drop()
+
+
+def test_non_finite_inputs_decline_the_batch(ctx):
+    rng = np.random.default_rng(6)
+    data = rng.random((6000, 64), dtype=np.float32)
+    queries = rng.random((6, 64), dtype=np.float32)
+    bad = data.copy()
+    bad[17, 3] = np.inf
+    bad[4000, 0] = np.nan
+    t = check_batch(ctx, bad, queries, 10, SQRT, expect_used=False)
+    assert t["declined"] == 1
+    qbad = queries.copy()
+    qbad[2, 5] = np.nan
+    t = check_batch(ctx, data, qbad, 10, SQRT, expect_used=False, nan_payload_free=True)
+    assert t["declined"] == 1
+
+
+def test_batch_equals_single_scans_at_scale(ctx):
+    n, dim, nq, k = 400_000, 768, 200, 100
+    ds = ctx.dataset(dim, n)
+    ds.fill_synthetic(n, 1234)
+    qd = ctx.dataset(dim, nq)
+    qd.fill_synthetic(nq, 7)
+    queries = qd.read(0, nq)
+    qd.drop()
+    for flags in (SQRT, SEQ):
+        rows, dist, cnt = ds.l2_topk(queries, k, flags)
+        t = ctx.last_batch_timing()
+        assert t["queries"] == nq and t["declined"] == 0, t
+        with batch_off():
+            r1, d1, c1 = ds.l2_topk(queries, k, flags)
+        assert ctx.last_batch_timing()["queries"] == 0
+        assert np.array_equal(cnt, c1)
+        assert np.array_equal(rows, r1)
+        assert np.array_equal(bits(dist), bits(d1))
+        print(flags, t)
+    ds.drop()
+
+
+def test_small_batches_use_the_single_query_path(ctx):
+    rng = np.random.default_rng(8)
+    data = rng.random((5000, 64), dtype=np.float32)
+    ds = ctx.dataset_from(data)
+    ds.l2_topk(rng.random((3, 64), dtype=np.float32), 5, SQRT)
+    assert ctx.last_batch_timing()["queries"] == 0
+    ds.drop()
