@@ -239,6 +239,14 @@ struct Shard {
     int di = 0;  // index into ctx->devs
     float *d_data = nullptr;
     u64 cap_rows = 0, n_rows = 0, first_row = 0;
+    // |x|^2 per row, computed on first use by the batched top-k and kept until the shard changes
+    float2 *d_norms = nullptr;
+    u64 norms_rows = 0, norms_cap = 0;
+    void drop_norms() {
+        if (d_norms) cudaFree(d_norms);
+        d_norms = nullptr;
+        norms_rows = norms_cap = 0;
+    }
 };
 
 struct Dataset {
@@ -726,6 +734,7 @@ void pqv_destroy(pqv_ctx *ctx) {
         for (auto &sh : kv.second.shards) {
             DevGuard guard(ctx->devs[sh.di].dev);
             if (sh.d_data) cudaFree(sh.d_data);
+            sh.drop_norms();
         }
     for (auto &D : ctx->devs) {
         DevGuard guard(D.dev);
@@ -855,6 +864,7 @@ int pqv_dataset_append(pqv_ctx *ctx, uint64_t handle, const float *values, uint6
                                cudaMemcpyHostToDevice, D.stream));
         CU_TRY(cudaStreamSynchronize(D.stream));  // values is only borrowed for the call
         sh->n_rows += take;
+        sh->norms_rows = 0;  // cached norms no longer cover the shard
         ds->n_rows += take;
         done += take;
     }
@@ -880,6 +890,7 @@ int pqv_dataset_drop(pqv_ctx *ctx, uint64_t handle) {
         DevGuard guard(ctx->devs[sh.di].dev);
         cudaStreamSynchronize(ctx->devs[sh.di].stream);
         if (sh.d_data) cudaFree(sh.d_data);
+        sh.drop_norms();
     }
     ctx->datasets.erase(handle);
     return PQV_OK;
@@ -898,6 +909,7 @@ int pqv_dataset_fill_synthetic(pqv_ctx *ctx, uint64_t handle, uint64_t n_rows, u
     for (auto &sh : ds->shards) {
         const u64 take = std::min<u64>(left, sh.cap_rows);
         sh.n_rows = take;
+        sh.norms_rows = 0;
         left -= take;
         ds->n_rows += take;
         if (!take) continue;
@@ -947,7 +959,7 @@ int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_
     if (n_queries && ds->n_rows && batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k)) {
         DeviceState &D = ctx->devs[ds->shards[0].di];
         DevGuard guard(D.dev);
-        PQV_TRY(batch_topk(ctx, D, ds->shards[0].d_data, ds->n_rows, ds->dim, queries, n_queries, k, flags, out_row_idx, out_dist,
+        PQV_TRY(batch_topk(ctx, D, ds->shards[0], ds->n_rows, ds->dim, queries, n_queries, k, flags, out_row_idx, out_dist,
                            out_count, handled));
     }
     for (uint32_t q = 0; q < n_queries; ++q)

@@ -819,12 +819,16 @@ __device__ __forceinline__ float f32_unordered(uint32_t o) {
     return __uint_as_float((o & 0x80000000u) ? (o & 0x7FFFFFFFu) : ~o);
 }
 
-// one CTA per query: theta_q from the k-th smallest of U[q][0..S) (MSB-first radix select, 4 passes of 8 bits), then
+// one CTA per query: theta_q from an upper bound of the k-th smallest of U[q][0..S).  The S values are folded into M
+// strided chunk minima (chunk c = elements c, c + M, ...; M >= 16 k): M distinct elements of the array, so their k-th
+// smallest is >= the array's k-th smallest, and equal to it unless two of the k smallest share a chunk.  The k-th smallest
+// of the M minima is then exact (MSB-first radix select in shared memory, 4 passes of 8 bits).
 //   theta_q = th + (2^-20 + 2.2 delta) max(th + q2_q, 0) + rounding slack      (header of this section)
 // queries >= nq (padding) get -inf so that they never produce candidates.  S < k: +inf (every row is a candidate).
 __global__ void __launch_bounds__(256) theta_select_kernel(const float *__restrict__ U, uint32_t ldU, uint32_t S, uint32_t k,
-                                                           uint32_t nq, const float *__restrict__ q2, float delta,
+                                                           uint32_t nq, const float *__restrict__ q2, float delta, uint32_t M,
                                                            float *__restrict__ qtheta) {
+    extern __shared__ float mins[];  // [M]
     const uint32_t q = blockIdx.x;
     if (q >= nq) {
         if (threadIdx.x == 0) qtheta[q] = __int_as_float(0xff800000);
@@ -837,18 +841,33 @@ __global__ void __launch_bounds__(256) theta_select_kernel(const float *__restri
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_remaining;
     const float *u = U + (size_t)q * ldU;
+    const float inf = __int_as_float(0x7f800000);
+    // chunk c is owned by thread c % 256: coalesced reads, no atomics
+    for (uint32_t c = threadIdx.x; c < M; c += blockDim.x) {
+        float m0 = inf, m1 = inf, m2 = inf, m3 = inf;
+        uint32_t i = c;
+        for (; i + 3 * M < S; i += 4 * M) {
+            m0 = fminf(m0, u[i]);
+            m1 = fminf(m1, u[i + M]);
+            m2 = fminf(m2, u[i + 2 * M]);
+            m3 = fminf(m3, u[i + 3 * M]);
+        }
+        for (; i < S; i += M) m0 = fminf(m0, u[i]);
+        mins[c] = fminf(fminf(m0, m1), fminf(m2, m3));  // +inf for an empty chunk (M > S): ranks above every real value
+    }
     if (threadIdx.x == 0) {
         s_prefix = 0u;
-        s_remaining = k;  // rank (1-based) of the wanted element among those matching the prefix
+        s_remaining = min(k, min(M, S));  // rank (1-based) of the wanted element among those matching the prefix
     }
+    __syncthreads();
     for (int pass = 3; pass >= 0; --pass) {
         hist[threadIdx.x] = 0u;
         __syncthreads();
         const uint32_t prefix = s_prefix;
         const uint32_t shift = 8u * (uint32_t)pass;
         const uint32_t himask = (pass == 3) ? 0u : (0xFFFFFFFFu << (shift + 8u));
-        for (uint32_t i = threadIdx.x; i < S; i += blockDim.x) {
-            const uint32_t o = f32_ordered(u[i]);
+        for (uint32_t i = threadIdx.x; i < M; i += blockDim.x) {
+            const uint32_t o = f32_ordered(mins[i]);
             if ((o & himask) == prefix) atomicAdd(&hist[(o >> shift) & 0xFFu], 1u);
         }
         __syncthreads();

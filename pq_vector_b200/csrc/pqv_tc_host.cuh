@@ -194,10 +194,11 @@ bool batch_path_applies(const Dataset &ds, const float *d_rows, uint32_t nq, uin
 
 // Answers every query it can decide exactly; handled[q] = 0 marks the queries the caller must run through the
 // single-query path (ties whose order depends on the reference heap's layout, or a declined batch).
-int batch_topk(pqv_ctx *ctx, DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const float *queries, uint32_t nq,
+int batch_topk(pqv_ctx *ctx, DeviceState &D, Shard &sh, u64 n, uint32_t dim, const float *queries, uint32_t nq,
                uint32_t k, uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
                std::vector<uint8_t> &handled) {
     namespace T = pqv::tc;
+    const float *d_rows = sh.d_data;
     handled.assign(nq, 0);
     pqv_batch_timing &bt = ctx->last_batch;
     bt = pqv_batch_timing{};
@@ -231,8 +232,13 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, const float *d_rows, u64 n, uint32_
     PQV_TRY(D.tb_cand.ensure((size_t)grid * region_cap));
     PQV_TRY(D.tb_seg.ensure((size_t)nq * cap_q));
     PQV_TRY(D.tb_keys.ensure((size_t)nq * k));
-    PQV_TRY(D.tc_stats.ensure(n));
     PQV_TRY(D.tc_mu.ensure(dim));
+    if (sh.norms_cap < n) {
+        sh.drop_norms();
+        cudaError_t e = cudaMalloc((void **)&sh.d_norms, (size_t)n * sizeof(float2));
+        if (e != cudaSuccess) return fail(PQV_ENOMEM, "row-norm cache of %llu rows: %s", (unsigned long long)n, cudaGetErrorString(e));
+        sh.norms_cap = n;
+    }
     PQV_TRY(D.h_batch_keys.ensure((size_t)nq * k + nq + 2));
     float *qw = D.tb_qf.p, *q2 = D.tb_qf.p + nq_pad, *qtheta = D.tb_qf.p + 2 * (size_t)nq_pad;
     uint32_t *qbounds = D.tb_u32.p, *dflags = D.tb_u32.p + 1, *cntq = D.tb_u32.p + 4, *region_count = D.tb_u32.p + 4 + nq;
@@ -260,12 +266,15 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, const float *d_rows, u64 n, uint32_
     CU_TRY(cudaMemsetAsync(D.tc_mu.p, 0, (size_t)dim * sizeof(float), st));
     CU_TRY(cudaMemcpyAsync(D.tb_Q.p, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, st));
     T::query_prep_kernel<<<nq_pad, 128, 0, st>>>(D.tb_Q.p, nq, dim, D.tb_Qp.p, qw, q2, nq_pad, qbounds);
-    T::row_stats_kernel<<<(uint32_t)D.sm_count * 8, 256, 0, st>>>(d_rows, n, dim, D.tc_mu.p, D.tc_stats.p);
+    if (sh.norms_rows != n) {  // |x|^2 per row: once per dataset state, not per batch
+        T::row_stats_kernel<<<(uint32_t)D.sm_count * 8, 256, 0, st>>>(d_rows, n, dim, D.tc_mu.p, sh.d_norms);
+        sh.norms_rows = n;
+    }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(D.ev[1], st));
 
     T::BatchParams p;
-    p.stats = D.tc_stats.p;
+    p.stats = sh.d_norms;
     p.qw = qw;
     p.qtheta = qtheta;
     p.qbounds = qbounds;
@@ -281,7 +290,16 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, const float *d_rows, u64 n, uint32_
     T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_SAMPLE>><<<grid_s, T::THREADS, T::SMEM_BYTES, st>>>(
         tmAs, tmB, T::GemmShape{num_mb_s, num_nb, num_kb}, p);
     const float delta = (float)(order == 1 ? dim + 8 : dim / 4 + 12) * 5.9604645e-08f;
-    T::theta_select_kernel<<<nq_pad, 256, 0, st>>>(D.tb_U.p, ldU, (uint32_t)S, k, nq, q2, delta, qtheta);
+    {
+        const uint32_t M = k <= 128 ? 2048u : 16384u;  // chunk minima kept per query (>= 16 k)
+        static std::once_flag sel_once;
+        static cudaError_t sel_err = cudaSuccess;
+        std::call_once(sel_once, [] {
+            sel_err = cudaFuncSetAttribute(T::theta_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4);
+        });
+        CU_TRY(sel_err);
+        T::theta_select_kernel<<<nq_pad, 256, M * sizeof(float), st>>>(D.tb_U.p, ldU, (uint32_t)S, k, nq, q2, delta, M, qtheta);
+    }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(D.ev[2], st));
     // phase B: candidates over all rows
