@@ -546,7 +546,7 @@ size_t emit_by_position(std::vector<u64> &keys, const RowMap &row_of, uint32_t k
 int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_ids, u64 n_ids, uint32_t k,
              uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
              std::vector<u64> *entrants_out = nullptr, uint32_t pos_offset = 0, const uint32_t *d_cand = nullptr,
-             const std::function<uint32_t(uint32_t)> *row_fn = nullptr) {
+             const std::function<uint32_t(uint32_t)> *row_fn = nullptr, u64 limit_rows = 0) {
     const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
     const bool gather = row_ids != nullptr || d_cand != nullptr;
     RowMap row_of;
@@ -583,6 +583,10 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
             }
         } else {
             n = sh.n_rows;
+            if (limit_rows) {  // brute force over the first limit_rows rows of the table only
+                if (sh.first_row >= limit_rows) continue;
+                n = std::min<u64>(n, limit_rows - sh.first_row);
+            }
         }
         if (n == 0) continue;
         PQV_TRY(D.d_query.ensure(ds.dim));
@@ -959,8 +963,8 @@ int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_
     if (n_queries && ds->n_rows && batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k)) {
         DeviceState &D = ctx->devs[ds->shards[0].di];
         DevGuard guard(D.dev);
-        PQV_TRY(batch_topk(ctx, D, ds->shards[0], ds->n_rows, ds->dim, queries, n_queries, k, flags, out_row_idx, out_dist,
-                           out_count, handled));
+        PQV_TRY(batch_topk(ctx, D, *ds, ds->n_rows, ds->dim, queries, n_queries, k, flags, out_row_idx, out_dist, out_count,
+                           handled));
     }
     for (uint32_t q = 0; q < n_queries; ++q)
         if (!handled[q])

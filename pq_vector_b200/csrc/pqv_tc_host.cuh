@@ -194,10 +194,11 @@ bool batch_path_applies(const Dataset &ds, const float *d_rows, uint32_t nq, uin
 
 // Answers every query it can decide exactly; handled[q] = 0 marks the queries the caller must run through the
 // single-query path (ties whose order depends on the reference heap's layout, or a declined batch).
-int batch_topk(pqv_ctx *ctx, DeviceState &D, Shard &sh, u64 n, uint32_t dim, const float *queries, uint32_t nq,
+int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, const float *queries, uint32_t nq,
                uint32_t k, uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
                std::vector<uint8_t> &handled) {
     namespace T = pqv::tc;
+    Shard &sh = ds.shards[0];
     const float *d_rows = sh.d_data;
     handled.assign(nq, 0);
     pqv_batch_timing &bt = ctx->last_batch;
@@ -340,10 +341,12 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Shard &sh, u64 n, uint32_t dim, con
         bt.declined = 1;
         return PQV_OK;
     }
+    std::vector<uint32_t> ties;
     for (uint32_t q = 0; q < nq; ++q) {
         const uint32_t info = h_info[q];
-        if ((info & T::SEL_OVERFLOW) || ((info & T::SEL_TIE) && !by_pos)) {
-            bt.tie_queries++;
+        if (info & T::SEL_OVERFLOW) continue;  // candidate list incomplete: the caller runs the full single-query scan
+        if ((info & T::SEL_TIE) && !by_pos) {
+            ties.push_back(q);
             continue;
         }
         const uint32_t cnt = info & 0xFFFFu;
@@ -354,6 +357,26 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Shard &sh, u64 n, uint32_t dim, con
             out_dist[(size_t)q * k + i] = (flags & PQV_SQRT) ? sqrtf(d) : d;
         }
         out_count[q] = cnt;
+        handled[q] = 1;
+    }
+    // Tie queries: the order (or the kept set) hinges on the layout of the reference's BinaryHeap, so its push sequence is
+    // replayed.  Rows the heap ever admits at positions >= S are all among the query's candidates
+    // (theta_q bounds the k-th smallest distance of the first S rows, the heap's threshold from position S on), and the
+    // admissions inside [0, S) come from the exact single-query scan of that prefix alone.
+    bt.tie_queries = (uint32_t)ties.size();
+    std::vector<u64> ent, seg_keys;
+    RowMap identity;
+    for (uint32_t q : ties) {
+        ent.clear();
+        uint32_t dummy_cnt = 0;
+        PQV_TRY(topk_one(ctx, ds, queries + (size_t)q * dim, nullptr, 0, k, flags, nullptr, nullptr, &dummy_cnt, &ent, 0, nullptr,
+                         nullptr, S));
+        const uint32_t cq = std::min<uint32_t>(h_cnt[q], cap_q);
+        seg_keys.resize(cq);
+        CU_TRY(cudaMemcpy(seg_keys.data(), D.tb_seg.p + (size_t)q * cap_q, (size_t)cq * 8, cudaMemcpyDeviceToHost));
+        for (u64 key : seg_keys)
+            if (key_pos(key) >= S) ent.push_back(key);
+        out_count[q] = (uint32_t)replay_reference_heap(ent, identity, k, flags, out_rows + (size_t)q * k, out_dist + (size_t)q * k);
         handled[q] = 1;
     }
     return PQV_OK;
