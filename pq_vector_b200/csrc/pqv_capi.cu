@@ -125,22 +125,68 @@ inline uint32_t key_pos(u64 key) { return (uint32_t)(key & 0xFFFFFFFFull); }
 struct RowMap {
     const uint32_t *ids = nullptr;
     const std::function<uint32_t(uint32_t)> *fn = nullptr;
-    uint32_t operator()(uint32_t pos) const { return fn ? (*fn)(pos) : (ids ? ids[pos] : pos); }
+    // sparse map for the entrants only: (position << 32 | row id), ascending (fused IVF search)
+    const u64 *pairs = nullptr;
+    size_t n_pairs = 0;
+    uint32_t operator()(uint32_t pos) const {
+        if (pairs) {
+            const u64 *it = std::lower_bound(pairs, pairs + n_pairs, (u64)pos << 32);
+            return (uint32_t)*it;
+        }
+        return fn ? (*fn)(pos) : (ids ? ids[pos] : pos);
+    }
 };
 
-size_t replay_reference_heap(std::vector<u64> &entrants, const RowMap &row_of, uint32_t k, uint32_t flags,
-                             uint32_t *out_rows, float *out_dist) {
-    std::sort(entrants.begin(), entrants.end(),
-              [](u64 a, u64 b) { return key_pos(a) < key_pos(b); });
+// stable LSD radix sort of u64 items by the 32-bit field (item >> shift) & 0xFFFFFFFF: 11-bit digits, passes whose
+// digit is constant are skipped.  ~10x faster than std::sort for the ~1e3 entrant keys of a query, and the replay sits
+// on the latency path of every search.
+void radix_sort_field(std::vector<u64> &v, unsigned shift) {
+    const size_t n = v.size();
+    if (n < 2) return;
+    if (n < 64) {
+        std::sort(v.begin(), v.end(), [shift](u64 a, u64 b) { return (uint32_t)(a >> shift) < (uint32_t)(b >> shift); });
+        return;
+    }
+    uint32_t lo = 0xFFFFFFFFu, hi = 0;
+    for (u64 x : v) {
+        const uint32_t f = (uint32_t)(x >> shift);
+        lo &= f;
+        hi |= f;
+    }
+    const uint32_t varying = lo ^ hi;  // bits that differ between at least two items
+    std::vector<u64> tmp(n);
+    u64 *src = v.data(), *dst = tmp.data();
+    for (unsigned d = 0; d < 32; d += 11) {
+        if (((varying >> d) & 0x7FFu) == 0) continue;
+        uint32_t hist[2048] = {0};
+        for (size_t i = 0; i < n; ++i) hist[((uint32_t)(src[i] >> shift) >> d) & 0x7FFu]++;
+        uint32_t run = 0;
+        for (uint32_t &h : hist) {
+            const uint32_t c = h;
+            h = run;
+            run += c;
+        }
+        for (size_t i = 0; i < n; ++i) dst[hist[((uint32_t)(src[i] >> shift) >> d) & 0x7FFu]++] = src[i];
+        std::swap(src, dst);
+    }
+    if (src != v.data()) memcpy(v.data(), src, n * 8);
+}
+
+// the reference loop (src/ivf/search.rs:115-127) over (distance, row id) items already in position order
+struct ReplayItem {
+    float d;
+    uint32_t row;
+};
+template <typename Next>
+size_t replay_ordered(size_t n, Next next, uint32_t k, uint32_t flags, uint32_t *out_rows, float *out_dist) {
     RustMaxHeap h;
     h.data.reserve((size_t)k + 1);
-    for (u64 key : entrants) {
-        const float d = key_dist(key);
-        const uint32_t pos = key_pos(key);
-        HeapItem it{d, row_of(pos)};
+    for (size_t i = 0; i < n; ++i) {
+        const ReplayItem e = next(i);
+        HeapItem it{e.d, e.row};
         if (h.data.size() < k) {
             h.push(it);
-        } else if (d < h.data[0].distance) {
+        } else if (e.d < h.data[0].distance) {
             h.pop();
             h.push(it);
         }
@@ -154,6 +200,63 @@ size_t replay_reference_heap(std::vector<u64> &entrants, const RowMap &row_of, u
         out_dist[i] = r[i].distance;
     }
     return r.size();
+}
+
+// Shortcut around the heap replay.  The replay over an entrant set E keeps the k smallest distances of E; which rows
+// those are is unique unless the k-th and (k+1)-th smallest distances of E are equal, and the output order (stable
+// sort by the returned value, src/ivf/search.rs:134-140 / src/df_vector/exec.rs:269-274) is unique unless two
+// returned values are equal.  When neither happens (and no NaN is involved) the answer is the k smallest keys in
+// ascending order, whatever the heap's layout history was; otherwise return false and let the caller replay.
+// row_at(i, pos) = row id of entrant i.
+template <typename RowAt>
+bool topk_without_replay(const u64 *keys, size_t n, uint32_t k, uint32_t flags, RowAt row_at, uint32_t *out_rows,
+                         float *out_dist, size_t *out_cnt) {
+    struct KeyIdx {
+        u64 key;
+        uint32_t idx;
+        bool operator<(const KeyIdx &o) const { return key < o.key; }
+    };
+    static thread_local std::vector<KeyIdx> v;
+    v.resize(n);
+    for (size_t i = 0; i < n; ++i) v[i] = KeyIdx{keys[i], (uint32_t)i};
+    const size_t take = std::min<size_t>(k, n);
+    if (n > take) {
+        std::nth_element(v.begin(), v.begin() + take, v.end());  // v[take] = (k+1)-th smallest, smaller ones before it
+        if (take && (uint32_t)(v[take].key >> 32) == (uint32_t)(std::max_element(v.begin(), v.begin() + take)->key >> 32))
+            return false;  // tie across the k boundary
+    }
+    std::sort(v.begin(), v.begin() + take);
+    if (take && (uint32_t)(v[take - 1].key >> 32) > 0x7F800000u) return false;  // NaN (or negative-sign bits): replay
+    for (size_t i = 0; i < take; ++i) {
+        const float d = key_dist(v[i].key);
+        out_dist[i] = (flags & PQV_SQRT) ? sqrtf(d) : d;
+        if (i && out_dist[i] == out_dist[i - 1]) return false;  // equal returned values: order hinges on the heap layout
+    }
+    for (size_t i = 0; i < take; ++i) out_rows[i] = row_at(v[i].idx, key_pos(v[i].key));
+    *out_cnt = take;
+    return true;
+}
+
+size_t replay_reference_heap(std::vector<u64> &entrants, const RowMap &row_of, uint32_t k, uint32_t flags,
+                             uint32_t *out_rows, float *out_dist) {
+    size_t fast_cnt = 0;
+    if (topk_without_replay(entrants.data(), entrants.size(), k, flags, [&](uint32_t, uint32_t pos) { return row_of(pos); },
+                            out_rows, out_dist, &fast_cnt))
+        return fast_cnt;
+    radix_sort_field(entrants, 0);  // by position
+    return replay_ordered(
+        entrants.size(),
+        [&](size_t i) {
+            const u64 key = entrants[i];
+            return ReplayItem{key_dist(key), row_of(key_pos(key))};
+        },
+        k, flags, out_rows, out_dist);
+}
+
+double trace_now_ms() {
+    timespec ts;
+    clock_gettime(CLOCK_MONOTONIC, &ts);
+    return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
 }
 
 uint32_t pow2ceil(uint32_t v) {
@@ -233,6 +336,11 @@ struct DeviceState {
     PinBuf<u64> h_batch_keys;
     PinBuf<u64> h_ent_out, h_final;
     PinBuf<float> h_query;
+    // fused IVF search: row ids of the entrants + (candidate count, NaN flag)
+    DevBuf<uint32_t> ent_rows;
+    DevBuf<u64> ivf_info;
+    PinBuf<uint32_t> h_ent_rows;
+    PinBuf<u64> h_ivf_info;
 };
 
 struct Shard {
@@ -441,7 +549,7 @@ int scan_geometry(pqv_ctx *ctx, DeviceState &D, const float *d_data, u64 n, uint
 // `final_out` if given, and entrant keys appended to `ent_out` ([0] = running count).
 int enqueue_scan(pqv_ctx *ctx, DeviceState &D, const float *d_data, const uint32_t *d_row_ids, u64 n, uint32_t dim,
                  const float *d_query, uint32_t k, int order, uint32_t pos_base, const u64 *d_carry, u64 *final_out,
-                 u64 *ent_out, uint32_t ent_out_cap, bool time_it, ScanGeom *geom_out) {
+                 u64 *ent_out, uint32_t ent_out_cap, bool time_it, ScanGeom *geom_out, const u64 *n_dev = nullptr) {
     ScanGeom g;
     PQV_TRY(scan_geometry(ctx, D, d_data, n, dim, k, order, d_row_ids != nullptr, &g));
     PQV_TRY(D.cta_topk.ensure((size_t)g.grid * g.kcap));
@@ -453,6 +561,7 @@ int enqueue_scan(pqv_ctx *ctx, DeviceState &D, const float *d_data, const uint32
     p.query = d_query;
     p.row_ids = d_row_ids;
     p.n = n;
+    p.n_dev = n_dev;
     p.dim = dim;
     p.k = k;
     p.kcap = g.kcap;
@@ -481,8 +590,8 @@ int enqueue_scan(pqv_ctx *ctx, DeviceState &D, const float *d_data, const uint32
                                                                D.group_prefix.p, final_out);
     CU_TRY(cudaGetLastError());
     pqv::entrant_filter_kernel<<<g.grid, 256, msmem, D.stream>>>(D.ent.p, D.ent_count.p, D.group_prefix.p,
-                                                                 D.within_prefix.p, k, g.kcap, D.gthr.p, n, ent_out,
-                                                                 ent_out_cap);
+                                                                 D.within_prefix.p, k, g.kcap, D.gthr.p, n, n_dev,
+                                                                 ent_out, ent_out_cap);
     CU_TRY(cudaGetLastError());
     if (time_it) CU_TRY(cudaEventRecord(D.ev[2], D.stream));
     if (geom_out) *geom_out = g;
@@ -549,6 +658,9 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
              const std::function<uint32_t(uint32_t)> *row_fn = nullptr, u64 limit_rows = 0) {
     const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
     const bool gather = row_ids != nullptr || d_cand != nullptr;
+    static const bool trace = getenv("PQV_TRACE") != nullptr;
+    double tt[4] = {0, 0, 0, 0};
+    if (trace) tt[0] = trace_now_ms();
     RowMap row_of;
     row_of.ids = row_ids;
     row_of.fn = row_fn;
@@ -603,6 +715,7 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
                              si == 0, &g));
         launched.push_back({&D, g, cap, n});
     }
+    if (trace) tt[1] = trace_now_ms();
     // collect
     for (auto &L : launched) {
         DeviceState &D = *L.D;
@@ -623,13 +736,15 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
                 const uint32_t cap2 = (uint32_t)std::min<size_t>(D.ent_out.cap - 1, 0xFFFFFFF0u);
                 CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
                 pqv::entrant_filter_kernel<<<L.g.grid, 256, (size_t)2 * L.g.kcap * 8, D.stream>>>(
-                    D.ent.p, D.ent_count.p, D.group_prefix.p, D.within_prefix.p, k, L.g.kcap, D.gthr.p, L.n, D.ent_out.p, cap2);
+                    D.ent.p, D.ent_count.p, D.group_prefix.p, D.within_prefix.p, k, L.g.kcap, D.gthr.p, L.n, nullptr, D.ent_out.p,
+                    cap2);
                 CU_TRY(cudaGetLastError());
                 PQV_TRY(fetch_entrants(D, D.ent_out.p, cap2, entrants, &overflow));
                 if (overflow) return fail(PQV_ECUDA, "entrant buffer overflow after regrow");
             }
         }
     }
+    if (trace) tt[2] = trace_now_ms();
     if (!launched.empty()) {
         DeviceState &D = *launched[0].D;
         float a = 0, b = 0;
@@ -657,6 +772,11 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
     }
     *out_count = (uint32_t)cnt;
     ctx->last = tm;
+    if (trace) {
+        tt[3] = trace_now_ms();
+        fprintf(stderr, "[pqv trace] topk_one: enqueue %.1f us, wait+fetch %.1f, replay %.1f (kernels %.1f)\n",
+                (tt[1] - tt[0]) * 1e3, (tt[2] - tt[1]) * 1e3, (tt[3] - tt[2]) * 1e3, tm.total_ms * 1e3);
+    }
     return PQV_OK;
 }
 
@@ -1097,11 +1217,34 @@ static int dist_launch(DeviceState &D, const float *d_data, const uint32_t *d_id
     const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_data) & 15) == 0);
     const size_t smem = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)SCAN_WARPS * pqv::TileCfg<0, true>::TILE_FLOATS * 4;
     const u64 NG = (n + 31) / 32;
+    constexpr uint32_t WIDE_MAX_DIM = 4096;
+    if (vec4 && dim <= WIDE_MAX_DIM && NG <= (u64)D.sm_count * 2 && (reinterpret_cast<uintptr_t>(d_vec) & 15) == 0) {
+        // short table (centroid ranking): one CTA per 32 rows instead of one warp (l2_dist_wide_kernel)
+        uint32_t ts = ((dim >> 2) + 3u) & ~3u;
+        if (((ts >> 2) & 1u) == 0) ts += 4;
+        static std::once_flag once;
+        static cudaError_t attr_err = cudaSuccess;
+        std::call_once(once, [] {
+            uint32_t tmax = ((WIDE_MAX_DIM >> 2) + 3u) & ~3u;
+            if (((tmax >> 2) & 1u) == 0) tmax += 4;
+            attr_err = cudaFuncSetAttribute(pqv::l2_dist_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)(32u * tmax * 4u));
+        });
+        if (attr_err != cudaSuccess) return fail(PQV_ECUDA, "l2_dist_wide_kernel attribute: %s", cudaGetErrorString(attr_err));
+        pqv::l2_dist_wide_kernel<<<(uint32_t)NG, 256, (size_t)32 * ts * 4, D.stream>>>(d_data, d_ids, n, dim, ts, d_vec, d_out,
+                                                                                     min_update);
+        CU_TRY(cudaGetLastError());
+        return PQV_OK;
+    }
     const uint32_t grid = (uint32_t)std::min<u64>((NG + SCAN_WARPS - 1) / SCAN_WARPS, (u64)D.sm_count * 4);
 #define DIST_GO(V, G)                                                                                        \
     do {                                                                                                     \
         auto kern = pqv::l2_dist_kernel<V, G, SCAN_WARPS>;                                                   \
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));          \
+        static size_t attr_smem = 0; /* sticky per kernel: only ever raise it */                             \
+        if (smem > attr_smem) {                                                                              \
+            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
+            attr_smem = smem;                                                                                \
+        }                                                                                                    \
         kern<<<grid, SCAN_WARPS * 32, smem, D.stream>>>(d_data, d_ids, n, dim, d_vec, d_out, min_update);    \
     } while (0)
     if (vec4) {

@@ -151,6 +151,136 @@ int rank_clusters(DeviceState &D, IvfIndex &ix, const float *query, uint32_t npr
     return PQV_OK;
 }
 
+constexpr uint32_t IVF_RANK_MAX_C = 16384;  // ivf_rank_kernel sorts pow2(C) u64 keys in shared memory (128 KiB)
+
+bool ivf_fused_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("PQV_IVF_FUSED");
+        return !(e && (!strcmp(e, "off") || !strcmp(e, "0")));
+    }();
+    return on;
+}
+
+// TopkBuilder::topk (src/ivf/search.rs:83-142) with one host<->device round trip: centroid distances, ranking
+// (index.rs:130-149), list expansion (index.rs:57-63), gathered scan + entrant filter and the entrants' row ids are all
+// enqueued back to back; the host only replays the reference heap over the ~1e3 entrants.  *done = false (nothing
+// written) when a centroid distance is NaN or the entrant buffer overflowed: the caller then takes the host-ranked path.
+int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, const float *query, uint32_t k,
+                     uint32_t nprobe, uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
+                     bool *done) {
+    *done = false;
+    static const bool trace = getenv("PQV_TRACE") != nullptr;
+    double tt[8] = {0};
+    if (trace) tt[0] = now_ms();
+    const uint32_t C = ix.n_clusters, np = std::min(nprobe, C), cp2 = pow2ceil(C);
+    const u64 n_bound = ix.ids.size();
+    const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
+    static std::once_flag attr_once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(attr_once, [] {
+        attr_err = cudaFuncSetAttribute(pqv::ivf_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(IVF_RANK_MAX_C * 8));
+    });
+    if (attr_err != cudaSuccess) return fail(PQV_ECUDA, "ivf_rank_kernel attribute: %s", cudaGetErrorString(attr_err));
+    PQV_TRY(D.d_query.ensure(ix.dim));
+    PQV_TRY(D.h_query.ensure(ix.dim));
+    PQV_TRY(D.final_topk.ensure(PQV_MAX_K));
+    PQV_TRY(D.ent_out.ensure((size_t)(1u << 16) + 1));
+    const uint32_t cap = (uint32_t)std::min<size_t>(D.ent_out.cap - 1, 0xFFFFFFF0u);
+    PQV_TRY(D.ent_rows.ensure(cap));
+    PQV_TRY(D.ivf_info.ensure(2));
+    PQV_TRY(D.h_ivf_info.ensure(2));
+    PQV_TRY(D.h_ent_out.ensure((size_t)ENT_FIRST_CHUNK + 1));
+    PQV_TRY(D.h_ent_rows.ensure(ENT_FIRST_CHUNK));
+    if (trace) tt[1] = now_ms();
+    memcpy(D.h_query.p, query, (size_t)ix.dim * 4);
+    CU_TRY(cudaMemcpyAsync(D.d_query.p, D.h_query.p, (size_t)ix.dim * 4, cudaMemcpyHostToDevice, D.stream));
+    CU_TRY(cudaMemsetAsync(D.ivf_info.p, 0, 16, D.stream));
+    CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
+    PQV_TRY(dist_launch(D, ix.d_centroids.p, nullptr, C, ix.dim, D.d_query.p, ix.d_cdist.p, 0));
+    pqv::ivf_rank_kernel<<<1, 1024, (size_t)cp2 * 8, D.stream>>>(ix.d_cdist.p, C, cp2, np, ix.d_offsets.p, ix.d_probe_cluster.p,
+                                                                 ix.d_probe_prefix.p, D.ivf_info.p,
+                                                                 reinterpret_cast<uint32_t *>(D.ivf_info.p + 1));
+    CU_TRY(cudaGetLastError());
+    pqv::ivf_expand_kernel<<<dim3(np, 8), 256, 0, D.stream>>>(ix.d_ids.p, ix.d_offsets.p, ix.d_probe_cluster.p,
+                                                              ix.d_probe_prefix.p, ix.d_cand.p);
+    CU_TRY(cudaGetLastError());
+    if (trace) tt[2] = now_ms();
+    ScanGeom g;
+    PQV_TRY(enqueue_scan(ctx, D, ds.shards[0].d_data, ix.d_cand.p, n_bound, ds.dim, D.d_query.p, k, order, 0u, nullptr,
+                         D.final_topk.p, D.ent_out.p, cap, true, &g, D.ivf_info.p));
+    pqv::ent_rows_kernel<<<32, 256, 0, D.stream>>>(D.ent_out.p, cap, ix.d_cand.p, D.ent_rows.p);
+    CU_TRY(cudaGetLastError());
+    const uint32_t first = std::min<uint32_t>(ENT_FIRST_CHUNK, cap);
+    CU_TRY(cudaMemcpyAsync(D.h_ent_out.p, D.ent_out.p, ((size_t)first + 1) * 8, cudaMemcpyDeviceToHost, D.stream));
+    CU_TRY(cudaMemcpyAsync(D.h_ent_rows.p, D.ent_rows.p, (size_t)first * 4, cudaMemcpyDeviceToHost, D.stream));
+    CU_TRY(cudaMemcpyAsync(D.h_ivf_info.p, D.ivf_info.p, 16, cudaMemcpyDeviceToHost, D.stream));
+    if (trace) tt[3] = now_ms();
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    if (trace) tt[4] = now_ms();
+    const u64 n_cand = D.h_ivf_info.p[0], count = D.h_ent_out.p[0];
+    if ((uint32_t)D.h_ivf_info.p[1] != 0 || count > cap) return PQV_OK;
+    std::vector<u64> entrants(count);
+    std::vector<uint32_t> erows(count);
+    const u64 got = std::min<u64>(count, first);
+    memcpy(entrants.data(), D.h_ent_out.p + 1, got * 8);
+    memcpy(erows.data(), D.h_ent_rows.p, got * 4);
+    if (count > got) {
+        CU_TRY(cudaMemcpyAsync(entrants.data() + got, D.ent_out.p + 1 + got, (count - got) * 8, cudaMemcpyDeviceToHost, D.stream));
+        CU_TRY(cudaMemcpyAsync(erows.data() + got, D.ent_rows.p + got, (count - got) * 4, cudaMemcpyDeviceToHost, D.stream));
+        CU_TRY(cudaStreamSynchronize(D.stream));
+    }
+    size_t cnt = 0;
+    const bool fast = !(flags & PQV_TIES_BY_POSITION) &&
+                      topk_without_replay(entrants.data(), count, k, flags, [&](uint32_t i, uint32_t) { return erows[i]; },
+                                          out_rows, out_dist, &cnt);
+    std::vector<u64> by_pos;  // (position << 32 | entrant index), sorted by position
+    if (!fast) {
+        by_pos.resize(count);
+        for (u64 i = 0; i < count; ++i) by_pos[i] = ((u64)key_pos(entrants[i]) << 32) | i;
+        radix_sort_field(by_pos, 32);
+    }
+    pqv_timing tm{};
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, D.ev[0], D.ev[1]);
+    cudaEventElapsedTime(&b, D.ev[1], D.ev[2]);
+    tm.scan_ms = a;
+    tm.post_ms = b;
+    tm.total_ms = a + b;
+    tm.scan_bytes = n_cand * (u64)ds.dim * 4;
+    tm.launches = 8;
+    tm.grid = g.grid;
+    tm.entrants = (uint32_t)count;
+    if (fast) {
+        // answered without the heap replay
+    } else if (flags & PQV_TIES_BY_POSITION) {
+        // the entrant set contains the k smallest keys (every key below the final threshold entered)
+        std::vector<u64> pairs(count);
+        for (u64 i = 0; i < count; ++i) pairs[i] = (by_pos[i] & 0xFFFFFFFF00000000ull) | erows[(uint32_t)by_pos[i]];
+        RowMap row_of;
+        row_of.pairs = pairs.data();
+        row_of.n_pairs = pairs.size();
+        cnt = emit_by_position(entrants, row_of, k, flags, out_rows, out_dist);
+    } else {
+        cnt = replay_ordered(
+            count,
+            [&](size_t i) {
+                const uint32_t e = (uint32_t)by_pos[i];
+                return ReplayItem{key_dist(entrants[e]), erows[e]};
+            },
+            k, flags, out_rows, out_dist);
+    }
+    *out_count = (uint32_t)cnt;
+    if (trace) {
+        tt[5] = now_ms();
+        fprintf(stderr, "[pqv trace] ivf_search: setup %.1f us, enqueue-rank %.1f, enqueue-scan %.1f, sync wait %.1f, replay %.1f\n",
+                (tt[1] - tt[0]) * 1e3, (tt[2] - tt[1]) * 1e3, (tt[3] - tt[2]) * 1e3, (tt[4] - tt[3]) * 1e3, (tt[5] - tt[4]) * 1e3);
+    }
+    ctx->last = tm;
+    *done = true;
+    return PQV_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -488,6 +618,11 @@ int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *q
     DeviceState &D = ctx->devs[ds->shards[0].di];
     DevGuard guard(D.dev);
     PQV_TRY(index_make_resident(D, *ix));
+    if (ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && !ix->ids.empty()) {
+        bool done = false;
+        PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, query, k, nprobe, flags, out_row_idx, out_dist, out_count, &done));
+        if (done) return PQV_OK;  // otherwise: NaN distance or entrant overflow -> host-ranked path below
+    }
     std::vector<uint32_t> ranked;
     PQV_TRY(rank_clusters(D, *ix, query, nprobe, ranked));
     const uint32_t np = (uint32_t)ranked.size();

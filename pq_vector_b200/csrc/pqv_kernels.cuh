@@ -235,6 +235,8 @@ struct ScanParams {
     const float *query;       // device
     const uint32_t *row_ids;  // device, GATHER only
     u64 n;                    // candidates to scan
+    const u64 *n_dev;         // device, may be null: overrides n at run time (candidate count produced on the device
+                              // by ivf_rank_kernel; n is then only the bound the launch was sized for)
     uint32_t dim;
     uint32_t k;
     uint32_t kcap;     // pow2 >= max(k, 32)
@@ -282,7 +284,11 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) l2_scan_topk_kernel(const Sc
     __shared__ uint32_t s_tau;
 
     const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const u64 NG = (p.n + 31) >> 5;
+    u64 n_rows = p.n;  // dense: stays a constant-bank operand (a register copy costs spills at 128 regs)
+    if constexpr (GATHER) {
+        if (p.n_dev) n_rows = *p.n_dev;
+    }
+    const u64 NG = (n_rows + 31) >> 5;
     const u64 g_begin = NG * blockIdx.x / gridDim.x;
     const u64 g_end = NG * (blockIdx.x + 1) / gridDim.x;
 
@@ -327,10 +333,10 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) l2_scan_topk_kernel(const Sc
         const u64 g = g0 + warp;
         const bool active = g < g_end;  // warp-uniform
         float d = 0.f;
-        if (active) d = group_distance<ORDER, VEC4, GATHER, RB, CBV>(p.data, p.row_ids, p.n, p.dim, g, s_query, tile, lane);
+        if (active) d = group_distance<ORDER, VEC4, GATHER, RB, CBV>(p.data, p.row_ids, n_rows, p.dim, g, s_query, tile, lane);
         const u64 pos = g * 32 + lane;
         const uint32_t bits = __float_as_uint(d);
-        const bool pass = active && pos < p.n && bits < s_tau;
+        const bool pass = active && pos < n_rows && bits < s_tau;
         const uint32_t m = __ballot_sync(0xffffffffu, pass);
         bool crossed = false;
         if (m) {
@@ -428,8 +434,8 @@ __global__ void __launch_bounds__(256) entrant_filter_kernel(const u64 *__restri
                                                              const u64 *__restrict__ group_prefix,
                                                              const u64 *__restrict__ within_prefix, const uint32_t k,
                                                              const uint32_t kcap, uint32_t *__restrict__ gthr,
-                                                             const u64 n, u64 *__restrict__ out,
-                                                             const uint32_t out_cap) {
+                                                             const u64 n_arg, const u64 *__restrict__ n_dev,
+                                                             u64 *__restrict__ out, const uint32_t out_cap) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *sA = reinterpret_cast<u64 *>(smem_raw);  // GP list
     u64 *sB = sA + kcap;                           // W list
@@ -457,6 +463,7 @@ __global__ void __launch_bounds__(256) entrant_filter_kernel(const u64 *__restri
     const uint32_t thr = s_thr;
     if (threadIdx.x == 0) gthr[b] = thr;
 
+    const u64 n = n_dev ? *n_dev : n_arg;  // must be what the scan kernel used (same CTA row ranges)
     const u64 NG = (n + 31) >> 5;
     const u64 base = (NG * b / G) * 32;
     const uint32_t cnt = ent_count[b];
@@ -508,6 +515,67 @@ __global__ void __launch_bounds__(WARPS * 32, 2) l2_dist_kernel(const float *__r
                 if (d < out[pos]) out[pos] = d;
             } else {
                 out[pos] = d;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// l2_dist_wide_kernel: the same sweep for SHORT tables (centroid ranking: C rows, index.rs:130-149).  With only a
+// few groups of 32 rows, one warp per group leaves the machine empty and the sweep becomes a chain of memory round
+// trips; here one CTA of 8 warps owns a group, warp w loads column blocks w, w+8, ... of all 32 rows and writes the
+// chain terms to a [32][dim/4] shared tile, then warp 0 runs the 32 serial chains (lane = row) in the reference order.
+// dim % 4 == 0, 16-byte aligned rows; ts = row stride of the tile in floats (ts % 4 == 0, ts/4 odd).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) l2_dist_wide_kernel(const float *__restrict__ data,
+                                                           const uint32_t *__restrict__ row_ids, const u64 n,
+                                                           const uint32_t dim, const uint32_t ts,
+                                                           const float *__restrict__ vec, float *__restrict__ out,
+                                                           const int min_update) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float *s_terms = reinterpret_cast<float *>(smem_raw);
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const u64 g_first = (u64)blockIdx.x * 32;
+    const uint32_t ncb = (dim + 127u) / 128u;
+    for (uint32_t cb = warp; cb < ncb; cb += 8) {
+        const uint32_t col0 = cb * 128u + (lane << 2);
+        if (col0 < dim) {
+            const float4 q4 = *reinterpret_cast<const float4 *>(vec + col0);
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 16) {
+                float4 v4[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    u64 pos = g_first + r0 + j;
+                    pos = pos < n ? pos : n - 1;
+                    const u64 row = row_ids ? (u64)row_ids[pos] : pos;
+                    v4[j] = ld_stream_v4(data + row * dim + col0);
+                }
+#pragma unroll
+                for (int j = 0; j < 16; ++j) s_terms[(r0 + j) * ts + (col0 >> 2)] = chunk4(q4, v4[j]);
+            }
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const float *trow = s_terms + lane * ts;
+        const uint32_t nt = dim >> 2;
+        float sum = 0.0f;
+        uint32_t j = 0;
+        for (; j + 4 <= nt; j += 4) {
+            const float4 t = *reinterpret_cast<const float4 *>(trow + j);
+            sum = __fadd_rn(sum, t.x);
+            sum = __fadd_rn(sum, t.y);
+            sum = __fadd_rn(sum, t.z);
+            sum = __fadd_rn(sum, t.w);
+        }
+        for (; j < nt; ++j) sum = __fadd_rn(sum, trow[j]);
+        const u64 pos = g_first + lane;
+        if (pos < n) {
+            if (min_update) {
+                if (sum < out[pos]) out[pos] = sum;
+            } else {
+                out[pos] = sum;
             }
         }
     }
@@ -723,7 +791,7 @@ __global__ void __launch_bounds__(256) gather_rows_kernel(const float *__restric
 
 // candidate_rows (src/ivf/index.rs:57-63): concatenate the inverted lists of the probed clusters in
 // rank order.  probe_cluster[r] = cluster id of rank r, probe_prefix[r] = first candidate position of
-// rank r (probe_prefix[nprobe] = n_cand).  One CTA per probed cluster.
+// rank r (probe_prefix[nprobe] = n_cand).  blockIdx.x = probed cluster, blockIdx.y = slice of its list.
 __global__ void __launch_bounds__(256) ivf_expand_kernel(const uint32_t *__restrict__ list_ids,
                                                          const u64 *__restrict__ list_offsets,
                                                          const uint32_t *__restrict__ probe_cluster,
@@ -732,7 +800,85 @@ __global__ void __launch_bounds__(256) ivf_expand_kernel(const uint32_t *__restr
     const uint32_t r = blockIdx.x;
     const uint32_t c = probe_cluster[r];
     const u64 src = list_offsets[c], len = list_offsets[c + 1] - src, dst = probe_prefix[r];
-    for (u64 i = threadIdx.x; i < len; i += blockDim.x) out_rows[dst + i] = list_ids[src + i];
+    for (u64 i = (u64)blockIdx.y * blockDim.x + threadIdx.x; i < len; i += (u64)gridDim.y * blockDim.x)
+        out_rows[dst + i] = list_ids[src + i];
+}
+
+// find_closest_centroids (src/ivf/index.rs:130-149) on the device: stable ascending sort of the C query-centroid
+// distances, keep the first nprobe.  For distances that are not NaN (sums of squares: >= +0, or +inf) the stable
+// sort under partial_cmp is the sort by (distance bits, cluster index); a NaN distance raises *nan_flag and the caller
+// ranks on the host instead.  Also emits the candidate-position prefix of the probed lists and the candidate count
+// (the scan kernel reads it through ScanParams::n_dev).  One CTA of 1024 threads, cp2 = pow2 >= C keys in shared memory.
+__global__ void __launch_bounds__(1024) ivf_rank_kernel(const float *__restrict__ cdist, const uint32_t C,
+                                                        const uint32_t cp2, const uint32_t nprobe,
+                                                        const u64 *__restrict__ list_offsets,
+                                                        uint32_t *__restrict__ probe_cluster,
+                                                        u64 *__restrict__ probe_prefix, u64 *__restrict__ n_cand_out,
+                                                        uint32_t *__restrict__ nan_flag) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *s = reinterpret_cast<u64 *>(smem_raw);
+    __shared__ u64 s_part[1024];
+    const uint32_t tid = threadIdx.x;
+    bool bad = false;
+    for (uint32_t i = tid; i < cp2; i += 1024) {
+        u64 key = KEY_MAX;
+        if (i < C) {
+            const float d = cdist[i];
+            bad |= (d != d);
+            key = ((u64)__float_as_uint(d) << 32) | i;
+        }
+        s[i] = key;
+    }
+    if (bad) atomicOr(nan_flag, 1u);
+    __syncthreads();
+    bitonic_sort_smem(s, cp2, tid, 1024);
+    __syncthreads();
+    const uint32_t per = (nprobe + 1023) / 1024;
+    const uint32_t b = min(nprobe, tid * per), e = min(nprobe, b + per);
+    u64 local = 0;
+    for (uint32_t r = b; r < e; ++r) {
+        const uint32_t c = (uint32_t)s[r];
+        local += list_offsets[c + 1] - list_offsets[c];
+    }
+    s_part[tid] = local;
+    __syncthreads();
+    if (tid < 32) {  // exclusive scan of the 1024 partials: 32 per lane, then across the warp
+        u64 acc = 0;
+        for (uint32_t i = 0; i < 32; ++i) acc += s_part[tid * 32 + i];
+        u64 incl = acc;
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)tid >= o) incl += v;
+        }
+        u64 run = incl - acc;
+        for (uint32_t i = 0; i < 32; ++i) {
+            const u64 v = s_part[tid * 32 + i];
+            s_part[tid * 32 + i] = run;
+            run += v;
+        }
+        if (tid == 31) {
+            probe_prefix[nprobe] = incl;
+            *n_cand_out = incl;
+        }
+    }
+    __syncthreads();
+    u64 run = s_part[tid];
+    for (uint32_t r = b; r < e; ++r) {
+        const uint32_t c = (uint32_t)s[r];
+        probe_cluster[r] = c;
+        probe_prefix[r] = run;
+        run += list_offsets[c + 1] - list_offsets[c];
+    }
+}
+
+// row ids of the surviving entrant keys of a gathered scan: rows_out[i] = cand[position of key i]
+// (keys = entrant_filter_kernel's out: [0] = count, keys from [1]).
+__global__ void __launch_bounds__(256) ent_rows_kernel(const u64 *__restrict__ ent_out, const uint32_t cap,
+                                                       const uint32_t *__restrict__ cand,
+                                                       uint32_t *__restrict__ rows_out) {
+    const u64 cnt = min(ent_out[0], (u64)cap);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (u64)gridDim.x * blockDim.x)
+        rows_out[i] = cand[(uint32_t)ent_out[1 + i]];
 }
 
 // centroid update (src/ivf/index.rs:436-453): per cluster, column-wise serial f32 sums over the member

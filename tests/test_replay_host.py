@@ -1,0 +1,65 @@
+"""CPU-only: pqv_replay_candidates (the host half of every top-k call: heap replay over the entrant keys, with the
+no-replay shortcut when the result cannot depend on the heap layout) against the oracle's restatement of the
+reference loop src/ivf/search.rs:112-141 / src/df_vector/exec.rs:264-275.  No GPU needed: the function is pure host."""
+import numpy as np
+import pytest
+
+import oracle as O
+import pq_vector_b200 as P
+
+
+def _keys(dist, pos):
+    return (dist.astype(np.float32).view(np.uint32).astype(np.uint64) << np.uint64(32)) | pos.astype(np.uint64)
+
+
+def _entrants(dist, k):
+    """rows the reference heap admits (push while len < k, else d < root), in position order"""
+    import heapq
+    h, keep = [], []
+    for i, d in enumerate(dist):
+        if len(h) < k:
+            heapq.heappush(h, -d)
+            keep.append(i)
+        elif d < -h[0]:
+            heapq.heapreplace(h, -d)
+            keep.append(i)
+    return np.array(keep, dtype=np.int64)
+
+
+@pytest.mark.parametrize("levels", [0, 3, 17, 1000])       # 0 = continuous (no ties), small = many exact ties
+@pytest.mark.parametrize("k", [1, 7, 100])
+@pytest.mark.parametrize("do_sqrt", [False, True])
+def test_replay_matches_oracle(levels, k, do_sqrt):
+    rng = np.random.default_rng(levels * 1000 + k)
+    n = 5000
+    dist = rng.random(n).astype(np.float32) * 4 + 0.5
+    if levels:
+        dist = (np.floor(dist * levels) / levels).astype(np.float32)
+    er, ed = O.heap_topk(dist, None, k, do_sqrt)
+    flags = P.PQV_SQRT if do_sqrt else 0
+    # (a) exactly the admitted rows, shuffled; (b) a superset: every row
+    ent = _entrants(dist, k)
+    for sel in (rng.permutation(ent), rng.permutation(n)):
+        rows, d = P.replay_candidates(_keys(dist[sel], sel), k, flags)
+        assert rows.tolist() == er.tolist()
+        assert d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+
+
+def test_replay_fewer_candidates_than_k_and_row_map():
+    dist = np.array([3.0, 1.0, 2.0, 1.0], dtype=np.float32)
+    ids = np.array([40, 30, 20, 10], dtype=np.uint32)
+    er, ed = O.heap_topk(dist, ids, 10, True)
+    rows, d = P.replay_candidates(_keys(dist, np.arange(4)), 10, P.PQV_SQRT, row_ids=ids)
+    assert rows.tolist() == er.tolist() and d.tolist() == ed.tolist()
+
+
+def test_replay_sqrt_collision_takes_the_heap_path():
+    # two distinct squared distances whose f32 square roots are equal: the output order is the heap's, not (d, pos)
+    a = np.float32(1.0)
+    b = np.nextafter(a, np.float32(2))
+    assert a != b and np.sqrt(a) == np.sqrt(b)
+    dist = np.array([b, 5.0, a, 4.0, 3.0], dtype=np.float32)
+    for k in (2, 3, 5):
+        er, ed = O.heap_topk(dist, None, k, True)
+        rows, d = P.replay_candidates(_keys(dist, np.arange(5)), k, P.PQV_SQRT)
+        assert rows.tolist() == er.tolist() and d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
