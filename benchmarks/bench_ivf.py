@@ -21,6 +21,7 @@ ap.add_argument("--max-iters", type=int, default=20)
 ap.add_argument("--nprobe", type=int, default=32)
 ap.add_argument("--k", type=int, default=100)
 ap.add_argument("--queries", type=int, default=50)
+ap.add_argument("--builds", type=int, default=3, help="builds to run; the first pays the one-time scratch allocations")
 a = ap.parse_args()
 
 ctx = P.Context([0])
@@ -30,18 +31,31 @@ qd = ctx.dataset(a.dim, a.queries)
 qd.fill_synthetic(a.queries, 7)
 queries = qd.read(0, a.queries)
 
-t0 = time.perf_counter()
-ix = ctx.ivf_build(ds, n_clusters=a.clusters, max_iters=a.max_iters, seed=42)
-build_s = time.perf_counter() - t0
-st = ix.build_stats()
+builds = []
+ix = None
+for _ in range(max(a.builds, 1)):
+    if ix is not None:
+        ix.drop()
+    t0 = time.perf_counter()
+    ix = ctx.ivf_build(ds, n_clusters=a.clusters, max_iters=a.max_iters, seed=42)
+    builds.append({"seconds": time.perf_counter() - t0, **ix.build_stats()})
+best = min(builds, key=lambda b: b["seconds"])
+build_s = best["seconds"]
+st = {k: v for k, v in best.items() if k != "seconds"}
 fa_s = st["final_assign_ms"] * 1e-3
 out = {
     "config": f"{a.rows} x {a.dim} f32, IVF C={a.clusters}, max_iters={a.max_iters}, seed=42; search nprobe={a.nprobe} k={a.k}",
-    "build_seconds": build_s, "build_breakdown_ms": st,
+    "build_seconds": build_s, "build_breakdown_ms": st, "first_build_seconds": builds[0]["seconds"],
+    "all_builds_seconds": [b["seconds"] for b in builds],
     "final_assign": {"seconds_incl_d2h_and_list_build": fa_s, "rows_gbs": a.rows * a.dim * 4 / fa_s / 1e9,
                      "f32_ops_per_s": 3.0 * a.rows * a.clusters * a.dim / fa_s,
                      "note": "3*N*C*dim non-fusable f32 ops (sub, mul, add), exact reference order"},
 }
+t0 = time.perf_counter()
+blob = ix.to_bytes()   # IvfIndex::to_bytes (index.rs:65-83): includes the one-time fetch of the device-built lists
+out["to_bytes_seconds"] = time.perf_counter() - t0
+out["blob_bytes"] = len(blob)
+del blob
 # search
 for q in queries[:3]:
     ix.search(ds, q, a.k, a.nprobe)

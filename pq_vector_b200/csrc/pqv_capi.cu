@@ -338,6 +338,8 @@ struct DeviceState {
     PinBuf<float> h_query;
     // fused IVF search: row ids of the entrants + (candidate count, NaN flag)
     DevBuf<uint32_t> ent_rows;
+    // device-side inverted-list build (csr_*_kernel)
+    DevBuf<uint32_t> csr_counts, csr_totals;
     DevBuf<u64> ivf_info;
     PinBuf<uint32_t> h_ent_rows;
     PinBuf<u64> h_ivf_info;

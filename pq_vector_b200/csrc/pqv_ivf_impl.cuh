@@ -67,7 +67,10 @@ struct IvfIndex {
     uint32_t dim = 0, n_clusters = 0;
     std::vector<float> centroids;
     std::vector<u64> offsets;  // n_clusters + 1
-    std::vector<uint32_t> ids;
+    std::vector<uint32_t> ids;  // host copy of the lists; after a device build it is fetched on first use
+    u64 n_ids = 0;
+    bool host_ids = true;        // `ids` holds the lists
+    bool lists_on_device = false;  // d_offsets / d_ids already hold the lists (device-built index)
     // device mirror (device 0 of the context), created on first search
     bool resident = false;
     DevBuf<float> d_centroids, d_cdist;
@@ -86,6 +89,40 @@ void csr_from_assign(const uint32_t *assign, u64 n, uint32_t n_clusters, std::ve
     ids.resize(n);
     std::vector<u64> cur(offsets.begin(), offsets.end() - 1);
     for (u64 i = 0; i < n; ++i) ids[cur[assign[i]]++] = (uint32_t)i;
+}
+
+// Inverted lists built on the device (csr_*_kernel, pqv_kernels.cuh).  *ok = false (nothing launched) when the cluster
+// count does not fit the kernels' shared-memory histogram; the caller then builds the lists on the host.
+constexpr uint32_t CSR_MAX_C = 51200;  // 200 KiB of u32 counters
+
+int csr_device(DeviceState &D, const uint32_t *d_assign, u64 n, uint32_t C, u64 *d_offsets, uint32_t *d_ids, bool *ok) {
+    *ok = false;
+    if (C > CSR_MAX_C || n == 0 || n > 0xFFFFFFFFull) return PQV_OK;
+    u64 R = (n + (u64)D.sm_count * 4 - 1) / ((u64)D.sm_count * 4);
+    R = std::min<u64>(std::max<u64>((R + 255) / 256 * 256, 256), 4096);
+    const u64 nb_max = std::max<u64>((64ull << 20) / C, 1);  // counts matrix <= 256 MiB
+    if ((n + R - 1) / R > nb_max) R = ((n + nb_max - 1) / nb_max + 255) / 256 * 256;
+    const uint32_t NB = (uint32_t)((n + R - 1) / R);
+    PQV_TRY(D.csr_counts.ensure((size_t)C * NB));
+    PQV_TRY(D.csr_totals.ensure(C));
+    const size_t smem = (size_t)C * 4;
+    static std::mutex mu;
+    static size_t attr_smem = 48 * 1024;
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        if (smem > attr_smem) {
+            CU_TRY(cudaFuncSetAttribute(pqv::csr_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CU_TRY(cudaFuncSetAttribute(pqv::csr_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            attr_smem = smem;
+        }
+    }
+    pqv::csr_count_kernel<<<NB, 256, smem, D.stream>>>(d_assign, n, (uint32_t)R, C, NB, D.csr_counts.p);
+    pqv::csr_scan_kernel<<<C, 256, 0, D.stream>>>(D.csr_counts.p, NB, D.csr_totals.p);
+    pqv::csr_offsets_kernel<<<1, 1024, 0, D.stream>>>(D.csr_totals.p, C, d_offsets);
+    pqv::csr_scatter_kernel<<<NB, 256, smem, D.stream>>>(d_assign, n, (uint32_t)R, C, NB, D.csr_counts.p, d_offsets, d_ids);
+    CU_TRY(cudaGetLastError());
+    *ok = true;
+    return PQV_OK;
 }
 
 int assign_device(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const float *d_centroids, uint32_t C,
@@ -107,18 +144,33 @@ IvfIndex *find_index(pqv_ctx *ctx, u64 h) {
 int index_make_resident(DeviceState &D, IvfIndex &ix) {
     if (ix.resident) return PQV_OK;
     PQV_TRY(ix.d_centroids.ensure(ix.centroids.size()));
-    PQV_TRY(ix.d_offsets.ensure(ix.offsets.size()));
-    PQV_TRY(ix.d_ids.ensure(std::max<size_t>(ix.ids.size(), 1)));
     PQV_TRY(ix.d_cdist.ensure(ix.n_clusters));
     PQV_TRY(ix.d_probe_cluster.ensure(ix.n_clusters));
     PQV_TRY(ix.d_probe_prefix.ensure((size_t)ix.n_clusters + 1));
-    PQV_TRY(ix.d_cand.ensure(std::max<size_t>(ix.ids.size(), 1)));
+    PQV_TRY(ix.d_cand.ensure(std::max<size_t>(ix.n_ids, 1)));
     CU_TRY(cudaMemcpyAsync(ix.d_centroids.p, ix.centroids.data(), ix.centroids.size() * 4, cudaMemcpyHostToDevice, D.stream));
-    CU_TRY(cudaMemcpyAsync(ix.d_offsets.p, ix.offsets.data(), ix.offsets.size() * 8, cudaMemcpyHostToDevice, D.stream));
-    if (!ix.ids.empty())
-        CU_TRY(cudaMemcpyAsync(ix.d_ids.p, ix.ids.data(), ix.ids.size() * 4, cudaMemcpyHostToDevice, D.stream));
+    if (!ix.lists_on_device) {
+        PQV_TRY(ix.d_offsets.ensure(ix.offsets.size()));
+        PQV_TRY(ix.d_ids.ensure(std::max<size_t>(ix.n_ids, 1)));
+        CU_TRY(cudaMemcpyAsync(ix.d_offsets.p, ix.offsets.data(), ix.offsets.size() * 8, cudaMemcpyHostToDevice, D.stream));
+        if (ix.n_ids)
+            CU_TRY(cudaMemcpyAsync(ix.d_ids.p, ix.ids.data(), ix.n_ids * 4, cudaMemcpyHostToDevice, D.stream));
+        ix.lists_on_device = true;
+    }
     CU_TRY(cudaStreamSynchronize(D.stream));
     ix.resident = true;
+    return PQV_OK;
+}
+
+// host copy of the lists of a device-built index (blob serialisation, candidate_rows, the host-ranked search)
+int index_host_ids(DeviceState &D, IvfIndex &ix) {
+    if (ix.host_ids) return PQV_OK;
+    ix.ids.resize(ix.n_ids);
+    if (ix.n_ids) {
+        CU_TRY(cudaMemcpyAsync(ix.ids.data(), ix.d_ids.p, ix.n_ids * 4, cudaMemcpyDeviceToHost, D.stream));
+        CU_TRY(cudaStreamSynchronize(D.stream));
+    }
+    ix.host_ids = true;
     return PQV_OK;
 }
 
@@ -173,7 +225,7 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
     double tt[8] = {0};
     if (trace) tt[0] = now_ms();
     const uint32_t C = ix.n_clusters, np = std::min(nprobe, C), cp2 = pow2ceil(C);
-    const u64 n_bound = ix.ids.size();
+    const u64 n_bound = ix.n_ids;
     const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
@@ -372,26 +424,35 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
         return bail(fail(PQV_ECUDA, "k-means init failed: %s", cudaGetErrorString(ce)));
     }
     int rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p, d_md.p, 0);  // index.rs:344-352
-    std::vector<float> md(init_n);
+    PinBuf<float> h_md;  // pinned: the sweep result comes back 1023 times
+    if (!rc) rc = h_md.ensure(init_n);
+    float *md = h_md.p;
     unsigned hw = std::thread::hardware_concurrency();
     const u64 workers = std::max<u64>(1, std::min<u64>(sum_workers ? sum_workers : (hw ? hw : 1), init_n));  // index.rs:259-265
     const u64 chunk = (init_n + workers - 1) / workers;
+    const u64 n_chunks = (init_n + chunk - 1) / chunk;
+    std::vector<float> local(n_chunks);
     for (uint32_t i = 1; i < C && !rc; ++i) {
         rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p + (size_t)(i - 1) * dim, d_md.p, 1);
         if (rc) break;
-        ce = cudaMemcpyAsync(md.data(), d_md.p, init_n * 4, cudaMemcpyDeviceToHost, D.stream);
+        ce = cudaMemcpyAsync(md, d_md.p, init_n * 4, cudaMemcpyDeviceToHost, D.stream);
         if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);
         if (ce != cudaSuccess) {
             rc = fail(PQV_ECUDA, "k-means++ sweep failed: %s", cudaGetErrorString(ce));
             break;
         }
-        float total = 0.0f;  // index.rs:356-370: per-chunk f32 sums, summed in chunk order
-        for (u64 s0 = 0; s0 < init_n; s0 += chunk) {
-            float local = 0.0f;
-            const u64 s1 = std::min<u64>(s0 + chunk, init_n);
-            for (u64 s = s0; s < s1; ++s) local += md[s];
-            total += local;
+        // index.rs:356-370: one serial f32 sum per worker chunk, then the chunk sums added in chunk order.  The chunk
+        // chains are independent, so they are advanced side by side (same bits, ~n_chunks x the instruction-level
+        // parallelism of walking them one after the other).
+        std::fill(local.begin(), local.end(), 0.0f);
+        const u64 full_chunks = init_n / chunk;  // chunks with all `chunk` elements
+        for (u64 o = 0; o < chunk; ++o) {
+            const float *col = md + o;
+            for (u64 c = 0; c < full_chunks; ++c) local[c] += col[c * chunk];
         }
+        for (u64 s = full_chunks * chunk; s < init_n; ++s) local[full_chunks] += md[s];
+        float total = 0.0f;
+        for (u64 c = 0; c < n_chunks; ++c) total += local[c];
         if (total > 0.0f) {  // index.rs:372-383
             const float threshold = rng.unit_f32() * total;
             float cumsum = 0.0f;
@@ -407,62 +468,125 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
         }
         if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "k-means++ pick failed: %s", cudaGetErrorString(ce));
     }
+    h_md.release();
     free_tmp();
     if (rc) return bail(rc);
     const double t_init = now_ms();
 
-    // ---- Lloyd (index.rs:392-454)
-    std::vector<uint32_t> assign(ns, 0), next(ns);
-    std::vector<u64> sizes(C, 0), moff;
+    // ---- Lloyd (index.rs:392-454).  Assignments, the changed count, the member lists and the centroid update all stay
+    // on the device; one 8-byte read per iteration decides whether to stop.
+    DevBuf<uint32_t> d_asg[2], d_mids;
+    DevBuf<u64> d_moff, d_changed;
+    PinBuf<u64> h_changed;
+    auto free_lloyd = [&]() {
+        d_asg[0].release();
+        d_asg[1].release();
+        d_mids.release();
+        d_moff.release();
+        d_changed.release();
+        h_changed.release();
+    };
+    rc = d_asg[0].ensure(ns);
+    if (!rc) rc = d_asg[1].ensure(ns);
+    if (!rc) rc = d_mids.ensure(ns);
+    if (!rc) rc = d_moff.ensure((size_t)C + 1);
+    if (!rc) rc = d_changed.ensure(1);
+    if (!rc) rc = h_changed.ensure(1);
+    if (!rc) {
+        ce = cudaMemsetAsync(d_asg[0].p, 0, ns * 4, D.stream);  // vec![0usize; n] (index.rs:392)
+        if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "Lloyd init failed: %s", cudaGetErrorString(ce));
+    }
+    int cur = 0;  // d_asg[cur] = assignments of the previous iteration
+    std::vector<uint32_t> h_assign;  // host fallback only (cluster count beyond the device list builder)
+    std::vector<u64> moff;
     std::vector<uint32_t> mids;
-    IVF_TRY(D.d_assign.ensure(ns));
-    DevBuf<uint32_t> d_mids;
-    DevBuf<u64> d_moff;
-    for (uint32_t iter = 0; iter < max_iters; ++iter) {
+    for (uint32_t iter = 0; iter < max_iters && !rc; ++iter) {
         ix->build_iters = iter + 1;
-        rc = assign_device(D, d_sample, ns, dim, D.d_centroids.p, C, D.d_assign.p);
-        if (!rc) {
-            ce = cudaMemcpyAsync(next.data(), D.d_assign.p, ns * 4, cudaMemcpyDeviceToHost, D.stream);
-            if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);
-            if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "Lloyd assignment failed: %s", cudaGetErrorString(ce));
+        uint32_t *prev = d_asg[cur].p, *next = d_asg[cur ^ 1].p;
+        rc = assign_device(D, d_sample, ns, dim, D.d_centroids.p, C, next);
+        if (rc) break;
+        ce = cudaMemsetAsync(d_changed.p, 0, 8, D.stream);
+        if (ce == cudaSuccess) {
+            pqv::count_changed_kernel<<<D.sm_count * 2, 256, 0, D.stream>>>(prev, next, ns,
+                                                                           reinterpret_cast<unsigned long long *>(d_changed.p));
+            ce = cudaGetLastError();
         }
-        if (rc) break;
-        u64 changed = 0;
-        for (u64 i = 0; i < ns; ++i) changed += assign[i] != next[i];
-        assign.swap(next);
-        if (changed == 0) break;  // index.rs:432-434
-        csr_from_assign(assign.data(), ns, C, moff, mids);
-        rc = d_mids.ensure(ns);
-        if (!rc) rc = d_moff.ensure((size_t)C + 1);
-        if (rc) break;
-        ce = cudaMemcpyAsync(d_mids.p, mids.data(), ns * 4, cudaMemcpyHostToDevice, D.stream);
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_moff.p, moff.data(), ((size_t)C + 1) * 8, cudaMemcpyHostToDevice, D.stream);
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_changed.p, d_changed.p, 8, cudaMemcpyDeviceToHost, D.stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);
         if (ce != cudaSuccess) {
-            rc = fail(PQV_ECUDA, "Lloyd update upload failed: %s", cudaGetErrorString(ce));
+            rc = fail(PQV_ECUDA, "Lloyd assignment failed: %s", cudaGetErrorString(ce));
             break;
+        }
+        cur ^= 1;
+        if (h_changed.p[0] == 0) break;  // index.rs:432-434
+        bool on_device = false;
+        rc = csr_device(D, next, ns, C, d_moff.p, d_mids.p, &on_device);
+        if (rc) break;
+        if (!on_device) {
+            h_assign.resize(ns);
+            ce = cudaMemcpyAsync(h_assign.data(), next, ns * 4, cudaMemcpyDeviceToHost, D.stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);
+            if (ce == cudaSuccess) {
+                csr_from_assign(h_assign.data(), ns, C, moff, mids);
+                ce = cudaMemcpyAsync(d_mids.p, mids.data(), ns * 4, cudaMemcpyHostToDevice, D.stream);
+            }
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_moff.p, moff.data(), ((size_t)C + 1) * 8, cudaMemcpyHostToDevice, D.stream);
+            if (ce != cudaSuccess) {
+                rc = fail(PQV_ECUDA, "Lloyd update upload failed: %s", cudaGetErrorString(ce));
+                break;
+            }
         }
         pqv::centroid_update_kernel<<<C, 256, 0, D.stream>>>(d_sample, dim, d_mids.p, d_moff.p, D.d_centroids.p);
         ce = cudaGetLastError();
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);  // mids/moff are reused next iteration
+        if (ce == cudaSuccess && !on_device) ce = cudaStreamSynchronize(D.stream);  // mids/moff are reused next iteration
         if (ce != cudaSuccess) {
             rc = fail(PQV_ECUDA, "centroid update failed: %s", cudaGetErrorString(ce));
             break;
         }
     }
-    d_mids.release();
-    d_moff.release();
+    if (!rc) {
+        ce = cudaStreamSynchronize(D.stream);
+        if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "Lloyd failed: %s", cudaGetErrorString(ce));
+    }
+    free_lloyd();
     if (rc) return bail(rc);
     const double t_lloyd = now_ms();
 
-    // ---- final assignment of all N rows (index.rs:189-206)
+    // ---- final assignment of all N rows (index.rs:189-206); the inverted lists are built on the device and stay
+    // there as the resident index, the host copy of the row ids is fetched when somebody asks for it (index_host_ids)
     ix->centroids.resize((size_t)C * dim);
     IVF_CU(cudaMemcpyAsync(ix->centroids.data(), D.d_centroids.p, (size_t)C * dim * 4, cudaMemcpyDeviceToHost, D.stream));
+    static const bool trace = getenv("PQV_TRACE") != nullptr;
+    double tf[4] = {now_ms(), 0, 0, 0};
     IVF_TRY(D.d_assign.ensure(n));
     IVF_TRY(assign_device(D, sh.d_data, n, dim, D.d_centroids.p, C, D.d_assign.p));
-    std::vector<uint32_t> full(n);
-    IVF_CU(cudaMemcpyAsync(full.data(), D.d_assign.p, n * 4, cudaMemcpyDeviceToHost, D.stream));
-    IVF_CU(cudaStreamSynchronize(D.stream));
-    csr_from_assign(full.data(), n, C, ix->offsets, ix->ids);
+    if (trace) {
+        cudaStreamSynchronize(D.stream);
+        tf[1] = now_ms();
+    }
+    IVF_TRY(ix->d_offsets.ensure((size_t)C + 1));
+    IVF_TRY(ix->d_ids.ensure(n));
+    bool lists_built = false;
+    IVF_TRY(csr_device(D, D.d_assign.p, n, C, ix->d_offsets.p, ix->d_ids.p, &lists_built));
+    if (trace) {
+        cudaStreamSynchronize(D.stream);
+        tf[2] = now_ms();
+        fprintf(stderr, "[pqv trace] ivf_build final: assign %.2f ms (device sweep %.2f), lists %.2f ms\n", tf[1] - tf[0],
+                ctx->last_assign.total_ms, tf[2] - tf[1]);
+    }
+    ix->n_ids = n;
+    if (lists_built) {
+        ix->offsets.resize((size_t)C + 1);
+        IVF_CU(cudaMemcpyAsync(ix->offsets.data(), ix->d_offsets.p, ((size_t)C + 1) * 8, cudaMemcpyDeviceToHost, D.stream));
+        IVF_CU(cudaStreamSynchronize(D.stream));
+        ix->lists_on_device = true;
+        ix->host_ids = false;
+    } else {
+        std::vector<uint32_t> full(n);
+        IVF_CU(cudaMemcpyAsync(full.data(), D.d_assign.p, n * 4, cudaMemcpyDeviceToHost, D.stream));
+        IVF_CU(cudaStreamSynchronize(D.stream));
+        csr_from_assign(full.data(), n, C, ix->offsets, ix->ids);
+    }
     const double t_end = now_ms();
     ix->build_ms[0] = t_init - t_begin;
     ix->build_ms[1] = t_lloyd - t_init;
@@ -522,6 +646,7 @@ int pqv_ivf_from_bytes(pqv_ctx *ctx, const uint8_t *bytes, uint64_t len, uint64_
         off += (u64)l * 4;
         ix->offsets[c + 1] = ix->offsets[c] + l;
     }
+    ix->n_ids = ix->ids.size();
     std::lock_guard<std::mutex> lk(ctx->mu);
     const u64 h = ctx->next_handle++;
     ctx->indexes[h] = ix;
@@ -534,9 +659,14 @@ int pqv_ivf_to_bytes(pqv_ctx *ctx, uint64_t index, uint8_t *out, uint64_t cap, u
     std::lock_guard<std::mutex> lk(ctx->mu);
     IvfIndex *ix = find_index(ctx, index);
     if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
-    const u64 need = 8 + (u64)ix->centroids.size() * 4 + (u64)ix->n_clusters * 4 + (u64)ix->ids.size() * 4;
+    const u64 need = 8 + (u64)ix->centroids.size() * 4 + (u64)ix->n_clusters * 4 + ix->n_ids * 4;
     *out_len = need;
     if (!out || cap < need) return out ? fail(PQV_ELIMIT, "blob needs %llu bytes", (unsigned long long)need) : PQV_OK;
+    {
+        DeviceState &D = ctx->devs[0];
+        DevGuard guard(D.dev);
+        PQV_TRY(index_host_ids(D, *ix));
+    }
     uint8_t *p = out;  // index.rs:65-83
     memcpy(p, &ix->dim, 4);
     p += 4;
@@ -561,7 +691,7 @@ int pqv_ivf_info(pqv_ctx *ctx, uint64_t index, uint32_t *out_dim, uint32_t *out_
     if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
     if (out_dim) *out_dim = ix->dim;
     if (out_clusters) *out_clusters = ix->n_clusters;
-    if (out_ids) *out_ids = ix->ids.size();
+    if (out_ids) *out_ids = ix->n_ids;
     return PQV_OK;
 }
 
@@ -587,6 +717,7 @@ int pqv_ivf_candidate_rows(pqv_ctx *ctx, uint64_t index, const float *query, uin
     DeviceState &D = ctx->devs[0];
     DevGuard guard(D.dev);
     PQV_TRY(index_make_resident(D, *ix));
+    PQV_TRY(index_host_ids(D, *ix));
     std::vector<uint32_t> ranked;
     PQV_TRY(rank_clusters(D, *ix, query, nprobe, ranked));
     u64 total = 0;
@@ -614,15 +745,16 @@ int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *q
     PQV_TRY(check_topk_args(k, ds->dim, flags));
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
     if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search needs a single-device dataset");
-    if (!ix->ids.empty() && ix->ids.size() > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %zu rows, dataset has %llu", ix->ids.size(), (unsigned long long)ds->n_rows);
+    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
     DeviceState &D = ctx->devs[ds->shards[0].di];
     DevGuard guard(D.dev);
     PQV_TRY(index_make_resident(D, *ix));
-    if (ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && !ix->ids.empty()) {
+    if (ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids) {
         bool done = false;
         PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, query, k, nprobe, flags, out_row_idx, out_dist, out_count, &done));
         if (done) return PQV_OK;  // otherwise: NaN distance or entrant overflow -> host-ranked path below
     }
+    PQV_TRY(index_host_ids(D, *ix));
     std::vector<uint32_t> ranked;
     PQV_TRY(rank_clusters(D, *ix, query, nprobe, ranked));
     const uint32_t np = (uint32_t)ranked.size();

@@ -881,6 +881,134 @@ __global__ void __launch_bounds__(256) ent_rows_kernel(const u64 *__restrict__ e
         rows_out[i] = cand[(uint32_t)ent_out[1 + i]];
 }
 
+// ------------------------------------------------------------------------------------------------
+// Inverted lists on the device (src/ivf/index.rs:202-206: per-cluster row ids, ascending) = a stable counting sort of
+// the row ids by cluster.  Block b owns rows [b*R, (b+1)*R):
+//   csr_count_kernel    counts[c*NB + b] = rows of block b assigned to cluster c              (shared-memory histogram)
+//   csr_scan_kernel     per cluster: counts[c*NB + .] -> exclusive prefix over blocks, totals[c] = list length
+//   csr_offsets_kernel  offsets[0..C] = exclusive prefix of totals (u64, the CSR offsets)
+//   csr_scatter_kernel  ids[offsets[c] + counts[c*NB + b] + rank within the block] = row
+// In the scatter the block walks its rows 256 at a time; inside a chunk the warps take their slots one after the other
+// (one barrier per warp) and a warp ranks its lanes with match_any, so every list comes out in ascending row order.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) csr_count_kernel(const uint32_t *__restrict__ assign, const u64 n,
+                                                        const uint32_t R, const uint32_t C, const uint32_t NB,
+                                                        uint32_t *__restrict__ counts) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *hist = reinterpret_cast<uint32_t *>(smem_raw);
+    for (uint32_t c = threadIdx.x; c < C; c += 256) hist[c] = 0;
+    __syncthreads();
+    const u64 r0 = (u64)blockIdx.x * R, r1 = min(n, r0 + R);
+    for (u64 r = r0 + threadIdx.x; r < r1; r += 256) atomicAdd(&hist[assign[r]], 1u);
+    __syncthreads();
+    for (uint32_t c = threadIdx.x; c < C; c += 256) counts[(u64)c * NB + blockIdx.x] = hist[c];
+}
+
+__global__ void __launch_bounds__(256) csr_scan_kernel(uint32_t *__restrict__ counts, const uint32_t NB,
+                                                       uint32_t *__restrict__ totals) {
+    __shared__ uint32_t s_part[256];
+    uint32_t *row = counts + (u64)blockIdx.x * NB;
+    const uint32_t per = (NB + 255) / 256;
+    const uint32_t b = min(NB, threadIdx.x * per), e = min(NB, b + per);
+    uint32_t local = 0;
+    for (uint32_t i = b; i < e; ++i) local += row[i];
+    s_part[threadIdx.x] = local;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        uint32_t acc = 0;
+        for (uint32_t i = 0; i < 8; ++i) acc += s_part[threadIdx.x * 8 + i];
+        uint32_t incl = acc;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)threadIdx.x >= o) incl += v;
+        }
+        uint32_t run = incl - acc;
+        for (uint32_t i = 0; i < 8; ++i) {
+            const uint32_t v = s_part[threadIdx.x * 8 + i];
+            s_part[threadIdx.x * 8 + i] = run;
+            run += v;
+        }
+        if (threadIdx.x == 31) totals[blockIdx.x] = incl;
+    }
+    __syncthreads();
+    uint32_t run = s_part[threadIdx.x];
+    for (uint32_t i = b; i < e; ++i) {
+        const uint32_t v = row[i];
+        row[i] = run;
+        run += v;
+    }
+}
+
+__global__ void __launch_bounds__(1024) csr_offsets_kernel(const uint32_t *__restrict__ totals, const uint32_t C,
+                                                           u64 *__restrict__ offsets) {
+    __shared__ u64 s_part[1024];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t per = (C + 1023) / 1024;
+    const uint32_t b = min(C, tid * per), e = min(C, b + per);
+    u64 local = 0;
+    for (uint32_t i = b; i < e; ++i) local += totals[i];
+    s_part[tid] = local;
+    __syncthreads();
+    if (tid < 32) {
+        u64 acc = 0;
+        for (uint32_t i = 0; i < 32; ++i) acc += s_part[tid * 32 + i];
+        u64 incl = acc;
+        for (int o = 1; o < 32; o <<= 1) {
+            const u64 v = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)tid >= o) incl += v;
+        }
+        u64 run = incl - acc;
+        for (uint32_t i = 0; i < 32; ++i) {
+            const u64 v = s_part[tid * 32 + i];
+            s_part[tid * 32 + i] = run;
+            run += v;
+        }
+        if (tid == 31) offsets[C] = incl;
+    }
+    __syncthreads();
+    u64 run = s_part[tid];
+    for (uint32_t i = b; i < e; ++i) {
+        offsets[i] = run;
+        run += totals[i];
+    }
+}
+
+__global__ void __launch_bounds__(256) csr_scatter_kernel(const uint32_t *__restrict__ assign, const u64 n,
+                                                          const uint32_t R, const uint32_t C, const uint32_t NB,
+                                                          const uint32_t *__restrict__ counts,
+                                                          const u64 *__restrict__ offsets, uint32_t *__restrict__ ids) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    uint32_t *cur = reinterpret_cast<uint32_t *>(smem_raw);  // next free slot of every list for this block
+    for (uint32_t c = threadIdx.x; c < C; c += 256) cur[c] = (uint32_t)offsets[c] + counts[(u64)c * NB + blockIdx.x];
+    __syncthreads();
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const u64 r0 = (u64)blockIdx.x * R, r1 = min(n, r0 + R);
+    for (u64 base = r0; base < r1; base += 256) {
+        const u64 r = base + threadIdx.x;
+        const bool active = r < r1;
+        const uint32_t c = active ? assign[r] : 0xFFFFFFFFu;
+        const uint32_t peers = __match_any_sync(0xffffffffu, c);
+        const uint32_t leader = __ffs(peers) - 1;
+        uint32_t slot = 0;
+        for (uint32_t w = 0; w < 8; ++w) {
+            if (warp == w && active && lane == leader) slot = atomicAdd(&cur[c], __popc(peers));
+            __syncthreads();
+        }
+        slot = __shfl_sync(0xffffffffu, slot, leader);
+        if (active) ids[slot + __popc(peers & ((1u << lane) - 1u))] = (uint32_t)r;
+    }
+}
+
+// Lloyd bookkeeping (src/ivf/index.rs:417-420): how many assignments changed since the previous iteration
+__global__ void __launch_bounds__(256) count_changed_kernel(const uint32_t *__restrict__ prev,
+                                                            const uint32_t *__restrict__ next, const u64 n,
+                                                            unsigned long long *__restrict__ changed) {
+    unsigned long long local = 0;
+    for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) local += prev[i] != next[i];
+    for (int o = 16; o > 0; o >>= 1) local += __shfl_down_sync(0xffffffffu, local, o);
+    if ((threadIdx.x & 31) == 0 && local) atomicAdd(changed, local);
+}
+
 // centroid update (src/ivf/index.rs:436-453): per cluster, column-wise serial f32 sums over the member
 // rows in ascending row order (the order the reference's `for i in 0..n` visits them), then `/= size`
 // when size > 0; an empty cluster becomes the origin.  One CTA per cluster, a thread per
