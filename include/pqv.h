@@ -180,6 +180,22 @@ PQV_API int pqv_l2_topk_candidates(pqv_ctx *ctx, uint64_t handle, const float *q
 PQV_API int pqv_replay_candidates(const uint64_t *keys, uint64_t n_keys, const uint32_t *row_ids, uint32_t k,
                                   uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count);
 
+/* Batched variant (config C5: many queries, rows sharded over the ranks).  pqv_l2_topk_batch_keys answers the batch
+ * over this rank's slice in one tensor-core pass and returns, per query, the k + 1 smallest
+ * exact keys of the slice: out_keys[q*(k+1) + i] ascending, out_count[q] of them valid; out_count[q] = 0xFFFFFFFF when
+ * the slice could not decide the query (non-finite inputs, candidate buffers full, batch too small for the pass).
+ * The ranks exchange keys and counts with ONE all-gather ([rank][query][k+1] u64 and [rank][query] u32) and each calls
+ * pqv_merge_batch_keys (pure host): the k + 1 smallest keys of the whole table are among the slices' k + 1 smallest,
+ * so a query is final when its k-th and (k+1)-th smallest distances differ and its k returned values are pairwise
+ * distinct -- then the reference loop (src/ivf/search.rs:112-141, src/df_vector/exec.rs:257-277) can only produce this
+ * answer.  out_needs_replay[q] = 1 marks the queries whose answer hinges on the reference heap's layout: those go
+ * through pqv_l2_topk_candidates + pqv_replay_candidates. */
+PQV_API int pqv_l2_topk_batch_keys(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k,
+                                   uint32_t flags, uint32_t pos_base, uint64_t *out_keys, uint32_t *out_count);
+PQV_API int pqv_merge_batch_keys(const uint64_t *keys, const uint32_t *counts, uint32_t n_ranks, uint32_t n_queries,
+                                 uint32_t k, uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count,
+                                 uint8_t *out_needs_replay);
+
 /* ---- measurement hooks (bench.py / ncu) ------------------------------------------------------- */
 typedef struct {
     double scan_ms;        /* CUDA-event time of the last distance+select kernel (on the library's stream) */

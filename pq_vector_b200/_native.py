@@ -72,6 +72,10 @@ SIGNATURES = {
     "pqv_l2_topk_candidates": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_uint64,
                                          u64p]),
     "pqv_replay_candidates": (C.c_int, [u64p, C.c_uint64, u32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),
+    "pqv_l2_topk_batch_keys": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u64p,
+                                         u32p]),
+    "pqv_merge_batch_keys": (C.c_int, [u64p, u32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p, u32p,
+                                       C.POINTER(C.c_uint8)]),
     "pqv_last_timing": (C.c_int, [ctxp, C.POINTER(PqvTiming)]),
     "pqv_last_batch_timing": (C.c_int, [ctxp, C.POINTER(PqvBatchTiming)]),
     "pqv_last_assign_timing": (C.c_int, [ctxp, C.POINTER(PqvAssignTiming)]),

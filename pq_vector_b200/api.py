@@ -252,6 +252,20 @@ class Dataset:
             _check(rc)
             return keys[:cnt.value]
 
+    def l2_topk_batch_keys(self, queries, k: int, flags: int = N.PQV_SQRT, pos_base: int = 0):
+        """Per-rank half of a sharded batched search: (keys [nq, k+1] u64, counts [nq] u32), see pqv.h."""
+        q = _f32(queries)
+        if q.ndim == 1:
+            q = q[None, :]
+        if q.shape[1] != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.shape[1]}")
+        nq = q.shape[0]
+        keys = np.full((nq, k + 1), np.iinfo(np.uint64).max, dtype=np.uint64)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        _check(_lib.pqv_l2_topk_batch_keys(self.ctx._h, self.handle, _ptr(q, C.c_float), nq, k, flags, pos_base,
+                                           _ptr(keys, C.c_uint64), _ptr(cnt, C.c_uint32)))
+        return keys, cnt
+
     def bench_scan(self, query, k: int, flags: int, iters: int) -> float:
         q = _f32(query)
         ms = C.c_double()
@@ -326,6 +340,23 @@ def replay_candidates(keys, k: int, flags: int = N.PQV_SQRT, row_ids=None):
     _check(_lib.pqv_replay_candidates(_ptr(keys, C.c_uint64), keys.size, _ptr(ids, C.c_uint32), k, flags,
                                       _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), C.byref(cnt)))
     return rows[:cnt.value].copy(), dist[:cnt.value].copy()
+
+
+def merge_batch_keys(keys, counts, k: int, flags: int = N.PQV_SQRT):
+    """Merge the ranks' per-query key lists (keys [world, nq, k+1] u64, counts [world, nq] u32; pqv_merge_batch_keys).
+    Returns (rows [nq, k], dist [nq, k], count [nq], needs_replay [nq] bool)."""
+    keys = np.ascontiguousarray(keys, dtype=np.uint64)
+    counts = np.ascontiguousarray(counts, dtype=np.uint32)
+    world, nq = counts.shape
+    assert keys.shape == (world, nq, k + 1)
+    rows = np.zeros((nq, k), dtype=np.uint32)
+    dist = np.zeros((nq, k), dtype=np.float32)
+    cnt = np.zeros(nq, dtype=np.uint32)
+    need = np.zeros(nq, dtype=np.uint8)
+    _check(_lib.pqv_merge_batch_keys(_ptr(keys, C.c_uint64), _ptr(counts, C.c_uint32), world, nq, k, flags,
+                                     _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), _ptr(cnt, C.c_uint32),
+                                     _ptr(need, C.c_uint8)))
+    return rows, dist, cnt, need.astype(bool)
 
 
 class TopkStream:

@@ -1149,6 +1149,72 @@ int pqv_replay_candidates(const uint64_t *keys, uint64_t n_keys, const uint32_t 
     return PQV_OK;
 }
 
+int pqv_l2_topk_batch_keys(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k,
+                           uint32_t flags, uint32_t pos_base, uint64_t *out_keys, uint32_t *out_count) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    if (n_queries && (!queries || !out_keys || !out_count)) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (flags & PQV_TIES_BY_POSITION) return fail(PQV_EINVAL, "batch keys are only defined for the reference tie order");
+    if ((u64)pos_base + ds->n_rows > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "global row ids are u32");
+    for (uint32_t q = 0; q < n_queries; ++q) out_count[q] = 0xFFFFFFFFu;
+    ctx->last_batch = pqv_batch_timing{};
+    if (n_queries && ds->n_rows == 0) {  // an empty slice contributes nothing
+        for (uint32_t q = 0; q < n_queries; ++q) out_count[q] = 0;
+        return PQV_OK;
+    }
+    if (n_queries && batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k)) {
+        DeviceState &D = ctx->devs[ds->shards[0].di];
+        DevGuard guard(D.dev);
+        std::vector<uint8_t> handled(n_queries, 0);
+        PQV_TRY(batch_topk(ctx, D, *ds, ds->n_rows, ds->dim, queries, n_queries, k, flags, nullptr, nullptr, nullptr, handled,
+                           reinterpret_cast<u64 *>(out_keys), out_count, pos_base));
+    }
+    return PQV_OK;
+}
+
+int pqv_merge_batch_keys(const uint64_t *keys, const uint32_t *counts, uint32_t n_ranks, uint32_t n_queries, uint32_t k,
+                         uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count,
+                         uint8_t *out_needs_replay) {
+    if (n_queries && n_ranks && (!keys || !counts)) return fail(PQV_EINVAL, "null argument");
+    if (n_queries && (!out_row_idx || !out_dist || !out_count || !out_needs_replay)) return fail(PQV_EINVAL, "null argument");
+    if (k == 0) return fail(PQV_EINVAL, "k must be > 0");
+    const size_t kp = (size_t)k + 1;
+    std::vector<u64> all;
+    for (uint32_t q = 0; q < n_queries; ++q) {
+        out_count[q] = 0;
+        out_needs_replay[q] = 0;
+        all.clear();
+        for (uint32_t r = 0; r < n_ranks; ++r) {
+            const uint32_t c = counts[(size_t)r * n_queries + q];
+            if (c == 0xFFFFFFFFu || c > kp) {  // some slice could not decide this query
+                out_needs_replay[q] = 1;
+                break;
+            }
+            const u64 *src = reinterpret_cast<const u64 *>(keys) + ((size_t)r * n_queries + q) * kp;
+            all.insert(all.end(), src, src + c);
+        }
+        if (out_needs_replay[q]) continue;
+        // the k + 1 smallest keys of the whole table are among the slices' k + 1 smallest
+        const size_t take = std::min<size_t>(kp, all.size());
+        std::partial_sort(all.begin(), all.begin() + take, all.end());
+        const size_t cnt = std::min<size_t>(k, all.size());
+        bool tie = all.size() > k && (uint32_t)(all[k - 1] >> 32) == (uint32_t)(all[k] >> 32);  // kept set = heap layout's
+        if (cnt && (uint32_t)(all[cnt - 1] >> 32) > 0x7F800000u) tie = true;                       // NaN: reference-specific
+        for (size_t i = 0; i < cnt && !tie; ++i) {
+            const float d = key_dist(all[i]);
+            out_row_idx[(size_t)q * k + i] = key_pos(all[i]);
+            out_dist[(size_t)q * k + i] = (flags & PQV_SQRT) ? sqrtf(d) : d;
+            if (i && out_dist[(size_t)q * k + i] == out_dist[(size_t)q * k + i - 1]) tie = true;  // order = heap layout's
+        }
+        if (tie) out_needs_replay[q] = 1;
+        else out_count[q] = (uint32_t)cnt;
+    }
+    return PQV_OK;
+}
+
 int pqv_last_timing(pqv_ctx *ctx, pqv_timing *out) {
     if (!ctx || !out) return fail(PQV_EINVAL, "null argument");
     *out = ctx->last;

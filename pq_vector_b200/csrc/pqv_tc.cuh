@@ -973,14 +973,15 @@ pair_dist_kernel(const float *__restrict__ rows, uint32_t dim, const float *__re
 }
 
 // one CTA per query: the kk = min(k + 1, cnt) smallest keys of the query's segment (8-pass MSB-first radix select on the
-// u64 keys, then a bitonic sort of the survivors in shared memory).  out_keys[q][0..k) ascending; out_info[q] =
+// u64 keys, then a bitonic sort of the survivors in shared memory).  out_keys[q][0..kout) ascending; out_info[q] =
 // count | TIE << 30 | OVERFLOW << 31 where TIE means the caller must re-run the query through the single-query path.
 constexpr uint32_t SEL_TIE = 1u << 30, SEL_OVERFLOW = 1u << 31;
 constexpr int SEL_MAX = 2048;  // >= PQV_MAX_K + 1, power of two
 
 __global__ void __launch_bounds__(256) topk_select_kernel(const u64 *__restrict__ seg, uint32_t cap_q,
                                                           const uint32_t *__restrict__ cntq, uint32_t k, int apply_sqrt,
-                                                          u64 *__restrict__ out_keys, uint32_t *__restrict__ out_info) {
+                                                          u64 *__restrict__ out_keys, uint32_t *__restrict__ out_info,
+                                                          uint32_t kout) {
     const uint32_t q = blockIdx.x;
     const uint32_t raw_cnt = cntq[q];
     const uint32_t cnt = min(raw_cnt, cap_q);
@@ -1047,9 +1048,11 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const u64 *__restrict_
             }
             __syncthreads();
         }
+    // kout = k: the k winners; kout = k + 1 (sharded search): the boundary key too, the ranks' lists are merged later
     const uint32_t nout = min(k, cnt);
+    if (kout > k && threadIdx.x == 0 && cnt > k) out_keys[(size_t)q * kout + k] = buf[k];
     for (uint32_t i = threadIdx.x; i < nout; i += blockDim.x) {
-        out_keys[(size_t)q * k + i] = buf[i];
+        out_keys[(size_t)q * kout + i] = buf[i];
         if (i + 1 < nout) {  // returned values must be pairwise distinct, else their order is the heap layout's
             const float d0 = __uint_as_float((uint32_t)(buf[i] >> 32)), d1 = __uint_as_float((uint32_t)(buf[i + 1] >> 32));
             const bool same = apply_sqrt ? (__fsqrt_rn(d0) == __fsqrt_rn(d1)) : (d0 == d1);
@@ -1060,7 +1063,7 @@ __global__ void __launch_bounds__(256) topk_select_kernel(const u64 *__restrict_
     if (threadIdx.x == 0 && cnt > k && (uint32_t)(buf[k - 1] >> 32) == (uint32_t)(buf[k] >> 32)) atomicOr(&s_tie, 1u);
     __syncthreads();
     if (threadIdx.x == 0)
-        out_info[q] = nout | (s_tie ? SEL_TIE : 0u) | ((raw_cnt > cap_q || s_fill > (uint32_t)SEL_MAX) ? SEL_OVERFLOW : 0u);
+        out_info[q] = min(kout, cnt) | (s_tie ? SEL_TIE : 0u) | ((raw_cnt > cap_q || s_fill > (uint32_t)SEL_MAX) ? SEL_OVERFLOW : 0u);
 }
 
 #undef BAR_FULL

@@ -196,7 +196,10 @@ bool batch_path_applies(const Dataset &ds, const float *d_rows, uint32_t nq, uin
 // single-query path (ties whose order depends on the reference heap's layout, or a declined batch).
 int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, const float *queries, uint32_t nq,
                uint32_t k, uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
-               std::vector<uint8_t> &handled) {
+               std::vector<uint8_t> &handled, u64 *raw_keys = nullptr, uint32_t *raw_count = nullptr, uint32_t pos_base = 0) {
+    // raw mode (raw_keys != null, the per-rank half of a sharded search): per query the k + 1 smallest exact keys of
+    // this slice go to raw_keys[q*(k+1) ..] with pos_base added to the positions, raw_count[q] = how many are valid, or
+    // 0xFFFFFFFF when this slice could not decide the query (the caller falls back to the single-query exchange)
     namespace T = pqv::tc;
     Shard &sh = ds.shards[0];
     const float *d_rows = sh.d_data;
@@ -232,7 +235,8 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     PQV_TRY(D.tb_U.ensure((size_t)nq_pad * ldU));
     PQV_TRY(D.tb_cand.ensure((size_t)grid * region_cap));
     PQV_TRY(D.tb_seg.ensure((size_t)nq * cap_q));
-    PQV_TRY(D.tb_keys.ensure((size_t)nq * k));
+    const uint32_t kout = raw_keys ? k + 1 : k;
+    PQV_TRY(D.tb_keys.ensure((size_t)nq * kout));
     PQV_TRY(D.tc_mu.ensure(dim));
     if (sh.norms_cap < n) {
         sh.drop_norms();
@@ -240,7 +244,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
         if (e != cudaSuccess) return fail(PQV_ENOMEM, "row-norm cache of %llu rows: %s", (unsigned long long)n, cudaGetErrorString(e));
         sh.norms_cap = n;
     }
-    PQV_TRY(D.h_batch_keys.ensure((size_t)nq * k + nq + 2));
+    PQV_TRY(D.h_batch_keys.ensure((size_t)nq * kout + nq + 2));
     float *qw = D.tb_qf.p, *q2 = D.tb_qf.p + nq_pad, *qtheta = D.tb_qf.p + 2 * (size_t)nq_pad;
     uint32_t *qbounds = D.tb_u32.p, *dflags = D.tb_u32.p + 1, *cntq = D.tb_u32.p + 4, *region_count = D.tb_u32.p + 4 + nq;
     PQV_TRY(D.tb_info.ensure(nq));
@@ -316,13 +320,14 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     else
         T::pair_dist_kernel<1><<<dim3(32, grid), T::PairCfg<1>::WARPS * 32, 0, st>>>(d_rows, dim, D.tb_Q.p, D.tb_cand.p, region_cap,
                                                                                     region_count, D.tb_seg.p, cap_q, cntq);
-    T::topk_select_kernel<<<nq, 256, 0, st>>>(D.tb_seg.p, cap_q, cntq, k, (flags & PQV_SQRT) ? 1 : 0, D.tb_keys.p, D.tb_info.p);
+    T::topk_select_kernel<<<nq, 256, 0, st>>>(D.tb_seg.p, cap_q, cntq, k, (flags & PQV_SQRT) ? 1 : 0, D.tb_keys.p, D.tb_info.p,
+                                              kout);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(D.ev[4], st));
     u64 *h_keys = D.h_batch_keys.p;
-    uint32_t *h_info = reinterpret_cast<uint32_t *>(h_keys + (size_t)nq * k);
+    uint32_t *h_info = reinterpret_cast<uint32_t *>(h_keys + (size_t)nq * kout);
     uint32_t *h_flags = h_info + nq;  // + region counts are not needed on the host
-    CU_TRY(cudaMemcpyAsync(h_keys, D.tb_keys.p, (size_t)nq * k * 8, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaMemcpyAsync(h_keys, D.tb_keys.p, (size_t)nq * kout * 8, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(h_info, D.tb_info.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
     CU_TRY(cudaMemcpyAsync(h_flags, dflags, 4, cudaMemcpyDeviceToHost, st));
     std::vector<uint32_t> h_cnt(nq);
@@ -339,6 +344,20 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     for (uint32_t q = 0; q < nq; ++q) bt.candidates += h_cnt[q];
     if (*h_flags) {  // non-finite rows or a full candidate region: nothing of this batch is trusted
         bt.declined = 1;
+        return PQV_OK;
+    }
+    if (raw_keys) {
+        for (uint32_t q = 0; q < nq; ++q) {
+            const uint32_t info = h_info[q];
+            if (info & T::SEL_OVERFLOW) {
+                raw_count[q] = 0xFFFFFFFFu;
+                continue;
+            }
+            const uint32_t cnt = info & 0xFFFFu;
+            for (uint32_t i = 0; i < cnt; ++i) raw_keys[(size_t)q * kout + i] = h_keys[(size_t)q * kout + i] + pos_base;
+            raw_count[q] = cnt;
+            handled[q] = 1;
+        }
         return PQV_OK;
     }
     std::vector<uint32_t> ties;

@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .api import replay_candidates
+from .api import merge_batch_keys, replay_candidates
 
 DEFAULT_CAP = 4096  # candidate keys per rank carried by the single all-gather (32 KiB)
 
@@ -63,3 +63,49 @@ class ShardedTopk:
             out, ok = self._exchange(keys, int(out.max()))
             assert ok
         return replay_candidates(out, k, flags)
+
+
+class ShardedBatchTopk:
+    """Batched queries over row-range shards (BASELINE config C5): every rank answers the whole batch over its own
+    slice in one tensor-core pass (pqv_l2_topk_batch_keys: k + 1 exact keys per query), ONE all-gather moves
+    world x nq x (k + 2) x 8 B, every rank merges (pqv_merge_batch_keys).  Queries whose answer hinges on the
+    reference heap's layout (exact ties) are re-run through the single-query candidate exchange of ShardedTopk, so
+    every query's result is bit-identical to its own reference loop over the whole table."""
+
+    def __init__(self, batch_fn, scan_fn, pos_base: int, device: "torch.device | str" = "cpu", group=None):
+        """batch_fn(queries, k, flags, pos_base) -> (keys [nq, k+1] u64, counts [nq] u32)  (Dataset.l2_topk_batch_keys)
+        scan_fn: as ShardedTopk (Dataset.l2_topk_candidates), used for the tie queries."""
+        self.batch_fn = batch_fn
+        self.pos_base = int(pos_base)
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.single = ShardedTopk(scan_fn, pos_base, device, group)
+        self.last_gather_bytes = 0
+        self.last_replayed = 0
+
+    def search(self, queries, k: int, flags: int):
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = queries.shape[0]
+        keys, counts = self.batch_fn(queries, k, flags, self.pos_base)
+        # one payload per rank: [nq, k+1] keys followed by the nq counts (widened to 64 bit)
+        payload = np.concatenate([keys.reshape(-1).view(np.int64), counts.astype(np.int64)])
+        send = torch.from_numpy(payload).to(self.device)
+        if self.world > 1:
+            recv = torch.empty(self.world * payload.size, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+            got = recv.cpu().numpy().reshape(self.world, payload.size)
+        else:
+            got = send.cpu().numpy()[None, :]
+        self.last_gather_bytes = got.nbytes
+        all_keys = got[:, :nq * (k + 1)].view(np.uint64).reshape(self.world, nq, k + 1)
+        all_counts = got[:, nq * (k + 1):].astype(np.uint32)
+        rows, dd, cnt, need = merge_batch_keys(all_keys, all_counts, k, flags)
+        # deterministic on identical gathered data -> every rank enters the same collective replays, in the same order
+        self.last_replayed = int(need.sum())
+        for q in np.nonzero(need)[0]:
+            r, d = self.single.search(queries[q], k, flags)
+            cnt[q] = r.size
+            rows[q, :r.size] = r
+            dd[q, :r.size] = d
+        return rows, dd, cnt

@@ -151,3 +151,44 @@ def test_small_batches_use_the_single_query_path(ctx):
     ds.l2_topk(rng.random((3, 64), dtype=np.float32), 5, SQRT)
     assert ctx.last_batch_timing()["queries"] == 0
     ds.drop()
+
+
+@pytest.mark.parametrize("n,dim,nq,k,flags,grid_data", [
+    (30000, 256, 32, 10, SEQ, False), (20001, 768, 12, 100, SQRT, False), (9000, 64, 16, 10, SQRT, True),
+    (600, 32, 6, 1000, SEQ, False),
+])
+def test_sharded_batch_keys_merge_to_the_whole_table_answer(ctx, n, dim, nq, k, flags, grid_data):
+    """Config C5's per-rank half (pqv_l2_topk_batch_keys) + pqv_merge_batch_keys, three uneven 'ranks' in one process:
+    final queries must equal the single-query reference loop over the WHOLE table; queries flagged for replay must be
+    exactly answerable by the candidate exchange (pqv_l2_topk_candidates + pqv_replay_candidates)."""
+    import pq_vector_b200 as P
+    rng = np.random.default_rng(n + k)
+    if grid_data:   # small-integer grid: exact ties across slices
+        data = rng.integers(0, 3, (n, dim)).astype(np.float32)
+        queries = rng.integers(0, 3, (nq, dim)).astype(np.float32)
+    else:
+        data = rng.random((n, dim), dtype=np.float32)
+        queries = rng.random((nq, dim), dtype=np.float32)
+        queries[0] = data[n - 1]
+    cuts = [0, n // 5, n // 5 + n // 2, n]
+    parts = [ctx.dataset_from(data[cuts[i]:cuts[i + 1]]) for i in range(3)]
+    keys = np.stack([p.l2_topk_batch_keys(queries, k, flags, cuts[i])[0] for i, p in enumerate(parts)])
+    counts = np.stack([p.l2_topk_batch_keys(queries, k, flags, cuts[i])[1] for i, p in enumerate(parts)])
+    assert (counts != 0xFFFFFFFF).all()
+    rows, dist, cnt, need = P.merge_batch_keys(keys, counts, k, flags)
+    order = 1 if flags & SEQ else 0
+    if grid_data:
+        assert need.any()
+    else:
+        assert not need.all()
+    for i, q in enumerate(queries):
+        er, ed = O.topk_rerank(q, data, None, k, order, bool(flags & SQRT))
+        if need[i]:
+            cand = np.concatenate([p.l2_topk_candidates(q, k, flags, cuts[j], cap=1 << 20) for j, p in enumerate(parts)])
+            r, d = P.replay_candidates(cand, k, flags)
+        else:
+            r, d = rows[i, :cnt[i]], dist[i, :cnt[i]]
+        assert r.tolist() == er.tolist(), (i, bool(need[i]))
+        assert bits(d).tolist() == bits(ed).tolist(), (i, bool(need[i]))
+    for p in parts:
+        p.drop()

@@ -46,3 +46,57 @@ def test_two_rank_exchange_matches_single_process(tmp_path, n, dim, k, flags, ca
     mp.spawn(_worker, args=(2, port, n, dim, k, flags, cap, seed, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
+
+
+def _batch_worker(rank, world, port, n, dim, nq, k, flags, seed, out_dir):
+    sys.path.insert(0, ROOT)
+    import oracle as O
+    from pq_vector_b200.sharded import ShardedBatchTopk
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    # odd seeds: small-integer grid -> many exact ties (the replay route); even seeds: continuous data (the merge route)
+    data = rng.integers(0, 3, (n, dim)).astype(np.float32) if seed % 2 else rng.random((n, dim), dtype=np.float32)
+    queries = (rng.integers(0, 3, (nq, dim)).astype(np.float32) if seed % 2 else rng.random((nq, dim), dtype=np.float32))
+    per = (n + world - 1) // world
+    lo, hi = rank * per, min(n, (rank + 1) * per)
+    order = 1 if flags & 1 else 0
+
+    def keys_of(query):
+        d = O.distances(data[lo:hi], query, order)
+        return (d.view(np.uint32).astype(np.uint64) << np.uint64(32)) | (np.arange(lo, hi, dtype=np.uint64))
+
+    def batch(qs, k_, flags_, pos_base):  # the oracle standing in for pqv_l2_topk_batch_keys
+        keys = np.full((qs.shape[0], k_ + 1), np.iinfo(np.uint64).max, dtype=np.uint64)
+        cnt = np.zeros(qs.shape[0], dtype=np.uint32)
+        for i, q in enumerate(qs):
+            kk = np.sort(keys_of(q))[:k_ + 1]
+            keys[i, :kk.size] = kk
+            cnt[i] = kk.size
+        if seed == 6:
+            cnt[1] = 0xFFFFFFFF  # a slice that could not decide query 1 -> replay route
+        return keys, cnt
+
+    sb = ShardedBatchTopk(batch, lambda q, k_, f_, pb: keys_of(q), lo, "cpu")
+    rows, dd, cnt = sb.search(queries, k, flags)
+    ok = True
+    for i in range(nq):
+        er, ed = O.topk_rerank(queries[i], data, None, k, order, bool(flags & 2))
+        ok &= cnt[i] == er.size and rows[i, :cnt[i]].tolist() == er.tolist()
+        ok &= dd[i, :cnt[i]].view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok), sb.last_replayed]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,dim,nq,k,flags,seed", [(2000, 8, 6, 10, 2, 2), (1500, 4, 5, 20, 1, 3), (7, 3, 4, 10, 2, 4),
+                                                    (1200, 6, 4, 5, 3, 6), (900, 5, 3, 3, 0, 7)])
+def test_two_rank_batched_exchange_matches_single_process(tmp_path, n, dim, nq, k, flags, seed):
+    port = 31500 + (os.getpid() + seed) % 2000
+    mp.spawn(_batch_worker, args=(2, port, n, dim, nq, k, flags, seed, str(tmp_path)), nprocs=2, join=True)
+    got = [np.load(tmp_path / f"ok{r}.npy") for r in range(2)]
+    assert all(g[0] == 1 for g in got)
+    assert got[0][1] == got[1][1]                 # both ranks took the same replay decisions
+    if seed % 2:
+        assert got[0][1] > 0                      # the tie-heavy cases really exercised the replay route
