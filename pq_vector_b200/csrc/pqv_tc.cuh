@@ -40,10 +40,20 @@ constexpr uint32_t A_BYTES = BM * BK * 4;
 constexpr uint32_t B_BYTES = BN * BK * 4;
 constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr uint32_t TMEM_COLS = 512;  // two accumulator stages of BN f32 columns
-constexpr int THREADS = 192;
+// threads per CTA: TMA warp + MMA warp + 4 * SPLIT epilogue warps.  TMEM lane quarter q is only readable by warps with
+// warp % 4 == q, so with SPLIT = 2 two warps share every row and each takes half of a tile's columns: a single epilogue warp
+// per SM sub-partition is latency-bound (ncu: 0.23 IPC) and the MMAs end up waiting for the accumulator to be drained
+constexpr int tc_threads(int split) { return 64 + 128 * split; }
 constexpr int EPI_WARP0 = 2;
 constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
 constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+// CTA-pair variant (tcgen05 cta_group::2): UMMA M = 256 over two SMs, each CTA stages its own 128 rows of A and HALF of
+// the B tile (128 table rows), so a stage is 32 KB per CTA instead of 48 KB and six stages fit
+constexpr int STAGES2 = 6;
+constexpr uint32_t B2_BYTES = (BN / 2) * BK * 4;
+constexpr uint32_t STAGE2_BYTES = A_BYTES + B2_BYTES;
+constexpr uint32_t BAR2_BYTES = 8 * (2 * STAGES2 + 4) + 16;
+constexpr size_t SMEM2_BYTES = (size_t)STAGES2 * STAGE2_BYTES + BAR2_BYTES + 1024;
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr int FIFO = 8;      // candidate slots per row (unordered; a slot is free once its score left the window)
 
@@ -53,6 +63,7 @@ constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
 // instruction descriptor (cute::UMMA::InstrDescriptor bit layout): c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2,
 // a/b major K [15],[16]=0, n_dim [17,23)=N>>3, m_dim [24,29)=M>>4
 constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+constexpr uint32_t IDESC_TF32_2CTA = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -121,6 +132,56 @@ __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint6
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// ---- cta_group::2 (CTA pair) forms
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {  // same offset in CTA `rank` of the cluster
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// destination in this CTA's shared memory, completion bytes on an mbarrier that may live in the peer CTA (`bar` is a
+// shared::cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *tm, int32_t c0, int32_t c1, uint32_t bar,
+                                                 uint64_t hint) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
+        " [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(dst),
+        "l"((uint64_t)tm), "r"(bar), "r"(c0), "r"(c1), "l"(hint)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_alloc_pair(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_pair() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_pair(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// arrives (once every tcgen05.mma issued so far has completed on both SMs) on the barrier at the same offset in every CTA
+// of cta_mask
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"(cta_mask)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+
 // 32 lanes x 32 consecutive f32 columns: thread t of the warp gets lane (taddr.lane + t), columns [col, col+32)
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     uint32_t r[32];
@@ -291,27 +352,36 @@ struct GemmShape {
     uint32_t num_mb, num_nb, num_kb;  // 128-row tiles of A, 256-row tiles of B, 32-column k blocks
 };
 
-// what an epilogue warp needs: barrier base, TMEM base, its TMEM lane quarter, and the CTA's scratch counter
+// what an epilogue warp needs: barrier base, TMEM base, its TMEM lane quarter, the CTA's scratch counter and the CTA's
+// walk over the 128-row tiles (mb = mb0, mb0 + mb_stride, ... < mb_end; in the CTA-pair kernel both CTAs of a pair take
+// the same number of steps, the odd CTA's last tile may lie past the table: its rows are simply not valid)
 struct EpiCtx {
-    uint32_t bar0, tmem_base, q, lane;
-    uint32_t *counter;  // shared memory, zeroed before the roles start
+    uint32_t tfull0;     // shared::cta address of this CTA's tfull[0] barrier (tfull[1] follows at +8)
+    uint32_t tempty0;    // address of tempty[0] of the CTA that issues the MMAs: shared::cta (single CTA) or shared::cluster
+    uint32_t remote;     // 1: tempty0 is a shared::cluster address (CTA-pair kernel)
+    uint32_t tmem_base, q, lane;
+    uint32_t *counter;   // shared memory, zeroed before the roles start
+    uint32_t mb0, mb_stride, mb_end;
+    uint32_t h;          // column half this warp drains (0 when the epilogue is not split)
     // wait for accumulator `tile` of this CTA; returns the TMEM address of this warp's 32 lanes x BN columns
     __device__ __forceinline__ uint32_t acquire(uint32_t tile) const {
         const uint32_t as = tile & 1u, aph = (tile >> 1) & 1u;
-        mbar_wait(BAR_TFULL(as), aph);
+        mbar_wait(tfull0 + 8u * as, aph);
         tc_fence_after();
         return tmem_base + ((q * 32u) << 16) + as * BN;
     }
     __device__ __forceinline__ void release(uint32_t tile) const {
         tc_fence_before();
-        mbar_arrive(BAR_TEMPTY(tile & 1u));
+        const uint32_t bar = tempty0 + 8u * (tile & 1u);
+        if (remote) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+        else mbar_arrive(bar);
     }
 };
 
 // D[128 x 256 per tile] = A[rows x dim] . B[table x dim]^T in tf32 on the tensor cores, persistent over the row tiles of A;
 // Epi::run consumes every accumulator tile straight from TMEM (nothing of D is ever written to memory as a matrix).
 template <class Epi>
-__global__ void __launch_bounds__(THREADS, 1)
+__global__ void __launch_bounds__(tc_threads(Epi::SPLIT), 1)
 tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
                        const typename Epi::Params p) {
     extern __shared__ uint8_t smem_raw[];
@@ -331,7 +401,7 @@ tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         }
         for (int a = 0; a < 2; ++a) {
             mbar_init(BAR_TFULL(a), 1);
-            mbar_init(BAR_TEMPTY(a), 128);
+            mbar_init(BAR_TEMPTY(a), 128 * Epi::SPLIT);
         }
         *counter = 0u;
         fence_barrier_init();
@@ -388,7 +458,9 @@ tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         __syncwarp();
     } else {
         // ===== epilogue warps: one row per thread; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
-        Epi::run(EpiCtx{bar0, tmem_base, warp & 3u, lane, counter}, g, p);
+        Epi::run(EpiCtx{BAR_TFULL(0), BAR_TEMPTY(0), 0u, tmem_base, warp & 3u, lane, counter, blockIdx.x, gridDim.x, g.num_mb,
+                        (warp - 2u) >> 2},
+                 g, p);
     }
     // ---- teardown
     tc_fence_before();
@@ -400,9 +472,128 @@ tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     }
 }
 
+// The same contraction on CTA PAIRS (tcgen05 cta_group::2, clusters of two CTAs on the two SMs of a TPC): one UMMA covers
+// 256 rows x 256 table entries, CTA r of the pair owns rows [128 r, 128 r + 128) of it (its own TMEM lanes) and stages
+// only ITS half of the B tile (table entries [128 r, 128 r + 128)); the tensor cores of both SMs read both halves.  Per
+// 128 x 256 x 32 block an SM now ingests 32 KB instead of 48 KB -- the L2 -> SM fill, not the tensor pipe, bounds this
+// kernel (profiles/r01_assign_tc_full.md).  Barrier protocol:
+//   full[s]    leader only, count 1: the leader's producer arms it with the bytes of BOTH CTAs; both producers' TMA loads
+//              complete on it (cp.async.bulk.tensor ... cta_group::2, barrier address mapped into the leader)
+//   empty[s]   in each CTA, count 1: tcgen05.commit multicast to both CTAs when the MMAs that read stage s are done
+//   tfull[a]   in each CTA, count 1: multicast commit when accumulator a is complete (each CTA drains its own TMEM)
+//   tempty[a]  leader only, count 256: the epilogue threads of both CTAs arrive (remote arrive from the peer)
+template <class Epi>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc_threads(Epi::SPLIT), 1)
+tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
+                            const typename Epi::Params p) {
+    extern __shared__ uint8_t smem_raw[];
+    const uint32_t raw = smem_u32(smem_raw);
+    const uint32_t base = (raw + 1023u) & ~1023u;
+    const uint32_t bar0 = base + STAGES2 * STAGE2_BYTES;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES2 + 4);
+    uint32_t *const counter = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot + 8u - raw));
+    const uint32_t rank = cluster_ctarank();
+    const uint32_t pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+    const uint32_t num_mb2 = (g.num_mb + 1u) >> 1;  // 256-row super tiles
+#define BAR2_FULL(s) (bar0 + 8u * (uint32_t)(s))
+#define BAR2_EMPTY(s) (bar0 + 8u * (uint32_t)(STAGES2 + (s)))
+#define BAR2_TFULL(a) (bar0 + 8u * (uint32_t)(2 * STAGES2 + (a)))
+#define BAR2_TEMPTY(a) (bar0 + 8u * (uint32_t)(2 * STAGES2 + 2 + (a)))
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        for (int s = 0; s < STAGES2; ++s) {
+            mbar_init(BAR2_FULL(s), 1);
+            mbar_init(BAR2_EMPTY(s), 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(BAR2_TFULL(a), 1);
+            mbar_init(BAR2_TEMPTY(a), 256 * Epi::SPLIT);
+        }
+        *counter = 0u;
+        fence_barrier_init();
+    }
+    if (warp == 1) {  // one warp of EACH CTA of the pair takes part in the paired allocation
+        tmem_alloc_pair(tmem_slot, TMEM_COLS);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();  // the peer's barriers are initialised before anything is signalled across the pair
+    tc_fence_after();
+    const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t *>(smem_raw + (tmem_slot - raw));
+    const uint32_t lead_bar0 = mapa_shared(bar0, 0u);
+
+    if (warp == 0) {
+        // ===== TMA producer (both CTAs; each fills its own stage buffers, bytes complete on the leader's barrier) =====
+        if (lane == 0) {
+            uint32_t it = 0;
+            for (uint32_t mb2 = pair; mb2 < num_mb2; mb2 += num_pairs)
+                for (uint32_t nb = 0; nb < g.num_nb; ++nb)
+                    for (uint32_t kb = 0; kb < g.num_kb; ++kb, ++it) {
+                        const uint32_t s = it % STAGES2, ph = (it / STAGES2) & 1u;
+                        mbar_wait(BAR2_EMPTY(s), ph ^ 1u);
+                        if (rank == 0u) mbar_expect_tx(BAR2_FULL(s), 2u * STAGE2_BYTES);
+                        const uint32_t sa = base + s * STAGE2_BYTES;
+                        const uint32_t lead_full = lead_bar0 + 8u * s;
+                        tma_load_2d_pair(sa, &tmA, (int32_t)(kb * BK), (int32_t)((mb2 * 2u + rank) * BM), lead_full, HINT_EVICT_NORMAL);
+                        tma_load_2d_pair(sa + A_BYTES, &tmB, (int32_t)(kb * BK), (int32_t)(nb * BN + rank * (BN / 2)), lead_full,
+                                         HINT_EVICT_LAST);
+                    }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===== MMA issuer: one thread of the leader CTA drives the tensor cores of both SMs =====
+        if (lane == 0 && rank == 0u) {
+            uint32_t it = 0, tile = 0;
+            for (uint32_t mb2 = pair; mb2 < num_mb2; mb2 += num_pairs)
+                for (uint32_t nb = 0; nb < g.num_nb; ++nb, ++tile) {
+                    const uint32_t as = tile & 1u, aph = (tile >> 1) & 1u;
+                    mbar_wait(BAR2_TEMPTY(as), aph ^ 1u);  // both CTAs' epilogues have drained this accumulator stage
+                    tc_fence_after();
+                    const uint32_t d_tmem = tmem_base + as * BN;
+                    for (uint32_t kb = 0; kb < g.num_kb; ++kb, ++it) {
+                        const uint32_t s = it % STAGES2, ph = (it / STAGES2) & 1u;
+                        mbar_wait(BAR2_FULL(s), ph);
+                        tc_fence_after();
+                        const uint32_t sa = base + s * STAGE2_BYTES;
+                        const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + A_BYTES);
+#pragma unroll
+                        for (uint32_t k = 0; k < BK / UMMA_K; ++k)
+                            umma_tf32_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, IDESC_TF32_2CTA, (kb | k) != 0u);
+                        umma_commit_pair(BAR2_EMPTY(s), 3);  // frees stage s in both CTAs
+                    }
+                    umma_commit_pair(BAR2_TFULL(as), 3);  // accumulator complete in both CTAs
+                }
+        }
+        __syncwarp();
+    } else {
+        // ===== epilogue warps of both CTAs: each drains its own 128 TMEM lanes =====
+        Epi::run(EpiCtx{BAR2_TFULL(0), lead_bar0 + 8u * (uint32_t)(2 * STAGES2 + 2), 1u, tmem_base, warp & 3u, lane, counter,
+                        pair * 2u + rank, num_pairs * 2u, num_mb2 * 2u, (warp - 2u) >> 2},
+                 g, p);
+    }
+    // ---- teardown: nobody leaves (or frees TMEM) while the peer can still signal into this CTA
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (threadIdx.x == 0) Epi::finish(counter, p);
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    }
+#undef BAR2_FULL
+#undef BAR2_EMPTY
+#undef BAR2_TFULL
+#undef BAR2_TEMPTY
+}
+
 // epilogue of the k-means assignment filter (see the header of this file)
 struct AssignEpi {
     typedef AssignTcParams Params;
+    static constexpr int SPLIT = 1;
     static __device__ __forceinline__ void finish(uint32_t *, const Params &) {}
     static __device__ void run(const EpiCtx c, const GemmShape g, const Params &p) {
         const uint32_t q = c.q, lane = c.lane;
@@ -416,7 +607,7 @@ struct AssignEpi {
         const bool table_ok = (cnmax < 1e30f) && (wmax < 1e30f) && (mun < 1e30f);
         const float inf = __int_as_float(0x7f800000);
         uint32_t tile = 0;
-        for (uint32_t mb = blockIdx.x; mb < g.num_mb; mb += gridDim.x) {
+        for (uint32_t mb = c.mb0; mb < c.mb_end; mb += c.mb_stride) {
             const u64 row = (u64)mb * BM + row_in_tile;
             const bool valid = row < p.n;
             const float2 st = valid ? p.stats[row] : make_float2(0.f, 0.f);
@@ -727,6 +918,7 @@ struct BatchParams {
 template <int MODE>
 struct BatchEpi {
     typedef BatchParams Params;
+    static constexpr int SPLIT = 2;  // every (row, query) pair is independent: the two warps of a row just split the columns
     static __device__ __forceinline__ void finish(uint32_t *counter, const Params &p) {
         if (MODE == BATCH_FILTER) p.region_count[blockIdx.x] = min(*counter, p.region_cap);
     }
@@ -737,7 +929,7 @@ struct BatchEpi {
         const float gamma = (float)(p.dim + 32) * 5.9604645e-08f;  // f32 summation error of row_stats_kernel
         uint2 *const region = (MODE == BATCH_FILTER) ? p.cand + (size_t)blockIdx.x * p.region_cap : nullptr;
         uint32_t tile = 0;
-        for (uint32_t mb = blockIdx.x; mb < g.num_mb; mb += gridDim.x) {
+        for (uint32_t mb = c.mb0; mb < c.mb_end; mb += c.mb_stride) {
             const u64 row = (u64)mb * BM + row_in_tile;
             const bool valid = row < p.n;
             const float x2c = valid ? p.stats[row].x : 0.f;
@@ -751,7 +943,7 @@ struct BatchEpi {
                 const float4 *w4 = reinterpret_cast<const float4 *>(p.qw + (size_t)nb * BN);
                 const float4 *t4 = reinterpret_cast<const float4 *>(p.qtheta + (size_t)nb * BN);
 #pragma unroll 1
-                for (uint32_t ch = 0; ch < BN / 32; ++ch) {
+                for (uint32_t ch = c.h * (BN / 32 / SPLIT); ch < (c.h + 1u) * (BN / 32 / SPLIT); ++ch) {
                     float v[32];
                     tmem_ld32(taddr + ch * 32u, v);
                     const uint32_t q0 = nb * BN + ch * 32u;

@@ -43,6 +43,34 @@ int make_row_tmap(CUtensorMap *tm, const float *d_ptr, u64 rows, uint32_t dim, u
 
 enum AssignPath { ASSIGN_SIMT = 0, ASSIGN_TC = 1 };
 
+// PQV_TC_PAIR=off selects the single-CTA tcgen05 kernel (cta_group::1); default: CTA pairs (cta_group::2)
+bool tc_pair_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("PQV_TC_PAIR");
+        return !(e && (!strcmp(e, "off") || !strcmp(e, "0")));
+    }();
+    return on;
+}
+
+// launch geometry of tc_rows_x_table(_pair)_kernel over num_mb 128-row tiles: CTAs, and 128-row tiles per CTA
+struct TcGrid {
+    bool pair;
+    uint32_t grid, tiles_per_cta;
+};
+TcGrid tc_grid_for(const DeviceState &D, uint32_t num_mb) {
+    TcGrid t;
+    t.pair = tc_pair_enabled() && D.sm_count >= 2;
+    if (t.pair) {
+        const uint32_t num_mb2 = (num_mb + 1) / 2, pairs = std::min<uint32_t>(num_mb2, (uint32_t)D.sm_count / 2);
+        t.grid = 2 * pairs;
+        t.tiles_per_cta = (num_mb2 + pairs - 1) / pairs;
+    } else {
+        t.grid = std::min<uint32_t>(num_mb, (uint32_t)D.sm_count);
+        t.tiles_per_cta = (num_mb + t.grid - 1) / t.grid;
+    }
+    return t;
+}
+
 // PQV_ASSIGN=simt|tc forces a path (tc still requires the layout preconditions); default: tc whenever it applies
 int assign_path_for(const float *d_rows, u64 n, uint32_t dim, const float *d_cent, uint32_t C) {
     const bool layout_ok = (dim % 4 == 0) && dim >= (uint32_t)pqv::tc::BK && ((reinterpret_cast<uintptr_t>(d_rows) & 15) == 0) &&
@@ -88,12 +116,16 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     std::call_once(attr_once, [] {
         attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_kernel<T::AssignEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)T::SMEM_BYTES);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_pair_kernel<T::AssignEpi>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM2_BYTES);
     });
     CU_TRY(attr_err);
 
+    const TcGrid tg = tc_grid_for(D, num_mb);
     CUtensorMap tmA, tmB;
     PQV_TRY(make_row_tmap(&tmA, d_rows, n, dim, T::BM));
-    PQV_TRY(make_row_tmap(&tmB, D.tc_bp.p, C, dim, T::BN));
+    PQV_TRY(make_row_tmap(&tmB, D.tc_bp.p, C, dim, tg.pair ? T::BN / 2 : T::BN));
 
     if (time_it) CU_TRY(cudaEventRecord(D.ev[0], D.stream));
     CU_TRY(cudaMemsetAsync(D.tc_u32.p, 0, 8 * sizeof(uint32_t), D.stream));
@@ -119,9 +151,9 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     p.dim = dim;
     p.C = C;
     const T::GemmShape shape{num_mb, num_nb, num_kb};
-    const uint32_t grid = std::min<uint32_t>(num_mb, (uint32_t)D.sm_count);
     if (time_it) CU_TRY(cudaEventRecord(D.ev[1], D.stream));
-    T::tc_rows_x_table_kernel<T::AssignEpi><<<grid, T::THREADS, T::SMEM_BYTES, D.stream>>>(tmA, tmB, shape, p);
+    if (tg.pair) T::tc_rows_x_table_pair_kernel<T::AssignEpi><<<tg.grid, T::tc_threads(T::AssignEpi::SPLIT), T::SMEM2_BYTES, D.stream>>>(tmA, tmB, shape, p);
+    else T::tc_rows_x_table_kernel<T::AssignEpi><<<tg.grid, T::tc_threads(T::AssignEpi::SPLIT), T::SMEM_BYTES, D.stream>>>(tmA, tmB, shape, p);
     CU_TRY(cudaGetLastError());
     if (time_it) CU_TRY(cudaEventRecord(D.ev[2], D.stream));
     // exact f32 chains: one per (row, candidate) pair of the ambiguous rows; the full scan for the overflow rows
@@ -222,9 +254,9 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     const u64 S = std::min<u64>(n, std::min<u64>(std::max<u64>(n / 16, 65536), 524288));
     const uint32_t num_mb_s = (uint32_t)((S + T::BM - 1) / T::BM);
     const uint32_t ldU = num_mb_s * T::BM;
-    const uint32_t grid = std::min<uint32_t>(num_mb, (uint32_t)D.sm_count);
-    const uint32_t grid_s = std::min<uint32_t>(num_mb_s, (uint32_t)D.sm_count);
-    const u64 rows_per_cta = (u64)((num_mb + grid - 1) / grid) * T::BM;
+    const TcGrid tg = tc_grid_for(D, num_mb), tg_s = tc_grid_for(D, num_mb_s);
+    const uint32_t grid = tg.grid, grid_s = tg_s.grid;
+    const u64 rows_per_cta = (u64)tg.tiles_per_cta * T::BM;
     const uint32_t region_cap = (uint32_t)std::min<u64>(rows_per_cta * nq, std::max<u64>(BATCH_TOTAL_CAND / grid, 1024));
     const uint32_t cap_q = (uint32_t)std::min<u64>(n, std::max<u64>(BATCH_TOTAL_CAND / nq, 4096));
 
@@ -257,13 +289,19 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
         if (attr_err == cudaSuccess)
             attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_FILTER>>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_pair_kernel<T::BatchEpi<T::BATCH_SAMPLE>>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM2_BYTES);
+        if (attr_err == cudaSuccess)
+            attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_pair_kernel<T::BatchEpi<T::BATCH_FILTER>>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM2_BYTES);
     });
     CU_TRY(attr_err);
 
     CUtensorMap tmAs, tmA, tmB;
     PQV_TRY(make_row_tmap(&tmAs, d_rows, S, dim, T::BM));
     PQV_TRY(make_row_tmap(&tmA, d_rows, n, dim, T::BM));
-    PQV_TRY(make_row_tmap(&tmB, D.tb_Qp.p, nq, dim, T::BN));
+    PQV_TRY(make_row_tmap(&tmB, D.tb_Qp.p, nq, dim, tg.pair ? T::BN / 2 : T::BN));
 
     cudaStream_t st = D.stream;
     CU_TRY(cudaEventRecord(D.ev[0], st));
@@ -292,8 +330,12 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     p.dim = dim;
     // phase A: upper bounds over the first S rows -> theta_q
     p.n = S;
-    T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_SAMPLE>><<<grid_s, T::THREADS, T::SMEM_BYTES, st>>>(
-        tmAs, tmB, T::GemmShape{num_mb_s, num_nb, num_kb}, p);
+    if (tg.pair)
+        T::tc_rows_x_table_pair_kernel<T::BatchEpi<T::BATCH_SAMPLE>><<<grid_s, T::tc_threads(2), T::SMEM2_BYTES, st>>>(
+            tmAs, tmB, T::GemmShape{num_mb_s, num_nb, num_kb}, p);
+    else
+        T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_SAMPLE>><<<grid_s, T::tc_threads(2), T::SMEM_BYTES, st>>>(
+            tmAs, tmB, T::GemmShape{num_mb_s, num_nb, num_kb}, p);
     const float delta = (float)(order == 1 ? dim + 8 : dim / 4 + 12) * 5.9604645e-08f;
     {
         const uint32_t M = k <= 128 ? 2048u : 16384u;  // chunk minima kept per query (>= 16 k)
@@ -309,8 +351,12 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     CU_TRY(cudaEventRecord(D.ev[2], st));
     // phase B: candidates over all rows
     p.n = n;
-    T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_FILTER>><<<grid, T::THREADS, T::SMEM_BYTES, st>>>(
-        tmA, tmB, T::GemmShape{num_mb, num_nb, num_kb}, p);
+    if (tg.pair)
+        T::tc_rows_x_table_pair_kernel<T::BatchEpi<T::BATCH_FILTER>><<<grid, T::tc_threads(2), T::SMEM2_BYTES, st>>>(
+            tmA, tmB, T::GemmShape{num_mb, num_nb, num_kb}, p);
+    else
+        T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_FILTER>><<<grid, T::tc_threads(2), T::SMEM_BYTES, st>>>(
+            tmA, tmB, T::GemmShape{num_mb, num_nb, num_kb}, p);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(D.ev[3], st));
     // exact distances of the candidates, per-query selection
