@@ -46,14 +46,18 @@ constexpr uint32_t TMEM_COLS = 512;  // two accumulator stages of BN f32 columns
 constexpr int tc_threads(int split) { return 64 + 128 * split; }
 constexpr int EPI_WARP0 = 2;
 constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024: manual 1 KB alignment
+// exchange area of the split epilogue (AssignEpi): 18 words per row of the tile, word-major so that a warp's accesses are
+// conflict-free
+constexpr int EXCH_WORDS = 18;
+constexpr uint32_t EXCH_BYTES = EXCH_WORDS * BM * 4;
+constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + BAR_BYTES + EXCH_BYTES + 1024;  // +1024: manual 1 KB alignment
 // CTA-pair variant (tcgen05 cta_group::2): UMMA M = 256 over two SMs, each CTA stages its own 128 rows of A and HALF of
 // the B tile (128 table rows), so a stage is 32 KB per CTA instead of 48 KB and six stages fit
 constexpr int STAGES2 = 6;
 constexpr uint32_t B2_BYTES = (BN / 2) * BK * 4;
 constexpr uint32_t STAGE2_BYTES = A_BYTES + B2_BYTES;
 constexpr uint32_t BAR2_BYTES = 8 * (2 * STAGES2 + 4) + 16;
-constexpr size_t SMEM2_BYTES = (size_t)STAGES2 * STAGE2_BYTES + BAR2_BYTES + 1024;
+constexpr size_t SMEM2_BYTES = (size_t)STAGES2 * STAGE2_BYTES + BAR2_BYTES + EXCH_BYTES + 1024;
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr int FIFO = 8;      // candidate slots per row (unordered; a slot is free once its score left the window)
 
@@ -363,6 +367,7 @@ struct EpiCtx {
     uint32_t *counter;   // shared memory, zeroed before the roles start
     uint32_t mb0, mb_stride, mb_end;
     uint32_t h;          // column half this warp drains (0 when the epilogue is not split)
+    uint32_t *exch;      // shared memory, EXCH_WORDS x BM words: hand-over between the two warps of a row (split epilogue)
     // wait for accumulator `tile` of this CTA; returns the TMEM address of this warp's 32 lanes x BN columns
     __device__ __forceinline__ uint32_t acquire(uint32_t tile) const {
         const uint32_t as = tile & 1u, aph = (tile >> 1) & 1u;
@@ -459,7 +464,7 @@ tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     } else {
         // ===== epilogue warps: one row per thread; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
         Epi::run(EpiCtx{BAR_TFULL(0), BAR_TEMPTY(0), 0u, tmem_base, warp & 3u, lane, counter, blockIdx.x, gridDim.x, g.num_mb,
-                        (warp - 2u) >> 2},
+                        (warp - 2u) >> 2, reinterpret_cast<uint32_t *>(smem_raw + (bar0 + BAR_BYTES - raw))},
                  g, p);
     }
     // ---- teardown
@@ -572,7 +577,8 @@ tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     } else {
         // ===== epilogue warps of both CTAs: each drains its own 128 TMEM lanes =====
         Epi::run(EpiCtx{BAR2_TFULL(0), lead_bar0 + 8u * (uint32_t)(2 * STAGES2 + 2), 1u, tmem_base, warp & 3u, lane, counter,
-                        pair * 2u + rank, num_pairs * 2u, num_mb2 * 2u, (warp - 2u) >> 2},
+                        pair * 2u + rank, num_pairs * 2u, num_mb2 * 2u, (warp - 2u) >> 2,
+                        reinterpret_cast<uint32_t *>(smem_raw + (bar0 + BAR2_BYTES - raw))},
                  g, p);
     }
     // ---- teardown: nobody leaves (or frees TMEM) while the peer can still signal into this CTA
@@ -593,7 +599,10 @@ tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 // epilogue of the k-means assignment filter (see the header of this file)
 struct AssignEpi {
     typedef AssignTcParams Params;
-    static constexpr int SPLIT = 1;
+    // two warps per row, each scanning half of every tile's columns with its own running minimum and candidate FIFO (its
+    // window is the wider one of its half, so nothing the full-width scan keeps is lost); after the last tile of the row the
+    // upper half hands (min, overflow flag, FIFO) to the lower half through shared memory, which merges and finalises
+    static constexpr int SPLIT = 2;
     static __device__ __forceinline__ void finish(uint32_t *, const Params &) {}
     static __device__ void run(const EpiCtx c, const GemmShape g, const Params &p) {
         const uint32_t q = c.q, lane = c.lane;
@@ -635,7 +644,7 @@ struct AssignEpi {
                 const float4 *cn4 = reinterpret_cast<const float4 *>(p.cn + (size_t)nb * BN);
                 const float4 *wv4 = reinterpret_cast<const float4 *>(p.wv + (size_t)nb * BN);
 #pragma unroll 1
-                for (uint32_t ch = 0; ch < BN / 32; ++ch) {
+                for (uint32_t ch = c.h * (BN / 32 / SPLIT); ch < (c.h + 1u) * (BN / 32 / SPLIT); ++ch) {
                     float v[32], w[32];
                     tmem_ld32(taddr + ch * 32u, v);
 #pragma unroll
@@ -681,6 +690,48 @@ struct AssignEpi {
                     }
                 }
                 c.release(tile);
+            }
+            // ---- hand-over between the two column halves (named barrier 1 + q: the two warps that own TMEM quarter q)
+            if (SPLIT == 2) {
+                uint32_t *ex = c.exch + row_in_tile;
+                if (c.h == 1u) {
+                    ex[0] = __float_as_uint(m);
+                    ex[BM] = ovf ? 1u : 0u;
+#pragma unroll
+                    for (int e = 0; e < FIFO; ++e) {
+                        ex[(2 + e) * BM] = __float_as_uint(fs[e]);
+                        ex[(2 + FIFO + e) * BM] = fi[e];
+                    }
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1u + q) : "memory");
+                float os[FIFO];
+                uint32_t oi[FIFO];
+                if (c.h == 0u) {
+                    m = fminf(m, __uint_as_float(ex[0]));
+                    ovf |= ex[BM] != 0u;
+#pragma unroll
+                    for (int e = 0; e < FIFO; ++e) {
+                        os[e] = __uint_as_float(ex[(2 + e) * BM]);
+                        oi[e] = ex[(2 + FIFO + e) * BM];
+                    }
+                }
+                asm volatile("bar.sync %0, 64;" ::"r"(1u + q) : "memory");  // the area may be overwritten for the next rows
+                if (c.h == 1u) continue;
+                const float thr_m = m + T2 + c2 * fmaxf(m + K2, 0.f);
+#pragma unroll
+                for (int i = 0; i < FIFO; ++i) {
+                    if (os[i] <= thr_m) {
+                        bool placed = false;
+#pragma unroll
+                        for (int e = 0; e < FIFO; ++e) {
+                            const bool take = !placed && !(fs[e] <= thr_m);
+                            fs[e] = take ? os[i] : fs[e];
+                            fi[e] = take ? oi[i] : fi[e];
+                            placed |= take;
+                        }
+                        ovf |= !placed;
+                    }
+                }
             }
             // ---- finalize the row
             const float thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
