@@ -62,7 +62,8 @@ qd.fill_synthetic(a.queries, 7)
 queries = qd.read(0, a.queries)
 qd.drop()
 sb = ShardedBatchTopk(lambda q, k_, f_, pb: ds.l2_topk_batch_keys(q, k_, f_, pb),
-                      lambda q, k_, f_, pb: ds.l2_topk_candidates(q, k_, f_, pb), pos_base, dev)
+                      lambda q, k_, f_, pb: ds.l2_topk_candidates(q, k_, f_, pb), pos_base, dev,
+                      tie_fn=lambda qi, q: ds.l2_topk_batch_tie_candidates(qi, q))
 for _ in range(2):
     sb.search(queries, a.k, a.flags)  # warm-up: allocations, row-norm cache, NCCL channels
 ts = []

@@ -192,6 +192,12 @@ PQV_API int pqv_replay_candidates(const uint64_t *keys, uint64_t n_keys, const u
  * through pqv_l2_topk_candidates + pqv_replay_candidates. */
 PQV_API int pqv_l2_topk_batch_keys(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k,
                                    uint32_t flags, uint32_t pos_base, uint64_t *out_keys, uint32_t *out_count);
+/* Cheaper candidates for a query pqv_merge_batch_keys flagged: valid right after pqv_l2_topk_batch_keys on the same
+ * dataset (the batched pass leaves every query's exact-distance candidates on the device).  Returns a superset of the rows
+ * the reference heap admits inside this slice -- exact scan of the first rows of the slice + the query's candidates
+ * behind them (0.65 ms instead of a full scan) -- as keys for pqv_replay_candidates, like pqv_l2_topk_candidates. */
+PQV_API int pqv_l2_topk_batch_tie_candidates(pqv_ctx *ctx, uint64_t handle, uint32_t q_index, const float *query,
+                                             uint64_t *out_keys, uint64_t cap, uint64_t *out_count);
 PQV_API int pqv_merge_batch_keys(const uint64_t *keys, const uint32_t *counts, uint32_t n_ranks, uint32_t n_queries,
                                  uint32_t k, uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count,
                                  uint8_t *out_needs_replay);

@@ -266,6 +266,20 @@ class Dataset:
                                            _ptr(keys, C.c_uint64), _ptr(cnt, C.c_uint32)))
         return keys, cnt
 
+    def l2_topk_batch_tie_candidates(self, q_index: int, query, cap: int = 16384):
+        """Candidate keys of query `q_index` of the batch last passed to l2_topk_batch_keys (see pqv.h)."""
+        q = _f32(query)
+        while True:
+            keys = np.empty(cap, dtype=np.uint64)
+            cnt = C.c_uint64()
+            rc = _lib.pqv_l2_topk_batch_tie_candidates(self.ctx._h, self.handle, q_index, _ptr(q, C.c_float),
+                                                       _ptr(keys, C.c_uint64), cap, C.byref(cnt))
+            if rc == N.PQV_ELIMIT and cnt.value > cap:
+                cap = int(cnt.value)
+                continue
+            _check(rc)
+            return keys[:cnt.value]
+
     def bench_scan(self, query, k: int, flags: int, iters: int) -> float:
         q = _f32(query)
         ms = C.c_double()

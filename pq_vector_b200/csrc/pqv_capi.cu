@@ -394,6 +394,15 @@ struct pqv_ctx {
     pqv_timing last{};
     pqv_assign_timing last_assign{};
     pqv_batch_timing last_batch{};
+    // what pqv_l2_topk_batch_keys left on the device for pqv_l2_topk_batch_tie_candidates (valid until the next batched
+    // call or any change of the dataset)
+    struct BatchState {
+        bool valid = false;
+        u64 handle = 0, S = 0;
+        uint32_t nq = 0, k = 0, flags = 0, cap_q = 0, pos_base = 0;
+        int dev_index = 0;
+        std::vector<uint32_t> seg_count;
+    } batch_state;
     int occ_override = 0;
     int scan_variant = 0;
 };
@@ -961,6 +970,7 @@ static int grow_shard(pqv_ctx *ctx, Dataset &ds, Shard &sh, u64 need_rows) {
 }
 
 int pqv_dataset_append(pqv_ctx *ctx, uint64_t handle, const float *values, uint64_t n_rows) {
+    if (ctx) ctx->batch_state.valid = false;
     if (!ctx) return fail(PQV_EINVAL, "null ctx");
     std::lock_guard<std::mutex> lk(ctx->mu);
     Dataset *ds = find_dataset(ctx, handle);
@@ -1008,6 +1018,7 @@ int pqv_dataset_rows(pqv_ctx *ctx, uint64_t handle, uint64_t *out_rows, uint32_t
 }
 
 int pqv_dataset_drop(pqv_ctx *ctx, uint64_t handle) {
+    if (ctx) ctx->batch_state.valid = false;
     if (!ctx) return fail(PQV_EINVAL, "null ctx");
     std::lock_guard<std::mutex> lk(ctx->mu);
     Dataset *ds = find_dataset(ctx, handle);
@@ -1023,6 +1034,7 @@ int pqv_dataset_drop(pqv_ctx *ctx, uint64_t handle) {
 }
 
 int pqv_dataset_fill_synthetic(pqv_ctx *ctx, uint64_t handle, uint64_t n_rows, uint64_t seed, uint64_t stream_first_row) {
+    if (ctx) ctx->batch_state.valid = false;
     if (!ctx) return fail(PQV_EINVAL, "null ctx");
     std::lock_guard<std::mutex> lk(ctx->mu);
     Dataset *ds = find_dataset(ctx, handle);
@@ -1082,6 +1094,7 @@ int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_
     // reference heap's layout (pqv_tc.cuh); the rest -- and small batches -- take the single-query scan
     std::vector<uint8_t> handled(n_queries, 0);
     ctx->last_batch = pqv_batch_timing{};
+    ctx->batch_state.valid = false;
     if (n_queries && ds->n_rows && batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k)) {
         DeviceState &D = ctx->devs[ds->shards[0].di];
         DevGuard guard(D.dev);
@@ -1161,6 +1174,7 @@ int pqv_l2_topk_batch_keys(pqv_ctx *ctx, uint64_t handle, const float *queries, 
     if ((u64)pos_base + ds->n_rows > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "global row ids are u32");
     for (uint32_t q = 0; q < n_queries; ++q) out_count[q] = 0xFFFFFFFFu;
     ctx->last_batch = pqv_batch_timing{};
+    ctx->batch_state.valid = false;
     if (n_queries && ds->n_rows == 0) {  // an empty slice contributes nothing
         for (uint32_t q = 0; q < n_queries; ++q) out_count[q] = 0;
         return PQV_OK;
@@ -1171,7 +1185,35 @@ int pqv_l2_topk_batch_keys(pqv_ctx *ctx, uint64_t handle, const float *queries, 
         std::vector<uint8_t> handled(n_queries, 0);
         PQV_TRY(batch_topk(ctx, D, *ds, ds->n_rows, ds->dim, queries, n_queries, k, flags, nullptr, nullptr, nullptr, handled,
                            reinterpret_cast<u64 *>(out_keys), out_count, pos_base));
+        if (ctx->batch_state.valid) ctx->batch_state.handle = handle;
     }
+    return PQV_OK;
+}
+
+int pqv_l2_topk_batch_tie_candidates(pqv_ctx *ctx, uint64_t handle, uint32_t q_index, const float *query, uint64_t *out_keys,
+                                     uint64_t cap, uint64_t *out_count) {
+    if (!ctx || !query || !out_count || (cap && !out_keys)) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    pqv_ctx::BatchState &bs = ctx->batch_state;
+    if (!bs.valid || bs.handle != handle) return fail(PQV_EINVAL, "no batched pass of this dataset is pending (call pqv_l2_topk_batch_keys first)");
+    if (q_index >= bs.nq) return fail(PQV_EINVAL, "query index %u out of range (batch of %u)", q_index, bs.nq);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    // admissions of the reference heap inside this slice: positions < S from the exact scan of that prefix alone,
+    // positions >= S are all among the query's candidates of the batched pass
+    std::vector<u64> ent;
+    uint32_t dummy = 0;
+    PQV_TRY(topk_one(ctx, *ds, query, nullptr, 0, bs.k, bs.flags, nullptr, nullptr, &dummy, &ent, bs.pos_base, nullptr, nullptr, bs.S));
+    DeviceState &D = ctx->devs[bs.dev_index];
+    DevGuard guard(D.dev);
+    const uint32_t cq = std::min<uint32_t>(bs.seg_count[q_index], bs.cap_q);
+    std::vector<u64> seg(cq);
+    if (cq) CU_TRY(cudaMemcpy(seg.data(), D.tb_seg.p + (size_t)q_index * bs.cap_q, (size_t)cq * 8, cudaMemcpyDeviceToHost));
+    for (u64 key : seg)
+        if (key_pos(key) >= bs.S) ent.push_back(key + bs.pos_base);
+    *out_count = ent.size();
+    if (ent.size() > cap) return fail(PQV_ELIMIT, "%zu candidate keys do not fit the caller's buffer of %llu", ent.size(), (unsigned long long)cap);
+    if (!ent.empty()) memcpy(out_keys, ent.data(), ent.size() * 8);
     return PQV_OK;
 }
 

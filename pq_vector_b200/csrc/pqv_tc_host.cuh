@@ -404,6 +404,16 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
             raw_count[q] = cnt;
             handled[q] = 1;
         }
+        pqv_ctx::BatchState &bs = ctx->batch_state;  // the per-query candidate segments stay on the device for tie queries
+        bs.valid = true;
+        bs.S = S;
+        bs.nq = nq;
+        bs.k = k;
+        bs.flags = flags;
+        bs.cap_q = cap_q;
+        bs.pos_base = pos_base;
+        bs.dev_index = (int)(&D - ctx->devs.data());
+        bs.seg_count = h_cnt;
         return PQV_OK;
     }
     std::vector<uint32_t> ties;

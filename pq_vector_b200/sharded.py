@@ -72,10 +72,14 @@ class ShardedBatchTopk:
     reference heap's layout (exact ties) are re-run through the single-query candidate exchange of ShardedTopk, so
     every query's result is bit-identical to its own reference loop over the whole table."""
 
-    def __init__(self, batch_fn, scan_fn, pos_base: int, device: "torch.device | str" = "cpu", group=None):
+    def __init__(self, batch_fn, scan_fn, pos_base: int, device: "torch.device | str" = "cpu", group=None, tie_fn=None):
         """batch_fn(queries, k, flags, pos_base) -> (keys [nq, k+1] u64, counts [nq] u32)  (Dataset.l2_topk_batch_keys)
-        scan_fn: as ShardedTopk (Dataset.l2_topk_candidates), used for the tie queries."""
+        scan_fn: as ShardedTopk (Dataset.l2_topk_candidates): full-scan candidates of one query.
+        tie_fn(q_index, query) -> candidate keys of a flagged query from what the batched pass left on the device
+        (Dataset.l2_topk_batch_tie_candidates); without it the flagged queries use scan_fn."""
         self.batch_fn = batch_fn
+        self.scan_fn = scan_fn
+        self.tie_fn = tie_fn
         self.pos_base = int(pos_base)
         self.device = torch.device(device)
         self.group = group
@@ -84,28 +88,46 @@ class ShardedBatchTopk:
         self.last_gather_bytes = 0
         self.last_replayed = 0
 
+    def _all_gather(self, arr: np.ndarray) -> np.ndarray:
+        """[world, len(arr)] int64, same on every rank"""
+        send = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.int64)).to(self.device)
+        if self.world == 1:
+            return send.cpu().numpy()[None, :]
+        recv = torch.empty(self.world * send.numel(), dtype=torch.int64, device=self.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        self.last_gather_bytes += recv.numel() * 8
+        return recv.cpu().numpy().reshape(self.world, send.numel())
+
     def search(self, queries, k: int, flags: int):
         queries = np.ascontiguousarray(queries, dtype=np.float32)
         nq = queries.shape[0]
+        self.last_gather_bytes = 0
         keys, counts = self.batch_fn(queries, k, flags, self.pos_base)
         # one payload per rank: [nq, k+1] keys followed by the nq counts (widened to 64 bit)
-        payload = np.concatenate([keys.reshape(-1).view(np.int64), counts.astype(np.int64)])
-        send = torch.from_numpy(payload).to(self.device)
-        if self.world > 1:
-            recv = torch.empty(self.world * payload.size, dtype=torch.int64, device=self.device)
-            dist.all_gather_into_tensor(recv, send, group=self.group)
-            got = recv.cpu().numpy().reshape(self.world, payload.size)
-        else:
-            got = send.cpu().numpy()[None, :]
-        self.last_gather_bytes = got.nbytes
+        got = self._all_gather(np.concatenate([keys.reshape(-1).view(np.int64), counts.astype(np.int64)]))
         all_keys = got[:, :nq * (k + 1)].view(np.uint64).reshape(self.world, nq, k + 1)
         all_counts = got[:, nq * (k + 1):].astype(np.uint32)
         rows, dd, cnt, need = merge_batch_keys(all_keys, all_counts, k, flags)
-        # deterministic on identical gathered data -> every rank enters the same collective replays, in the same order
-        self.last_replayed = int(need.sum())
-        for q in np.nonzero(need)[0]:
-            r, d = self.single.search(queries[q], k, flags)
-            cnt[q] = r.size
-            rows[q, :r.size] = r
-            dd[q, :r.size] = d
+        # deterministic on identical gathered data -> every rank sees the same flagged queries, in the same order
+        ties = np.nonzero(need)[0]
+        self.last_replayed = int(ties.size)
+        if ties.size == 0:
+            return rows, dd, cnt
+        # candidates of ALL flagged queries travel together: one all-gather of their lengths, one of the padded keys
+        declined = bool((all_counts == 0xFFFFFFFF).any())   # a slice without a batched pass has nothing left on the device
+        use_tie = self.tie_fn is not None and not declined
+        cand = [np.ascontiguousarray(self.tie_fn(int(q), queries[q]) if use_tie else
+                                     self.scan_fn(queries[q], k, flags, self.pos_base), dtype=np.uint64) for q in ties]
+        lens = self._all_gather(np.array([c.size for c in cand], dtype=np.int64))        # [world, n_ties]
+        cap = max(int(lens.max()), 1)
+        padded = np.zeros((ties.size, cap), dtype=np.int64)
+        for i, c in enumerate(cand):
+            padded[i, :c.size] = c.view(np.int64)
+        allc = self._all_gather(padded.reshape(-1)).reshape(self.world, ties.size, cap)
+        for i, q in enumerate(ties):
+            union = np.concatenate([allc[r, i, :int(lens[r, i])] for r in range(self.world)]).view(np.uint64)
+            r_, d_ = replay_candidates(union, k, flags)
+            cnt[q] = r_.size
+            rows[q, :r_.size] = r_
+            dd[q, :r_.size] = d_
         return rows, dd, cnt

@@ -172,9 +172,17 @@ def test_sharded_batch_keys_merge_to_the_whole_table_answer(ctx, n, dim, nq, k, 
         queries[0] = data[n - 1]
     cuts = [0, n // 5, n // 5 + n // 2, n]
     parts = [ctx.dataset_from(data[cuts[i]:cuts[i + 1]]) for i in range(3)]
-    keys = np.stack([p.l2_topk_batch_keys(queries, k, flags, cuts[i])[0] for i, p in enumerate(parts)])
-    counts = np.stack([p.l2_topk_batch_keys(queries, k, flags, cuts[i])[1] for i, p in enumerate(parts)])
+    keys, counts, tie_cand = [], [], []
+    for i, p in enumerate(parts):
+        kk, cc = p.l2_topk_batch_keys(queries, k, flags, cuts[i])
+        keys.append(kk)
+        counts.append(cc)
+        # what the pass left on the device for flagged queries (only valid until the next batched call)
+        tie_cand.append([p.l2_topk_batch_tie_candidates(qi, q, cap=64) for qi, q in enumerate(queries)])
+    keys, counts = np.stack(keys), np.stack(counts)
     assert (counts != 0xFFFFFFFF).all()
+    with pytest.raises(P.PqvError):   # the state belongs to the last batched call only
+        parts[0].l2_topk_batch_tie_candidates(0, queries[0])
     rows, dist, cnt, need = P.merge_batch_keys(keys, counts, k, flags)
     order = 1 if flags & SEQ else 0
     if grid_data:
@@ -186,6 +194,8 @@ def test_sharded_batch_keys_merge_to_the_whole_table_answer(ctx, n, dim, nq, k, 
         if need[i]:
             cand = np.concatenate([p.l2_topk_candidates(q, k, flags, cuts[j], cap=1 << 20) for j, p in enumerate(parts)])
             r, d = P.replay_candidates(cand, k, flags)
+            r2, d2 = P.replay_candidates(np.concatenate([tc[i] for tc in tie_cand]), k, flags)
+            assert r2.tolist() == er.tolist() and bits(d2).tolist() == bits(ed).tolist(), i
         else:
             r, d = rows[i, :cnt[i]], dist[i, :cnt[i]]
         assert r.tolist() == er.tolist(), (i, bool(need[i]))

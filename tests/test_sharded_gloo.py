@@ -78,7 +78,9 @@ def _batch_worker(rank, world, port, n, dim, nq, k, flags, seed, out_dir):
             cnt[1] = 0xFFFFFFFF  # a slice that could not decide query 1 -> replay route
         return keys, cnt
 
-    sb = ShardedBatchTopk(batch, lambda q, k_, f_, pb: keys_of(q), lo, "cpu")
+    # even seeds also exercise the tie_fn route (candidates taken from the batched pass' leftovers)
+    tie_fn = (lambda qi, q: keys_of(q)) if seed in (3, 7) else None
+    sb = ShardedBatchTopk(batch, lambda q, k_, f_, pb: keys_of(q), lo, "cpu", tie_fn=tie_fn)
     rows, dd, cnt = sb.search(queries, k, flags)
     ok = True
     for i in range(nq):
