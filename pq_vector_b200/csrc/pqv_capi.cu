@@ -1323,12 +1323,12 @@ int pqv_bench_scan(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k
 
 // ---- k-means pieces ------------------------------------------------------------------------------
 static int dist_launch(DeviceState &D, const float *d_data, const uint32_t *d_ids, u64 n, uint32_t dim, const float *d_vec,
-                       float *d_out, int min_update) {
+                       float *d_out, int min_update, float *h_mirror = nullptr) {
     const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_data) & 15) == 0);
     const size_t smem = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)SCAN_WARPS * pqv::TileCfg<0, true>::TILE_FLOATS * 4;
     const u64 NG = (n + 31) / 32;
     constexpr uint32_t WIDE_MAX_DIM = 4096;
-    if (vec4 && dim <= WIDE_MAX_DIM && NG <= (u64)D.sm_count * 2 && (reinterpret_cast<uintptr_t>(d_vec) & 15) == 0) {
+    if (!h_mirror && vec4 && dim <= WIDE_MAX_DIM && NG <= (u64)D.sm_count * 2 && (reinterpret_cast<uintptr_t>(d_vec) & 15) == 0) {
         // short table (centroid ranking): one CTA per 32 rows instead of one warp (l2_dist_wide_kernel)
         uint32_t ts = ((dim >> 2) + 3u) & ~3u;
         if (((ts >> 2) & 1u) == 0) ts += 4;
@@ -1355,7 +1355,7 @@ static int dist_launch(DeviceState &D, const float *d_data, const uint32_t *d_id
             CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
             attr_smem = smem;                                                                                \
         }                                                                                                    \
-        kern<<<grid, SCAN_WARPS * 32, smem, D.stream>>>(d_data, d_ids, n, dim, d_vec, d_out, min_update);    \
+        kern<<<grid, SCAN_WARPS * 32, smem, D.stream>>>(d_data, d_ids, n, dim, d_vec, d_out, min_update, h_mirror); \
     } while (0)
     if (vec4) {
         if (d_ids) DIST_GO(true, true);

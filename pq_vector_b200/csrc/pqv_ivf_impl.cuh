@@ -46,15 +46,33 @@ std::vector<uint32_t> sample_indices(SplitMix64 &rng, u64 n, u64 amount) {
             std::swap(all[i], all[j]);
         }
         out.assign(all.begin(), all.begin() + amount);
-    } else {  // Floyd's algorithm, then shuffle
-        std::map<uint32_t, bool> seen;
+    } else {  // Floyd's algorithm, then shuffle; membership in an open-addressing table (a std::map costs 25 ms at 100 k draws)
+        u64 cap = 16;
+        while (cap < amount * 4) cap <<= 1;
+        const uint32_t EMPTY = 0xFFFFFFFFu;  // never a valid index here: amount * 2 < n <= 2^32 - 1 leaves it unused or handled below
+        std::vector<uint32_t> table(cap, EMPTY);
+        bool has_empty_value = false;  // the value 0xFFFFFFFF itself (only possible when n = 2^32)
+        auto contains_or_insert = [&](uint32_t v) -> bool {  // true if v was already present
+            if (v == EMPTY) {
+                const bool was = has_empty_value;
+                has_empty_value = true;
+                return was;
+            }
+            u64 h = ((u64)v * 0x9E3779B97F4A7C15ull) >> 32;
+            for (u64 i = h & (cap - 1);; i = (i + 1) & (cap - 1)) {
+                if (table[i] == v) return true;
+                if (table[i] == EMPTY) {
+                    table[i] = v;
+                    return false;
+                }
+            }
+        };
         for (u64 j = n - amount; j < n; ++j) {
             const uint32_t t = (uint32_t)rng.below(j + 1);
-            if (seen.count(t)) {
-                seen[(uint32_t)j] = true;
+            if (contains_or_insert(t)) {
+                contains_or_insert((uint32_t)j);
                 out.push_back((uint32_t)j);
             } else {
-                seen[t] = true;
                 out.push_back(t);
             }
         }
@@ -432,11 +450,15 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
     const u64 chunk = (init_n + workers - 1) / workers;
     const u64 n_chunks = (init_n + chunk - 1) / chunk;
     std::vector<float> local(n_chunks);
+    static const bool trace_pp = getenv("PQV_TRACE") != nullptr;
+    double tp[4] = {0, 0, 0, 0}, t_a = 0, t_b = 0, t_c = 0;
     for (uint32_t i = 1; i < C && !rc; ++i) {
-        rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p + (size_t)(i - 1) * dim, d_md.p, 1);
+        if (trace_pp) t_a = now_ms();
+        // the sweep writes its result to d_md and, in the same pass, to the page-locked host buffer md
+        rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p + (size_t)(i - 1) * dim, d_md.p, 1, md);
         if (rc) break;
-        ce = cudaMemcpyAsync(md, d_md.p, init_n * 4, cudaMemcpyDeviceToHost, D.stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);
+        ce = cudaStreamSynchronize(D.stream);
+        if (trace_pp) t_b = now_ms();
         if (ce != cudaSuccess) {
             rc = fail(PQV_ECUDA, "k-means++ sweep failed: %s", cudaGetErrorString(ce));
             break;
@@ -453,6 +475,7 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
         for (u64 s = full_chunks * chunk; s < init_n; ++s) local[full_chunks] += md[s];
         float total = 0.0f;
         for (u64 c = 0; c < n_chunks; ++c) total += local[c];
+        if (trace_pp) t_c = now_ms();
         if (total > 0.0f) {  // index.rs:372-383
             const float threshold = rng.unit_f32() * total;
             float cumsum = 0.0f;
@@ -467,7 +490,16 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
             ce = set_centroid(i, init_idx[rng.below(init_n)]);
         }
         if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "k-means++ pick failed: %s", cudaGetErrorString(ce));
+        if (trace_pp) {
+            const double t_d = now_ms();
+            tp[0] += t_b - t_a;
+            tp[1] += t_c - t_b;
+            tp[2] += t_d - t_c;
+        }
     }
+    if (trace_pp)
+        fprintf(stderr, "[pqv trace] k-means++ (%u picks over %llu rows): sweep+readback %.1f ms, chunk sums %.1f ms, cumsum pick %.1f ms\n",
+                C - 1, (unsigned long long)init_n, tp[0], tp[1], tp[2]);
     h_md.release();
     free_tmp();
     if (rc) return bail(rc);

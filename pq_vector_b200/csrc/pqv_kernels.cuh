@@ -496,7 +496,10 @@ template <bool VEC4, bool GATHER, int WARPS>
 __global__ void __launch_bounds__(WARPS * 32, 2) l2_dist_kernel(const float *__restrict__ data,
                                                              const uint32_t *__restrict__ row_ids, const u64 n,
                                                              const uint32_t dim, const float *__restrict__ vec,
-                                                             float *__restrict__ out, const int min_update) {
+                                                             float *__restrict__ out, const int min_update,
+                                                             float *__restrict__ mirror = nullptr) {
+    // mirror (may be null): page-locked host memory that receives the same final values while the kernel runs, so the
+    // k-means++ loop (1023 dependent sweeps, each followed by a host-side pick) needs no separate read-back copy
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int TILE_FLOATS = TileCfg<0, VEC4>::TILE_FLOATS;
     const uint32_t dim_pad = (dim + 3u) & ~3u;
@@ -511,11 +514,15 @@ __global__ void __launch_bounds__(WARPS * 32, 2) l2_dist_kernel(const float *__r
         const float d = group_distance<0, VEC4, GATHER>(data, row_ids, n, dim, g, s_vec, tile, lane);
         const u64 pos = g * 32 + lane;
         if (pos < n) {
+            float keep = d;
             if (min_update) {
-                if (d < out[pos]) out[pos] = d;
+                const float old = out[pos];
+                if (d < old) out[pos] = d;
+                else keep = old;
             } else {
                 out[pos] = d;
             }
+            if (mirror) mirror[pos] = keep;
         }
     }
 }
@@ -609,9 +616,7 @@ __global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__re
     __shared__ __align__(16) float Bs[2][AS_BN * AS_LD];
     const uint32_t tid = threadIdx.x;
     const uint32_t tx = tid & 15, ty = tid >> 4;
-    const u64 row0 = (u64)blockIdx.x * AS_BM;
     const u64 n = GATHER ? (u64)*n_dev : n_arg;
-    if (GATHER && row0 >= n) return;
     const uint32_t n4 = dim >> 2;                       // full 4-chunks (chain terms)
     const uint32_t nkb = (n4 + 7) >> 3;                 // blocks of 8 chunks = 32 columns
     const uint32_t tail0 = n4 << 2, ntail = dim - tail0;  // scalar tail terms (dim % 4)
@@ -637,6 +642,9 @@ __global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__re
         }
     };
 
+    // dense: one row tile per CTA (the grid covers the table).  GATHER: the list length is only known on the device, so
+    // a fixed grid walks the tiles (a grid sized for the worst case would launch a million CTAs that exit at once)
+    for (u64 row0 = (u64)blockIdx.x * AS_BM; row0 < n; row0 += (u64)gridDim.x * AS_BM) {
     float run_d[4];
     uint32_t run_i[4];
 #pragma unroll
@@ -743,6 +751,7 @@ __global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__re
             }
         }
     }
+    }  // row tiles
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1021,7 +1030,16 @@ __global__ void __launch_bounds__(256) centroid_update_kernel(const float *__res
     const u64 b = member_offsets[j], e = member_offsets[j + 1];
     for (uint32_t d = threadIdx.x; d < dim; d += blockDim.x) {
         float acc = 0.f;
-        for (u64 m = b; m < e; ++m) acc = __fadd_rn(acc, data[(u64)member_ids[m] * dim + d]);
+        u64 m = b;
+        // the additions form one serial chain per (cluster, column); the loads do not depend on it: 8 in flight
+        for (; m + 8 <= e; m += 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __ldg(data + (u64)__ldg(member_ids + m + i) * dim + d);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) acc = __fadd_rn(acc, v[i]);
+        }
+        for (; m < e; ++m) acc = __fadd_rn(acc, __ldg(data + (u64)__ldg(member_ids + m) * dim + d));
         if (e > b) acc = __fdiv_rn(acc, (float)(e - b));
         centroids[(u64)j * dim + d] = acc;
     }
