@@ -79,6 +79,9 @@ PQV_API int pqv_dataset_fill_synthetic(pqv_ctx *ctx, uint64_t handle, uint64_t n
                                        uint64_t stream_first_row);
 /* read rows back (tests, and fetching the k winners) */
 PQV_API int pqv_dataset_read(pqv_ctx *ctx, uint64_t handle, uint64_t first_row, uint64_t n_rows, float *out);
+/* rows row_ids[0 .. n_ids) in that order (gathered on the device, one copy back): the k winners of a search, or a rank's
+ * share of the k-means training sample (src/ivf/index.rs:234-239) */
+PQV_API int pqv_dataset_read_rows(pqv_ctx *ctx, uint64_t handle, const uint32_t *row_ids, uint64_t n_ids, float *out);
 
 /* ---- brute-force and gathered top-k ---------------------------------------------------------
  * pqv_l2_topk        replaces the re-rank loop of src/ivf/search.rs:112-141 when every row is a
@@ -156,6 +159,19 @@ PQV_API int pqv_centroid_rank(pqv_ctx *ctx, const float *centroids, uint32_t n_c
  *                    (replaces read_index_from_parquet + read_embeddings_for_rows + the re-rank loop). */
 PQV_API int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint32_t max_iters, uint64_t seed,
                           uint32_t sum_workers, uint64_t *out_index);
+/* The pieces of pqv_ivf_build for a table that is sharded over several processes: training stays on one
+ * GPU, only the final assignment of all rows is sharded.
+ * pqv_ivf_sample_rows  (pure host) the sizing rules of src/ivf/index.rs:161-174 and the training-sample draw of :222-242 for
+ *                      a table of n_rows: *out_clusters = C, out_rows[0 .. *out_n) = the global row ids pqv_ivf_build would
+ *                      train on, in its order.  out_rows == NULL just reports the sizes.
+ * pqv_kmeans_train     k_means (src/ivf/index.rs:323-457) over ALL rows of the dataset `handle` (the gathered sample):
+ *                      out_centroids[n_clusters * dim]; identical to what pqv_ivf_build computes from the same sample rows.
+ * Every rank then calls pqv_kmeans_assign on its slice with these centroids; the lists are the per-rank lists concatenated in
+ * rank order (ascending row ids, index.rs:202-206). */
+PQV_API int pqv_ivf_sample_rows(uint64_t n_rows, uint32_t n_clusters_or_0, uint64_t seed, uint32_t *out_rows, uint64_t cap,
+                                uint64_t *out_n, uint32_t *out_clusters);
+PQV_API int pqv_kmeans_train(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters, uint32_t max_iters, uint64_t seed,
+                             uint32_t sum_workers, float *out_centroids, uint32_t *out_iters);
 PQV_API int pqv_ivf_build_stats(pqv_ctx *ctx, uint64_t index, uint32_t *out_lloyd_iters, double *out_ms4);
 PQV_API int pqv_ivf_from_bytes(pqv_ctx *ctx, const uint8_t *bytes, uint64_t len, uint64_t *out_index);
 PQV_API int pqv_ivf_to_bytes(pqv_ctx *ctx, uint64_t index, uint8_t *out, uint64_t cap, uint64_t *out_len);

@@ -50,6 +50,7 @@ SIGNATURES = {
     "pqv_dataset_drop": (C.c_int, [ctxp, C.c_uint64]),
     "pqv_dataset_fill_synthetic": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, C.c_uint64, C.c_uint64]),
     "pqv_dataset_read": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, C.c_uint64, f32p]),
+    "pqv_dataset_read_rows": (C.c_int, [ctxp, C.c_uint64, u32p, C.c_uint64, f32p]),
     "pqv_l2_topk": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),
     "pqv_l2_topk_gather": (C.c_int, [ctxp, C.c_uint64, f32p, u32p, C.c_uint64, C.c_uint32, C.c_uint32, u32p, f32p,
                                      u32p]),
@@ -61,6 +62,8 @@ SIGNATURES = {
     "pqv_min_dist_update": (C.c_int, [ctxp, C.c_uint64, f32p, u64p, C.c_uint64, C.c_uint32, f32p, C.c_int, f32p]),
     "pqv_centroid_rank": (C.c_int, [ctxp, f32p, C.c_uint32, C.c_uint32, f32p, C.c_uint32, C.c_uint32, u32p, u32p]),
     "pqv_ivf_build": (C.c_int, [ctxp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, u64p]),
+    "pqv_ivf_sample_rows": (C.c_int, [C.c_uint64, C.c_uint32, C.c_uint64, u32p, C.c_uint64, u64p, u32p]),
+    "pqv_kmeans_train": (C.c_int, [ctxp, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint64, C.c_uint32, f32p, u32p]),
     "pqv_ivf_build_stats": (C.c_int, [ctxp, C.c_uint64, u32p, f64p]),
     "pqv_ivf_from_bytes": (C.c_int, [ctxp, C.POINTER(C.c_uint8), C.c_uint64, u64p]),
     "pqv_ivf_to_bytes": (C.c_int, [ctxp, C.c_uint64, C.POINTER(C.c_uint8), C.c_uint64, u64p]),

@@ -132,6 +132,16 @@ class Context:
         _check(_lib.pqv_ivf_build(self._h, dataset.handle, n_clusters or 0, max_iters, seed, sum_workers, C.byref(h)))
         return IvfIndex(self, h.value)
 
+    def kmeans_train(self, dataset: "Dataset", n_clusters: int, max_iters: int = 20, seed: int = 42,
+                     sum_workers: int = 0) -> np.ndarray:
+        """k_means (src/ivf/index.rs:323-457) over all rows of `dataset`; returns the C x dim centroids."""
+        out = np.empty((n_clusters, dataset.dim), dtype=np.float32)
+        it = C.c_uint32()
+        _check(_lib.pqv_kmeans_train(self._h, dataset.handle, n_clusters, max_iters, seed, sum_workers,
+                                     _ptr(out, C.c_float), C.byref(it)))
+        self.last_train_iters = it.value
+        return out
+
     def ivf_from_bytes(self, blob: bytes) -> "IvfIndex":
         buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob if blob else b"\0")
         h = C.c_uint64()
@@ -197,6 +207,12 @@ class Dataset:
     def read(self, first_row: int, n_rows: int) -> np.ndarray:
         out = np.empty((n_rows, self.dim), dtype=np.float32)
         _check(_lib.pqv_dataset_read(self.ctx._h, self.handle, first_row, n_rows, _ptr(out, C.c_float)))
+        return out
+
+    def read_rows(self, row_ids) -> np.ndarray:
+        ids = np.ascontiguousarray(row_ids, dtype=np.uint32).reshape(-1)
+        out = np.empty((ids.size, self.dim), dtype=np.float32)
+        _check(_lib.pqv_dataset_read_rows(self.ctx._h, self.handle, _ptr(ids, C.c_uint32), ids.size, _ptr(out, C.c_float)))
         return out
 
     def drop(self):
@@ -342,6 +358,15 @@ class IvfIndex:
         if self.handle:
             _check(_lib.pqv_ivf_drop(self.ctx._h, self.handle))
             self.handle = 0
+
+
+def ivf_sample_rows(n_rows: int, n_clusters=None, seed: int = 42):
+    """(global row ids of the training sample pqv_ivf_build would draw for a table of n_rows, cluster count C)."""
+    n, c = C.c_uint64(), C.c_uint32()
+    _check(_lib.pqv_ivf_sample_rows(n_rows, n_clusters or 0, seed, None, 0, C.byref(n), C.byref(c)))
+    out = np.empty(n.value, dtype=np.uint32)
+    _check(_lib.pqv_ivf_sample_rows(n_rows, n_clusters or 0, seed, _ptr(out, C.c_uint32), out.size, C.byref(n), C.byref(c)))
+    return out, c.value
 
 
 def replay_candidates(keys, k: int, flags: int = N.PQV_SQRT, row_ids=None):

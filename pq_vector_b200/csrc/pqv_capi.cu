@@ -1081,6 +1081,28 @@ int pqv_dataset_read(pqv_ctx *ctx, uint64_t handle, uint64_t first_row, uint64_t
     return PQV_OK;
 }
 
+int pqv_dataset_read_rows(pqv_ctx *ctx, uint64_t handle, const uint32_t *row_ids, uint64_t n_ids, float *out) {
+    if (!ctx || (n_ids && (!row_ids || !out))) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_dataset_read_rows needs a single-device dataset");
+    if (n_ids == 0) return PQV_OK;
+    for (u64 i = 0; i < n_ids; ++i)
+        if (row_ids[i] >= ds->n_rows) return fail(PQV_EINVAL, "row %u out of range (%llu rows)", row_ids[i], (unsigned long long)ds->n_rows);
+    Shard &sh = ds->shards[0];
+    DeviceState &D = ctx->devs[sh.di];
+    DevGuard guard(D.dev);
+    PQV_TRY(D.d_row_ids.ensure(n_ids));
+    PQV_TRY(D.d_tmp_rows.ensure((size_t)n_ids * ds->dim));
+    CU_TRY(cudaMemcpyAsync(D.d_row_ids.p, row_ids, n_ids * 4, cudaMemcpyHostToDevice, D.stream));
+    pqv::gather_rows_kernel<<<D.sm_count * 8, 256, 0, D.stream>>>(sh.d_data, D.d_row_ids.p, n_ids, ds->dim, D.d_tmp_rows.p);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaMemcpyAsync(out, D.d_tmp_rows.p, (size_t)n_ids * ds->dim * 4, cudaMemcpyDeviceToHost, D.stream));
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    return PQV_OK;
+}
+
 // ---- top-k -------------------------------------------------------------------------------------
 int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k, uint32_t flags,
                 uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {

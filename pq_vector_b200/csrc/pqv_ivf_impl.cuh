@@ -351,6 +351,202 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
     return PQV_OK;
 }
 
+// function-local device / pinned scratch: released on every exit path
+template <typename T>
+struct ScopedDev : DevBuf<T> {
+    ScopedDev() = default;
+    ScopedDev(const ScopedDev &) = delete;
+    ScopedDev &operator=(const ScopedDev &) = delete;
+    ~ScopedDev() { this->release(); }
+};
+template <typename T>
+struct ScopedPin : PinBuf<T> {
+    ScopedPin() = default;
+    ScopedPin(const ScopedPin &) = delete;
+    ScopedPin &operator=(const ScopedPin &) = delete;
+    ~ScopedPin() { this->release(); }
+};
+
+// k_means (src/ivf/index.rs:323-457) over the ns rows at d_sample (device): k-means++ over an init set, Lloyd until nothing
+// changes or max_iters; the centroids are left in D.d_centroids (C x dim).  Shared by pqv_ivf_build and pqv_kmeans_train.
+int kmeans_train_device(DeviceState &D, const float *d_sample, u64 ns, uint32_t dim, uint32_t C, uint32_t max_iters, u64 seed,
+                        uint32_t sum_workers, uint32_t *iters_out, double *t_init_out) {
+    // ---- k_means (index.rs:323-457)
+    SplitMix64 rng(seed);  // the reference re-seeds StdRng with the same seed inside k_means (index.rs:327)
+    const u64 init_n = std::max<u64>(std::min<u64>(ns, 50000), C);  // index.rs:332
+    std::vector<uint32_t> init_idx;
+    if (init_n == ns) {
+        init_idx.resize(ns);
+        for (u64 i = 0; i < ns; ++i) init_idx[i] = (uint32_t)i;
+    } else {
+        init_idx = sample_indices(rng, ns, init_n);
+    }
+    PQV_TRY(D.d_centroids.ensure((size_t)C * dim));
+    CU_TRY(cudaMemsetAsync(D.d_centroids.p, 0, (size_t)C * dim * 4, D.stream));  // vec![0.0; C*dim] (index.rs:330)
+    ScopedDev<uint32_t> d_init;
+    ScopedDev<float> d_md;
+    PQV_TRY(d_init.ensure(init_n));
+    PQV_TRY(d_md.ensure(init_n));
+    auto free_tmp = [&]() {
+        d_init.release();
+        d_md.release();
+    };
+    cudaError_t ce = cudaMemcpyAsync(d_init.p, init_idx.data(), init_n * 4, cudaMemcpyHostToDevice, D.stream);
+    const u64 first_choice = rng.below(init_n);  // index.rs:340
+    auto set_centroid = [&](uint32_t i, uint32_t sample_row) {
+        return cudaMemcpyAsync(D.d_centroids.p + (size_t)i * dim, d_sample + (size_t)sample_row * dim, (size_t)dim * 4,
+                               cudaMemcpyDeviceToDevice, D.stream);
+    };
+    if (ce == cudaSuccess) ce = set_centroid(0, init_idx[first_choice]);
+    if (ce != cudaSuccess) {
+        free_tmp();
+        return fail(PQV_ECUDA, "k-means init failed: %s", cudaGetErrorString(ce));
+    }
+    int rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p, d_md.p, 0);  // index.rs:344-352
+    ScopedPin<float> h_md;  // pinned: the sweep result comes back 1023 times
+    if (!rc) rc = h_md.ensure(init_n);
+    float *md = h_md.p;
+    unsigned hw = std::thread::hardware_concurrency();
+    const u64 workers = std::max<u64>(1, std::min<u64>(sum_workers ? sum_workers : (hw ? hw : 1), init_n));  // index.rs:259-265
+    const u64 chunk = (init_n + workers - 1) / workers;
+    const u64 n_chunks = (init_n + chunk - 1) / chunk;
+    std::vector<float> local(n_chunks);
+    static const bool trace_pp = getenv("PQV_TRACE") != nullptr;
+    double tp[4] = {0, 0, 0, 0}, t_a = 0, t_b = 0, t_c = 0;
+    for (uint32_t i = 1; i < C && !rc; ++i) {
+        if (trace_pp) t_a = now_ms();
+        // the sweep writes its result to d_md and, in the same pass, to the page-locked host buffer md
+        rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p + (size_t)(i - 1) * dim, d_md.p, 1, md);
+        if (rc) break;
+        ce = cudaStreamSynchronize(D.stream);
+        if (trace_pp) t_b = now_ms();
+        if (ce != cudaSuccess) {
+            rc = fail(PQV_ECUDA, "k-means++ sweep failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+        // index.rs:356-370: one serial f32 sum per worker chunk, then the chunk sums added in chunk order.  The chunk
+        // chains are independent, so they are advanced side by side (same bits, ~n_chunks x the instruction-level
+        // parallelism of walking them one after the other).
+        std::fill(local.begin(), local.end(), 0.0f);
+        const u64 full_chunks = init_n / chunk;  // chunks with all `chunk` elements
+        for (u64 o = 0; o < chunk; ++o) {
+            const float *col = md + o;
+            for (u64 c = 0; c < full_chunks; ++c) local[c] += col[c * chunk];
+        }
+        for (u64 s = full_chunks * chunk; s < init_n; ++s) local[full_chunks] += md[s];
+        float total = 0.0f;
+        for (u64 c = 0; c < n_chunks; ++c) total += local[c];
+        if (trace_pp) t_c = now_ms();
+        if (total > 0.0f) {  // index.rs:372-383
+            const float threshold = rng.unit_f32() * total;
+            float cumsum = 0.0f;
+            for (u64 s = 0; s < init_n; ++s) {
+                cumsum += md[s];
+                if (cumsum >= threshold) {
+                    ce = set_centroid(i, init_idx[s]);
+                    break;
+                }
+            }
+        } else {  // index.rs:384-389
+            ce = set_centroid(i, init_idx[rng.below(init_n)]);
+        }
+        if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "k-means++ pick failed: %s", cudaGetErrorString(ce));
+        if (trace_pp) {
+            const double t_d = now_ms();
+            tp[0] += t_b - t_a;
+            tp[1] += t_c - t_b;
+            tp[2] += t_d - t_c;
+        }
+    }
+    if (trace_pp)
+        fprintf(stderr, "[pqv trace] k-means++ (%u picks over %llu rows): sweep+readback %.1f ms, chunk sums %.1f ms, cumsum pick %.1f ms\n",
+                C - 1, (unsigned long long)init_n, tp[0], tp[1], tp[2]);
+    h_md.release();
+    free_tmp();
+    if (rc) return rc;
+    if (t_init_out) *t_init_out = now_ms();
+
+    // ---- Lloyd (index.rs:392-454).  Assignments, the changed count, the member lists and the centroid update all stay
+    // on the device; one 8-byte read per iteration decides whether to stop.
+    ScopedDev<uint32_t> d_asg[2], d_mids;
+    ScopedDev<u64> d_moff, d_changed;
+    ScopedPin<u64> h_changed;
+    auto free_lloyd = [&]() {
+        d_asg[0].release();
+        d_asg[1].release();
+        d_mids.release();
+        d_moff.release();
+        d_changed.release();
+        h_changed.release();
+    };
+    rc = d_asg[0].ensure(ns);
+    if (!rc) rc = d_asg[1].ensure(ns);
+    if (!rc) rc = d_mids.ensure(ns);
+    if (!rc) rc = d_moff.ensure((size_t)C + 1);
+    if (!rc) rc = d_changed.ensure(1);
+    if (!rc) rc = h_changed.ensure(1);
+    if (!rc) {
+        ce = cudaMemsetAsync(d_asg[0].p, 0, ns * 4, D.stream);  // vec![0usize; n] (index.rs:392)
+        if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "Lloyd init failed: %s", cudaGetErrorString(ce));
+    }
+    int cur = 0;  // d_asg[cur] = assignments of the previous iteration
+    std::vector<uint32_t> h_assign;  // host fallback only (cluster count beyond the device list builder)
+    std::vector<u64> moff;
+    std::vector<uint32_t> mids;
+    for (uint32_t iter = 0; iter < max_iters && !rc; ++iter) {
+        if (iters_out) *iters_out = iter + 1;
+        uint32_t *prev = d_asg[cur].p, *next = d_asg[cur ^ 1].p;
+        rc = assign_device(D, d_sample, ns, dim, D.d_centroids.p, C, next);
+        if (rc) break;
+        ce = cudaMemsetAsync(d_changed.p, 0, 8, D.stream);
+        if (ce == cudaSuccess) {
+            pqv::count_changed_kernel<<<D.sm_count * 2, 256, 0, D.stream>>>(prev, next, ns,
+                                                                           reinterpret_cast<unsigned long long *>(d_changed.p));
+            ce = cudaGetLastError();
+        }
+        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_changed.p, d_changed.p, 8, cudaMemcpyDeviceToHost, D.stream);
+        if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);
+        if (ce != cudaSuccess) {
+            rc = fail(PQV_ECUDA, "Lloyd assignment failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+        cur ^= 1;
+        if (h_changed.p[0] == 0) break;  // index.rs:432-434
+        bool on_device = false;
+        rc = csr_device(D, next, ns, C, d_moff.p, d_mids.p, &on_device);
+        if (rc) break;
+        if (!on_device) {
+            h_assign.resize(ns);
+            ce = cudaMemcpyAsync(h_assign.data(), next, ns * 4, cudaMemcpyDeviceToHost, D.stream);
+            if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);
+            if (ce == cudaSuccess) {
+                csr_from_assign(h_assign.data(), ns, C, moff, mids);
+                ce = cudaMemcpyAsync(d_mids.p, mids.data(), ns * 4, cudaMemcpyHostToDevice, D.stream);
+            }
+            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_moff.p, moff.data(), ((size_t)C + 1) * 8, cudaMemcpyHostToDevice, D.stream);
+            if (ce != cudaSuccess) {
+                rc = fail(PQV_ECUDA, "Lloyd update upload failed: %s", cudaGetErrorString(ce));
+                break;
+            }
+        }
+        pqv::centroid_update_kernel<<<C, 256, 0, D.stream>>>(d_sample, dim, d_mids.p, d_moff.p, D.d_centroids.p);
+        ce = cudaGetLastError();
+        if (ce == cudaSuccess && !on_device) ce = cudaStreamSynchronize(D.stream);  // mids/moff are reused next iteration
+        if (ce != cudaSuccess) {
+            rc = fail(PQV_ECUDA, "centroid update failed: %s", cudaGetErrorString(ce));
+            break;
+        }
+    }
+    if (!rc) {
+        ce = cudaStreamSynchronize(D.stream);
+        if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "Lloyd failed: %s", cudaGetErrorString(ce));
+    }
+    free_lloyd();
+    if (rc) return rc;
+
+    return PQV_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -411,177 +607,8 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
     }
 
     // ---- k_means (index.rs:323-457)
-    SplitMix64 rng(seed);  // the reference re-seeds StdRng with the same seed inside k_means (index.rs:327)
-    const u64 init_n = std::max<u64>(std::min<u64>(ns, 50000), C);  // index.rs:332
-    std::vector<uint32_t> init_idx;
-    if (init_n == ns) {
-        init_idx.resize(ns);
-        for (u64 i = 0; i < ns; ++i) init_idx[i] = (uint32_t)i;
-    } else {
-        init_idx = sample_indices(rng, ns, init_n);
-    }
-    IVF_TRY(D.d_centroids.ensure((size_t)C * dim));
-    IVF_CU(cudaMemsetAsync(D.d_centroids.p, 0, (size_t)C * dim * 4, D.stream));  // vec![0.0; C*dim] (index.rs:330)
-    DevBuf<uint32_t> d_init;
-    DevBuf<float> d_md;
-    IVF_TRY(d_init.ensure(init_n));
-    IVF_TRY(d_md.ensure(init_n));
-    auto free_tmp = [&]() {
-        d_init.release();
-        d_md.release();
-    };
-    cudaError_t ce = cudaMemcpyAsync(d_init.p, init_idx.data(), init_n * 4, cudaMemcpyHostToDevice, D.stream);
-    const u64 first_choice = rng.below(init_n);  // index.rs:340
-    auto set_centroid = [&](uint32_t i, uint32_t sample_row) {
-        return cudaMemcpyAsync(D.d_centroids.p + (size_t)i * dim, d_sample + (size_t)sample_row * dim, (size_t)dim * 4,
-                               cudaMemcpyDeviceToDevice, D.stream);
-    };
-    if (ce == cudaSuccess) ce = set_centroid(0, init_idx[first_choice]);
-    if (ce != cudaSuccess) {
-        free_tmp();
-        return bail(fail(PQV_ECUDA, "k-means init failed: %s", cudaGetErrorString(ce)));
-    }
-    int rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p, d_md.p, 0);  // index.rs:344-352
-    PinBuf<float> h_md;  // pinned: the sweep result comes back 1023 times
-    if (!rc) rc = h_md.ensure(init_n);
-    float *md = h_md.p;
-    unsigned hw = std::thread::hardware_concurrency();
-    const u64 workers = std::max<u64>(1, std::min<u64>(sum_workers ? sum_workers : (hw ? hw : 1), init_n));  // index.rs:259-265
-    const u64 chunk = (init_n + workers - 1) / workers;
-    const u64 n_chunks = (init_n + chunk - 1) / chunk;
-    std::vector<float> local(n_chunks);
-    static const bool trace_pp = getenv("PQV_TRACE") != nullptr;
-    double tp[4] = {0, 0, 0, 0}, t_a = 0, t_b = 0, t_c = 0;
-    for (uint32_t i = 1; i < C && !rc; ++i) {
-        if (trace_pp) t_a = now_ms();
-        // the sweep writes its result to d_md and, in the same pass, to the page-locked host buffer md
-        rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p + (size_t)(i - 1) * dim, d_md.p, 1, md);
-        if (rc) break;
-        ce = cudaStreamSynchronize(D.stream);
-        if (trace_pp) t_b = now_ms();
-        if (ce != cudaSuccess) {
-            rc = fail(PQV_ECUDA, "k-means++ sweep failed: %s", cudaGetErrorString(ce));
-            break;
-        }
-        // index.rs:356-370: one serial f32 sum per worker chunk, then the chunk sums added in chunk order.  The chunk
-        // chains are independent, so they are advanced side by side (same bits, ~n_chunks x the instruction-level
-        // parallelism of walking them one after the other).
-        std::fill(local.begin(), local.end(), 0.0f);
-        const u64 full_chunks = init_n / chunk;  // chunks with all `chunk` elements
-        for (u64 o = 0; o < chunk; ++o) {
-            const float *col = md + o;
-            for (u64 c = 0; c < full_chunks; ++c) local[c] += col[c * chunk];
-        }
-        for (u64 s = full_chunks * chunk; s < init_n; ++s) local[full_chunks] += md[s];
-        float total = 0.0f;
-        for (u64 c = 0; c < n_chunks; ++c) total += local[c];
-        if (trace_pp) t_c = now_ms();
-        if (total > 0.0f) {  // index.rs:372-383
-            const float threshold = rng.unit_f32() * total;
-            float cumsum = 0.0f;
-            for (u64 s = 0; s < init_n; ++s) {
-                cumsum += md[s];
-                if (cumsum >= threshold) {
-                    ce = set_centroid(i, init_idx[s]);
-                    break;
-                }
-            }
-        } else {  // index.rs:384-389
-            ce = set_centroid(i, init_idx[rng.below(init_n)]);
-        }
-        if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "k-means++ pick failed: %s", cudaGetErrorString(ce));
-        if (trace_pp) {
-            const double t_d = now_ms();
-            tp[0] += t_b - t_a;
-            tp[1] += t_c - t_b;
-            tp[2] += t_d - t_c;
-        }
-    }
-    if (trace_pp)
-        fprintf(stderr, "[pqv trace] k-means++ (%u picks over %llu rows): sweep+readback %.1f ms, chunk sums %.1f ms, cumsum pick %.1f ms\n",
-                C - 1, (unsigned long long)init_n, tp[0], tp[1], tp[2]);
-    h_md.release();
-    free_tmp();
-    if (rc) return bail(rc);
-    const double t_init = now_ms();
-
-    // ---- Lloyd (index.rs:392-454).  Assignments, the changed count, the member lists and the centroid update all stay
-    // on the device; one 8-byte read per iteration decides whether to stop.
-    DevBuf<uint32_t> d_asg[2], d_mids;
-    DevBuf<u64> d_moff, d_changed;
-    PinBuf<u64> h_changed;
-    auto free_lloyd = [&]() {
-        d_asg[0].release();
-        d_asg[1].release();
-        d_mids.release();
-        d_moff.release();
-        d_changed.release();
-        h_changed.release();
-    };
-    rc = d_asg[0].ensure(ns);
-    if (!rc) rc = d_asg[1].ensure(ns);
-    if (!rc) rc = d_mids.ensure(ns);
-    if (!rc) rc = d_moff.ensure((size_t)C + 1);
-    if (!rc) rc = d_changed.ensure(1);
-    if (!rc) rc = h_changed.ensure(1);
-    if (!rc) {
-        ce = cudaMemsetAsync(d_asg[0].p, 0, ns * 4, D.stream);  // vec![0usize; n] (index.rs:392)
-        if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "Lloyd init failed: %s", cudaGetErrorString(ce));
-    }
-    int cur = 0;  // d_asg[cur] = assignments of the previous iteration
-    std::vector<uint32_t> h_assign;  // host fallback only (cluster count beyond the device list builder)
-    std::vector<u64> moff;
-    std::vector<uint32_t> mids;
-    for (uint32_t iter = 0; iter < max_iters && !rc; ++iter) {
-        ix->build_iters = iter + 1;
-        uint32_t *prev = d_asg[cur].p, *next = d_asg[cur ^ 1].p;
-        rc = assign_device(D, d_sample, ns, dim, D.d_centroids.p, C, next);
-        if (rc) break;
-        ce = cudaMemsetAsync(d_changed.p, 0, 8, D.stream);
-        if (ce == cudaSuccess) {
-            pqv::count_changed_kernel<<<D.sm_count * 2, 256, 0, D.stream>>>(prev, next, ns,
-                                                                           reinterpret_cast<unsigned long long *>(d_changed.p));
-            ce = cudaGetLastError();
-        }
-        if (ce == cudaSuccess) ce = cudaMemcpyAsync(h_changed.p, d_changed.p, 8, cudaMemcpyDeviceToHost, D.stream);
-        if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);
-        if (ce != cudaSuccess) {
-            rc = fail(PQV_ECUDA, "Lloyd assignment failed: %s", cudaGetErrorString(ce));
-            break;
-        }
-        cur ^= 1;
-        if (h_changed.p[0] == 0) break;  // index.rs:432-434
-        bool on_device = false;
-        rc = csr_device(D, next, ns, C, d_moff.p, d_mids.p, &on_device);
-        if (rc) break;
-        if (!on_device) {
-            h_assign.resize(ns);
-            ce = cudaMemcpyAsync(h_assign.data(), next, ns * 4, cudaMemcpyDeviceToHost, D.stream);
-            if (ce == cudaSuccess) ce = cudaStreamSynchronize(D.stream);
-            if (ce == cudaSuccess) {
-                csr_from_assign(h_assign.data(), ns, C, moff, mids);
-                ce = cudaMemcpyAsync(d_mids.p, mids.data(), ns * 4, cudaMemcpyHostToDevice, D.stream);
-            }
-            if (ce == cudaSuccess) ce = cudaMemcpyAsync(d_moff.p, moff.data(), ((size_t)C + 1) * 8, cudaMemcpyHostToDevice, D.stream);
-            if (ce != cudaSuccess) {
-                rc = fail(PQV_ECUDA, "Lloyd update upload failed: %s", cudaGetErrorString(ce));
-                break;
-            }
-        }
-        pqv::centroid_update_kernel<<<C, 256, 0, D.stream>>>(d_sample, dim, d_mids.p, d_moff.p, D.d_centroids.p);
-        ce = cudaGetLastError();
-        if (ce == cudaSuccess && !on_device) ce = cudaStreamSynchronize(D.stream);  // mids/moff are reused next iteration
-        if (ce != cudaSuccess) {
-            rc = fail(PQV_ECUDA, "centroid update failed: %s", cudaGetErrorString(ce));
-            break;
-        }
-    }
-    if (!rc) {
-        ce = cudaStreamSynchronize(D.stream);
-        if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "Lloyd failed: %s", cudaGetErrorString(ce));
-    }
-    free_lloyd();
-    if (rc) return bail(rc);
+    double t_init = t_begin;
+    IVF_TRY(kmeans_train_device(D, d_sample, ns, dim, C, max_iters, seed, sum_workers, &ix->build_iters, &t_init));
     const double t_lloyd = now_ms();
 
     // ---- final assignment of all N rows (index.rs:189-206); the inverted lists are built on the device and stay
@@ -629,6 +656,51 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
     const u64 h = ctx->next_handle++;
     ctx->indexes[h] = ix;
     *out_index = h;
+    return PQV_OK;
+}
+
+int pqv_kmeans_train(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters, uint32_t max_iters, uint64_t seed,
+                     uint32_t sum_workers, float *out_centroids, uint32_t *out_iters) {
+    if (!ctx || !out_centroids) return fail(PQV_EINVAL, "null argument");
+    if (max_iters == 0) return fail(PQV_EINVAL, "max_iters must be > 0");
+    if (n_clusters == 0) return fail(PQV_EINVAL, "Cluster count must be > 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_kmeans_train needs a single-device dataset");
+    if (ds->n_rows == 0) return fail(PQV_EINVAL, "Cannot build IVF index with zero vectors");
+    if (n_clusters > ds->n_rows) return fail(PQV_EINVAL, "n_clusters cannot exceed number of vectors");
+    Shard &sh = ds->shards[0];
+    DeviceState &D = ctx->devs[sh.di];
+    DevGuard guard(D.dev);
+    uint32_t iters = 0;
+    PQV_TRY(kmeans_train_device(D, sh.d_data, ds->n_rows, ds->dim, n_clusters, max_iters, seed, sum_workers, &iters, nullptr));
+    CU_TRY(cudaMemcpyAsync(out_centroids, D.d_centroids.p, (size_t)n_clusters * ds->dim * 4, cudaMemcpyDeviceToHost, D.stream));
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    if (out_iters) *out_iters = iters;
+    return PQV_OK;
+}
+
+int pqv_ivf_sample_rows(uint64_t n_rows, uint32_t n_clusters_or_0, uint64_t seed, uint32_t *out_rows, uint64_t cap,
+                        uint64_t *out_n, uint32_t *out_clusters) {
+    if (!out_n || !out_clusters) return fail(PQV_EINVAL, "null argument");
+    if (n_rows == 0) return fail(PQV_EINVAL, "Cannot build IVF index with zero vectors");  // index.rs:157-159
+    if (n_rows > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "row ids are u32");
+    const u64 C64 = n_clusters_or_0 ? n_clusters_or_0 : (u64)std::ceil(std::sqrt((double)n_rows));  // index.rs:161-167
+    if (C64 > n_rows) return fail(PQV_EINVAL, "n_clusters cannot exceed number of vectors");
+    u64 sample_size = std::max<u64>(n_rows / 20, 1);  // index.rs:172-174
+    sample_size = std::min<u64>(sample_size, 100000);
+    sample_size = std::min<u64>(std::max<u64>(sample_size, C64), n_rows);
+    *out_n = sample_size;
+    *out_clusters = (uint32_t)C64;
+    if (sample_size > cap || !out_rows) return out_rows ? fail(PQV_ELIMIT, "%llu sample rows do not fit the caller's buffer", (unsigned long long)sample_size) : PQV_OK;
+    if (sample_size == n_rows) {  // index.rs:182-183: the whole table, in order
+        for (u64 i = 0; i < n_rows; ++i) out_rows[i] = (uint32_t)i;
+    } else {
+        SplitMix64 rng(seed);
+        const std::vector<uint32_t> idx = sample_indices(rng, n_rows, sample_size);
+        memcpy(out_rows, idx.data(), sample_size * 4);
+    }
     return PQV_OK;
 }
 

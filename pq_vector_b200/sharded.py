@@ -11,7 +11,7 @@ import numpy as np
 import torch
 import torch.distributed as dist
 
-from .api import merge_batch_keys, replay_candidates
+from .api import ivf_sample_rows, merge_batch_keys, replay_candidates
 
 DEFAULT_CAP = 4096  # candidate keys per rank carried by the single all-gather (32 KiB)
 
@@ -131,3 +131,80 @@ class ShardedBatchTopk:
             rows[q, :r_.size] = r_
             dd[q, :r_.size] = d_
         return rows, dd, cnt
+
+
+def index_to_bytes(centroids: np.ndarray, offsets: np.ndarray, ids: np.ndarray) -> bytes:
+    """IvfIndex::to_bytes (src/ivf/index.rs:65-83): u32 dim, u32 C, f32[C*dim], then per cluster u32 len + u32[len]."""
+    c, dim = centroids.shape
+    parts = [np.array([dim, c], dtype="<u4").tobytes(), np.ascontiguousarray(centroids, dtype="<f4").tobytes()]
+    ids = np.ascontiguousarray(ids, dtype="<u4")
+    for j in range(c):
+        lo, hi = int(offsets[j]), int(offsets[j + 1])
+        parts.append(np.array([hi - lo], dtype="<u4").tobytes())
+        parts.append(ids[lo:hi].tobytes())
+    return b"".join(parts)
+
+
+class ShardedIvfBuild:
+    """build_ivf_index (src/ivf/index.rs:152-214) over a table whose rows are sharded across the ranks:
+    the training sample (<= 100 k rows, drawn from the whole table by the same rule and stream as pqv_ivf_build) is
+    gathered to rank 0, k-means runs there on one GPU, the centroids (C x dim f32, 3 MB at C = 1024, dim = 768) are
+    broadcast, every rank assigns ITS rows with pqv_kmeans_assign, and the per-rank assignments are gathered so that each
+    rank can lay the lists out in ascending global row id -- the result is byte-identical to the single-GPU build of
+    the concatenated table.
+
+    read_rows(local_ids) -> [m, dim] f32 rows of this rank's slice      (Dataset.read per run of ids)
+    train(sample [S, dim], C, max_iters, seed) -> [C, dim] centroids     (Context.kmeans_train over a scratch dataset)
+    assign(centroids) -> u32[n_local] assignment of this rank's rows     (Context.kmeans_assign on the resident slice)"""
+
+    def __init__(self, read_rows, train, assign, n_local: int, pos_base: int, n_global: int, dim: int,
+                 device: "torch.device | str" = "cpu", group=None):
+        self.read_rows, self.train, self.assign = read_rows, train, assign
+        self.n_local, self.pos_base, self.n_global, self.dim = int(n_local), int(pos_base), int(n_global), int(dim)
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+
+    def _gather_var(self, arr: np.ndarray, dtype) -> "list[np.ndarray]":
+        """all ranks' 1-D arrays (different lengths), as a list in rank order"""
+        arr = np.ascontiguousarray(arr, dtype=dtype)
+        if self.world == 1:
+            return [arr]
+        n = torch.tensor([arr.size], dtype=torch.int64, device=self.device)
+        sizes = [torch.zeros(1, dtype=torch.int64, device=self.device) for _ in range(self.world)]
+        dist.all_gather(sizes, n, group=self.group)
+        sizes = [int(x.item()) for x in sizes]
+        cap = max(max(sizes), 1)
+        send = torch.zeros(cap, dtype=torch.from_numpy(arr[:0]).dtype, device=self.device)
+        send[:arr.size] = torch.from_numpy(arr).to(self.device)
+        recv = torch.empty(self.world * cap, dtype=send.dtype, device=self.device)
+        dist.all_gather_into_tensor(recv, send, group=self.group)
+        got = recv.cpu().numpy().reshape(self.world, cap)
+        return [got[r, :sizes[r]].astype(dtype, copy=False) for r in range(self.world)]
+
+    def build(self, n_clusters=None, max_iters: int = 20, seed: int = 42) -> bytes:
+        sample_ids, C = ivf_sample_rows(self.n_global, n_clusters, seed)        # same on every rank
+        mine = (sample_ids >= self.pos_base) & (sample_ids < self.pos_base + self.n_local)
+        where = np.nonzero(mine)[0]                                             # positions inside the sample
+        rows = self.read_rows(sample_ids[mine].astype(np.int64) - self.pos_base) if where.size else \
+            np.empty((0, self.dim), np.float32)
+        parts_pos = self._gather_var(where.astype(np.int64), np.int64)
+        parts_rows = self._gather_var(np.ascontiguousarray(rows, np.float32).reshape(-1).view(np.int32), np.int32)
+        centroids = np.empty((C, self.dim), dtype=np.float32)
+        if self.rank == 0:
+            sample = np.empty((sample_ids.size, self.dim), dtype=np.float32)
+            for pos, flat in zip(parts_pos, parts_rows):
+                if pos.size:
+                    sample[pos] = flat.view(np.float32).reshape(-1, self.dim)
+            centroids[:] = self.train(sample, C, max_iters, seed)
+        if self.world > 1:
+            t = torch.from_numpy(centroids).to(self.device)
+            dist.broadcast(t, src=0, group=self.group)
+            centroids = t.cpu().numpy()
+        local = np.ascontiguousarray(self.assign(centroids), dtype=np.uint32)
+        assign = np.concatenate(self._gather_var(local.view(np.int32), np.int32)).view(np.uint32)   # rank order = row order
+        order = np.argsort(assign, kind="stable").astype(np.uint32)             # per cluster, ascending row id
+        offsets = np.zeros(C + 1, dtype=np.uint64)
+        np.cumsum(np.bincount(assign, minlength=C), out=offsets[1:])
+        return index_to_bytes(centroids, offsets, order)

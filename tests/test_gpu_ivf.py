@@ -174,3 +174,26 @@ def test_vldb_c1_through_the_index(ctx, vldb):
         # distances are those of the table, and on this data there are no ties inside the top 10 -> same ids
         assert r.tolist() == ids
     ix.drop(); ds.drop()
+
+
+@pytest.mark.parametrize("n,dim,C", [(30000, 64, 40), (2500, 32, None), (120, 8, 120)])
+def test_sharded_build_pieces_equal_the_monolithic_build(ctx, n, dim, C):
+    """pqv_ivf_sample_rows + pqv_kmeans_train + pqv_kmeans_assign, glued by ShardedIvfBuild (world of one here; the
+    two-rank exchange is covered by the gloo test and benchmarks/check_sharded_ivf.py), give the blob of pqv_ivf_build."""
+    from pq_vector_b200.sharded import ShardedIvfBuild
+    rng = np.random.default_rng(n)
+    cent0 = rng.standard_normal((25, dim)).astype(np.float32)
+    data = (cent0[rng.integers(0, 25, n)] + 0.3 * rng.standard_normal((n, dim))).astype(np.float32)
+    ds = ctx.dataset_from(data)
+    want = ctx.ivf_build(ds, n_clusters=C, max_iters=7, seed=5).to_bytes()
+
+    def train(sample, c, max_iters, seed):
+        sd = ctx.dataset_from(sample)
+        out = ctx.kmeans_train(sd, c, max_iters, seed)
+        sd.drop()
+        return out
+
+    sb = ShardedIvfBuild(ds.read_rows, train, lambda cent: ctx.kmeans_assign(ds, cent), n, 0, n, dim)
+    assert np.array_equal(ds.read_rows([n - 1, 0, 7]), data[[n - 1, 0, 7]])
+    assert sb.build(C, 7, 5) == want
+    ds.drop()

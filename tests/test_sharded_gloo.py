@@ -102,3 +102,41 @@ def test_two_rank_batched_exchange_matches_single_process(tmp_path, n, dim, nq, 
     assert got[0][1] == got[1][1]                 # both ranks took the same replay decisions
     if seed % 2:
         assert got[0][1] > 0                      # the tie-heavy cases really exercised the replay route
+
+
+def _ivf_worker(rank, world, port, n, dim, C, seed, out_dir):
+    sys.path.insert(0, ROOT)
+    import oracle as O
+    from pq_vector_b200.sharded import ShardedIvfBuild
+    from pq_vector_b200.api import ivf_sample_rows
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    data = rng.random((n, dim), dtype=np.float32)
+    per = (n + world - 1) // world
+    lo, hi = rank * per, min(n, (rank + 1) * per)
+
+    def train(sample, c, max_iters, seed_):     # stand-in for Context.kmeans_train: any deterministic function of the sample
+        return np.ascontiguousarray(sample[:c] * np.float32(0.5) + np.float32(0.25))
+
+    sb = ShardedIvfBuild(lambda ids: data[lo:hi][ids], train, lambda cent: O.assign(data[lo:hi], cent, workers=2),
+                         hi - lo, lo, n, dim, "cpu")
+    blob = sb.build(C, 5, seed)
+    # the single-process answer: same sample rule, same train, oracle assignment + lists over the whole table
+    sample_ids, c = ivf_sample_rows(n, C, seed)
+    cent = train(data[sample_ids], c, 5, seed)
+    a = O.assign(data, cent, workers=2)
+    offsets, ids = O.inverted_lists(a, c)
+    want = O.index_to_bytes(dim, cent, offsets, ids)
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(blob == want)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,dim,C,seed", [(4000, 6, 9, 1), (333, 4, None, 2), (50, 3, 50, 3)])
+def test_two_rank_ivf_build_matches_single_process(tmp_path, n, dim, C, seed):
+    port = 33500 + (os.getpid() + seed) % 2000
+    mp.spawn(_ivf_worker, args=(2, port, n, dim, C, seed, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
