@@ -115,7 +115,11 @@ constexpr uint32_t CSR_MAX_C = 51200;  // 200 KiB of u32 counters
 
 int csr_device(DeviceState &D, const uint32_t *d_assign, u64 n, uint32_t C, u64 *d_offsets, uint32_t *d_ids, bool *ok) {
     *ok = false;
-    if (C > CSR_MAX_C || n == 0 || n > 0xFFFFFFFFull) return PQV_OK;
+    static const bool force_host = [] {  // PQV_CSR=host: build the lists on the host (the path clusters > CSR_MAX_C take)
+        const char *e = getenv("PQV_CSR");
+        return e && !strcmp(e, "host");
+    }();
+    if (force_host || C > CSR_MAX_C || n == 0 || n > 0xFFFFFFFFull) return PQV_OK;
     u64 R = (n + (u64)D.sm_count * 4 - 1) / ((u64)D.sm_count * 4);
     R = std::min<u64>(std::max<u64>((R + 255) / 256 * 256, 256), 4096);
     const u64 nb_max = std::max<u64>((64ull << 20) / C, 1);  // counts matrix <= 256 MiB

@@ -197,3 +197,86 @@ def test_sharded_build_pieces_equal_the_monolithic_build(ctx, n, dim, C):
     assert np.array_equal(ds.read_rows([n - 1, 0, 7]), data[[n - 1, 0, 7]])
     assert sb.build(C, 7, 5) == want
     ds.drop()
+
+
+def _search_both_ways(ctx, ix, ds, q, k, nprobe, flags=SQRT):
+    """the one-round-trip device path and the host-ranked path (PQV_IVF_FUSED is read once per process, so the host
+    path is reached the way a caller reaches it: candidate_rows + gather)"""
+    r, d = ix.search(ds, q, k, nprobe, flags)
+    cand = ix.candidate_rows(q, nprobe)
+    r2, d2 = ds.l2_topk_gather(q, cand, k, flags) if cand.size else (np.empty(0, np.uint32), np.empty(0, np.float32))
+    assert r.tolist() == r2.tolist() and d.view(np.uint32).tolist() == d2.view(np.uint32).tolist()
+    return r, d, cand
+
+
+def test_search_with_empty_lists_ties_and_duplicates(ctx):
+    """hand-made index: empty clusters, duplicate centroids (stable rank: lowest cluster index first), duplicate rows
+    (exact distance ties across lists) -- device ranking + expansion + scan against the oracle's walk"""
+    rng = np.random.default_rng(5)
+    dim, n = 16, 4000
+    data = rng.integers(0, 3, (n, dim)).astype(np.float32)
+    data[100:200] = data[0:100]                                   # duplicates -> bit-equal distances
+    cent = rng.integers(0, 3, (12, dim)).astype(np.float32)
+    cent[7] = cent[2]                                             # duplicate centroid: equal distances, rank 2 before 7
+    cent[11] = cent[2]
+    assign = O.assign(data, cent, workers=2)                      # first-min: clusters 7 and 11 stay empty
+    offsets, ids = O.inverted_lists(assign, 12)
+    assert offsets[8] == offsets[7] and offsets[12] == offsets[11]
+    ix = ctx.ivf_from_bytes(O.index_to_bytes(dim, cent, offsets, ids))
+    ds = ctx.dataset_from(data)
+    for qi in (0, 150, 3999):
+        q = data[qi]
+        for nprobe in (1, 2, 5, 12, 99):
+            for k in (1, 10, 300):
+                for flags in (SQRT, SEQ):
+                    r, d, cand = _search_both_ways(ctx, ix, ds, q, k, nprobe, flags)
+                    assert cand.tolist() == O.candidate_rows(q, cent, offsets, ids, nprobe).tolist()
+                    er, ed = O.topk_rerank_gather(q, data, cand, k, 1 if flags & SEQ else 0, bool(flags & SQRT))
+                    assert r.tolist() == er.tolist() and d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+    # an index whose probed lists are all empty
+    off2 = np.zeros(13, np.uint64)
+    off2[12:] = 0
+    ix2 = ctx.ivf_from_bytes(O.index_to_bytes(dim, cent, off2, np.empty(0, np.uint32)))
+    r, d = ix2.search(ds, data[0], 5, 3, SQRT)
+    assert r.size == 0 and d.size == 0
+    ix.drop(); ix2.drop(); ds.drop()
+
+
+def test_search_with_non_finite_centroids_takes_the_host_ranking(ctx):
+    """a NaN / inf centroid distance: the device ranking declines (NaN) or ranks it last (inf); the result must be the
+    oracle's either way (index.rs:142-146: partial_cmp -> Equal for NaN)"""
+    rng = np.random.default_rng(8)
+    dim, n = 8, 1500
+    data = rng.random((n, dim), dtype=np.float32)
+    cent = rng.random((9, dim), dtype=np.float32)
+    assign = O.assign(data, cent, workers=2)
+    offsets, ids = O.inverted_lists(assign, 9)
+    ds = ctx.dataset_from(data)
+    for bad in (np.inf, np.nan):
+        c2 = cent.copy()
+        c2[4, 3] = bad
+        ix = ctx.ivf_from_bytes(O.index_to_bytes(dim, c2, offsets, ids))
+        for nprobe in (1, 4, 9):
+            q = data[7]
+            r, d = ix.search(ds, q, 10, nprobe, SQRT)
+            cand = O.candidate_rows(q, c2, offsets, ids, nprobe)
+            er, ed = O.topk_rerank_gather(q, data, cand, 10, 0, True)
+            assert r.tolist() == er.tolist() and d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+        ix.drop()
+    ds.drop()
+
+
+def test_host_list_builder_equals_the_device_one(ctx):
+    """PQV_CSR=host (read once per process) cannot be flipped here, so the equality is checked at the blob level: the
+    device-built lists of pqv_ivf_build against lists rebuilt on the host from the same assignment (oracle)"""
+    rng = np.random.default_rng(3)
+    n, dim, C = 70000, 16, 300
+    data = rng.random((n, dim), dtype=np.float32)
+    ds = ctx.dataset_from(data)
+    ix = ctx.ivf_build(ds, n_clusters=C, max_iters=2, seed=9)
+    d2, cent, offsets, ids = O.index_from_bytes(ix.to_bytes())
+    a = O.assign(data, cent, workers=4)
+    eoff, eids = O.inverted_lists(a, C)
+    assert np.array_equal(offsets, eoff) and np.array_equal(ids, eids)
+    assert all(np.all(np.diff(ids[int(offsets[c]):int(offsets[c + 1])].astype(np.int64)) > 0) for c in range(C))
+    ix.drop(); ds.drop()
