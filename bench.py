@@ -48,6 +48,9 @@ def parse_args():
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-cold", action="store_true")
+    ap.add_argument("--exchange", default="p2p", choices=["p2p", "nccl"],
+                    help="N > 1: candidate exchange over NVLink peer memory (default; falls back to nccl if the IPC "
+                         "set-up fails) or one NCCL all-gather per query")
     ap.add_argument("--cold-rows", type=int, default=2_000_000)
     return ap.parse_args()
 
@@ -239,6 +242,20 @@ def run_ours(args):
     qds.drop()
 
     sharded = ShardedTopk(lambda q, k_, f_, pb: ds.l2_topk_candidates(q, k_, f_, pb), pos_base, dev)
+    exchange = "none" if world == 1 else "nccl"
+    if world > 1 and args.exchange == "p2p":
+        try:
+            sharded.enable_p2p(ctx, ds)
+            ok = 1.0
+        except Exception as e:  # noqa: BLE001  (IPC not available in this container, ...)
+            print(f"[bench] rank {rank}: peer exchange set-up failed ({e}); using the NCCL all-gather", file=sys.stderr)
+            ok = 0.0
+        t_ok = torch.tensor([ok], dtype=torch.float64, device=dev)
+        dist.all_reduce(t_ok, op=dist.ReduceOp.MIN)     # all ranks or none
+        if float(t_ok.item()) < 1.0:
+            sharded._p2p = None
+        else:
+            exchange = "p2p"
 
     sampler = ClockSampler(local) if rank == 0 else None
 
@@ -269,8 +286,12 @@ def run_ours(args):
     for i in range(args.steps):
         res = search(queries[args.warmup + i])
         t = ctx.last_timing()
-        h2d += dim * 4 + (sharded.cap + 1) * 8 * (world > 1)
-        d2h += 8 * (1 + max(t["entrants"], 8192)) + (sharded.last_gather_bytes if world > 1 else 0)
+        if exchange == "p2p":   # query in; the exchanged block of all ranks (world x (1 + cap) keys) out
+            h2d += dim * 4
+            d2h += world * (sharded.cap + 1) * 8
+        else:
+            h2d += dim * 4 + (sharded.cap + 1) * 8 * (world > 1)
+            d2h += 8 * (1 + max(t["entrants"], 8192)) + (sharded.last_gather_bytes if world > 1 else 0)
     barrier()
     e2e_s = max_over_ranks((time.perf_counter() - t0) / args.steps)
     clocks = sampler.stop() if sampler else None
@@ -334,16 +355,22 @@ def run_ours(args):
                 "global_qps": 1.0 / (step_ms * 1e-3),
                 "l2_policy": f"inputs ({scan_bytes / 1e9:.2f} GB per GPU per step) are larger than L2 (126 MB); no flush needed",
                 "tie_order": "reference BinaryHeap replay (bit-exact row order)",
-                "sharding": "contiguous row ranges, one all-gather of per-rank heap-entrant candidates" if world > 1 else "single GPU",
+                "sharding": ("single GPU" if world == 1 else
+                             "contiguous row ranges; per-rank heap-entrant candidates exchanged " +
+                             ("by peer writes over NVLink from the scan's tail kernel (pqv_peer.cuh)" if exchange == "p2p"
+                              else "with one NCCL all-gather")),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "l2_scan_topk_kernel<ORDER=0,VEC4,dense,WARPS=8,RB=8,CBV=2,MINB=2>",
                          "algorithmic_bytes_per_launch": scan_bytes, "kernel_ms": scan_ms, "post_kernels_ms": post_ms},
             "e2e": {"value": world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_s * 1e3,
+                    "exchange": exchange,
                     "path": ("pqv_l2_topk: host query in, host (row_idx, distance) out" if world == 1 else
-                             "pqv_l2_topk_candidates (host query in, host candidate keys out) + one all-gather + "
-                             "pqv_replay_candidates")},
+                             ("pqv_l2_topk_candidates_p2p (host query in, union of all ranks' candidate keys out) + "
+                              "pqv_replay_candidates" if exchange == "p2p" else
+                              "pqv_l2_topk_candidates (host query in, host candidate keys out) + one all-gather + "
+                              "pqv_replay_candidates"))},
             "gpu_launches": 4 * args.steps,
             "clocks": clocks,
             "aggregate_gbs": world * scan_bytes / (step_ms * 1e-3) / 1e9,

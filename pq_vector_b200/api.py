@@ -142,6 +142,17 @@ class Context:
         self.last_train_iters = it.value
         return out
 
+    def peer_exchange_create(self, world: int, rank: int, cap_keys: int = 4096) -> bytes:
+        """Allocate this rank's NVLink exchange buffer; returns its 64-byte CUDA IPC handle (pqv_peer_exchange_create)."""
+        h = (C.c_uint8 * 64)()
+        _check(_lib.pqv_peer_exchange_create(self._h, world, rank, cap_keys, h))
+        return bytes(h)
+
+    def peer_exchange_open(self, handles: bytes):
+        """Map the peers' buffers: `handles` = the world ranks' 64-byte handles concatenated in rank order."""
+        buf = (C.c_uint8 * len(handles)).from_buffer_copy(handles)
+        _check(_lib.pqv_peer_exchange_open(self._h, buf))
+
     def ivf_from_bytes(self, blob: bytes) -> "IvfIndex":
         buf = (C.c_uint8 * max(len(blob), 1)).from_buffer_copy(blob if blob else b"\0")
         h = C.c_uint64()
@@ -267,6 +278,18 @@ class Dataset:
                 continue
             _check(rc)
             return keys[:cnt.value]
+
+    def l2_topk_candidates_p2p(self, query, k: int, flags: int = N.PQV_SQRT, pos_base: int = 0, cap_total: int = 1 << 16):
+        """Scan this rank's slice and exchange the candidates with the peers over NVLink (pqv_l2_topk_candidates_p2p):
+        returns the union of all ranks' candidate keys, or None when a rank overflowed its slot (all ranks see that)."""
+        q = _f32(query)
+        if q.size != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.size}")
+        keys = np.empty(cap_total, dtype=np.uint64)
+        cnt, ovf = C.c_uint64(), C.c_uint32()
+        _check(_lib.pqv_l2_topk_candidates_p2p(self.ctx._h, self.handle, _ptr(q, C.c_float), k, flags, pos_base,
+                                               _ptr(keys, C.c_uint64), cap_total, C.byref(cnt), C.byref(ovf)))
+        return None if ovf.value else keys[:cnt.value]
 
     def l2_topk_batch_keys(self, queries, k: int, flags: int = N.PQV_SQRT, pos_base: int = 0):
         """Per-rank half of a sharded batched search: (keys [nq, k+1] u64, counts [nq] u32), see pqv.h."""

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "pqv_kernels.cuh"
+#include "pqv_peer.cuh"
 
 using pqv::u64;
 
@@ -382,6 +383,19 @@ struct StreamState {
     bool any = false;
 };
 
+// NVLink peer-memory candidate exchange (pqv_peer.cuh)
+struct PeerExchange {
+    bool ready = false;
+    uint32_t world = 0, rank = 0, cap = 0;
+    u64 seq = 0;
+    u64 *local = nullptr;      // this rank's buffer (cudaMalloc, exported through CUDA IPC)
+    std::vector<u64 *> peers;  // peers[d]: rank d's buffer mapped into this process (peers[rank] == local)
+    u64 **d_peers = nullptr;   // device copy of `peers`
+    uint32_t *d_timeout = nullptr;
+    PinBuf<u64> h_block;       // world x (1 + cap) words + 1 (timeout flag)
+    size_t words() const { return 2ull * world * (1ull + cap) + 2ull * world; }
+};
+
 }  // namespace
 
 struct pqv_ctx {
@@ -405,6 +419,7 @@ struct pqv_ctx {
     } batch_state;
     int occ_override = 0;
     int scan_variant = 0;
+    PeerExchange peer;
 };
 
 namespace {
@@ -847,8 +862,23 @@ int pqv_init(pqv_ctx **out, const int *device_ids, int n_devices) {
     return PQV_OK;
 }
 
+static void peer_release(pqv_ctx *ctx) {
+    PeerExchange &px = ctx->peer;
+    if (!px.local && px.peers.empty()) return;
+    DevGuard guard(ctx->devs[0].dev);
+    cudaStreamSynchronize(ctx->devs[0].stream);
+    for (uint32_t d = 0; d < px.peers.size(); ++d)
+        if (px.peers[d] && px.peers[d] != px.local) cudaIpcCloseMemHandle(px.peers[d]);
+    if (px.local) cudaFree(px.local);
+    if (px.d_peers) cudaFree(px.d_peers);
+    if (px.d_timeout) cudaFree(px.d_timeout);
+    px.h_block.release();
+    px = PeerExchange{};
+}
+
 void pqv_destroy(pqv_ctx *ctx) {
     if (!ctx) return;
+    peer_release(ctx);
     for (auto &kv : ctx->streams) {
         StreamState *s = kv.second;
         DevGuard guard(ctx->devs[0].dev);
@@ -874,6 +904,12 @@ void pqv_destroy(pqv_ctx *ctx) {
     for (auto &D : ctx->devs) {
         DevGuard guard(D.dev);
         cudaStreamSynchronize(D.stream);
+        D.ent_rows.release();
+        D.ivf_info.release();
+        D.csr_counts.release();
+        D.csr_totals.release();
+        D.h_ent_rows.release();
+        D.h_ivf_info.release();
         D.d_query.release();
         D.cta_topk.release();
         D.ent.release();
@@ -1275,6 +1311,132 @@ int pqv_merge_batch_keys(const uint64_t *keys, const uint32_t *counts, uint32_t 
         }
         if (tie) out_needs_replay[q] = 1;
         else out_count[q] = (uint32_t)cnt;
+    }
+    return PQV_OK;
+}
+
+int pqv_peer_exchange_create(pqv_ctx *ctx, uint32_t world, uint32_t rank, uint32_t cap_keys, uint8_t *out_handle64) {
+    if (!ctx || !out_handle64) return fail(PQV_EINVAL, "null argument");
+    if (world == 0 || rank >= world || cap_keys == 0) return fail(PQV_EINVAL, "bad world / rank / capacity");
+    if (ctx->devs.size() != 1) return fail(PQV_EINVAL, "the peer exchange is for one process per GPU (single-device context)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    peer_release(ctx);
+    DeviceState &D = ctx->devs[0];
+    DevGuard guard(D.dev);
+    PeerExchange &px = ctx->peer;
+    px.world = world;
+    px.rank = rank;
+    px.cap = cap_keys;
+    px.seq = 0;
+    cudaError_t e = cudaMalloc((void **)&px.local, px.words() * 8);
+    if (e != cudaSuccess) return fail(PQV_ENOMEM, "peer exchange buffer: %s", cudaGetErrorString(e));
+    CU_TRY(cudaMemset(px.local, 0, px.words() * 8));  // flags 0: sequence numbers start at 1
+    CU_TRY(cudaMalloc((void **)&px.d_peers, (size_t)world * sizeof(u64 *)));
+    CU_TRY(cudaMalloc((void **)&px.d_timeout, 4));
+    PQV_TRY(px.h_block.ensure((size_t)world * (1 + (size_t)cap_keys) + 1));
+    cudaIpcMemHandle_t h;
+    CU_TRY(cudaIpcGetMemHandle(&h, px.local));
+    memcpy(out_handle64, &h, 64);
+    return PQV_OK;
+}
+
+int pqv_peer_exchange_open(pqv_ctx *ctx, const uint8_t *handles) {
+    if (!ctx || !handles) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PeerExchange &px = ctx->peer;
+    if (!px.local) return fail(PQV_EINVAL, "pqv_peer_exchange_create has not been called");
+    DeviceState &D = ctx->devs[0];
+    DevGuard guard(D.dev);
+    px.peers.assign(px.world, nullptr);
+    for (uint32_t d = 0; d < px.world; ++d) {
+        if (d == px.rank) {
+            px.peers[d] = px.local;
+            continue;
+        }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, handles + (size_t)d * 64, 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(PQV_ECUDA, "cudaIpcOpenMemHandle(rank %u): %s", d, cudaGetErrorString(e));
+        px.peers[d] = static_cast<u64 *>(p);
+    }
+    CU_TRY(cudaMemcpy(px.d_peers, px.peers.data(), (size_t)px.world * sizeof(u64 *), cudaMemcpyHostToDevice));
+    px.ready = true;
+    return PQV_OK;
+}
+
+int pqv_l2_topk_candidates_p2p(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t pos_base,
+                               uint64_t *out_keys, uint64_t cap_total, uint64_t *out_count, uint32_t *out_overflow) {
+    if (!ctx || !query || !out_keys || !out_count || !out_overflow) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PeerExchange &px = ctx->peer;
+    if (!px.ready) return fail(PQV_EINVAL, "the peer exchange is not set up (pqv_peer_exchange_create / _open)");
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (flags & PQV_TIES_BY_POSITION) return fail(PQV_EINVAL, "candidates are only defined for the reference tie order");
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "single-device dataset expected");
+    if ((u64)pos_base + ds->n_rows > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "global row ids are u32");
+    Shard &sh = ds->shards[0];
+    DeviceState &D = ctx->devs[sh.di];
+    DevGuard guard(D.dev);
+    const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
+    const u64 seq = ++px.seq;  // every rank calls this the same number of times: the sequence numbers agree
+    PQV_TRY(D.d_query.ensure(ds->dim));
+    PQV_TRY(D.h_query.ensure(ds->dim));
+    PQV_TRY(D.final_topk.ensure(PQV_MAX_K));
+    PQV_TRY(D.ent_out.ensure((size_t)(1u << 16) + 1));
+    const uint32_t cap_local = (uint32_t)std::min<size_t>(D.ent_out.cap - 1, 0xFFFFFFF0u);
+    memcpy(D.h_query.p, query, (size_t)ds->dim * 4);
+    CU_TRY(cudaMemcpyAsync(D.d_query.p, D.h_query.p, (size_t)ds->dim * 4, cudaMemcpyHostToDevice, D.stream));
+    CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
+    CU_TRY(cudaMemsetAsync(px.d_timeout, 0, 4, D.stream));
+    ScanGeom g;
+    if (ds->n_rows) {
+        PQV_TRY(enqueue_scan(ctx, D, sh.d_data, nullptr, ds->n_rows, ds->dim, D.d_query.p, k, order, pos_base, nullptr,
+                             D.final_topk.p, D.ent_out.p, cap_local, true, &g));
+    } else {
+        CU_TRY(cudaEventRecord(D.ev[0], D.stream));
+        CU_TRY(cudaEventRecord(D.ev[1], D.stream));
+        CU_TRY(cudaEventRecord(D.ev[2], D.stream));
+        g.grid = 0;
+    }
+    pqv::peer_publish_kernel<<<px.world, 256, 0, D.stream>>>(D.ent_out.p, px.cap, px.d_peers, px.rank, px.world, seq);
+    pqv::peer_wait_kernel<<<1, 32, 0, D.stream>>>(px.local, px.cap, px.world, seq, px.d_timeout);
+    CU_TRY(cudaGetLastError());
+    const size_t block_words = (size_t)px.world * (1 + (size_t)px.cap);
+    CU_TRY(cudaMemcpyAsync(px.h_block.p, px.local + (seq & 1ull) * block_words, block_words * 8, cudaMemcpyDeviceToHost, D.stream));
+    CU_TRY(cudaMemcpyAsync(px.h_block.p + block_words, px.d_timeout, 4, cudaMemcpyDeviceToHost, D.stream));
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    if ((uint32_t)px.h_block.p[block_words] != 0) return fail(PQV_ECUDA, "peer exchange timed out waiting for the other ranks (sequence %llu)", (unsigned long long)seq);
+    u64 total = 0;
+    *out_overflow = 0;
+    for (uint32_t r = 0; r < px.world; ++r) {
+        const u64 c = px.h_block.p[(size_t)r * (1 + px.cap)];
+        if (c > px.cap) *out_overflow = 1;  // some rank had more candidates than a slot holds: every rank sees it
+        total += std::min<u64>(c, px.cap);
+    }
+    *out_count = total;
+    pqv_timing tm{};
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, D.ev[0], D.ev[1]);
+    cudaEventElapsedTime(&b, D.ev[1], D.ev[2]);
+    tm.scan_ms = a;
+    tm.post_ms = b;
+    tm.total_ms = a + b;
+    tm.scan_bytes = ds->n_rows * (u64)ds->dim * 4;
+    tm.launches = 6;
+    tm.grid = g.grid;
+    tm.entrants = (uint32_t)total;
+    ctx->last = tm;
+    if (*out_overflow) return PQV_OK;
+    if (total > cap_total) return fail(PQV_ELIMIT, "%llu candidate keys do not fit the caller's buffer of %llu", (unsigned long long)total, (unsigned long long)cap_total);
+    u64 o = 0;
+    for (uint32_t r = 0; r < px.world; ++r) {
+        const u64 *slot = px.h_block.p + (size_t)r * (1 + px.cap);
+        memcpy(out_keys + o, slot + 1, slot[0] * 8);
+        o += slot[0];
     }
     return PQV_OK;
 }

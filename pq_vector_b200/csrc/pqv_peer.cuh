@@ -1,0 +1,57 @@
+// pqv_peer.cuh -- the candidate exchange of a sharded search over NVLink peer memory (included by pqv_capi.cu).
+//
+// One process per GPU, every rank scans its own rows.  The only exchange of the path is the per-rank
+// heap-entrant candidate list (a few KB).  With NCCL that costs a host round trip on each side of the collective plus its
+// launch; here the ranks map one another's exchange buffer once (CUDA IPC) and the scan's tail kernel WRITES the rank's
+// candidates straight into every peer's buffer over NVLink, publishes a sequence flag, and waits for the peers' flags:
+//
+//   l2_scan_topk_kernel -> merge -> entrant_filter_kernel -> peer_publish_kernel -> peer_wait_kernel -> one D2H
+//
+// Buffer of a rank (device memory, local):   2 parities x [ world slots x (1 + cap) u64 ]  +  2 x world u64 flags.
+// Slot r of parity p holds rank r's (count, keys) of the search with sequence number s, s % 2 == p; flag[p][r] == s once
+// the slot is complete.  A rank can be at most one search ahead of its peers (its search s + 1 only finishes when every
+// peer has published s + 1, i.e. has finished reading s), so two parities are enough.
+#pragma once
+
+namespace pqv {
+
+// CTA d copies this rank's candidate block (count + min(count, cap) keys) into slot `rank` of peer d's buffer, makes it
+// visible system-wide and then releases the flag.
+__global__ void __launch_bounds__(256) peer_publish_kernel(const u64 *__restrict__ ent_out, const uint32_t cap,
+                                                           u64 *const *__restrict__ peer_base, const uint32_t rank,
+                                                           const uint32_t world, const u64 seq) {
+    const uint32_t d = blockIdx.x;
+    const u64 par = seq & 1ull;
+    const u64 slot_words = 1ull + cap;
+    u64 *slot = peer_base[d] + (par * world + rank) * slot_words;
+    u64 *flag = peer_base[d] + 2ull * world * slot_words + par * world + rank;
+    const u64 count = ent_out[0];
+    const u64 n = count < (u64)cap ? count : (u64)cap;
+    for (u64 i = threadIdx.x; i < n; i += blockDim.x) slot[1 + i] = ent_out[1 + i];
+    if (threadIdx.x == 0) slot[0] = count;
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+    }
+}
+
+// waits until every rank's flag of this parity carries `seq` (bounded: a lost peer must surface as an error, not a hang)
+__global__ void __launch_bounds__(32) peer_wait_kernel(const u64 *__restrict__ local_base, const uint32_t cap,
+                                                       const uint32_t world, const u64 seq, uint32_t *__restrict__ timed_out) {
+    const u64 par = seq & 1ull;
+    const u64 *flags = local_base + 2ull * world * (1ull + cap) + par * world;
+    for (uint32_t r = threadIdx.x; r < world; r += 32) {
+        u64 v = 0;
+        uint64_t spins = 0;
+        do {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+            if (v == seq) break;
+            __nanosleep(200);
+        } while (++spins < (1ull << 24));  // ~ several seconds
+        if (v != seq) atomicOr(timed_out, 1u);
+    }
+}
+
+}  // namespace pqv
+

@@ -30,6 +30,25 @@ class ShardedTopk:
         self._send = torch.zeros(cap + 1, dtype=torch.int64, device=self.device)
         self._recv = torch.zeros(self.world * (cap + 1), dtype=torch.int64, device=self.device)
         self.last_gather_bytes = 0
+        self._p2p = None
+
+    def enable_p2p(self, ctx, dataset):
+        """Switch the per-query exchange from the NCCL all-gather to NVLink peer writes (pqv_peer.cuh): the ranks swap
+        the CUDA IPC handles of their exchange buffers once (one all-gather of 64 bytes per rank); from then on a search
+        is scan -> filter -> publish into every peer's buffer -> wait for the peers' flags, with no collective call."""
+        rank = dist.get_rank(self.group) if dist.is_initialized() else 0
+        mine = ctx.peer_exchange_create(self.world, rank, self.cap)
+        send = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+        if self.world > 1:
+            recv = torch.empty(self.world * 64, dtype=torch.uint8, device=self.device)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+            handles = bytes(recv.cpu().numpy().tobytes())
+        else:
+            handles = mine
+        ctx.peer_exchange_open(handles)
+        if self.world > 1:
+            dist.barrier(group=self.group)   # nobody publishes before every rank has mapped every buffer
+        self._p2p = dataset
 
     def _exchange(self, keys: np.ndarray, cap: int) -> "tuple[np.ndarray, bool]":
         if cap != self._send.numel() - 1:
@@ -54,6 +73,12 @@ class ShardedTopk:
         return union, True
 
     def search(self, query, k: int, flags: int):
+        if self._p2p is not None:
+            union = self._p2p.l2_topk_candidates_p2p(query, k, flags, self.pos_base)
+            self.last_gather_bytes = 0
+            if union is not None:
+                return replay_candidates(union, k, flags)
+            # a rank had more candidates than a slot holds -- every rank saw it: all take the collective path below
         keys = np.ascontiguousarray(self.scan_fn(query, k, flags, self.pos_base), dtype=np.uint64)
         if self.world == 1:  # nothing to exchange
             self.last_gather_bytes = 0
