@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(32) peer_wait_kernel(const u64 *__restrict__ l
             asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
             if (v == seq) break;
             __nanosleep(200);
-        } while (++spins < (1ull << 24));  // ~ several seconds
+        } while (++spins < (1ull << 27));  // ~ half a minute: ranks may be skewed by first-call allocations
         if (v != seq) atomicOr(timed_out, 1u);
     }
 }
