@@ -331,3 +331,35 @@ def test_c2_scale_properties(ctx):
     dd = O.distances(O.synth(1000, dim, seed, first_row=blk0), q, 0)
     assert int(np.argmin(dd)) + blk0 == int(r[0])
     ds.drop()
+
+
+def test_peer_exchange_world_of_one(ctx, P):
+    """pqv_peer_exchange_* + pqv_l2_topk_candidates_p2p with a single rank (the buffer is its own peer): publish / flag /
+    wait kernels, sequence parity over several searches, and the slot-overflow signal.  The multi-rank exchange is
+    checked by benchmarks/check_p2p_exchange.py under torchrun."""
+    from pq_vector_b200.sharded import ShardedTopk
+    rng = np.random.default_rng(21)
+    n, dim, k = 50000, 96, 20
+    data = rng.random((n, dim), dtype=np.float32)
+    ds = ctx.dataset_from(data)
+    st = ShardedTopk(lambda q, k_, f_, pb: ds.l2_topk_candidates(q, k_, f_, pb), 0, "cpu", cap=2048)
+    st.enable_p2p(ctx, ds)
+    for i in range(5):                                   # both buffer parities, several sequence numbers
+        q = rng.random(dim, dtype=np.float32)
+        r, d = st.search(q, k, SQRT)
+        er, ed = O.topk_rerank(q, data, None, k, 0, True)
+        assert r.tolist() == er.tolist() and bits(d).tolist() == bits(ed).tolist()
+    keys = ds.l2_topk_candidates_p2p(data[3], k, SQRT, 1000)
+    assert keys is not None and ((keys & np.uint64(0xFFFFFFFF)) >= 1000).all()      # pos_base applied
+    # descending distances: every row enters the heap -> far more candidates than the slot holds -> overflow signal,
+    # and ShardedTopk falls back to the collective path with the right answer
+    desc = np.zeros((4000, 4), np.float32)
+    desc[:, 0] = np.arange(4000, 0, -1)
+    ds2 = ctx.dataset_from(desc)
+    st2 = ShardedTopk(lambda q, k_, f_, pb: ds2.l2_topk_candidates(q, k_, f_, pb), 0, "cpu", cap=64)
+    st2.enable_p2p(ctx, ds2)
+    assert ds2.l2_topk_candidates_p2p(np.zeros(4, np.float32), 5, SQRT) is None
+    r, d = st2.search(np.zeros(4, np.float32), 5, SQRT)
+    er, ed = O.topk_rerank(np.zeros(4, np.float32), desc, None, 5, 0, True)
+    assert r.tolist() == er.tolist() and bits(d).tolist() == bits(ed).tolist()
+    ds.drop(); ds2.drop()
