@@ -271,6 +271,40 @@ PQV_API int pqv_bench_assign(pqv_ctx *ctx, uint64_t handle, uint64_t n, const fl
 PQV_API int pqv_bench_scan(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags,
                    uint32_t iters, double *out_ms_per_scan);
 
+/* ---- coalescing front door for concurrent single-query callers ---------------------------------
+ * The reference API is single-query (src/ivf/search.rs:49-54 `query: &[f32]`, src/df_vector/exec.rs:43) and its callers
+ * are concurrent tasks (TopkBuilder::search is async; VectorTopKExec::execute is a stream::once per plan,
+ * src/df_vector/exec.rs:387).  pqv_l2_topk_coalesced has the single-query contract of pqv_l2_topk (n_queries = 1) and may
+ * be called from any number of threads: the first caller runs; calls arriving while a pass over the table is in flight
+ * queue up and are answered together by ONE batched pass (pqv_l2_topk with n_queries = batch) as
+ * soon as the running one finishes.  Every caller still receives exactly the output of its own single-query call.
+ * Requests with a different (dataset, k, flags) are not mixed into one batch.  The calling thread blocks (wrap in
+ * spawn_blocking on the Rust side).  pqv_coalesce_config: max_batch (default 1024) bounds a batch; window_us > 0 lets
+ * the leading caller linger that long for a burst to assemble (default 0: batches form only behind a running pass). */
+PQV_API int pqv_l2_topk_coalesced(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags,
+                          uint32_t *out_row_idx, float *out_dist, uint32_t *out_count);
+PQV_API int pqv_coalesce_config(pqv_ctx *ctx, uint32_t max_batch, uint32_t window_us);
+PQV_API int pqv_coalesce_stats(pqv_ctx *ctx, uint64_t *out_queries, uint64_t *out_batches, uint64_t *out_max_batch);
+
+/* ---- the un-indexed `array_distance` arm ---------------------------------------------------------
+ * `ORDER BY array_distance(col, [..]) LIMIT k` over a file WITHOUT an embedded index is left alone by pq-vector's
+ * optimizer rule (src/df_vector/physical.rs:198-214), so DataFusion's built-in UDF runs per row under SortExec(TopK)
+ * (datafusion-functions-nested 52.1.0, Cargo.lock:1041-1042 -- not vendored in the reference; call sites
+ * benches/query.rs:79-81, examples/datafusion_sql.rs:54-55, src/df_vector/tests.rs:77-80).  Upstream semantics as
+ * published: both lists cast to Float64, sum of (a - b)^2 folded in element order in f64, sqrt; a length mismatch is an
+ * error.  PARITY UNPINNED: the reference's tests never reach the UDF.
+ *   pqv_array_distance       the UDF itself: out[i] = distance(row i, query) as Float64, one value per resident row.
+ *   pqv_array_distance_topk  UDF + SortExec(TopK): the k smallest by f64 total order (NaN last); ties by ascending row
+ *                            (the stock operator leaves that order unspecified).  out_count = min(k, rows).
+ * metric: PQV_METRIC_L2 = Euclidean (above).  PQV_METRIC_COSINE = 1 - a.b / (sqrt(a.a) sqrt(b.b)), the three sums
+ * folded in element order in f64 -- additive: the reference has no cosine distance. */
+#define PQV_METRIC_L2      0u
+#define PQV_METRIC_COSINE  1u
+PQV_API int pqv_array_distance(pqv_ctx *ctx, uint64_t handle, const double *query, uint32_t query_len, uint32_t metric,
+                       double *out /* n_rows */);
+PQV_API int pqv_array_distance_topk(pqv_ctx *ctx, uint64_t handle, const double *query, uint32_t query_len, uint32_t metric,
+                            uint32_t k, uint32_t *out_row_idx, double *out_dist, uint32_t *out_count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -58,6 +58,10 @@ def lib():
             "pqo_index_to_bytes": (C.c_uint64, [C.c_uint32, C.c_uint32, f32p, u64p, u32p, u8p]),
             "pqo_index_from_bytes": (C.c_int, [u8p, C.c_uint64, u32p, u32p, u64p, f32p, u64p, u32p]),
             "pqo_synth_fill": (None, [f32p, C.c_uint64, C.c_uint64, C.c_uint64]),
+            "pqo_array_distance": (C.c_double, [f32p, f64p, C.c_size_t]),
+            "pqo_cosine_distance": (C.c_double, [f32p, f64p, C.c_size_t]),
+            "pqo_array_distance_column": (None, [f32p, C.c_uint64, C.c_uint32, f64p, C.c_int, f64p]),
+            "pqo_array_distance_topk": (C.c_size_t, [f32p, C.c_uint64, C.c_uint32, f64p, C.c_int, C.c_size_t, u32p, f64p]),
             "pqo_scan_topk_mt": (C.c_size_t, [f32p, C.c_uint64, C.c_uint32, f32p, C.c_size_t, C.c_int, C.c_int,
                                               u32p, f32p]),
         }
@@ -288,3 +292,23 @@ def synth(n_rows, dim, seed, first_row=0) -> np.ndarray:
     out = np.empty((n_rows, dim), dtype=np.float32)
     lib().pqo_synth_fill(_p(out, C.c_float), first_row * dim, n_rows * dim, seed)
     return out
+
+
+# ---- the un-indexed array_distance arm (DataFusion built-in; PARITY UNPINNED, see pqv_oracle.c) -------------------
+def array_distance_column(rows, query, metric=0) -> np.ndarray:
+    rows = _f32(rows)
+    q = np.ascontiguousarray(query, dtype=np.float64)
+    out = np.empty(rows.shape[0], dtype=np.float64)
+    lib().pqo_array_distance_column(_p(rows, C.c_float), rows.shape[0], rows.shape[1], _p(q, C.c_double), int(metric),
+                                    _p(out, C.c_double))
+    return out
+
+
+def array_distance_topk(rows, query, k, metric=0):
+    rows = _f32(rows)
+    q = np.ascontiguousarray(query, dtype=np.float64)
+    out_r = np.empty(max(k, 1), dtype=np.uint32)
+    out_d = np.empty(max(k, 1), dtype=np.float64)
+    m = lib().pqo_array_distance_topk(_p(rows, C.c_float), rows.shape[0], rows.shape[1], _p(q, C.c_double), int(metric), k,
+                                      _p(out_r, C.c_uint32), _p(out_d, C.c_double))
+    return out_r[:m].copy(), out_d[:m].copy()

@@ -615,4 +615,81 @@ PQO_API size_t pqo_scan_topk_mt(const float *rows, uint64_t n_rows, uint32_t dim
     return n;
 }
 
+/* ------------------------------------------------------------------------------------------ */
+/* the un-indexed `array_distance` arm -- PARITY UNPINNED           */
+/* ------------------------------------------------------------------------------------------ */
+/* DataFusion's built-in UDF (crate datafusion-functions-nested 52.1.0, Cargo.lock:1041-1042; the source is NOT under
+ * /root/reference).  Call sites in the reference: benches/query.rs:79-81, examples/datafusion_sql.rs:54-55,
+ * src/df_vector/tests.rs:77-80 (there the optimizer rule plans it away).  Restated from the published upstream
+ * algorithm (distance.rs, compute_array_distance): both lists are cast to Float64, then
+ *     sum_squares = zip(a, b).map(|(x, y)| { let d = x - y; d * d }).sum::<f64>();   result = sum_squares.sqrt()
+ * i.e. a sequential f64 fold in element order.  No golden vector of the reference reaches this function (all three SQL
+ * tests run with the optimizer rule), so parity of this arm is UNPINNED; tests check it against an independent numpy
+ * float64 cumulative sum. */
+PQO_API double pqo_array_distance(const float *row, const double *query, size_t len) {
+    double sum = 0.0;
+    for (size_t i = 0; i < len; ++i) {
+        double d = (double)row[i] - query[i];
+        sum += d * d;
+    }
+    return sqrt(sum);
+}
+
+/* Cosine distance: additive (the reference has none).  1 - a.b / (sqrt(a.a) * sqrt(b.b)), sequential f64. */
+PQO_API double pqo_cosine_distance(const float *row, const double *query, size_t len) {
+    double dot = 0.0, na = 0.0, nb = 0.0;
+    for (size_t i = 0; i < len; ++i) {
+        double x = (double)row[i];
+        dot += x * query[i];
+        na += x * x;
+    }
+    for (size_t i = 0; i < len; ++i) nb += query[i] * query[i];
+    return 1.0 - dot / (sqrt(na) * sqrt(nb));
+}
+
+PQO_API void pqo_array_distance_column(const float *rows, uint64_t n, uint32_t dim, const double *query, int metric,
+                                       double *out) {
+    for (uint64_t i = 0; i < n; ++i)
+        out[i] = metric ? pqo_cosine_distance(rows + i * (uint64_t)dim, query, dim)
+                        : pqo_array_distance(rows + i * (uint64_t)dim, query, dim);
+}
+
+/* f64 total order with every NaN last (how DataFusion's sort treats NaN for ASC), as an unsigned key */
+static inline uint64_t f64_ordered_bits(double d) {
+    uint64_t b;
+    memcpy(&b, &d, 8);
+    if ((b & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) b = 0x7FF8000000000000ull;
+    return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
+}
+typedef struct {
+    uint64_t key;
+    uint32_t row;
+} adist_item;
+static int adist_cmp(const void *a, const void *b) {
+    const adist_item *x = (const adist_item *)a, *y = (const adist_item *)b;
+    if (x->key != y->key) return x->key < y->key ? -1 : 1;
+    return x->row < y->row ? -1 : (x->row > y->row ? 1 : 0);
+}
+/* UDF + SortExec(TopK): k smallest by (f64 total order, row).  The stock TopK leaves the order among equal keys
+ * unspecified; ascending row is this build's convention. */
+PQO_API size_t pqo_array_distance_topk(const float *rows, uint64_t n, uint32_t dim, const double *query, int metric,
+                                       size_t k, uint32_t *out_rows, double *out_dist) {
+    double *col = (double *)malloc(sizeof(double) * (size_t)(n + 1));
+    adist_item *it = (adist_item *)malloc(sizeof(adist_item) * (size_t)(n + 1));
+    pqo_array_distance_column(rows, n, dim, query, metric, col);
+    for (uint64_t i = 0; i < n; ++i) {
+        it[i].key = f64_ordered_bits(col[i]);
+        it[i].row = (uint32_t)i;
+    }
+    qsort(it, (size_t)n, sizeof(adist_item), adist_cmp);
+    size_t m = k < n ? k : (size_t)n;
+    for (size_t i = 0; i < m; ++i) {
+        out_rows[i] = it[i].row;
+        out_dist[i] = col[it[i].row];
+    }
+    free(col);
+    free(it);
+    return m;
+}
+
 PQO_API const char *pqo_build_flags(void) { return "gcc -O3 -ffp-contract=off -fno-fast-math"; }

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libpqv.so")
 PQV_OK, PQV_EINVAL, PQV_ENODEV, PQV_ECUDA, PQV_ENOMEM, PQV_EHANDLE, PQV_ELIMIT = range(7)
 PQV_SUM_UNROLL4, PQV_SUM_SEQ, PQV_SQRT, PQV_TIES_BY_POSITION = 0, 1, 2, 4
 PQV_MAX_K, PQV_MAX_DIM = 1024, 16384
+PQV_METRIC_L2, PQV_METRIC_COSINE = 0, 1
 
 
 class PqvTiming(C.Structure):
@@ -90,6 +91,11 @@ SIGNATURES = {
     "pqv_bench_assign": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32,
                                    C.POINTER(PqvAssignTiming), u32p]),
     "pqv_bench_scan": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, f64p]),
+    "pqv_l2_topk_coalesced": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),
+    "pqv_coalesce_config": (C.c_int, [ctxp, C.c_uint32, C.c_uint32]),
+    "pqv_coalesce_stats": (C.c_int, [ctxp, u64p, u64p, u64p]),
+    "pqv_array_distance": (C.c_int, [ctxp, C.c_uint64, f64p, C.c_uint32, C.c_uint32, f64p]),
+    "pqv_array_distance_topk": (C.c_int, [ctxp, C.c_uint64, f64p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f64p, u32p]),
 }
 
 

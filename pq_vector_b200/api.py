@@ -162,6 +162,14 @@ class Context:
     def topk_stream(self, query, k, flags=N.PQV_SUM_SEQ) -> "TopkStream":
         return TopkStream(self, query, k, flags)
 
+    def coalesce_config(self, max_batch: int = 1024, window_us: int = 0):
+        _check(_lib.pqv_coalesce_config(self._h, max_batch, window_us))
+
+    def coalesce_stats(self) -> dict:
+        q, b, m = C.c_uint64(), C.c_uint64(), C.c_uint64()
+        _check(_lib.pqv_coalesce_stats(self._h, C.byref(q), C.byref(b), C.byref(m)))
+        return {"queries": q.value, "batches": b.value, "max_batch": m.value}
+
     def last_batch_timing(self) -> dict:
         """What the batched pass of the last l2_topk_batch / pqv_l2_topk call did (queries == 0: not used)."""
         t = N.PqvBatchTiming()
@@ -249,6 +257,38 @@ class Dataset:
         if single:
             return rows[0, :cnt[0]].copy(), dist[0, :cnt[0]].copy()
         return rows, dist, cnt
+
+    def l2_topk_coalesced(self, query, k: int, flags: int = N.PQV_SQRT):
+        """Single-query top-k through the coalescing front door (pqv_l2_topk_coalesced): safe to call from many threads
+        (ctypes drops the GIL); calls that arrive while a pass is running are answered by one batched pass."""
+        q = _f32(query)
+        if q.ndim != 1 or q.size != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.size}")
+        kk = max(k, 1)
+        rows = np.zeros(kk, dtype=np.uint32)
+        dist = np.zeros(kk, dtype=np.float32)
+        cnt = C.c_uint32()
+        _check(_lib.pqv_l2_topk_coalesced(self.ctx._h, self.handle, _ptr(q, C.c_float), k, flags, _ptr(rows, C.c_uint32),
+                                          _ptr(dist, C.c_float), C.byref(cnt)))
+        return rows[:cnt.value].copy(), dist[:cnt.value].copy()
+
+    def array_distance(self, query, metric: int = N.PQV_METRIC_L2) -> np.ndarray:
+        """The DataFusion built-in `array_distance(column, literal)` as a Float64 column (pqv_array_distance)."""
+        q = np.ascontiguousarray(query, dtype=np.float64).ravel()
+        out = np.empty(self.rows(), dtype=np.float64)
+        _check(_lib.pqv_array_distance(self.ctx._h, self.handle, _ptr(q, C.c_double), q.size, metric, _ptr(out, C.c_double)))
+        return out
+
+    def array_distance_topk(self, query, k: int, metric: int = N.PQV_METRIC_L2):
+        """`ORDER BY array_distance(column, literal) LIMIT k` without an index: (row_idx u32, distance f64), ascending."""
+        q = np.ascontiguousarray(query, dtype=np.float64).ravel()
+        kk = max(k, 1)
+        rows = np.zeros(kk, dtype=np.uint32)
+        dist = np.zeros(kk, dtype=np.float64)
+        cnt = C.c_uint32()
+        _check(_lib.pqv_array_distance_topk(self.ctx._h, self.handle, _ptr(q, C.c_double), q.size, metric, k,
+                                            _ptr(rows, C.c_uint32), _ptr(dist, C.c_double), C.byref(cnt)))
+        return rows[:cnt.value].copy(), dist[:cnt.value].copy()
 
     def l2_topk_gather(self, query, row_ids, k: int, flags: int = N.PQV_SQRT):
         q = _f32(query)

@@ -11,7 +11,9 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <condition_variable>
 #include <cstring>
+#include <deque>
 #include <functional>
 #include <map>
 #include <mutex>
@@ -22,6 +24,7 @@
 
 #include "pqv_kernels.cuh"
 #include "pqv_peer.cuh"
+#include "pqv_adist.cuh"
 
 using pqv::u64;
 
@@ -344,6 +347,13 @@ struct DeviceState {
     DevBuf<u64> ivf_info;
     PinBuf<uint32_t> h_ent_rows;
     PinBuf<u64> h_ivf_info;
+    // un-indexed array_distance arm (pqv_adist.cuh): f64 query, f64 distance column, radix-select state, k winners
+    DevBuf<double> ad_query, ad_col, ad_out_dist;
+    DevBuf<uint32_t> ad_out_row;
+    DevBuf<pqv::SelState> ad_state;
+    PinBuf<double> h_ad_dist;
+    PinBuf<uint32_t> h_ad_row;
+    PinBuf<pqv::SelState> h_ad_state;
 };
 
 struct Shard {
@@ -420,6 +430,26 @@ struct pqv_ctx {
     int occ_override = 0;
     int scan_variant = 0;
     PeerExchange peer;
+    // coalescing front door for concurrent single-query callers (pqv_l2_topk_coalesced)
+    struct CoalesceReq {
+        u64 handle = 0;
+        uint32_t k = 0, flags = 0;
+        const float *query = nullptr;
+        uint32_t *rows = nullptr;
+        float *dist = nullptr;
+        uint32_t *count = nullptr;
+        int status = 0;
+        std::string err;
+        bool done = false, lead = false;
+    };
+    struct Coalescer {
+        std::mutex m;
+        std::condition_variable cv;
+        std::deque<CoalesceReq *> pending;
+        bool leader_active = false;
+        uint32_t max_batch = 1024, window_us = 0;
+        u64 n_queries = 0, n_batches = 0, max_seen = 0;
+    } co;
 };
 
 namespace {
@@ -910,6 +940,14 @@ void pqv_destroy(pqv_ctx *ctx) {
         D.csr_totals.release();
         D.h_ent_rows.release();
         D.h_ivf_info.release();
+        D.ad_query.release();
+        D.ad_col.release();
+        D.ad_out_dist.release();
+        D.ad_out_row.release();
+        D.ad_state.release();
+        D.h_ad_dist.release();
+        D.h_ad_row.release();
+        D.h_ad_state.release();
         D.d_query.release();
         D.cta_topk.release();
         D.ent.release();
@@ -1872,3 +1910,4 @@ int pqv_topk_stream_finish(pqv_ctx *ctx, uint64_t stream, uint32_t *out_row_idx,
 }  // extern "C"
 
 #include "pqv_ivf_impl.cuh"
+#include "pqv_adist_impl.cuh"

@@ -354,3 +354,38 @@ def _fill_kat():
 
 
 _fill_kat()
+
+
+# ---- the un-indexed array_distance arm (DataFusion built-in; parity unpinned) ---------------------
+def test_array_distance_published_examples_and_independent_fold():
+    # DataFusion's documented example: array_distance([1, 2], [1, 4]) = 2.0; the reference's own L2 KAT vectors give sqrt(27)
+    assert O.array_distance_column(np.array([[1, 2]], np.float32), [1.0, 4.0]).tolist() == [2.0]
+    assert O.array_distance_column(np.array([[1, 2, 3]], np.float32), [4.0, 5.0, 6.0]).tolist() == [np.sqrt(27.0)]
+    rng = np.random.default_rng(11)
+    for dim in (1, 7, 64, 769):
+        x = rng.random((40, dim), dtype=np.float32)
+        q = rng.random(dim)                                   # f64 literal, not f32-representable
+        t = (x.astype(np.float64) - q) ** 2
+        ref = np.sqrt(np.cumsum(t, axis=1)[:, -1])            # numpy cumsum = the same left-to-right f64 fold
+        assert O.array_distance_column(x, q).view(np.uint64).tolist() == ref.view(np.uint64).tolist()
+        xd = x.astype(np.float64)
+        dot = np.cumsum(xd * q, axis=1)[:, -1]
+        na = np.cumsum(xd * xd, axis=1)[:, -1]
+        nb = np.cumsum(q * q)[-1]
+        cos = 1.0 - dot / (np.sqrt(na) * np.sqrt(nb))
+        assert O.array_distance_column(x, q, 1).view(np.uint64).tolist() == cos.view(np.uint64).tolist()
+
+
+def test_array_distance_topk_order():
+    x = np.array([[0, 0], [1, 0], [0, 2], [5, 5], [2, 2], [0.1, 0.1]], np.float32)    # df_vector/tests.rs:31-39 rows
+    r, d = O.array_distance_topk(x, [0.0, 0.0], 3)
+    assert r.tolist() == [0, 5, 1] and d[0] == 0.0 and d[2] == 1.0
+    dup = np.concatenate([x, x])
+    r, _ = O.array_distance_topk(dup, [0.0, 0.0], 4)
+    assert r.tolist() == [0, 6, 5, 11]                                           # equal keys: ascending row
+    x2 = x.copy()
+    x2[0, 0] = np.inf
+    r, d = O.array_distance_topk(x2, [np.inf, 0.0], 6)
+    assert r.tolist()[-1] == 0 and np.isnan(d[-1]) and np.isinf(d[:-1]).all()    # NaN sorts last
+    r, _ = O.array_distance_topk(x, [0.0, 0.0], 100)
+    assert r.size == 6
