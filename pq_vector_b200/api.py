@@ -275,7 +275,7 @@ class Dataset:
     def array_distance(self, query, metric: int = N.PQV_METRIC_L2) -> np.ndarray:
         """The DataFusion built-in `array_distance(column, literal)` as a Float64 column (pqv_array_distance)."""
         q = np.ascontiguousarray(query, dtype=np.float64).ravel()
-        out = np.empty(self.rows(), dtype=np.float64)
+        out = np.empty(self.rows, dtype=np.float64)
         _check(_lib.pqv_array_distance(self.ctx._h, self.handle, _ptr(q, C.c_double), q.size, metric, _ptr(out, C.c_double)))
         return out
 

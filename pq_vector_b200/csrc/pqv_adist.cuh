@@ -31,9 +31,11 @@ namespace pqv {
 constexpr int ADIST_L2 = 0;      // sqrt(sum (x - q)^2)         (DataFusion array_distance)
 constexpr int ADIST_COSINE = 1;  // 1 - x.q / (|x| |q|)          (additive; no reference semantics)
 
-constexpr int ADIST_TSTRIDE = 66;  // doubles per tile row: 64 + 2; 528 B = 16 x 33 -> LDS.128 conflict-free
-constexpr int ADIST_WARPS = 4;
-constexpr int ADIST_TILE_BYTES = 32 * ADIST_TSTRIDE * 8;
+constexpr int ADIST_BLK = 64;      // columns per block: a warp reads 256 contiguous bytes of each row per request
+constexpr int ADIST_TSTRIDE = 68;  // floats per tile row: 64 + 4; 272 B = 16 x 17 -> LDS.128 by row is conflict-free
+constexpr int ADIST_WARPS = 8;
+constexpr int ADIST_TILE_BYTES = 32 * ADIST_TSTRIDE * 4;  // 8704 B per warp
+constexpr uint32_t ADIST_QSMEM_MAX_DIM = 4096;            // f64 query staged in shared memory up to here (32 KB)
 
 __device__ __forceinline__ float2 ld_stream_v2(const float *p) {
     float2 r;
@@ -41,92 +43,129 @@ __device__ __forceinline__ float2 ld_stream_v2(const float *p) {
     return r;
 }
 
-// MODE 0: L2, two columns per lane (dim even, 8-byte aligned rows)      tile pair = (t(col), t(col+1))
-// MODE 1: L2, one column per lane (any dim / alignment)                 tile pair = (t(col), unused)
-// MODE 2: cosine, one column per lane                                   tile pair = (x*q, x*x)
-template <int MODE, int RB>
+// One warp owns 32 consecutive rows.  Per 64-column block all lanes load the rows coalesced (16 rows x 2 halves kept in
+// registers), park the RAW f32 values in the warp's padded shared-memory tile, and lane r then walks row r: widen to
+// f64, subtract, square (independent, they run ahead) and the serial f64 add chain in element order.  The loads of the
+// NEXT block (or of the next group's first block) are issued before the chain starts, so every warp has 8 KB in flight
+// while it computes.  Earlier form (f64 terms transposed instead of raw f32): twice the tile, 178 registers, 8 warps
+// per SM -> 3.6 TB/s at best (profiles/r01_adist_*.md).
+//   VEC2  : dim even and 8-byte aligned rows -> 64-bit loads; otherwise two scalar loads per lane and row.
+//   QSMEM : f64 query staged in shared memory (dim <= ADIST_QSMEM_MAX_DIM); otherwise read through L1 (uniform address).
+template <int METRIC, bool VEC2, bool QSMEM>
 __global__ void __launch_bounds__(ADIST_WARPS * 32)
 array_distance_kernel(const float *__restrict__ data, const u64 n, const uint32_t dim, const double *__restrict__ query,
                       const double q_norm2, double *__restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr uint32_t CPL = (MODE == 0) ? 2u : 1u;  // columns per lane per block
-    constexpr uint32_t BLK = 32u * CPL;
-    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    double *tile = reinterpret_cast<double *>(smem_raw) + (size_t)warp * 32 * ADIST_TSTRIDE;
-    const double *trow = tile + lane * ADIST_TSTRIDE;
+    constexpr int HB = 16;  // rows per register half
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t dim_pad = (dim + ADIST_BLK - 1) & ~(uint32_t)(ADIST_BLK - 1);
+    double *s_q = reinterpret_cast<double *>(smem_raw);
+    float *tile = reinterpret_cast<float *>(smem_raw + (QSMEM ? (size_t)dim_pad * 8 : 0)) + (size_t)warp * 32 * ADIST_TSTRIDE;
+    const float *trow = tile + lane * ADIST_TSTRIDE;
+    if (QSMEM) {
+        for (uint32_t i = tid; i < dim_pad; i += ADIST_WARPS * 32) s_q[i] = i < dim ? query[i] : 0.0;
+        __syncthreads();
+    }
     const u64 NG = (n + 31) >> 5;
-    const uint32_t ncb = (dim + BLK - 1) / BLK;
+    const u64 gstride = (u64)gridDim.x * ADIST_WARPS;
+    const uint32_t ncb = dim_pad / ADIST_BLK;
+    u64 g = (u64)blockIdx.x * ADIST_WARPS + warp;
+    if (g >= NG) return;
 
-    for (u64 g = (u64)blockIdx.x * ADIST_WARPS + warp; g < NG; g += (u64)gridDim.x * ADIST_WARPS) {
-        const u64 g_first = g * 32;
-        double acc0 = 0.0, acc1 = 0.0;  // L2: acc0 = sum; cosine: acc0 = dot, acc1 = |x|^2
+    float2 va[HB], vb[HB];
+    auto issue_half = [&](const u64 gg, const uint32_t cb, const int r0, float2(&v)[HB]) {
+        // gg >= NG (nothing left for this warp): every load is predicated off
+        const uint32_t c0 = cb * ADIST_BLK + (VEC2 ? 2 * lane : lane);
+        const bool live = gg < NG;
+        const bool in0 = live && c0 < dim;
+        const bool in1 = live && (VEC2 ? in0 : c0 + 32 < dim);
+#pragma unroll
+        for (int j = 0; j < HB; ++j) {
+            u64 row = gg * 32 + (r0 + j);
+            row = row < n ? row : n - 1;
+            const float *rp = data + row * dim + c0;
+            v[j] = make_float2(0.f, 0.f);
+            if (VEC2) {
+                if (in0) v[j] = ld_stream_v2(rp);
+            } else {
+                if (in0) v[j].x = ld_stream_f32(rp);
+                if (in1) v[j].y = ld_stream_f32(rp + 32);
+            }
+        }
+    };
+    auto park_half = [&](const int r0, const float2(&v)[HB]) {
+#pragma unroll
+        for (int j = 0; j < HB; ++j) {
+            float *tr = tile + (r0 + j) * ADIST_TSTRIDE;
+            if (VEC2) {
+                *reinterpret_cast<float2 *>(tr + 2 * lane) = v[j];
+            } else {
+                tr[lane] = v[j].x;
+                tr[32 + lane] = v[j].y;
+            }
+        }
+    };
+    double acc0, acc1;  // L2: acc0 = sum; cosine: acc0 = dot, acc1 = |x|^2
+    auto step = [&](const float xf, const double q) {
+        const double x = (double)xf;
+        if (METRIC == ADIST_COSINE) {
+            acc0 = __dadd_rn(acc0, __dmul_rn(x, q));
+            acc1 = __dadd_rn(acc1, __dmul_rn(x, x));
+        } else {
+            const double d = __dsub_rn(x, q);
+            acc0 = __dadd_rn(acc0, __dmul_rn(d, d));
+        }
+    };
+
+    issue_half(g, 0, 0, va);
+    issue_half(g, 0, HB, vb);
+    for (;;) {
+        acc0 = 0.0;
+        acc1 = 0.0;
+#pragma unroll 1
         for (uint32_t cb = 0; cb < ncb; ++cb) {
-            const uint32_t col = cb * BLK + lane * CPL;
-            const bool inb = col < dim;
-            double q0 = 0.0, q1 = 0.0;
-            if (inb) {
-                q0 = __ldg(query + col);
-                if (MODE == 0) q1 = __ldg(query + col + 1);
-            }
-#pragma unroll
-            for (int r0 = 0; r0 < 32; r0 += RB) {
-                float2 v[RB];
-#pragma unroll
-                for (int j = 0; j < RB; ++j) {
-                    u64 row = g_first + (r0 + j);
-                    row = row < n ? row : n - 1;
-                    const float *rp = data + row * dim + col;
-                    v[j] = make_float2(0.f, 0.f);
-                    if (inb) {
-                        if (MODE == 0) v[j] = ld_stream_v2(rp);
-                        else v[j].x = ld_stream_f32(rp);
-                    }
-                }
-#pragma unroll
-                for (int j = 0; j < RB; ++j) {
-                    double2 t;
-                    if (MODE == 2) {
-                        const double x = (double)v[j].x;
-                        t.x = __dmul_rn(x, q0);
-                        t.y = __dmul_rn(x, x);
-                    } else {
-                        const double d0 = __dsub_rn((double)v[j].x, q0);
-                        t.x = __dmul_rn(d0, d0);
-                        const double d1 = __dsub_rn((double)v[j].y, q1);
-                        t.y = (MODE == 0) ? __dmul_rn(d1, d1) : 0.0;
-                    }
-                    *reinterpret_cast<double2 *>(tile + (r0 + j) * ADIST_TSTRIDE + 2 * lane) = t;
-                }
-            }
+            park_half(0, va);
+            park_half(HB, vb);
             __syncwarp();
-            // serial chain, lane = row; cnt = lanes of this block that hold real columns
-            const uint32_t left = dim - cb * BLK;
-            const uint32_t cnt = left >= BLK ? 32u : (left + CPL - 1) / CPL;
-            if (cnt == 32u) {
+            const bool last = cb + 1 == ncb;
+            const u64 ng = last ? g + gstride : g;
+            const uint32_t ncb_next = last ? 0u : cb + 1;
+            issue_half(ng, ncb_next, 0, va);
+            issue_half(ng, ncb_next, HB, vb);
+            // serial chain in element order, lane = row
+            const uint32_t c0 = cb * ADIST_BLK;
+            const uint32_t cnt = dim - c0 < (uint32_t)ADIST_BLK ? dim - c0 : (uint32_t)ADIST_BLK;
+            if (cnt == (uint32_t)ADIST_BLK) {
 #pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const double2 t = *reinterpret_cast<const double2 *>(trow + 2 * j);
-                    acc0 = __dadd_rn(acc0, t.x);
-                    if (MODE == 0) acc0 = __dadd_rn(acc0, t.y);
-                    if (MODE == 2) acc1 = __dadd_rn(acc1, t.y);
+                for (int jj = 0; jj < ADIST_BLK / 4; ++jj) {
+                    const float4 x = *reinterpret_cast<const float4 *>(trow + 4 * jj);
+                    double2 qa, qb;
+                    if (QSMEM) {
+                        qa = *reinterpret_cast<const double2 *>(s_q + c0 + 4 * jj);
+                        qb = *reinterpret_cast<const double2 *>(s_q + c0 + 4 * jj + 2);
+                    } else {
+                        qa = make_double2(__ldg(query + c0 + 4 * jj), __ldg(query + c0 + 4 * jj + 1));
+                        qb = make_double2(__ldg(query + c0 + 4 * jj + 2), __ldg(query + c0 + 4 * jj + 3));
+                    }
+                    step(x.x, qa.x);
+                    step(x.y, qa.y);
+                    step(x.z, qb.x);
+                    step(x.w, qb.y);
                 }
             } else {
-                for (uint32_t j = 0; j < cnt; ++j) {
-                    const double2 t = *reinterpret_cast<const double2 *>(trow + 2 * j);
-                    acc0 = __dadd_rn(acc0, t.x);
-                    if (MODE == 0) acc0 = __dadd_rn(acc0, t.y);  // MODE 0 has dim even: both columns are real
-                    if (MODE == 2) acc1 = __dadd_rn(acc1, t.y);
-                }
+                for (uint32_t e = 0; e < cnt; ++e) step(trow[e], QSMEM ? s_q[c0 + e] : __ldg(query + c0 + e));
             }
             __syncwarp();
         }
-        const u64 row = g_first + lane;
+        const u64 row = g * 32 + lane;
         if (row < n) {
             double r;
-            if (MODE == 2) r = __dsub_rn(1.0, __ddiv_rn(acc0, __dmul_rn(__dsqrt_rn(acc1), __dsqrt_rn(q_norm2))));
+            if (METRIC == ADIST_COSINE) r = __dsub_rn(1.0, __ddiv_rn(acc0, __dmul_rn(__dsqrt_rn(acc1), __dsqrt_rn(q_norm2))));
             else r = __dsqrt_rn(acc0);
             out[row] = r;
         }
+        g += gstride;
+        if (g >= NG) break;
     }
 }
 

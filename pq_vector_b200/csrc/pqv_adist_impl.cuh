@@ -19,23 +19,40 @@ int adist_launch(DeviceState &D, const float *d_data, u64 n, uint32_t dim, const
     double qn2 = 0.0;
     if (metric == PQV_METRIC_COSINE)
         for (uint32_t i = 0; i < dim; ++i) qn2 += h_query[i] * h_query[i];  // sequential f64 fold (host code is built without FMA)
-    const size_t smem = (size_t)pqv::ADIST_WARPS * pqv::ADIST_TILE_BYTES;
+    const bool qsmem = dim <= pqv::ADIST_QSMEM_MAX_DIM;
+    const uint32_t dim_pad = (dim + pqv::ADIST_BLK - 1) / pqv::ADIST_BLK * pqv::ADIST_BLK;
+    const size_t smem = (size_t)pqv::ADIST_WARPS * pqv::ADIST_TILE_BYTES + (qsmem ? (size_t)dim_pad * 8 : 0);
     const u64 groups = (n + 31) / 32;
-    const uint32_t grid = (uint32_t)std::max<u64>(1, std::min<u64>((u64)D.sm_count * 3, (groups + pqv::ADIST_WARPS - 1) / pqv::ADIST_WARPS));
     const bool vec2 = (dim % 2 == 0) && ((uintptr_t)d_data % 8 == 0);
-    const int mode = metric == PQV_METRIC_COSINE ? 2 : (vec2 ? 0 : 1);
+    const int variant = (metric == PQV_METRIC_COSINE ? 4 : 0) | (vec2 ? 2 : 0) | (qsmem ? 1 : 0);
     cudaError_t attr_err = cudaSuccess;
-#define PQV_ADIST_CASE(M)                                                                                                   \
-    case M: {                                                                                                               \
-        auto *fn = pqv::array_distance_kernel<M, 16>;                                                                       \
-        attr_err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                        \
-        if (attr_err == cudaSuccess) fn<<<grid, pqv::ADIST_WARPS * 32, smem, D.stream>>>(d_data, n, dim, D.ad_query.p, qn2, d_out); \
-        break;                                                                                                              \
+#define PQV_ADIST_CASE(V, METRIC, VEC2, QS)                                                                                  \
+    case V: {                                                                                                                \
+        auto *fn = pqv::array_distance_kernel<METRIC, VEC2, QS>;                                                             \
+        static int occ = 0;  /* CTAs per SM at this shared-memory size; the grid is persistent */                           \
+        static size_t occ_smem = 0;                                                                                          \
+        if (!occ || occ_smem != smem) {                                                                                      \
+            attr_err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
+            if (attr_err == cudaSuccess)                                                                                     \
+                attr_err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pqv::ADIST_WARPS * 32, smem);             \
+            if (attr_err != cudaSuccess) break;                                                                              \
+            if (occ < 1) occ = 1;                                                                                            \
+            occ_smem = smem;                                                                                                 \
+        }                                                                                                                    \
+        const uint32_t grid = (uint32_t)std::max<u64>(                                                                       \
+            1, std::min<u64>((u64)D.sm_count * occ, (groups + pqv::ADIST_WARPS - 1) / pqv::ADIST_WARPS));                    \
+        fn<<<grid, pqv::ADIST_WARPS * 32, smem, D.stream>>>(d_data, n, dim, D.ad_query.p, qn2, d_out);                      \
+        break;                                                                                                               \
     }
-    switch (mode) {
-        PQV_ADIST_CASE(0)
-        PQV_ADIST_CASE(1)
-        PQV_ADIST_CASE(2)
+    switch (variant) {
+        PQV_ADIST_CASE(0, pqv::ADIST_L2, false, false)
+        PQV_ADIST_CASE(1, pqv::ADIST_L2, false, true)
+        PQV_ADIST_CASE(2, pqv::ADIST_L2, true, false)
+        PQV_ADIST_CASE(3, pqv::ADIST_L2, true, true)
+        PQV_ADIST_CASE(4, pqv::ADIST_COSINE, false, false)
+        PQV_ADIST_CASE(5, pqv::ADIST_COSINE, false, true)
+        PQV_ADIST_CASE(6, pqv::ADIST_COSINE, true, false)
+        PQV_ADIST_CASE(7, pqv::ADIST_COSINE, true, true)
     }
 #undef PQV_ADIST_CASE
     CU_TRY(attr_err);
@@ -170,16 +187,28 @@ int pqv_coalesce_stats(pqv_ctx *ctx, uint64_t *out_queries, uint64_t *out_batche
 int pqv_l2_topk_coalesced(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t *out_row_idx,
                           float *out_dist, uint32_t *out_count) {
     if (!ctx || !query || !out_row_idx || !out_dist || !out_count) return fail(PQV_EINVAL, "null argument");
-    uint32_t dim = 0;
-    {   // reject what the reference rejects per call (search.rs:66-74, 91-98) before the request can join a batch
-        std::lock_guard<std::mutex> lk(ctx->mu);
-        Dataset *ds = find_dataset(ctx, handle);
-        if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
-        PQV_TRY(check_topk_args(k, ds->dim, flags));
-        dim = ds->dim;
-    }
     typedef pqv_ctx::CoalesceReq Req;
     pqv_ctx::Coalescer &co = ctx->co;
+    // reject what the reference rejects per call (search.rs:66-74, 91-98) before the request can join a batch.  ctx->mu
+    // is held by a running pass for its whole duration, so the dimension comes from the coalescer's own cache (handles
+    // are never reused); only the first call per dataset looks it up under ctx->mu.
+    uint32_t dim = 0;
+    {
+        std::lock_guard<std::mutex> lk(co.m);
+        auto it = co.dims.find(handle);
+        if (it != co.dims.end()) dim = it->second;
+    }
+    if (!dim) {
+        {
+            std::lock_guard<std::mutex> lk(ctx->mu);
+            Dataset *ds = find_dataset(ctx, handle);
+            if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+            dim = ds->dim;
+        }
+        std::lock_guard<std::mutex> lk(co.m);
+        co.dims[handle] = dim;
+    }
+    PQV_TRY(check_topk_args(k, dim, flags));
     Req me;
     me.handle = handle;
     me.k = k;

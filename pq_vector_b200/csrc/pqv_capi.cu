@@ -449,6 +449,7 @@ struct pqv_ctx {
         bool leader_active = false;
         uint32_t max_batch = 1024, window_us = 0;
         u64 n_queries = 0, n_batches = 0, max_seen = 0;
+        std::map<u64, uint32_t> dims;  // dataset handle -> dim, so that enqueueing never waits on ctx->mu
     } co;
 };
 
@@ -457,8 +458,15 @@ namespace {
 struct DevGuard {
     int prev = -1;
     explicit DevGuard(int dev) {
+        // a thread that never called cudaSetDevice reports device 0 but has NO current context: runtime calls bind one
+        // lazily, the driver entry points used for TMA descriptors (cuTensorMapEncodeTiled) fail with INVALID_CONTEXT.
+        // Callers are arbitrary threads (tokio workers), so bind explicitly once per thread.
+        static thread_local bool bound = false;
         cudaGetDevice(&prev);
-        if (prev != dev) cudaSetDevice(dev);
+        if (prev != dev || !bound) {
+            cudaSetDevice(dev);
+            bound = true;
+        }
     }
     ~DevGuard() {
         if (prev >= 0) cudaSetDevice(prev);
@@ -1104,6 +1112,10 @@ int pqv_dataset_drop(pqv_ctx *ctx, uint64_t handle) {
         sh.drop_norms();
     }
     ctx->datasets.erase(handle);
+    {
+        std::lock_guard<std::mutex> lk2(ctx->co.m);
+        ctx->co.dims.erase(handle);
+    }
     return PQV_OK;
 }
 
