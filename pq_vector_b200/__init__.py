@@ -8,8 +8,9 @@ from ._native import (PQV_MAX_DIM, PQV_MAX_K, PQV_METRIC_COSINE, PQV_METRIC_L2, 
                       LIB_PATH)
 from .builders import (IndexBuilder, PqVectorError, SearchResult, TopkBuilder, VectorTopKOptions,  # noqa: E402
                        has_pq_vector_index, vector_topk)
+from .session import SessionContext, SessionStateBuilder  # noqa: E402
 from .api import Context, Dataset, IvfIndex, PqvError, TopkStream, merge_batch_keys, replay_candidates
 
-__all__ = ["IndexBuilder", "TopkBuilder", "SearchResult", "VectorTopKOptions", "has_pq_vector_index", "vector_topk",
+__all__ = ["SessionStateBuilder", "SessionContext", "IndexBuilder", "TopkBuilder", "SearchResult", "VectorTopKOptions", "has_pq_vector_index", "vector_topk",
            "PqVectorError", "Context", "Dataset", "TopkStream", "IvfIndex", "PqvError", "replay_candidates", "merge_batch_keys", "PQV_SQRT", "PQV_SUM_SEQ", "PQV_SUM_UNROLL4",
            "PQV_TIES_BY_POSITION", "PQV_METRIC_L2", "PQV_METRIC_COSINE", "PQV_MAX_K", "PQV_MAX_DIM", "LIB_PATH"]
