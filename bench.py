@@ -193,7 +193,7 @@ def run_reference(args):
         "e2e": {"value": qps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -381,7 +381,7 @@ def run_ours(args):
         if world == 1 and not args.no_cpu_baseline:
             base, _ = cpu_baseline(min(args.cpu_sample_rows, n), dim, k, n, reps=5)
             line["cpu_baseline"] = base
-        print(json.dumps(line), flush=True)
+        emit(line)
     ds.drop()
     ctx.close()
     if world > 1:
@@ -389,8 +389,26 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """The ONE JSON line goes to the process's original stdout; everything else that writes to fd 1 while the bench
+    runs (NCCL's "NCCL version ..." banner, library chatter) is diverted to stderr so the line stays alone."""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
     args = parse_args()
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -58,6 +58,30 @@ static int fail(int code, const char *fmt, ...) {
         if (rc__) return rc__; \
     } while (0)
 
+// Stable ascending sort for the reference's `sort_by(|a, b| a.partial_cmp(b).unwrap_or(Equal))` sites
+// (src/ivf/index.rs:143, src/ivf/search.rs:136-140, src/df_vector/exec.rs:270-274).  For NaN-free keys every stable sort
+// gives the same result.  With a NaN the comparator is not an order and the outcome depends on the algorithm -- Rust's
+// own changes with the std version (merge sort / driftsort), so it cannot be pinned; this is the plain top-down merge
+// (split at n/2, the right element is taken only if strictly smaller) that the oracle uses, so product and checker
+// agree on those inputs too.
+template <typename T, typename Less>
+static void merge_sort_stable_rec(T *a, T *tmp, size_t n, Less less) {
+    if (n < 2) return;
+    const size_t mid = n / 2;
+    merge_sort_stable_rec(a, tmp, mid, less);
+    merge_sort_stable_rec(a + mid, tmp, n - mid, less);
+    size_t i = 0, j = mid, o = 0;
+    while (i < mid && j < n) tmp[o++] = less(a[j], a[i]) ? a[j++] : a[i++];
+    while (i < mid) tmp[o++] = a[i++];
+    while (j < n) tmp[o++] = a[j++];
+    for (size_t t = 0; t < n; ++t) a[t] = tmp[t];
+}
+template <typename T, typename Less>
+static void merge_sort_stable(std::vector<T> &v, Less less) {
+    std::vector<T> tmp(v.size());
+    merge_sort_stable_rec(v.data(), tmp.data(), v.size(), less);
+}
+
 // ------------------------------------------------------------------------------------------------
 // Rust std::collections::BinaryHeap<HeapItem> (max-heap on distance, NaN -> Equal), written against
 // the published std source: push = sift_up(0, old_len); pop = swap last into root +
@@ -198,7 +222,7 @@ size_t replay_ordered(size_t n, Next next, uint32_t k, uint32_t flags, uint32_t 
     std::vector<HeapItem> &r = h.data;
     if (flags & PQV_SQRT)
         for (auto &it : r) it.distance = sqrtf(it.distance);
-    std::stable_sort(r.begin(), r.end(), [](const HeapItem &a, const HeapItem &b) { return a.distance < b.distance; });
+    merge_sort_stable(r, [](const HeapItem &a, const HeapItem &b) { return a.distance < b.distance; });
     for (size_t i = 0; i < r.size(); ++i) {
         out_rows[i] = r[i].row_idx;
         out_dist[i] = r[i].distance;
@@ -1763,7 +1787,7 @@ int pqv_centroid_rank(pqv_ctx *ctx, const float *centroids, uint32_t n_clusters,
     CU_TRY(cudaMemcpyAsync(D.d_centroids.p, centroids, (size_t)n_clusters * dim * 4, cudaMemcpyHostToDevice, D.stream));
     std::vector<float> dist(n_clusters);
     std::vector<uint32_t> idx(n_clusters);
-    for (uint32_t q = 0; q < n_queries; ++q) {
+    auto rank_one = [&](uint32_t q) -> int {
         CU_TRY(cudaMemcpyAsync(D.d_vec.p, queries + (size_t)q * dim, (size_t)dim * 4, cudaMemcpyHostToDevice, D.stream));
         // index.rs:138 squared_l2_distance(query, centroid); (q-c)^2 == (c-q)^2 bit for bit
         PQV_TRY(dist_launch(D, D.d_centroids.p, nullptr, n_clusters, dim, D.d_vec.p, D.d_dist.p, 0));
@@ -1771,9 +1795,57 @@ int pqv_centroid_rank(pqv_ctx *ctx, const float *centroids, uint32_t n_clusters,
         CU_TRY(cudaStreamSynchronize(D.stream));
         for (uint32_t i = 0; i < n_clusters; ++i) idx[i] = i;
         // index.rs:143 stable sort, partial_cmp -> Equal for NaN
-        std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return dist[a] < dist[b]; });
+        merge_sort_stable(idx, [&](uint32_t a, uint32_t b) { return dist[a] < dist[b]; });
         memcpy(out_cluster_ids + (size_t)q * np, idx.data(), (size_t)np * 4);
+        return PQV_OK;
+    };
+    // batches: all nq x C distances in one launch (exact order), one CTA per query ranks on the device
+    uint32_t cp2 = 32;
+    while (cp2 < n_clusters) cp2 <<= 1;
+    const bool batched = n_queries >= 2 && (size_t)cp2 * 8 <= 128 * 1024 && getenv("PQV_RANK_BATCH_OFF") == nullptr;
+    if (!batched) {
+        for (uint32_t q = 0; q < n_queries; ++q) PQV_TRY(rank_one(q));
+        return PQV_OK;
     }
+    const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(D.d_centroids.p) & 15) == 0);
+    const size_t smem = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)SCAN_WARPS * pqv::TileCfg<0, true>::TILE_FLOATS * 4;
+    const u64 NG = ((u64)n_clusters + 31) / 32;
+    static size_t attr_dist[2] = {0, 0};
+    static size_t attr_rank = 0;
+    auto *k_vec = pqv::l2_dist_batch_kernel<true, SCAN_WARPS>;
+    auto *k_sca = pqv::l2_dist_batch_kernel<false, SCAN_WARPS>;
+    if (smem > attr_dist[vec4]) {
+        if (vec4) CU_TRY(cudaFuncSetAttribute(k_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CU_TRY(cudaFuncSetAttribute(k_sca, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        attr_dist[vec4] = smem;
+    }
+    if ((size_t)cp2 * 8 > attr_rank) {
+        CU_TRY(cudaFuncSetAttribute(pqv::rank_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cp2 * 8)));
+        attr_rank = (size_t)cp2 * 8;
+    }
+    constexpr uint32_t CHUNK = 16384;  // queries per launch (gridDim.y limit, scratch size)
+    const uint32_t chunk_max = std::min(n_queries, CHUNK);
+    PQV_TRY(D.d_tmp_rows.ensure((size_t)chunk_max * dim));
+    PQV_TRY(D.d_dist.ensure((size_t)chunk_max * n_clusters));
+    PQV_TRY(D.d_assign.ensure((size_t)chunk_max * np));
+    PQV_TRY(D.d_row_ids.ensure(chunk_max));
+    std::vector<uint32_t> flags(chunk_max);
+    std::vector<uint32_t> redo;
+    for (uint32_t q0 = 0; q0 < n_queries; q0 += CHUNK) {
+        const uint32_t nq = std::min(CHUNK, n_queries - q0);
+        CU_TRY(cudaMemcpyAsync(D.d_tmp_rows.p, queries + (size_t)q0 * dim, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, D.stream));
+        const dim3 grid((uint32_t)((NG + SCAN_WARPS - 1) / SCAN_WARPS), nq);
+        if (vec4) k_vec<<<grid, SCAN_WARPS * 32, smem, D.stream>>>(D.d_centroids.p, n_clusters, dim, D.d_tmp_rows.p, D.d_dist.p);
+        else k_sca<<<grid, SCAN_WARPS * 32, smem, D.stream>>>(D.d_centroids.p, n_clusters, dim, D.d_tmp_rows.p, D.d_dist.p);
+        pqv::rank_batch_kernel<<<nq, 1024, (size_t)cp2 * 8, D.stream>>>(D.d_dist.p, n_clusters, cp2, np, D.d_assign.p, D.d_row_ids.p);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(out_cluster_ids + (size_t)q0 * np, D.d_assign.p, (size_t)nq * np * 4, cudaMemcpyDeviceToHost, D.stream));
+        CU_TRY(cudaMemcpyAsync(flags.data(), D.d_row_ids.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, D.stream));
+        CU_TRY(cudaStreamSynchronize(D.stream));
+        for (uint32_t i = 0; i < nq; ++i)
+            if (flags[i]) redo.push_back(q0 + i);
+    }
+    for (uint32_t q : redo) PQV_TRY(rank_one(q));  // NaN distances: the reference comparator on the host
     return PQV_OK;
 }
 

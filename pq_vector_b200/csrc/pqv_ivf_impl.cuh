@@ -219,7 +219,7 @@ int rank_clusters(DeviceState &D, IvfIndex &ix, const float *query, uint32_t npr
     CU_TRY(cudaStreamSynchronize(D.stream));
     std::vector<uint32_t> idx(ix.n_clusters);
     for (uint32_t i = 0; i < ix.n_clusters; ++i) idx[i] = i;
-    std::stable_sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) { return dist[a] < dist[b]; });
+    merge_sort_stable(idx, [&](uint32_t a, uint32_t b) { return dist[a] < dist[b]; });
     const uint32_t np = std::min(nprobe, ix.n_clusters);
     ranked.assign(idx.begin(), idx.begin() + np);
     return PQV_OK;

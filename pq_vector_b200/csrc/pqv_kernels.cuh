@@ -528,6 +528,61 @@ __global__ void __launch_bounds__(WARPS * 32, 2) l2_dist_kernel(const float *__r
 }
 
 // ------------------------------------------------------------------------------------------------
+// Batched centroid ranking (find_closest_centroids for every query of a batch, index.rs:130-149; SURVEY row a6 "becomes
+// a (queries x centroids) contraction when batched").  The table is short (C x dim, L2-resident), so the contraction
+// stays in the reference's exact f32 order on the SIMT path: blockIdx.y = query, the CTA stages that query and its warps
+// take groups of 32 centroids.  rank_batch_kernel then sorts each query's (distance bits, cluster) keys in shared memory
+// -- for non-NaN distances exactly the reference's stable ascending sort -- and writes the first np cluster ids; a NaN
+// distance raises the query's flag and the host ranks that query with the reference comparator instead.
+// ------------------------------------------------------------------------------------------------
+template <bool VEC4, int WARPS>
+__global__ void __launch_bounds__(WARPS * 32, 2) l2_dist_batch_kernel(const float *__restrict__ data, const u64 n,
+                                                                   const uint32_t dim, const float *__restrict__ vecs,
+                                                                   float *__restrict__ out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TILE_FLOATS = TileCfg<0, VEC4>::TILE_FLOATS;
+    const uint32_t dim_pad = (dim + 3u) & ~3u;
+    float *s_vec = reinterpret_cast<float *>(smem_raw);
+    float *s_tiles = s_vec + dim_pad;
+    const uint32_t tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const float *vec = vecs + (size_t)blockIdx.y * dim;
+    float *o = out + (size_t)blockIdx.y * n;
+    for (uint32_t i = tid; i < dim; i += WARPS * 32) s_vec[i] = vec[i];
+    __syncthreads();
+    float *tile = s_tiles + warp * TILE_FLOATS;
+    const u64 NG = (n + 31) >> 5;
+    for (u64 g = (u64)blockIdx.x * WARPS + warp; g < NG; g += (u64)gridDim.x * WARPS) {
+        // index.rs:138 squared_l2_distance(query, centroid): a = query (s_vec), b = row -- group_distance<0> order
+        const float d = group_distance<0, VEC4, false>(data, nullptr, n, dim, g, s_vec, tile, lane);
+        const u64 pos = g * 32 + lane;
+        if (pos < n) o[pos] = d;
+    }
+}
+
+__global__ void __launch_bounds__(1024) rank_batch_kernel(const float *__restrict__ cdist, const uint32_t C,
+                                                          const uint32_t cp2, const uint32_t np,
+                                                          uint32_t *__restrict__ out_ids, uint32_t *__restrict__ nan_flags) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *s = reinterpret_cast<u64 *>(smem_raw);
+    const uint32_t tid = threadIdx.x;
+    const float *d_q = cdist + (size_t)blockIdx.x * C;
+    bool bad = false;
+    for (uint32_t i = tid; i < cp2; i += 1024) {
+        u64 key = KEY_MAX;
+        if (i < C) {
+            const float d = d_q[i];
+            bad |= (d != d);
+            key = ((u64)__float_as_uint(d) << 32) | i;
+        }
+        s[i] = key;
+    }
+    const int any_bad = __syncthreads_or(bad);
+    if (tid == 0) nan_flags[blockIdx.x] = any_bad ? 1u : 0u;
+    bitonic_sort_smem(s, cp2, tid, 1024);
+    for (uint32_t r = tid; r < np; r += 1024) out_ids[(size_t)blockIdx.x * np + r] = (uint32_t)s[r];
+}
+
+// ------------------------------------------------------------------------------------------------
 // l2_dist_wide_kernel: the same sweep for SHORT tables (centroid ranking: C rows, index.rs:130-149).  With only a
 // few groups of 32 rows, one warp per group leaves the machine empty and the sweep becomes a chain of memory round
 // trips; here one CTA of 8 warps owns a group, warp w loads column blocks w, w+8, ... of all 32 rows and writes the

@@ -80,7 +80,7 @@ def test_reference_kats_through_the_abi(ctx):
 
 # ---- seeded random inputs vs oracle ------------------------------------------------------------------
 @pytest.mark.parametrize("n,dim", [(1, 4), (31, 8), (32, 3), (33, 5), (257, 1), (1000, 7), (4096, 128), (5000, 130),
-                                   (3000, 768), (2000, 1000), (1500, 1536), (700, 4096), (50_000, 64)])
+                                   (3000, 768), (2000, 1000), (1500, 1536), (700, 4096), (50_000, 64), (70, 16384)])
 def test_bruteforce_matches_oracle(ctx, n, dim):
     rng = np.random.default_rng(n * 31 + dim)
     data = rng.random((n, dim), dtype=np.float32)
@@ -246,6 +246,34 @@ def test_centroid_rank_matches_oracle(ctx):
         for i in range(5):
             assert got[i].tolist() == O.find_closest_centroids(qs[i], cent, nprobe).tolist()
     assert ctx.centroid_rank(cent, cent[10], 3)[0].tolist() == [10, 50, 200]
+
+
+@pytest.mark.parametrize("C,dim,nq", [(1024, 768, 256), (23, 4096, 40), (777, 50, 33), (4097, 8, 7)])
+def test_batched_centroid_rank(ctx, C, dim, nq):
+    """Row a6 batched (config C5): one launch for all queries x centroids, ranked on the device -- identical to the
+    per-query reference ranking (index.rs:130-149), incl. exact ties (stable by index) and NaN centroids (host comparator)."""
+    import os
+    rng = np.random.default_rng(C + dim)
+    cent = rng.random((C, dim), dtype=np.float32)
+    cent[C // 2] = cent[3]
+    cent[C - 1] = cent[3]
+    qs = rng.random((nq, dim), dtype=np.float32)
+    qs[1] = cent[3]
+    for nprobe in (1, 32, C):
+        got = ctx.centroid_rank(cent, qs, nprobe)
+        for i in range(0, nq, max(1, nq // 16)):
+            assert got[i].tolist() == O.find_closest_centroids(qs[i], cent, nprobe).tolist(), (i, nprobe)
+    assert ctx.centroid_rank(cent, qs, 3)[1].tolist() == [3, C // 2, C - 1]
+    os.environ["PQV_RANK_BATCH_OFF"] = "1"
+    try:
+        one_by_one = ctx.centroid_rank(cent, qs, 32)
+    finally:
+        del os.environ["PQV_RANK_BATCH_OFF"]
+    assert np.array_equal(ctx.centroid_rank(cent, qs, 32), one_by_one)
+    cent[5, 0] = np.nan                                   # NaN distance for every query: partial_cmp -> Equal
+    got = ctx.centroid_rank(cent, qs[:4], 16)
+    for i in range(4):
+        assert got[i].tolist() == O.find_closest_centroids(qs[i], cent, 16).tolist()
 
 
 def test_ivf_search_pipeline_matches_oracle(ctx, vldb):
