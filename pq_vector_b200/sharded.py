@@ -233,3 +233,47 @@ class ShardedIvfBuild:
         offsets = np.zeros(C + 1, dtype=np.uint64)
         np.cumsum(np.bincount(assign, minlength=C), out=offsets[1:])
         return index_to_bytes(centroids, offsets, order)
+
+
+class ShardedArrayDistanceTopk:
+    """The un-indexed `array_distance` arm over row-range shards (SURVEY row a10 at config C5's 8-GPU shape): every rank
+    takes the exact f64 top-k of its own slice (Dataset.array_distance_topk), ONE all-gather moves world x (1 + 2k) x 8 B,
+    and every rank merges by (f64 total order with NaN last, global row) -- the k smallest of the whole table are among
+    the slices' k smallest, and the key is unique per row, so all ranks produce the same list."""
+
+    def __init__(self, local_fn, pos_base: int, device: "torch.device | str" = "cpu", group=None):
+        """local_fn(query_f64, k) -> (row_idx u32 local to the slice, distance f64), ascending."""
+        self.local_fn = local_fn
+        self.pos_base = int(pos_base)
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.last_gather_bytes = 0
+
+    @staticmethod
+    def _ordered(d: np.ndarray) -> np.ndarray:
+        b = np.ascontiguousarray(d, dtype=np.float64).view(np.uint64).copy()
+        b[np.isnan(d)] = np.uint64(0x7FF8000000000000)
+        neg = (b >> np.uint64(63)).astype(bool)
+        return np.where(neg, ~b, b | np.uint64(0x8000000000000000))
+
+    def search(self, query, k: int):
+        rows, d = self.local_fn(np.ascontiguousarray(query, dtype=np.float64), k)
+        n = int(rows.size)
+        send = np.zeros(1 + 2 * k, dtype=np.int64)
+        send[0] = n
+        send[1:1 + n] = rows.astype(np.int64) + self.pos_base
+        send[1 + k:1 + k + n] = np.ascontiguousarray(d, dtype=np.float64).view(np.int64)
+        if self.world > 1:
+            t_send = torch.from_numpy(send).to(self.device)
+            t_recv = torch.empty(self.world * send.size, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(t_recv, t_send, group=self.group)
+            got = t_recv.cpu().numpy().reshape(self.world, send.size)
+            self.last_gather_bytes = got.nbytes
+        else:
+            got = send[None, :]
+            self.last_gather_bytes = 0
+        all_rows = np.concatenate([got[r, 1:1 + int(got[r, 0])] for r in range(got.shape[0])]).astype(np.uint32)
+        all_d = np.concatenate([got[r, 1 + k:1 + k + int(got[r, 0])] for r in range(got.shape[0])]).view(np.float64)
+        order = np.lexsort((all_rows, self._ordered(all_d)))[:k]
+        return all_rows[order], all_d[order]

@@ -140,3 +140,42 @@ def test_two_rank_ivf_build_matches_single_process(tmp_path, n, dim, C, seed):
     mp.spawn(_ivf_worker, args=(2, port, n, dim, C, seed, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
+
+
+def _adist_worker(rank, world, port, n, dim, k, seed, out_dir):
+    sys.path.insert(0, ROOT)
+    import oracle as O
+    from pq_vector_b200.sharded import ShardedArrayDistanceTopk
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    # odd seeds: small-integer grid -> many equal f64 distances across the two slices (ties by global row)
+    data = rng.integers(0, 3, (n, dim)).astype(np.float32) if seed % 2 else rng.random((n, dim), dtype=np.float32)
+    if seed == 8:
+        data[3, 0] = np.inf
+        data[n - 2, 0] = np.inf
+    q = rng.random(dim) if seed % 2 == 0 else np.zeros(dim)
+    if seed == 8:
+        q[0] = np.inf            # rows 3 and n-2: NaN distance (sorted last); every other row: +inf
+    per = (n + world - 1) // world
+    lo, hi = rank * per, min(n, (rank + 1) * per)
+
+    def local(query, k_):        # the oracle standing in for Dataset.array_distance_topk on this rank's slice
+        return O.array_distance_topk(data[lo:hi], query, k_)
+
+    st = ShardedArrayDistanceTopk(local, lo, "cpu")
+    rows, dd = st.search(q, k)
+    er, ed = O.array_distance_topk(data, q, k)
+    ok = rows.tolist() == er.tolist() and dd.view(np.uint64).tolist() == ed.view(np.uint64).tolist()
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,dim,k,seed", [(1000, 8, 10, 2), (3000, 4, 100, 3), (5, 3, 10, 4), (600, 6, 600, 8)])
+def test_two_rank_array_distance_topk(tmp_path, n, dim, k, seed):
+    port = 31500 + (os.getpid() + seed) % 2000
+    mp.spawn(_adist_worker, args=(2, port, n, dim, k, seed, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
