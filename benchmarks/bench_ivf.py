@@ -73,4 +73,26 @@ t = ctx.last_timing()
 out["search"] = {"qps_e2e": 1.0 / float(np.mean(lat)), "ms_per_query_e2e": float(np.mean(lat)) * 1e3,
                  "mean_candidates": float(np.mean(cands)), "recall_at_k_vs_bruteforce": float(np.mean(recall)),
                  "gather_gbs_e2e": float(np.mean(cands)) * (a.dim * 4 + 4) / float(np.mean(lat)) / 1e9}
+# VectorTopKExec over the same resident table + index (pqv_vector_topk_indexed): candidates in row order, sequential-order
+# sums, with and without a filter bitmap (here: id >= N/2) -- the reference's operator re-reads the rows from Parquet
+rng_mask = np.arange(a.rows) >= a.rows // 2
+for name, mask in (("vector_topk_exec", None), ("vector_topk_exec_filtered", rng_mask)):
+    for q in queries[:3]:
+        ix.vector_topk(ds, q, a.k, a.nprobe, P.PQV_SUM_SEQ, None, mask)
+    lat, scored, kern = [], [], []
+    for q in queries:
+        t0 = time.perf_counter()
+        r, d, total, ns = ix.vector_topk(ds, q, a.k, a.nprobe, P.PQV_SUM_SEQ, None, mask)
+        lat.append(time.perf_counter() - t0)
+        scored.append(ns)
+        kern.append(ctx.last_timing()["scan_ms"])
+    same = None
+    if mask is None:  # same candidate set as TopkBuilder's search; only summation order / visiting order differ
+        r0, _ = ix.search(ds, queries[-1], a.k, a.nprobe, P.PQV_SUM_SEQ)
+        same = sorted(r0.tolist()) == sorted(r.tolist())
+    out[name] = {"qps_e2e": 1.0 / float(np.mean(lat)), "ms_per_query_e2e": float(np.mean(lat)) * 1e3,
+                 "mean_rows_scored": float(np.mean(scored)), "gather_scan_ms": float(np.mean(kern)),
+                 "gather_scan_gbs": float(np.mean(scored)) * a.dim * 4 / (float(np.mean(kern)) * 1e-3) / 1e9,
+                 "same_rows_as_search": same,
+                 "mask_bytes_h2d_per_query": 0 if mask is None else (a.rows + 7) // 8}
 print(json.dumps(out))

@@ -417,6 +417,28 @@ class IvfIndex:
                                    _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), C.byref(cnt)))
         return rows[:cnt.value].copy(), dist[:cnt.value].copy()
 
+    def vector_topk(self, dataset: "Dataset", query, k: int, nprobe: int, flags: int = N.PQV_SUM_SEQ,
+                    max_candidates=None, row_mask=None):
+        """VectorTopKExec over a resident indexed table (pqv_vector_topk_indexed): candidates capped in rank order,
+        visited in row order, rows with row_mask[r] == False dropped before scoring.
+        Returns (row_idx, squared distance, candidate_rows, rows_scored)."""
+        q = _f32(query)
+        if q.size != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.size}")
+        bits = None
+        if row_mask is not None:
+            m = np.ascontiguousarray(row_mask, dtype=bool)
+            if m.size != dataset.rows:
+                raise PqvError(N.PQV_EINVAL, f"row_mask has {m.size} entries, the table {dataset.rows} rows")
+            bits = np.packbits(m, bitorder="little")
+        rows = np.zeros(max(k, 1), dtype=np.uint32)
+        dist = np.zeros(max(k, 1), dtype=np.float32)
+        cnt, cand, scored = C.c_uint32(), C.c_uint64(), C.c_uint64()
+        _check(_lib.pqv_vector_topk_indexed(self.ctx._h, dataset.handle, self.handle, _ptr(q, C.c_float), k, nprobe, flags,
+                                            int(max_candidates or 0), _ptr(bits, C.c_uint8), _ptr(rows, C.c_uint32),
+                                            _ptr(dist, C.c_float), C.byref(cnt), C.byref(cand), C.byref(scored)))
+        return rows[:cnt.value].copy(), dist[:cnt.value].copy(), cand.value, scored.value
+
     def drop(self):
         if self.handle:
             _check(_lib.pqv_ivf_drop(self.ctx._h, self.handle))

@@ -371,6 +371,8 @@ struct DeviceState {
     DevBuf<u64> ivf_info;
     PinBuf<uint32_t> h_ent_rows;
     PinBuf<u64> h_ivf_info;
+    // VectorTopKExec candidate handling (ivf_mark / bitmap_* kernels): candidate bitmap, filter bitmap, block sums
+    DevBuf<uint32_t> vt_bitmap, vt_mask, vt_sums;
     // un-indexed array_distance arm (pqv_adist.cuh): f64 query, f64 distance column, radix-select state, k winners
     DevBuf<double> ad_query, ad_col, ad_out_dist;
     DevBuf<uint32_t> ad_out_row;
@@ -972,6 +974,9 @@ void pqv_destroy(pqv_ctx *ctx) {
         D.csr_totals.release();
         D.h_ent_rows.release();
         D.h_ivf_info.release();
+        D.vt_bitmap.release();
+        D.vt_mask.release();
+        D.vt_sums.release();
         D.ad_query.release();
         D.ad_col.release();
         D.ad_out_dist.release();

@@ -239,15 +239,24 @@ bool ivf_fused_enabled() {
 // (index.rs:130-149), list expansion (index.rs:57-63), gathered scan + entrant filter and the entrants' row ids are all
 // enqueued back to back; the host only replays the reference heap over the ~1e3 entrants.  *done = false (nothing
 // written) when a centroid distance is NaN or the entrant buffer overflowed: the caller then takes the host-ranked path.
+// RowOrder != nullptr selects VectorTopKExec's candidate handling (exec.rs:207-245): the first max_candidates candidates
+// in rank order, visited in ascending row order, rows whose filter bit is clear dropped before scoring.
+struct RowOrder {
+    u64 max_candidates = ~0ull;      // ~0: no cap
+    const uint8_t *h_mask = nullptr;  // host, ceil(n_rows / 8) bytes, bit r (LSB first) = row r passes the filter; null = all
+    u64 candidate_rows = 0;           // out: probed candidates before cap and filter
+    u64 rows_scored = 0;              // out
+};
+
 int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, const float *query, uint32_t k,
                      uint32_t nprobe, uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
-                     bool *done) {
+                     bool *done, RowOrder *ro = nullptr) {
     *done = false;
     static const bool trace = getenv("PQV_TRACE") != nullptr;
     double tt[8] = {0};
     if (trace) tt[0] = now_ms();
     const uint32_t C = ix.n_clusters, np = std::min(nprobe, C), cp2 = pow2ceil(C);
-    const u64 n_bound = ix.n_ids;
+    const u64 n_bound = ro ? std::min<u64>(ix.n_ids, ro->max_candidates) : ix.n_ids;
     const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
     static std::once_flag attr_once;
     static cudaError_t attr_err = cudaSuccess;
@@ -262,22 +271,42 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
     PQV_TRY(D.ent_out.ensure((size_t)(1u << 16) + 1));
     const uint32_t cap = (uint32_t)std::min<size_t>(D.ent_out.cap - 1, 0xFFFFFFF0u);
     PQV_TRY(D.ent_rows.ensure(cap));
-    PQV_TRY(D.ivf_info.ensure(2));
-    PQV_TRY(D.h_ivf_info.ensure(2));
+    PQV_TRY(D.ivf_info.ensure(4));
+    PQV_TRY(D.h_ivf_info.ensure(4));
     PQV_TRY(D.h_ent_out.ensure((size_t)ENT_FIRST_CHUNK + 1));
     PQV_TRY(D.h_ent_rows.ensure(ENT_FIRST_CHUNK));
     if (trace) tt[1] = now_ms();
     memcpy(D.h_query.p, query, (size_t)ix.dim * 4);
     CU_TRY(cudaMemcpyAsync(D.d_query.p, D.h_query.p, (size_t)ix.dim * 4, cudaMemcpyHostToDevice, D.stream));
-    CU_TRY(cudaMemsetAsync(D.ivf_info.p, 0, 16, D.stream));
+    CU_TRY(cudaMemsetAsync(D.ivf_info.p, 0, 32, D.stream));
     CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
+    const u64 n_words = (ds.n_rows + 31) / 32;
+    const uint32_t bm_blocks = (uint32_t)((n_words + pqv::BM_WORDS_PER_BLOCK - 1) / pqv::BM_WORDS_PER_BLOCK);
+    if (ro) {
+        PQV_TRY(D.vt_bitmap.ensure(n_words));
+        PQV_TRY(D.vt_sums.ensure(bm_blocks));
+        CU_TRY(cudaMemsetAsync(D.vt_bitmap.p, 0, n_words * 4, D.stream));
+        if (ro->h_mask) {
+            PQV_TRY(D.vt_mask.ensure(n_words));
+            CU_TRY(cudaMemcpyAsync(D.vt_mask.p, ro->h_mask, (size_t)((ds.n_rows + 7) / 8), cudaMemcpyHostToDevice, D.stream));
+        }
+    }
     PQV_TRY(dist_launch(D, ix.d_centroids.p, nullptr, C, ix.dim, D.d_query.p, ix.d_cdist.p, 0));
     pqv::ivf_rank_kernel<<<1, 1024, (size_t)cp2 * 8, D.stream>>>(ix.d_cdist.p, C, cp2, np, ix.d_offsets.p, ix.d_probe_cluster.p,
                                                                  ix.d_probe_prefix.p, D.ivf_info.p,
                                                                  reinterpret_cast<uint32_t *>(D.ivf_info.p + 1));
     CU_TRY(cudaGetLastError());
-    pqv::ivf_expand_kernel<<<dim3(np, 8), 256, 0, D.stream>>>(ix.d_ids.p, ix.d_offsets.p, ix.d_probe_cluster.p,
-                                                              ix.d_probe_prefix.p, ix.d_cand.p);
+    if (!ro) {
+        pqv::ivf_expand_kernel<<<dim3(np, 8), 256, 0, D.stream>>>(ix.d_ids.p, ix.d_offsets.p, ix.d_probe_cluster.p,
+                                                                  ix.d_probe_prefix.p, ix.d_cand.p);
+    } else {
+        const uint32_t *d_mask = ro->h_mask ? D.vt_mask.p : nullptr;
+        pqv::ivf_mark_kernel<<<dim3(np, 8), 256, 0, D.stream>>>(ix.d_ids.p, ix.d_offsets.p, ix.d_probe_cluster.p,
+                                                                ix.d_probe_prefix.p, ro->max_candidates, ds.n_rows, D.vt_bitmap.p);
+        pqv::bitmap_count_kernel<<<bm_blocks, 256, 0, D.stream>>>(D.vt_bitmap.p, d_mask, n_words, D.vt_sums.p);
+        pqv::bitmap_scan_kernel<<<1, 1024, 0, D.stream>>>(D.vt_sums.p, bm_blocks, D.ivf_info.p);
+        pqv::bitmap_compact_kernel<<<bm_blocks, 256, 0, D.stream>>>(D.vt_bitmap.p, d_mask, n_words, D.vt_sums.p, ix.d_cand.p);
+    }
     CU_TRY(cudaGetLastError());
     if (trace) tt[2] = now_ms();
     ScanGeom g;
@@ -288,12 +317,16 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
     const uint32_t first = std::min<uint32_t>(ENT_FIRST_CHUNK, cap);
     CU_TRY(cudaMemcpyAsync(D.h_ent_out.p, D.ent_out.p, ((size_t)first + 1) * 8, cudaMemcpyDeviceToHost, D.stream));
     CU_TRY(cudaMemcpyAsync(D.h_ent_rows.p, D.ent_rows.p, (size_t)first * 4, cudaMemcpyDeviceToHost, D.stream));
-    CU_TRY(cudaMemcpyAsync(D.h_ivf_info.p, D.ivf_info.p, 16, cudaMemcpyDeviceToHost, D.stream));
+    CU_TRY(cudaMemcpyAsync(D.h_ivf_info.p, D.ivf_info.p, 32, cudaMemcpyDeviceToHost, D.stream));
     if (trace) tt[3] = now_ms();
     CU_TRY(cudaStreamSynchronize(D.stream));
     if (trace) tt[4] = now_ms();
     const u64 n_cand = D.h_ivf_info.p[0], count = D.h_ent_out.p[0];
     if ((uint32_t)D.h_ivf_info.p[1] != 0 || count > cap) return PQV_OK;
+    if (ro) {
+        ro->candidate_rows = D.h_ivf_info.p[2];
+        ro->rows_scored = n_cand;
+    }
     std::vector<u64> entrants(count);
     std::vector<uint32_t> erows(count);
     const u64 got = std::min<u64>(count, first);
@@ -322,7 +355,7 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
     tm.post_ms = b;
     tm.total_ms = a + b;
     tm.scan_bytes = n_cand * (u64)ds.dim * 4;
-    tm.launches = 8;
+    tm.launches = ro ? 12 : 8;
     tm.grid = g.grid;
     tm.entrants = (uint32_t)count;
     if (fast) {
@@ -885,6 +918,62 @@ int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *q
     };
     return topk_one(ctx, *ds, query, nullptr, n_cand, k, flags, out_row_idx, out_dist, out_count, nullptr, 0,
                     ix->d_cand.p, &row_fn);
+}
+
+int pqv_vector_topk_indexed(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k, uint32_t nprobe,
+                            uint32_t flags, uint64_t max_candidates, const uint8_t *row_mask, uint32_t *out_row_idx,
+                            float *out_dist, uint32_t *out_count, uint64_t *out_candidate_rows, uint64_t *out_rows_scored) {
+    if (!ctx || !query || !out_row_idx || !out_dist || !out_count) return fail(PQV_EINVAL, "null argument");
+    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);  // index_exec.rs:152-158
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_vector_topk_indexed needs a single-device dataset");
+    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    DeviceState &D = ctx->devs[ds->shards[0].di];
+    DevGuard guard(D.dev);
+    PQV_TRY(index_make_resident(D, *ix));
+    RowOrder ro;
+    ro.max_candidates = max_candidates ? max_candidates : ~0ull;   // options.rs:10-11: None = no cap
+    ro.h_mask = row_mask;
+    *out_count = 0;
+    if (ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids) {
+        bool done = false;
+        PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, query, k, nprobe, flags, out_row_idx, out_dist, out_count, &done, &ro));
+        if (done) {
+            if (out_candidate_rows) *out_candidate_rows = ro.candidate_rows;
+            if (out_rows_scored) *out_rows_scored = ro.rows_scored;
+            return PQV_OK;
+        }
+    }
+    // host-ranked path (NaN centroid distance, entrant overflow, very large C): same selection on the host
+    PQV_TRY(index_host_ids(D, *ix));
+    std::vector<uint32_t> ranked;
+    PQV_TRY(rank_clusters(D, *ix, query, nprobe, ranked));
+    std::vector<uint32_t> rows;
+    u64 total = 0;
+    for (uint32_t c : ranked) {
+        const u64 b = ix->offsets[c], e = ix->offsets[c + 1];
+        for (u64 i = b; i < e; ++i, ++total)
+            if (total < ro.max_candidates) rows.push_back(ix->ids[i]);
+    }
+    std::sort(rows.begin(), rows.end());
+    if (row_mask) {
+        size_t o = 0;
+        for (uint32_t r : rows)
+            if (row_mask[r >> 3] & (1u << (r & 7))) rows[o++] = r;
+        rows.resize(o);
+    }
+    if (out_candidate_rows) *out_candidate_rows = total;
+    if (out_rows_scored) *out_rows_scored = rows.size();
+    if (rows.empty()) return PQV_OK;
+    for (uint32_t r : rows)
+        if (r >= ds->n_rows) return fail(PQV_EINVAL, "row id %u is out of range (%llu rows)", r, (unsigned long long)ds->n_rows);
+    return topk_one(ctx, *ds, query, rows.data(), rows.size(), k, flags, out_row_idx, out_dist, out_count);
 }
 
 }  // extern "C"

@@ -868,6 +868,124 @@ __global__ void __launch_bounds__(256) ivf_expand_kernel(const uint32_t *__restr
         out_rows[dst + i] = list_ids[src + i];
 }
 
+// ------------------------------------------------------------------------------------------------
+// VectorTopKExec's candidate handling on the device (src/df_vector/exec.rs:207-245, access.rs:107-176): of the probed
+// lists' rows in rank order only the first `max_candidates` count (CandidateCursor over one file = a prefix), the rows
+// are then visited in FILE order (RowSelection per row group) and the scan subtree's filter drops rows before they are
+// scored.  On the device: the kept candidates set their bit in an N-bit map, the map is ANDed with the caller's filter
+// bitmap and compacted in order -> ascending row ids, count in info[0] (what the gathered scan reads through n_dev);
+// info[2] keeps the un-capped, un-filtered candidate count (the `candidate_rows` metric of VectorIndexScanExec).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ivf_mark_kernel(const uint32_t *__restrict__ list_ids,
+                                                       const u64 *__restrict__ list_offsets,
+                                                       const uint32_t *__restrict__ probe_cluster,
+                                                       const u64 *__restrict__ probe_prefix, const u64 max_candidates,
+                                                       const u64 n_rows, uint32_t *__restrict__ bitmap) {
+    const uint32_t r = blockIdx.x;
+    const uint32_t c = probe_cluster[r];
+    const u64 src = list_offsets[c], len = list_offsets[c + 1] - src, dst = probe_prefix[r];
+    for (u64 i = (u64)blockIdx.y * blockDim.x + threadIdx.x; i < len; i += (u64)gridDim.y * blockDim.x) {
+        if (dst + i >= max_candidates) break;  // positions only grow along the list
+        const uint32_t row = list_ids[src + i];
+        if (row < n_rows) atomicOr(&bitmap[row >> 5], 1u << (row & 31));
+    }
+}
+
+constexpr uint32_t BM_WORDS_PER_THREAD = 4;
+constexpr uint32_t BM_WORDS_PER_BLOCK = 256 * BM_WORDS_PER_THREAD;
+
+__global__ void __launch_bounds__(256) bitmap_count_kernel(const uint32_t *__restrict__ bitmap,
+                                                           const uint32_t *__restrict__ mask, const u64 n_words,
+                                                           uint32_t *__restrict__ block_sums) {
+    __shared__ uint32_t s_warp[8];
+    const u64 w0 = ((u64)blockIdx.x * 256 + threadIdx.x) * BM_WORDS_PER_THREAD;
+    uint32_t cnt = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < BM_WORDS_PER_THREAD; ++i)
+        if (w0 + i < n_words) cnt += __popc(bitmap[w0 + i] & (mask ? mask[w0 + i] : 0xFFFFFFFFu));
+    for (int o = 16; o > 0; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if ((threadIdx.x & 31) == 0) s_warp[threadIdx.x >> 5] = cnt;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t t = 0;
+        for (int i = 0; i < 8; ++i) t += s_warp[i];
+        block_sums[blockIdx.x] = t;
+    }
+}
+
+// one CTA: block_sums -> exclusive prefix in place; info[2] = info[0] (all probed candidates), info[0] = rows kept
+__global__ void __launch_bounds__(1024) bitmap_scan_kernel(uint32_t *__restrict__ block_sums, const uint32_t n_blocks,
+                                                           u64 *__restrict__ info) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (uint32_t base = 0; base < n_blocks; base += 1024) {
+        const uint32_t i = base + tid;
+        const uint32_t v = i < n_blocks ? block_sums[i] : 0;
+        uint32_t incl = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if ((int)lane >= o) incl += t;
+        }
+        if (lane == 31) s_warp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane], wi = w;
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, wi, o);
+                if ((int)lane >= o) wi += t;
+            }
+            s_warp[lane] = wi - w;  // exclusive prefix of the warp totals
+        }
+        __syncthreads();
+        const uint32_t carry = s_carry;
+        if (i < n_blocks) block_sums[i] = carry + s_warp[warp] + incl - v;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[warp] + incl;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        info[2] = info[0];
+        info[0] = s_carry;
+    }
+}
+
+__global__ void __launch_bounds__(256) bitmap_compact_kernel(const uint32_t *__restrict__ bitmap,
+                                                             const uint32_t *__restrict__ mask, const u64 n_words,
+                                                             const uint32_t *__restrict__ block_offsets,
+                                                             uint32_t *__restrict__ out_rows) {
+    __shared__ uint32_t s_warp[8];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const u64 w0 = ((u64)blockIdx.x * 256 + tid) * BM_WORDS_PER_THREAD;
+    uint32_t bits[BM_WORDS_PER_THREAD];
+    uint32_t cnt = 0;
+#pragma unroll
+    for (uint32_t i = 0; i < BM_WORDS_PER_THREAD; ++i) {
+        bits[i] = (w0 + i < n_words) ? (bitmap[w0 + i] & (mask ? mask[w0 + i] : 0xFFFFFFFFu)) : 0u;
+        cnt += __popc(bits[i]);
+    }
+    uint32_t incl = cnt;
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((int)lane >= o) incl += t;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    uint32_t off = block_offsets[blockIdx.x] + incl - cnt;
+    for (uint32_t w = 0; w < warp; ++w) off += s_warp[w];
+#pragma unroll
+    for (uint32_t i = 0; i < BM_WORDS_PER_THREAD; ++i) {
+        uint32_t b = bits[i];
+        while (b) {
+            const uint32_t j = __ffs(b) - 1;
+            out_rows[off++] = (uint32_t)((w0 + i) << 5) + j;
+            b &= b - 1;
+        }
+    }
+}
+
 // find_closest_centroids (src/ivf/index.rs:130-149) on the device: stable ascending sort of the C query-centroid
 // distances, keep the first nprobe.  For distances that are not NaN (sums of squares: >= +0, or +inf) the stable
 // sort under partial_cmp is the sort by (distance bits, cluster index); a NaN distance raises *nan_flag and the caller

@@ -187,9 +187,8 @@ class DataFrame:
         query = q.literal.astype(np.float32)                                 # scalar_to_f32_list, physical.rs:229
         if q.k <= 0:
             raise PqVectorError("k must be > 0")
-        cursor = CandidateCursor(len(files))
-        total = 0
-        for i, path in enumerate(files):
+        indexes = []
+        for path in files:
             if not B.has_pq_vector_index(path):
                 raise PqVectorError(f"Missing pq-vector index metadata in '{path}'")                  # index_exec.rs:116-121
             ix, column = B._resident_index(path)
@@ -197,34 +196,43 @@ class DataFrame:
                 raise PqVectorError(f"IVF index column mismatch: expected '{q.column}', found '{column}'")  # :123-129
             if ix.dim != query.size:
                 raise PqVectorError(f"Query dimension mismatch: expected {ix.dim}, got {query.size}")       # :152-158
-            cand = ix.candidate_rows(query, opt.nprobe)
-            cursor.add_candidates(i, cand)
-            total += int(cand.size)
-        target = min(opt.max_candidates if opt.max_candidates is not None else total, total)             # exec.rs:222-223
-        if len(files) == 1:      # the round-robin over one file is a prefix of its candidate list
-            per_file = [cursor.candidates[0][:target]]
+            indexes.append(ix)
+        fetched = batches = total = 0
+        results = []        # (squared distance f32, scan position, file, row)
+        if opt.max_candidates == 0:
+            pass                                                             # Some(0): target_candidates = 0, exec.rs:222-223
+        elif len(files) == 1:
+            # one file: CandidateCursor is a prefix of the candidate list -> the whole operator is ONE device round trip
+            ds, _, dim = B._resident_table(files[0], q.column)
+            r, d, total, fetched = indexes[0].vector_topk(ds, query, q.k, opt.nprobe, N.PQV_SUM_SEQ, opt.max_candidates, masks[0])
+            batches = 1 if fetched else 0
+            results = [(float(dd), i, 0, int(rr)) for i, (dd, rr) in enumerate(zip(d, r))]
         else:
+            cursor = CandidateCursor(len(files))
+            for i, ix in enumerate(indexes):
+                cand = ix.candidate_rows(query, opt.nprobe)
+                cursor.add_candidates(i, cand)
+                total += int(cand.size)
+            target = min(opt.max_candidates if opt.max_candidates is not None else total, total)         # exec.rs:222-223
             per_file = [[] for _ in files]
             for f, r in cursor.next_batch(target):
                 per_file[f].append(r)
-        fetched = batches = 0
-        results = []        # (squared distance f32, scan position, file, row)
-        pos0 = 0
-        for f, path in enumerate(files):
-            rows = np.unique(np.asarray(per_file[f], dtype=np.uint32))       # RowSelection: file order, access.rs:107-176
-            if masks[f] is not None and rows.size:
-                rows = rows[masks[f][rows]]                                    # FilterExec above the scan
-            if rows.size == 0:
-                continue
-            ds, _, dim = B._resident_table(path, q.column)
-            if dim != query.size:
-                continue                                                       # rows of another length are skipped, exec.rs:526-528
-            r, d = ds.l2_topk_gather(query, rows, q.k, N.PQV_SUM_SEQ)         # squared distances, reference heap order
-            fetched += int(rows.size)
-            batches += 1
-            where = np.searchsorted(rows, r)
-            results += [(float(dd), pos0 + int(w), f, int(rr)) for dd, w, rr in zip(d, where, r)]
-            pos0 += int(rows.size)
+            pos0 = 0
+            for f, path in enumerate(files):
+                rows = np.unique(np.asarray(per_file[f], dtype=np.uint32))   # RowSelection: file order, access.rs:107-176
+                if masks[f] is not None and rows.size:
+                    rows = rows[masks[f][rows]]                                # FilterExec above the scan
+                if rows.size == 0:
+                    continue
+                ds, _, dim = B._resident_table(path, q.column)
+                if dim != query.size:
+                    continue                                                   # rows of another length are skipped, exec.rs:526-528
+                r, d = ds.l2_topk_gather(query, rows, q.k, N.PQV_SUM_SEQ)     # squared distances, reference heap order
+                fetched += int(rows.size)
+                batches += 1
+                where = np.searchsorted(rows, r)
+                results += [(float(dd), pos0 + int(w), f, int(rr)) for dd, w, rr in zip(d, where, r)]
+                pos0 += int(rows.size)
         self.metrics = {"candidate_rows": total, "files": len(files), "files_scanned": len(files),
                         "embeddings_fetched": fetched, "batches_fetched": batches, "k": q.k, "nprobe": opt.nprobe,
                         "query_dim": int(query.size), "column": q.column}

@@ -280,3 +280,70 @@ def test_host_list_builder_equals_the_device_one(ctx):
     assert np.array_equal(offsets, eoff) and np.array_equal(ids, eids)
     assert all(np.all(np.diff(ids[int(offsets[c]):int(offsets[c + 1])].astype(np.int64)) > 0) for c in range(C))
     ix.drop(); ds.drop()
+
+
+# ---- VectorTopKExec over a resident indexed table in one call (pqv_vector_topk_indexed) -------------------------------
+def _expected_vector_topk(q, data, cent, offsets, ids, k, nprobe, order, do_sqrt, cap, mask):
+    cand = O.candidate_rows(q, cent, offsets, ids, nprobe)        # index_exec.rs:159-163, rank order
+    total = cand.size
+    if cap is not None:
+        cand = cand[:cap]                                         # CandidateCursor over one file = a prefix (access.rs:193-243)
+    rows = np.sort(cand)                                          # RowSelection: file order (access.rs:107-176)
+    if mask is not None:
+        rows = rows[mask[rows]]                                   # FilterExec before scoring (tests.rs:151-241)
+    er, ed = O.topk_rerank_gather(q, data, rows, k, order, do_sqrt) if rows.size else (np.empty(0, np.uint32), np.empty(0, np.float32))
+    return er, ed, total, rows.size
+
+
+@pytest.mark.parametrize("n,dim,C,grid", [(20000, 64, 64, False), (6000, 8, 37, True), (3000, 130, 5, False)])
+def test_vector_topk_indexed_matches_the_operator_semantics(ctx, n, dim, C, grid):
+    rng = np.random.default_rng(n + C)
+    # grid data: few distinct coordinates -> many bit-equal distances, so the ORDER in which rows reach the heap matters
+    data = rng.integers(0, 3, (n, dim)).astype(np.float32) if grid else rng.random((n, dim), dtype=np.float32)
+    cent = data[rng.choice(n, C, replace=False)] + (0.0 if grid else 0.01)
+    assign = O.assign(data, cent, workers=2)
+    offsets, ids = O.inverted_lists(assign, C)
+    ix = ctx.ivf_from_bytes(O.index_to_bytes(dim, cent, offsets, ids))
+    ds = ctx.dataset_from(data)
+    masks = [None, rng.random(n) < 0.5, np.zeros(n, bool), np.arange(n) >= n // 3]
+    for qi in range(3):
+        q = data[rng.integers(n)] if grid else rng.random(dim, dtype=np.float32)
+        for nprobe in (1, max(2, C // 4), C + 5):
+            for cap in (None, 1, 777, 10 ** 9):
+                for mask in masks:
+                    for k, flags in ((10, SEQ), (100, SQRT)):
+                        r, d, total, scored = ix.vector_topk(ds, q, k, nprobe, flags, cap, mask)
+                        er, ed, etotal, escored = _expected_vector_topk(q, data, cent, offsets, ids, k, nprobe,
+                                                                        1 if flags & SEQ else 0, bool(flags & SQRT), cap, mask)
+                        assert (total, scored) == (etotal, escored), (nprobe, cap)
+                        assert r.tolist() == er.tolist(), (qi, nprobe, cap, k, flags)
+                        assert d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+    ix.drop()
+    ds.drop()
+
+
+def test_vector_topk_indexed_reference_examples_and_fallback(ctx):
+    import pq_vector_b200 as P
+    # df_vector/tests.rs:31-39 and :166-174 with their filters as row masks
+    for rows, min_id, expect, fetched in [([(0, 0), (1, 0), (0, 2), (5, 5), (2, 2), (.1, .1)], 2, [5, 2], 4),
+                                          ([(0, 0), (.05, .05), (.2, .2), (1, 1), (1.1, 1.1), (1.4, 1.4)], 3, [3, 4], 3)]:
+        data = np.array(rows, np.float32)
+        cent = data[[0, 3, 4]].copy()
+        offsets, ids = O.inverted_lists(O.assign(data, cent), 3)
+        ix = ctx.ivf_from_bytes(O.index_to_bytes(2, cent, offsets, ids))
+        ds = ctx.dataset_from(data)
+        r, d, total, scored = ix.vector_topk(ds, np.zeros(2, np.float32), 2, 64, SEQ, None, np.arange(6) >= min_id)
+        assert r.tolist() == expect and (total, scored) == (6, fetched)
+        # a NaN centroid distance: the device ranking declines, the host-ranked path must give the same selection
+        c2 = cent.copy()
+        c2[1, 0] = np.nan
+        ix2 = ctx.ivf_from_bytes(O.index_to_bytes(2, c2, offsets, ids))
+        r2, _, total2, _ = ix2.vector_topk(ds, np.zeros(2, np.float32), 2, 64, SEQ, None, np.arange(6) >= min_id)
+        assert r2.tolist() == expect and total2 == 6
+        with pytest.raises(P.PqvError, match="row_mask has"):
+            ix.vector_topk(ds, np.zeros(2, np.float32), 2, 64, SEQ, None, np.ones(5, bool))
+        with pytest.raises(P.PqvError, match="nprobe must be > 0"):
+            ix.vector_topk(ds, np.zeros(2, np.float32), 2, 0)
+        ix.drop()
+        ix2.drop()
+        ds.drop()
