@@ -271,6 +271,19 @@ PQV_API int pqv_bench_assign(pqv_ctx *ctx, uint64_t handle, uint64_t n, const fl
 PQV_API int pqv_bench_scan(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags,
                    uint32_t iters, double *out_ms_per_scan);
 
+/* IVF search with the rows sharded over ranks ("the index is replicated; each rank filters candidate
+ * ids to its row range").  Each rank loads the index restricted to its slice (same centroids, every list cut to the rank's
+ * row range with local ids: pq_vector_b200/sharded.py) and calls pqv_ivf_search_candidates: the per-rank half of
+ * pqv_ivf_search -- ranking, expansion, gathered scan, entrant filter -- returning the heap-entrant keys
+ * (bits(squared distance) << 32 | position in THIS rank's candidate sequence), their local row ids and the probed
+ * clusters in rank order (out_probe, min(nprobe, C) entries).  Lists are ascending and slices contiguous, so the global
+ * candidate sequence of src/ivf/index.rs:57-63 is, list by list, rank 0's part, rank 1's part, ...: the ranks translate
+ * positions with the per-list per-rank counts, exchange the keys with ONE all-gather and replay the reference heap
+ * (pqv_replay_candidates).  PQV_ELIMIT with *out_count = the number needed when `cap` is too small. */
+PQV_API int pqv_ivf_search_candidates(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k,
+                              uint32_t nprobe, uint32_t flags, uint64_t *out_keys, uint32_t *out_rows, uint64_t cap,
+                              uint64_t *out_count, uint32_t *out_probe, uint32_t *out_nprobe_eff);
+
 /* ---- VectorTopKExec over a resident, indexed table in ONE call ------------------------------------
  * Replaces execute_with_candidates + topk_from_batches (src/df_vector/exec.rs:207-277) when the file's embedding column
  * and index are resident (pqv_dataset_*, pqv_ivf_from_bytes): the index's candidate rows for `nprobe`

@@ -91,6 +91,8 @@ SIGNATURES = {
     "pqv_bench_assign": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32,
                                    C.POINTER(PqvAssignTiming), u32p]),
     "pqv_bench_scan": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, f64p]),
+    "pqv_ivf_search_candidates": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p,
+                                            C.c_uint64, u64p, u32p, u32p]),
     "pqv_vector_topk_indexed": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                           C.POINTER(C.c_uint8), u32p, f32p, u32p, u64p, u64p]),
     "pqv_l2_topk_coalesced": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),

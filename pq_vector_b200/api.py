@@ -417,6 +417,26 @@ class IvfIndex:
                                    _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), C.byref(cnt)))
         return rows[:cnt.value].copy(), dist[:cnt.value].copy()
 
+    def search_candidates(self, dataset: "Dataset", query, k: int, nprobe: int, flags: int = N.PQV_SQRT, cap: int = 1 << 16):
+        """Per-rank half of a sharded IVF search (pqv_ivf_search_candidates): (keys u64 with positions in this rank's
+        candidate sequence, local row ids u32, probed clusters in rank order)."""
+        q = _f32(query)
+        if q.size != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.size}")
+        while True:
+            keys = np.empty(cap, dtype=np.uint64)
+            rows = np.empty(cap, dtype=np.uint32)
+            probe = np.empty(max(self.n_clusters, 1), dtype=np.uint32)
+            n, npe = C.c_uint64(), C.c_uint32()
+            rc = _lib.pqv_ivf_search_candidates(self.ctx._h, dataset.handle, self.handle, _ptr(q, C.c_float), k, nprobe, flags,
+                                                _ptr(keys, C.c_uint64), _ptr(rows, C.c_uint32), cap, C.byref(n),
+                                                _ptr(probe, C.c_uint32), C.byref(npe))
+            if rc == N.PQV_ELIMIT and n.value > cap:
+                cap = int(n.value)
+                continue
+            _check(rc)
+            return keys[:n.value].copy(), rows[:n.value].copy(), probe[:npe.value].copy()
+
     def vector_topk(self, dataset: "Dataset", query, k: int, nprobe: int, flags: int = N.PQV_SUM_SEQ,
                     max_candidates=None, row_mask=None):
         """VectorTopKExec over a resident indexed table (pqv_vector_topk_indexed): candidates capped in rank order,

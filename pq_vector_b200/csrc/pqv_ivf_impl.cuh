@@ -247,10 +247,18 @@ struct RowOrder {
     u64 candidate_rows = 0;           // out: probed candidates before cap and filter
     u64 rows_scored = 0;              // out
 };
+// EntrantsOut != nullptr: return the heap-entrant keys (bits(d) << 32 | candidate position), their row ids and the probed
+// clusters in rank order instead of replaying the heap (one process per GPU: the replay happens over all ranks' entrants)
+struct EntrantsOut {
+    std::vector<u64> keys;
+    std::vector<uint32_t> rows;
+    std::vector<uint32_t> probe;
+    u64 n_cand = 0;
+};
 
 int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, const float *query, uint32_t k,
                      uint32_t nprobe, uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
-                     bool *done, RowOrder *ro = nullptr) {
+                     bool *done, RowOrder *ro = nullptr, EntrantsOut *eo = nullptr) {
     *done = false;
     static const bool trace = getenv("PQV_TRACE") != nullptr;
     double tt[8] = {0};
@@ -318,6 +326,10 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
     CU_TRY(cudaMemcpyAsync(D.h_ent_out.p, D.ent_out.p, ((size_t)first + 1) * 8, cudaMemcpyDeviceToHost, D.stream));
     CU_TRY(cudaMemcpyAsync(D.h_ent_rows.p, D.ent_rows.p, (size_t)first * 4, cudaMemcpyDeviceToHost, D.stream));
     CU_TRY(cudaMemcpyAsync(D.h_ivf_info.p, D.ivf_info.p, 32, cudaMemcpyDeviceToHost, D.stream));
+    if (eo) {
+        eo->probe.resize(np);
+        CU_TRY(cudaMemcpyAsync(eo->probe.data(), ix.d_probe_cluster.p, (size_t)np * 4, cudaMemcpyDeviceToHost, D.stream));
+    }
     if (trace) tt[3] = now_ms();
     CU_TRY(cudaStreamSynchronize(D.stream));
     if (trace) tt[4] = now_ms();
@@ -336,6 +348,13 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
         CU_TRY(cudaMemcpyAsync(entrants.data() + got, D.ent_out.p + 1 + got, (count - got) * 8, cudaMemcpyDeviceToHost, D.stream));
         CU_TRY(cudaMemcpyAsync(erows.data() + got, D.ent_rows.p + got, (count - got) * 4, cudaMemcpyDeviceToHost, D.stream));
         CU_TRY(cudaStreamSynchronize(D.stream));
+    }
+    if (eo) {
+        eo->keys.swap(entrants);
+        eo->rows.swap(erows);
+        eo->n_cand = n_cand;
+        *done = true;
+        return PQV_OK;
     }
     size_t cnt = 0;
     const bool fast = !(flags & PQV_TIES_BY_POSITION) &&
@@ -918,6 +937,57 @@ int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *q
     };
     return topk_one(ctx, *ds, query, nullptr, n_cand, k, flags, out_row_idx, out_dist, out_count, nullptr, 0,
                     ix->d_cand.p, &row_fn);
+}
+
+int pqv_ivf_search_candidates(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k, uint32_t nprobe,
+                              uint32_t flags, uint64_t *out_keys, uint32_t *out_rows, uint64_t cap, uint64_t *out_count,
+                              uint32_t *out_probe, uint32_t *out_nprobe_eff) {
+    if (!ctx || !query || !out_count || !out_probe || !out_nprobe_eff || (cap && (!out_keys || !out_rows))) return fail(PQV_EINVAL, "null argument");
+    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (flags & PQV_TIES_BY_POSITION) return fail(PQV_EINVAL, "candidates are only defined for the reference tie order");
+    if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search_candidates needs a single-device dataset");
+    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    DeviceState &D = ctx->devs[ds->shards[0].di];
+    DevGuard guard(D.dev);
+    PQV_TRY(index_make_resident(D, *ix));
+    EntrantsOut eo;
+    bool done = false;
+    if (ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids) {
+        uint32_t dummy_rows[1], dummy_cnt = 0;
+        float dummy_dist[1];
+        PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, query, k, nprobe, flags, dummy_rows, dummy_dist, &dummy_cnt, &done, nullptr, &eo));
+    }
+    if (!done) {  // host-ranked path: NaN centroid distance, entrant overflow, empty or very wide index
+        PQV_TRY(index_host_ids(D, *ix));
+        PQV_TRY(rank_clusters(D, *ix, query, nprobe, eo.probe));
+        std::vector<uint32_t> rows;
+        for (uint32_t c : eo.probe) rows.insert(rows.end(), ix->ids.begin() + ix->offsets[c], ix->ids.begin() + ix->offsets[c + 1]);
+        eo.keys.clear();
+        eo.rows.clear();
+        if (!rows.empty()) {
+            for (uint32_t r : rows)
+                if (r >= ds->n_rows) return fail(PQV_EINVAL, "row id %u is out of range (%llu rows)", r, (unsigned long long)ds->n_rows);
+            PQV_TRY(topk_one(ctx, *ds, query, rows.data(), rows.size(), k, flags, nullptr, nullptr, nullptr, &eo.keys, 0));
+            eo.rows.resize(eo.keys.size());
+            for (size_t i = 0; i < eo.keys.size(); ++i) eo.rows[i] = rows[key_pos(eo.keys[i])];
+        }
+    }
+    *out_nprobe_eff = (uint32_t)eo.probe.size();
+    memcpy(out_probe, eo.probe.data(), eo.probe.size() * 4);
+    *out_count = eo.keys.size();
+    if (eo.keys.size() > cap) return fail(PQV_ELIMIT, "%zu candidate keys do not fit the caller's buffer of %llu", eo.keys.size(), (unsigned long long)cap);
+    if (!eo.keys.empty()) {
+        memcpy(out_keys, eo.keys.data(), eo.keys.size() * 8);
+        memcpy(out_rows, eo.rows.data(), eo.rows.size() * 4);
+    }
+    return PQV_OK;
 }
 
 int pqv_vector_topk_indexed(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k, uint32_t nprobe,

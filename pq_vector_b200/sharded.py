@@ -277,3 +277,98 @@ class ShardedArrayDistanceTopk:
         all_d = np.concatenate([got[r, 1 + k:1 + k + int(got[r, 0])] for r in range(got.shape[0])]).view(np.float64)
         order = np.lexsort((all_rows, self._ordered(all_d)))[:k]
         return all_rows[order], all_d[order]
+
+
+# ---- IVF search over row-range shards ----------------------------------------------------------
+def shard_counts(offsets: np.ndarray, ids: np.ndarray, bounds) -> np.ndarray:
+    """counts[c, s] = rows of inverted list c that fall into shard s = [bounds[s], bounds[s+1]) (lists are ascending,
+    src/ivf/index.rs:202-206, so every list is cut by binary search)."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    C, world = offsets.size - 1, len(bounds) - 1
+    counts = np.zeros((C, world), dtype=np.int64)
+    b = np.asarray(bounds, dtype=np.int64)
+    for c in range(C):
+        cut = np.searchsorted(ids[offsets[c]:offsets[c + 1]], b, side="left")
+        counts[c] = np.diff(cut)
+    return counts
+
+
+def shard_index(offsets: np.ndarray, ids: np.ndarray, lo: int, hi: int):
+    """The index restricted to rows [lo, hi): every list cut to the range, ids made local (minus lo).  Same cluster
+    numbering, so the centroid ranking of a query is identical on every rank."""
+    offsets = np.asarray(offsets, dtype=np.int64)
+    keep = (ids >= lo) & (ids < hi)
+    local_ids = (ids[keep].astype(np.int64) - lo).astype(np.uint32)
+    cs = np.concatenate([[0], np.cumsum(keep.astype(np.int64))])
+    per_list = cs[offsets[1:]] - cs[offsets[:-1]]
+    local_offsets = np.concatenate([[0], np.cumsum(per_list)]).astype(np.uint64)
+    return local_offsets, local_ids
+
+
+class ShardedIvfSearch:
+    """TopkBuilder::search (src/ivf/search.rs:83-142) with the table's rows sharded over ranks and the index replicated:
+    rank s scans only the candidates inside its row range (IvfIndex.search_candidates over its slice and the index cut to
+    the slice), ONE all-gather moves the heap-entrant keys, every rank replays the reference heap over the union.
+    The global candidate sequence (index.rs:57-63) is, probed list by probed list, rank 0's rows, rank 1's rows, ...
+    (ascending lists, contiguous slices), so a local candidate position translates to its global position with the
+    per-list per-rank counts alone."""
+
+    def __init__(self, cand_fn, counts: np.ndarray, rank: int, lo: int, device: "torch.device | str" = "cpu", group=None,
+                 cap: int = DEFAULT_CAP):
+        """cand_fn(query, k, nprobe, flags) -> (keys u64, local row ids u32, probed clusters in rank order)."""
+        self.cand_fn = cand_fn
+        self.counts = np.asarray(counts, dtype=np.int64)
+        self.rank, self.lo = int(rank), int(lo)
+        self.device = torch.device(device)
+        self.group = group
+        self.cap = cap
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.last_gather_bytes = 0
+
+    def translate(self, keys: np.ndarray, probe: np.ndarray) -> "tuple[np.ndarray, int]":
+        """local candidate positions -> global candidate positions; returns (keys with global positions, total candidates)"""
+        cnt = self.counts[np.asarray(probe, dtype=np.int64)]                 # [np, world]
+        lens = cnt.sum(axis=1)
+        base = np.concatenate([[0], np.cumsum(lens)[:-1]]) if lens.size else np.zeros(0, np.int64)
+        within = cnt[:, :self.rank].sum(axis=1)
+        lp = np.concatenate([[0], np.cumsum(cnt[:, self.rank])])
+        pos = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        r = np.searchsorted(lp, pos, side="right") - 1
+        gpos = base[r] + within[r] + (pos - lp[r])
+        return (keys & np.uint64(0xFFFFFFFF00000000)) | gpos.astype(np.uint64), int(lens.sum())
+
+    def _exchange(self, keys: np.ndarray, rows: np.ndarray, cap: int):
+        n = int(keys.size)
+        send = np.zeros(1 + 2 * cap, dtype=np.int64)
+        send[0] = n
+        m = min(n, cap)
+        send[1:1 + m] = keys[:m].view(np.int64)
+        send[1 + cap:1 + cap + m] = rows[:m]
+        if self.world > 1:
+            t_send = torch.from_numpy(send).to(self.device)
+            t_recv = torch.empty(self.world * send.size, dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(t_recv, t_send, group=self.group)
+            got = t_recv.cpu().numpy().reshape(self.world, send.size)
+        else:
+            got = send[None, :]
+        self.last_gather_bytes = got.nbytes if self.world > 1 else 0
+        counts = got[:, 0]
+        if int(counts.max()) > cap:
+            return None, None, int(counts.max())
+        k_all = np.concatenate([got[s, 1:1 + int(counts[s])] for s in range(got.shape[0])]).view(np.uint64)
+        r_all = np.concatenate([got[s, 1 + cap:1 + cap + int(counts[s])] for s in range(got.shape[0])]).astype(np.uint32)
+        return k_all, r_all, 0
+
+    def search(self, query, k: int, nprobe: int, flags: int):
+        keys, rows, probe = self.cand_fn(query, k, nprobe, flags)
+        gkeys, n_total = self.translate(np.ascontiguousarray(keys, dtype=np.uint64), probe)
+        grows = rows.astype(np.int64) + self.lo
+        k_all, r_all, need = self._exchange(gkeys, grows, self.cap)
+        if k_all is None:  # a rank had more entrants than the default payload: one more round, sized to fit
+            k_all, r_all, need = self._exchange(gkeys, grows, need)
+            assert k_all is not None
+        if n_total == 0 or k_all.size == 0:
+            return np.empty(0, np.uint32), np.empty(0, np.float32)
+        row_of = np.zeros(n_total, dtype=np.uint32)          # candidate position -> row id, filled for the entrants only
+        row_of[(k_all & np.uint64(0xFFFFFFFF)).astype(np.int64)] = r_all
+        return replay_candidates(k_all, k, flags, row_ids=row_of)

@@ -347,3 +347,53 @@ def test_vector_topk_indexed_reference_examples_and_fallback(ctx):
         ix.drop()
         ix2.drop()
         ds.drop()
+
+
+# ---- IVF search with the rows sharded over ranks (pqv_ivf_search_candidates + ShardedIvfSearch.translate) --------------
+@pytest.mark.parametrize("n,dim,C,grid", [(30000, 64, 48, False), (9000, 8, 21, True)])
+def test_sharded_ivf_search_pieces_equal_the_whole_table_search(ctx, n, dim, C, grid):
+    """Three slices of one table on one GPU stand in for three ranks: per-slice entrant candidates, positions translated
+    to the global candidate sequence, union replayed -> exactly TopkBuilder's answer over the whole table."""
+    import pq_vector_b200 as P
+    from pq_vector_b200.sharded import ShardedIvfSearch, index_to_bytes, shard_counts, shard_index
+    rng = np.random.default_rng(n)
+    data = rng.integers(0, 3, (n, dim)).astype(np.float32) if grid else rng.random((n, dim), dtype=np.float32)
+    cent = data[rng.choice(n, C, replace=False)].copy()
+    offsets, ids = O.inverted_lists(O.assign(data, cent, workers=2), C)
+    bounds = [0, n // 5, n // 2, n]
+    counts = shard_counts(offsets, ids, bounds)
+    parts = []
+    for s in range(3):
+        lo, hi = bounds[s], bounds[s + 1]
+        l_off, l_ids = shard_index(offsets, ids, lo, hi)
+        ix = ctx.ivf_from_bytes(index_to_bytes(cent, l_off, l_ids))
+        ds = ctx.dataset_from(data[lo:hi])
+        parts.append((ix, ds, ShardedIvfSearch(None, counts, s, lo)))
+    whole_ix = ctx.ivf_from_bytes(O.index_to_bytes(dim, cent, offsets, ids))
+    whole_ds = ctx.dataset_from(data)
+    for qi in range(4):
+        q = data[rng.integers(n)] if grid else rng.random(dim, dtype=np.float32)
+        for nprobe in (1, 5, C):
+            for k, flags in ((10, SQRT), (100, SEQ)):
+                k_all, r_all, total = [], [], 0
+                for ix, ds, sh in parts:
+                    keys, rows, probe = ix.search_candidates(ds, q, k, nprobe, flags)
+                    gk, total = sh.translate(keys, probe)
+                    k_all.append(gk)
+                    r_all.append(rows.astype(np.int64) + sh.lo)
+                k_all, r_all = np.concatenate(k_all), np.concatenate(r_all).astype(np.uint32)
+                row_of = np.zeros(max(total, 1), np.uint32)
+                row_of[(k_all & np.uint64(0xFFFFFFFF)).astype(np.int64)] = r_all
+                r, d = P.replay_candidates(k_all, k, flags, row_ids=row_of)
+                cand = O.candidate_rows(q, cent, offsets, ids, nprobe)
+                assert total == cand.size
+                er, ed = O.topk_rerank_gather(q, data, cand, k, 1 if flags & SEQ else 0, bool(flags & SQRT))
+                assert r.tolist() == er.tolist(), (qi, nprobe, k)
+                assert d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+                wr, wd = whole_ix.search(whole_ds, q, k, nprobe, flags)
+                assert wr.tolist() == r.tolist()
+    for ix, ds, _ in parts:
+        ix.drop()
+        ds.drop()
+    whole_ix.drop()
+    whole_ds.drop()

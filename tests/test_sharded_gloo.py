@@ -179,3 +179,46 @@ def test_two_rank_array_distance_topk(tmp_path, n, dim, k, seed):
     mp.spawn(_adist_worker, args=(2, port, n, dim, k, seed, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
+
+
+def _ivf_worker(rank, world, port, n, dim, C, k, nprobe, flags, seed, out_dir):
+    sys.path.insert(0, ROOT)
+    import oracle as O
+    from pq_vector_b200.sharded import ShardedIvfSearch, shard_counts, shard_index
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    data = rng.integers(0, 3, (n, dim)).astype(np.float32) if seed % 2 else rng.random((n, dim), dtype=np.float32)
+    cent = data[rng.choice(n, C, replace=False)].copy()
+    offsets, ids = O.inverted_lists(O.assign(data, cent), C)
+    q = data[5].copy() if seed % 2 else rng.random(dim, dtype=np.float32)
+    per = (n + world - 1) // world
+    bounds = [min(n, s * per) for s in range(world + 1)]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    l_off, l_ids = shard_index(offsets, ids, lo, hi)
+    order = 1 if flags & 1 else 0
+
+    def cand(query, k_, nprobe_, flags_):       # the oracle standing in for IvfIndex.search_candidates on this rank's slice
+        probe = O.find_closest_centroids(query, cent, nprobe_)
+        rows = O.candidate_rows(query, cent, l_off, l_ids, nprobe_)
+        d = O.distances(data[lo:hi][rows], query, order) if rows.size else np.empty(0, np.float32)
+        keys = (d.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.arange(rows.size, dtype=np.uint64)
+        return keys, rows, probe
+
+    st = ShardedIvfSearch(cand, shard_counts(offsets, ids, bounds), rank, lo, "cpu", cap=64 if seed == 5 else 4096)
+    rows, dd = st.search(q, k, nprobe, flags)
+    er, ed = O.topk_rerank_gather(q, data, O.candidate_rows(q, cent, offsets, ids, nprobe), k, order, bool(flags & 2))
+    ok = rows.tolist() == er.tolist() and dd.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,dim,C,k,nprobe,flags,seed", [(2000, 8, 16, 10, 4, 2, 2), (3000, 4, 9, 100, 3, 1, 3),
+                                                          (900, 6, 30, 50, 30, 3, 5), (40, 3, 7, 10, 2, 2, 6)])
+def test_two_rank_ivf_search(tmp_path, n, dim, C, k, nprobe, flags, seed):
+    port = 33500 + (os.getpid() + seed) % 2000
+    mp.spawn(_ivf_worker, args=(2, port, n, dim, C, k, nprobe, flags, seed, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
