@@ -37,12 +37,6 @@ constexpr int ADIST_WARPS = 8;
 constexpr int ADIST_TILE_BYTES = 32 * ADIST_TSTRIDE * 4;  // 8704 B per warp
 constexpr uint32_t ADIST_QSMEM_MAX_DIM = 4096;            // f64 query staged in shared memory up to here (32 KB)
 
-__device__ __forceinline__ float2 ld_stream_v2(const float *p) {
-    float2 r;
-    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
-    return r;
-}
-
 // One warp owns 32 consecutive rows.  Per 64-column block all lanes load the rows coalesced (16 rows x 2 halves kept in
 // registers), park the RAW f32 values in the warp's padded shared-memory tile, and lane r then walks row r: widen to
 // f64, subtract, square (independent, they run ahead) and the serial f64 add chain in element order.  The loads of the

@@ -28,6 +28,11 @@ __device__ __forceinline__ float4 ld_stream_v4(const float *p) {
                  : "l"(p));
     return r;
 }
+__device__ __forceinline__ float2 ld_stream_v2(const float *p) {
+    float2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
 __device__ __forceinline__ float ld_stream_f32(const float *p) {
     float r;
     asm volatile("ld.global.nc.L1::no_allocate.f32 %0, [%1];" : "=f"(r) : "l"(p));
@@ -53,13 +58,15 @@ __device__ __forceinline__ float sq1(const float a, const float b) {
 //   ORDER 1: sequential,     diff = row - s_vec             (exec.rs:531    value - q)
 //   VEC4   : dim % 4 == 0 and 16-byte aligned rows -> 128-bit loads; otherwise scalar loads.
 //   GATHER : row index taken from row_ids[position].
-// tile: per-warp shared memory, 32 rows x TSTRIDE floats (TSTRIDE = 36, or 132 for ORDER 1 + VEC4).
+// tile: per-warp shared memory, 32 rows x TSTRIDE floats (TSTRIDE = 36, or 68 for ORDER 1 + VEC4).
 // ------------------------------------------------------------------------------------------------
 // CBV = float4 loads per lane per row per column block (ORDER 0 + VEC4 only): a warp then reads CBV*512
 // contiguous bytes of a row per block.
 template <int ORDER, bool VEC4, int CBV = 1>
 struct TileCfg {
-    static constexpr int TERMS = (ORDER == 1 && VEC4) ? 4 : CBV;  // chain terms per lane per column block
+    // ORDER 1 (sequential sum, every element its own chain term): 64-column blocks, 2 terms per lane, so that the tile is
+    // 8.7 KB per warp and two CTAs fit an SM (with 128-column blocks = 16.9 KB per warp only one did: 3.4 TB/s)
+    static constexpr int TERMS = (ORDER == 1 && VEC4) ? 2 : CBV;  // chain terms per lane per column block
     static constexpr int TSTRIDE = 32 * TERMS + 4;                // floats; /4 is odd -> LDS.128 conflict-free
     static constexpr int TILE_FLOATS = 32 * TSTRIDE;
 };
@@ -87,7 +94,60 @@ __device__ __forceinline__ float group_distance(const float *__restrict__ data,
     float sum = 0.0f;
     float *trow = tile + lane * TSTRIDE;
 
-    if constexpr (VEC4) {
+    if constexpr (VEC4 && ORDER == 1) {
+        // sequential order: 64-column blocks, one 64-bit load per lane and row (a warp reads 256 contiguous bytes of a
+        // row), 2 chain terms per lane; RB rows in flight
+        constexpr uint32_t BLK = 64u;
+        const uint32_t ncb = (dim + BLK - 1) / BLK;
+        for (uint32_t cb = 0; cb < ncb; ++cb) {
+            const uint32_t col0 = cb * BLK + (lane << 1);
+            const bool inb = col0 < dim;  // dim % 4 == 0: both columns of the pair are in range together
+            float2 q2 = make_float2(0.f, 0.f);
+            if (inb) q2 = *reinterpret_cast<const float2 *>(s_vec + col0);
+            // dense: rows of the group are dim floats apart from gp; the table's last group clamps to its last row
+            // (32-bit offsets: 32 rows x dim <= 2^19 floats)
+            const float *gp = data + g_first * dim + col0;
+            const uint32_t last_rel = (uint32_t)((n - 1 - g_first) < 31 ? (n - 1 - g_first) : 31);
+#pragma unroll
+            for (int r0 = 0; r0 < 32; r0 += 2 * RB) {
+                float2 v2[2 * RB];
+#pragma unroll
+                for (int j = 0; j < 2 * RB; ++j) {
+                    const float *rp;
+                    if constexpr (GATHER) {
+                        rp = data + (u64)__shfl_sync(0xffffffffu, (uint32_t)my_row, r0 + j) * dim + col0;
+                    } else {
+                        const uint32_t rel = (uint32_t)(r0 + j) < last_rel ? (uint32_t)(r0 + j) : last_rel;
+                        rp = gp + rel * dim;
+                    }
+                    v2[j] = make_float2(0.f, 0.f);
+                    if (inb) v2[j] = ld_stream_v2(rp);
+                }
+#pragma unroll
+                for (int j = 0; j < 2 * RB; ++j) {
+                    float2 p;
+                    p.x = sq1(v2[j].x, q2.x);
+                    p.y = sq1(v2[j].y, q2.y);
+                    *reinterpret_cast<float2 *>(tile + (r0 + j) * TSTRIDE + (lane << 1)) = p;
+                }
+            }
+            __syncwarp();
+            const uint32_t rem = dim - cb * BLK;  // elements left in this block (multiple of 4)
+            if (rem >= BLK) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    const float4 t = *reinterpret_cast<const float4 *>(trow + 4 * j);
+                    sum = __fadd_rn(sum, t.x);
+                    sum = __fadd_rn(sum, t.y);
+                    sum = __fadd_rn(sum, t.z);
+                    sum = __fadd_rn(sum, t.w);
+                }
+            } else {
+                for (uint32_t j = 0; j < rem; ++j) sum = __fadd_rn(sum, trow[j]);
+            }
+            __syncwarp();
+        }
+    } else if constexpr (VEC4) {
         constexpr uint32_t BLK = 128u * CBV;  // columns per block
         const uint32_t ncb = (dim + BLK - 1) / BLK;
         for (uint32_t cb = 0; cb < ncb; ++cb) {
