@@ -247,22 +247,27 @@ int pqv_l2_topk_coalesced(pqv_ctx *ctx, uint64_t handle, const float *query, uin
     const uint32_t nq = (uint32_t)batch.size();
     int rc = PQV_OK;
     std::string err;
-    if (nq == 1) {
-        rc = pqv_l2_topk(ctx, handle, query, 1, k, flags, out_row_idx, out_dist, out_count);
-        if (rc) err = g_err;
-    } else {
-        std::vector<float> q((size_t)nq * dim);
-        std::vector<uint32_t> rows((size_t)nq * k), counts(nq);
-        std::vector<float> dist((size_t)nq * k);
-        for (uint32_t i = 0; i < nq; ++i) memcpy(q.data() + (size_t)i * dim, batch[i]->query, (size_t)dim * 4);
-        rc = pqv_l2_topk(ctx, handle, q.data(), nq, k, flags, rows.data(), dist.data(), counts.data());
-        if (rc) err = g_err;
-        else
-            for (uint32_t i = 0; i < nq; ++i) {
-                memcpy(batch[i]->rows, rows.data() + (size_t)i * k, (size_t)counts[i] * 4);
-                memcpy(batch[i]->dist, dist.data() + (size_t)i * k, (size_t)counts[i] * 4);
-                *batch[i]->count = counts[i];
-            }
+    try {  // nothing may escape before the followers are released below
+        if (nq == 1) {
+            rc = pqv_l2_topk(ctx, handle, query, 1, k, flags, out_row_idx, out_dist, out_count);
+            if (rc) err = g_err;
+        } else {
+            std::vector<float> q((size_t)nq * dim);
+            std::vector<uint32_t> rows((size_t)nq * k), counts(nq);
+            std::vector<float> dist((size_t)nq * k);
+            for (uint32_t i = 0; i < nq; ++i) memcpy(q.data() + (size_t)i * dim, batch[i]->query, (size_t)dim * 4);
+            rc = pqv_l2_topk(ctx, handle, q.data(), nq, k, flags, rows.data(), dist.data(), counts.data());
+            if (rc) err = g_err;
+            else
+                for (uint32_t i = 0; i < nq; ++i) {
+                    memcpy(batch[i]->rows, rows.data() + (size_t)i * k, (size_t)counts[i] * 4);
+                    memcpy(batch[i]->dist, dist.data() + (size_t)i * k, (size_t)counts[i] * 4);
+                    *batch[i]->count = counts[i];
+                }
+        }
+    } catch (const std::exception &e) {
+        rc = PQV_ENOMEM;
+        err = std::string("coalesced batch failed: ") + e.what();
     }
 
     lk.lock();
