@@ -341,6 +341,7 @@ struct PinBuf {
 
 constexpr uint32_t ENT_FIRST_CHUNK = 8192;  // entrant keys fetched with the first D2H (64 KiB)
 
+struct AppendPool;
 struct DeviceState {
     int dev = 0;
     int sm_count = 0;
@@ -371,6 +372,15 @@ struct DeviceState {
     DevBuf<u64> ivf_info;
     PinBuf<uint32_t> h_ent_rows;
     PinBuf<u64> h_ivf_info;
+    // table load (pqv_dataset_append of a large pageable buffer): independent double-buffered staging lanes, one host
+    // thread each (append_staged)
+    struct AppendLane {
+        cudaStream_t st = nullptr;
+        cudaEvent_t ev[2] = {nullptr, nullptr};
+        PinBuf<unsigned char> buf[2];
+    };
+    std::vector<AppendLane> lanes;
+    AppendPool *pool = nullptr;  // persistent copy threads, created on the first large append
     // VectorTopKExec candidate handling (ivf_mark / bitmap_* kernels): candidate bitmap, filter bitmap, block sums
     DevBuf<uint32_t> vt_bitmap, vt_mask, vt_sums;
     // un-indexed array_distance arm (pqv_adist.cuh): f64 query, f64 distance column, radix-select state, k winners
@@ -380,6 +390,68 @@ struct DeviceState {
     PinBuf<double> h_ad_dist;
     PinBuf<uint32_t> h_ad_row;
     PinBuf<pqv::SelState> h_ad_state;
+};
+
+constexpr size_t APPEND_CHUNK = 8u << 20;
+constexpr size_t APPEND_STAGED_MIN = 32u << 20;
+constexpr size_t APPEND_MAX_LANES = 8;
+
+// persistent worker threads (thread creation + the CUDA runtime's per-thread set-up cost ~10 ms per call otherwise)
+struct AppendPool {
+    std::vector<std::thread> th;
+    std::mutex m;
+    std::condition_variable cv_job, cv_done;
+    u64 job_id = 0;
+    size_t pending = 0;
+    bool stop = false;
+    // the current job
+    DeviceState *D = nullptr;
+    unsigned char *dst = nullptr;
+    const unsigned char *src = nullptr;
+    size_t bytes = 0, n_chunks = 0, T = 0;
+    cudaError_t errs[APPEND_MAX_LANES];
+
+    void lane_run(size_t t) {
+        DeviceState::AppendLane &L = D->lanes[t];
+        cudaError_t e = cudaSuccess;
+        size_t turn = 0;
+        for (size_t c = t; c < n_chunks && e == cudaSuccess; c += T, ++turn) {
+            const int b = (int)(turn & 1);
+            const size_t off = c * APPEND_CHUNK, len = std::min(APPEND_CHUNK, bytes - off);
+            e = cudaEventSynchronize(L.ev[b]);  // the DMA that last read this staging buffer is done
+            if (e != cudaSuccess) break;
+            memcpy(L.buf[b].p, src + off, len);
+            e = cudaMemcpyAsync(dst + off, L.buf[b].p, len, cudaMemcpyHostToDevice, L.st);
+            if (e == cudaSuccess) e = cudaEventRecord(L.ev[b], L.st);
+        }
+        const cudaError_t s2 = cudaStreamSynchronize(L.st);
+        errs[t] = e != cudaSuccess ? e : s2;
+    }
+    void worker(size_t t, int dev) {
+        cudaSetDevice(dev);
+        u64 seen = 0;
+        std::unique_lock<std::mutex> lk(m);
+        for (;;) {
+            cv_job.wait(lk, [&] { return stop || job_id != seen; });
+            if (stop) return;
+            seen = job_id;
+            if (t < T) {
+                lk.unlock();
+                lane_run(t);
+                lk.lock();
+                if (--pending == 0) cv_done.notify_all();
+            }
+        }
+    }
+    void shutdown() {
+        {
+            std::lock_guard<std::mutex> lk(m);
+            stop = true;
+        }
+        cv_job.notify_all();
+        for (auto &x : th) x.join();
+        th.clear();
+    }
 };
 
 struct Shard {
@@ -974,6 +1046,19 @@ void pqv_destroy(pqv_ctx *ctx) {
         D.csr_totals.release();
         D.h_ent_rows.release();
         D.h_ivf_info.release();
+        if (D.pool) {
+            D.pool->shutdown();
+            delete D.pool;
+            D.pool = nullptr;
+        }
+        for (auto &L : D.lanes) {
+            if (L.st) cudaStreamDestroy(L.st);
+            for (auto &e : L.ev)
+                if (e) cudaEventDestroy(e);
+            L.buf[0].release();
+            L.buf[1].release();
+        }
+        D.lanes.clear();
         D.vt_bitmap.release();
         D.vt_mask.release();
         D.vt_sums.release();
@@ -1080,6 +1165,50 @@ static int grow_shard(pqv_ctx *ctx, Dataset &ds, Shard &sh, u64 need_rows) {
     return PQV_OK;
 }
 
+// Host -> HBM copy of a large PAGEABLE buffer.  A plain cudaMemcpy of pageable memory is staged by the driver through one
+// bounce buffer (11-16 GB/s measured on this box); here T host threads each run their own double-buffered lane -- copy an
+// 8 MB chunk into page-locked staging, cudaMemcpyAsync it, fill the other buffer while that DMA runs -- so the CPU copies
+// proceed in parallel and the copy engine always has a transfer queued (benchmarks/probe_append.py).  Page-locked
+// sources (cudaHostRegister'ed Arrow buffers) skip the staging: the DMA reads them directly.
+
+static int append_staged(DeviceState &D, unsigned char *dst, const unsigned char *src, size_t bytes) {
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const size_t n_chunks = (bytes + APPEND_CHUNK - 1) / APPEND_CHUNK;
+    const size_t lanes = std::min<size_t>(APPEND_MAX_LANES, std::max<size_t>(1, hw / 2));
+    if (D.lanes.size() < lanes) D.lanes.resize(lanes);
+    for (size_t t = 0; t < lanes; ++t) {
+        DeviceState::AppendLane &L = D.lanes[t];
+        if (!L.st) CU_TRY(cudaStreamCreateWithFlags(&L.st, cudaStreamNonBlocking));
+        for (auto &e : L.ev)
+            if (!e) CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        PQV_TRY(L.buf[0].ensure(APPEND_CHUNK));
+        PQV_TRY(L.buf[1].ensure(APPEND_CHUNK));
+    }
+    if (!D.pool) {
+        D.pool = new AppendPool();
+        for (size_t t = 0; t < lanes; ++t) D.pool->th.emplace_back(&AppendPool::worker, D.pool, t, D.dev);
+    }
+    AppendPool &P = *D.pool;
+    const size_t T = std::min(lanes, n_chunks);
+    {
+        std::unique_lock<std::mutex> lk(P.m);
+        P.D = &D;
+        P.dst = dst;
+        P.src = src;
+        P.bytes = bytes;
+        P.n_chunks = n_chunks;
+        P.T = T;
+        P.pending = T;
+        for (auto &e : P.errs) e = cudaSuccess;
+        P.job_id++;
+        P.cv_job.notify_all();
+        P.cv_done.wait(lk, [&] { return P.pending == 0; });
+    }
+    for (size_t t = 0; t < T; ++t)
+        if (P.errs[t] != cudaSuccess) return fail(PQV_ECUDA, "staged host->device copy failed: %s", cudaGetErrorString(P.errs[t]));
+    return PQV_OK;
+}
+
 int pqv_dataset_append(pqv_ctx *ctx, uint64_t handle, const float *values, uint64_t n_rows) {
     if (ctx) ctx->batch_state.valid = false;
     if (!ctx) return fail(PQV_EINVAL, "null ctx");
@@ -1107,9 +1236,24 @@ int pqv_dataset_append(pqv_ctx *ctx, uint64_t handle, const float *values, uint6
         const u64 take = std::min<u64>(n_rows - done, sh->cap_rows - sh->n_rows);
         DeviceState &D = ctx->devs[sh->di];
         DevGuard guard(D.dev);
-        CU_TRY(cudaMemcpyAsync(sh->d_data + sh->n_rows * ds->dim, values + done * ds->dim, (size_t)take * ds->dim * 4,
-                               cudaMemcpyHostToDevice, D.stream));
-        CU_TRY(cudaStreamSynchronize(D.stream));  // values is only borrowed for the call
+        const size_t bytes = (size_t)take * ds->dim * 4;
+        bool staged = false;
+        if (bytes >= APPEND_STAGED_MIN && getenv("PQV_APPEND_DIRECT") == nullptr) {
+            cudaPointerAttributes pa{};
+            const bool pinned = cudaPointerGetAttributes(&pa, values) == cudaSuccess && pa.type != cudaMemoryTypeUnregistered;
+            cudaGetLastError();  // an unregistered pointer may leave a sticky-less error code behind on old drivers
+            if (!pinned) {
+                CU_TRY(cudaStreamSynchronize(D.stream));
+                PQV_TRY(append_staged(D, reinterpret_cast<unsigned char *>(sh->d_data + sh->n_rows * ds->dim),
+                                      reinterpret_cast<const unsigned char *>(values + done * ds->dim), bytes));
+                staged = true;
+            }
+        }
+        if (!staged) {
+            CU_TRY(cudaMemcpyAsync(sh->d_data + sh->n_rows * ds->dim, values + done * ds->dim, bytes, cudaMemcpyHostToDevice,
+                                   D.stream));
+            CU_TRY(cudaStreamSynchronize(D.stream));  // values is only borrowed for the call
+        }
         sh->n_rows += take;
         sh->norms_rows = 0;  // cached norms no longer cover the shard
         ds->n_rows += take;
