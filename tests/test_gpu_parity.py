@@ -391,3 +391,30 @@ def test_peer_exchange_world_of_one(ctx, P):
     er, ed = O.topk_rerank(np.zeros(4, np.float32), desc, None, 5, 0, True)
     assert r.tolist() == er.tolist() and bits(d).tolist() == bits(ed).tolist()
     ds.drop(); ds2.drop()
+
+
+def test_large_pageable_append_goes_through_the_staging_lanes_intact(ctx):
+    """>= 32 MB from pageable memory: multi-lane pinned staging (append_staged); the table must hold the same bytes as
+    with the plain copy, across chunk borders and for a ragged tail, and searches over it must agree with the oracle."""
+    import os
+    rng = np.random.default_rng(77)
+    dim, n = 96, 120_001                       # 46 MB: 5.5 staging chunks of 8 MB, ragged tail
+    data = rng.random((n, dim), dtype=np.float32)
+    ds = ctx.dataset(dim, 16)                  # small hint: the shard also has to grow
+    ds.append(data[:7])
+    ds.append(data[7:])                        # staged
+    assert ds.rows == n
+    for lo in (0, 7, 21845 - 3, 60000, n - 50):          # 21845.33 rows per 8 MB chunk
+        assert np.array_equal(ds.read(lo, 50 if lo + 50 <= n else n - lo), data[lo:lo + 50])
+    q = rng.random(dim, dtype=np.float32)
+    check_topk(ds, data, q, 10, SQRT)
+    os.environ["PQV_APPEND_DIRECT"] = "1"
+    try:
+        ds2 = ctx.dataset_from(data)
+    finally:
+        del os.environ["PQV_APPEND_DIRECT"]
+    r1, d1 = ds.l2_topk(q, 25, SEQ)
+    r2, d2 = ds2.l2_topk(q, 25, SEQ)
+    assert r1.tolist() == r2.tolist() and d1.view(np.uint32).tolist() == d2.view(np.uint32).tolist()
+    ds.drop()
+    ds2.drop()
