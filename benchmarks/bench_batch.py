@@ -56,4 +56,20 @@ out["single_query_qps"] = 1.0 / single
 out["speedup_vs_single_query_scans"] = single * a.queries / e2e
 out["paths_identical_on"] = int(nchk) if (np.array_equal(rows[:nchk], r1) and np.array_equal(cnt[:nchk], c1) and
                                            np.array_equal(dist[:nchk].view(np.uint32), d1.view(np.uint32))) else -1
+# the reference's CPU loop for the same batch: nq independent serial scans (exec.rs:257-277 / search.rs:112-141), oracle
+# port on a bounded row sample, 1 thread per query as the reference runs it and all cores side by side as a charitable figure
+import oracle as O  # noqa: E402  (cpu baseline only)
+cores = os.cpu_count() or 1
+samp = min(200_000, a.rows)
+host = O.synth(samp, a.dim, 1234)
+order = 1 if a.flags & P.PQV_SUM_SEQ else 0
+t0 = time.perf_counter()
+O.scan_topk_mt(host, queries[0], a.k, order, 1)
+dt1 = time.perf_counter() - t0
+per_query = dt1 * a.rows / samp
+out["cpu_reference"] = {"kind": "port", "cores": 1,
+                        "sample": f"one query over {samp} x {a.dim} rows, 1 thread: {dt1:.3f} s, scaled x{a.rows / samp:g} in rows",
+                        "seconds_per_query": per_query, "qps": 1.0 / per_query,
+                        "qps_if_one_query_per_core": cores / per_query, "host_cores": cores,
+                        "gpu_speedup_vs_one_core": out["e2e_qps"] * per_query}
 print(json.dumps(out))

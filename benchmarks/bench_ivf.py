@@ -95,4 +95,28 @@ for name, mask in (("vector_topk_exec", None), ("vector_topk_exec_filtered", rng
                  "gather_scan_gbs": float(np.mean(scored)) * a.dim * 4 / (float(np.mean(kern)) * 1e-3) / 1e9,
                  "same_rows_as_search": same,
                  "mask_bytes_h2d_per_query": 0 if mask is None else (a.rows + 7) // 8}
+# the reference's CPU loops (oracle port) on bounded samples of the same work, timed on this box's host cores
+import oracle as O  # noqa: E402  (cpu baseline only)
+cores = os.cpu_count() or 1
+cent = ix.centroids()
+samp = min(20_000, a.rows)
+host = O.synth(samp, a.dim, 1234)
+t0 = time.perf_counter()
+O.assign(host, cent, workers=cores)              # index.rs:193-201 runs on available_parallelism() threads
+dt_assign = time.perf_counter() - t0
+samp_c = min(100_000, a.rows)
+host_c = O.synth(samp_c, a.dim, 1234)
+t0 = time.perf_counter()
+O.topk_rerank(queries[0], host_c, None, a.k, 0, True)   # search.rs:112-141 is serial
+dt_rerank = time.perf_counter() - t0
+mean_c = out["search"]["mean_candidates"]
+out["cpu_reference"] = {
+    "kind": "port", "cores_assign": cores, "cores_rerank": 1,
+    "final_assign_seconds_extrapolated": dt_assign * a.rows / samp,
+    "final_assign_sample": f"{samp} rows x {a.clusters} centroids x {a.dim} on {cores} threads: {dt_assign:.3f} s, scaled x{a.rows / samp:g}",
+    "search_rerank_seconds_extrapolated": dt_rerank * mean_c / samp_c,
+    "search_sample": f"{samp_c} candidate rows x {a.dim}, 1 thread: {dt_rerank:.3f} s, scaled to {mean_c:.0f} candidates "
+                     "(distance loop only; the reference also re-reads index and rows from Parquet per query)",
+    "gpu_final_assign_speedup": dt_assign * a.rows / samp / fa_s,
+    "gpu_search_speedup": dt_rerank * mean_c / samp_c / (out["search"]["ms_per_query_e2e"] * 1e-3)}
 print(json.dumps(out))
