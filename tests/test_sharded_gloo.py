@@ -181,7 +181,7 @@ def test_two_rank_array_distance_topk(tmp_path, n, dim, k, seed):
         assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
 
 
-def _ivf_worker(rank, world, port, n, dim, C, k, nprobe, flags, seed, out_dir):
+def _ivf_search_worker(rank, world, port, n, dim, C, k, nprobe, flags, seed, out_dir):
     sys.path.insert(0, ROOT)
     import oracle as O
     from pq_vector_b200.sharded import ShardedIvfSearch, shard_counts, shard_index
@@ -219,6 +219,6 @@ def _ivf_worker(rank, world, port, n, dim, C, k, nprobe, flags, seed, out_dir):
                                                           (900, 6, 30, 50, 30, 3, 5), (40, 3, 7, 10, 2, 2, 6)])
 def test_two_rank_ivf_search(tmp_path, n, dim, C, k, nprobe, flags, seed):
     port = 33500 + (os.getpid() + seed) % 2000
-    mp.spawn(_ivf_worker, args=(2, port, n, dim, C, k, nprobe, flags, seed, str(tmp_path)), nprocs=2, join=True)
+    mp.spawn(_ivf_search_worker, args=(2, port, n, dim, C, k, nprobe, flags, seed, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
