@@ -95,6 +95,30 @@ for name, mask in (("vector_topk_exec", None), ("vector_topk_exec_filtered", rng
                  "gather_scan_gbs": float(np.mean(scored)) * a.dim * 4 / (float(np.mean(kern)) * 1e-3) / 1e9,
                  "same_rows_as_search": same,
                  "mask_bytes_h2d_per_query": 0 if mask is None else (a.rows + 7) // 8}
+# batched IVF search: 1024 independent searches in one masked tensor-core pass (pqv_ivf_search_batch)
+nqb = 1024
+qb = ctx.dataset(a.dim, nqb)
+qb.fill_synthetic(nqb, 7)
+bq = qb.read(0, nqb)
+qb.drop()
+out["search_batch"] = {}
+for kk in (10, a.k):
+    ix.search_batch(ds, bq, kk, a.nprobe)
+    ts = []
+    for _ in range(3):
+        t0 = time.perf_counter()
+        br, bd, bc = ix.search_batch(ds, bq, kk, a.nprobe)
+        ts.append(time.perf_counter() - t0)
+    bt = ctx.last_batch_timing()
+    same = True
+    for i in range(0, nqb, 64):
+        r1, d1 = ix.search(ds, bq[i], kk, a.nprobe)
+        same &= bool(bc[i] == r1.size and np.array_equal(br[i, :bc[i]], r1) and
+                     np.array_equal(bd[i, :bc[i]].view(np.uint32), d1.view(np.uint32)))
+    tb = float(np.median(ts))
+    out["search_batch"][f"k{kk}"] = {"queries": nqb, "seconds_per_batch": tb, "qps_e2e": nqb / tb, "timing": bt,
+                                     "identical_to_single_searches_on": 16 if same else -1,
+                                     "speedup_vs_single_searches": tb and (nqb * out["search"]["ms_per_query_e2e"] * 1e-3) / tb}
 # the reference's CPU loops (oracle port) on bounded samples of the same work, timed on this box's host cores
 import oracle as O  # noqa: E402  (cpu baseline only)
 cores = os.cpu_count() or 1

@@ -50,6 +50,9 @@ extern "C" {
 #define PQV_SQRT         2u  /* apply sqrt to the kept distances BEFORE the final stable sort and return
                                 them (src/ivf/search.rs:129-140); without it squared distances are sorted
                                 and returned (src/df_vector/exec.rs:269-274)                                */
+#define PQV_ROW_ORDER    8u  /* pqv_ivf_search_batch only: candidates are visited in ascending row order (the
+                                RowSelection order of VectorTopKExec, src/df_vector/access.rs:107-176) instead of
+                                list-rank order (src/ivf/index.rs:57-63); matters among bit-equal distances only */
 #define PQV_TIES_BY_POSITION 4u /* skip the reference heap replay: order strictly by (distance, candidate
                                    position).  Differs from the reference only among bit-equal distances.  */
 
@@ -270,6 +273,15 @@ PQV_API int pqv_bench_assign(pqv_ctx *ctx, uint64_t handle, uint64_t n, const fl
  * outputs in HBM and returns the mean kernel time (CUDA events on the launch stream). */
 PQV_API int pqv_bench_scan(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags,
                    uint32_t iters, double *out_ms_per_scan);
+
+/* Batched IVF search: n_queries independent TopkBuilder::search calls (src/ivf/search.rs:83-142) -- or, with
+ * PQV_ROW_ORDER | PQV_SUM_SEQ, VectorTopKExec executions without cap and filter (src/df_vector/exec.rs:207-277) -- over
+ * one resident table + index, answered by ONE tensor-core pass over the table restricted per query to the clusters it
+ * probes.  Output layout as pqv_l2_topk (out_*[q*k + i], out_count[q]); every query's result is
+ * identical to its own single-query call (ties, NaN rankings and declined batches take the single-query pipeline). */
+PQV_API int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *queries, uint32_t n_queries,
+                         uint32_t k, uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist,
+                         uint32_t *out_count);
 
 /* IVF search with the rows sharded over ranks ("the index is replicated; each rank filters candidate
  * ids to its row range").  Each rank loads the index restricted to its slice (same centroids, every list cut to the rank's

@@ -10,7 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libpqv.so")
 
 PQV_OK, PQV_EINVAL, PQV_ENODEV, PQV_ECUDA, PQV_ENOMEM, PQV_EHANDLE, PQV_ELIMIT = range(7)
-PQV_SUM_UNROLL4, PQV_SUM_SEQ, PQV_SQRT, PQV_TIES_BY_POSITION = 0, 1, 2, 4
+PQV_SUM_UNROLL4, PQV_SUM_SEQ, PQV_SQRT, PQV_TIES_BY_POSITION, PQV_ROW_ORDER = 0, 1, 2, 4, 8
 PQV_MAX_K, PQV_MAX_DIM = 1024, 16384
 PQV_METRIC_L2, PQV_METRIC_COSINE = 0, 1
 
@@ -91,6 +91,8 @@ SIGNATURES = {
     "pqv_bench_assign": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32,
                                    C.POINTER(PqvAssignTiming), u32p]),
     "pqv_bench_scan": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, f64p]),
+    "pqv_ivf_search_batch": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p,
+                                       f32p, u32p]),
     "pqv_ivf_search_candidates": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p,
                                             C.c_uint64, u64p, u32p, u32p]),
     "pqv_vector_topk_indexed": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,

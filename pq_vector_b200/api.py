@@ -417,6 +417,20 @@ class IvfIndex:
                                    _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), C.byref(cnt)))
         return rows[:cnt.value].copy(), dist[:cnt.value].copy()
 
+    def search_batch(self, dataset: "Dataset", queries, k: int, nprobe: int, flags: int = N.PQV_SQRT):
+        """nq independent searches in one pass over the table (pqv_ivf_search_batch).
+        Returns (row_idx [nq,k] u32, dist [nq,k] f32, count [nq])."""
+        q = np.atleast_2d(_f32(queries))
+        if q.shape[1] != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.shape[1]}")
+        nq, kk = q.shape[0], max(k, 1)
+        rows = np.zeros((nq, kk), dtype=np.uint32)
+        dist = np.zeros((nq, kk), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        _check(_lib.pqv_ivf_search_batch(self.ctx._h, dataset.handle, self.handle, _ptr(q, C.c_float), nq, k, nprobe, flags,
+                                         _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), _ptr(cnt, C.c_uint32)))
+        return rows, dist, cnt
+
     def search_candidates(self, dataset: "Dataset", query, k: int, nprobe: int, flags: int = N.PQV_SQRT, cap: int = 1 << 16):
         """Per-rank half of a sharded IVF search (pqv_ivf_search_candidates): (keys u64 with positions in this rank's
         candidate sequence, local row ids u32, probed clusters in rank order)."""

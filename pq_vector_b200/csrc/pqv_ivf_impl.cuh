@@ -94,6 +94,9 @@ struct IvfIndex {
     DevBuf<float> d_centroids, d_cdist;
     DevBuf<u64> d_offsets, d_probe_prefix;
     DevBuf<uint32_t> d_ids, d_probe_cluster, d_cand;
+    // batched search: cluster of every row (from the lists), valid for a table of row_cluster_rows rows
+    DevBuf<uint32_t> d_row_cluster;
+    u64 row_cluster_rows = 0;
     uint32_t build_iters = 0;   // Lloyd iterations the build ran
     double build_ms[4] = {0, 0, 0, 0};  // sample+init, lloyd, final assign, total
 };
@@ -204,6 +207,7 @@ void index_free(IvfIndex *ix) {
     ix->d_ids.release();
     ix->d_probe_cluster.release();
     ix->d_cand.release();
+    ix->d_row_cluster.release();
     delete ix;
 }
 
@@ -893,21 +897,9 @@ int pqv_ivf_candidate_rows(pqv_ctx *ctx, uint64_t index, const float *query, uin
     return PQV_OK;
 }
 
-int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k, uint32_t nprobe,
-                   uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
-    if (!ctx || !query || !out_row_idx || !out_dist || !out_count) return fail(PQV_EINVAL, "null argument");
-    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");  // src/ivf/search.rs:72
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    Dataset *ds = find_dataset(ctx, handle);
-    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
-    IvfIndex *ix = find_index(ctx, index);
-    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
-    PQV_TRY(check_topk_args(k, ds->dim, flags));
-    if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
-    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search needs a single-device dataset");
-    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
-    DeviceState &D = ctx->devs[ds->shards[0].di];
-    DevGuard guard(D.dev);
+// one query of TopkBuilder::search over a resident table + index (the body of pqv_ivf_search; ctx->mu held)
+static int ivf_search_one(pqv_ctx *ctx, Dataset *ds, DeviceState &D, IvfIndex *ix, const float *query, uint32_t k,
+                          uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
     PQV_TRY(index_make_resident(D, *ix));
     if (ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids) {
         bool done = false;
@@ -938,6 +930,132 @@ int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *q
     return topk_one(ctx, *ds, query, nullptr, n_cand, k, flags, out_row_idx, out_dist, out_count, nullptr, 0,
                     ix->d_cand.p, &row_fn);
 }
+
+int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k, uint32_t nprobe,
+                   uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
+    if (!ctx || !query || !out_row_idx || !out_dist || !out_count) return fail(PQV_EINVAL, "null argument");
+    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");  // src/ivf/search.rs:72
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search needs a single-device dataset");
+    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    DeviceState &D = ctx->devs[ds->shards[0].di];
+    DevGuard guard(D.dev);
+    return ivf_search_one(ctx, ds, D, ix, query, k, nprobe, flags, out_row_idx, out_dist, out_count);
+}
+
+// Batched IVF search: nq independent TopkBuilder::search calls (src/ivf/search.rs:83-142; PQV_ROW_ORDER: the candidate
+// handling of VectorTopKExec, src/df_vector/exec.rs:207-277, without cap and filter) over one resident table + index,
+// answered by ONE tensor-core pass over the table restricted, per query, to the rows of the
+// clusters that query probes: all centroid rankings in one launch (l2_dist_batch_kernel + rank_batch_kernel), the probe
+// sets as a [cluster][query] bit matrix, the row -> cluster map from the lists, and the mask applied in the filter's
+// epilogues (pqv_tc.cuh: one word per 32 queries).  A query whose k + 1 best candidates hold an exact tie, a NaN centroid
+// distance, or a batch the filter declines goes through the single-query pipeline -- every result equals its own call.
+int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *queries, uint32_t n_queries, uint32_t k,
+                         uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    if (n_queries && (!queries || !out_row_idx || !out_dist || !out_count)) return fail(PQV_EINVAL, "null argument");
+    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");
+    const bool row_order = (flags & PQV_ROW_ORDER) != 0;
+    flags &= ~PQV_ROW_ORDER;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search_batch needs a single-device dataset");
+    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    DeviceState &D = ctx->devs[ds->shards[0].di];
+    DevGuard guard(D.dev);
+    PQV_TRY(index_make_resident(D, *ix));
+    const uint32_t C = ix->n_clusters, dim = ds->dim, np = std::min(nprobe, C);
+    std::vector<uint8_t> handled(n_queries, 0);
+    ctx->last_batch = pqv_batch_timing{};
+    ctx->batch_state.valid = false;
+    uint32_t cp2 = 32;
+    while (cp2 < C) cp2 <<= 1;
+    const bool can_batch = n_queries && ix->n_ids && batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k) &&
+                           !(flags & PQV_TIES_BY_POSITION) && (size_t)cp2 * 8 <= 128 * 1024 && (size_t)n_queries * np < (1ull << 31);
+    if (can_batch) {
+        namespace T = pqv::tc;
+        const uint32_t nq = n_queries;
+        const uint32_t nq_pad = (nq + T::BN - 1) / T::BN * T::BN, qwords = nq_pad / 32;
+        // row -> cluster, once per (index, table size)
+        if (ix->row_cluster_rows != ds->n_rows) {
+            PQV_TRY(ix->d_row_cluster.ensure(ds->n_rows));
+            CU_TRY(cudaMemsetAsync(ix->d_row_cluster.p, 0xFF, (size_t)ds->n_rows * 4, D.stream));
+            pqv::row_cluster_kernel<<<dim3(C, 8), 256, 0, D.stream>>>(ix->d_ids.p, ix->d_offsets.p, ds->n_rows, ix->d_row_cluster.p);
+            CU_TRY(cudaGetLastError());
+            ix->row_cluster_rows = ds->n_rows;
+        }
+        // all rankings in one launch
+        const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(ix->d_centroids.p) & 15) == 0);
+        const size_t smem = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)SCAN_WARPS * pqv::TileCfg<0, true>::TILE_FLOATS * 4;
+        auto *k_vec = pqv::l2_dist_batch_kernel<true, SCAN_WARPS>;
+        auto *k_sca = pqv::l2_dist_batch_kernel<false, SCAN_WARPS>;
+        if (vec4) CU_TRY(cudaFuncSetAttribute(k_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        else CU_TRY(cudaFuncSetAttribute(k_sca, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CU_TRY(cudaFuncSetAttribute(pqv::rank_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cp2 * 8)));
+        PQV_TRY(D.d_tmp_rows.ensure((size_t)nq * dim));
+        PQV_TRY(D.d_dist.ensure((size_t)nq * C));
+        PQV_TRY(D.d_assign.ensure((size_t)nq * np));
+        PQV_TRY(D.d_row_ids.ensure(nq));
+        PQV_TRY(D.vt_mask.ensure((size_t)C * qwords));
+        std::vector<uint32_t> nan_flags(nq);
+        const u64 NG = ((u64)C + 31) / 32;
+        const uint32_t gy_max = 16384;
+        CU_TRY(cudaMemcpyAsync(D.d_tmp_rows.p, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, D.stream));
+        for (uint32_t q0 = 0; q0 < nq; q0 += gy_max) {
+            const uint32_t cnt = std::min(gy_max, nq - q0);
+            const dim3 grid((uint32_t)((NG + SCAN_WARPS - 1) / SCAN_WARPS), cnt);
+            if (vec4) k_vec<<<grid, SCAN_WARPS * 32, smem, D.stream>>>(ix->d_centroids.p, C, dim, D.d_tmp_rows.p + (size_t)q0 * dim, D.d_dist.p + (size_t)q0 * C);
+            else k_sca<<<grid, SCAN_WARPS * 32, smem, D.stream>>>(ix->d_centroids.p, C, dim, D.d_tmp_rows.p + (size_t)q0 * dim, D.d_dist.p + (size_t)q0 * C);
+        }
+        pqv::rank_batch_kernel<<<nq, 1024, (size_t)cp2 * 8, D.stream>>>(D.d_dist.p, C, cp2, np, D.d_assign.p, D.d_row_ids.p);
+        CU_TRY(cudaMemsetAsync(D.vt_mask.p, 0, (size_t)C * qwords * 4, D.stream));
+        pqv::probe_build_kernel<<<(uint32_t)(((u64)nq * np + 255) / 256), 256, 0, D.stream>>>(D.d_assign.p, nq, np, D.d_row_ids.p, qwords, D.vt_mask.p);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaMemcpyAsync(nan_flags.data(), D.d_row_ids.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, D.stream));
+        BatchMask bm{ix->d_row_cluster.p, D.vt_mask.p, qwords};
+        PQV_TRY(batch_topk(ctx, D, *ds, ds->n_rows, dim, queries, nq, k, flags, out_row_idx, out_dist, out_count, handled, nullptr,
+                           nullptr, 0, &bm));
+        CU_TRY(cudaStreamSynchronize(D.stream));  // nan_flags is in (batch_topk may have returned before its own sync)
+        for (uint32_t q = 0; q < nq; ++q)
+            if (nan_flags[q]) handled[q] = 0;
+    }
+    for (uint32_t q = 0; q < n_queries; ++q) {
+        if (handled[q]) continue;
+        const float *qv = queries + (size_t)q * dim;
+        uint32_t *orow = out_row_idx + (size_t)q * k;
+        float *odist = out_dist + (size_t)q * k;
+        if (!row_order) {
+            PQV_TRY(ivf_search_one(ctx, ds, D, ix, qv, k, nprobe, flags, orow, odist, out_count + q));
+        } else {
+            RowOrder ro;
+            bool done = false;
+            out_count[q] = 0;
+            if (ivf_fused_enabled() && C <= IVF_RANK_MAX_C && ix->n_ids)
+                PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, qv, k, nprobe, flags, orow, odist, out_count + q, &done, &ro));
+            if (!done) {  // host-ranked selection in row order (as pqv_vector_topk_indexed)
+                PQV_TRY(index_host_ids(D, *ix));
+                std::vector<uint32_t> ranked, rows;
+                PQV_TRY(rank_clusters(D, *ix, qv, nprobe, ranked));
+                for (uint32_t c : ranked) rows.insert(rows.end(), ix->ids.begin() + ix->offsets[c], ix->ids.begin() + ix->offsets[c + 1]);
+                std::sort(rows.begin(), rows.end());
+                if (!rows.empty()) PQV_TRY(topk_one(ctx, *ds, qv, rows.data(), rows.size(), k, flags, orow, odist, out_count + q));
+            }
+        }
+    }
+    return PQV_OK;
+}
+
 
 int pqv_ivf_search_candidates(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k, uint32_t nprobe,
                               uint32_t flags, uint64_t *out_keys, uint32_t *out_rows, uint64_t cap, uint64_t *out_count,

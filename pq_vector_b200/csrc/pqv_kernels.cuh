@@ -1046,6 +1046,29 @@ __global__ void __launch_bounds__(256) bitmap_compact_kernel(const uint32_t *__r
     }
 }
 
+// Batched IVF search (pqv_ivf_search_batch): row -> cluster map from the inverted lists, and the probe bit matrix
+// probe_T[c][q / 32] from the ranked cluster ids of every query (rank_batch_kernel output, np per query).
+__global__ void __launch_bounds__(256) row_cluster_kernel(const uint32_t *__restrict__ list_ids,
+                                                          const u64 *__restrict__ list_offsets, const u64 n_rows,
+                                                          uint32_t *__restrict__ row_cluster) {
+    const uint32_t c = blockIdx.x;
+    const u64 b = list_offsets[c], e = list_offsets[c + 1];
+    for (u64 i = b + (u64)blockIdx.y * blockDim.x + threadIdx.x; i < e; i += (u64)gridDim.y * blockDim.x) {
+        const uint32_t r = list_ids[i];
+        if (r < n_rows) row_cluster[r] = c;
+    }
+}
+__global__ void __launch_bounds__(256) probe_build_kernel(const uint32_t *__restrict__ ranked, const uint32_t nq,
+                                                          const uint32_t np, const uint32_t *__restrict__ skip,
+                                                          const uint32_t qwords, uint32_t *__restrict__ probe_T) {
+    const u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= (u64)nq * np) return;
+    const uint32_t q = (uint32_t)(i / np);
+    if (skip[q]) return;  // NaN centroid distance: this query is ranked and answered on the host path
+    const uint32_t c = ranked[i];
+    atomicOr(&probe_T[(size_t)c * qwords + (q >> 5)], 1u << (q & 31));
+}
+
 // find_closest_centroids (src/ivf/index.rs:130-149) on the device: stable ascending sort of the C query-centroid
 // distances, keep the first nprobe.  For distances that are not NaN (sums of squares: >= +0, or +inf) the stable
 // sort under partial_cmp is the sort by (distance bits, cluster index); a NaN distance raises *nan_flag and the caller

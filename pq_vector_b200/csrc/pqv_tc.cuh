@@ -964,6 +964,11 @@ struct BatchParams {
     uint32_t *flags;         // FLAG_*
     u64 n;                   // rows covered by this launch
     uint32_t dim;
+    // IVF mask (batched IVF search, all three null/0 otherwise): a (row, query) pair only counts if the row's cluster is
+    // among the query's probed clusters.  probe_T[c * qwords + (q >> 5)] bit (q & 31): query q probes cluster c.
+    const uint32_t *row_cluster;  // [n] cluster of each row, 0xFFFFFFFF = in no list
+    const uint32_t *probe_T;      // [C][qwords]
+    uint32_t qwords;              // nq_pad / 32
 };
 
 template <int MODE>
@@ -989,6 +994,12 @@ struct BatchEpi {
             const float a = sqrtf(x2hi) * 1.000001f;
             const float rho = 1.5f * gamma * x2hi + (x2hi + 2.f * a * bnmax) * 9.5367432e-07f + 1e-37f;
             const float x2s = (MODE == BATCH_SAMPLE) ? x2c + rho : x2c - rho;
+            // IVF mask: the probe words of this row's cluster (one word per 32 queries)
+            const uint32_t *probe_row = nullptr;
+            if (p.row_cluster && valid) {
+                const uint32_t cl = p.row_cluster[row];
+                if (cl != 0xFFFFFFFFu) probe_row = p.probe_T + (size_t)cl * p.qwords;
+            }
             for (uint32_t nb = 0; nb < g.num_nb; ++nb, ++tile) {
                 const uint32_t taddr = c.acquire(tile);
                 const float4 *w4 = reinterpret_cast<const float4 *>(p.qw + (size_t)nb * BN);
@@ -998,6 +1009,7 @@ struct BatchEpi {
                     float v[32];
                     tmem_ld32(taddr + ch * 32u, v);
                     const uint32_t q0 = nb * BN + ch * 32u;
+                    const uint32_t pm = !p.row_cluster ? 0xFFFFFFFFu : (probe_row ? __ldg(probe_row + (q0 >> 5)) : 0u);
                     if (MODE == BATCH_SAMPLE) {
 #pragma unroll
                         for (int i4 = 0; i4 < 8; ++i4) {
@@ -1005,7 +1017,8 @@ struct BatchEpi {
                             const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                const float u = __fmaf_rn(a, wv[e], __fmaf_rn(-2.f, v[4 * i4 + e], x2s));
+                                float u = __fmaf_rn(a, wv[e], __fmaf_rn(-2.f, v[4 * i4 + e], x2s));
+                                if (!((pm >> (4 * i4 + e)) & 1u)) u = 3.0e38f;  // not probed by this query: never among its k smallest
                                 if (valid) p.U[(size_t)(q0 + 4 * i4 + e) * p.ldU + row] = u;  // lanes = consecutive rows: coalesced
                             }
                         }
@@ -1024,6 +1037,7 @@ struct BatchEpi {
                             }
                         }
                         if (!valid) mask = 0;
+                        mask &= pm;
                         if (__any_sync(0xffffffffu, mask != 0u)) {
                             const uint32_t cnt = (uint32_t)__popc(mask);
                             uint32_t incl = cnt;

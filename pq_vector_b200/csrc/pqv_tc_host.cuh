@@ -216,6 +216,12 @@ constexpr uint32_t BATCH_MIN_QUERIES = 4;          // below this the single-quer
 constexpr u64 BATCH_TOTAL_CAND = 64ull << 20;      // candidate (row, query) records kept per batch (8 B each)
 
 // PQV_BATCH=off disables the path (every query then takes the single-query scan)
+struct BatchMask {
+    const uint32_t *row_cluster;  // device, [n]
+    const uint32_t *probe_T;      // device, [C][qwords]
+    uint32_t qwords;              // ceil(nq / BN) * BN / 32
+};
+
 bool batch_path_applies(const Dataset &ds, const float *d_rows, uint32_t nq, uint32_t k) {
     const char *e = getenv("PQV_BATCH");
     if (e && !strcmp(e, "off")) return false;
@@ -228,7 +234,10 @@ bool batch_path_applies(const Dataset &ds, const float *d_rows, uint32_t nq, uin
 // single-query path (ties whose order depends on the reference heap's layout, or a declined batch).
 int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, const float *queries, uint32_t nq,
                uint32_t k, uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
-               std::vector<uint8_t> &handled, u64 *raw_keys = nullptr, uint32_t *raw_count = nullptr, uint32_t pos_base = 0) {
+               std::vector<uint8_t> &handled, u64 *raw_keys = nullptr, uint32_t *raw_count = nullptr, uint32_t pos_base = 0,
+               const BatchMask *bmask = nullptr) {
+    // bmask != null (batched IVF search): only (row, query) pairs whose row lies in a cluster the query probes count;
+    // tie queries are left unhandled (their order follows the IVF candidate sequence, which the caller replays)
     // raw mode (raw_keys != null, the per-rank half of a sharded search): per query the k + 1 smallest exact keys of
     // this slice go to raw_keys[q*(k+1) ..] with pos_base added to the positions, raw_count[q] = how many are valid, or
     // 0xFFFFFFFF when this slice could not decide the query (the caller falls back to the single-query exchange)
@@ -328,6 +337,9 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     p.region_count = region_count;
     p.flags = dflags;
     p.dim = dim;
+    p.row_cluster = bmask ? bmask->row_cluster : nullptr;
+    p.probe_T = bmask ? bmask->probe_T : nullptr;
+    p.qwords = bmask ? bmask->qwords : 0;
     // phase A: upper bounds over the first S rows -> theta_q
     p.n = S;
     if (tg.pair)
@@ -421,7 +433,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
         const uint32_t info = h_info[q];
         if (info & T::SEL_OVERFLOW) continue;  // candidate list incomplete: the caller runs the full single-query scan
         if ((info & T::SEL_TIE) && !by_pos) {
-            ties.push_back(q);
+            if (!bmask) ties.push_back(q);
             continue;
         }
         const uint32_t cnt = info & 0xFFFFu;

@@ -397,3 +397,44 @@ def test_sharded_ivf_search_pieces_equal_the_whole_table_search(ctx, n, dim, C, 
         ds.drop()
     whole_ix.drop()
     whole_ds.drop()
+
+
+# ---- batched IVF search (pqv_ivf_search_batch): one masked tensor-core pass for all queries ----------------------------
+@pytest.mark.parametrize("n,dim,C,nq,grid", [(40000, 64, 48, 40, False), (30000, 128, 100, 300, False), (12000, 8, 21, 17, True)])
+def test_batched_ivf_search_equals_single_searches(ctx, n, dim, C, nq, grid):
+    import pq_vector_b200 as P
+    rng = np.random.default_rng(n + nq)
+    data = rng.integers(0, 3, (n, dim)).astype(np.float32) if grid else rng.random((n, dim), dtype=np.float32)
+    cent = data[rng.choice(n, C, replace=False)].copy() + (0.0 if grid else 0.01)
+    offsets, ids = O.inverted_lists(O.assign(data, cent, workers=2), C)
+    ix = ctx.ivf_from_bytes(O.index_to_bytes(dim, cent, offsets, ids))
+    ds = ctx.dataset_from(data)
+    queries = (data[rng.integers(0, n, nq)] if grid else rng.random((nq, dim), dtype=np.float32)).copy()
+    used = 0
+    for nprobe in (1, max(2, C // 8), C):
+        for k, flags in ((10, SQRT), (100, SEQ), (10, SEQ | P.PQV_ROW_ORDER)):
+            rows, dist, cnt = ix.search_batch(ds, queries, k, nprobe, flags)
+            bt = ctx.last_batch_timing()
+            used += bt["queries"] > 0 and not bt["declined"]
+            order, do_sqrt = (1 if flags & SEQ else 0), bool(flags & SQRT)
+            for i in range(0, nq, max(1, nq // 25)):
+                cand = O.candidate_rows(queries[i], cent, offsets, ids, nprobe)
+                if flags & P.PQV_ROW_ORDER:
+                    cand = np.sort(cand)
+                er, ed = O.topk_rerank_gather(queries[i], data, cand, k, order, do_sqrt)
+                assert cnt[i] == er.size, (i, nprobe, k, flags, bt)
+                assert rows[i, :cnt[i]].tolist() == er.tolist(), (i, nprobe, k, flags, bt)
+                assert dist[i, :cnt[i]].view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+    if not grid:
+        assert used > 0            # the masked tensor-core pass really ran (grid data may decline it: ties everywhere)
+    # a NaN centroid: that ranking is not an order -> those queries take the host-ranked single-query path
+    c2 = cent.copy()
+    c2[C // 2, 0] = np.nan
+    ix2 = ctx.ivf_from_bytes(O.index_to_bytes(dim, c2, offsets, ids))
+    rows, dist, cnt = ix2.search_batch(ds, queries[:8], 10, 3, SQRT)
+    for i in range(8):
+        r1, d1 = ix2.search(ds, queries[i], 10, 3, SQRT)
+        assert rows[i, :cnt[i]].tolist() == r1.tolist() and dist[i, :cnt[i]].view(np.uint32).tolist() == d1.view(np.uint32).tolist()
+    ix.drop()
+    ix2.drop()
+    ds.drop()
