@@ -19,7 +19,8 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import pq_vector_b200 as P  # noqa: E402
-from pq_vector_b200.sharded import (ShardedArrayDistanceTopk, ShardedIvfBuild, ShardedIvfSearch, index_to_bytes,  # noqa: E402
+from pq_vector_b200.sharded import (ShardedArrayDistanceTopk, ShardedBatchIvfSearch, ShardedIvfBuild, ShardedIvfSearch,  # noqa: E402
+                                    index_to_bytes,
                                     shard_counts, shard_index)
 
 ap = argparse.ArgumentParser()
@@ -89,6 +90,23 @@ def timed(fn):
 
 
 r_ivf, t_ivf = timed(lambda q: ivf.search(q, a.k, a.nprobe, P.PQV_SQRT))
+# batched: 256 searches in one masked pass per rank + one all-gather
+nqb, kb = 256, 10
+qb = ctx.dataset(a.dim, nqb)
+qb.fill_synthetic(nqb, 9)
+bq = qb.read(0, nqb)
+qb.drop()
+sbatch = ShardedBatchIvfSearch(lambda qs, k, nprobe, flags, pb: local_ix.search_batch_keys(ds, qs, k, nprobe, flags, pb), ivf, lo, dev)
+sbatch.search(bq, kb, a.nprobe, P.PQV_SQRT)
+if world > 1:
+    dist.barrier()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+b_rows, b_dist, b_cnt = sbatch.search(bq, kb, a.nprobe, P.PQV_SQRT)
+torch.cuda.synchronize()
+if world > 1:
+    dist.barrier()
+t_batch = time.perf_counter() - t0
 r_ad, t_ad = timed(lambda q: adist.search(q.astype(np.float64), a.k))
 if rank == 0:
     whole = ctx.dataset(a.dim, n_glob)
@@ -103,7 +121,13 @@ if rank == 0:
     for q, (r, d) in zip(queries, r_ad):
         wr, wd = whole.array_distance_topk(q.astype(np.float64), a.k)
         same_ad &= wr.tolist() == r.tolist() and wd.view(np.uint64).tolist() == d.view(np.uint64).tolist()
-    print(json.dumps({"config": f"{n_glob} x {a.dim} over {world} GPU(s), C={a.clusters}, nprobe={a.nprobe}, k={a.k}",
+    w_rows, w_dist, w_cnt = wix.search_batch(whole, bq, kb, a.nprobe, P.PQV_SQRT)
+    same_batch = bool(np.array_equal(w_cnt, b_cnt) and all(
+        np.array_equal(w_rows[i, :w_cnt[i]], b_rows[i, :b_cnt[i]]) and
+        np.array_equal(w_dist[i, :w_cnt[i]].view(np.uint32), b_dist[i, :b_cnt[i]].view(np.uint32)) for i in range(nqb)))
+    print(json.dumps({"sharded_batch_ivf": {"queries": nqb, "k": kb, "seconds_per_batch": t_batch, "qps": nqb / t_batch,
+                                            "replayed_queries": sbatch.last_replayed, "identical_to_single_gpu_batch": same_batch},
+                      "config": f"{n_glob} x {a.dim} over {world} GPU(s), C={a.clusters}, nprobe={a.nprobe}, k={a.k}",
                       "sharded_ivf_search_ms": t_ivf * 1e3, "single_gpu_ivf_search_ms": t_whole * 1e3,
                       "sharded_array_distance_topk_ms": t_ad * 1e3, "ivf_identical_to_single_gpu": bool(same_ivf),
                       "array_distance_identical_to_single_gpu": bool(same_ad), "queries": len(queries)}))

@@ -283,6 +283,15 @@ PQV_API int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, 
                          uint32_t k, uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist,
                          uint32_t *out_count);
 
+/* Per-rank half of a SHARDED batched IVF search (config C5 with the index): `index` holds the lists cut to this rank's
+ * row range (local ids), pos_base = first global row of the slice.  Returns per query the k + 1 smallest exact keys
+ * (bits(squared distance) << 32 | pos_base + local row) among the probed rows of the slice, layout and meaning as
+ * pqv_l2_topk_batch_keys (out_count[q] = 0xFFFFFFFF: undecided here).  The ranks exchange keys and counts with ONE
+ * all-gather and call pqv_merge_batch_keys; queries it flags go through pqv_ivf_search_candidates + the replay. */
+PQV_API int pqv_ivf_search_batch_keys(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *queries,
+                              uint32_t n_queries, uint32_t k, uint32_t nprobe, uint32_t flags, uint32_t pos_base,
+                              uint64_t *out_keys, uint32_t *out_count);
+
 /* IVF search with the rows sharded over ranks ("the index is replicated; each rank filters candidate
  * ids to its row range").  Each rank loads the index restricted to its slice (same centroids, every list cut to the rank's
  * row range with local ids: pq_vector_b200/sharded.py) and calls pqv_ivf_search_candidates: the per-rank half of

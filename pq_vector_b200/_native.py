@@ -93,6 +93,8 @@ SIGNATURES = {
     "pqv_bench_scan": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, f64p]),
     "pqv_ivf_search_batch": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p,
                                        f32p, u32p]),
+    "pqv_ivf_search_batch_keys": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                            C.c_uint32, u64p, u32p]),
     "pqv_ivf_search_candidates": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, u32p,
                                             C.c_uint64, u64p, u32p, u32p]),
     "pqv_vector_topk_indexed": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,

@@ -431,6 +431,18 @@ class IvfIndex:
                                          _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), _ptr(cnt, C.c_uint32)))
         return rows, dist, cnt
 
+    def search_batch_keys(self, dataset: "Dataset", queries, k: int, nprobe: int, flags: int = N.PQV_SQRT, pos_base: int = 0):
+        """Per-rank half of a sharded batched IVF search (pqv_ivf_search_batch_keys): (keys [nq, k+1] u64, counts [nq] u32)."""
+        q = np.atleast_2d(_f32(queries))
+        if q.shape[1] != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.shape[1]}")
+        nq = q.shape[0]
+        keys = np.full((nq, k + 1), np.iinfo(np.uint64).max, dtype=np.uint64)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        _check(_lib.pqv_ivf_search_batch_keys(self.ctx._h, dataset.handle, self.handle, _ptr(q, C.c_float), nq, k, nprobe, flags,
+                                              pos_base, _ptr(keys, C.c_uint64), _ptr(cnt, C.c_uint32)))
+        return keys, cnt
+
     def search_candidates(self, dataset: "Dataset", query, k: int, nprobe: int, flags: int = N.PQV_SQRT, cap: int = 1 << 16):
         """Per-rank half of a sharded IVF search (pqv_ivf_search_candidates): (keys u64 with positions in this rank's
         candidate sequence, local row ids u32, probed clusters in rank order)."""

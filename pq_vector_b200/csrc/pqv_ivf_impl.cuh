@@ -949,34 +949,14 @@ int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *q
     return ivf_search_one(ctx, ds, D, ix, query, k, nprobe, flags, out_row_idx, out_dist, out_count);
 }
 
-// Batched IVF search: nq independent TopkBuilder::search calls (src/ivf/search.rs:83-142; PQV_ROW_ORDER: the candidate
-// handling of VectorTopKExec, src/df_vector/exec.rs:207-277, without cap and filter) over one resident table + index,
-// answered by ONE tensor-core pass over the table (DESIGN.md section 4.6) restricted, per query, to the rows of the
-// clusters that query probes: all centroid rankings in one launch (l2_dist_batch_kernel + rank_batch_kernel), the probe
-// sets as a [cluster][query] bit matrix, the row -> cluster map from the lists, and the mask applied in the filter's
-// epilogues (pqv_tc.cuh: one word per 32 queries).  A query whose k + 1 best candidates hold an exact tie, a NaN centroid
-// distance, or a batch the filter declines goes through the single-query pipeline -- every result equals its own call.
-int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *queries, uint32_t n_queries, uint32_t k,
-                         uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
-    if (!ctx) return fail(PQV_EINVAL, "null ctx");
-    if (n_queries && (!queries || !out_row_idx || !out_dist || !out_count)) return fail(PQV_EINVAL, "null argument");
-    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");
-    const bool row_order = (flags & PQV_ROW_ORDER) != 0;
-    flags &= ~PQV_ROW_ORDER;
-    std::lock_guard<std::mutex> lk(ctx->mu);
-    Dataset *ds = find_dataset(ctx, handle);
-    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
-    IvfIndex *ix = find_index(ctx, index);
-    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
-    PQV_TRY(check_topk_args(k, ds->dim, flags));
-    if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
-    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search_batch needs a single-device dataset");
-    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
-    DeviceState &D = ctx->devs[ds->shards[0].di];
-    DevGuard guard(D.dev);
-    PQV_TRY(index_make_resident(D, *ix));
+// the masked batched pass shared by pqv_ivf_search_batch (final results) and pqv_ivf_search_batch_keys (raw k + 1 keys per
+// query for the sharded merge).  handled[q] = 1 where the pass decided query q.  ctx->mu held, device selected.
+static int ivf_batch_masked(pqv_ctx *ctx, Dataset *ds, DeviceState &D, IvfIndex *ix, const float *queries, uint32_t n_queries,
+                            uint32_t k, uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist,
+                            uint32_t *out_count, std::vector<uint8_t> &handled, u64 *raw_keys, uint32_t *raw_count,
+                            uint32_t pos_base) {
     const uint32_t C = ix->n_clusters, dim = ds->dim, np = std::min(nprobe, C);
-    std::vector<uint8_t> handled(n_queries, 0);
+    handled.assign(n_queries, 0);
     ctx->last_batch = pqv_batch_timing{};
     ctx->batch_state.valid = false;
     uint32_t cp2 = 32;
@@ -1024,12 +1004,46 @@ int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const fl
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaMemcpyAsync(nan_flags.data(), D.d_row_ids.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, D.stream));
         BatchMask bm{ix->d_row_cluster.p, D.vt_mask.p, qwords};
-        PQV_TRY(batch_topk(ctx, D, *ds, ds->n_rows, dim, queries, nq, k, flags, out_row_idx, out_dist, out_count, handled, nullptr,
-                           nullptr, 0, &bm));
+        PQV_TRY(batch_topk(ctx, D, *ds, ds->n_rows, dim, queries, nq, k, flags, out_row_idx, out_dist, out_count, handled, raw_keys,
+                           raw_count, pos_base, &bm));
+        ctx->batch_state.valid = false;  // the candidate segments left on the device are masked: not for the dense tie API
         CU_TRY(cudaStreamSynchronize(D.stream));  // nan_flags is in (batch_topk may have returned before its own sync)
         for (uint32_t q = 0; q < nq; ++q)
             if (nan_flags[q]) handled[q] = 0;
     }
+    return PQV_OK;
+}
+
+// Batched IVF search: nq independent TopkBuilder::search calls (src/ivf/search.rs:83-142; PQV_ROW_ORDER: the candidate
+// handling of VectorTopKExec, src/df_vector/exec.rs:207-277, without cap and filter) over one resident table + index,
+// answered by ONE tensor-core pass over the table (DESIGN.md section 4.6) restricted, per query, to the rows of the
+// clusters that query probes: all centroid rankings in one launch (l2_dist_batch_kernel + rank_batch_kernel), the probe
+// sets as a [cluster][query] bit matrix, the row -> cluster map from the lists, and the mask applied in the filter's
+// epilogues (pqv_tc.cuh: one word per 32 queries).  A query whose k + 1 best candidates hold an exact tie, a NaN centroid
+// distance, or a batch the filter declines goes through the single-query pipeline -- every result equals its own call.
+int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *queries, uint32_t n_queries, uint32_t k,
+                         uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    if (n_queries && (!queries || !out_row_idx || !out_dist || !out_count)) return fail(PQV_EINVAL, "null argument");
+    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");
+    const bool row_order = (flags & PQV_ROW_ORDER) != 0;
+    flags &= ~PQV_ROW_ORDER;
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search_batch needs a single-device dataset");
+    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    DeviceState &D = ctx->devs[ds->shards[0].di];
+    DevGuard guard(D.dev);
+    PQV_TRY(index_make_resident(D, *ix));
+    const uint32_t C = ix->n_clusters, dim = ds->dim;
+    std::vector<uint8_t> handled;
+    PQV_TRY(ivf_batch_masked(ctx, ds, D, ix, queries, n_queries, k, nprobe, flags, out_row_idx, out_dist, out_count, handled,
+                             nullptr, nullptr, 0));
     for (uint32_t q = 0; q < n_queries; ++q) {
         if (handled[q]) continue;
         const float *qv = queries + (size_t)q * dim;
@@ -1053,6 +1067,42 @@ int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const fl
             }
         }
     }
+    return PQV_OK;
+}
+
+
+// per-rank half of a sharded batched IVF search: the k + 1 smallest exact keys (bits(d) << 32 | pos_base + local row) of
+// every query among the probed rows of THIS rank's slice (index = the lists cut to the slice); out_count[q] = 0xFFFFFFFF
+// where the slice could not decide the query.  Merge with pqv_merge_batch_keys; flagged queries: pqv_ivf_search_candidates.
+int pqv_ivf_search_batch_keys(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *queries, uint32_t n_queries, uint32_t k,
+                              uint32_t nprobe, uint32_t flags, uint32_t pos_base, uint64_t *out_keys, uint32_t *out_count) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    if (n_queries && (!queries || !out_keys || !out_count)) return fail(PQV_EINVAL, "null argument");
+    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (flags & PQV_TIES_BY_POSITION) return fail(PQV_EINVAL, "batch keys are only defined for the reference tie order");
+    if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search_batch_keys needs a single-device dataset");
+    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    if ((u64)pos_base + ds->n_rows > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "global row ids are u32");
+    for (uint32_t q = 0; q < n_queries; ++q) out_count[q] = 0xFFFFFFFFu;
+    if (n_queries && ix->n_ids == 0) {  // nothing of this slice is in any list
+        for (uint32_t q = 0; q < n_queries; ++q) out_count[q] = 0;
+        return PQV_OK;
+    }
+    DeviceState &D = ctx->devs[ds->shards[0].di];
+    DevGuard guard(D.dev);
+    PQV_TRY(index_make_resident(D, *ix));
+    std::vector<uint8_t> handled;
+    std::vector<uint32_t> counts(n_queries, 0xFFFFFFFFu);
+    PQV_TRY(ivf_batch_masked(ctx, ds, D, ix, queries, n_queries, k, nprobe, flags, nullptr, nullptr, nullptr, handled,
+                             reinterpret_cast<u64 *>(out_keys), counts.data(), pos_base));
+    for (uint32_t q = 0; q < n_queries; ++q) out_count[q] = handled[q] ? counts[q] : 0xFFFFFFFFu;
     return PQV_OK;
 }
 

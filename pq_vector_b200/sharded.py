@@ -372,3 +372,46 @@ class ShardedIvfSearch:
         row_of = np.zeros(n_total, dtype=np.uint32)          # candidate position -> row id, filled for the entrants only
         row_of[(k_all & np.uint64(0xFFFFFFFF)).astype(np.int64)] = r_all
         return replay_candidates(k_all, k, flags, row_ids=row_of)
+
+
+class ShardedBatchIvfSearch:
+    """Batched IVF searches over row-range shards (config C5 with the index registered): every rank answers the whole batch
+    over its slice in one masked tensor-core pass (IvfIndex.search_batch_keys: k + 1 exact keys per query among the probed
+    rows of the slice), ONE all-gather, pqv_merge_batch_keys on every rank; the queries it flags (exact ties, undecided
+    slices) go through ShardedIvfSearch one by one.  Every query's result equals its own search over the whole table."""
+
+    def __init__(self, batch_fn, single: ShardedIvfSearch, pos_base: int, device: "torch.device | str" = "cpu", group=None):
+        """batch_fn(queries, k, nprobe, flags, pos_base) -> (keys [nq, k+1] u64, counts [nq] u32)"""
+        self.batch_fn = batch_fn
+        self.single = single
+        self.pos_base = int(pos_base)
+        self.device = torch.device(device)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.last_gather_bytes = 0
+        self.last_replayed = 0
+
+    def search(self, queries, k: int, nprobe: int, flags: int):
+        queries = np.ascontiguousarray(queries, dtype=np.float32)
+        nq = queries.shape[0]
+        keys, counts = self.batch_fn(queries, k, nprobe, flags, self.pos_base)
+        send = torch.from_numpy(np.concatenate([keys.reshape(-1).view(np.int64), counts.astype(np.int64)])).to(self.device)
+        if self.world > 1:
+            recv = torch.empty(self.world * send.numel(), dtype=torch.int64, device=self.device)
+            dist.all_gather_into_tensor(recv, send, group=self.group)
+            got = recv.cpu().numpy().reshape(self.world, send.numel())
+            self.last_gather_bytes = got.nbytes
+        else:
+            got = send.cpu().numpy()[None, :]
+            self.last_gather_bytes = 0
+        all_keys = got[:, :nq * (k + 1)].view(np.uint64).reshape(self.world, nq, k + 1)
+        all_counts = got[:, nq * (k + 1):].astype(np.uint32)
+        rows, dd, cnt, need = merge_batch_keys(all_keys, all_counts, k, flags)
+        ties = np.nonzero(need)[0]        # identical on every rank: the merge is deterministic on identical gathered data
+        self.last_replayed = int(ties.size)
+        for q in ties:
+            r_, d_ = self.single.search(queries[q], k, nprobe, flags)
+            cnt[q] = r_.size
+            rows[q, :r_.size] = r_
+            dd[q, :r_.size] = d_
+        return rows, dd, cnt

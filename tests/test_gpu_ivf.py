@@ -438,3 +438,39 @@ def test_batched_ivf_search_equals_single_searches(ctx, n, dim, C, nq, grid):
     ix.drop()
     ix2.drop()
     ds.drop()
+
+
+def test_sharded_batched_ivf_keys_merge_to_the_whole_table_answer(ctx):
+    """Three slices on one GPU stand in for three ranks: per-slice k + 1 keys from the masked batched pass, merged
+    (pqv_merge_batch_keys); flagged queries answered by the single-query route -> the whole-table batched answer."""
+    import pq_vector_b200 as P
+    from pq_vector_b200.sharded import index_to_bytes, shard_index
+    rng = np.random.default_rng(2024)
+    n, dim, C, nq, k, nprobe = 45000, 64, 40, 64, 10, 6
+    data = rng.random((n, dim), dtype=np.float32)
+    cent = data[rng.choice(n, C, replace=False)].copy() + 0.01
+    offsets, ids = O.inverted_lists(O.assign(data, cent, workers=2), C)
+    queries = rng.random((nq, dim), dtype=np.float32)
+    bounds = [0, 9000, 30000, n]
+    keys, counts = [], []
+    used = 0
+    for s in range(3):
+        lo, hi = bounds[s], bounds[s + 1]
+        l_off, l_ids = shard_index(offsets, ids, lo, hi)
+        ix = ctx.ivf_from_bytes(index_to_bytes(cent, l_off, l_ids))
+        ds = ctx.dataset_from(data[lo:hi])
+        kq, cq = ix.search_batch_keys(ds, queries, k, nprobe, SQRT, pos_base=lo)
+        used += ctx.last_batch_timing()["queries"] > 0
+        keys.append(kq)
+        counts.append(cq)
+        ix.drop()
+        ds.drop()
+    assert used == 3
+    rows, dd, cnt, need = P.merge_batch_keys(np.stack(keys), np.stack(counts), k, SQRT)
+    for i in range(nq):
+        er, ed = O.topk_rerank_gather(queries[i], data, O.candidate_rows(queries[i], cent, offsets, ids, nprobe), k, 0, True)
+        if need[i]:
+            continue
+        assert cnt[i] == er.size and rows[i, :cnt[i]].tolist() == er.tolist(), i
+        assert dd[i, :cnt[i]].view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+    assert int(need.sum()) < nq // 2

@@ -222,3 +222,63 @@ def test_two_rank_ivf_search(tmp_path, n, dim, C, k, nprobe, flags, seed):
     mp.spawn(_ivf_search_worker, args=(2, port, n, dim, C, k, nprobe, flags, seed, str(tmp_path)), nprocs=2, join=True)
     for r in range(2):
         assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
+
+
+def _ivf_batch_worker(rank, world, port, n, dim, C, nq, k, nprobe, flags, seed, out_dir):
+    sys.path.insert(0, ROOT)
+    import oracle as O
+    from pq_vector_b200.sharded import ShardedBatchIvfSearch, ShardedIvfSearch, shard_counts, shard_index
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(seed)
+    data = rng.integers(0, 3, (n, dim)).astype(np.float32) if seed % 2 else rng.random((n, dim), dtype=np.float32)
+    cent = data[rng.choice(n, C, replace=False)].copy()
+    offsets, ids = O.inverted_lists(O.assign(data, cent), C)
+    queries = data[rng.integers(0, n, nq)].copy() if seed % 2 else rng.random((nq, dim), dtype=np.float32)
+    per = (n + world - 1) // world
+    bounds = [min(n, s * per) for s in range(world + 1)]
+    lo, hi = bounds[rank], bounds[rank + 1]
+    l_off, l_ids = shard_index(offsets, ids, lo, hi)
+    order = 1 if flags & 1 else 0
+
+    def cand(query, k_, nprobe_, flags_):
+        probe = O.find_closest_centroids(query, cent, nprobe_)
+        rows = O.candidate_rows(query, cent, l_off, l_ids, nprobe_)
+        d = O.distances(data[lo:hi][rows], query, order) if rows.size else np.empty(0, np.float32)
+        return (d.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.arange(rows.size, dtype=np.uint64), rows, probe
+
+    def batch(qs, k_, nprobe_, flags_, pos_base):   # the oracle standing in for IvfIndex.search_batch_keys
+        keys = np.full((qs.shape[0], k_ + 1), np.iinfo(np.uint64).max, dtype=np.uint64)
+        cnt = np.zeros(qs.shape[0], dtype=np.uint32)
+        for i, q in enumerate(qs):
+            rows = O.candidate_rows(q, cent, l_off, l_ids, nprobe_)
+            d = O.distances(data[lo:hi][rows], q, order) if rows.size else np.empty(0, np.float32)
+            kk = np.sort((d.view(np.uint32).astype(np.uint64) << np.uint64(32)) | (rows.astype(np.uint64) + np.uint64(pos_base)))[:k_ + 1]
+            keys[i, :kk.size] = kk
+            cnt[i] = kk.size
+        if seed == 6:
+            cnt[2] = 0xFFFFFFFF          # a slice that could not decide query 2 -> single-query route
+        return keys, cnt
+
+    single = ShardedIvfSearch(cand, shard_counts(offsets, ids, bounds), rank, lo, "cpu")
+    sb = ShardedBatchIvfSearch(batch, single, lo, "cpu")
+    rows, dd, cnt = sb.search(queries, k, nprobe, flags)
+    ok = True
+    for i, q in enumerate(queries):
+        er, ed = O.topk_rerank_gather(q, data, O.candidate_rows(q, cent, offsets, ids, nprobe), k, order, bool(flags & 2))
+        ok &= cnt[i] == er.size and rows[i, :cnt[i]].tolist() == er.tolist()
+        ok &= dd[i, :cnt[i]].view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+    replayed_ok = sb.last_replayed > 0 if seed % 2 or seed == 6 else True      # grid data / undecided slice: the replay route ran
+    np.save(os.path.join(out_dir, f"ok{rank}.npy"), np.array([int(ok and replayed_ok)]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("n,dim,C,nq,k,nprobe,flags,seed", [(2000, 8, 16, 12, 10, 4, 2, 2), (1500, 4, 9, 9, 20, 3, 1, 3),
+                                                             (900, 6, 30, 8, 50, 30, 3, 6)])
+def test_two_rank_batched_ivf_search(tmp_path, n, dim, C, nq, k, nprobe, flags, seed):
+    port = 35500 + (os.getpid() + seed) % 2000
+    mp.spawn(_ivf_batch_worker, args=(2, port, n, dim, C, nq, k, nprobe, flags, seed, str(tmp_path)), nprocs=2, join=True)
+    for r in range(2):
+        assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
