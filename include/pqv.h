@@ -321,6 +321,14 @@ PQV_API int pqv_vector_topk_indexed(pqv_ctx *ctx, uint64_t handle, uint64_t inde
                             uint32_t *out_row_idx, float *out_dist, uint32_t *out_count, uint64_t *out_candidate_rows,
                             uint64_t *out_rows_scored);
 
+/* n_queries executions of the operator that share one scan-subtree filter (row_mask as above, may be NULL) and have no
+ * candidate cap -- e.g. the same SQL text with different literals -- answered by one tensor-core pass over the table with
+ * the probe sets and the filter bitmap applied inside the pass; every query's result equals its own
+ * pqv_vector_topk_indexed call.  Output layout as pqv_l2_topk. */
+PQV_API int pqv_vector_topk_indexed_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *queries,
+                                  uint32_t n_queries, uint32_t k, uint32_t nprobe, uint32_t flags, const uint8_t *row_mask,
+                                  uint32_t *out_row_idx, float *out_dist, uint32_t *out_count);
+
 /* ---- coalescing front door for concurrent single-query callers ---------------------------------
  * The reference API is single-query (src/ivf/search.rs:49-54 `query: &[f32]`, src/df_vector/exec.rs:43) and its callers
  * are concurrent tasks (TopkBuilder::search is async; VectorTopKExec::execute is a stream::once per plan,

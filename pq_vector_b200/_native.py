@@ -99,6 +99,8 @@ SIGNATURES = {
                                             C.c_uint64, u64p, u32p, u32p]),
     "pqv_vector_topk_indexed": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint64,
                                           C.POINTER(C.c_uint8), u32p, f32p, u32p, u64p, u64p]),
+    "pqv_vector_topk_indexed_batch": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                C.POINTER(C.c_uint8), u32p, f32p, u32p]),
     "pqv_l2_topk_coalesced": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),
     "pqv_coalesce_config": (C.c_int, [ctxp, C.c_uint32, C.c_uint32]),
     "pqv_coalesce_stats": (C.c_int, [ctxp, u64p, u64p, u64p]),

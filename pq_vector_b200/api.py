@@ -485,6 +485,27 @@ class IvfIndex:
                                             _ptr(dist, C.c_float), C.byref(cnt), C.byref(cand), C.byref(scored)))
         return rows[:cnt.value].copy(), dist[:cnt.value].copy(), cand.value, scored.value
 
+    def vector_topk_batch(self, dataset: "Dataset", queries, k: int, nprobe: int, flags: int = N.PQV_SUM_SEQ, row_mask=None):
+        """nq VectorTopKExec executions sharing one filter in one pass (pqv_vector_topk_indexed_batch).
+        Returns (row_idx [nq,k] u32, dist [nq,k] f32, count [nq])."""
+        q = np.atleast_2d(_f32(queries))
+        if q.shape[1] != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.shape[1]}")
+        bits = None
+        if row_mask is not None:
+            m = np.ascontiguousarray(row_mask, dtype=bool)
+            if m.size != dataset.rows:
+                raise PqvError(N.PQV_EINVAL, f"row_mask has {m.size} entries, the table {dataset.rows} rows")
+            bits = np.packbits(m, bitorder="little")
+        nq, kk = q.shape[0], max(k, 1)
+        rows = np.zeros((nq, kk), dtype=np.uint32)
+        dist = np.zeros((nq, kk), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        _check(_lib.pqv_vector_topk_indexed_batch(self.ctx._h, dataset.handle, self.handle, _ptr(q, C.c_float), nq, k, nprobe, flags,
+                                                  _ptr(bits, C.c_uint8), _ptr(rows, C.c_uint32), _ptr(dist, C.c_float),
+                                                  _ptr(cnt, C.c_uint32)))
+        return rows, dist, cnt
+
     def drop(self):
         if self.handle:
             _check(_lib.pqv_ivf_drop(self.ctx._h, self.handle))

@@ -954,7 +954,7 @@ int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *q
 static int ivf_batch_masked(pqv_ctx *ctx, Dataset *ds, DeviceState &D, IvfIndex *ix, const float *queries, uint32_t n_queries,
                             uint32_t k, uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist,
                             uint32_t *out_count, std::vector<uint8_t> &handled, u64 *raw_keys, uint32_t *raw_count,
-                            uint32_t pos_base) {
+                            uint32_t pos_base, const uint8_t *h_row_mask = nullptr) {
     const uint32_t C = ix->n_clusters, dim = ds->dim, np = std::min(nprobe, C);
     handled.assign(n_queries, 0);
     ctx->last_batch = pqv_batch_timing{};
@@ -1003,7 +1003,15 @@ static int ivf_batch_masked(pqv_ctx *ctx, Dataset *ds, DeviceState &D, IvfIndex 
         pqv::probe_build_kernel<<<(uint32_t)(((u64)nq * np + 255) / 256), 256, 0, D.stream>>>(D.d_assign.p, nq, np, D.d_row_ids.p, qwords, D.vt_mask.p);
         CU_TRY(cudaGetLastError());
         CU_TRY(cudaMemcpyAsync(nan_flags.data(), D.d_row_ids.p, (size_t)nq * 4, cudaMemcpyDeviceToHost, D.stream));
-        BatchMask bm{ix->d_row_cluster.p, D.vt_mask.p, qwords};
+        const uint32_t *d_row_mask = nullptr;
+        if (h_row_mask) {  // the scan subtree's filter, shared by every query of the batch
+            const u64 n_words = (ds->n_rows + 31) / 32;
+            PQV_TRY(D.vt_bitmap.ensure(n_words));
+            CU_TRY(cudaMemsetAsync(D.vt_bitmap.p + (n_words - 1), 0, 4, D.stream));
+            CU_TRY(cudaMemcpyAsync(D.vt_bitmap.p, h_row_mask, (size_t)((ds->n_rows + 7) / 8), cudaMemcpyHostToDevice, D.stream));
+            d_row_mask = D.vt_bitmap.p;
+        }
+        BatchMask bm{ix->d_row_cluster.p, D.vt_mask.p, qwords, d_row_mask};
         PQV_TRY(batch_topk(ctx, D, *ds, ds->n_rows, dim, queries, nq, k, flags, out_row_idx, out_dist, out_count, handled, raw_keys,
                            raw_count, pos_base, &bm));
         ctx->batch_state.valid = false;  // the candidate segments left on the device are masked: not for the dense tie API
@@ -1154,6 +1162,60 @@ int pqv_ivf_search_candidates(pqv_ctx *ctx, uint64_t handle, uint64_t index, con
     if (!eo.keys.empty()) {
         memcpy(out_keys, eo.keys.data(), eo.keys.size() * 8);
         memcpy(out_rows, eo.rows.data(), eo.rows.size() * 4);
+    }
+    return PQV_OK;
+}
+
+// Batched VectorTopKExec over a resident indexed table: n_queries executions of the operator (exec.rs:207-277) that share
+// one scan subtree filter (row_mask, may be NULL), no candidate cap.  One masked tensor-core pass (probe sets AND filter
+// bitmap inside the epilogues); undecided queries go through pqv_vector_topk_indexed's single-query pipeline.
+int pqv_vector_topk_indexed_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *queries, uint32_t n_queries,
+                                  uint32_t k, uint32_t nprobe, uint32_t flags, const uint8_t *row_mask, uint32_t *out_row_idx,
+                                  float *out_dist, uint32_t *out_count) {
+    if (!ctx) return fail(PQV_EINVAL, "null ctx");
+    if (n_queries && (!queries || !out_row_idx || !out_dist || !out_count)) return fail(PQV_EINVAL, "null argument");
+    if (nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    IvfIndex *ix = find_index(ctx, index);
+    if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
+    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_vector_topk_indexed_batch needs a single-device dataset");
+    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    DeviceState &D = ctx->devs[ds->shards[0].di];
+    DevGuard guard(D.dev);
+    PQV_TRY(index_make_resident(D, *ix));
+    const uint32_t dim = ds->dim;
+    std::vector<uint8_t> handled;
+    PQV_TRY(ivf_batch_masked(ctx, ds, D, ix, queries, n_queries, k, nprobe, flags, out_row_idx, out_dist, out_count, handled,
+                             nullptr, nullptr, 0, row_mask));
+    for (uint32_t q = 0; q < n_queries; ++q) {
+        if (handled[q]) continue;
+        const float *qv = queries + (size_t)q * dim;
+        uint32_t *orow = out_row_idx + (size_t)q * k;
+        float *odist = out_dist + (size_t)q * k;
+        RowOrder ro;
+        ro.h_mask = row_mask;
+        bool done = false;
+        out_count[q] = 0;
+        if (ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids)
+            PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, qv, k, nprobe, flags, orow, odist, out_count + q, &done, &ro));
+        if (!done) {
+            PQV_TRY(index_host_ids(D, *ix));
+            std::vector<uint32_t> ranked, rows;
+            PQV_TRY(rank_clusters(D, *ix, qv, nprobe, ranked));
+            for (uint32_t c : ranked) rows.insert(rows.end(), ix->ids.begin() + ix->offsets[c], ix->ids.begin() + ix->offsets[c + 1]);
+            std::sort(rows.begin(), rows.end());
+            if (row_mask) {
+                size_t o = 0;
+                for (uint32_t r : rows)
+                    if (row_mask[r >> 3] & (1u << (r & 7))) rows[o++] = r;
+                rows.resize(o);
+            }
+            if (!rows.empty()) PQV_TRY(topk_one(ctx, *ds, qv, rows.data(), rows.size(), k, flags, orow, odist, out_count + q));
+        }
     }
     return PQV_OK;
 }

@@ -969,6 +969,7 @@ struct BatchParams {
     const uint32_t *row_cluster;  // [n] cluster of each row, 0xFFFFFFFF = in no list
     const uint32_t *probe_T;      // [C][qwords]
     uint32_t qwords;              // nq_pad / 32
+    const uint32_t *row_mask;     // [ceil(n / 32)] or null: bit r = row r passes the scan subtree's filter (all queries)
 };
 
 template <int MODE>
@@ -996,7 +997,9 @@ struct BatchEpi {
             const float x2s = (MODE == BATCH_SAMPLE) ? x2c + rho : x2c - rho;
             // IVF mask: the probe words of this row's cluster (one word per 32 queries)
             const uint32_t *probe_row = nullptr;
-            if (p.row_cluster && valid) {
+            bool dead = false;  // filtered out for every query
+            if (p.row_mask && valid) dead = !((__ldg(p.row_mask + (row >> 5)) >> (row & 31)) & 1u);
+            if (p.row_cluster && valid && !dead) {
                 const uint32_t cl = p.row_cluster[row];
                 if (cl != 0xFFFFFFFFu) probe_row = p.probe_T + (size_t)cl * p.qwords;
             }
@@ -1009,7 +1012,7 @@ struct BatchEpi {
                     float v[32];
                     tmem_ld32(taddr + ch * 32u, v);
                     const uint32_t q0 = nb * BN + ch * 32u;
-                    const uint32_t pm = !p.row_cluster ? 0xFFFFFFFFu : (probe_row ? __ldg(probe_row + (q0 >> 5)) : 0u);
+                    const uint32_t pm = dead ? 0u : (!p.row_cluster ? 0xFFFFFFFFu : (probe_row ? __ldg(probe_row + (q0 >> 5)) : 0u));
                     if (MODE == BATCH_SAMPLE) {
 #pragma unroll
                         for (int i4 = 0; i4 < 8; ++i4) {

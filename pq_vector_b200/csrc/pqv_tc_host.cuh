@@ -220,6 +220,7 @@ struct BatchMask {
     const uint32_t *row_cluster;  // device, [n]
     const uint32_t *probe_T;      // device, [C][qwords]
     uint32_t qwords;              // ceil(nq / BN) * BN / 32
+    const uint32_t *row_mask;     // device, [ceil(n / 32)] or null
 };
 
 bool batch_path_applies(const Dataset &ds, const float *d_rows, uint32_t nq, uint32_t k) {
@@ -340,6 +341,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     p.row_cluster = bmask ? bmask->row_cluster : nullptr;
     p.probe_T = bmask ? bmask->probe_T : nullptr;
     p.qwords = bmask ? bmask->qwords : 0;
+    p.row_mask = bmask ? bmask->row_mask : nullptr;
     // phase A: upper bounds over the first S rows -> theta_q
     p.n = S;
     if (tg.pair)

@@ -474,3 +474,31 @@ def test_sharded_batched_ivf_keys_merge_to_the_whole_table_answer(ctx):
         assert cnt[i] == er.size and rows[i, :cnt[i]].tolist() == er.tolist(), i
         assert dd[i, :cnt[i]].view(np.uint32).tolist() == ed.view(np.uint32).tolist()
     assert int(need.sum()) < nq // 2
+
+
+@pytest.mark.parametrize("n,dim,C,nq,grid", [(40000, 64, 48, 48, False), (9000, 8, 21, 13, True)])
+def test_batched_vector_topk_with_a_shared_filter(ctx, n, dim, C, nq, grid):
+    rng = np.random.default_rng(n * 3 + nq)
+    data = rng.integers(0, 3, (n, dim)).astype(np.float32) if grid else rng.random((n, dim), dtype=np.float32)
+    cent = data[rng.choice(n, C, replace=False)].copy() + (0.0 if grid else 0.01)
+    offsets, ids = O.inverted_lists(O.assign(data, cent, workers=2), C)
+    ix = ctx.ivf_from_bytes(O.index_to_bytes(dim, cent, offsets, ids))
+    ds = ctx.dataset_from(data)
+    queries = (data[rng.integers(0, n, nq)] if grid else rng.random((nq, dim), dtype=np.float32)).copy()
+    used = 0
+    for mask in (None, rng.random(n) < 0.3, np.arange(n) >= n // 2, np.zeros(n, bool)):
+        for nprobe in (2, C):
+            for k, flags in ((10, SEQ), (50, SQRT)):
+                rows, dist, cnt = ix.vector_topk_batch(ds, queries, k, nprobe, flags, mask)
+                bt = ctx.last_batch_timing()
+                used += bt["queries"] > 0 and not bt["declined"]
+                for i in range(0, nq, max(1, nq // 12)):
+                    er, ed, _, _ = _expected_vector_topk(queries[i], data, cent, offsets, ids, k, nprobe,
+                                                         1 if flags & SEQ else 0, bool(flags & SQRT), None, mask)
+                    assert cnt[i] == er.size, (i, nprobe, k, bt)
+                    assert rows[i, :cnt[i]].tolist() == er.tolist(), (i, nprobe, k, bt)
+                    assert dist[i, :cnt[i]].view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+    if not grid:
+        assert used > 0
+    ix.drop()
+    ds.drop()
