@@ -341,6 +341,10 @@ PQV_API int pqv_vector_topk_indexed_batch(pqv_ctx *ctx, uint64_t handle, uint64_
  * the leading caller linger that long for a burst to assemble (default 0: batches form only behind a running pass). */
 PQV_API int pqv_l2_topk_coalesced(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags,
                           uint32_t *out_row_idx, float *out_dist, uint32_t *out_count);
+/* the same front door for TopkBuilder::search callers (src/ivf/search.rs:76-80 is an async fn): the single-query contract of
+ * pqv_ivf_search; concurrent calls with the same (table, index, k, nprobe, flags) are answered by one pqv_ivf_search_batch. */
+PQV_API int pqv_ivf_search_coalesced(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k,
+                             uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count);
 PQV_API int pqv_coalesce_config(pqv_ctx *ctx, uint32_t max_batch, uint32_t window_us);
 PQV_API int pqv_coalesce_stats(pqv_ctx *ctx, uint64_t *out_queries, uint64_t *out_batches, uint64_t *out_max_batch);
 

@@ -102,6 +102,8 @@ SIGNATURES = {
     "pqv_vector_topk_indexed_batch": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                                 C.POINTER(C.c_uint8), u32p, f32p, u32p]),
     "pqv_l2_topk_coalesced": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, u32p, f32p, u32p]),
+    "pqv_ivf_search_coalesced": (C.c_int, [ctxp, C.c_uint64, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p,
+                                           u32p]),
     "pqv_coalesce_config": (C.c_int, [ctxp, C.c_uint32, C.c_uint32]),
     "pqv_coalesce_stats": (C.c_int, [ctxp, u64p, u64p, u64p]),
     "pqv_array_distance": (C.c_int, [ctxp, C.c_uint64, f64p, C.c_uint32, C.c_uint32, f64p]),

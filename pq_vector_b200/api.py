@@ -417,6 +417,18 @@ class IvfIndex:
                                    _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), C.byref(cnt)))
         return rows[:cnt.value].copy(), dist[:cnt.value].copy()
 
+    def search_coalesced(self, dataset: "Dataset", query, k: int, nprobe: int, flags: int = N.PQV_SQRT):
+        """TopkBuilder::search through the coalescing front door (pqv_ivf_search_coalesced): call from many threads."""
+        q = _f32(query)
+        if q.size != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.size}")
+        rows = np.zeros(max(k, 1), dtype=np.uint32)
+        dist = np.zeros(max(k, 1), dtype=np.float32)
+        cnt = C.c_uint32()
+        _check(_lib.pqv_ivf_search_coalesced(self.ctx._h, dataset.handle, self.handle, _ptr(q, C.c_float), k, nprobe, flags,
+                                             _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), C.byref(cnt)))
+        return rows[:cnt.value].copy(), dist[:cnt.value].copy()
+
     def search_batch(self, dataset: "Dataset", queries, k: int, nprobe: int, flags: int = N.PQV_SQRT):
         """nq independent searches in one pass over the table (pqv_ivf_search_batch).
         Returns (row_idx [nq,k] u32, dist [nq,k] f32, count [nq])."""

@@ -184,9 +184,11 @@ int pqv_coalesce_stats(pqv_ctx *ctx, uint64_t *out_queries, uint64_t *out_batche
     return PQV_OK;
 }
 
-int pqv_l2_topk_coalesced(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t *out_row_idx,
-                          float *out_dist, uint32_t *out_count) {
+// index == 0: brute force (pqv_l2_topk); otherwise an IVF search over (table, index) with `nprobe` (pqv_ivf_search)
+static int coalesced_submit(pqv_ctx *ctx, uint64_t handle, uint64_t index, uint32_t nprobe, const float *query, uint32_t k,
+                            uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
     if (!ctx || !query || !out_row_idx || !out_dist || !out_count) return fail(PQV_EINVAL, "null argument");
+    if (index && nprobe == 0) return fail(PQV_EINVAL, "nprobe must be > 0");  // src/ivf/search.rs:72
     typedef pqv_ctx::CoalesceReq Req;
     pqv_ctx::Coalescer &co = ctx->co;
     // reject what the reference rejects per call (search.rs:66-74, 91-98) before the request can join a batch.  ctx->mu
@@ -211,6 +213,8 @@ int pqv_l2_topk_coalesced(pqv_ctx *ctx, uint64_t handle, const float *query, uin
     PQV_TRY(check_topk_args(k, dim, flags));
     Req me;
     me.handle = handle;
+    me.index = index;
+    me.nprobe = nprobe;
     me.k = k;
     me.flags = flags;
     me.query = query;
@@ -238,7 +242,9 @@ int pqv_l2_topk_coalesced(pqv_ctx *ctx, uint64_t handle, const float *query, uin
     std::vector<Req *> batch;
     std::deque<Req *> rest;
     for (Req *r : co.pending) {
-        if (batch.size() < co.max_batch && r->handle == me.handle && r->k == me.k && r->flags == me.flags) batch.push_back(r);
+        if (batch.size() < co.max_batch && r->handle == me.handle && r->index == me.index && r->nprobe == me.nprobe &&
+            r->k == me.k && r->flags == me.flags)
+            batch.push_back(r);
         else rest.push_back(r);
     }
     co.pending.swap(rest);
@@ -249,14 +255,16 @@ int pqv_l2_topk_coalesced(pqv_ctx *ctx, uint64_t handle, const float *query, uin
     std::string err;
     try {  // nothing may escape before the followers are released below
         if (nq == 1) {
-            rc = pqv_l2_topk(ctx, handle, query, 1, k, flags, out_row_idx, out_dist, out_count);
+            rc = index ? pqv_ivf_search(ctx, handle, index, query, k, nprobe, flags, out_row_idx, out_dist, out_count)
+                       : pqv_l2_topk(ctx, handle, query, 1, k, flags, out_row_idx, out_dist, out_count);
             if (rc) err = g_err;
         } else {
             std::vector<float> q((size_t)nq * dim);
             std::vector<uint32_t> rows((size_t)nq * k), counts(nq);
             std::vector<float> dist((size_t)nq * k);
             for (uint32_t i = 0; i < nq; ++i) memcpy(q.data() + (size_t)i * dim, batch[i]->query, (size_t)dim * 4);
-            rc = pqv_l2_topk(ctx, handle, q.data(), nq, k, flags, rows.data(), dist.data(), counts.data());
+            rc = index ? pqv_ivf_search_batch(ctx, handle, index, q.data(), nq, k, nprobe, flags, rows.data(), dist.data(), counts.data())
+                       : pqv_l2_topk(ctx, handle, q.data(), nq, k, flags, rows.data(), dist.data(), counts.data());
             if (rc) err = g_err;
             else
                 for (uint32_t i = 0; i < nq; ++i) {
@@ -286,6 +294,18 @@ int pqv_l2_topk_coalesced(pqv_ctx *ctx, uint64_t handle, const float *query, uin
     co.cv.notify_all();
     if (rc) g_err = err;
     return rc;
+}
+
+
+int pqv_l2_topk_coalesced(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t *out_row_idx,
+                          float *out_dist, uint32_t *out_count) {
+    return coalesced_submit(ctx, handle, 0, 0, query, k, flags, out_row_idx, out_dist, out_count);
+}
+
+int pqv_ivf_search_coalesced(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k, uint32_t nprobe,
+                             uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
+    if (!index) return fail(PQV_EHANDLE, "unknown index handle 0");
+    return coalesced_submit(ctx, handle, index, nprobe, query, k, flags, out_row_idx, out_dist, out_count);
 }
 
 }  // extern "C"

@@ -531,6 +531,8 @@ struct pqv_ctx {
     // coalescing front door for concurrent single-query callers (pqv_l2_topk_coalesced)
     struct CoalesceReq {
         u64 handle = 0;
+        u64 index = 0;       // 0: brute force (pqv_l2_topk); else the IVF index (pqv_ivf_search)
+        uint32_t nprobe = 0;
         uint32_t k = 0, flags = 0;
         const float *query = nullptr;
         uint32_t *rows = nullptr;

@@ -102,3 +102,41 @@ def test_errors_stay_with_their_caller(ctx):
     r, d = ds.l2_topk_coalesced(np.zeros(8, np.float32), 5)      # the front door still works afterwards
     assert r.size == 5
     ds.drop()
+
+
+def test_concurrent_ivf_searches_are_coalesced(ctx):
+    """TopkBuilder::search callers (search.rs:76-80 is async): concurrent single-query IVF searches through
+    pqv_ivf_search_coalesced get exactly their own result; brute-force and IVF requests never share a batch."""
+    n, dim, C, k, nprobe, nthreads = 50000, 64, 40, 10, 5, 40
+    rng = np.random.default_rng(12)
+    data = rng.random((n, dim), dtype=np.float32)
+    cent = data[rng.choice(n, C, replace=False)].copy() + 0.01
+    offsets, ids = O.inverted_lists(O.assign(data, cent, workers=2), C)
+    ix = ctx.ivf_from_bytes(O.index_to_bytes(dim, cent, offsets, ids))
+    ds = ctx.dataset_from(data)
+    queries = rng.random((nthreads, dim), dtype=np.float32)
+    ctx.coalesce_config(1024, 30000)
+    before = ctx.coalesce_stats()
+
+    def fn(i):
+        if i % 4 == 3:
+            return ds.l2_topk_coalesced(queries[i], k, SQRT)
+        return ix.search_coalesced(ds, queries[i], k, nprobe, SQRT)
+
+    out, errs = run_threads(nthreads, fn)
+    assert not errs, errs
+    after = ctx.coalesce_stats()
+    assert after["queries"] - before["queries"] == nthreads and after["max_batch"] >= 4
+    for i in range(nthreads):
+        if i % 4 == 3:
+            er, ed = O.topk_rerank(queries[i], data, None, k, 0, True)
+        else:
+            er, ed = O.topk_rerank_gather(queries[i], data, O.candidate_rows(queries[i], cent, offsets, ids, nprobe), k, 0, True)
+        assert out[i][0].tolist() == er.tolist(), i
+        assert out[i][1].view(np.uint32).tolist() == ed.view(np.uint32).tolist(), i
+    import pq_vector_b200 as P
+    with pytest.raises(P.PqvError, match="nprobe must be > 0"):
+        ix.search_coalesced(ds, queries[0], k, 0)
+    ctx.coalesce_config(1024, 0)
+    ix.drop()
+    ds.drop()
