@@ -332,7 +332,9 @@ class TopkBuilder:
         ds, _, dim = _resident_table(self._path, column)
         if dim != ix.dim:
             raise PqVectorError(f"Embedding dimension mismatch: expected {ix.dim}, got {dim}")  # search.rs:224-231
-        rows, dist = ix.search(ds, self._query, self._k, self._nprobe, N.PQV_SQRT)
+        # through the coalescing front door: concurrent search() callers (the reference's is an async fn, search.rs:76-80)
+        # are answered together by one batched pass; a lone caller gets the plain single-query pipeline
+        rows, dist = ix.search_coalesced(ds, self._query, self._k, self._nprobe, N.PQV_SQRT)
         return [SearchResult(int(r), float(d)) for r, d in zip(rows, dist)]
 
 
