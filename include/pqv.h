@@ -366,6 +366,11 @@ PQV_API int pqv_array_distance(pqv_ctx *ctx, uint64_t handle, const double *quer
                        double *out /* n_rows */);
 PQV_API int pqv_array_distance_topk(pqv_ctx *ctx, uint64_t handle, const double *query, uint32_t query_len, uint32_t metric,
                             uint32_t k, uint32_t *out_row_idx, double *out_dist, uint32_t *out_count);
+/* the same under a WHERE clause: row_mask = the filter of the scan subtree evaluated over the table's rows (an Arrow boolean
+ * buffer: bit (r & 7) of byte (r >> 3) = row r passes; NULL = no filter); filtered rows never reach the sort. */
+PQV_API int pqv_array_distance_topk_filtered(pqv_ctx *ctx, uint64_t handle, const double *query, uint32_t query_len,
+                                     uint32_t metric, uint32_t k, const uint8_t *row_mask, uint32_t *out_row_idx,
+                                     double *out_dist, uint32_t *out_count);
 
 #ifdef __cplusplus
 }

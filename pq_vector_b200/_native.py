@@ -108,6 +108,8 @@ SIGNATURES = {
     "pqv_coalesce_stats": (C.c_int, [ctxp, u64p, u64p, u64p]),
     "pqv_array_distance": (C.c_int, [ctxp, C.c_uint64, f64p, C.c_uint32, C.c_uint32, f64p]),
     "pqv_array_distance_topk": (C.c_int, [ctxp, C.c_uint64, f64p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f64p, u32p]),
+    "pqv_array_distance_topk_filtered": (C.c_int, [ctxp, C.c_uint64, f64p, C.c_uint32, C.c_uint32, C.c_uint32,
+                                                   C.POINTER(C.c_uint8), u32p, f64p, u32p]),
 }
 
 

@@ -279,15 +279,23 @@ class Dataset:
         _check(_lib.pqv_array_distance(self.ctx._h, self.handle, _ptr(q, C.c_double), q.size, metric, _ptr(out, C.c_double)))
         return out
 
-    def array_distance_topk(self, query, k: int, metric: int = N.PQV_METRIC_L2):
-        """`ORDER BY array_distance(column, literal) LIMIT k` without an index: (row_idx u32, distance f64), ascending."""
+    def array_distance_topk(self, query, k: int, metric: int = N.PQV_METRIC_L2, row_mask=None):
+        """`[WHERE ..] ORDER BY array_distance(column, literal) LIMIT k` without an index: (row_idx u32, distance f64),
+        ascending; row_mask (bool per row, optional) = the WHERE clause evaluated over the table."""
         q = np.ascontiguousarray(query, dtype=np.float64).ravel()
         kk = max(k, 1)
         rows = np.zeros(kk, dtype=np.uint32)
         dist = np.zeros(kk, dtype=np.float64)
         cnt = C.c_uint32()
-        _check(_lib.pqv_array_distance_topk(self.ctx._h, self.handle, _ptr(q, C.c_double), q.size, metric, k,
-                                            _ptr(rows, C.c_uint32), _ptr(dist, C.c_double), C.byref(cnt)))
+        bits = None
+        if row_mask is not None:
+            m = np.ascontiguousarray(row_mask, dtype=bool)
+            if m.size != self.rows:
+                raise PqvError(N.PQV_EINVAL, f"row_mask has {m.size} entries, the table {self.rows} rows")
+            bits = np.packbits(m, bitorder="little")
+        _check(_lib.pqv_array_distance_topk_filtered(self.ctx._h, self.handle, _ptr(q, C.c_double), q.size, metric, k,
+                                                     _ptr(bits, C.c_uint8), _ptr(rows, C.c_uint32), _ptr(dist, C.c_double),
+                                                     C.byref(cnt)))
         return rows[:cnt.value].copy(), dist[:cnt.value].copy()
 
     def l2_topk_gather(self, query, row_ids, k: int, flags: int = N.PQV_SQRT):

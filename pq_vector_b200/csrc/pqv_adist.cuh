@@ -195,7 +195,13 @@ __global__ void sel_init_kernel(SelState *st, const uint32_t k) {
 
 // pass 0..7: digit = byte (7 - pass) of the ordered bits among keys whose higher bytes equal the prefix;
 // pass 8..11: digit = byte (11 - pass) of the row among keys with bits == prefix and higher row bytes equal.
-__global__ void __launch_bounds__(256) sel_hist_kernel(const double *__restrict__ col, const u64 n, const int pass, SelState *st) {
+// row_mask (may be null): bit r set = row r takes part (the scan subtree's filter of a stock-plan query)
+__device__ __forceinline__ bool sel_row_live(const uint32_t *__restrict__ row_mask, const u64 i) {
+    return !row_mask || ((row_mask[i >> 5] >> (i & 31)) & 1u);
+}
+
+__global__ void __launch_bounds__(256) sel_hist_kernel(const double *__restrict__ col, const u64 n, const int pass, SelState *st,
+                                                       const uint32_t *__restrict__ row_mask) {
     __shared__ uint32_t s_hist[256];
     const uint32_t tid = threadIdx.x;
     s_hist[tid] = 0;
@@ -206,7 +212,7 @@ __global__ void __launch_bounds__(256) sel_hist_kernel(const double *__restrict_
     for (u64 i = (u64)blockIdx.x * 256 + tid; i < n_round; i += (u64)gridDim.x * 256) {
         bool take = false;
         uint32_t digit = 0;
-        if (i < n) {
+        if (i < n && sel_row_live(row_mask, i)) {
             const u64 u = f64_ordered_bits(col[i]);
             if (pass < 8) {
                 const int sh = 8 * (7 - pass);
@@ -249,10 +255,12 @@ __global__ void sel_pick_kernel(const int pass, SelState *st) {
 // every key <= (prefix, prefix_row): exactly min(k, n) of them, in arbitrary order (the host sorts k items)
 __global__ void __launch_bounds__(256) sel_collect_kernel(const double *__restrict__ col, const u64 n, SelState *st,
                                                           const uint32_t cap, double *__restrict__ out_dist,
-                                                          uint32_t *__restrict__ out_row) {
+                                                          uint32_t *__restrict__ out_row,
+                                                          const uint32_t *__restrict__ row_mask) {
     const u64 prefix = st->prefix;
     const uint32_t prow = st->prefix_row;
     for (u64 i = (u64)blockIdx.x * 256 + threadIdx.x; i < n; i += (u64)gridDim.x * 256) {
+        if (!sel_row_live(row_mask, i)) continue;
         const double d = col[i];
         const u64 u = f64_ordered_bits(d);
         if (u < prefix || (u == prefix && (uint32_t)i <= prow)) {

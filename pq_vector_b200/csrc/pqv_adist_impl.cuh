@@ -93,8 +93,8 @@ int pqv_array_distance(pqv_ctx *ctx, uint64_t handle, const double *query, uint3
     return PQV_OK;
 }
 
-int pqv_array_distance_topk(pqv_ctx *ctx, uint64_t handle, const double *query, uint32_t query_len, uint32_t metric, uint32_t k,
-                            uint32_t *out_row_idx, double *out_dist, uint32_t *out_count) {
+static int adist_topk_impl(pqv_ctx *ctx, uint64_t handle, const double *query, uint32_t query_len, uint32_t metric, uint32_t k,
+                           const uint8_t *row_mask, uint32_t *out_row_idx, double *out_dist, uint32_t *out_count) {
     if (!ctx || !out_count) return fail(PQV_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
     Dataset *ds = nullptr;
@@ -104,10 +104,27 @@ int pqv_array_distance_topk(pqv_ctx *ctx, uint64_t handle, const double *query, 
     *out_count = 0;
     if (ds->n_rows == 0) return PQV_OK;
     const u64 n = ds->n_rows;
-    const uint32_t k_eff = (uint32_t)std::min<u64>(k, n);
     Shard &sh = ds->shards[0];
     DeviceState &D = ctx->devs[sh.di];
     DevGuard guard(D.dev);
+    // the scan subtree's filter: rows whose bit is clear never reach the sort (FilterExec below SortExec)
+    const uint32_t *d_mask = nullptr;
+    u64 live = n;
+    if (row_mask) {
+        const u64 n_words = (n + 31) / 32;
+        PQV_TRY(D.vt_bitmap.ensure(n_words));
+        CU_TRY(cudaMemsetAsync(D.vt_bitmap.p + (n_words - 1), 0, 4, D.stream));
+        CU_TRY(cudaMemcpyAsync(D.vt_bitmap.p, row_mask, (size_t)((n + 7) / 8), cudaMemcpyHostToDevice, D.stream));
+        d_mask = D.vt_bitmap.p;
+        live = 0;
+        for (u64 i = 0; i < n / 8; ++i) live += (u64)__builtin_popcount(row_mask[i]);
+        for (u64 r = n / 8 * 8; r < n; ++r) live += (row_mask[r >> 3] >> (r & 7)) & 1u;
+        if (live == 0) {
+            CU_TRY(cudaStreamSynchronize(D.stream));
+            return PQV_OK;
+        }
+    }
+    const uint32_t k_eff = (uint32_t)std::min<u64>(k, live);
     PQV_TRY(D.ad_col.ensure(n));
     PQV_TRY(D.ad_state.ensure(1));
     PQV_TRY(D.ad_out_dist.ensure(k_eff));
@@ -121,10 +138,10 @@ int pqv_array_distance_topk(pqv_ctx *ctx, uint64_t handle, const double *query, 
     const uint32_t hgrid = (uint32_t)std::max<u64>(1, std::min<u64>((u64)D.sm_count * 8, (n + 255) / 256));
     pqv::sel_init_kernel<<<1, 256, 0, D.stream>>>(D.ad_state.p, k_eff);
     for (int pass = 0; pass < 12; ++pass) {
-        pqv::sel_hist_kernel<<<hgrid, 256, 0, D.stream>>>(D.ad_col.p, n, pass, D.ad_state.p);
+        pqv::sel_hist_kernel<<<hgrid, 256, 0, D.stream>>>(D.ad_col.p, n, pass, D.ad_state.p, d_mask);
         pqv::sel_pick_kernel<<<1, 256, 0, D.stream>>>(pass, D.ad_state.p);
     }
-    pqv::sel_collect_kernel<<<hgrid, 256, 0, D.stream>>>(D.ad_col.p, n, D.ad_state.p, k_eff, D.ad_out_dist.p, D.ad_out_row.p);
+    pqv::sel_collect_kernel<<<hgrid, 256, 0, D.stream>>>(D.ad_col.p, n, D.ad_state.p, k_eff, D.ad_out_dist.p, D.ad_out_row.p, d_mask);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(D.ev[2], D.stream));
     CU_TRY(cudaMemcpyAsync(D.h_ad_dist.p, D.ad_out_dist.p, (size_t)k_eff * 8, cudaMemcpyDeviceToHost, D.stream));
@@ -163,6 +180,17 @@ int pqv_array_distance_topk(pqv_ctx *ctx, uint64_t handle, const double *query, 
     }
     *out_count = k_eff;
     return PQV_OK;
+}
+
+int pqv_array_distance_topk(pqv_ctx *ctx, uint64_t handle, const double *query, uint32_t query_len, uint32_t metric, uint32_t k,
+                            uint32_t *out_row_idx, double *out_dist, uint32_t *out_count) {
+    return adist_topk_impl(ctx, handle, query, query_len, metric, k, nullptr, out_row_idx, out_dist, out_count);
+}
+
+int pqv_array_distance_topk_filtered(pqv_ctx *ctx, uint64_t handle, const double *query, uint32_t query_len, uint32_t metric,
+                                     uint32_t k, const uint8_t *row_mask, uint32_t *out_row_idx, double *out_dist,
+                                     uint32_t *out_count) {
+    return adist_topk_impl(ctx, handle, query, query_len, metric, k, row_mask, out_row_idx, out_dist, out_count);
 }
 
 // ---- coalescing front door ---------------------------------------------------------------------------------------------

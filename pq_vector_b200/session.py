@@ -251,14 +251,7 @@ class DataFrame:
             if dim != q.literal.size:
                 raise PqVectorError("Both arrays must have the same length")
             scanned += n
-            if masks[f] is None:
-                r, d = ds.array_distance_topk(q.literal, q.k)
-            else:
-                col = ds.array_distance(q.literal)
-                rows = np.nonzero(masks[f])[0]
-                key = np.where(np.isnan(col[rows]), np.inf, col[rows])
-                order = np.lexsort((rows, np.isnan(col[rows]), key))[:q.k]     # f64 order, NaN last, ties by row
-                r, d = rows[order], col[rows][order]
+            r, d = ds.array_distance_topk(q.literal, q.k, row_mask=masks[f])      # the filter is applied on the device
             found += [(float(dd), f, int(rr)) for dd, rr in zip(d, r)]
         self.metrics = {"rows_scanned": scanned, "files": len(files), "k": q.k, "query_dim": int(q.literal.size),
                         "column": q.column}

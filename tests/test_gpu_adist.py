@@ -127,3 +127,26 @@ def test_large_table_properties(ctx):
     t = ctx.last_timing()
     assert t["scan_bytes"] == n * dim * 4
     ds.drop()
+
+
+def test_topk_under_a_filter(ctx):
+    """WHERE below the sort: rows whose mask bit is clear never reach the top-k (pqv_array_distance_topk_filtered)."""
+    import pq_vector_b200 as P
+    rng = np.random.default_rng(21)
+    n, dim = 33_333, 48
+    data = rng.integers(0, 4, (n, dim)).astype(np.float32)          # many equal distances: ties by row under the mask too
+    q = rng.random(dim)
+    ds = ctx.dataset_from(data)
+    for mask in (rng.random(n) < 0.5, np.arange(n) % 97 == 3, np.zeros(n, bool), np.ones(n, bool)):
+        keep = np.nonzero(mask)[0]
+        for k in (1, 10, 500):
+            rows, dist = ds.array_distance_topk(q, k, row_mask=mask)
+            if keep.size == 0:
+                assert rows.size == 0
+                continue
+            er, ed = O.array_distance_topk(data[keep], q, k)
+            assert rows.tolist() == keep[er].tolist(), k
+            assert bits(dist).tolist() == bits(ed).tolist()
+    with pytest.raises(P.PqvError, match="row_mask has"):
+        ds.array_distance_topk(q, 3, row_mask=np.ones(5, bool))
+    ds.drop()
