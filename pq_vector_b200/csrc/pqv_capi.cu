@@ -393,7 +393,8 @@ struct DeviceState {
 };
 
 constexpr size_t APPEND_CHUNK = 8u << 20;
-constexpr size_t APPEND_STAGED_MIN = 32u << 20;
+constexpr size_t APPEND_STAGED_MIN = 2u << 20;   // below this one plain copy is as fast
+constexpr size_t APPEND_CHUNK_MIN = 512u << 10;
 constexpr size_t APPEND_MAX_LANES = 8;
 
 // persistent worker threads (thread creation + the CUDA runtime's per-thread set-up cost ~10 ms per call otherwise)
@@ -408,7 +409,7 @@ struct AppendPool {
     DeviceState *D = nullptr;
     unsigned char *dst = nullptr;
     const unsigned char *src = nullptr;
-    size_t bytes = 0, n_chunks = 0, T = 0;
+    size_t bytes = 0, n_chunks = 0, T = 0, chunk = APPEND_CHUNK;
     cudaError_t errs[APPEND_MAX_LANES];
 
     void lane_run(size_t t) {
@@ -417,7 +418,7 @@ struct AppendPool {
         size_t turn = 0;
         for (size_t c = t; c < n_chunks && e == cudaSuccess; c += T, ++turn) {
             const int b = (int)(turn & 1);
-            const size_t off = c * APPEND_CHUNK, len = std::min(APPEND_CHUNK, bytes - off);
+            const size_t off = c * chunk, len = std::min(chunk, bytes - off);
             e = cudaEventSynchronize(L.ev[b]);  // the DMA that last read this staging buffer is done
             if (e != cudaSuccess) break;
             memcpy(L.buf[b].p, src + off, len);
@@ -1175,8 +1176,10 @@ static int grow_shard(pqv_ctx *ctx, Dataset &ds, Shard &sh, u64 need_rows) {
 
 static int append_staged(DeviceState &D, unsigned char *dst, const unsigned char *src, size_t bytes) {
     const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
-    const size_t n_chunks = (bytes + APPEND_CHUNK - 1) / APPEND_CHUNK;
     const size_t lanes = std::min<size_t>(APPEND_MAX_LANES, std::max<size_t>(1, hw / 2));
+    // a record batch (a few MB) is cut into one piece per lane so that the host copies still run in parallel
+    const size_t chunk = std::min(APPEND_CHUNK, std::max(APPEND_CHUNK_MIN, (bytes / lanes + 4095) & ~(size_t)4095));
+    const size_t n_chunks = (bytes + chunk - 1) / chunk;
     if (D.lanes.size() < lanes) D.lanes.resize(lanes);
     for (size_t t = 0; t < lanes; ++t) {
         DeviceState::AppendLane &L = D.lanes[t];
@@ -1199,6 +1202,7 @@ static int append_staged(DeviceState &D, unsigned char *dst, const unsigned char
         P.src = src;
         P.bytes = bytes;
         P.n_chunks = n_chunks;
+        P.chunk = chunk;
         P.T = T;
         P.pending = T;
         for (auto &e : P.errs) e = cudaSuccess;
