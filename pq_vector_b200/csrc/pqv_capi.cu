@@ -1385,8 +1385,29 @@ int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_
     if (n_queries && ds->n_rows && batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k)) {
         DeviceState &D = ctx->devs[ds->shards[0].di];
         DevGuard guard(D.dev);
-        PQV_TRY(batch_topk(ctx, D, *ds, ds->n_rows, ds->dim, queries, n_queries, k, flags, out_row_idx, out_dist, out_count,
-                           handled));
+        // at most BATCH_MAX_QUERIES queries per pass over the table (the pass' scratch grows with the batch)
+        pqv_batch_timing total{};
+        std::vector<uint8_t> part;
+        for (uint32_t q0 = 0; q0 < n_queries; q0 += BATCH_MAX_QUERIES) {
+            const uint32_t nq = std::min(BATCH_MAX_QUERIES, n_queries - q0);
+            if (nq < BATCH_MIN_QUERIES) break;  // a short tail takes the single-query scans
+            PQV_TRY(batch_topk(ctx, D, *ds, ds->n_rows, ds->dim, queries + (size_t)q0 * ds->dim, nq, k, flags,
+                               out_row_idx + (size_t)q0 * k, out_dist + (size_t)q0 * k, out_count + q0, part));
+            for (uint32_t i = 0; i < nq; ++i) handled[q0 + i] = part[i];
+            const pqv_batch_timing &b = ctx->last_batch;
+            total.queries += b.queries;
+            total.declined |= b.declined;
+            total.tie_queries += b.tie_queries;
+            total.rows = b.rows;
+            total.sample_rows = b.sample_rows;
+            total.candidates += b.candidates;
+            total.prep_ms += b.prep_ms;
+            total.sample_ms += b.sample_ms;
+            total.filter_ms += b.filter_ms;
+            total.rerank_ms += b.rerank_ms;
+            total.total_ms += b.total_ms;
+        }
+        ctx->last_batch = total;
     }
     for (uint32_t q = 0; q < n_queries; ++q)
         if (!handled[q])
@@ -1466,6 +1487,8 @@ int pqv_l2_topk_batch_keys(pqv_ctx *ctx, uint64_t handle, const float *queries, 
         for (uint32_t q = 0; q < n_queries; ++q) out_count[q] = 0;
         return PQV_OK;
     }
+    if (n_queries > BATCH_MAX_QUERIES)
+        return fail(PQV_ELIMIT, "at most %u queries per pqv_l2_topk_batch_keys call (got %u)", BATCH_MAX_QUERIES, n_queries);
     if (n_queries && batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k)) {
         DeviceState &D = ctx->devs[ds->shards[0].di];
         DevGuard guard(D.dev);

@@ -1049,9 +1049,13 @@ int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const fl
     DevGuard guard(D.dev);
     PQV_TRY(index_make_resident(D, *ix));
     const uint32_t C = ix->n_clusters, dim = ds->dim;
-    std::vector<uint8_t> handled;
-    PQV_TRY(ivf_batch_masked(ctx, ds, D, ix, queries, n_queries, k, nprobe, flags, out_row_idx, out_dist, out_count, handled,
-                             nullptr, nullptr, 0));
+    std::vector<uint8_t> handled(n_queries, 0), part;
+    for (uint32_t q0 = 0; q0 < n_queries; q0 += BATCH_MAX_QUERIES) {  // the pass' scratch grows with the batch
+        const uint32_t nq = std::min(BATCH_MAX_QUERIES, n_queries - q0);
+        PQV_TRY(ivf_batch_masked(ctx, ds, D, ix, queries + (size_t)q0 * dim, nq, k, nprobe, flags, out_row_idx + (size_t)q0 * k,
+                                 out_dist + (size_t)q0 * k, out_count + q0, part, nullptr, nullptr, 0));
+        for (uint32_t i = 0; i < nq; ++i) handled[q0 + i] = part[i];
+    }
     for (uint32_t q = 0; q < n_queries; ++q) {
         if (handled[q]) continue;
         const float *qv = queries + (size_t)q * dim;
@@ -1098,6 +1102,8 @@ int pqv_ivf_search_batch_keys(pqv_ctx *ctx, uint64_t handle, uint64_t index, con
     if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search_batch_keys needs a single-device dataset");
     if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
     if ((u64)pos_base + ds->n_rows > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "global row ids are u32");
+    if (n_queries > BATCH_MAX_QUERIES)
+        return fail(PQV_ELIMIT, "at most %u queries per pqv_ivf_search_batch_keys call (got %u)", BATCH_MAX_QUERIES, n_queries);
     for (uint32_t q = 0; q < n_queries; ++q) out_count[q] = 0xFFFFFFFFu;
     if (n_queries && ix->n_ids == 0) {  // nothing of this slice is in any list
         for (uint32_t q = 0; q < n_queries; ++q) out_count[q] = 0;
@@ -1188,9 +1194,13 @@ int pqv_vector_topk_indexed_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index,
     DevGuard guard(D.dev);
     PQV_TRY(index_make_resident(D, *ix));
     const uint32_t dim = ds->dim;
-    std::vector<uint8_t> handled;
-    PQV_TRY(ivf_batch_masked(ctx, ds, D, ix, queries, n_queries, k, nprobe, flags, out_row_idx, out_dist, out_count, handled,
-                             nullptr, nullptr, 0, row_mask));
+    std::vector<uint8_t> handled(n_queries, 0), part;
+    for (uint32_t q0 = 0; q0 < n_queries; q0 += BATCH_MAX_QUERIES) {
+        const uint32_t nq = std::min(BATCH_MAX_QUERIES, n_queries - q0);
+        PQV_TRY(ivf_batch_masked(ctx, ds, D, ix, queries + (size_t)q0 * dim, nq, k, nprobe, flags, out_row_idx + (size_t)q0 * k,
+                                 out_dist + (size_t)q0 * k, out_count + q0, part, nullptr, nullptr, 0, row_mask));
+        for (uint32_t i = 0; i < nq; ++i) handled[q0 + i] = part[i];
+    }
     for (uint32_t q = 0; q < n_queries; ++q) {
         if (handled[q]) continue;
         const float *qv = queries + (size_t)q * dim;

@@ -213,6 +213,7 @@ void record_assign_timing(pqv_ctx *ctx, DeviceState &D, int path, u64 rows, cons
 // batched brute-force top-k (pqv_tc.cuh, "Batched brute-force top-k")
 // ------------------------------------------------------------------------------------------------
 constexpr uint32_t BATCH_MIN_QUERIES = 4;          // below this the single-query scans are cheaper than the prep
+constexpr uint32_t BATCH_MAX_QUERIES = 4096;       // queries per pass: the sample-bound matrix U is nq x 512 k floats (8.6 GB here)
 constexpr u64 BATCH_TOTAL_CAND = 64ull << 20;      // candidate (row, query) records kept per batch (8 B each)
 
 // PQV_BATCH=off disables the path (every query then takes the single-query scan)

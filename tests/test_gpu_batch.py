@@ -202,3 +202,19 @@ def test_sharded_batch_keys_merge_to_the_whole_table_answer(ctx, n, dim, nq, k, 
         assert bits(d).tolist() == bits(ed).tolist(), (i, bool(need[i]))
     for p in parts:
         p.drop()
+
+
+def test_more_queries_than_one_pass_takes(ctx):
+    """n_queries > BATCH_MAX_QUERIES (4096): several passes, a short tail through the single-query scans."""
+    rng = np.random.default_rng(4)
+    n, dim, nq, k = 6000, 32, 4096 + 4096 + 3, 5
+    data = rng.random((n, dim), dtype=np.float32)
+    queries = rng.random((nq, dim), dtype=np.float32)
+    ds = ctx.dataset_from(data)
+    rows, dist, cnt = ds.l2_topk(queries, k, SQRT)
+    assert ctx.last_batch_timing()["queries"] == 8192
+    for i in list(range(0, nq, 397)) + [4095, 4096, 8191, 8192, nq - 1]:
+        er, ed = O.topk_rerank(queries[i], data, None, k, 0, True)
+        assert cnt[i] == k and rows[i].tolist() == er.tolist(), i
+        assert bits(dist[i]).tolist() == bits(ed).tolist()
+    ds.drop()
