@@ -42,4 +42,23 @@ ds.append(host)
 dt = time.perf_counter() - t0
 out["batch_1000000_direct_pageable"] = {"gbs": host.nbytes / dt / 1e9, "seconds": dt}
 ds.drop()
+# cold streaming top-k (pqv_topk_stream_*, the VectorTopKExec feed) from PAGEABLE batches: staged lanes vs the driver's copy
+del os.environ["PQV_APPEND_DIRECT"]
+m, batch = 2_000_000, 65536
+rows = np.random.default_rng(1).random((m, dim), dtype=np.float32)       # ordinary numpy memory
+q = np.random.default_rng(2).random(dim, dtype=np.float32)
+res = {}
+for name, env in (("staged", None), ("direct_pageable", "1")):
+    if env:
+        os.environ["PQV_APPEND_DIRECT"] = env
+    for rep in range(2):
+        t0 = time.perf_counter()
+        st = ctx.topk_stream(q, 10, P.PQV_SUM_SEQ)
+        for s0 in range(0, m, batch):
+            st.push(rows[s0:s0 + batch])
+        r, d = st.finish()
+        dt = time.perf_counter() - t0
+    res[name] = (r.tolist(), d.view(np.uint32).tolist())
+    out[f"stream_push_{name}"] = {"gbs": rows.nbytes / dt / 1e9, "seconds": dt, "batch_rows": batch}
+out["stream_push_results_identical"] = res["staged"] == res["direct_pageable"]
 print(json.dumps(out))
