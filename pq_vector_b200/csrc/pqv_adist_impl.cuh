@@ -1,13 +1,15 @@
-// pqv_adist_impl.cuh -- host side of two entry points that sit next to the indexed path (included at the end of
+// pqv_adist_impl.cuh -- host side of the entry points that sit next to the indexed path (included at the end of
 // pqv_capi.cu; same translation unit so it shares pqv_ctx / DeviceState):
 //
-//   pqv_array_distance / pqv_array_distance_topk   the un-indexed `array_distance` arm:
+//   pqv_array_distance / pqv_array_distance_topk[_filtered]   the un-indexed `array_distance` arm:
 //       DataFusion's built-in UDF + SortExec(TopK), reached from benches/query.rs:79-81 and
-//       examples/datafusion_sql.rs:54-55 when the file carries no index (kernels: pqv_adist.cuh).
-//   pqv_l2_topk_coalesced                          the coalescing front door SURVEY section 8b asks for: the reference API
-//       is single-query (search.rs:49-54, exec.rs:43) and its callers are concurrent tokio tasks; calls that
-//       arrive while a pass over the table is running are answered together by ONE batched tensor-core pass
-//       (pqv_l2_topk with n_queries > 1), each caller still receiving exactly its own single-query result.
+//       examples/datafusion_sql.rs:54-55 when no optimizer rule is registered (kernels: pqv_adist.cuh); the filtered form
+//       takes the WHERE clause of the scan subtree as a row bitmap.
+//   pqv_l2_topk_coalesced / pqv_ivf_search_coalesced           the coalescing front door SURVEY section 8b asks for: the
+//       reference API is single-query (search.rs:49-54, exec.rs:43) and its callers are concurrent tokio tasks;
+//       calls that arrive while a pass over the table is running are answered together by ONE batched tensor-core pass
+//       (pqv_l2_topk with n_queries > 1, or pqv_ivf_search_batch), each caller still receiving exactly its own
+//       single-query result.
 #pragma once
 
 namespace {
