@@ -74,3 +74,58 @@ def test_hot_kernels_do_not_spill():
         regs, stack, local = (int(re.search(p + r":(\d+)", u).group(1)) for p in ("REG", "STACK", "LOCAL"))
         if "ILi0ELb1ELb0ELi8ELi8ELi2ELi2E" in name or "ILi0ELb1ELb1ELi8ELi4ELi2ELi2E" in name or "ILi1ELb1ELb" in name:
             assert stack == 0 and local == 0 and regs <= 128, (name, u)   # the shipped vector variants
+
+
+def _header_arity():
+    txt = re.sub(r"/\*.*?\*/", " ", open(os.path.join(ROOT, "include", "pqv.h")).read(), flags=re.S)
+    out = {}
+    for m in re.finditer(r"PQV_API\s+[^;(]*?\b(pqv_\w+)\s*\(([^;]*?)\)\s*;", txt, flags=re.S):
+        args = " ".join(m.group(2).split())
+        out[m.group(1)] = 0 if args in ("", "void") else args.count(",") + 1
+    return out
+
+
+def _rust_calls(src):
+    """(name, n_args) of every `sys::pqv_*(...)` call: arguments split at top-level commas."""
+    for m in re.finditer(r"sys::(pqv_\w+)\s*\(", src):
+        depth, i, commas, seen = 1, m.end(), 0, False
+        while depth:
+            ch = src[i]
+            if ch in "([{":
+                depth += 1
+            elif ch in ")]}":
+                depth -= 1
+            elif ch == "," and depth == 1:
+                commas += 1
+            elif not ch.isspace():
+                seen = True
+            i += 1
+        yield m.group(1), (commas + 1 if seen else 0)
+
+
+def test_rust_sys_block_is_generated_from_the_header():
+    """integration/rust/src/pqv_sys.rs (the extern "C" block a pq-vector maintainer links against) is what gen_sys.py emits
+    from include/pqv.h today, and declares every exported function."""
+    import subprocess
+    import sys
+    gen = os.path.join(ROOT, "integration", "rust", "gen_sys.py")
+    assert subprocess.run([sys.executable, gen, "--check"]).returncode == 0, "pqv_sys.rs is stale: run gen_sys.py"
+    rs = open(os.path.join(ROOT, "integration", "rust", "src", "pqv_sys.rs")).read()
+    assert sorted(set(re.findall(r"pub fn (pqv_\w+)\(", rs))) == header_symbols()
+
+
+def test_rust_wrappers_call_the_abi_with_the_declared_arity():
+    arity = _header_arity()
+    assert sorted(arity) == header_symbols()
+    src = open(os.path.join(ROOT, "integration", "rust", "src", "gpu.rs")).read()
+    calls = list(_rust_calls(src))
+    assert len(calls) >= 25
+    for name, n in calls:
+        assert name in arity, name
+        assert n == arity[name], (name, n, arity[name])
+    # the call sites of SURVEY section 8b are all reachable from the safe layer
+    used = {n for n, _ in calls}
+    for must in ["pqv_l2_topk_gather", "pqv_topk_stream_begin", "pqv_topk_stream_push", "pqv_topk_stream_finish",
+                 "pqv_kmeans_assign", "pqv_min_dist_update", "pqv_centroid_rank", "pqv_ivf_search_coalesced",
+                 "pqv_vector_topk_indexed", "pqv_array_distance"]:
+        assert must in used, must
