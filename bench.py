@@ -65,12 +65,14 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def ncu_traffic():
-    """dram bytes per launch of the scan kernel from the committed ncu --set full capture, if any."""
+def ncu_traffic(scan_bytes):
+    """dram bytes per launch of the scan kernel from the committed ncu --set full capture -- only when this run's launch
+    is the shape that was captured (the capture is of the BASELINE config); null for any other --rows / --dim."""
     p = os.path.join(ROOT, "profiles", "scan_kernel_ncu.json")
     if os.path.exists(p):
         try:
-            return json.load(open(p)).get("dram_bytes_per_launch")
+            cap = json.load(open(p))
+            return cap.get("dram_bytes_per_launch") if cap.get("algorithmic_bytes_per_launch", ROWS_PER_GPU * DIM * 4) == scan_bytes else None
         except Exception:
             return None
     return None
@@ -361,7 +363,7 @@ def run_ours(args):
                               else "with one NCCL all-gather")),
             },
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": ncu_traffic(), "peak_source": peak_src, "kernel": "l2_scan_topk_kernel<ORDER=0,VEC4,dense,WARPS=8,RB=8,CBV=2,MINB=2>",
+                         "traffic": ncu_traffic(scan_bytes), "peak_source": peak_src, "kernel": "l2_scan_topk_kernel<ORDER=0,VEC4,dense,WARPS=8,RB=8,CBV=2,MINB=2>",
                          "algorithmic_bytes_per_launch": scan_bytes, "kernel_ms": scan_ms, "post_kernels_ms": post_ms},
             "e2e": {"value": world / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d // args.steps,
                     "d2h_bytes_per_step": d2h // args.steps, "ms_per_step": e2e_s * 1e3,
