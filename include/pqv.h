@@ -100,8 +100,8 @@ PQV_API int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uin
 typedef struct {
     uint32_t queries;      /* batch size of the last pqv_l2_topk call (0: batched pass not used)                        */
     uint32_t declined;     /* 1: batch abandoned (non-finite inputs, candidate buffers full) -> single-query scans      */
-    uint32_t tie_queries;  /* queries re-run through the single-query path (order hinges on the reference heap layout) */
-    uint32_t reserved;
+    uint32_t tie_queries;  /* queries whose order hinges on the reference heap layout: the heap is replayed for them    */
+    uint32_t tie_batched;  /* of those: resolved together from one pass over the sample prefix (PQV_TIE_BATCH=off: none) */
     uint64_t rows;
     uint64_t sample_rows;  /* rows of the threshold pass                                                               */
     uint64_t candidates;   /* (row, query) pairs re-evaluated exactly                                                  */

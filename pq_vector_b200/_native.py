@@ -29,7 +29,7 @@ class PqvAssignTiming(C.Structure):
 
 
 class PqvBatchTiming(C.Structure):
-    _fields_ = [("queries", C.c_uint32), ("declined", C.c_uint32), ("tie_queries", C.c_uint32), ("reserved", C.c_uint32),
+    _fields_ = [("queries", C.c_uint32), ("declined", C.c_uint32), ("tie_queries", C.c_uint32), ("tie_batched", C.c_uint32),
                 ("rows", C.c_uint64), ("sample_rows", C.c_uint64), ("candidates", C.c_uint64), ("prep_ms", C.c_double),
                 ("sample_ms", C.c_double), ("filter_ms", C.c_double), ("rerank_ms", C.c_double), ("total_ms", C.c_double)]
 

@@ -25,6 +25,7 @@
 #include "pqv_kernels.cuh"
 #include "pqv_peer.cuh"
 #include "pqv_adist.cuh"
+#include "pqv_tie.cuh"
 
 using pqv::u64;
 
@@ -265,10 +266,12 @@ bool topk_without_replay(const u64 *keys, size_t n, uint32_t k, uint32_t flags, 
     return true;
 }
 
+// known_tie: the caller already knows the shortcut cannot decide this query (a tie query of a batch)
 size_t replay_reference_heap(std::vector<u64> &entrants, const RowMap &row_of, uint32_t k, uint32_t flags,
-                             uint32_t *out_rows, float *out_dist) {
+                             uint32_t *out_rows, float *out_dist, bool known_tie = false) {
     size_t fast_cnt = 0;
-    if (topk_without_replay(entrants.data(), entrants.size(), k, flags, [&](uint32_t, uint32_t pos) { return row_of(pos); },
+    if (!known_tie &&
+        topk_without_replay(entrants.data(), entrants.size(), k, flags, [&](uint32_t, uint32_t pos) { return row_of(pos); },
                             out_rows, out_dist, &fast_cnt))
         return fast_cnt;
     radix_sort_field(entrants, 0);  // by position
@@ -363,6 +366,12 @@ struct DeviceState {
     DevBuf<uint2> tb_cand;
     DevBuf<u64> tb_seg, tb_keys;
     PinBuf<u64> h_batch_keys;
+    // tie queries of a batch resolved together (pqv_tie.cuh): prefix distance matrix, selected query ids, entrant regions
+    DevBuf<float> tie_dmat;
+    DevBuf<uint32_t> tie_qsel;
+    DevBuf<u64> tie_ent;
+    PinBuf<u64> h_tie_ent, h_tie_seg;
+    PinBuf<uint32_t> h_tie_qsel;
     PinBuf<u64> h_ent_out, h_final;
     PinBuf<float> h_query;
     // fused IVF search: row ids of the entrants + (candidate count, NaN flag)
@@ -1108,6 +1117,12 @@ void pqv_destroy(pqv_ctx *ctx) {
         D.tb_seg.release();
         D.tb_keys.release();
         D.h_batch_keys.release();
+        D.tie_dmat.release();
+        D.tie_qsel.release();
+        D.tie_ent.release();
+        D.h_tie_ent.release();
+        D.h_tie_seg.release();
+        D.h_tie_qsel.release();
         D.h_ent_out.release();
         D.h_final.release();
         D.h_query.release();
@@ -1398,6 +1413,7 @@ int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_
             total.queries += b.queries;
             total.declined |= b.declined;
             total.tie_queries += b.tie_queries;
+            total.tie_batched += b.tie_batched;
             total.rows = b.rows;
             total.sample_rows = b.sample_rows;
             total.candidates += b.candidates;

@@ -232,6 +232,121 @@ bool batch_path_applies(const Dataset &ds, const float *d_rows, uint32_t nq, uin
            k + 1 <= (uint32_t)pqv::tc::SEL_MAX && tmap_encoder() != nullptr;
 }
 
+// Tie queries of a dense batch, resolved together (pqv_tie.cuh): one pass over the sample prefix [0, S) gives the exact
+// distances of every prefix row against every tie query, one CTA per query turns its row of that matrix into a superset of
+// the rows the reference heap admits inside the prefix, and the host replays the reference loop over those keys + the
+// query's candidates behind the prefix (still on the device from the batched pass).  Queries whose entrant region
+// overflowed (adversarial row order: most rows enter the heap) are returned in `slow` for the one-by-one path.
+// PQV_TIE_BATCH=off sends every tie query through the one-by-one path instead.
+constexpr uint32_t TIE_CHUNK_Q = 128;   // tie queries per pass: the distance matrix is TIE_CHUNK_Q x S floats (268 MB)
+constexpr uint32_t TIE_ENT_CAP = 8192;  // entrant keys per query (expected: 2048 + ~k ln(S / 2048))
+
+bool tie_batch_enabled() {
+    const char *e = getenv("PQV_TIE_BATCH");
+    return !(e && !strcmp(e, "off"));
+}
+
+// host threads for the independent heap replays of a tie batch (PQV_TIE_THREADS, default min(8, hardware threads))
+size_t tie_threads() {
+    if (const char *e = getenv("PQV_TIE_THREADS")) return (size_t)std::max(1, atoi(e));
+    const unsigned hw = std::thread::hardware_concurrency();
+    return std::min<size_t>(8, hw ? hw : 1);
+}
+
+int resolve_ties_together(DeviceState &D, const float *d_rows, u64 S, uint32_t dim, int order, uint32_t k, uint32_t flags,
+                          const std::vector<uint32_t> &ties, const std::vector<uint32_t> &h_cnt, uint32_t cap_q,
+                          uint32_t *out_rows, float *out_dist, uint32_t *out_count, std::vector<uint8_t> &handled,
+                          std::vector<uint32_t> &slow) {
+    namespace TI = pqv::tie;
+    const u64 ldo = (S + 63) & ~63ull;
+    const uint32_t kcap = std::max<uint32_t>(32, pow2ceil(k));
+    const size_t region = (size_t)TIE_ENT_CAP + 1;
+    cudaStream_t st = D.stream;
+    static const bool trace = getenv("PQV_TRACE") != nullptr;
+    for (size_t c0 = 0; c0 < ties.size(); c0 += TIE_CHUNK_Q) {
+        const uint32_t tq = (uint32_t)std::min<size_t>(TIE_CHUNK_Q, ties.size() - c0);
+        PQV_TRY(D.tie_dmat.ensure((size_t)tq * ldo));
+        PQV_TRY(D.tie_qsel.ensure(tq));
+        PQV_TRY(D.tie_ent.ensure((size_t)tq * region));
+        PQV_TRY(D.h_tie_ent.ensure((size_t)tq * region));
+        PQV_TRY(D.h_tie_qsel.ensure(tq));
+        size_t seg_total = 0;
+        for (uint32_t j = 0; j < tq; ++j) {
+            D.h_tie_qsel.p[j] = ties[c0 + j];
+            seg_total += std::min<uint32_t>(h_cnt[ties[c0 + j]], cap_q);
+        }
+        PQV_TRY(D.h_tie_seg.ensure(std::max<size_t>(seg_total, 1)));
+        const double t_begin = trace ? trace_now_ms() : 0.0;
+        CU_TRY(cudaMemcpyAsync(D.tie_qsel.p, D.h_tie_qsel.p, (size_t)tq * 4, cudaMemcpyHostToDevice, st));
+        if (trace) CU_TRY(cudaEventRecord(D.ev[0], st));
+        const dim3 grid((uint32_t)((S + TI::TN - 1) / TI::TN), (tq + TI::TM - 1) / TI::TM);
+        if (order == 0)
+            TI::prefix_dist_matrix_kernel<0><<<grid, 256, 0, st>>>(d_rows, S, dim, D.tb_Q.p, D.tie_qsel.p, tq, D.tie_dmat.p, ldo);
+        else
+            TI::prefix_dist_matrix_kernel<1><<<grid, 256, 0, st>>>(d_rows, S, dim, D.tb_Q.p, D.tie_qsel.p, tq, D.tie_dmat.p, ldo);
+        CU_TRY(cudaGetLastError());
+        if (trace) CU_TRY(cudaEventRecord(D.ev[1], st));
+        TI::prefix_entrants_kernel<<<tq, 1024, 0, st>>>(D.tie_dmat.p, ldo, (uint32_t)S, k, kcap, D.tie_ent.p, TIE_ENT_CAP);
+        CU_TRY(cudaGetLastError());
+        if (trace) CU_TRY(cudaEventRecord(D.ev[2], st));
+        CU_TRY(cudaMemcpyAsync(D.h_tie_ent.p, D.tie_ent.p, (size_t)tq * region * 8, cudaMemcpyDeviceToHost, st));
+        size_t off = 0;
+        for (uint32_t j = 0; j < tq; ++j) {
+            const uint32_t q = ties[c0 + j], cq = std::min<uint32_t>(h_cnt[q], cap_q);
+            if (cq)
+                CU_TRY(cudaMemcpyAsync(D.h_tie_seg.p + off, D.tb_seg.p + (size_t)q * cap_q, (size_t)cq * 8, cudaMemcpyDeviceToHost, st));
+            off += cq;
+        }
+        CU_TRY(cudaStreamSynchronize(st));
+        const double t_dev = trace ? trace_now_ms() : 0.0;
+        // the replays are independent: spread them over a few host threads (each ~0.1 ms: sort by position + heap replay)
+        std::vector<size_t> seg_off(tq);
+        std::vector<uint32_t> todo;
+        off = 0;
+        for (uint32_t j = 0; j < tq; ++j) {
+            const uint32_t q = ties[c0 + j];
+            seg_off[j] = off;
+            off += std::min<uint32_t>(h_cnt[q], cap_q);
+            if (D.h_tie_ent.p[(size_t)j * region] > TIE_ENT_CAP) slow.push_back(q);
+            else todo.push_back(j);
+        }
+        auto replay_range = [&](size_t lo, size_t hi) {
+            std::vector<u64> ent;
+            RowMap identity;
+            for (size_t t = lo; t < hi; ++t) {
+                const uint32_t j = todo[t], q = ties[c0 + j], cq = std::min<uint32_t>(h_cnt[q], cap_q);
+                const u64 *reg = D.h_tie_ent.p + (size_t)j * region;
+                const u64 *seg = D.h_tie_seg.p + seg_off[j];
+                ent.assign(reg + 1, reg + 1 + reg[0]);
+                for (uint32_t i = 0; i < cq; ++i)
+                    if (key_pos(seg[i]) >= S) ent.push_back(seg[i]);
+                out_count[q] = (uint32_t)replay_reference_heap(ent, identity, k, flags, out_rows + (size_t)q * k, out_dist + (size_t)q * k,
+                                                                /*known_tie=*/true);
+                handled[q] = 1;
+            }
+        };
+        const size_t nt = std::min<size_t>(tie_threads(), (todo.size() + 3) / 4);  // at least 4 replays per thread
+        if (nt <= 1) {
+            replay_range(0, todo.size());
+        } else {
+            std::vector<std::thread> th;
+            const size_t per = (todo.size() + nt - 1) / nt;
+            for (size_t t = 1; t < nt; ++t) th.emplace_back(replay_range, std::min(t * per, todo.size()), std::min((t + 1) * per, todo.size()));
+            replay_range(0, std::min(per, todo.size()));
+            for (auto &x : th) x.join();
+        }
+        if (trace) {
+            float a = 0, b = 0;
+            cudaEventElapsedTime(&a, D.ev[0], D.ev[1]);
+            cudaEventElapsedTime(&b, D.ev[1], D.ev[2]);
+            fprintf(stderr, "[pqv trace] tie batch: %u queries, prefix %llu rows: matrix %.3f ms, entrants %.3f ms, enqueue->sync %.3f ms, "
+                            "replay %.3f ms on %zu thread(s), %zu overflowed\n",
+                    tq, (unsigned long long)S, a, b, t_dev - t_begin, trace_now_ms() - t_dev, std::max<size_t>(nt, 1), tq - todo.size());
+        }
+    }
+    return PQV_OK;
+}
+
 // Answers every query it can decide exactly; handled[q] = 0 marks the queries the caller must run through the
 // single-query path (ties whose order depends on the reference heap's layout, or a declined batch).
 int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, const float *queries, uint32_t nq,
@@ -456,7 +571,14 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     bt.tie_queries = (uint32_t)ties.size();
     std::vector<u64> ent, seg_keys;
     RowMap identity;
-    for (uint32_t q : ties) {
+    std::vector<uint32_t> slow;
+    if (tie_batch_enabled() && !ties.empty())
+        PQV_TRY(resolve_ties_together(D, d_rows, S, dim, order, k, flags, ties, h_cnt, cap_q, out_rows, out_dist, out_count, handled,
+                                      slow));
+    else
+        slow.swap(ties);
+    bt.tie_batched = bt.tie_queries - (uint32_t)slow.size();
+    for (uint32_t q : slow) {
         ent.clear();
         uint32_t dummy_cnt = 0;
         PQV_TRY(topk_one(ctx, ds, queries + (size_t)q * dim, nullptr, 0, k, flags, nullptr, nullptr, &dummy_cnt, &ent, 0, nullptr,

@@ -218,3 +218,78 @@ def test_more_queries_than_one_pass_takes(ctx):
         assert cnt[i] == k and rows[i].tolist() == er.tolist(), i
         assert bits(dist[i]).tolist() == bits(ed).tolist()
     ds.drop()
+
+
+class tie_batch_off:
+    """PQV_TIE_BATCH=off: every tie query takes the one-by-one path (an exact scan of the sample prefix each)"""
+    def __enter__(self):
+        self.old = os.environ.get("PQV_TIE_BATCH")
+        os.environ["PQV_TIE_BATCH"] = "off"
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            os.environ.pop("PQV_TIE_BATCH", None)
+        else:
+            os.environ["PQV_TIE_BATCH"] = self.old
+
+
+class nullcontext:
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        return False
+
+
+def test_tie_queries_resolved_together(ctx):
+    """The tie queries of a batch share ONE exact pass over the sample prefix (pqv_tie.cuh) instead of one
+    prefix scan each; every answer must still be the reference loop's, bit for bit (row order among equal distances
+    included), in both summation orders and for prefixes shorter and longer than one 2048-row chunk."""
+    rng = np.random.default_rng(14)
+    with nullcontext():
+        base = rng.random((3000, 64), dtype=np.float32)
+        data = np.concatenate([base, base[:1500], base[:700]])
+        queries = rng.random((12, 64), dtype=np.float32)
+        for flags, k in ((SQRT, 50), (SEQ, 50), (SQRT, 1), (SEQ, 1024)):
+            t = check_batch(ctx, data, queries, k, flags)
+            assert t["tie_queries"] >= 1 and t["tie_batched"] == t["tie_queries"], t
+        # small-integer grid: many exactly equal distances, ties across the k boundary; prefix = several chunks
+        grid = rng.integers(0, 3, (70000, 32)).astype(np.float32)
+        gq = rng.integers(0, 3, (8, 32)).astype(np.float32)
+        for flags in (SEQ, SQRT):
+            t = check_batch(ctx, grid, gq, 10, flags)
+            assert t["tie_queries"] >= 1 and t["tie_batched"] == t["tie_queries"], t
+        # a table shorter than k and shorter than one chunk; dim not a multiple of 32 (zero-padded last column block)
+        small = rng.integers(0, 2, (40, 36)).astype(np.float32)
+        t = check_batch(ctx, small, rng.integers(0, 2, (5, 36)).astype(np.float32), 100, SQRT)
+        assert t["tie_batched"] == t["tie_queries"], t
+        # descending distances: every row enters the heap -> the entrant region overflows -> one-by-one path, same answer
+        n = 30000
+        ramp = np.zeros((n, 32), np.float32)
+        ramp[:, 0] = np.arange(n, 0, -1, dtype=np.float32) / np.float32(n)
+        ramp[-7:, 0] = ramp[-8, 0]              # bit-equal distances inside the top-k
+        t = check_batch(ctx, ramp, np.zeros((4, 32), np.float32), 10, SQRT, expect_used=False)
+        if t["queries"] and not t["declined"]:
+            assert t["tie_queries"] == 4 and t["tie_batched"] == 0, t
+
+
+def test_tie_batch_equals_one_by_one_at_scale(ctx):
+    """400k x 768 synthetic rows, 200 queries, k = 100 with sqrt (about 5 % of the queries collapse two squared distances
+    onto one returned value): resolving the ties together returns what the one-by-one path returns."""
+    n, dim, nq, k = 400_000, 768, 200, 100
+    ds = ctx.dataset(dim, n)
+    ds.fill_synthetic(n, 1234)
+    qd = ctx.dataset(dim, nq)
+    qd.fill_synthetic(nq, 7)
+    queries = qd.read(0, nq)
+    qd.drop()
+    for flags in (SQRT, SEQ):
+        with tie_batch_off():
+            r0, d0, c0 = ds.l2_topk(queries, k, flags)
+            t0 = ctx.last_batch_timing()
+        r1, d1, c1 = ds.l2_topk(queries, k, flags)
+        t1 = ctx.last_batch_timing()
+        assert t0["tie_batched"] == 0 and t1["tie_batched"] == t1["tie_queries"] == t0["tie_queries"], (t0, t1)
+        assert np.array_equal(c0, c1) and np.array_equal(r0, r1) and np.array_equal(bits(d0), bits(d1))
+        print(flags, t1)
+    ds.drop()
