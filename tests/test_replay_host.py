@@ -63,3 +63,40 @@ def test_replay_sqrt_collision_takes_the_heap_path():
         er, ed = O.heap_topk(dist, None, k, True)
         rows, d = P.replay_candidates(_keys(dist, np.arange(5)), k, P.PQV_SQRT)
         assert rows.tolist() == er.tolist() and d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+
+
+def _chunked_threshold_superset(dist, k, chunk=2048):
+    """numpy model of prefix_entrants_kernel (pq_vector_b200/csrc/pqv_tie.cuh): the first chunk whole, then every row
+    below the exact k-th smallest distance of all rows BEFORE its chunk (the threshold in force at the chunk's start)."""
+    n = dist.size
+    keep = list(range(min(n, chunk)))
+    for base in range(chunk, n, chunk):
+        thr = np.partition(dist[:base], k - 1)[k - 1]          # k <= chunk <= base
+        keep.extend((base + np.nonzero(dist[base:base + chunk] < thr)[0]).tolist())
+    return np.array(keep, dtype=np.int64)
+
+
+@pytest.mark.parametrize("levels", [0, 5, 200])
+@pytest.mark.parametrize("k", [1, 10, 100, 1024])
+@pytest.mark.parametrize("trend", ["random", "descending"])
+def test_chunked_threshold_entrants_are_a_superset_of_the_heap_admissions(levels, k, trend):
+    """The batched tie path replays the reference heap over the rows a per-chunk threshold lets
+    through instead of over every row: that set must contain every row the reference heap admits, and the replay over it
+    must return the reference answer (order among equal distances included)."""
+    rng = np.random.default_rng(levels + 7 * k)
+    n = 20000
+    dist = rng.random(n).astype(np.float32) * 4 + 0.5
+    if trend == "descending":                                   # every row is admitted: the superset is everything
+        dist = (dist * 0.01 + np.linspace(9, 1, n)).astype(np.float32)
+    if levels:
+        dist = (np.floor(dist * levels) / levels).astype(np.float32)
+    sup = _chunked_threshold_superset(dist, k)
+    adm = _entrants(dist, k)
+    assert np.isin(adm, sup).all()
+    if trend == "random" and k <= 100:
+        assert sup.size < 2048 + 40 * k                         # and it is small: first chunk + O(k log(n / chunk))
+    for do_sqrt in (False, True):
+        er, ed = O.heap_topk(dist, None, k, do_sqrt)
+        rows, d = P.replay_candidates(_keys(dist[sup], sup), k, P.PQV_SQRT if do_sqrt else 0)
+        assert rows.tolist() == er.tolist()
+        assert d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
