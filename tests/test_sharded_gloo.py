@@ -13,6 +13,22 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
+def _run_cases(rank, world, port0, fn_name, cases, out_dir):
+    """all cases of one test in ONE pair of processes (a spawn costs ~10 s of interpreter + torch start-up): every case
+    gets its own rendezvous port, process group and output directory"""
+    fn = globals()[fn_name]
+    for i, case in enumerate(cases):
+        d = os.path.join(out_dir, f"case{i}")
+        os.makedirs(d, exist_ok=True)
+        fn(rank, world, port0 + i, *case, d)
+
+
+def _spawn_cases(fn, cases, tmp_path, port_base):
+    port0 = port_base + (os.getpid() * 16) % 1900
+    mp.spawn(_run_cases, args=(2, port0, fn.__name__, cases, str(tmp_path)), nprocs=2, join=True)
+    return [(case, tmp_path / f"case{i}") for i, case in enumerate(cases)]
+
+
 def _worker(rank, world, port, n, dim, k, flags, cap, seed, out_dir):
     sys.path.insert(0, ROOT)
     import oracle as O
@@ -39,13 +55,11 @@ def _worker(rank, world, port, n, dim, k, flags, cap, seed, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,dim,k,flags,cap,seed", [(1000, 8, 10, 2, 4096, 2), (3000, 4, 100, 1, 64, 3),
-                                                     (5, 3, 10, 2, 16, 4), (2000, 6, 50, 3, 4096, 5)])
-def test_two_rank_exchange_matches_single_process(tmp_path, n, dim, k, flags, cap, seed):
-    port = 29500 + (os.getpid() + seed) % 2000
-    mp.spawn(_worker, args=(2, port, n, dim, k, flags, cap, seed, str(tmp_path)), nprocs=2, join=True)
-    for r in range(2):
-        assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
+def test_two_rank_exchange_matches_single_process(tmp_path):
+    cases = [(1000, 8, 10, 2, 4096, 2), (3000, 4, 100, 1, 64, 3), (5, 3, 10, 2, 16, 4), (2000, 6, 50, 3, 4096, 5)]
+    for (n,dim,k,flags,cap,seed), d in _spawn_cases(_worker, cases, tmp_path, 29500):
+        for r in range(2):
+            assert np.load(d / f"ok{r}.npy")[0] == 1, (n, dim, k, flags, cap, seed)
 
 
 def _batch_worker(rank, world, port, n, dim, nq, k, flags, seed, out_dir):
@@ -92,16 +106,14 @@ def _batch_worker(rank, world, port, n, dim, nq, k, flags, seed, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,dim,nq,k,flags,seed", [(2000, 8, 6, 10, 2, 2), (1500, 4, 5, 20, 1, 3), (7, 3, 4, 10, 2, 4),
-                                                    (1200, 6, 4, 5, 3, 6), (900, 5, 3, 3, 0, 7)])
-def test_two_rank_batched_exchange_matches_single_process(tmp_path, n, dim, nq, k, flags, seed):
-    port = 31500 + (os.getpid() + seed) % 2000
-    mp.spawn(_batch_worker, args=(2, port, n, dim, nq, k, flags, seed, str(tmp_path)), nprocs=2, join=True)
-    got = [np.load(tmp_path / f"ok{r}.npy") for r in range(2)]
-    assert all(g[0] == 1 for g in got)
-    assert got[0][1] == got[1][1]                 # both ranks took the same replay decisions
-    if seed % 2:
-        assert got[0][1] > 0                      # the tie-heavy cases really exercised the replay route
+def test_two_rank_batched_exchange_matches_single_process(tmp_path):
+    cases = [(2000, 8, 6, 10, 2, 2), (1500, 4, 5, 20, 1, 3), (7, 3, 4, 10, 2, 4), (1200, 6, 4, 5, 3, 6), (900, 5, 3, 3, 0, 7)]
+    for (n,dim,nq,k,flags,seed), d in _spawn_cases(_batch_worker, cases, tmp_path, 31500):
+        got = [np.load(d / f"ok{r}.npy") for r in range(2)]
+        assert all(g[0] == 1 for g in got), (n, dim, nq, k, flags, seed)
+        assert got[0][1] == got[1][1]                 # both ranks took the same replay decisions
+        if seed % 2:
+            assert got[0][1] > 0                      # the tie-heavy cases really exercised the replay route
 
 
 def _ivf_worker(rank, world, port, n, dim, C, seed, out_dir):
@@ -134,12 +146,11 @@ def _ivf_worker(rank, world, port, n, dim, C, seed, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,dim,C,seed", [(4000, 6, 9, 1), (333, 4, None, 2), (50, 3, 50, 3)])
-def test_two_rank_ivf_build_matches_single_process(tmp_path, n, dim, C, seed):
-    port = 33500 + (os.getpid() + seed) % 2000
-    mp.spawn(_ivf_worker, args=(2, port, n, dim, C, seed, str(tmp_path)), nprocs=2, join=True)
-    for r in range(2):
-        assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
+def test_two_rank_ivf_build_matches_single_process(tmp_path):
+    cases = [(4000, 6, 9, 1), (333, 4, None, 2), (50, 3, 50, 3)]
+    for (n,dim,C,seed), d in _spawn_cases(_ivf_worker, cases, tmp_path, 33500):
+        for r in range(2):
+            assert np.load(d / f"ok{r}.npy")[0] == 1, (n, dim, C, seed)
 
 
 def _adist_worker(rank, world, port, n, dim, k, seed, out_dir):
@@ -173,12 +184,11 @@ def _adist_worker(rank, world, port, n, dim, k, seed, out_dir):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,dim,k,seed", [(1000, 8, 10, 2), (3000, 4, 100, 3), (5, 3, 10, 4), (600, 6, 600, 8)])
-def test_two_rank_array_distance_topk(tmp_path, n, dim, k, seed):
-    port = 31500 + (os.getpid() + seed) % 2000
-    mp.spawn(_adist_worker, args=(2, port, n, dim, k, seed, str(tmp_path)), nprocs=2, join=True)
-    for r in range(2):
-        assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
+def test_two_rank_array_distance_topk(tmp_path):
+    cases = [(1000, 8, 10, 2), (3000, 4, 100, 3), (5, 3, 10, 4), (600, 6, 600, 8)]
+    for (n,dim,k,seed), d in _spawn_cases(_adist_worker, cases, tmp_path, 37500):
+        for r in range(2):
+            assert np.load(d / f"ok{r}.npy")[0] == 1, (n, dim, k, seed)
 
 
 def _ivf_search_worker(rank, world, port, n, dim, C, k, nprobe, flags, seed, out_dir):
@@ -215,13 +225,11 @@ def _ivf_search_worker(rank, world, port, n, dim, C, k, nprobe, flags, seed, out
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,dim,C,k,nprobe,flags,seed", [(2000, 8, 16, 10, 4, 2, 2), (3000, 4, 9, 100, 3, 1, 3),
-                                                          (900, 6, 30, 50, 30, 3, 5), (40, 3, 7, 10, 2, 2, 6)])
-def test_two_rank_ivf_search(tmp_path, n, dim, C, k, nprobe, flags, seed):
-    port = 33500 + (os.getpid() + seed) % 2000
-    mp.spawn(_ivf_search_worker, args=(2, port, n, dim, C, k, nprobe, flags, seed, str(tmp_path)), nprocs=2, join=True)
-    for r in range(2):
-        assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
+def test_two_rank_ivf_search(tmp_path):
+    cases = [(2000, 8, 16, 10, 4, 2, 2), (3000, 4, 9, 100, 3, 1, 3), (900, 6, 30, 50, 30, 3, 5), (40, 3, 7, 10, 2, 2, 6)]
+    for (n,dim,C,k,nprobe,flags,seed), d in _spawn_cases(_ivf_search_worker, cases, tmp_path, 39500):
+        for r in range(2):
+            assert np.load(d / f"ok{r}.npy")[0] == 1, (n, dim, C, k, nprobe, flags, seed)
 
 
 def _ivf_batch_worker(rank, world, port, n, dim, C, nq, k, nprobe, flags, seed, out_dir):
@@ -275,10 +283,8 @@ def _ivf_batch_worker(rank, world, port, n, dim, C, nq, k, nprobe, flags, seed, 
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("n,dim,C,nq,k,nprobe,flags,seed", [(2000, 8, 16, 12, 10, 4, 2, 2), (1500, 4, 9, 9, 20, 3, 1, 3),
-                                                             (900, 6, 30, 8, 50, 30, 3, 6)])
-def test_two_rank_batched_ivf_search(tmp_path, n, dim, C, nq, k, nprobe, flags, seed):
-    port = 35500 + (os.getpid() + seed) % 2000
-    mp.spawn(_ivf_batch_worker, args=(2, port, n, dim, C, nq, k, nprobe, flags, seed, str(tmp_path)), nprocs=2, join=True)
-    for r in range(2):
-        assert np.load(tmp_path / f"ok{r}.npy")[0] == 1
+def test_two_rank_batched_ivf_search(tmp_path):
+    cases = [(2000, 8, 16, 12, 10, 4, 2, 2), (1500, 4, 9, 9, 20, 3, 1, 3), (900, 6, 30, 8, 50, 30, 3, 6)]
+    for (n,dim,C,nq,k,nprobe,flags,seed), d in _spawn_cases(_ivf_batch_worker, cases, tmp_path, 35500):
+        for r in range(2):
+            assert np.load(d / f"ok{r}.npy")[0] == 1, (n, dim, C, nq, k, nprobe, flags, seed)
