@@ -187,7 +187,9 @@ def run_reference(args):
         "warmup": args.warmup, "ms_per_step": dt * scale * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"brute-force L2 top-{args.k}, 1 query, {args.rows} x {args.dim} f32 (BASELINE configs[1])",
-                   "rows": args.rows, "dim": args.dim, "k": args.k},
+                   "rows": args.rows, "dim": args.dim, "k": args.k,
+                   "value_definition": "as the GPU arm: global queries/s x n_gpus, row-normalised (a serial scan of n_gpus x rows "
+                                       "rows takes n_gpus x as long, so the figure is queries/s over `rows` rows at every N)"},
         "cpu_baseline": {"value": qps, "unit": UNIT, "cores": 1, "kind": "port", "sample": sample_txt,
                          "gbs": sample * args.dim * 4 / dt / 1e9,
                          "all_cores": {"value": 1.0 / (tall * scale), "cores": cores,
