@@ -470,6 +470,29 @@ std::vector<SearchResult> TopkBuilder::search() {
     return out;
 }
 
+// ---- VectorTopKExec over one resident, indexed file -------------------------------------------------------------------
+VectorTopKRows vector_topk_indexed(const std::string &parquet_path, const std::vector<float> &query, size_t k,
+                                   const VectorTopKOptions &options, const uint8_t *filter_mask, size_t filter_mask_bytes) {
+    if (k == 0) fail("k must be > 0");
+    if (options.nprobe == 0) fail("nprobe must be > 0");
+    const ResidentIndex ix = resident_index(parquet_path);  // "Missing pq-vector index metadata ..." for an un-indexed file
+    if (query.size() != ix.dim)                             // index_exec.rs:152-158
+        fail("Query dimension mismatch: expected " + std::to_string(ix.dim) + ", got " + std::to_string(query.size()));
+    const ResidentTable t = resident_table(parquet_path, ix.column);
+    if (filter_mask && filter_mask_bytes < (t.rows + 7) / 8)
+        fail("filter mask has " + std::to_string(filter_mask_bytes) + " bytes, the file " + std::to_string(t.rows) + " rows");
+    VectorTopKRows out;
+    out.rows.resize(k);
+    out.distances.resize(k);
+    uint32_t n = 0;
+    gpu_check(pqv_vector_topk_indexed(gpu(), t.handle, ix.handle, query.data(), (uint32_t)k, (uint32_t)options.nprobe, PQV_SUM_SEQ,
+                                      options.has_max_candidates ? (uint64_t)options.max_candidates : 0ull, filter_mask,
+                                      out.rows.data(), out.distances.data(), &n, &out.candidate_rows, &out.embeddings_fetched));
+    out.rows.resize(n);
+    out.distances.resize(n);
+    return out;
+}
+
 // ---- VectorTopKExec::topk_from_batches ---------------------------------------------------------------------------------
 std::shared_ptr<arrow::RecordBatch> vector_topk(const std::vector<std::shared_ptr<arrow::RecordBatch>> &batches,
                                                 const std::string &column, const std::vector<float> &query, size_t k,

@@ -83,6 +83,32 @@ std::shared_ptr<arrow::RecordBatch> vector_topk(const std::vector<std::shared_pt
                                                 const std::string &column, const std::vector<float> &query, size_t k,
                                                 std::vector<float> *distances = nullptr);
 
+/// src/df_vector/options.rs:5-19 (defaults as the crate's `Default`)
+struct VectorTopKOptions {
+    size_t nprobe = 5;
+    bool has_max_candidates = false;  // Option<usize>: None = no cap
+    size_t max_candidates = 0;
+};
+
+/// What VectorTopKExec yields for ONE indexed file (execute_with_candidates + topk_from_batches,
+/// src/df_vector/exec.rs:207-277): the winning file rows in the operator's output order, their squared distances, and the
+/// two plan counters of the crate's snapshots (`candidate_rows`, `embeddings_fetched`).
+struct VectorTopKRows {
+    std::vector<uint32_t> rows;
+    std::vector<float> distances;
+    uint64_t candidate_rows = 0, embeddings_fetched = 0;
+};
+
+/// The operator over a file whose embedding column and index are resident: the index's candidates for `options.nprobe`
+/// (index_exec.rs:152-163), the first `max_candidates` of them in rank order (CandidateCursor, access.rs:193-243), visited in
+/// file order (the RowSelection of access.rs:107-176), rows failing the scan subtree's predicate dropped BEFORE scoring
+/// (tests.rs:151-241), then the bounded heap of k in the operator's arithmetic (exec.rs:529-533).  `filter_mask`: the
+/// predicate evaluated over the file's rows as an Arrow boolean buffer (bit r & 7 of byte r >> 3 = row r passes), at least
+/// ceil(rows / 8) bytes; null = no FilterExec under the scan.  One host<->device round trip (pqv_vector_topk_indexed).
+VectorTopKRows vector_topk_indexed(const std::string &parquet_path, const std::vector<float> &query, size_t k,
+                                   const VectorTopKOptions &options = VectorTopKOptions(), const uint8_t *filter_mask = nullptr,
+                                   size_t filter_mask_bytes = 0);
+
 /// Drop every table and index this process keeps resident in HBM (keyed by path, size, mtime).
 void drop_resident();
 

@@ -79,8 +79,21 @@ int main(int argc, char **argv) {
             auto out = pv::vector_topk(batches, argv[3], read_query(argv[5]), std::stoull(argv[4]), &dist);
             auto keys = std::static_pointer_cast<arrow::Int64Array>(out->GetColumnByName(argv[6]));
             for (int64_t i = 0; i < out->num_rows(); ++i) std::cout << keys->Value(i) << " " << bits(dist[(size_t)i]) << "\n";
+        } else if (cmd == "vector-topk-indexed" && (argc == 7 || argc == 8)) {
+            // <indexed parquet> <k> <nprobe> <max_candidates or -> <query file> [filter: packed bits file]
+            pv::VectorTopKOptions opt;
+            opt.nprobe = std::stoull(argv[4]);
+            if (strcmp(argv[5], "-") != 0) {
+                opt.has_max_candidates = true;
+                opt.max_candidates = std::stoull(argv[5]);
+            }
+            std::string mask = argc == 8 ? slurp(argv[7]) : std::string();
+            auto r = pv::vector_topk_indexed(argv[2], read_query(argv[6]), std::stoull(argv[3]), opt,
+                                             argc == 8 ? reinterpret_cast<const uint8_t *>(mask.data()) : nullptr, mask.size());
+            std::cout << r.candidate_rows << " " << r.embeddings_fetched << "\n";
+            for (size_t i = 0; i < r.rows.size(); ++i) std::cout << r.rows[i] << " " << bits(r.distances[i]) << "\n";
         } else {
-            std::cerr << "usage: pqv_host_cli has-index|append-index|read-index|read-embeddings|build-inplace|build-new|search|vector-topk ...\n";
+            std::cerr << "usage: pqv_host_cli has-index|append-index|read-index|read-embeddings|build-inplace|build-new|search|vector-topk|vector-topk-indexed ...\n";
             return 2;
         }
     } catch (const std::exception &e) {

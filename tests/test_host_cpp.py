@@ -226,3 +226,37 @@ def test_cpp_vector_topk_is_the_operators_answer(tmp_path):
     pq.write_table(pa.table({"id": pa.array(np.arange(5, dtype=np.int64)), "embedding": col}), p2)
     out = cli("vector-topk", p2, "embedding", 10, q, "id").stdout.split()
     assert [int(x) for x in out[0::2]] == [3, 0, 4]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("rows,min_id,want_ids,fetched", [
+    ([(0, 0), (1, 0), (0, 2), (5, 5), (2, 2), (0.1, 0.1)], 2, [5, 2], 4),                       # df_vector/tests.rs:16-104
+    ([(0, 0), (.05, .05), (.2, .2), (1, 1), (1.1, 1.1), (1.4, 1.4)], 3, [3, 4], 3),             # df_vector/tests.rs:151-241
+])
+def test_cpp_vector_topk_indexed_passes_the_crates_sql_tests(tmp_path, rows, min_id, want_ids, fetched):
+    """The crate's two SQL tests at the operator: `WHERE id >= m ORDER BY array_distance(vec, [0, 0]) LIMIT 2` over the
+    file IndexBuilder::build_new wrote, options {nprobe: 64, max_candidates: None}; ids and the snapshot counters
+    (`candidate_rows: 6`, `embeddings_fetched`) as pinned by the crate."""
+    emb = np.array(rows, np.float32)
+    src, out = str(tmp_path / "source.parquet"), str(tmp_path / "indexed.parquet")
+    t = pa.table({"id": pa.array(np.arange(6, dtype=np.int32)),
+                  "vec": pa.array([r.tolist() for r in emb], type=pa.list_(pa.float32()))})
+    pq.write_table(t, src)
+    cli("build-new", src, "vec", out)                                   # IndexBuilder::new(source, "vec").build_new(indexed)
+    assert cli("has-index", out).stdout.strip() == "1" and pq.read_table(out).column("id").to_pylist() == list(range(6))
+    q = tmp_path / "q.bin"
+    q.write_bytes(np.zeros(2, np.float32).tobytes())
+    mask = tmp_path / "mask.bin"                                        # the FilterExec predicate over the file's rows
+    mask.write_bytes(np.packbits(np.arange(6) >= min_id, bitorder="little").tobytes())
+    lines = cli("vector-topk-indexed", out, 2, 64, "-", q, mask).stdout.split("\n")
+    assert lines[0].split() == ["6", str(fetched)]
+    got = [int(l.split()[0]) for l in lines[1:] if l]
+    assert got == want_ids
+    # without the filter the closest two rows win; a cap of 3 candidates (rank order) is reported in the counters
+    lines = cli("vector-topk-indexed", out, 2, 64, "-", q).stdout.split("\n")
+    assert lines[0].split() == ["6", "6"] and [int(l.split()[0]) for l in lines[1:] if l][0] == 0
+    lines = cli("vector-topk-indexed", out, 2, 64, 3, q).stdout.split("\n")
+    assert lines[0].split()[1] == "3"
+    q3 = tmp_path / "q3.bin"
+    q3.write_bytes(np.zeros(3, np.float32).tobytes())
+    assert "Query dimension mismatch: expected 2, got 3" in cli("vector-topk-indexed", out, 2, 64, "-", q3, ok=False).stderr
