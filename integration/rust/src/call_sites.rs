@@ -58,10 +58,10 @@ pub fn resident_file(path: &Path, embedding_column: &EmbeddingColumn, index_blob
         }
         let first = list.value_offsets()[0] as usize;
         let len = list.len() * dim;
-        let t = match &table {
-            Some(t) => t,
-            None => table.insert(gpu.create_table(dim, rows)?),
-        };
+        if table.is_none() {
+            table = Some(gpu.create_table(dim, rows)?);
+        }
+        let t = table.as_ref().expect("created above");
         if let Some(values) = list.values().as_any().downcast_ref::<Float32Array>() {
             if values.null_count() > 0 {
                 return Err("Embedding values contain nulls".into());
