@@ -52,7 +52,13 @@ pub fn resident_file(path: &Path, embedding_column: &EmbeddingColumn, index_blob
         if list.null_count() > 0 {
             return Err("Embedding column contains null rows".into());
         }
+        if list.is_empty() {
+            continue;
+        }
         let dim = list.value_length(0) as usize;
+        if dim == 0 {
+            return Err("Embedding row has zero length".into());
+        }
         if (0..list.len()).any(|r| list.value_length(r) as usize != dim) {
             return Err("Embedding vectors have inconsistent dimensions".into());
         }
