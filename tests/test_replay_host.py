@@ -100,3 +100,37 @@ def test_chunked_threshold_entrants_are_a_superset_of_the_heap_admissions(levels
         rows, d = P.replay_candidates(_keys(dist[sup], sup), k, P.PQV_SQRT if do_sqrt else 0)
         assert rows.tolist() == er.tolist()
         assert d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+
+
+@pytest.mark.parametrize("levels", [0, 50])
+@pytest.mark.parametrize("k", [1, 10, 100])
+@pytest.mark.parametrize("do_sqrt", [False, True])
+def test_short_prefix_plus_thresholded_candidates_replay_to_the_reference_answer(levels, k, do_sqrt):
+    """Model of the plan in DESIGN.md section 8 for the tie queries of the masked IVF pass: the pass knows every candidate
+    with d < tau (tau >= the final k-th smallest distance) but not the early rows the heap admits while its threshold is
+    still above tau.  Those can only sit before the position P* where the k-th candidate of the sequence appears -- from
+    P* on the heap's threshold is below tau -- so exact distances are needed for the prefix [0, P*] only:
+    replay(admissions of the exact prefix + candidates behind it) must equal the reference loop over the whole sequence."""
+    rng = np.random.default_rng(1000 * levels + 10 * k + do_sqrt)
+    n = 30000
+    dist = (rng.random(n).astype(np.float32) * 4 + 0.5)
+    if levels:
+        dist = (np.floor(dist * levels) / levels).astype(np.float32)
+    er, ed = O.heap_topk(dist, None, k, do_sqrt)
+    # tau as the batched pass derives it: the k-th smallest distance of a SAMPLE of the rows (an upper bound of the final one)
+    sample = rng.choice(n, n // 16, replace=False)
+    tau = np.partition(dist[sample], k - 1)[k - 1]
+    cand = np.nonzero(dist < tau)[0]                       # strict: rows equal to tau are not guaranteed to be candidates
+    if cand.size < k:                                      # (possible with heavy ties) -> the whole sequence is the prefix
+        p_star = n - 1
+    else:
+        p_star = int(cand[k - 1])                          # position of the k-th candidate in sequence order
+    prefix_adm = _entrants(dist[:p_star + 1], k)           # exact distances over the short prefix only
+    later = cand[cand > p_star]
+    sel = np.concatenate([prefix_adm, later])
+    assert np.isin(_entrants(dist, k), sel).all()          # nothing the reference heap admits is missing
+    if levels == 0 and k == 100:
+        assert p_star < n // 8                             # and the prefix is short: ~ k / (candidates per row)
+    rows, d = P.replay_candidates(_keys(dist[sel], sel), k, P.PQV_SQRT if do_sqrt else 0)
+    assert rows.tolist() == er.tolist()
+    assert d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
