@@ -966,7 +966,7 @@ static void pqv_free_all_indexes(pqv_ctx *ctx);
 extern "C" {
 
 const char *pqv_last_error(void) { return g_err.c_str(); }
-const char *pqv_version(void) { return "pq-vector-b200 0.2.0 (sm_100a)"; }
+const char *pqv_version(void) { return "pq-vector-b200 0.3.0 (sm_100a)"; }
 
 int pqv_init(pqv_ctx **out, const int *device_ids, int n_devices) {
     if (!out) return fail(PQV_EINVAL, "out is null");
