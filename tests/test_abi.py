@@ -129,3 +129,39 @@ def test_rust_wrappers_call_the_abi_with_the_declared_arity():
                  "pqv_kmeans_assign", "pqv_min_dist_update", "pqv_centroid_rank", "pqv_ivf_search_coalesced",
                  "pqv_vector_topk_indexed", "pqv_array_distance"]:
         assert must in used, must
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """The boundary is a C ABI: include/pqv.h must compile as C99 on its own, and a C program must be able to link
+    libpqv.so and call it (without a GPU: pqv_init reports PQV_ENODEV and a message, nothing else happens)."""
+    import shutil
+    import subprocess
+    from pq_vector_b200 import _native as N
+    gcc = shutil.which("gcc")
+    if not gcc:
+        pytest.skip("gcc not available")
+    hdr = os.path.join(ROOT, "include", "pqv.h")
+    r = subprocess.run([gcc, "-std=c99", "-pedantic", "-Wall", "-Werror", "-fsyntax-only", "-x", "c", hdr], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    src = tmp_path / "c_caller.c"
+    src.write_text('#include <stdio.h>\n#include "pqv.h"\n'
+                   'int main(void) {\n'
+                   '    pqv_ctx *ctx = NULL;\n'
+                   '    int rc = pqv_init(&ctx, NULL, 0);\n'
+                   '    printf("%s|%d|%s\\n", pqv_version(), rc, rc ? pqv_last_error() : "");\n'
+                   '    if (!rc) { printf("devices %d\\n", pqv_device_count(ctx)); pqv_destroy(ctx); }\n'
+                   '    return 0;\n}\n')
+    exe = tmp_path / "c_caller"
+    libdir = os.path.dirname(N.LIB_PATH)
+    r = subprocess.run([gcc, "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                        "-L", libdir, "-lpqv", f"-Wl,-rpath,{libdir}"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stderr
+    version, rc, msg = out.stdout.splitlines()[0].split("|")
+    assert version.startswith("pq-vector-b200")
+    import torch
+    if torch.cuda.is_available():
+        assert rc == "0"
+    else:
+        assert rc == "2" and "no CPU fallback" in msg      # PQV_ENODEV
