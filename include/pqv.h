@@ -309,13 +309,15 @@ PQV_API int pqv_ivf_search_candidates(pqv_ctx *ctx, uint64_t handle, uint64_t in
  * Replaces execute_with_candidates + topk_from_batches (src/df_vector/exec.rs:207-277) when the file's embedding column
  * and index are resident (pqv_dataset_*, pqv_ivf_from_bytes): the index's candidate rows for `nprobe`
  * (src/df_vector/index_exec.rs:159-163), of which the first `max_candidates` in rank order count (CandidateCursor over
- * one file, src/df_vector/access.rs:193-243; 0 = no cap, options.rs:10-11), visited in ascending row order (the
+ * one file, src/df_vector/access.rs:193-243; PQV_NO_CANDIDATE_CAP = `None`, no cap, options.rs:10-11; 0 = `Some(0)`: no
+ * row is fetched and the result is empty, src/df_vector/exec.rs:222-223), visited in ascending row order (the
  * RowSelection of access.rs:107-176), rows whose bit in `row_mask` is clear dropped BEFORE scoring (the FilterExec of the
  * scan subtree, src/df_vector/tests.rs:151-241), then the bounded heap of k.  Use flags = PQV_SUM_SEQ for the operator's
  * own arithmetic (exec.rs:529-533, squared distances out).  row_mask: NULL = every row passes; else ceil(n_rows / 8)
  * bytes, bit (r & 7) of byte (r >> 3) = row r passes (an Arrow boolean buffer).  out_candidate_rows / out_rows_scored
  * (may be NULL) are the plan counters `candidate_rows` and `embeddings_fetched` of the reference's snapshots.
  * Ranking, candidate bitmap, ordered compaction, gathered scan and top-k run in one host<->device round trip. */
+#define PQV_NO_CANDIDATE_CAP 0xFFFFFFFFFFFFFFFFull  /* VectorTopKOptions::max_candidates == None */
 PQV_API int pqv_vector_topk_indexed(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *query, uint32_t k,
                             uint32_t nprobe, uint32_t flags, uint64_t max_candidates, const uint8_t *row_mask,
                             uint32_t *out_row_idx, float *out_dist, uint32_t *out_count, uint64_t *out_candidate_rows,

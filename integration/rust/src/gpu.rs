@@ -214,7 +214,7 @@ impl Table {
         let (mut candidates, mut scored) = (0u64, 0u64);
         check(unsafe {
             sys::pqv_vector_topk_indexed(self.gpu.raw(), self.handle, index.handle, query.as_ptr(), k as u32, nprobe as u32,
-                                         sys::PQV_SUM_SEQ, max_candidates.unwrap_or(0) as u64,
+                                         sys::PQV_SUM_SEQ, max_candidates.map_or(sys::PQV_NO_CANDIDATE_CAP, |m| m as u64),
                                          row_mask.map_or(std::ptr::null(), |m| m.as_ptr()), idx.as_mut_ptr(),
                                          dist.as_mut_ptr(), &mut n, &mut candidates, &mut scored)
         })?;

@@ -501,7 +501,7 @@ class IvfIndex:
         dist = np.zeros(max(k, 1), dtype=np.float32)
         cnt, cand, scored = C.c_uint32(), C.c_uint64(), C.c_uint64()
         _check(_lib.pqv_vector_topk_indexed(self.ctx._h, dataset.handle, self.handle, _ptr(q, C.c_float), k, nprobe, flags,
-                                            int(max_candidates or 0), _ptr(bits, C.c_uint8), _ptr(rows, C.c_uint32),
+                                            (0xFFFFFFFFFFFFFFFF if max_candidates is None else int(max_candidates)), _ptr(bits, C.c_uint8), _ptr(rows, C.c_uint32),
                                             _ptr(dist, C.c_float), C.byref(cnt), C.byref(cand), C.byref(scored)))
         return rows[:cnt.value].copy(), dist[:cnt.value].copy(), cand.value, scored.value
 

@@ -175,37 +175,174 @@ def read_index_payload(path) -> "tuple[bytes, str]":
     return payload[header_len:header_len + index_len], column
 
 
+# --- thrift compact protocol, just enough to edit FileMetaData.key_value_metadata (field 5) of an existing footer -------
+def _tc_varint(buf, pos):
+    shift = val = 0
+    while True:
+        b = buf[pos]
+        pos += 1
+        val |= (b & 0x7F) << shift
+        if not b & 0x80:
+            return val, pos
+        shift += 7
+
+
+def _tc_put_varint(v: int) -> bytes:
+    out = bytearray()
+    while True:
+        if v < 0x80:
+            out.append(v)
+            return bytes(out)
+        out.append((v & 0x7F) | 0x80)
+        v >>= 7
+
+
+def _tc_skip(buf, pos, t):
+    """end position of a value of compact-protocol type t that starts at pos"""
+    if t in (1, 2):          # bool carried by the field header
+        return pos
+    if t == 3:               # byte
+        return pos + 1
+    if t in (4, 5, 6):       # zigzag varints
+        return _tc_varint(buf, pos)[1]
+    if t == 7:               # double
+        return pos + 8
+    if t == 8:               # binary / string
+        n, pos = _tc_varint(buf, pos)
+        return pos + n
+    if t in (9, 10):         # list / set
+        head = buf[pos]
+        pos += 1
+        n, et = head >> 4, head & 0x0F
+        if n == 15:
+            n, pos = _tc_varint(buf, pos)
+        for _ in range(n):
+            pos = pos + 1 if et in (1, 2) else _tc_skip(buf, pos, et)
+        return pos
+    if t == 11:              # map
+        n, pos = _tc_varint(buf, pos)
+        if n:
+            kt, vt = buf[pos] >> 4, buf[pos] & 0x0F
+            pos += 1
+            for _ in range(n):
+                pos = pos + 1 if kt in (1, 2) else _tc_skip(buf, pos, kt)
+                pos = pos + 1 if vt in (1, 2) else _tc_skip(buf, pos, vt)
+        return pos
+    if t == 12:              # struct
+        for _fid, ft, _s, e in _tc_fields(buf, pos):
+            pos = e
+        return pos + 1       # STOP byte
+    raise PqVectorError(f"Unsupported thrift type {t} in parquet footer")
+
+
+def _tc_fields(buf, pos):
+    """(field id, type, value start, value end) of every field of the struct that starts at pos"""
+    last = 0
+    while True:
+        head = buf[pos]
+        pos += 1
+        if head == 0:
+            return
+        t, delta = head & 0x0F, head >> 4
+        if delta:
+            fid = last + delta
+        else:
+            z, pos = _tc_varint(buf, pos)
+            fid = (z >> 1) ^ -(z & 1)
+        end = _tc_skip(buf, pos, t)
+        yield fid, t, pos, end
+        last, pos = fid, end
+
+
+def _tc_field_header(fid: int, last: int, t: int) -> bytes:
+    d = fid - last
+    if 0 < d <= 15:
+        return bytes([(d << 4) | t])
+    return bytes([t]) + _tc_put_varint((fid << 1) ^ (fid >> 31))
+
+
+def _tc_string(b: bytes) -> bytes:
+    return _tc_put_varint(len(b)) + b
+
+
+def footer_with_key_values(footer: bytes, drop_keys, add: "list[tuple[bytes, bytes]]") -> bytes:
+    """The FileMetaData thrift struct `footer` with key_value_metadata (field 5) = its old entries minus drop_keys plus
+    `add`, every other field byte for byte as it was (schema, row groups, created_by, column orders: parquet.rs:566-583
+    rebuilds FileMetaData from exactly those parts)."""
+    fields = list(_tc_fields(footer, 0))
+    entries = []
+    for fid, t, s, e in fields:
+        if fid != 5:
+            continue
+        if t != 9:
+            raise PqVectorError("key_value_metadata is not a list in this parquet footer")
+        head = footer[s]
+        pos = s + 1
+        n = head >> 4
+        if n == 15:
+            n, pos = _tc_varint(footer, pos)
+        for _ in range(n):
+            key = None
+            for kf, kt, ks, ke in _tc_fields(footer, pos):
+                if kf == 1 and kt == 8:
+                    ln, kp = _tc_varint(footer, ks)
+                    key = bytes(footer[kp:kp + ln])
+            end = _tc_skip(footer, pos, 12)
+            if key not in drop_keys:
+                entries.append(bytes(footer[pos:end]))
+            pos = end
+    for k, v in add:  # KeyValue { 1: required string key, 2: optional string value }
+        entries.append(b"\x18" + _tc_string(k) + b"\x18" + _tc_string(v) + b"\x00")
+    kv_list = (bytes([(len(entries) << 4) | 12]) if len(entries) < 15 else bytes([0xF0 | 12]) + _tc_put_varint(len(entries)))
+    kv_list += b"".join(entries)
+    out = bytearray()
+    last, placed = 0, False
+    for fid, t, s, e in fields:
+        if fid == 5:
+            continue
+        if fid > 5 and not placed:
+            out += _tc_field_header(5, last, 9) + kv_list
+            last, placed = 5, True
+        out += _tc_field_header(fid, last, t) + footer[s:e]
+        last = fid
+    if not placed:
+        out += _tc_field_header(5, last, 9) + kv_list
+    out.append(0)
+    return bytes(out)
+
+
 def append_index_inplace(path, index_bytes: bytes, embedding_column: str):
     """parquet.rs:542-611: the payload goes where the 8-byte footer tail was (the old footer bytes stay behind as dead
-    space, exactly as in the reference), followed by a new footer = the old one + the two key-values.  Data pages do
-    not move, so every column-chunk offset stays valid."""
+    space, exactly as in the reference), followed by a new footer = the old one with the two key-values replaced /
+    appended.  The footer is edited at the thrift level, so schema, row groups, created_by and every foreign key-value
+    (ARROW:schema included) survive byte for byte whichever writer produced the file (parquet-rs, pyarrow, ...).  Data
+    pages do not move, so every column-chunk offset stays valid."""
     size = os.path.getsize(path)
     if size < 8:
         raise PqVectorError("Parquet file too small to contain a footer")
-    md = pq.read_metadata(path)
-    kv = {k: v for k, v in (md.metadata or {}).items()
-          if k not in (b"ARROW:schema", PQ_VECTOR_INDEX_OFFSET_KEY, PQ_VECTOR_EMBEDDING_COLUMN_KEY)}
+    with open(path, "rb") as f:
+        f.seek(size - 8)
+        tail = f.read(8)
+        if tail[4:] == b"PARE":
+            raise PqVectorError("Encrypted parquet footers are not supported for in-place indexing")
+        if tail[4:] != b"PAR1":
+            raise PqVectorError("Invalid parquet footer magic")
+        (old_len,) = struct.unpack("<I", tail[:4])
+        if old_len + 8 > size:
+            raise PqVectorError("Parquet footer length exceeds file size")
+        f.seek(size - 8 - old_len)
+        old_footer = f.read(old_len)
     index_offset = size - 8
-    kv[PQ_VECTOR_INDEX_OFFSET_KEY] = str(index_offset).encode()
-    kv[PQ_VECTOR_EMBEDDING_COLUMN_KEY] = embedding_column.encode()
-    # pyarrow serialises a footer for us as a metadata-only file: PAR1 | FileMetaData | u32 length | PAR1
-    tmp = f"{path}.pqv_footer_tmp"
-    try:
-        pq.write_metadata(md.schema.to_arrow_schema().with_metadata(kv), tmp, metadata_collector=[md])
-        with open(tmp, "rb") as f:
-            meta_file = f.read()
-    finally:
-        if os.path.exists(tmp):
-            os.remove(tmp)
-    (footer_len,) = struct.unpack("<I", meta_file[-8:-4])
-    footer = meta_file[-8 - footer_len:-8]
+    footer = footer_with_key_values(
+        old_footer, (PQ_VECTOR_INDEX_OFFSET_KEY, PQ_VECTOR_EMBEDDING_COLUMN_KEY),
+        [(PQ_VECTOR_INDEX_OFFSET_KEY, str(index_offset).encode()), (PQ_VECTOR_EMBEDDING_COLUMN_KEY, embedding_column.encode())])
     with open(path, "r+b") as f:
         f.seek(index_offset)
         f.write(PQ_VECTOR_INDEX_MAGIC)
         f.write(struct.pack("<Q", len(index_bytes)))
         f.write(index_bytes)
         f.write(footer)
-        f.write(struct.pack("<I", footer_len))
+        f.write(struct.pack("<I", len(footer)))
         f.write(b"PAR1")
         f.truncate()
 

@@ -87,6 +87,7 @@ struct IvfIndex {
     std::vector<u64> offsets;  // n_clusters + 1
     std::vector<uint32_t> ids;  // host copy of the lists; after a device build it is fetched on first use
     u64 n_ids = 0;
+    uint32_t max_id = 0;         // largest row id in any list (from_bytes: taken from the blob; device build: n - 1)
     bool host_ids = true;        // `ids` holds the lists
     bool lists_on_device = false;  // d_offsets / d_ids already hold the lists (device-built index)
     // device mirror (device 0 of the context), created on first search
@@ -164,6 +165,17 @@ double now_ms() {
 IvfIndex *find_index(pqv_ctx *ctx, u64 h) {
     auto it = ctx->indexes.find(h);
     return it == ctx->indexes.end() ? nullptr : static_cast<IvfIndex *>(it->second);
+}
+
+// An index may only be paired with a table that holds every row its lists name: the gather kernels read
+// data + id * dim without further checks, and a stale or foreign blob (file rewritten, index of another table) must fail
+// as cleanly as the reference does, not with an illegal address.
+int check_index_fits(const IvfIndex &ix, const Dataset &ds) {
+    if (ix.n_ids > ds.n_rows)
+        return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix.n_ids, (unsigned long long)ds.n_rows);
+    if (ix.n_ids && (u64)ix.max_id >= ds.n_rows)
+        return fail(PQV_EINVAL, "index lists name row %u, dataset has %llu rows", ix.max_id, (unsigned long long)ds.n_rows);
+    return PQV_OK;
 }
 
 int index_make_resident(DeviceState &D, IvfIndex &ix) {
@@ -694,6 +706,7 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
                 ctx->last_assign.total_ms, tf[2] - tf[1]);
     }
     ix->n_ids = n;
+    ix->max_id = (uint32_t)(n - 1);
     if (lists_built) {
         ix->offsets.resize((size_t)C + 1);
         IVF_CU(cudaMemcpyAsync(ix->offsets.data(), ix->d_offsets.p, ((size_t)C + 1) * 8, cudaMemcpyDeviceToHost, D.stream));
@@ -811,6 +824,7 @@ int pqv_ivf_from_bytes(pqv_ctx *ctx, const uint8_t *bytes, uint64_t len, uint64_
         ix->offsets[c + 1] = ix->offsets[c] + l;
     }
     ix->n_ids = ix->ids.size();
+    for (uint32_t id : ix->ids) ix->max_id = std::max(ix->max_id, id);
     std::lock_guard<std::mutex> lk(ctx->mu);
     const u64 h = ctx->next_handle++;
     ctx->indexes[h] = ix;
@@ -943,7 +957,7 @@ int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *q
     PQV_TRY(check_topk_args(k, ds->dim, flags));
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
     if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search needs a single-device dataset");
-    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    PQV_TRY(check_index_fits(*ix, *ds));
     DeviceState &D = ctx->devs[ds->shards[0].di];
     DevGuard guard(D.dev);
     return ivf_search_one(ctx, ds, D, ix, query, k, nprobe, flags, out_row_idx, out_dist, out_count);
@@ -1044,7 +1058,7 @@ int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const fl
     PQV_TRY(check_topk_args(k, ds->dim, flags));
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
     if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search_batch needs a single-device dataset");
-    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    PQV_TRY(check_index_fits(*ix, *ds));
     DeviceState &D = ctx->devs[ds->shards[0].di];
     DevGuard guard(D.dev);
     PQV_TRY(index_make_resident(D, *ix));
@@ -1100,7 +1114,7 @@ int pqv_ivf_search_batch_keys(pqv_ctx *ctx, uint64_t handle, uint64_t index, con
     if (flags & PQV_TIES_BY_POSITION) return fail(PQV_EINVAL, "batch keys are only defined for the reference tie order");
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
     if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search_batch_keys needs a single-device dataset");
-    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    PQV_TRY(check_index_fits(*ix, *ds));
     if ((u64)pos_base + ds->n_rows > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "global row ids are u32");
     if (n_queries > BATCH_MAX_QUERIES)
         return fail(PQV_ELIMIT, "at most %u queries per pqv_ivf_search_batch_keys call (got %u)", BATCH_MAX_QUERIES, n_queries);
@@ -1135,7 +1149,7 @@ int pqv_ivf_search_candidates(pqv_ctx *ctx, uint64_t handle, uint64_t index, con
     if (flags & PQV_TIES_BY_POSITION) return fail(PQV_EINVAL, "candidates are only defined for the reference tie order");
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
     if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search_candidates needs a single-device dataset");
-    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    PQV_TRY(check_index_fits(*ix, *ds));
     DeviceState &D = ctx->devs[ds->shards[0].di];
     DevGuard guard(D.dev);
     PQV_TRY(index_make_resident(D, *ix));
@@ -1189,7 +1203,7 @@ int pqv_vector_topk_indexed_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index,
     PQV_TRY(check_topk_args(k, ds->dim, flags));
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
     if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_vector_topk_indexed_batch needs a single-device dataset");
-    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    PQV_TRY(check_index_fits(*ix, *ds));
     DeviceState &D = ctx->devs[ds->shards[0].di];
     DevGuard guard(D.dev);
     PQV_TRY(index_make_resident(D, *ix));
@@ -1243,14 +1257,25 @@ int pqv_vector_topk_indexed(pqv_ctx *ctx, uint64_t handle, uint64_t index, const
     PQV_TRY(check_topk_args(k, ds->dim, flags));
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);  // index_exec.rs:152-158
     if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_vector_topk_indexed needs a single-device dataset");
-    if (ix->n_ids > ds->n_rows) return fail(PQV_EINVAL, "index lists hold %llu rows, dataset has %llu", (unsigned long long)ix->n_ids, (unsigned long long)ds->n_rows);
+    PQV_TRY(check_index_fits(*ix, *ds));
     DeviceState &D = ctx->devs[ds->shards[0].di];
     DevGuard guard(D.dev);
     PQV_TRY(index_make_resident(D, *ix));
     RowOrder ro;
-    ro.max_candidates = max_candidates ? max_candidates : ~0ull;   // options.rs:10-11: None = no cap
+    ro.max_candidates = max_candidates;   // PQV_NO_CANDIDATE_CAP = ~0: None = no cap (options.rs:10-11)
     ro.h_mask = row_mask;
     *out_count = 0;
+    if (max_candidates == 0) {
+        // Some(0): target_candidates = 0 (exec.rs:222-223) -- the index scan still reports its candidates, nothing is
+        // fetched or scored, the operator emits no row
+        std::vector<uint32_t> ranked0;
+        PQV_TRY(rank_clusters(D, *ix, query, nprobe, ranked0));
+        u64 total0 = 0;
+        for (uint32_t c : ranked0) total0 += ix->offsets[c + 1] - ix->offsets[c];
+        if (out_candidate_rows) *out_candidate_rows = total0;
+        if (out_rows_scored) *out_rows_scored = 0;
+        return PQV_OK;
+    }
     if (ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids) {
         bool done = false;
         PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, query, k, nprobe, flags, out_row_idx, out_dist, out_count, &done, &ro));

@@ -486,7 +486,7 @@ VectorTopKRows vector_topk_indexed(const std::string &parquet_path, const std::v
     out.distances.resize(k);
     uint32_t n = 0;
     gpu_check(pqv_vector_topk_indexed(gpu(), t.handle, ix.handle, query.data(), (uint32_t)k, (uint32_t)options.nprobe, PQV_SUM_SEQ,
-                                      options.has_max_candidates ? (uint64_t)options.max_candidates : 0ull, filter_mask,
+                                      options.has_max_candidates ? (uint64_t)options.max_candidates : PQV_NO_CANDIDATE_CAP, filter_mask,
                                       out.rows.data(), out.distances.data(), &n, &out.candidate_rows, &out.embeddings_fetched));
     out.rows.resize(n);
     out.distances.resize(n);

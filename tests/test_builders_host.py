@@ -136,3 +136,60 @@ def test_dense_rows_of_every_list_flavour():
         B._dense_rows(pa.array([1.0, 2.0]), q)
     with pytest.raises(B.PqVectorError, match="Vector column must be Float32 or Float64 list"):
         B._dense_rows(pa.array([[1, 2]], pa.list_(pa.int64())), q)
+
+
+def _check_surgery_keeps_footer(path):
+    """append_index_inplace on `path` keeps schema, created_by, row-group metadata and foreign key-values byte for byte"""
+    md0 = pq.read_metadata(path)
+    before = pq.read_table(path)
+    kv0 = dict(md0.metadata or {})
+    size0 = os.path.getsize(path)
+    blob = bytes(range(64))
+    for rep in range(2):                                             # the second build replaces the two keys (parquet.rs:573-575)
+        B.append_index_inplace(path, blob, "embedding")
+        md1 = pq.read_metadata(path)
+        kv1 = dict(md1.metadata)
+        assert md1.schema.equals(md0.schema) and md1.created_by == md0.created_by
+        assert md1.num_rows == md0.num_rows and md1.num_row_groups == md0.num_row_groups
+        for i in range(md0.num_row_groups):
+            assert md1.row_group(i).to_dict() == md0.row_group(i).to_dict()
+        assert {k: v for k, v in kv1.items() if not k.startswith(b"pq_vector_")} == kv0     # ARROW:schema included
+        assert kv1[b"pq_vector_embedding_column"] == b"embedding"
+        assert int(kv1[b"pq_vector_index_offset"]) == (size0 - 8 if rep == 0 else size1 - 8)
+        assert B.read_index_payload(path) == (blob, "embedding")
+        assert pq.read_table(path).equals(before)
+        size1 = os.path.getsize(path)
+
+
+def test_append_index_inplace_keeps_foreign_footers(tmp_path):
+    """Files written by arrow-rs / DataFusion / the reference crate name list children `item` (pyarrow: `element`) and carry
+    nested columns; the surgery must not re-derive the schema (pq.write_metadata + AppendRowGroups refused
+    them).  use_compliant_nested_type=False gives the arrow-rs naming from pyarrow."""
+    path = str(tmp_path / "rs_style.parquet")
+    n = 40
+    t = pa.table({"id": pa.array(range(n), pa.int64()),
+                  "authors": pa.array([["a", "b"]] * n, pa.list_(pa.string())),
+                  "embedding": pa.array([[float(i), 1.0, 2.0] for i in range(n)], pa.list_(pa.float32())),
+                  "meta": pa.array([{"x": i, "y": str(i)} for i in range(n)])})
+    pq.write_table(t, path, compression="NONE", use_compliant_nested_type=False, row_group_size=16)
+    assert pq.read_metadata(path).schema.column(1).path == "authors.list.item"
+    _check_surgery_keeps_footer(path)
+    # no key-value metadata at all in the source footer (field 5 absent -> inserted, the following field's header re-based)
+    bare = str(tmp_path / "bare.parquet")
+    pq.write_table(t, bare, compression="SNAPPY", store_schema=False)
+    assert not pq.read_metadata(bare).metadata
+    _check_surgery_keeps_footer(bare)
+    # more than 14 key-values: long-form thrift list header
+    many = str(tmp_path / "many.parquet")
+    pq.write_table(t.replace_schema_metadata({f"k{i}": "v" * i for i in range(20)}), many)
+    _check_surgery_keeps_footer(many)
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/data/vldb_2025.parquet"), reason="reference checkout not present")
+def test_append_index_inplace_on_the_reference_dataset(tmp_path):
+    """the parquet-rs 55.2.0 file the crate ships (14 columns, List<Float32> embeddings)"""
+    import shutil
+    path = str(tmp_path / "vldb.parquet")
+    shutil.copy("/root/reference/data/vldb_2025.parquet", path)
+    assert b"parquet-rs" in pq.read_metadata(path).created_by.encode()
+    _check_surgery_keeps_footer(path)

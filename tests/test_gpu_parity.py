@@ -361,6 +361,64 @@ def test_c2_scale_properties(ctx):
     ds.drop()
 
 
+def _oracle_distances_full(n, dim, seed, q, order, block=500_000):
+    """squared distances of q to every one of the n synthetic rows, in the oracle's arithmetic: blocks generated and scored
+    on all host threads (the loop body is per-row independent; ctypes releases the GIL), one f32 per row kept"""
+    import ctypes as C
+    import os
+    import threading
+    out = np.empty(n, dtype=np.float32)
+    L = O.lib()
+    nthreads = os.cpu_count() or 1
+    starts = list(range(0, n, block))
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                if not starts:
+                    return
+                s = starts.pop()
+            m = min(block, n - s)
+            blk = np.empty((m, dim), dtype=np.float32)
+            L.pqo_synth_fill(blk.ctypes.data_as(C.POINTER(C.c_float)), s * dim, m * dim, seed)
+            L.pqo_distances(blk.ctypes.data_as(C.POINTER(C.c_float)), m, dim, q.ctypes.data_as(C.POINTER(C.c_float)), order,
+                            out[s:s + m].ctypes.data_as(C.POINTER(C.c_float)))
+
+    th = [threading.Thread(target=work) for _ in range(nthreads)]
+    for t in th:
+        t.start()
+    for t in th:
+        t.join()
+    return out
+
+
+def test_full_scale_c2_equals_the_oracle_top100(ctx):
+    """BASELINE configs[1] at its full size: the GPU's top-100 of 10M x 768 is the reference loop's top-100 -- same row ids
+    in the same order, same f32 bits -- for both summation orders.  Oracle side: exact distances of ALL 10M rows (blocks on
+    every host core), then the reference's bounded BinaryHeap + sqrt + stable sort over the 10M values
+    (pqo_heap_topk = src/ivf/search.rs:112-141)."""
+    n, dim, seed, k = 10_000_000, 768, 1234, 100
+    ds = ctx.dataset(dim, n)
+    ds.fill_synthetic(n, seed)
+    qs = O.synth(3, dim, 7)
+    for qi, flags in ((0, SQRT), (1, SQRT), (2, SEQ)):
+        q = np.ascontiguousarray(qs[qi])
+        r, d = ds.l2_topk(q, k, flags)
+        dist = _oracle_distances_full(n, dim, seed, q, 1 if flags & SEQ else 0)
+        er, ed = O.heap_topk(dist, None, k, bool(flags & SQRT))
+        assert r.tolist() == er.tolist()
+        assert bits(d).tolist() == bits(ed).tolist()
+    # the batched tensor-core pass over the same table: every query equals its own oracle loop too
+    qb = np.ascontiguousarray(O.synth(8, dim, 11))
+    rows, dd, cnt = ds.l2_topk(qb, 10, SEQ)
+    for i in (0, 7):
+        dist = _oracle_distances_full(n, dim, seed, np.ascontiguousarray(qb[i]), 1)
+        er, ed = O.heap_topk(dist, None, 10, False)
+        assert cnt[i] == 10 and rows[i].tolist() == er.tolist() and bits(dd[i]).tolist() == bits(ed).tolist()
+    ds.drop()
+
+
 def test_peer_exchange_world_of_one(ctx, P):
     """pqv_peer_exchange_* + pqv_l2_topk_candidates_p2p with a single rank (the buffer is its own peer): publish / flag /
     wait kernels, sequence parity over several searches, and the slot-overflow signal.  The multi-rank exchange is

@@ -13,19 +13,35 @@ import torch.multiprocessing as mp
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _run_cases(rank, world, port0, fn_name, cases, out_dir):
+def _run_cases(rank, world, ports, fn_name, cases, out_dir):
     """all cases of one test in ONE pair of processes (a spawn costs ~10 s of interpreter + torch start-up): every case
     gets its own rendezvous port, process group and output directory"""
     fn = globals()[fn_name]
     for i, case in enumerate(cases):
         d = os.path.join(out_dir, f"case{i}")
         os.makedirs(d, exist_ok=True)
-        fn(rank, world, port0 + i, *case, d)
+        fn(rank, world, ports[i], *case, d)
 
 
-def _spawn_cases(fn, cases, tmp_path, port_base):
-    port0 = port_base + (os.getpid() * 16) % 1900
-    mp.spawn(_run_cases, args=(2, port0, fn.__name__, cases, str(tmp_path)), nprocs=2, join=True)
+def _free_ports(n):
+    """n rendezvous ports the kernel reports as free right now (bind to port 0), all held open until every one is chosen
+    so that they are distinct"""
+    import socket
+    socks = []
+    for _ in range(n):
+        s = socket.socket(socket.AF_INET, socket.SOCK_STREAM)
+        s.setsockopt(socket.SOL_SOCKET, socket.SO_REUSEADDR, 1)
+        s.bind(("127.0.0.1", 0))
+        socks.append(s)
+    ports = [s.getsockname()[1] for s in socks]
+    for s in socks:
+        s.close()
+    return ports
+
+
+def _spawn_cases(fn, cases, tmp_path, port_base=None):
+    ports = _free_ports(len(cases))
+    mp.spawn(_run_cases, args=(2, ports, fn.__name__, cases, str(tmp_path)), nprocs=2, join=True)
     return [(case, tmp_path / f"case{i}") for i, case in enumerate(cases)]
 
 
