@@ -247,12 +247,12 @@ typedef struct {
     uint32_t reserved;
 } pqv_timing;
 PQV_API int pqv_last_timing(pqv_ctx *ctx, pqv_timing *out);
-/* what the last pqv_kmeans_assign / pqv_bench_assign did.  path 1 = tcgen05 tf32 filter
+/* what the last pqv_kmeans_assign / pqv_bench_assign did.  path 1 = tcgen05 filter
  * (tensor cores decide every row whose candidate window holds one centroid; the rest are re-evaluated in the
  * reference's exact f32 order), path 0 = exact SIMT kernel for every (row, centroid) pair. */
 typedef struct {
     uint32_t path;            /* 0 = exact SIMT, 1 = tcgen05 filter + exact re-check                        */
-    uint32_t reserved;
+    uint32_t kind;            /* tcgen05 operand: 1 = the rows' fp16 shadow (kind::f16), 0 = f32 rows (kind::tf32) */
     uint64_t rows;
     uint64_t ambiguous_rows;  /* rows with 2..4 candidates after the filter (exact chain over those only)  */
     uint64_t overflow_rows;   /* rows sent to the full exact scan (non-finite norms, > 4 candidates)       */
@@ -260,7 +260,9 @@ typedef struct {
     double filter_ms;         /* the tcgen05 kernel (path 1) or the SIMT kernel (path 0), CUDA events      */
     double recheck_ms;        /* exact re-evaluation kernels (pairs + overflow scan + finalize)            */
     double pair_ms;           /* of which: the (row, candidate) pair kernel                                */
-    double total_ms;
+    double total_ms;          /* prep + filter + recheck                                                   */
+    double shadow_ms;         /* building the rows' 16-bit shadow, when this call had to (resident tables: once
+                                 per table, not per sweep; not part of total_ms)                           */
 } pqv_assign_timing;
 PQV_API int pqv_last_assign_timing(pqv_ctx *ctx, pqv_assign_timing *out);
 /* device-resident loop for roofline timing of the assignment sweep (src/ivf/index.rs:189-206): `iters` sweeps of

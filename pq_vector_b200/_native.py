@@ -22,10 +22,10 @@ class PqvTiming(C.Structure):
 
 
 class PqvAssignTiming(C.Structure):
-    _fields_ = [("path", C.c_uint32), ("reserved", C.c_uint32), ("rows", C.c_uint64),
+    _fields_ = [("path", C.c_uint32), ("kind", C.c_uint32), ("rows", C.c_uint64),
                 ("ambiguous_rows", C.c_uint64), ("overflow_rows", C.c_uint64), ("prep_ms", C.c_double),
                 ("filter_ms", C.c_double), ("recheck_ms", C.c_double), ("pair_ms", C.c_double),
-                ("total_ms", C.c_double)]
+                ("total_ms", C.c_double), ("shadow_ms", C.c_double)]
 
 
 class PqvBatchTiming(C.Structure):

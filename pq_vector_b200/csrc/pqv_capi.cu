@@ -23,6 +23,7 @@
 #include <vector>
 
 #include "pqv_kernels.cuh"
+#include "pqv_half.cuh"
 #include "pqv_peer.cuh"
 #include "pqv_adist.cuh"
 #include "pqv_tie.cuh"
@@ -356,6 +357,13 @@ struct DeviceState {
     DevBuf<float> d_vec, d_tmp_rows, d_centroids, d_dist;
     // tcgen05 assignment filter scratch (pqv_tc_host.cuh)
     DevBuf<float> tc_bp, tc_mu, tc_cn;
+    DevBuf<uint32_t> tc_wc;
+    // 16-bit shadow of rows that do not belong to a resident table (host rows streamed through, the k-means training sample)
+    DevBuf<__half> ts_half;
+    DevBuf<float2> ts_stats;
+    DevBuf<float> ts_mu;
+    DevBuf<pqv::half16::Globals> ts_g;
+    cudaEvent_t ev_shadow[2] = {nullptr, nullptr};
     DevBuf<float2> tc_stats;
     DevBuf<uint2> tc_pairs;
     DevBuf<u64> tc_best;
@@ -464,17 +472,43 @@ struct AppendPool {
     }
 };
 
+// 16-bit operand shadow of a shard (pqv_half.cuh): fp16 copy of the rows, per-row (|x|^2, x.mu), the data mean mu and the
+// table-wide residual bound.  Created on the first tensor-core pass over the shard, extended when rows are appended.
+struct HalfShadow {
+    __half *h = nullptr;
+    float2 *stats = nullptr;
+    float *mu = nullptr;
+    pqv::half16::Globals *g = nullptr;
+    u64 rows = 0, cap = 0;  // rows covered / allocated
+    void drop() {
+        if (h) cudaFree(h);
+        if (stats) cudaFree(stats);
+        if (mu) cudaFree(mu);
+        if (g) cudaFree(g);
+        h = nullptr;
+        stats = nullptr;
+        mu = nullptr;
+        g = nullptr;
+        rows = cap = 0;
+    }
+};
+
 struct Shard {
     int di = 0;  // index into ctx->devs
     float *d_data = nullptr;
     u64 cap_rows = 0, n_rows = 0, first_row = 0;
-    // |x|^2 per row, computed on first use by the batched top-k and kept until the shard changes
+    // |x|^2 per row for the tf32 form of the batched top-k (no shadow), kept until the shard changes
     float2 *d_norms = nullptr;
     u64 norms_rows = 0, norms_cap = 0;
+    HalfShadow shadow;
     void drop_norms() {
         if (d_norms) cudaFree(d_norms);
         d_norms = nullptr;
         norms_rows = norms_cap = 0;
+    }
+    void drop_derived() {
+        drop_norms();
+        shadow.drop();
     }
 };
 
@@ -1004,6 +1038,7 @@ int pqv_init(pqv_ctx **out, const int *device_ids, int n_devices) {
         CU_TRY(cudaStreamCreateWithFlags(&D.stream, cudaStreamNonBlocking));
         CU_TRY(cudaStreamCreateWithFlags(&D.copy_stream, cudaStreamNonBlocking));
         for (auto &ev : D.ev) CU_TRY(cudaEventCreate(&ev));
+        for (auto &ev : D.ev_shadow) CU_TRY(cudaEventCreate(&ev));
         ctx->devs.push_back(D);
     }
     *out = ctx;
@@ -1047,7 +1082,7 @@ void pqv_destroy(pqv_ctx *ctx) {
         for (auto &sh : kv.second.shards) {
             DevGuard guard(ctx->devs[sh.di].dev);
             if (sh.d_data) cudaFree(sh.d_data);
-            sh.drop_norms();
+            sh.drop_derived();
         }
     for (auto &D : ctx->devs) {
         DevGuard guard(D.dev);
@@ -1098,6 +1133,13 @@ void pqv_destroy(pqv_ctx *ctx) {
         D.d_tmp_rows.release();
         D.d_centroids.release();
         D.d_dist.release();
+        D.tc_wc.release();
+        D.ts_half.release();
+        D.ts_stats.release();
+        D.ts_mu.release();
+        D.ts_g.release();
+        for (auto &e : D.ev_shadow)
+            if (e) cudaEventDestroy(e);
         D.tc_bp.release();
         D.tc_mu.release();
         D.tc_cn.release();
@@ -1180,6 +1222,7 @@ static int grow_shard(pqv_ctx *ctx, Dataset &ds, Shard &sh, u64 need_rows) {
     cudaFree(sh.d_data);
     sh.d_data = nd;
     sh.cap_rows = new_cap;
+    sh.shadow.drop();  // sized for the old allocation; rebuilt on the next tensor-core pass
     return PQV_OK;
 }
 
@@ -1303,7 +1346,7 @@ int pqv_dataset_drop(pqv_ctx *ctx, uint64_t handle) {
         DevGuard guard(ctx->devs[sh.di].dev);
         cudaStreamSynchronize(ctx->devs[sh.di].stream);
         if (sh.d_data) cudaFree(sh.d_data);
-        sh.drop_norms();
+        sh.drop_derived();
     }
     ctx->datasets.erase(handle);
     {
@@ -1328,6 +1371,7 @@ int pqv_dataset_fill_synthetic(pqv_ctx *ctx, uint64_t handle, uint64_t n_rows, u
         const u64 take = std::min<u64>(left, sh.cap_rows);
         sh.n_rows = take;
         sh.norms_rows = 0;
+        sh.shadow.rows = 0;  // rows rewritten in place: the 16-bit shadow is rebuilt on the next tensor-core pass
         left -= take;
         ds->n_rows += take;
         if (!take) continue;
@@ -1823,7 +1867,8 @@ static int dist_launch(DeviceState &D, const float *d_data, const uint32_t *d_id
 
 // resolve (handle, rows) to a device pointer for the first `n` rows; streams host rows into scratch
 static int resolve_rows(pqv_ctx *ctx, uint64_t handle, const float *rows, u64 n, uint32_t dim, DeviceState **Dout,
-                        const float **d_rows) {
+                        const float **d_rows, Dataset **ds_out = nullptr) {
+    if (ds_out) *ds_out = nullptr;
     if (rows) {
         DeviceState &D = ctx->devs[0];
         DevGuard guard(D.dev);
@@ -1840,6 +1885,18 @@ static int resolve_rows(pqv_ctx *ctx, uint64_t handle, const float *rows, u64 n,
     if (n > ds->n_rows) return fail(PQV_EINVAL, "n = %llu exceeds the dataset's %llu rows", (unsigned long long)n, (unsigned long long)ds->n_rows);
     *Dout = &ctx->devs[ds->shards[0].di];
     *d_rows = ds->shards[0].d_data;
+    if (ds_out) *ds_out = ds;
+    return PQV_OK;
+}
+
+// the 16-bit shadow of a resident table for an assignment sweep over its first n rows (null view: none -- layout, memory)
+static int sweep_shadow(DeviceState &D, Dataset *ds, const float *d_rows, u64 n, ShadowView *sv, bool *have, bool *built) {
+    *have = false;
+    *built = false;
+    if (!ds || n < 2048 || !shadow_layout_ok(ds->dim, d_rows)) return PQV_OK;  // small sweeps take the SIMT kernel anyway
+    const int rc = shard_shadow(D, *ds, ds->shards[0], sv, built);
+    if (rc == PQV_OK) *have = true;
+    else if (rc != PQV_ENOMEM) return rc;
     return PQV_OK;
 }
 
@@ -1857,21 +1914,26 @@ int pqv_kmeans_assign(pqv_ctx *ctx, uint64_t handle, const float *rows, uint64_t
         const u64 cnt = std::min<u64>(piece, n - off);
         DeviceState *D = nullptr;
         const float *d_rows = nullptr;
-        PQV_TRY(resolve_rows(ctx, handle, rows ? rows + off * dim : nullptr, rows ? cnt : n, dim, &D, &d_rows));
+        Dataset *rds = nullptr;
+        PQV_TRY(resolve_rows(ctx, handle, rows ? rows + off * dim : nullptr, rows ? cnt : n, dim, &D, &d_rows, &rds));
         DevGuard guard(D->dev);
         if (!rows) d_rows += off * dim;
         PQV_TRY(D->d_centroids.ensure((size_t)n_clusters * dim));
         if (off == 0)
             CU_TRY(cudaMemcpyAsync(D->d_centroids.p, centroids, (size_t)n_clusters * dim * 4, cudaMemcpyHostToDevice, D->stream));
         PQV_TRY(D->d_assign.ensure(cnt));
-        int path = 0;
-        PQV_TRY(assign_dispatch(*D, d_rows, cnt, dim, D->d_centroids.p, n_clusters, D->d_assign.p, &path, true));
+        int path = 0, kind = 0;
+        ShadowView sv;
+        bool have_sv = false, built = false, built2 = false;
+        if (!rows) PQV_TRY(sweep_shadow(*D, rds, d_rows, cnt, &sv, &have_sv, &built));
+        PQV_TRY(assign_dispatch(*D, d_rows, cnt, dim, D->d_centroids.p, n_clusters, D->d_assign.p, &path, true,
+                                have_sv ? &sv : nullptr, &kind, &built2));
         uint32_t h_counts[2] = {0, 0};
         if (path == ASSIGN_TC)
-            CU_TRY(cudaMemcpyAsync(h_counts, D->tc_u32.p + 4, sizeof h_counts, cudaMemcpyDeviceToHost, D->stream));
+            CU_TRY(cudaMemcpyAsync(h_counts, D->tc_u32.p + TC_COUNTS_OFFSET, sizeof h_counts, cudaMemcpyDeviceToHost, D->stream));
         CU_TRY(cudaMemcpyAsync(out_assign + off, D->d_assign.p, cnt * 4, cudaMemcpyDeviceToHost, D->stream));
         CU_TRY(cudaStreamSynchronize(D->stream));
-        record_assign_timing(ctx, *D, path, cnt, h_counts, off == 0);
+        record_assign_timing(ctx, *D, path, cnt, h_counts, off == 0, kind, built || built2);
     }
     if (out_sizes)
         for (u64 i = 0; i < n; ++i) out_sizes[out_assign[i]]++;
@@ -1894,7 +1956,8 @@ int pqv_bench_assign(pqv_ctx *ctx, uint64_t handle, uint64_t n, const float *cen
     if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
     DeviceState *D = nullptr;
     const float *d_rows = nullptr;
-    PQV_TRY(resolve_rows(ctx, handle, nullptr, n, ds->dim, &D, &d_rows));
+    Dataset *rds = nullptr;
+    PQV_TRY(resolve_rows(ctx, handle, nullptr, n, ds->dim, &D, &d_rows, &rds));
     DevGuard guard(D->dev);
     const uint32_t dim = ds->dim;
     PQV_TRY(D->d_centroids.ensure((size_t)n_clusters * dim));
@@ -1902,15 +1965,21 @@ int pqv_bench_assign(pqv_ctx *ctx, uint64_t handle, uint64_t n, const float *cen
     CU_TRY(cudaMemcpyAsync(D->d_centroids.p, centroids, (size_t)n_clusters * dim * 4, cudaMemcpyHostToDevice, D->stream));
     pqv_assign_timing acc{};
     for (uint32_t it = 0; it < iters; ++it) {
-        int path = 0;
-        PQV_TRY(assign_dispatch(*D, d_rows, n, dim, D->d_centroids.p, n_clusters, D->d_assign.p, &path, true));
+        int path = 0, kind = 0;
+        ShadowView sv;
+        bool have_sv = false, built = false, built2 = false;
+        PQV_TRY(sweep_shadow(*D, rds, d_rows, n, &sv, &have_sv, &built));  // the table's shadow: built by the first sweep only
+        PQV_TRY(assign_dispatch(*D, d_rows, n, dim, D->d_centroids.p, n_clusters, D->d_assign.p, &path, true,
+                                have_sv ? &sv : nullptr, &kind, &built2));
         uint32_t h_counts[2] = {0, 0};
         if (path == ASSIGN_TC)
-            CU_TRY(cudaMemcpyAsync(h_counts, D->tc_u32.p + 4, sizeof h_counts, cudaMemcpyDeviceToHost, D->stream));
+            CU_TRY(cudaMemcpyAsync(h_counts, D->tc_u32.p + TC_COUNTS_OFFSET, sizeof h_counts, cudaMemcpyDeviceToHost, D->stream));
         CU_TRY(cudaStreamSynchronize(D->stream));
-        record_assign_timing(ctx, *D, path, n, h_counts, true);
+        record_assign_timing(ctx, *D, path, n, h_counts, true, kind, built || built2);
         const pqv_assign_timing &t = ctx->last_assign;
         acc.path = t.path;
+        acc.kind = t.kind;
+        acc.shadow_ms += t.shadow_ms;  // not averaged: the one-time build, if it fell into this call
         acc.rows = t.rows;
         acc.ambiguous_rows = t.ambiguous_rows;
         acc.overflow_rows = t.overflow_rows;

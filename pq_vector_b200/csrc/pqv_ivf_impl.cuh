@@ -152,8 +152,8 @@ int csr_device(DeviceState &D, const uint32_t *d_assign, u64 n, uint32_t C, u64 
 }
 
 int assign_device(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const float *d_centroids, uint32_t C,
-                  uint32_t *d_out) {
-    return assign_dispatch(D, d_rows, n, dim, d_centroids, C, d_out);  // tcgen05 filter or exact SIMT, pqv_tc_host.cuh
+                  uint32_t *d_out, const ShadowView *sv = nullptr) {
+    return assign_dispatch(D, d_rows, n, dim, d_centroids, C, d_out, nullptr, false, sv);  // tcgen05 filter or exact SIMT, pqv_tc_host.cuh
 }
 
 double now_ms() {
@@ -561,6 +561,13 @@ int kmeans_train_device(DeviceState &D, const float *d_sample, u64 ns, uint32_t 
         ce = cudaMemsetAsync(d_asg[0].p, 0, ns * 4, D.stream);  // vec![0usize; n] (index.rs:392)
         if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "Lloyd init failed: %s", cudaGetErrorString(ce));
     }
+    // the 20 sweeps read the same sample: its 16-bit shadow (operand of the tensor-core filter) is built once
+    ShadowView tsv;
+    bool have_tsv = false;
+    if (!rc && shadow_layout_ok(dim, d_sample) && assign_path_for(d_sample, ns, dim, D.d_centroids.p, C) == ASSIGN_TC) {
+        rc = temp_shadow(D, d_sample, ns, dim, &tsv);
+        have_tsv = !rc;
+    }
     int cur = 0;  // d_asg[cur] = assignments of the previous iteration
     std::vector<uint32_t> h_assign;  // host fallback only (cluster count beyond the device list builder)
     std::vector<u64> moff;
@@ -568,7 +575,7 @@ int kmeans_train_device(DeviceState &D, const float *d_sample, u64 ns, uint32_t 
     for (uint32_t iter = 0; iter < max_iters && !rc; ++iter) {
         if (iters_out) *iters_out = iter + 1;
         uint32_t *prev = d_asg[cur].p, *next = d_asg[cur ^ 1].p;
-        rc = assign_device(D, d_sample, ns, dim, D.d_centroids.p, C, next);
+        rc = assign_device(D, d_sample, ns, dim, D.d_centroids.p, C, next, have_tsv ? &tsv : nullptr);
         if (rc) break;
         ce = cudaMemsetAsync(d_changed.p, 0, 8, D.stream);
         if (ce == cudaSuccess) {
@@ -690,7 +697,13 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
     static const bool trace = getenv("PQV_TRACE") != nullptr;
     double tf[4] = {now_ms(), 0, 0, 0};
     IVF_TRY(D.d_assign.ensure(n));
-    IVF_TRY(assign_device(D, sh.d_data, n, dim, D.d_centroids.p, C, D.d_assign.p));
+    {
+        // the table's own shadow: stays with the shard for later sweeps and batched searches
+        ShadowView fsv;
+        bool have_fsv = false, built = false;
+        IVF_TRY(sweep_shadow(D, ds, sh.d_data, n, &fsv, &have_fsv, &built));
+        IVF_TRY(assign_device(D, sh.d_data, n, dim, D.d_centroids.p, C, D.d_assign.p, have_fsv ? &fsv : nullptr));
+    }
     if (trace) {
         cudaStreamSynchronize(D.stream);
         tf[1] = now_ms();

@@ -1,4 +1,4 @@
-// pqv_tc.cuh -- tcgen05 / TMEM / TMA path for the k-means assignment sweeps (sm_100a only).
+// pqv_tc.cuh -- tcgen05 / TMEM / TMA path for the k-means assignment sweeps and the batched top-k (sm_100a only).
 //
 // Reference loops replaced: nearest_centroid + the final assignment  src/ivf/index.rs:244-257, 189-206
 //                           the Lloyd assignment step                 src/ivf/index.rs:395-430
@@ -8,33 +8,43 @@
 // reference's:
 //
 //   s_j := |c_j|^2 - 2 x.(c_j - mu)          differs from |x - c_j|^2 by a per-row constant (|x|^2 - 2 x.mu)
-//   ŝ_j := cn_j - 2 * tf32_mma(x, B'_j)      B'_j = tf32_rn(c_j - mu) precomputed, x truncated by the tensor core
-//   |ŝ_j - s_j| <= E(row) = |x| * W + Z      W, Z from the error model below (Cauchy-Schwarz on the dropped bits)
+//   ŝ_j := cn_j - 2 * mma(x^, B^_j)          B^_j = the rounded (c_j - mu), x^ = the operand the tensor core sees
+//   |ŝ_j - s_j| <= a w_j                      a >= |x|, w_j = 2 (rn_j + (kappa + eps_acc (1 + kappa)) bn_j)   (pqv_half.cuh)
 //   d_ref_j = d_true_j (1 + theta), |theta| <= delta = (dim/4 + 12) 2^-24   (serial f32 chain, all terms >= 0)
 //
-// so the reference argmin lies in  { j : ŝ_j <= min_j ŝ_j + 2E + G },  G >= 2.1 delta max_j d_true_j.  Rows whose
-// set has one element are final; the others (and rows with non-finite norms or a full candidate FIFO) are
+// so the reference argmin lies in  { j : ŝ_j - a w_j <= min_j (ŝ_j + a w_j) + G },  G >= 2.2 delta max_j d_true_j.  Rows
+// whose set has one element are final; the others (and rows with non-finite norms or a full candidate FIFO) are
 // re-evaluated with the exact serial-order f32 chain (pair_exact_kernel / the sliced kmeans_assign_kernel<.., GATHER>).
 //
-// Kernel shape (one persistent CTA per SM, 192 threads):
-//   warp 0   : TMA producer      rows tile 128 x 32 f32 + centroid tile 256 x 32 f32 per stage (SWIZZLE_128B), 4 stages
-//   warp 1   : MMA issuer        tcgen05.mma.cta_group::1.kind::tf32, M=128 N=256 K=8, 4 per stage; owns TMEM alloc
-//   warps 2-5: epilogue          tcgen05.ld 32x32b.x32 of the f32 accumulator (2 x 256 TMEM columns, double buffered),
-//                                running min + candidate FIFO per row, one row per thread
+// Operand kinds (template parameter KIND of the kernels):
+//   KIND_F16   the table's 16-bit shadow (pqv_half.cuh) under tcgen05 kind::f16: 64 columns per 128-byte stage row, half
+//              the L2 -> shared-memory fill per flop and twice the MMA rate of tf32, kappa measured (~2^-12.3)
+//   KIND_TF32  the f32 rows read directly under kind::tf32 (the tensor core truncates them: kappa = 2^-10); used when no
+//              shadow exists (dim % 8 != 0, PQV_TC_KIND=tf32)
+//
+// Kernel shape (persistent, CTA pairs = clusters of two CTAs on the two SMs of a TPC):
+//   warp 0   : TMA producer      own 128-row tile of A + half of the 256-row table tile per stage (SWIZZLE_128B), 6 stages
+//   warp 1   : MMA issuer        tcgen05.mma.cta_group::2, M=256 over both SMs, N=256, 32 bytes of K per instruction
+//   warps 2+ : epilogue          tcgen05.ld 32x32b.x32 of the f32 accumulator (2 x 256 TMEM columns, double buffered);
+//                                SPLIT warps share each TMEM lane quarter and split a tile's columns
 #pragma once
 #include <cuda.h>
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "pqv_half.cuh"
 #include "pqv_kernels.cuh"
 
 namespace pqv {
 namespace tc {
 
+enum { KIND_TF32 = 0, KIND_F16 = 1 };
 constexpr int BM = 128;      // rows per tile (UMMA M)
 constexpr int BN = 256;      // centroids per tile (UMMA N)
-constexpr int BK = 32;       // f32 columns per stage = 128 B = one SWIZZLE_128B atom row
-constexpr int UMMA_K = 8;    // tf32: 32 bytes of K per instruction
+constexpr int BK = 32;       // 4-byte slots per stage row = 128 B = one SWIZZLE_128B atom row
+__host__ __device__ constexpr int bk_elems(int kind) { return kind == KIND_F16 ? 64 : 32; }  // operand columns per stage
+constexpr int UMMA_STEPS = 4;  // MMAs per stage: 32 bytes of K each (8 tf32 / 16 f16 elements)
 constexpr int STAGES = 4;
 constexpr uint32_t A_BYTES = BM * BK * 4;
 constexpr uint32_t B_BYTES = BN * BK * 4;
@@ -46,28 +56,32 @@ constexpr uint32_t TMEM_COLS = 512;  // two accumulator stages of BN f32 columns
 constexpr int tc_threads(int split) { return 64 + 128 * split; }
 constexpr int EPI_WARP0 = 2;
 constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
-// exchange area of the split epilogue (AssignEpi): 18 words per row of the tile, word-major so that a warp's accesses are
-// conflict-free
-constexpr int EXCH_WORDS = 18;
-constexpr uint32_t EXCH_BYTES = EXCH_WORDS * BM * 4;
-constexpr size_t SMEM_BYTES = (size_t)STAGES * STAGE_BYTES + BAR_BYTES + EXCH_BYTES + 1024;  // +1024: manual 1 KB alignment
+// shared memory behind the barriers: the hand-over area of a split epilogue (Epi::EXCH_BYTES) and EPI_TAB_FLOATS floats of
+// per-column constants the epilogue reads for every tile (centroid norms / halved query thresholds), staged once per CTA
+constexpr uint32_t EPI_TAB_FLOATS = 4096;
+constexpr uint32_t EPI_TAB_BYTES = EPI_TAB_FLOATS * 4;
+constexpr size_t smem_bytes_single(uint32_t exch_bytes) {
+    return (size_t)STAGES * STAGE_BYTES + BAR_BYTES + exch_bytes + EPI_TAB_BYTES + 1024;  // +1024: manual 1 KB alignment
+}
 // CTA-pair variant (tcgen05 cta_group::2): UMMA M = 256 over two SMs, each CTA stages its own 128 rows of A and HALF of
 // the B tile (128 table rows), so a stage is 32 KB per CTA instead of 48 KB and six stages fit
 constexpr int STAGES2 = 6;
 constexpr uint32_t B2_BYTES = (BN / 2) * BK * 4;
 constexpr uint32_t STAGE2_BYTES = A_BYTES + B2_BYTES;
 constexpr uint32_t BAR2_BYTES = 8 * (2 * STAGES2 + 4) + 16;
-constexpr size_t SMEM2_BYTES = (size_t)STAGES2 * STAGE2_BYTES + BAR2_BYTES + EXCH_BYTES + 1024;
+constexpr size_t smem_bytes_pair(uint32_t exch_bytes) {
+    return (size_t)STAGES2 * STAGE2_BYTES + BAR2_BYTES + exch_bytes + EPI_TAB_BYTES + 1024;
+}
 constexpr uint32_t NONE = 0xFFFFFFFFu;
-constexpr int FIFO = 8;      // candidate slots per row (unordered; a slot is free once its score left the window)
 
 constexpr uint64_t HINT_EVICT_NORMAL = 0x1000000000000000ull;
 constexpr uint64_t HINT_EVICT_LAST = 0x14F0000000000000ull;
 
-// instruction descriptor (cute::UMMA::InstrDescriptor bit layout): c_format F32 [4,6)=1, a/b_format TF32 [7,10)/[10,13)=2,
-// a/b major K [15],[16]=0, n_dim [17,23)=N>>3, m_dim [24,29)=M>>4
-constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-constexpr uint32_t IDESC_TF32_2CTA = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+// instruction descriptor (cute::UMMA::InstrDescriptor bit layout): c_format F32 [4,6)=1, a/b_format [7,10)/[10,13)
+// (kind::tf32: TF32 = 2; kind::f16: F16 = 0, BF16 = 1), a/b major K [15],[16]=0, n_dim [17,23)=N>>3, m_dim [24,29)=M>>4
+__host__ __device__ constexpr uint32_t idesc_for(int kind, int m) {
+    return (1u << 4) | (kind == KIND_TF32 ? ((2u << 7) | (2u << 10)) : 0u) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -128,13 +142,22 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
-__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+template <int KIND>
+__device__ __forceinline__ void umma_single(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == KIND_TF32)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
 // ---- cta_group::2 (CTA pair) forms
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -176,14 +199,22 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar, uint16_t cta_mask
                  "h"(cta_mask)
                  : "memory");
 }
-__device__ __forceinline__ void umma_tf32_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                               uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+template <int KIND>
+__device__ __forceinline__ void umma_pair(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    if (KIND == KIND_TF32)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
 
 // 32 lanes x 32 consecutive f32 columns: thread t of the warp gets lane (taddr.lane + t), columns [col, col+32)
@@ -204,6 +235,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// the same load without the wait: several can be in flight; tmem_ld_fence() makes their registers readable.  The empty
+// volatile asm per register pins every use behind the wait (volatile asms keep their order, plain arithmetic does not).
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld_fence(uint32_t (&r)[32], float (&v)[32]) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) {
+        asm volatile("" : "+r"(r[i]));
+        v[i] = __uint_as_float(r[i]);
+    }
+}
+
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor bit layout) for a K-major SWIZZLE_128B tile whose rows are
 // 128 B: start address >> 4 in [0,14), LBO [16,30) unused for this layout (0), SBO [32,46) = 8 rows * 128 B = 1024 B >> 4,
 // version [46,48) = 1 (sm_100), base offset 0 (tiles are 1 KB aligned), layout type [61,64) = 2 (SWIZZLE_128B).
@@ -212,19 +266,39 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// preparation kernels (tiny): column mean of the centroid table, centred + tf32-rounded table, norms, bounds
+// preparation kernels (tiny): column mean of the centroid table, centred + rounded table, norms, bounds
 // ------------------------------------------------------------------------------------------------
-// bounds[0] = max_j 2 (eps_mma bn_j + rn_j)   bounds[1] = max_j |c_j|^2   bounds[2] = max_j bn_j   bounds[3] = |mu|^2
-// (f32 bit patterns, >= 0; zeroed by the caller before centroid_mean_kernel)
-__global__ void centroid_mean_kernel(const float *__restrict__ cent, uint32_t C, uint32_t dim, float *__restrict__ mu,
-                                     uint32_t *__restrict__ bounds) {
+// bounds[] (f32 bit patterns, >= 0; zeroed by the caller before centroid_mean_kernel):
+//   [0] max_j w_j   [1] max_j |c_j|^2   [2] max_j bn_j   [3] |mu_d|^2   [4] |mu - mu_d|^2
+//   [5] max |c - mu| over the table (centroid_absmax_kernel), replaced by the table's operand scale (a power of two, f32)
+// mu = column mean of the centroids (the vector the table is centred on); mu_d = the vector the per-row statistic x.mu_d
+// was computed against: the same mu (mu_data == nullptr: row_stats_kernel ran for this sweep) or the table's cached data
+// mean (pqv_half.cuh).  The consumer needs x.mu only inside a bound: x.mu = x.mu_d + x.(mu - mu_d), |x.(mu - mu_d)| <= |x| |mu - mu_d|.
+__global__ void centroid_mean_kernel(const float *__restrict__ cent, uint32_t C, uint32_t dim, const float *__restrict__ mu_data,
+                                     float *__restrict__ mu, uint32_t *__restrict__ bounds) {
     const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= dim) return;
     float s = 0.f;
     for (uint32_t j = 0; j < C; ++j) s += cent[(size_t)j * dim + col];
     const float m = s / (float)C;  // any vector is valid here; the mean just keeps |c - mu| small
     mu[col] = m;
-    atomicAdd(reinterpret_cast<float *>(&bounds[3]), m * m);  // |mu|^2 (order-dependent rounding: only feeds an inflated bound)
+    const float md = mu_data ? mu_data[col] : m;
+    const float dl = m - md;
+    // order-dependent rounding of these sums only feeds inflated bounds
+    atomicAdd(reinterpret_cast<float *>(&bounds[3]), md * md);
+    atomicAdd(reinterpret_cast<float *>(&bounds[4]), dl * dl);
+}
+
+// max |c_j[col] - mu[col]| over the table as f32 bits (atomicMax into *out): picks the fp16 operand scale of the table
+__global__ void __launch_bounds__(256) centroid_absmax_kernel(const float *__restrict__ cent, uint32_t C, uint32_t dim,
+                                                              const float *__restrict__ mu, uint32_t *__restrict__ out) {
+    uint32_t m = 0;
+    const u64 count = (u64)C * dim;
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (u64)gridDim.x * blockDim.x)
+        m = max(m, __float_as_uint(cent[i] - mu[i % dim]) & 0x7FFFFFFFu);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if ((threadIdx.x & 31) == 0 && m) atomicMax(out, m);
 }
 
 __device__ __forceinline__ float tf32_rn(float v) {
@@ -233,12 +307,27 @@ __device__ __forceinline__ float tf32_rn(float v) {
     return __uint_as_float(r);
 }
 
+// accumulation error of the tensor core per unit |x^| |B^|: products of tf32 / f16 operands are exact in f32, the f32
+// accumulation over the K dimension is charged 2^-19 per 8 products (conservative for a non-IEEE adder tree)
+__device__ __forceinline__ double eps_acc(uint32_t dim) { return ((double)(dim / 8 + 4)) * ldexp(1.0, -19); }
+// operand-A residual per unit |x|: the table-wide maximum measured by the shadow pass (inflated by the f32 summation error
+// of its two sums), or 2^-10 for f32 rows truncated to tf32 by the tensor core
+__device__ __forceinline__ double kappa_of(const half16::Globals *g, uint32_t dim) {
+    if (!g) return ldexp(1.0, -10);
+    return (double)__uint_as_float(g->kappa_bits) * (1.0 + 2.0 * (double)(dim + 32) * ldexp(1.0, -24) + 1e-6) + 1e-30;
+}
+
+// B^_j = rounded (c_j - mu) in the operand type of the kernel (tf32-rounded f32, or fp16 with the sub-normal range flushed),
+// cn_j = |c_j|^2, w_j, and wc[j / 32] = max of w over the 32-column chunk of j
+template <int KIND>
 __global__ void __launch_bounds__(128) centroid_prep_kernel(const float *__restrict__ cent, uint32_t C, uint32_t dim,
-                                                            const float *__restrict__ mu, float *__restrict__ Bp,
-                                                            float *__restrict__ cn, float *__restrict__ wv, uint32_t cn_len,
-                                                            uint32_t *__restrict__ bounds) {
+                                                            const float *__restrict__ mu, void *__restrict__ Bp_,
+                                                            float *__restrict__ cn, float *__restrict__ wv,
+                                                            uint32_t *__restrict__ wc, uint32_t cn_len,
+                                                            uint32_t *__restrict__ bounds, const half16::Globals *__restrict__ hg) {
     const uint32_t j = blockIdx.x;
     __shared__ double red[3][4];
+    const float sb = KIND == KIND_F16 ? __uint_as_float(bounds[5]) : 1.f;  // power of two (scale_from_absmax_kernel)
     if (j >= C) {  // padding entries of cn: +inf never passes "ŝ <= thr"
         if (threadIdx.x == 0 && j < cn_len) {
             cn[j] = __int_as_float(0x7f800000);
@@ -250,9 +339,16 @@ __global__ void __launch_bounds__(128) centroid_prep_kernel(const float *__restr
     for (uint32_t col = threadIdx.x; col < dim; col += blockDim.x) {
         const float c = cent[(size_t)j * dim + col];
         const double cp = (double)c - (double)mu[col];
-        const float b = tf32_rn((float)cp);
-        Bp[(size_t)j * dim + col] = b;
-        const double r = cp - (double)b;
+        float b;
+        if (KIND == KIND_F16) {
+            const __half h = half16::to_half_flushed((float)cp * sb);
+            reinterpret_cast<__half *>(Bp_)[(size_t)j * dim + col] = h;
+            b = __half2float(h) / sb;  // exact: sb is a power of two
+        } else {
+            b = tf32_rn((float)cp);
+            reinterpret_cast<float *>(Bp_)[(size_t)j * dim + col] = b;
+        }
+        const double r = cp - (double)b;  // includes the f32 rounding of cp and an overflow to inf (-> non-finite bounds)
         r2 += r * r;
         b2 += (double)b * (double)b;
         c2 += (double)c * (double)c;
@@ -276,20 +372,21 @@ __global__ void __launch_bounds__(128) centroid_prep_kernel(const float *__restr
         c2 = red[2][0] + red[2][1] + red[2][2] + red[2][3];
         const double up = 1.0 + 1e-6;
         const double bn = sqrt(b2) * up, rn = sqrt(r2) * up + 1e-300;
-        // tensor-core error model per unit |x| |B'_j|: operand A truncated to tf32 (2^-10), B' exact in tf32, products exact in
-        // f32, fp32 accumulation over dim/8 instructions (2^-19 each, conservative for a non-IEEE adder tree)
-        const double eps = ldexp(1.0, -10) + ((double)(dim / 8 + 4)) * ldexp(1.0, -19);
+        const double kap = kappa_of(hg, dim);
+        const double eps = kap + eps_acc(dim) * (1.0 + kap);
         const float wj = (float)(2.0 * (eps * bn + rn) * up);
         const float cnj = (float)c2;
         cn[j] = cnj;
         wv[j] = wj;  // |ŝ_j - s_j| <= |x| wv[j] + rounding slack
-        atomicMax(&bounds[0], __float_as_uint(wj));   // non-negative floats (and NaN/inf above them) order as unsigned
+        atomicMax(&wc[j >> 5], __float_as_uint(wj));  // non-negative floats (and NaN/inf above them) order as unsigned
+        atomicMax(&bounds[0], __float_as_uint(wj));
         atomicMax(&bounds[1], __float_as_uint(cnj));
         atomicMax(&bounds[2], __float_as_uint((float)bn));
     }
 }
 
-// per row: (|x|^2, x.mu) in f32 (any order: they only feed the error bounds, inflated by the consumer)
+// per row: (|x|^2, x.mu) in f32 (any order: they only feed the error bounds, inflated by the consumer).  Only the
+// KIND_TF32 path runs this per sweep; with a 16-bit shadow the statistics are part of the shadow (pqv_half.cuh).
 __global__ void __launch_bounds__(256) row_stats_kernel(const float *__restrict__ rows, u64 n, uint32_t dim,
                                                         const float *__restrict__ mu, float2 *__restrict__ stats) {
     const uint32_t lane = threadIdx.x & 31;
@@ -330,10 +427,12 @@ __global__ void __launch_bounds__(256) row_stats_kernel(const float *__restrict_
 // the tensor-core filter
 // ------------------------------------------------------------------------------------------------
 struct AssignTcParams {
-    const float2 *stats;    // [n] (|x|^2, x.mu) per row (row_stats_kernel)
+    const float2 *stats;    // [n] (|x|^2, x.mu_d) per row (shadow pass or row_stats_kernel)
     const float *cn;        // [num_nb * BN] centroid squared norms, +inf padded
     const float *wv;        // [num_nb * BN] per-centroid error weight w_j (0 padded): |ŝ_j - s_j| <= |x| w_j + slack
-    const uint32_t *bounds; // [4] see centroid_prep_kernel
+    const float *wc;        // [num_nb * BN / 32] per 32-column chunk: max_j w_j (chunk pre-test)
+    const uint32_t *bounds; // [8] see centroid_mean_kernel
+    const float *scale_a;   // operand scale of the rows (half16::Globals::scale), nullptr = 1
     uint32_t *assign;       // [n] out: final for rows the filter decides
     uint32_t *counts;       // [0] ambiguous rows, [1] overflow rows, [2] (row, candidate) pairs; zeroed by the caller
     uint32_t *amb_rows;     // [n]
@@ -353,7 +452,7 @@ struct AssignTcParams {
 #define BAR_TEMPTY(a) (bar0 + 8u * (uint32_t)(2 * STAGES + 2 + (a)))
 
 struct GemmShape {
-    uint32_t num_mb, num_nb, num_kb;  // 128-row tiles of A, 256-row tiles of B, 32-column k blocks
+    uint32_t num_mb, num_nb, num_kb;  // 128-row tiles of A, 256-row tiles of B, k blocks of bk_elems(KIND) columns
 };
 
 // what an epilogue warp needs: barrier base, TMEM base, its TMEM lane quarter, the CTA's scratch counter and the CTA's
@@ -366,8 +465,10 @@ struct EpiCtx {
     uint32_t tmem_base, q, lane;
     uint32_t *counter;   // shared memory, zeroed before the roles start
     uint32_t mb0, mb_stride, mb_end;
-    uint32_t h;          // column half this warp drains (0 when the epilogue is not split)
-    uint32_t *exch;      // shared memory, EXCH_WORDS x BM words: hand-over between the two warps of a row (split epilogue)
+    uint32_t h;          // column slice this warp drains (0 .. SPLIT-1)
+    uint32_t *exch;      // shared memory, Epi::EXCH_BYTES: hand-over between the warps of a row (split epilogue)
+    float *tab;          // shared memory, EPI_TAB_FLOATS floats: per-column constants staged by the epilogue warps
+    uint32_t et;         // index of this thread among the epilogue threads (0 .. 128 * SPLIT - 1)
     // wait for accumulator `tile` of this CTA; returns the TMEM address of this warp's 32 lanes x BN columns
     __device__ __forceinline__ uint32_t acquire(uint32_t tile) const {
         const uint32_t as = tile & 1u, aph = (tile >> 1) & 1u;
@@ -381,11 +482,15 @@ struct EpiCtx {
         if (remote) asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
         else mbar_arrive(bar);
     }
+    // all epilogue threads of the CTA (named barrier 9)
+    __device__ __forceinline__ void sync_epilogue(uint32_t nthreads) const {
+        asm volatile("bar.sync 9, %0;" ::"r"(nthreads) : "memory");
+    }
 };
 
-// D[128 x 256 per tile] = A[rows x dim] . B[table x dim]^T in tf32 on the tensor cores, persistent over the row tiles of A;
+// D[128 x 256 per tile] = A[rows x dim] . B[table x dim]^T on the tensor cores, persistent over the row tiles of A;
 // Epi::run consumes every accumulator tile straight from TMEM (nothing of D is ever written to memory as a matrix).
-template <class Epi>
+template <class Epi, int KIND>
 __global__ void __launch_bounds__(tc_threads(Epi::SPLIT), 1)
 tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
                        const typename Epi::Params p) {
@@ -396,6 +501,8 @@ tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t tmem_slot = bar0 + 8u * (2 * STAGES + 4);
     uint32_t *const counter = reinterpret_cast<uint32_t *>(smem_raw + (tmem_slot + 8u - raw));
+    constexpr int BKE = bk_elems(KIND);
+    constexpr uint32_t IDESC = idesc_for(KIND, BM);
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmA);
@@ -431,8 +538,8 @@ tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         mbar_wait(BAR_EMPTY(s), ph ^ 1u);
                         mbar_expect_tx(BAR_FULL(s), STAGE_BYTES);
                         const uint32_t sa = base + s * STAGE_BYTES;
-                        tma_load_2d(sa, &tmA, (int32_t)(kb * BK), (int32_t)(mb * BM), BAR_FULL(s), HINT_EVICT_NORMAL);
-                        tma_load_2d(sa + A_BYTES, &tmB, (int32_t)(kb * BK), (int32_t)(nb * BN), BAR_FULL(s), HINT_EVICT_LAST);
+                        tma_load_2d(sa, &tmA, (int32_t)(kb * BKE), (int32_t)(mb * BM), BAR_FULL(s), HINT_EVICT_NORMAL);
+                        tma_load_2d(sa + A_BYTES, &tmB, (int32_t)(kb * BKE), (int32_t)(nb * BN), BAR_FULL(s), HINT_EVICT_LAST);
                     }
         }
         __syncwarp();
@@ -453,8 +560,8 @@ tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
                         const uint32_t sa = base + s * STAGE_BYTES;
                         const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + A_BYTES);
 #pragma unroll
-                        for (uint32_t k = 0; k < BK / UMMA_K; ++k)  // +32 B of K inside the swizzle atom = +2 in the >>4 address field
-                            umma_tf32(d_tmem, adesc + 2u * k, bdesc + 2u * k, IDESC_TF32, (kb | k) != 0u);
+                        for (uint32_t k = 0; k < UMMA_STEPS; ++k)  // +32 B of K inside the swizzle atom = +2 in the >>4 address field
+                            umma_single<KIND>(d_tmem, adesc + 2u * k, bdesc + 2u * k, IDESC, (kb | k) != 0u);
                         umma_commit(BAR_EMPTY(s));  // frees the smem stage once these MMAs have read it
                     }
                     umma_commit(BAR_TFULL(as));  // accumulator complete
@@ -463,8 +570,10 @@ tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         __syncwarp();
     } else {
         // ===== epilogue warps: one row per thread; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
+        uint8_t *const after_bars = smem_raw + (bar0 + BAR_BYTES - raw);
         Epi::run(EpiCtx{BAR_TFULL(0), BAR_TEMPTY(0), 0u, tmem_base, warp & 3u, lane, counter, blockIdx.x, gridDim.x, g.num_mb,
-                        (warp - 2u) >> 2, reinterpret_cast<uint32_t *>(smem_raw + (bar0 + BAR_BYTES - raw))},
+                        (warp - 2u) >> 2, reinterpret_cast<uint32_t *>(after_bars),
+                        reinterpret_cast<float *>(after_bars + Epi::EXCH_BYTES), threadIdx.x - 64u},
                  g, p);
     }
     // ---- teardown
@@ -487,7 +596,7 @@ tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
 //   empty[s]   in each CTA, count 1: tcgen05.commit multicast to both CTAs when the MMAs that read stage s are done
 //   tfull[a]   in each CTA, count 1: multicast commit when accumulator a is complete (each CTA drains its own TMEM)
 //   tempty[a]  leader only, count 256: the epilogue threads of both CTAs arrive (remote arrive from the peer)
-template <class Epi>
+template <class Epi, int KIND>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc_threads(Epi::SPLIT), 1)
 tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
                             const typename Epi::Params p) {
@@ -501,6 +610,8 @@ tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
     const uint32_t rank = cluster_ctarank();
     const uint32_t pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
     const uint32_t num_mb2 = (g.num_mb + 1u) >> 1;  // 256-row super tiles
+    constexpr int BKE = bk_elems(KIND);
+    constexpr uint32_t IDESC = idesc_for(KIND, 2 * BM);
 #define BAR2_FULL(s) (bar0 + 8u * (uint32_t)(s))
 #define BAR2_EMPTY(s) (bar0 + 8u * (uint32_t)(STAGES2 + (s)))
 #define BAR2_TFULL(a) (bar0 + 8u * (uint32_t)(2 * STAGES2 + (a)))
@@ -543,8 +654,8 @@ tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                         if (rank == 0u) mbar_expect_tx(BAR2_FULL(s), 2u * STAGE2_BYTES);
                         const uint32_t sa = base + s * STAGE2_BYTES;
                         const uint32_t lead_full = lead_bar0 + 8u * s;
-                        tma_load_2d_pair(sa, &tmA, (int32_t)(kb * BK), (int32_t)((mb2 * 2u + rank) * BM), lead_full, HINT_EVICT_NORMAL);
-                        tma_load_2d_pair(sa + A_BYTES, &tmB, (int32_t)(kb * BK), (int32_t)(nb * BN + rank * (BN / 2)), lead_full,
+                        tma_load_2d_pair(sa, &tmA, (int32_t)(kb * BKE), (int32_t)((mb2 * 2u + rank) * BM), lead_full, HINT_EVICT_NORMAL);
+                        tma_load_2d_pair(sa + A_BYTES, &tmB, (int32_t)(kb * BKE), (int32_t)(nb * BN + rank * (BN / 2)), lead_full,
                                          HINT_EVICT_LAST);
                     }
         }
@@ -566,8 +677,8 @@ tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
                         const uint32_t sa = base + s * STAGE2_BYTES;
                         const uint64_t adesc = smem_desc_sw128(sa), bdesc = smem_desc_sw128(sa + A_BYTES);
 #pragma unroll
-                        for (uint32_t k = 0; k < BK / UMMA_K; ++k)
-                            umma_tf32_pair(d_tmem, adesc + 2u * k, bdesc + 2u * k, IDESC_TF32_2CTA, (kb | k) != 0u);
+                        for (uint32_t k = 0; k < UMMA_STEPS; ++k)
+                            umma_pair<KIND>(d_tmem, adesc + 2u * k, bdesc + 2u * k, IDESC, (kb | k) != 0u);
                         umma_commit_pair(BAR2_EMPTY(s), 3);  // frees stage s in both CTAs
                     }
                     umma_commit_pair(BAR2_TFULL(as), 3);  // accumulator complete in both CTAs
@@ -576,9 +687,11 @@ tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         __syncwarp();
     } else {
         // ===== epilogue warps of both CTAs: each drains its own 128 TMEM lanes =====
+        uint8_t *const after_bars = smem_raw + (bar0 + BAR2_BYTES - raw);
         Epi::run(EpiCtx{BAR2_TFULL(0), lead_bar0 + 8u * (uint32_t)(2 * STAGES2 + 2), 1u, tmem_base, warp & 3u, lane, counter,
                         pair * 2u + rank, num_pairs * 2u, num_mb2 * 2u, (warp - 2u) >> 2,
-                        reinterpret_cast<uint32_t *>(smem_raw + (bar0 + BAR2_BYTES - raw))},
+                        reinterpret_cast<uint32_t *>(after_bars), reinterpret_cast<float *>(after_bars + Epi::EXCH_BYTES),
+                        threadIdx.x - 64u},
                  g, p);
     }
     // ---- teardown: nobody leaves (or frees TMEM) while the peer can still signal into this CTA
@@ -596,24 +709,69 @@ tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 #undef BAR2_TEMPTY
 }
 
-// epilogue of the k-means assignment filter (see the header of this file)
+// epilogue of the k-means assignment filter (see the header of this file).
+// Two warps share a row, each scanning half of every tile's columns with its own running minimum and its own candidate
+// list in shared memory (its window is the wider one of its slice, so nothing the full-width scan keeps is lost); after the
+// last tile of the row slice 1 publishes (min, count, overflow flag) and slice 0 finalises over both lists.  The list is
+// append-only -- a few instructions per candidate instead of a search for a stale register slot -- and compacted against
+// the current threshold when its 8 entries are used up (stale entries: columns that were record minima when they passed).
+//
+// Per 32-column chunk the common path is one FFMA and half a three-input minimum per column:
+//     s_j = cn_j - 2 acc_j ,  smin = min_j s_j ,  awc = a * max_{j in chunk} w_j
+//     m  <- min(m, smin + awc)              (an upper bound of min_j s_j^true: s_j^true <= ŝ_j + a w_j <= s_j + awc)
+//     a column can only matter if  s_j - awc <= thr(m)  -- tested once per chunk on smin.  Only chunks that hold such a
+//     column walk their columns, and there the decision uses the column's OWN w_j (one far-out centroid -- an empty
+//     cluster at the origin, src/ivf/index.rs:446-453 -- must not widen the window of its 31 neighbours):
+//     m <- min(m, s_j + a w_j),  candidate iff  s_j - a w_j <= thr(m).
 struct AssignEpi {
     typedef AssignTcParams Params;
-    // two warps per row, each scanning half of every tile's columns with its own running minimum and candidate FIFO (its
-    // window is the wider one of its half, so nothing the full-width scan keeps is lost); after the last tile of the row the
-    // upper half hands (min, overflow flag, FIFO) to the lower half through shared memory, which merges and finalises
     static constexpr int SPLIT = 2;
+    static constexpr int NCH = BN / 32 / SPLIT;      // chunks per warp and tile
+    static constexpr int LIST = 8;                   // candidate entries per row and slice (shared memory, append + compact)
+    static constexpr int ETHREADS = 128 * SPLIT;     // epilogue threads per CTA
+    // shared memory of the epilogue: LIST x ETHREADS entries (score bits, column) + per slice-1 thread (min bits, count | ovf << 31)
+    static constexpr uint32_t LIST_BYTES = LIST * ETHREADS * 8;
+    static constexpr uint32_t EXCH_BYTES = LIST_BYTES + 128 * 8;
     static __device__ __forceinline__ void finish(uint32_t *, const Params &) {}
+
+    // drops the entries whose score has left the window (thr only ever shrinks while a row is scanned); returns the new count
+    static __device__ __noinline__ uint32_t compact(uint2 *mine, uint32_t cnt, float thr) {
+        uint32_t o = 0;
+        for (uint32_t e = 0; e < cnt; ++e) {
+            const uint2 it = mine[e * ETHREADS];
+            if (__uint_as_float(it.x) <= thr) mine[(o++) * ETHREADS] = it;
+        }
+        return o;
+    }
+
     static __device__ void run(const EpiCtx c, const GemmShape g, const Params &p) {
         const uint32_t q = c.q, lane = c.lane;
         const uint32_t row_in_tile = q * 32u + lane;
+        // centroid norms and error weights for every tile of this CTA: staged once in shared memory when the table is short enough
+        const uint32_t cn_len = g.num_nb * BN;
+        const float *cnp = p.cn, *wvp = p.wv;
+        if (2u * cn_len <= EPI_TAB_FLOATS) {
+            for (uint32_t i = c.et; i < cn_len; i += ETHREADS) {
+                c.tab[i] = p.cn[i];
+                c.tab[cn_len + i] = p.wv[i];
+            }
+            c.sync_epilogue(ETHREADS);
+            cnp = c.tab;
+            wvp = c.tab + cn_len;
+        }
+        uint2 *const lists = reinterpret_cast<uint2 *>(c.exch);
+        uint2 *const mine = lists + c.et;                                   // entry e of this thread: mine[e * ETHREADS]
+        uint2 *const meta = lists + LIST * ETHREADS + row_in_tile;          // written by slice 1, read by slice 0 (same row)
         const float wmax = __uint_as_float(p.bounds[0]), cnmax = __uint_as_float(p.bounds[1]);
         const float bnmax = __uint_as_float(p.bounds[2]);
-        const float mun = sqrtf(__uint_as_float(p.bounds[3])) * 1.000001f;
+        // the tensor cores saw (sa x) and (sb B'): -2 / (sa sb) undoes both scales exactly (powers of two)
+        const float neg2u = -2.f / ((p.scale_a ? *p.scale_a : 1.f) * __uint_as_float(p.bounds[5]));
+        const float mun = sqrtf(__uint_as_float(p.bounds[3])) * 1.000001f;      // |mu_d|
+        const float dmu = sqrtf(__uint_as_float(p.bounds[4])) * 1.000001f;      // |mu - mu_d|
         const float delta = (float)(p.dim / 4 + 12) * 5.9604645e-08f;   // 2^-24: reference's serial f32 chain, terms >= 0
-        const float gamma = (float)(p.dim + 32) * 5.9604645e-08f;       // row_stats_kernel's f32 sums
+        const float gamma = (float)(p.dim + 32) * 5.9604645e-08f;       // f32 sums of the row statistics
         const float c2 = 2.2f * delta;
-        const bool table_ok = (cnmax < 1e30f) && (wmax < 1e30f) && (mun < 1e30f);
+        const bool table_ok = (cnmax < 1e30f) && (wmax < 1e30f) && (mun < 1e30f) && (dmu < 1e30f);
         const float inf = __int_as_float(0x7f800000);
         uint32_t tile = 0;
         for (uint32_t mb = c.mb0; mb < c.mb_end; mb += c.mb_stride) {
@@ -622,182 +780,147 @@ struct AssignEpi {
             const float2 st = valid ? p.stats[row] : make_float2(0.f, 0.f);
             const float x2 = st.x * (1.f + gamma) + 1e-37f;
             const float a = sqrtf(x2) * 1.000001f;
-            // per centroid:  L_j = ŝ_j - a w_j <= s_j <= U_j = ŝ_j + a w_j  (up to the rounding slack folded into T2).  With
-            // m = min_j U_j the reference argmin satisfies  L_j <= thr(m) = m + T2 + 2.2 delta max(m + K2, 0):  m + K2 bounds
+            // per column:  L_j = ŝ_j - a w_j <= s_j <= U_j = ŝ_j + a w_j  (up to the rounding slack folded into T2).  With
+            // m >= min_j U_j the reference argmin satisfies  L_j <= thr(m) = m + T2 + 2.2 delta max(m + K2, 0):  m + K2 bounds
             // |x - c_j'|^2 for the j' attaining m, because s_j and d_j differ by exactly |x|^2 - 2 x.mu <= K2.
-            const float na = -a;
-            const float mag = cnmax + 2.f * a * bnmax + a * wmax;                        // bound on |ŝ|, |L|, |U|
-            const float kmag = x2 + 2.f * fabsf(st.y);
-            const float T2 = mag * 9.5367432e-07f + 1e-37f;                              // 2^-20: cn/fma/thr roundings
-            const float K2 = (x2 - 2.f * st.y) + 2.02f * gamma * a * mun + (kmag + mag) * 9.5367432e-07f;
+            const float mag = cnmax + 2.f * a * bnmax + 2.f * a * wmax;                  // bound on |ŝ|, |ŝ -+ a wc|
+            const float kmag = x2 + 2.f * fabsf(st.y) + 2.f * a * dmu;
+            const float T2 = mag * 1.9073486e-06f + 1e-37f;                              // 2^-19: cn / fma / awc / thr roundings
+            const float K2 = (x2 - 2.f * st.y) + 2.f * a * dmu + 2.02f * gamma * a * mun + (kmag + mag) * 9.5367432e-07f;
             float m = inf;
-            float fs[FIFO];
-            uint32_t fi[FIFO];
-#pragma unroll
-            for (int e = 0; e < FIFO; ++e) {
-                fs[e] = inf;
-                fi[e] = NONE;
-            }
+            uint32_t cnt = 0;   // live entries of this thread's list
             bool ovf = false;
             for (uint32_t nb = 0; nb < g.num_nb; ++nb, ++tile) {
                 const uint32_t taddr = c.acquire(tile);
-                const float4 *cn4 = reinterpret_cast<const float4 *>(p.cn + (size_t)nb * BN);
-                const float4 *wv4 = reinterpret_cast<const float4 *>(p.wv + (size_t)nb * BN);
+                const float4 *cn4 = reinterpret_cast<const float4 *>(cnp + (size_t)nb * BN);
+                const float *wv1 = wvp + (size_t)nb * BN;
+                const float *wcp = p.wc + (size_t)nb * (BN / 32);
 #pragma unroll 1
-                for (uint32_t ch = c.h * (BN / 32 / SPLIT); ch < (c.h + 1u) * (BN / 32 / SPLIT); ++ch) {
-                    float v[32], w[32];
+                for (uint32_t ch = c.h * NCH; ch < (c.h + 1u) * NCH; ++ch) {
+                    float v[32];
                     tmem_ld32(taddr + ch * 32u, v);
 #pragma unroll
                     for (int i4 = 0; i4 < 8; ++i4) {
-                        const float4 c = __ldg(cn4 + ch * 8 + i4);
-                        const float4 ww = __ldg(wv4 + ch * 8 + i4);
-                        v[4 * i4 + 0] = __fmaf_rn(-2.f, v[4 * i4 + 0], c.x);
-                        v[4 * i4 + 1] = __fmaf_rn(-2.f, v[4 * i4 + 1], c.y);
-                        v[4 * i4 + 2] = __fmaf_rn(-2.f, v[4 * i4 + 2], c.z);
-                        v[4 * i4 + 3] = __fmaf_rn(-2.f, v[4 * i4 + 3], c.w);
-                        w[4 * i4 + 0] = ww.x;
-                        w[4 * i4 + 1] = ww.y;
-                        w[4 * i4 + 2] = ww.z;
-                        w[4 * i4 + 3] = ww.w;
+                        const float4 cc = cn4[ch * 8 + i4];
+                        v[4 * i4 + 0] = __fmaf_rn(neg2u, v[4 * i4 + 0], cc.x);
+                        v[4 * i4 + 1] = __fmaf_rn(neg2u, v[4 * i4 + 1], cc.y);
+                        v[4 * i4 + 2] = __fmaf_rn(neg2u, v[4 * i4 + 2], cc.z);
+                        v[4 * i4 + 3] = __fmaf_rn(neg2u, v[4 * i4 + 3], cc.w);
                     }
-                    float cm = inf;
+                    float sm[8];
 #pragma unroll
-                    for (int i = 0; i < 32; ++i) cm = fminf(cm, __fmaf_rn(a, w[i], v[i]));   // min U_j
-                    m = fminf(m, cm);
-                    const float thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
-                    bool any = false;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        v[i] = __fmaf_rn(na, w[i], v[i]);                                    // L_j
-                        any |= (v[i] <= thr);
-                    }
-                    if (any) {
+                    for (int i = 0; i < 8; ++i) sm[i] = fminf(fminf(v[4 * i], v[4 * i + 1]), fminf(v[4 * i + 2], v[4 * i + 3]));
+                    const float smin = fminf(fminf(fminf(sm[0], sm[1]), fminf(sm[2], sm[3])), fminf(fminf(sm[4], sm[5]), fminf(sm[6], sm[7])));
+                    const float awc = a * __ldg(wcp + ch);
+                    m = fminf(m, smin + awc);
+                    float thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
+                    const float ts = thr + awc;   // s_j <= ts  <=>  s_j - awc <= thr (rounding of the two forms: inside T2)
+                    if (smin <= ts) {
                         const uint32_t j0 = nb * BN + ch * 32u;
+                        const float *wj = wv1 + ch * 32u;
 #pragma unroll
                         for (int i = 0; i < 32; ++i) {
-                            if (v[i] <= thr) {
-                                bool placed = false;  // take any slot whose lower bound has left the window
-#pragma unroll
-                                for (int e = 0; e < FIFO; ++e) {
-                                    const bool take = !placed && !(fs[e] <= thr);
-                                    fs[e] = take ? v[i] : fs[e];
-                                    fi[e] = take ? j0 + i : fi[e];
-                                    placed |= take;
+                            if (v[i] <= ts) {   // pre-test with the chunk's widest w; the column's own w decides
+                                const float aw = a * wj[i];
+                                m = fminf(m, v[i] + aw);
+                                thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
+                                const float lj = v[i] - aw;
+                                if (lj <= thr) {
+                                    if (cnt == (uint32_t)LIST) cnt = compact(mine, cnt, thr);
+                                    if (cnt < (uint32_t)LIST) mine[(cnt++) * ETHREADS] = make_uint2(__float_as_uint(lj), j0 + (uint32_t)i);
+                                    else ovf = true;
                                 }
-                                ovf |= !placed;
                             }
                         }
                     }
                 }
                 c.release(tile);
             }
-            // ---- hand-over between the two column halves (named barrier 1 + q: the two warps that own TMEM quarter q)
-            if (SPLIT == 2) {
-                uint32_t *ex = c.exch + row_in_tile;
-                if (c.h == 1u) {
-                    ex[0] = __float_as_uint(m);
-                    ex[BM] = ovf ? 1u : 0u;
-#pragma unroll
-                    for (int e = 0; e < FIFO; ++e) {
-                        ex[(2 + e) * BM] = __float_as_uint(fs[e]);
-                        ex[(2 + FIFO + e) * BM] = fi[e];
+            // ---- hand-over between the two column slices (named barrier 1 + q: the two warps that own TMEM quarter q): slice 1
+            // publishes (min, count, overflow); its entries are read in place by slice 0, which finalises the row
+            if (c.h != 0u) *meta = make_uint2(__float_as_uint(m), cnt | (ovf ? 0x80000000u : 0u));
+            asm volatile("bar.sync %0, 64;" ::"r"(1u + q) : "memory");
+            if (c.h == 0u) {
+                const uint2 om = *meta;
+                const uint32_t ocnt = om.y & 0x7FFFFFFFu;
+                const uint2 *const other = lists + (c.et + 128u);   // the same row's thread of slice 1
+                m = fminf(m, __uint_as_float(om.x));
+                ovf |= (om.y >> 31) != 0u;
+                const float thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
+                // pass 1: how many entries of both lists are still inside the final window
+                uint32_t nv = 0, only = NONE;
+                for (uint32_t e = 0; e < cnt; ++e) {
+                    const uint2 it = mine[e * ETHREADS];
+                    if (__uint_as_float(it.x) <= thr) {
+                        ++nv;
+                        only = it.y;
                     }
                 }
-                asm volatile("bar.sync %0, 64;" ::"r"(1u + q) : "memory");
-                float os[FIFO];
-                uint32_t oi[FIFO];
-                if (c.h == 0u) {
-                    m = fminf(m, __uint_as_float(ex[0]));
-                    ovf |= ex[BM] != 0u;
-#pragma unroll
-                    for (int e = 0; e < FIFO; ++e) {
-                        os[e] = __uint_as_float(ex[(2 + e) * BM]);
-                        oi[e] = ex[(2 + FIFO + e) * BM];
+                for (uint32_t e = 0; e < ocnt; ++e) {
+                    const uint2 it = other[e * ETHREADS];
+                    if (__uint_as_float(it.x) <= thr) {
+                        ++nv;
+                        only = it.y;
                     }
                 }
-                asm volatile("bar.sync %0, 64;" ::"r"(1u + q) : "memory");  // the area may be overwritten for the next rows
-                if (c.h == 1u) continue;
-                const float thr_m = m + T2 + c2 * fmaxf(m + K2, 0.f);
+                const bool finite = table_ok && (x2 < 1e30f) && (m < 1e30f) && (m > -1e30f) && (kmag < 1e30f);
+                bool is_ovf = valid && (ovf || !finite || nv == 0u);
+                bool is_amb = valid && !is_ovf && nv > 1u;
+                if (valid && !is_ovf && nv == 1u) p.assign[row] = only;
+                // (row, candidate) pairs of the ambiguous rows: warp-aggregated reservation
+                const uint32_t want = is_amb ? nv : 0u;
+                uint32_t incl = want;
 #pragma unroll
-                for (int i = 0; i < FIFO; ++i) {
-                    if (os[i] <= thr_m) {
-                        bool placed = false;
-#pragma unroll
-                        for (int e = 0; e < FIFO; ++e) {
-                            const bool take = !placed && !(fs[e] <= thr_m);
-                            fs[e] = take ? os[i] : fs[e];
-                            fi[e] = take ? oi[i] : fi[e];
-                            placed |= take;
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+                    if ((int)lane >= o) incl += t;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t pbase = 0;
+                if (total) {
+                    if (lane == 0) pbase = atomicAdd(&p.counts[2], total);
+                    pbase = __shfl_sync(0xffffffffu, pbase, 0);
+                }
+                const bool fits = (u64)pbase + total <= (u64)p.pair_cap;
+                if (is_amb) {
+                    // pass 2: a reservation that does not fit leaves sentinels behind and the row takes the full scan
+                    uint32_t slot = pbase + incl - want;
+                    for (uint32_t e = 0; e < cnt + ocnt; ++e) {
+                        const uint2 it = e < cnt ? mine[e * ETHREADS] : other[(e - cnt) * ETHREADS];
+                        if (__uint_as_float(it.x) <= thr) {
+                            if (slot < p.pair_cap) p.pairs[slot] = fits ? make_uint2((uint32_t)row, it.y) : make_uint2(NONE, NONE);
+                            ++slot;
                         }
-                        ovf |= !placed;
+                    }
+                    if (!fits) {
+                        is_amb = false;
+                        is_ovf = true;
                     }
                 }
-            }
-            // ---- finalize the row
-            const float thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
-            uint32_t nv = 0;
-            uint32_t only = NONE;
-#pragma unroll
-            for (int e = 0; e < FIFO; ++e) {
-                const bool ok = fs[e] <= thr;
-                fi[e] = ok ? fi[e] : NONE;
-                only = ok ? fi[e] : only;
-                nv += ok ? 1u : 0u;
-            }
-            const bool finite = table_ok && (x2 < 1e30f) && (m < 1e30f) && (m > -1e30f) && (kmag < 1e30f);
-            bool is_ovf = valid && (ovf || !finite || nv == 0u);
-            bool is_amb = valid && !is_ovf && nv > 1u;
-            if (valid && !is_ovf && nv == 1u) p.assign[row] = only;
-            // (row, candidate) pairs of the ambiguous rows: warp-aggregated reservation
-            const uint32_t cnt = is_amb ? nv : 0u;
-            uint32_t incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((int)lane >= o) incl += t;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            uint32_t pbase = 0;
-            if (total) {
-                if (lane == 0) pbase = atomicAdd(&p.counts[2], total);
-                pbase = __shfl_sync(0xffffffffu, pbase, 0);
-            }
-            const bool fits = (u64)pbase + total <= (u64)p.pair_cap;
-            if (is_amb) {
-                uint32_t slot = pbase + incl - cnt;
-#pragma unroll
-                for (int e = 0; e < FIFO; ++e)
-                    if (fi[e] != NONE) {
-                        // a reservation that does not fit leaves sentinels behind and the row takes the full scan
-                        if (slot < p.pair_cap) p.pairs[slot] = fits ? make_uint2((uint32_t)row, fi[e]) : make_uint2(NONE, NONE);
-                        ++slot;
-                    }
-                if (!fits) {
-                    is_amb = false;
-                    is_ovf = true;
+                const uint32_t amb_mask = __ballot_sync(0xffffffffu, is_amb);
+                const uint32_t ovf_mask = __ballot_sync(0xffffffffu, is_ovf);
+                uint32_t amb_base = 0, ovf_base = 0;
+                if (lane == 0) {
+                    if (amb_mask) amb_base = atomicAdd(&p.counts[0], (uint32_t)__popc(amb_mask));
+                    if (ovf_mask) ovf_base = atomicAdd(&p.counts[1], (uint32_t)__popc(ovf_mask));
+                }
+                amb_base = __shfl_sync(0xffffffffu, amb_base, 0);
+                ovf_base = __shfl_sync(0xffffffffu, ovf_base, 0);
+                const uint32_t below = (1u << lane) - 1u;
+                if (is_amb) {
+                    p.amb_rows[amb_base + (uint32_t)__popc(amb_mask & below)] = (uint32_t)row;
+                    p.best[row] = KEY_MAX;
+                }
+                if (is_ovf) {
+                    p.ovf_rows[ovf_base + (uint32_t)__popc(ovf_mask & below)] = (uint32_t)row;
+                    p.best[row] = KEY_MAX;
                 }
             }
-            const uint32_t amb_mask = __ballot_sync(0xffffffffu, is_amb);
-            const uint32_t ovf_mask = __ballot_sync(0xffffffffu, is_ovf);
-            uint32_t amb_base = 0, ovf_base = 0;
-            if (lane == 0) {
-                if (amb_mask) amb_base = atomicAdd(&p.counts[0], (uint32_t)__popc(amb_mask));
-                if (ovf_mask) ovf_base = atomicAdd(&p.counts[1], (uint32_t)__popc(ovf_mask));
-            }
-            amb_base = __shfl_sync(0xffffffffu, amb_base, 0);
-            ovf_base = __shfl_sync(0xffffffffu, ovf_base, 0);
-            const uint32_t below = (1u << lane) - 1u;
-            if (is_amb) {
-                p.amb_rows[amb_base + (uint32_t)__popc(amb_mask & below)] = (uint32_t)row;
-                p.best[row] = KEY_MAX;
-            }
-            if (is_ovf) {
-                p.ovf_rows[ovf_base + (uint32_t)__popc(ovf_mask & below)] = (uint32_t)row;
-                p.best[row] = KEY_MAX;
-            }
+            asm volatile("bar.sync %0, 64;" ::"r"(1u + q) : "memory");  // slice 1 may overwrite its list / meta for the next rows
         }
     }
 };
+
 
 
 // ------------------------------------------------------------------------------------------------
@@ -901,13 +1024,16 @@ __global__ void __launch_bounds__(256) best_finalize_kernel(const uint32_t *__re
 enum { BATCH_SAMPLE = 0, BATCH_FILTER = 1 };
 constexpr uint32_t FLAG_NONFINITE_ROW = 1u, FLAG_REGION_FULL = 2u;
 
-// per query: Q' = tf32_rn(q), w_q, q2 = |q|^2 rounded up; qbounds[0] = max_q |Q'_q|
+// per query: Q^ = the rounded query in the operand type of the kernel, w_q, q2 = |q|^2 rounded up; qbounds[0] = max_q |Q^_q|;
+// qwc[j / 32] = max of w over the 32-query chunk of j (zeroed by the caller)
+template <int KIND>
 __global__ void __launch_bounds__(128) query_prep_kernel(const float *__restrict__ Q, uint32_t nq, uint32_t dim,
-                                                         float *__restrict__ Qp, float *__restrict__ qw,
-                                                         float *__restrict__ q2, uint32_t nq_pad,
-                                                         uint32_t *__restrict__ qbounds) {
+                                                         void *__restrict__ Qp_, float *__restrict__ qw,
+                                                         float *__restrict__ q2, uint32_t *__restrict__ qwc, uint32_t nq_pad,
+                                                         uint32_t *__restrict__ qbounds, const half16::Globals *__restrict__ hg) {
     const uint32_t j = blockIdx.x;
     __shared__ double red[3][4];
+    const float sq = KIND == KIND_F16 ? __uint_as_float(qbounds[2]) : 1.f;  // power of two (scale_from_absmax_kernel)
     if (j >= nq) {
         if (threadIdx.x == 0 && j < nq_pad) {
             qw[j] = 0.f;
@@ -918,8 +1044,15 @@ __global__ void __launch_bounds__(128) query_prep_kernel(const float *__restrict
     double r2 = 0.0, b2 = 0.0, c2 = 0.0;
     for (uint32_t col = threadIdx.x; col < dim; col += blockDim.x) {
         const float c = Q[(size_t)j * dim + col];
-        const float b = tf32_rn(c);
-        Qp[(size_t)j * dim + col] = b;
+        float b;
+        if (KIND == KIND_F16) {
+            const __half h = half16::to_half_flushed(c * sq);
+            reinterpret_cast<__half *>(Qp_)[(size_t)j * dim + col] = h;
+            b = __half2float(h) / sq;  // exact: sq is a power of two
+        } else {
+            b = tf32_rn(c);
+            reinterpret_cast<float *>(Qp_)[(size_t)j * dim + col] = b;
+        }
         const double r = (double)c - (double)b;
         r2 += r * r;
         b2 += (double)b * (double)b;
@@ -944,9 +1077,12 @@ __global__ void __launch_bounds__(128) query_prep_kernel(const float *__restrict
         c2 = red[2][0] + red[2][1] + red[2][2] + red[2][3];
         const double up = 1.0 + 1e-6;
         const double bn = sqrt(b2) * up, rn = sqrt(r2) * up + 1e-300;
-        const double eps = ldexp(1.0, -10) + ((double)(dim / 8 + 4)) * ldexp(1.0, -19);  // as centroid_prep_kernel
-        qw[j] = (float)(2.0 * (eps * bn + rn) * up);
+        const double kap = kappa_of(hg, dim);
+        const double eps = kap + eps_acc(dim) * (1.0 + kap);  // as centroid_prep_kernel
+        const float wj = (float)(2.0 * (eps * bn + rn) * up);
+        qw[j] = wj;
         q2[j] = (float)(c2 * up);
+        atomicMax(&qwc[j >> 5], __float_as_uint(wj));
         atomicMax(&qbounds[0], __float_as_uint((float)bn));
     }
 }
@@ -955,7 +1091,9 @@ struct BatchParams {
     const float2 *stats;     // [n] (.x = |x|^2 in f32, row_stats_kernel)
     const float *qw;         // [nq_pad] w_q, 0 padded
     const float *qtheta;     // [nq_pad] theta_q (-inf padded)                       BATCH_FILTER
-    const uint32_t *qbounds; // [0] = max_q |Q'_q| (f32 bits)
+    const float *qwc;        // [nq_pad / 32] per 32-query chunk: max_q w_q             BATCH_FILTER (chunk pre-test)
+    const uint32_t *qbounds; // [0] = max_q |Q^_q| (f32 bits), [2] = operand scale of the queries (a power of two, f32)
+    const float *scale_a;    // operand scale of the rows (half16::Globals::scale), nullptr = 1
     float *U;                // [nq_pad][ldU] upper bounds of s over the sample rows   BATCH_SAMPLE
     uint32_t ldU;
     uint2 *cand;             // [gridDim.x][region_cap] (row, query)                   BATCH_FILTER
@@ -976,14 +1114,25 @@ template <int MODE>
 struct BatchEpi {
     typedef BatchParams Params;
     static constexpr int SPLIT = 2;  // every (row, query) pair is independent: the two warps of a row just split the columns
+    static constexpr uint32_t EXCH_BYTES = 0;
     static __device__ __forceinline__ void finish(uint32_t *counter, const Params &p) {
         if (MODE == BATCH_FILTER) p.region_count[blockIdx.x] = min(*counter, p.region_cap);
     }
     static __device__ void run(const EpiCtx c, const GemmShape g, const Params &p) {
         const uint32_t lane = c.lane;
         const uint32_t row_in_tile = c.q * 32u + lane;
+        // FILTER: theta_q / 2 for every query column, staged once per CTA (halving is exact; -inf padding stays -inf)
+        const uint32_t nq_pad = g.num_nb * BN;
+        const bool th_smem = (MODE == BATCH_FILTER) && nq_pad <= EPI_TAB_FLOATS;
+        if (th_smem) {
+            for (uint32_t i = c.et; i < nq_pad; i += 128u * SPLIT) c.tab[i] = 0.5f * p.qtheta[i];
+            c.sync_epilogue(128u * SPLIT);
+        }
         const float bnmax = __uint_as_float(p.qbounds[0]);
-        const float gamma = (float)(p.dim + 32) * 5.9604645e-08f;  // f32 summation error of row_stats_kernel
+        // the tensor cores saw (sa x) and (sq q): u undoes both scales exactly (powers of two)
+        const float u1 = 1.f / ((p.scale_a ? *p.scale_a : 1.f) * __uint_as_float(p.qbounds[2]));
+        const float neg2u = -2.f * u1;
+        const float gamma = (float)(p.dim + 32) * 5.9604645e-08f;  // f32 summation error of the row statistics
         uint2 *const region = (MODE == BATCH_FILTER) ? p.cand + (size_t)blockIdx.x * p.region_cap : nullptr;
         uint32_t tile = 0;
         for (uint32_t mb = c.mb0; mb < c.mb_end; mb += c.mb_stride) {
@@ -995,6 +1144,7 @@ struct BatchEpi {
             const float a = sqrtf(x2hi) * 1.000001f;
             const float rho = 1.5f * gamma * x2hi + (x2hi + 2.f * a * bnmax) * 9.5367432e-07f + 1e-37f;
             const float x2s = (MODE == BATCH_SAMPLE) ? x2c + rho : x2c - rho;
+            const float hslack = (x2hi + 2.f * a * bnmax) * 9.5367432e-07f + 1e-37f;  // roundings of the exact test and of the pre-test
             // IVF mask: the probe words of this row's cluster (one word per 32 queries)
             const uint32_t *probe_row = nullptr;
             bool dead = false;  // filtered out for every query
@@ -1020,23 +1170,43 @@ struct BatchEpi {
                             const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                float u = __fmaf_rn(a, wv[e], __fmaf_rn(-2.f, v[4 * i4 + e], x2s));
+                                float u = __fmaf_rn(a, wv[e], __fmaf_rn(neg2u, v[4 * i4 + e], x2s));
                                 if (!((pm >> (4 * i4 + e)) & 1u)) u = 3.0e38f;  // not probed by this query: never among its k smallest
                                 if (valid) p.U[(size_t)(q0 + 4 * i4 + e) * p.ldU + row] = u;  // lanes = consecutive rows: coalesced
                             }
                         }
                     } else {
+                        // chunk pre-test: a pair hits iff  -2 v + x2s <= a w_q + theta_q  <=>  v + theta_q / 2 >= (x2s - a w_q) / 2;
+                        // with wcq >= w_q of the chunk and the roundings of both forms inside hslack, the maximum of
+                        // v + theta/2 over the chunk decides whether ANY pair of it can hit (one FADD + half a maximum per pair)
+                        bool maybe = valid && !dead;
+                        if (th_smem) {
+                            const float4 *h4 = reinterpret_cast<const float4 *>(c.tab + q0);
+                            float tm[8];
+#pragma unroll
+                            for (int i4 = 0; i4 < 8; ++i4) {
+                                const float4 hh = h4[i4];
+                                tm[i4] = fmaxf(fmaxf(__fmaf_rn(u1, v[4 * i4 + 0], hh.x), __fmaf_rn(u1, v[4 * i4 + 1], hh.y)),
+                                               fmaxf(__fmaf_rn(u1, v[4 * i4 + 2], hh.z), __fmaf_rn(u1, v[4 * i4 + 3], hh.w)));
+                            }
+                            const float tmax = fmaxf(fmaxf(fmaxf(tm[0], tm[1]), fmaxf(tm[2], tm[3])), fmaxf(fmaxf(tm[4], tm[5]), fmaxf(tm[6], tm[7])));
+                            const float awq = a * __ldg(p.qwc + (q0 >> 5));
+                            const float hcut = 0.5f * (x2s - awq) - hslack;
+                            maybe = maybe && !(tmax < hcut);   // NaN (non-finite rows are flagged separately) falls through to the exact test
+                        }
                         uint32_t mask = 0;
+                        if (maybe) {
 #pragma unroll
-                        for (int i4 = 0; i4 < 8; ++i4) {
-                            const float4 ww = __ldg(w4 + ch * 8 + i4);
-                            const float4 tt = __ldg(t4 + ch * 8 + i4);
-                            const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
-                            const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
+                            for (int i4 = 0; i4 < 8; ++i4) {
+                                const float4 ww = __ldg(w4 + ch * 8 + i4);
+                                const float4 tt = __ldg(t4 + ch * 8 + i4);
+                                const float wv[4] = {ww.x, ww.y, ww.z, ww.w};
+                                const float tv[4] = {tt.x, tt.y, tt.z, tt.w};
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const bool hit = __fmaf_rn(-2.f, v[4 * i4 + e], x2s) <= __fmaf_rn(a, wv[e], tv[e]);
-                                mask |= hit ? (1u << (4 * i4 + e)) : 0u;
+                                for (int e = 0; e < 4; ++e) {
+                                    const bool hit = __fmaf_rn(neg2u, v[4 * i4 + e], x2s) <= __fmaf_rn(a, wv[e], tv[e]);
+                                    mask |= hit ? (1u << (4 * i4 + e)) : 0u;
+                                }
                             }
                         }
                         if (!valid) mask = 0;

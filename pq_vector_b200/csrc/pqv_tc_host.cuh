@@ -24,20 +24,120 @@ PFN_tmapEncodeTiled tmap_encoder() {
     return fn;
 }
 
-// row-major [rows][dim] f32 table viewed as a 2-D tensor {dim (inner), rows}; box = 32 columns x box_rows rows, 128 B swizzle;
-// out-of-bounds elements (row tail, dim % 32 tail) are filled with zeros and still count towards the transaction bytes
-int make_row_tmap(CUtensorMap *tm, const float *d_ptr, u64 rows, uint32_t dim, uint32_t box_rows) {
+// row-major [rows][dim] table (f32, or its fp16 shadow) viewed as a 2-D tensor {dim (inner), rows}; box = one 128-byte
+// stage row (32 f32 / 64 f16 columns) x box_rows rows, 128 B swizzle; out-of-bounds elements (row tail, dim tail) are
+// filled with zeros and still count towards the transaction bytes
+int make_row_tmap(CUtensorMap *tm, const void *d_ptr, u64 rows, uint32_t dim, uint32_t box_rows, int kind) {
     PFN_tmapEncodeTiled enc = tmap_encoder();
     if (!enc) return fail(PQV_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    const bool f16 = kind == pqv::tc::KIND_F16;
     cuuint64_t gdim[2] = {dim, rows};
-    cuuint64_t gstride[1] = {(cuuint64_t)dim * 4};
-    cuuint32_t box[2] = {(cuuint32_t)pqv::tc::BK, box_rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)dim * (f16 ? 2 : 4)};
+    cuuint32_t box[2] = {(cuuint32_t)pqv::tc::bk_elems(kind), box_rows};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(d_ptr), gdim, gstride, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+    CUresult r = enc(tm, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(d_ptr), gdim,
+                     gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(PQV_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu dim=%u)", (int)r,
-                                       (unsigned long long)rows, dim);
+    if (r != CUDA_SUCCESS) return fail(PQV_ECUDA, "cuTensorMapEncodeTiled failed with CUresult %d (rows=%llu dim=%u kind=%d)", (int)r,
+                                       (unsigned long long)rows, dim, kind);
+    return PQV_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// 16-bit operand shadow (pqv_half.cuh)
+// ------------------------------------------------------------------------------------------------
+struct ShadowView {
+    const __half *h = nullptr;
+    const float2 *stats = nullptr;
+    const float *mu = nullptr;
+    const pqv::half16::Globals *g = nullptr;
+};
+
+// PQV_TC_KIND=tf32 keeps the tensor-core filters on the f32 rows (kind::tf32); default: the fp16 shadow wherever the layout
+// allows it (dim % 8 == 0: 16-byte aligned rows of halves for TMA)
+bool half_kind_enabled() {  // read on every call: tests and benchmarks switch kinds inside one process
+    const char *e = getenv("PQV_TC_KIND");
+    return !(e && !strcmp(e, "tf32"));
+}
+bool shadow_layout_ok(uint32_t dim, const void *d_rows) {
+    return half_kind_enabled() && (dim % 8 == 0) && dim >= 64 && ((reinterpret_cast<uintptr_t>(d_rows) & 15) == 0);
+}
+
+constexpr u64 SHADOW_MEAN_ROWS = 65536;  // rows the data mean is taken over
+
+// zeroes the shadow's globals and derives the data mean and the operand scale from the first rows of the table
+int shadow_begin(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, float *mu, pqv::half16::Globals *g) {
+    const u64 ns = std::min<u64>(n, SHADOW_MEAN_ROWS);
+    CU_TRY(cudaMemsetAsync(g, 0, sizeof(pqv::half16::Globals), D.stream));
+    pqv::half16::column_mean_kernel<<<(dim + 127) / 128, 128, 0, D.stream>>>(d_rows, ns, dim, mu);
+    // absmax of the sample lands (as bits) in the `reserved-for-scale` word, then becomes the power-of-two scale in place
+    uint32_t *word = reinterpret_cast<uint32_t *>(&g->scale);
+    pqv::half16::absmax_kernel<<<(uint32_t)D.sm_count * 4, 256, 0, D.stream>>>(d_rows, ns * dim, word);
+    pqv::half16::scale_from_absmax_kernel<<<1, 32, 0, D.stream>>>(word, &g->scale);
+    CU_TRY(cudaGetLastError());
+    return PQV_OK;
+}
+
+int shadow_launch(DeviceState &D, const float *d_rows, u64 first, u64 n, uint32_t dim, const float *mu, __half *h, float2 *stats,
+                  pqv::half16::Globals *g) {
+    if (n == 0) return PQV_OK;
+    pqv::half16::shadow_rows_kernel<<<(uint32_t)D.sm_count * 8, 256, 0, D.stream>>>(d_rows, first, n, dim, mu, h, stats, g);
+    CU_TRY(cudaGetLastError());
+    return PQV_OK;
+}
+
+// the shadow of a resident shard, created / extended on demand (enqueued on D.stream); *ms_out += its build time when one ran
+int shard_shadow(DeviceState &D, const Dataset &ds, Shard &sh, ShadowView *out, bool *built = nullptr) {
+    HalfShadow &S = sh.shadow;
+    const u64 n = sh.n_rows;
+    const uint32_t dim = ds.dim;
+    if (built) *built = false;
+    if (S.cap < n || !S.h) {
+        CU_TRY(cudaStreamSynchronize(D.stream));
+        S.drop();
+        const u64 cap = std::max<u64>(n, sh.cap_rows);
+        cudaError_t e = cudaMalloc((void **)&S.h, (size_t)cap * dim * sizeof(__half));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&S.stats, (size_t)cap * sizeof(float2));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&S.mu, (size_t)dim * sizeof(float));
+        if (e == cudaSuccess) e = cudaMalloc((void **)&S.g, sizeof(pqv::half16::Globals));
+        if (e != cudaSuccess) {
+            S.drop();
+            cudaGetLastError();
+            return fail(PQV_ENOMEM, "16-bit shadow of %llu x %u rows (%.2f GB): %s", (unsigned long long)cap, dim,
+                        cap * (double)dim * 2 / 1e9, cudaGetErrorString(e));
+        }
+        S.cap = cap;
+        S.rows = 0;
+    }
+    if (S.rows == 0 && n) PQV_TRY(shadow_begin(D, sh.d_data, n, dim, S.mu, S.g));
+    if (S.rows < n) {
+        CU_TRY(cudaEventRecord(D.ev_shadow[0], D.stream));
+        PQV_TRY(shadow_launch(D, sh.d_data, S.rows, n - S.rows, dim, S.mu, S.h, S.stats, S.g));
+        CU_TRY(cudaEventRecord(D.ev_shadow[1], D.stream));
+        S.rows = n;
+        if (built) *built = true;
+    }
+    out->h = S.h;
+    out->stats = S.stats;
+    out->mu = S.mu;
+    out->g = S.g;
+    return PQV_OK;
+}
+
+// shadow of n rows at d_rows that are not a resident shard (scratch of the device state; valid until the next call)
+int temp_shadow(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, ShadowView *out) {
+    PQV_TRY(D.ts_half.ensure((size_t)n * dim));
+    PQV_TRY(D.ts_stats.ensure(n));
+    PQV_TRY(D.ts_mu.ensure(dim));
+    PQV_TRY(D.ts_g.ensure(1));
+    PQV_TRY(shadow_begin(D, d_rows, n, dim, D.ts_mu.p, D.ts_g.p));
+    CU_TRY(cudaEventRecord(D.ev_shadow[0], D.stream));
+    PQV_TRY(shadow_launch(D, d_rows, 0, n, dim, D.ts_mu.p, D.ts_half.p, D.ts_stats.p, D.ts_g.p));
+    CU_TRY(cudaEventRecord(D.ev_shadow[1], D.stream));
+    out->h = D.ts_half.p;
+    out->stats = D.ts_stats.p;
+    out->mu = D.ts_mu.p;
+    out->g = D.ts_g.p;
     return PQV_OK;
 }
 
@@ -92,54 +192,90 @@ int assign_simt(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const 
     return PQV_OK;
 }
 
-int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const float *d_cent, uint32_t C, uint32_t *d_out,
-              bool time_it) {
+// one launcher for every (epilogue, operand kind, single / pair) instance: raises the kernel's dynamic shared-memory limit
+// once, then launches
+template <class Epi, int KIND, bool PAIR>
+int tc_launch_inst(uint32_t grid, cudaStream_t st, const CUtensorMap &tmA, const CUtensorMap &tmB, const pqv::tc::GemmShape &shape,
+                   const typename Epi::Params &p) {
     namespace T = pqv::tc;
+    constexpr size_t smem = PAIR ? T::smem_bytes_pair(Epi::EXCH_BYTES) : T::smem_bytes_single(Epi::EXCH_BYTES);
+    static_assert(smem <= 227 * 1024, "tensor-core kernel exceeds the shared memory of an SM");
+    static std::once_flag once;
+    static cudaError_t attr_err = cudaSuccess;
+    std::call_once(once, [] {
+        if (PAIR) attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_pair_kernel<Epi, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        else attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_kernel<Epi, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    });
+    CU_TRY(attr_err);
+    if (PAIR) T::tc_rows_x_table_pair_kernel<Epi, KIND><<<grid, T::tc_threads(Epi::SPLIT), smem, st>>>(tmA, tmB, shape, p);
+    else T::tc_rows_x_table_kernel<Epi, KIND><<<grid, T::tc_threads(Epi::SPLIT), smem, st>>>(tmA, tmB, shape, p);
+    CU_TRY(cudaGetLastError());
+    return PQV_OK;
+}
+template <class Epi>
+int tc_launch(bool pair, int kind, uint32_t grid, cudaStream_t st, const CUtensorMap &tmA, const CUtensorMap &tmB,
+              const pqv::tc::GemmShape &shape, const typename Epi::Params &p) {
+    namespace T = pqv::tc;
+    if (kind == T::KIND_F16)
+        return pair ? tc_launch_inst<Epi, T::KIND_F16, true>(grid, st, tmA, tmB, shape, p)
+                    : tc_launch_inst<Epi, T::KIND_F16, false>(grid, st, tmA, tmB, shape, p);
+    return pair ? tc_launch_inst<Epi, T::KIND_TF32, true>(grid, st, tmA, tmB, shape, p)
+                : tc_launch_inst<Epi, T::KIND_TF32, false>(grid, st, tmA, tmB, shape, p);
+}
+
+// sv != nullptr: the rows' 16-bit shadow (kind::f16 filter, statistics from the shadow pass); nullptr: f32 rows under
+// kind::tf32 with the per-sweep row_stats_kernel pass
+int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const float *d_cent, uint32_t C, uint32_t *d_out,
+              bool time_it, const ShadowView *sv) {
+    namespace T = pqv::tc;
+    const int kind = sv ? T::KIND_F16 : T::KIND_TF32;
+    const uint32_t bke = (uint32_t)T::bk_elems(kind);
     const uint32_t num_mb = (uint32_t)((n + T::BM - 1) / T::BM);
     const uint32_t num_nb = (C + T::BN - 1) / T::BN;
-    const uint32_t num_kb = (dim + T::BK - 1) / T::BK;
+    const uint32_t num_kb = (dim + bke - 1) / bke;
     const uint32_t cn_len = num_nb * T::BN;
     const u64 pair_cap64 = std::min<u64>(4 * n + 1024, 0xFFFFFFF0ull);
-    PQV_TRY(D.tc_bp.ensure((size_t)C * dim));
+    PQV_TRY(D.tc_bp.ensure((size_t)C * dim));  // f32-sized: holds the tf32-rounded table or its fp16 form
     PQV_TRY(D.tc_mu.ensure(dim));
     PQV_TRY(D.tc_cn.ensure(2 * (size_t)cn_len));
-    PQV_TRY(D.tc_stats.ensure(n));
-    PQV_TRY(D.tc_u32.ensure(8));
+    PQV_TRY(D.tc_wc.ensure(cn_len / 32));
+    if (!sv) PQV_TRY(D.tc_stats.ensure(n));
+    PQV_TRY(D.tc_u32.ensure(16));
     PQV_TRY(D.tc_amb_rows.ensure(n));
     PQV_TRY(D.tc_pairs.ensure(pair_cap64));
     PQV_TRY(D.tc_best.ensure(n));
     PQV_TRY(D.tc_ovf_rows.ensure(n));
-    uint32_t *bounds = D.tc_u32.p, *counts = D.tc_u32.p + 4;
-
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_kernel<T::AssignEpi>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)T::SMEM_BYTES);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_pair_kernel<T::AssignEpi>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM2_BYTES);
-    });
-    CU_TRY(attr_err);
+    uint32_t *bounds = D.tc_u32.p, *counts = D.tc_u32.p + 8;
 
     const TcGrid tg = tc_grid_for(D, num_mb);
     CUtensorMap tmA, tmB;
-    PQV_TRY(make_row_tmap(&tmA, d_rows, n, dim, T::BM));
-    PQV_TRY(make_row_tmap(&tmB, D.tc_bp.p, C, dim, tg.pair ? T::BN / 2 : T::BN));
+    PQV_TRY(make_row_tmap(&tmA, sv ? (const void *)sv->h : (const void *)d_rows, n, dim, T::BM, kind));
+    PQV_TRY(make_row_tmap(&tmB, D.tc_bp.p, C, dim, tg.pair ? T::BN / 2 : T::BN, kind));
 
     if (time_it) CU_TRY(cudaEventRecord(D.ev[0], D.stream));
-    CU_TRY(cudaMemsetAsync(D.tc_u32.p, 0, 8 * sizeof(uint32_t), D.stream));
-    T::centroid_mean_kernel<<<(dim + 127) / 128, 128, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, bounds);
-    T::centroid_prep_kernel<<<cn_len, 128, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, D.tc_bp.p, D.tc_cn.p, D.tc_cn.p + cn_len,
-                                                              cn_len, bounds);
-    T::row_stats_kernel<<<(uint32_t)D.sm_count * 8, 256, 0, D.stream>>>(d_rows, n, dim, D.tc_mu.p, D.tc_stats.p);
+    CU_TRY(cudaMemsetAsync(D.tc_u32.p, 0, 16 * sizeof(uint32_t), D.stream));
+    CU_TRY(cudaMemsetAsync(D.tc_wc.p, 0, (size_t)(cn_len / 32) * sizeof(uint32_t), D.stream));
+    T::centroid_mean_kernel<<<(dim + 127) / 128, 128, 0, D.stream>>>(d_cent, C, dim, sv ? sv->mu : nullptr, D.tc_mu.p, bounds);
+    // operand scale of the centred table: bounds[5] = max |c - mu| (fp16 only), then the power of two derived from it (1 for tf32)
+    if (sv) T::centroid_absmax_kernel<<<(uint32_t)D.sm_count, 256, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, bounds + 5);
+    pqv::half16::scale_from_absmax_kernel<<<1, 32, 0, D.stream>>>(bounds + 5, reinterpret_cast<float *>(bounds + 5));
+    if (sv) {
+        T::centroid_prep_kernel<T::KIND_F16><<<cn_len, 128, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, D.tc_bp.p, D.tc_cn.p,
+                                                                          D.tc_cn.p + cn_len, D.tc_wc.p, cn_len, bounds, sv->g);
+    } else {
+        T::centroid_prep_kernel<T::KIND_TF32><<<cn_len, 128, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, D.tc_bp.p, D.tc_cn.p,
+                                                                           D.tc_cn.p + cn_len, D.tc_wc.p, cn_len, bounds, nullptr);
+        T::row_stats_kernel<<<(uint32_t)D.sm_count * 8, 256, 0, D.stream>>>(d_rows, n, dim, D.tc_mu.p, D.tc_stats.p);
+    }
     CU_TRY(cudaGetLastError());
 
     T::AssignTcParams p;
-    p.stats = D.tc_stats.p;
+    p.stats = sv ? sv->stats : D.tc_stats.p;
     p.cn = D.tc_cn.p;
     p.wv = D.tc_cn.p + cn_len;
+    p.wc = reinterpret_cast<const float *>(D.tc_wc.p);
     p.bounds = bounds;
+    p.scale_a = sv ? &sv->g->scale : nullptr;
     p.assign = d_out;
     p.counts = counts;
     p.amb_rows = D.tc_amb_rows.p;
@@ -152,9 +288,7 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     p.C = C;
     const T::GemmShape shape{num_mb, num_nb, num_kb};
     if (time_it) CU_TRY(cudaEventRecord(D.ev[1], D.stream));
-    if (tg.pair) T::tc_rows_x_table_pair_kernel<T::AssignEpi><<<tg.grid, T::tc_threads(T::AssignEpi::SPLIT), T::SMEM2_BYTES, D.stream>>>(tmA, tmB, shape, p);
-    else T::tc_rows_x_table_kernel<T::AssignEpi><<<tg.grid, T::tc_threads(T::AssignEpi::SPLIT), T::SMEM_BYTES, D.stream>>>(tmA, tmB, shape, p);
-    CU_TRY(cudaGetLastError());
+    PQV_TRY(tc_launch<T::AssignEpi>(tg.pair, kind, tg.grid, D.stream, tmA, tmB, shape, p));
     if (time_it) CU_TRY(cudaEventRecord(D.ev[2], D.stream));
     // exact f32 chains: one per (row, candidate) pair of the ambiguous rows; the full scan for the overflow rows
     T::pair_exact_kernel<<<(uint32_t)D.sm_count * 4, T::PAIR_WARPS * 32, 0, D.stream>>>(d_rows, dim, d_cent, counts, p.pair_cap,
@@ -173,12 +307,30 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     return PQV_OK;
 }
 
+// device offset of the (ambiguous, overflow) row counters inside D.tc_u32 after an assign_tc launch
+constexpr size_t TC_COUNTS_OFFSET = 8;
+
 // Enqueues the assignment of n device rows on D.stream (no synchronisation).  *path_out reports the path taken.
+// sv: the 16-bit shadow of exactly these rows if the caller has one (a resident shard's, or one it built for rows it
+// sweeps repeatedly); otherwise a scratch shadow is built here when the layout allows it (one extra pass over the rows).
 int assign_dispatch(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const float *d_cent, uint32_t C, uint32_t *d_out,
-                    int *path_out = nullptr, bool time_it = false) {
+                    int *path_out = nullptr, bool time_it = false, const ShadowView *sv = nullptr, int *kind_out = nullptr,
+                    bool *shadow_built = nullptr) {
     const int path = assign_path_for(d_rows, n, dim, d_cent, C);
     if (path_out) *path_out = path;
-    if (path == ASSIGN_TC) return assign_tc(D, d_rows, n, dim, d_cent, C, d_out, time_it);
+    if (kind_out) *kind_out = 0;
+    if (shadow_built) *shadow_built = false;
+    if (path == ASSIGN_TC) {
+        ShadowView tmp;
+        if (!sv && shadow_layout_ok(dim, d_rows)) {
+            PQV_TRY(temp_shadow(D, d_rows, n, dim, &tmp));
+            sv = &tmp;
+            if (shadow_built) *shadow_built = true;
+        }
+        if (sv && !shadow_layout_ok(dim, d_rows)) sv = nullptr;
+        if (kind_out) *kind_out = sv ? 1 : 0;
+        return assign_tc(D, d_rows, n, dim, d_cent, C, d_out, time_it, sv);
+    }
     if (time_it) CU_TRY(cudaEventRecord(D.ev[0], D.stream));
     if (time_it) CU_TRY(cudaEventRecord(D.ev[1], D.stream));
     PQV_TRY(assign_simt(D, d_rows, n, dim, d_cent, C, d_out));
@@ -189,16 +341,19 @@ int assign_dispatch(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, co
 }
 
 // Reads the events recorded by assign_dispatch(time_it = true) into ctx->last_assign; the stream must be idle.
-void record_assign_timing(pqv_ctx *ctx, DeviceState &D, int path, u64 rows, const uint32_t counts[2], bool first_piece) {
+void record_assign_timing(pqv_ctx *ctx, DeviceState &D, int path, u64 rows, const uint32_t counts[2], bool first_piece,
+                          int kind = 0, bool shadow_built = false) {
     float prep = 0.f, filt = 0.f, post = 0.f;
     cudaEventElapsedTime(&prep, D.ev[0], D.ev[1]);
     cudaEventElapsedTime(&filt, D.ev[1], D.ev[2]);
     cudaEventElapsedTime(&post, D.ev[2], D.ev[3]);
-    float pair_ms = 0.f;
+    float pair_ms = 0.f, shadow_ms = 0.f;
     cudaEventElapsedTime(&pair_ms, D.ev[2], D.ev[4]);
+    if (shadow_built) cudaEventElapsedTime(&shadow_ms, D.ev_shadow[0], D.ev_shadow[1]);
     pqv_assign_timing &t = ctx->last_assign;
     if (first_piece) t = pqv_assign_timing{};
     t.path = (uint32_t)path;
+    t.kind = (uint32_t)kind;
     t.rows += rows;
     t.ambiguous_rows += counts[0];
     t.overflow_rows += counts[1];
@@ -206,6 +361,7 @@ void record_assign_timing(pqv_ctx *ctx, DeviceState &D, int path, u64 rows, cons
     t.filter_ms += filt;
     t.recheck_ms += post;
     t.pair_ms += pair_ms;
+    t.shadow_ms += shadow_ms;
     t.total_ms += (double)prep + filt + post;
 }
 
@@ -367,16 +523,26 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     bt = pqv_batch_timing{};
     bt.queries = nq;
     bt.rows = n;
+    // operand kind: the shard's fp16 shadow when the layout allows it (created on first use), else the f32 rows under tf32
+    ShadowView sv;
+    int kind = T::KIND_TF32;
+    if (shadow_layout_ok(dim, d_rows) && n == sh.n_rows) {
+        const int rc = shard_shadow(D, ds, sh, &sv);
+        if (rc == PQV_OK) kind = T::KIND_F16;
+        else if (rc != PQV_ENOMEM) return rc;  // no room for the shadow: the tf32 form needs none
+    }
     // non-finite or huge queries: the reference's NaN/inf heap behaviour is reproduced by the single-query path only
+    const float qlim = 1e15f;
     for (size_t i = 0; i < (size_t)nq * dim; ++i)
-        if (!(fabsf(queries[i]) < 1e15f)) {
+        if (!(fabsf(queries[i]) < qlim)) {
             bt.declined = 1;
             return PQV_OK;
         }
     const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
     const bool by_pos = (flags & PQV_TIES_BY_POSITION) != 0;
     const uint32_t nq_pad = (nq + T::BN - 1) / T::BN * T::BN;
-    const uint32_t num_nb = nq_pad / T::BN, num_kb = (dim + T::BK - 1) / T::BK;
+    const uint32_t bke = (uint32_t)T::bk_elems(kind);
+    const uint32_t num_nb = nq_pad / T::BN, num_kb = (dim + bke - 1) / bke;
     const uint32_t num_mb = (uint32_t)((n + T::BM - 1) / T::BM);
     const u64 S = std::min<u64>(n, std::min<u64>(std::max<u64>(n / 16, 65536), 524288));
     const uint32_t num_mb_s = (uint32_t)((S + T::BM - 1) / T::BM);
@@ -390,6 +556,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     PQV_TRY(D.tb_Q.ensure((size_t)nq * dim));
     PQV_TRY(D.tb_Qp.ensure((size_t)nq * dim));
     PQV_TRY(D.tb_qf.ensure(3 * (size_t)nq_pad));
+    PQV_TRY(D.tc_wc.ensure(nq_pad / 32));
     PQV_TRY(D.tb_u32.ensure(4 + (size_t)nq + grid));
     PQV_TRY(D.tb_U.ensure((size_t)nq_pad * ldU));
     PQV_TRY(D.tb_cand.ensure((size_t)grid * region_cap));
@@ -397,7 +564,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     const uint32_t kout = raw_keys ? k + 1 : k;
     PQV_TRY(D.tb_keys.ensure((size_t)nq * kout));
     PQV_TRY(D.tc_mu.ensure(dim));
-    if (sh.norms_cap < n) {
+    if (kind == T::KIND_TF32 && sh.norms_cap < n) {
         sh.drop_norms();
         cudaError_t e = cudaMalloc((void **)&sh.d_norms, (size_t)n * sizeof(float2));
         if (e != cudaSuccess) return fail(PQV_ENOMEM, "row-norm cache of %llu rows: %s", (unsigned long long)n, cudaGetErrorString(e));
@@ -408,46 +575,40 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     uint32_t *qbounds = D.tb_u32.p, *dflags = D.tb_u32.p + 1, *cntq = D.tb_u32.p + 4, *region_count = D.tb_u32.p + 4 + nq;
     PQV_TRY(D.tb_info.ensure(nq));
 
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_SAMPLE>>,
-                                        cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_FILTER>>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM_BYTES);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_pair_kernel<T::BatchEpi<T::BATCH_SAMPLE>>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM2_BYTES);
-        if (attr_err == cudaSuccess)
-            attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_pair_kernel<T::BatchEpi<T::BATCH_FILTER>>,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T::SMEM2_BYTES);
-    });
-    CU_TRY(attr_err);
-
     CUtensorMap tmAs, tmA, tmB;
-    PQV_TRY(make_row_tmap(&tmAs, d_rows, S, dim, T::BM));
-    PQV_TRY(make_row_tmap(&tmA, d_rows, n, dim, T::BM));
-    PQV_TRY(make_row_tmap(&tmB, D.tb_Qp.p, nq, dim, tg.pair ? T::BN / 2 : T::BN));
+    const void *a_ptr = kind == T::KIND_F16 ? (const void *)sv.h : (const void *)d_rows;
+    PQV_TRY(make_row_tmap(&tmAs, a_ptr, S, dim, T::BM, kind));
+    PQV_TRY(make_row_tmap(&tmA, a_ptr, n, dim, T::BM, kind));
+    PQV_TRY(make_row_tmap(&tmB, D.tb_Qp.p, nq, dim, tg.pair ? T::BN / 2 : T::BN, kind));
 
     cudaStream_t st = D.stream;
     CU_TRY(cudaEventRecord(D.ev[0], st));
     CU_TRY(cudaMemsetAsync(D.tb_u32.p, 0, (4 + (size_t)nq + grid) * sizeof(uint32_t), st));
-    CU_TRY(cudaMemsetAsync(D.tc_mu.p, 0, (size_t)dim * sizeof(float), st));
+    CU_TRY(cudaMemsetAsync(D.tc_wc.p, 0, (size_t)(nq_pad / 32) * sizeof(uint32_t), st));
     CU_TRY(cudaMemcpyAsync(D.tb_Q.p, queries, (size_t)nq * dim * 4, cudaMemcpyHostToDevice, st));
-    T::query_prep_kernel<<<nq_pad, 128, 0, st>>>(D.tb_Q.p, nq, dim, D.tb_Qp.p, qw, q2, nq_pad, qbounds);
-    if (sh.norms_rows != n) {  // |x|^2 per row: once per dataset state, not per batch
-        T::row_stats_kernel<<<(uint32_t)D.sm_count * 8, 256, 0, st>>>(d_rows, n, dim, D.tc_mu.p, sh.d_norms);
-        sh.norms_rows = n;
+    // operand scale of the queries: qbounds[2] = max |q| (fp16 only), then the power of two derived from it (1 for tf32)
+    if (kind == T::KIND_F16) pqv::half16::absmax_kernel<<<(uint32_t)D.sm_count, 256, 0, st>>>(D.tb_Q.p, (u64)nq * dim, qbounds + 2);
+    pqv::half16::scale_from_absmax_kernel<<<1, 32, 0, st>>>(qbounds + 2, reinterpret_cast<float *>(qbounds + 2));
+    if (kind == T::KIND_F16) {
+        T::query_prep_kernel<T::KIND_F16><<<nq_pad, 128, 0, st>>>(D.tb_Q.p, nq, dim, D.tb_Qp.p, qw, q2, D.tc_wc.p, nq_pad, qbounds, sv.g);
+    } else {
+        T::query_prep_kernel<T::KIND_TF32><<<nq_pad, 128, 0, st>>>(D.tb_Q.p, nq, dim, D.tb_Qp.p, qw, q2, D.tc_wc.p, nq_pad, qbounds, nullptr);
+        if (sh.norms_rows != n) {  // |x|^2 per row: once per dataset state, not per batch
+            CU_TRY(cudaMemsetAsync(D.tc_mu.p, 0, (size_t)dim * sizeof(float), st));
+            T::row_stats_kernel<<<(uint32_t)D.sm_count * 8, 256, 0, st>>>(d_rows, n, dim, D.tc_mu.p, sh.d_norms);
+            sh.norms_rows = n;
+        }
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(D.ev[1], st));
 
     T::BatchParams p;
-    p.stats = sh.d_norms;
+    p.stats = kind == T::KIND_F16 ? sv.stats : sh.d_norms;
     p.qw = qw;
     p.qtheta = qtheta;
+    p.qwc = reinterpret_cast<const float *>(D.tc_wc.p);
     p.qbounds = qbounds;
+    p.scale_a = kind == T::KIND_F16 ? &sv.g->scale : nullptr;
     p.U = D.tb_U.p;
     p.ldU = ldU;
     p.cand = D.tb_cand.p;
@@ -461,12 +622,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     p.row_mask = bmask ? bmask->row_mask : nullptr;
     // phase A: upper bounds over the first S rows -> theta_q
     p.n = S;
-    if (tg.pair)
-        T::tc_rows_x_table_pair_kernel<T::BatchEpi<T::BATCH_SAMPLE>><<<grid_s, T::tc_threads(2), T::SMEM2_BYTES, st>>>(
-            tmAs, tmB, T::GemmShape{num_mb_s, num_nb, num_kb}, p);
-    else
-        T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_SAMPLE>><<<grid_s, T::tc_threads(2), T::SMEM_BYTES, st>>>(
-            tmAs, tmB, T::GemmShape{num_mb_s, num_nb, num_kb}, p);
+    PQV_TRY(tc_launch<T::BatchEpi<T::BATCH_SAMPLE>>(tg_s.pair, kind, grid_s, st, tmAs, tmB, T::GemmShape{num_mb_s, num_nb, num_kb}, p));
     const float delta = (float)(order == 1 ? dim + 8 : dim / 4 + 12) * 5.9604645e-08f;
     {
         const uint32_t M = k <= 128 ? 2048u : 16384u;  // chunk minima kept per query (>= 16 k)
@@ -482,13 +638,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     CU_TRY(cudaEventRecord(D.ev[2], st));
     // phase B: candidates over all rows
     p.n = n;
-    if (tg.pair)
-        T::tc_rows_x_table_pair_kernel<T::BatchEpi<T::BATCH_FILTER>><<<grid, T::tc_threads(2), T::SMEM2_BYTES, st>>>(
-            tmA, tmB, T::GemmShape{num_mb, num_nb, num_kb}, p);
-    else
-        T::tc_rows_x_table_kernel<T::BatchEpi<T::BATCH_FILTER>><<<grid, T::tc_threads(2), T::SMEM_BYTES, st>>>(
-            tmA, tmB, T::GemmShape{num_mb, num_nb, num_kb}, p);
-    CU_TRY(cudaGetLastError());
+    PQV_TRY(tc_launch<T::BatchEpi<T::BATCH_FILTER>>(tg.pair, kind, grid, st, tmA, tmB, T::GemmShape{num_mb, num_nb, num_kb}, p));
     CU_TRY(cudaEventRecord(D.ev[3], st));
     // exact distances of the candidates, per-query selection
     if (order == 0)

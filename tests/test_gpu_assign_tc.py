@@ -35,6 +35,26 @@ class forced:
             os.environ["PQV_ASSIGN"] = self.old
 
 
+class operand_kind:
+    """PQV_TC_KIND=tf32 keeps the filter on the f32 rows (kind::tf32) instead of their fp16 shadow (read at call time)."""
+
+    def __init__(self, kind):
+        self.kind = kind
+
+    def __enter__(self):
+        self.old = os.environ.get("PQV_TC_KIND")
+        if self.kind == "tf32":
+            os.environ["PQV_TC_KIND"] = "tf32"
+        else:
+            os.environ.pop("PQV_TC_KIND", None)
+
+    def __exit__(self, *exc):
+        if self.old is None:
+            os.environ.pop("PQV_TC_KIND", None)
+        else:
+            os.environ["PQV_TC_KIND"] = self.old
+
+
 def kmeans_like_centroids(data, c, rng, per=40):
     """centroids as means of random row subsets: close together, like Lloyd's on unclustered data"""
     idx = rng.integers(0, data.shape[0], (c, per))
@@ -61,6 +81,23 @@ def test_uniform_rows_near_tied_centroids(ctx, n, dim, c):
     cent = kmeans_like_centroids(data, c, rng)
     t = check(ctx, data, cent)
     assert t["ambiguous_rows"] + t["overflow_rows"] <= n
+
+
+@pytest.mark.parametrize("kind,code", [("f16", 1), ("tf32", 0)])
+def test_both_operand_kinds(ctx, kind, code):
+    """the same sweeps through the fp16-shadow filter (kind::f16) and the f32/tf32 one: identical assignments, and the
+    narrower fp16 residual leaves fewer rows for the exact re-check"""
+    rng = np.random.default_rng(77)
+    data = rng.random((30000, 768), dtype=np.float32)
+    cent = kmeans_like_centroids(data, 1024, rng)
+    with operand_kind(kind):
+        t = check(ctx, data, cent)
+        assert t["kind"] == code, t
+        # scale invariance of the fp16 operands: the shadow is scaled by a power of two, tiny / large magnitudes keep their window
+        for scale in (2.0 ** -20, 2.0 ** 15):
+            t2 = check(ctx, (data * np.float32(scale)).astype(np.float32), (cent * np.float32(scale)).astype(np.float32))
+            assert t2["kind"] == code and abs(t2["ambiguous_rows"] - t["ambiguous_rows"]) <= 300, (t, t2)
+    print(kind, t)
 
 
 def test_duplicate_centroids_lowest_index_wins(ctx):
