@@ -141,6 +141,14 @@ struct RustMaxHeap {
     }
 };
 
+// bits(d) of a NaN distance (either sign): the kernels emit such rows as entrants unconditionally (pqv_kernels.cuh)
+inline bool key_is_nan(u64 key) { return ((uint32_t)(key >> 32) & 0x7FFFFFFFu) > 0x7F800000u; }
+inline bool any_nan_key(const u64 *keys, size_t n) {
+    for (size_t i = 0; i < n; ++i)
+        if (key_is_nan(keys[i])) return true;
+    return false;
+}
+
 inline float key_dist(u64 key) {
     uint32_t b = (uint32_t)(key >> 32);
     float f;
@@ -247,6 +255,7 @@ bool topk_without_replay(const u64 *keys, size_t n, uint32_t k, uint32_t flags, 
         bool operator<(const KeyIdx &o) const { return key < o.key; }
     };
     static thread_local std::vector<KeyIdx> v;
+    if (any_nan_key(keys, n)) return false;  // a NaN inside the reference heap changes which rows it admits: replay
     v.resize(n);
     for (size_t i = 0; i < n; ++i) v[i] = KeyIdx{keys[i], (uint32_t)i};
     const size_t take = std::min<size_t>(k, n);
@@ -533,7 +542,27 @@ struct StreamState {
     DevBuf<u64> ent_acc;  // [0] = count, then keys
     std::vector<u64> host_entrants;
     bool any = false;
+    // distance of every pushed row, in push order (4 bytes per row next to dim * 4 read): only read back when a NaN distance
+    // shows up among the entrants, to replay the reference loop literally (src/df_vector/exec.rs:467-482)
+    DevBuf<float> dist_log;
+    bool log_ok = true;
 };
+constexpr u64 STREAM_LOG_MAX_ROWS = 1ull << 30;  // 4 GB of log; beyond that a NaN distance is answered from the entrants alone
+
+static void stream_state_free(StreamState *s) {
+    s->staging[0].release();
+    s->staging[1].release();
+    s->staging64.release();
+    s->carry[0].release();
+    s->carry[1].release();
+    s->d_query.release();
+    s->ent_acc.release();
+    s->dist_log.release();
+    for (auto &ev : s->scan_done)
+        if (ev) cudaEventDestroy(ev);
+    if (s->copy_done) cudaEventDestroy(s->copy_done);
+    delete s;
+}
 
 // NVLink peer-memory candidate exchange (pqv_peer.cuh)
 struct PeerExchange {
@@ -554,6 +583,9 @@ struct pqv_ctx {
     std::vector<DeviceState> devs;
     std::map<u64, Dataset> datasets;
     std::map<u64, StreamState *> streams;
+    // device buffers and events of the last finished streaming top-k, kept for the next pqv_topk_stream_begin: a
+    // VectorTopKExec execution per query would otherwise pay cudaMalloc + cudaFree of ~0.5 GB of staging every time
+    StreamState *stream_cache = nullptr;
     std::map<u64, void *> indexes;  // IvfIndex*, see pqv_ivf_impl.cuh
     u64 next_handle = 1;
     std::mutex mu;
@@ -757,7 +789,8 @@ int scan_geometry(pqv_ctx *ctx, DeviceState &D, const float *d_data, u64 n, uint
 // `final_out` if given, and entrant keys appended to `ent_out` ([0] = running count).
 int enqueue_scan(pqv_ctx *ctx, DeviceState &D, const float *d_data, const uint32_t *d_row_ids, u64 n, uint32_t dim,
                  const float *d_query, uint32_t k, int order, uint32_t pos_base, const u64 *d_carry, u64 *final_out,
-                 u64 *ent_out, uint32_t ent_out_cap, bool time_it, ScanGeom *geom_out, const u64 *n_dev = nullptr) {
+                 u64 *ent_out, uint32_t ent_out_cap, bool time_it, ScanGeom *geom_out, const u64 *n_dev = nullptr,
+                 float *dist_out = nullptr) {
     ScanGeom g;
     PQV_TRY(scan_geometry(ctx, D, d_data, n, dim, k, order, d_row_ids != nullptr, &g));
     PQV_TRY(D.cta_topk.ensure((size_t)g.grid * g.kcap));
@@ -781,6 +814,7 @@ int enqueue_scan(pqv_ctx *ctx, DeviceState &D, const float *d_data, const uint32
     p.cta_topk = D.cta_topk.p;
     p.ent = D.ent.p;
     p.ent_count = D.ent_count.p;
+    p.dist_out = dist_out;
     if (time_it) CU_TRY(cudaEventRecord(D.ev[0], D.stream));
     if (g.variant > 0) PQV_TRY(scan_variant_dispatch(g.variant, p, g.grid, g.smem, D.stream, nullptr));
     else PQV_TRY(SCAN_DISPATCH(scan_launch_t, order, g.vec4, d_row_ids != nullptr, p, g.grid, g.smem, D.stream));
@@ -880,6 +914,9 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
         ScanGeom g;
         uint32_t cap;
         u64 n;
+        const float *d_data;
+        const uint32_t *d_ids;
+        uint32_t pos_base;
     };
     std::vector<Launched> launched;
 
@@ -918,10 +955,10 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
         const uint32_t cap = (uint32_t)std::min<size_t>(D.ent_out.cap - 1, 0xFFFFFFF0u);
         CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
         ScanGeom g;
-        PQV_TRY(enqueue_scan(ctx, D, sh.d_data, d_ids, n, ds.dim, D.d_query.p, k, order,
-                             gather ? 0u : (uint32_t)sh.first_row + pos_offset, nullptr, D.final_topk.p, D.ent_out.p, cap,
-                             si == 0, &g));
-        launched.push_back({&D, g, cap, n});
+        const uint32_t pos_base = gather ? 0u : (uint32_t)sh.first_row + pos_offset;
+        PQV_TRY(enqueue_scan(ctx, D, sh.d_data, d_ids, n, ds.dim, D.d_query.p, k, order, pos_base, nullptr, D.final_topk.p,
+                             D.ent_out.p, cap, si == 0, &g));
+        launched.push_back({&D, g, cap, n, sh.d_data, d_ids, pos_base});
     }
     if (trace) tt[1] = trace_now_ms();
     // collect
@@ -966,6 +1003,41 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
         tm.grid = launched[0].g.grid;
     }
     size_t cnt;
+    // A NaN distance among the entrants: the reference heap no longer behaves like a threshold (src/ivf/search.rs:119-126
+    // with `partial_cmp -> Equal`), so nothing short of its own loop over EVERY candidate, in order, reproduces it.  The scan is
+    // repeated with a per-candidate distance log and the loop is replayed literally on the host (or, for a rank's half of a
+    // sharded search, every row of the slice becomes a candidate).
+    if (!(flags & PQV_TIES_BY_POSITION) && any_nan_key(entrants.data(), entrants.size())) {
+        std::vector<float> dist;
+        std::vector<uint32_t> poses;
+        for (auto &L : launched) {
+            DeviceState &D = *L.D;
+            DevGuard guard(D.dev);
+            PQV_TRY(D.d_dist.ensure(L.n));
+            CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
+            PQV_TRY(enqueue_scan(ctx, D, L.d_data, L.d_ids, L.n, ds.dim, D.d_query.p, k, order, L.pos_base, nullptr, D.final_topk.p,
+                                 D.ent_out.p, L.cap, false, nullptr, nullptr, D.d_dist.p));
+            const size_t base = dist.size();
+            dist.resize(base + L.n);
+            CU_TRY(cudaMemcpyAsync(dist.data() + base, D.d_dist.p, L.n * 4, cudaMemcpyDeviceToHost, D.stream));
+            CU_TRY(cudaStreamSynchronize(D.stream));
+            for (u64 i = 0; i < L.n; ++i) poses.push_back(L.pos_base + (uint32_t)i);
+        }
+        tm.entrants = (uint32_t)dist.size();
+        ctx->last = tm;
+        if (entrants_out) {
+            entrants_out->resize(dist.size());
+            for (size_t i = 0; i < dist.size(); ++i) {
+                uint32_t b;
+                memcpy(&b, &dist[i], 4);
+                (*entrants_out)[i] = ((u64)b << 32) | poses[i];
+            }
+            return PQV_OK;
+        }
+        *out_count = (uint32_t)replay_ordered(
+            dist.size(), [&](size_t i) { return ReplayItem{dist[i], row_of(poses[i])}; }, k, flags, out_rows, out_dist);
+        return PQV_OK;
+    }
     if (entrants_out) {
         tm.entrants = (uint32_t)entrants.size();
         entrants_out->swap(entrants);
@@ -1063,19 +1135,13 @@ void pqv_destroy(pqv_ctx *ctx) {
     if (!ctx) return;
     peer_release(ctx);
     for (auto &kv : ctx->streams) {
-        StreamState *s = kv.second;
         DevGuard guard(ctx->devs[0].dev);
-        s->staging[0].release();
-        s->staging[1].release();
-        s->staging64.release();
-        s->carry[0].release();
-        s->carry[1].release();
-        s->d_query.release();
-        s->ent_acc.release();
-        for (auto &ev : s->scan_done)
-            if (ev) cudaEventDestroy(ev);
-        if (s->copy_done) cudaEventDestroy(s->copy_done);
-        delete s;
+        stream_state_free(kv.second);
+    }
+    if (ctx->stream_cache) {
+        DevGuard guard(ctx->devs[0].dev);
+        stream_state_free(ctx->stream_cache);
+        ctx->stream_cache = nullptr;
     }
     pqv_free_all_indexes(ctx);
     for (auto &kv : ctx->datasets)
@@ -2119,24 +2185,33 @@ int pqv_topk_stream_begin(pqv_ctx *ctx, uint32_t dim, const float *query, uint32
     std::lock_guard<std::mutex> lk(ctx->mu);
     DeviceState &D = ctx->devs[0];
     DevGuard guard(D.dev);
-    StreamState *s = new StreamState();
+    StreamState *s = ctx->stream_cache ? ctx->stream_cache : new StreamState();
+    const bool recycled = ctx->stream_cache != nullptr;
+    ctx->stream_cache = nullptr;
     s->dim = dim;
     s->k = k;
     s->flags = flags;
+    s->rows_pushed = s->ent_rows_bound = 0;
+    s->cur = s->carry_cur = 0;
+    s->host_entrants.clear();
+    s->any = false;
+    s->log_ok = true;
     int rc = s->d_query.ensure(dim);
     if (!rc) rc = s->carry[0].ensure(PQV_MAX_K);
     if (!rc) rc = s->carry[1].ensure(PQV_MAX_K);
     if (!rc) rc = s->ent_acc.ensure((size_t)(1u << 22) + 1);
     if (rc) {
-        delete s;
+        stream_state_free(s);
         return rc;
     }
     CU_TRY(cudaMemcpyAsync(s->d_query.p, query, (size_t)dim * 4, cudaMemcpyHostToDevice, D.stream));
     CU_TRY(cudaMemsetAsync(s->carry[0].p, 0xFF, (size_t)PQV_MAX_K * 8, D.stream));
     CU_TRY(cudaMemsetAsync(s->ent_acc.p, 0, 8, D.stream));
     CU_TRY(cudaStreamSynchronize(D.stream));
-    for (auto &ev : s->scan_done) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-    CU_TRY(cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming));
+    if (!recycled) {
+        for (auto &ev : s->scan_done) CU_TRY(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&s->copy_done, cudaEventDisableTiming));
+    }
     const u64 h = ctx->next_handle++;
     ctx->streams[h] = s;
     *out_stream = h;
@@ -2209,9 +2284,28 @@ static int stream_push_impl(pqv_ctx *ctx, uint64_t stream, const void *values, u
     CU_TRY(cudaStreamWaitEvent(D.stream, s->copy_done, 0));
     const int order = (s->flags & PQV_SUM_SEQ) ? 1 : 0;
     const int cc = s->carry_cur;
+    float *log_at = nullptr;
+    if (s->log_ok && s->rows_pushed + n_rows <= STREAM_LOG_MAX_ROWS) {
+        if (s->rows_pushed + n_rows > s->dist_log.cap) {  // grow (geometric), keeping what is logged so far
+            DevBuf<float> bigger;
+            const size_t want = std::max<size_t>((size_t)(s->rows_pushed + n_rows) * 2, (size_t)1 << 22);
+            if (bigger.ensure(want) == PQV_OK) {
+                if (s->rows_pushed)
+                    CU_TRY(cudaMemcpyAsync(bigger.p, s->dist_log.p, (size_t)s->rows_pushed * 4, cudaMemcpyDeviceToDevice, D.stream));
+                CU_TRY(cudaStreamSynchronize(D.stream));
+                s->dist_log.release();
+                s->dist_log = bigger;
+            } else {
+                s->log_ok = false;  // no room for the log: the stream still answers, NaN distances from the entrants alone
+            }
+        }
+        if (s->log_ok) log_at = s->dist_log.p + s->rows_pushed;
+    } else {
+        s->log_ok = false;
+    }
     PQV_TRY(enqueue_scan(ctx, D, s->staging[cur].p, nullptr, n_rows, s->dim, s->d_query.p, s->k, order,
                          (uint32_t)s->rows_pushed, s->carry[cc].p, s->carry[cc ^ 1].p, s->ent_acc.p,
-                         (uint32_t)(s->ent_acc.cap - 1), false, nullptr));
+                         (uint32_t)(s->ent_acc.cap - 1), false, nullptr, nullptr, log_at));
     CU_TRY(cudaEventRecord(s->scan_done[cur], D.stream));
     s->carry_cur ^= 1;
     s->cur ^= 1;
@@ -2248,22 +2342,24 @@ int pqv_topk_stream_finish(pqv_ctx *ctx, uint64_t stream, uint32_t *out_row_idx,
         else cnt = emit_by_position(keys, RowMap{}, s->k, s->flags, out_row_idx, out_dist);
     } else {
         rc = stream_drain(D, s);
-        if (!rc) cnt = replay_reference_heap(s->host_entrants, RowMap{}, s->k, s->flags, out_row_idx, out_dist);
+        if (!rc && s->log_ok && any_nan_key(s->host_entrants.data(), s->host_entrants.size())) {
+            // a NaN distance: the reference loop over every pushed row, from the distance log (see topk_one)
+            std::vector<float> dist(s->rows_pushed);
+            cudaError_t e = cudaMemcpyAsync(dist.data(), s->dist_log.p, (size_t)s->rows_pushed * 4, cudaMemcpyDeviceToHost, D.stream);
+            if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+            if (e != cudaSuccess) rc = fail(PQV_ECUDA, "stream distance log copy failed: %s", cudaGetErrorString(e));
+            else
+                cnt = replay_ordered(
+                    dist.size(), [&](size_t i) { return ReplayItem{dist[i], (uint32_t)i}; }, s->k, s->flags, out_row_idx, out_dist);
+        } else if (!rc) {
+            cnt = replay_reference_heap(s->host_entrants, RowMap{}, s->k, s->flags, out_row_idx, out_dist);
+        }
     }
     cudaStreamSynchronize(D.stream);
     cudaStreamSynchronize(D.copy_stream);
-    s->staging[0].release();
-    s->staging[1].release();
-    s->staging64.release();
-    s->carry[0].release();
-    s->carry[1].release();
-    s->d_query.release();
-    s->ent_acc.release();
-    for (auto &ev : s->scan_done)
-        if (ev) cudaEventDestroy(ev);
-    if (s->copy_done) cudaEventDestroy(s->copy_done);
-    delete s;
     ctx->streams.erase(it);
+    if (ctx->stream_cache) stream_state_free(s);  // one retired set is kept
+    else ctx->stream_cache = s;
     if (rc) return rc;
     *out_count = (uint32_t)cnt;
     return PQV_OK;

@@ -365,6 +365,8 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
         CU_TRY(cudaMemcpyAsync(erows.data() + got, D.ent_rows.p + got, (count - got) * 4, cudaMemcpyDeviceToHost, D.stream));
         CU_TRY(cudaStreamSynchronize(D.stream));
     }
+    // a NaN distance among the entrants: only the reference loop over every candidate answers that (topk_one's fallback)
+    if (!(flags & PQV_TIES_BY_POSITION) && any_nan_key(entrants.data(), entrants.size())) return PQV_OK;  // *done stays false
     if (eo) {
         eo->keys.swap(entrants);
         eo->rows.swap(erows);

@@ -309,7 +309,14 @@ struct ScanParams {
     u64 *cta_topk;      // [grid][kcap]
     u64 *ent;           // [n]
     uint32_t *ent_count;  // [grid]
+    float *dist_out;    // may be null: distance of candidate i of this launch at dist_out[i] (streaming top-k keeps a log of
+                        // every distance so that a NaN can be answered by replaying the reference loop literally)
 };
+
+// A NaN distance breaks the threshold structure of the reference heap (src/ivf/search.rs:121-122: `d < top` is false
+// against a NaN root and for a NaN candidate).  The kernels therefore never decide anything about such a row: its key is
+// always emitted as an entrant, and the host, on seeing one, replays the reference loop over ALL candidates.
+__device__ __forceinline__ bool is_nan_bits(const uint32_t bits) { return (bits & 0x7FFFFFFFu) > 0x7F800000u; }
 
 __device__ __forceinline__ void bitonic_sort_smem(u64 *s, const uint32_t n, const uint32_t tid,
                                                   const uint32_t nthreads) {
@@ -396,7 +403,8 @@ __global__ void __launch_bounds__(WARPS * 32, MINB) l2_scan_topk_kernel(const Sc
         if (active) d = group_distance<ORDER, VEC4, GATHER, RB, CBV>(p.data, p.row_ids, n_rows, p.dim, g, s_query, tile, lane);
         const u64 pos = g * 32 + lane;
         const uint32_t bits = __float_as_uint(d);
-        const bool pass = active && pos < n_rows && bits < s_tau;
+        const bool pass = active && pos < n_rows && (bits < s_tau || is_nan_bits(bits));
+        if (p.dist_out && active && pos < n_rows) p.dist_out[pos] = d;
         const uint32_t m = __ballot_sync(0xffffffffu, pass);
         bool crossed = false;
         if (m) {
@@ -534,7 +542,7 @@ __global__ void __launch_bounds__(256) entrant_filter_kernel(const u64 *__restri
         bool keep = false;
         if (i < cnt) {
             key = ent[base + i];
-            keep = (uint32_t)(key >> 32) < thr;
+            keep = (uint32_t)(key >> 32) < thr || is_nan_bits((uint32_t)(key >> 32));
         }
         const uint32_t m = __ballot_sync(0xffffffffu, keep);
         if (m) {

@@ -266,6 +266,48 @@ def test_search_with_non_finite_centroids_takes_the_host_ranking(ctx):
     ds.drop()
 
 
+def _nbits(a):
+    a = np.asarray(a, np.float32)
+    return np.where(np.isnan(a), np.uint32(0x7FC00000), a.view(np.uint32))   # NaN payloads are hardware-specific
+
+
+def test_search_with_nan_rows_replays_the_reference_loop(ctx):
+    """table rows with a NaN coordinate (assigned to cluster 0 by the strict `<` of nearest_centroid, index.rs:244-257):
+    once such a row sits in the re-rank heap the reference stops behaving like a threshold (search.rs:119-126); single
+    searches, the batched search and the one-call operator must all give the oracle's answer"""
+    rng = np.random.default_rng(123)
+    dim, n, C = 16, 6000, 10
+    data = rng.random((n, dim), dtype=np.float32)
+    for r in (0, 5, 17, 400, 4000, 5999):
+        data[r, r % dim] = np.nan
+    cent = rng.random((C, dim), dtype=np.float32)
+    assign = O.assign(data, cent, workers=2)
+    assert assign[5] == 0
+    offsets, ids = O.inverted_lists(assign, C)
+    ix = ctx.ivf_from_bytes(O.index_to_bytes(dim, cent, offsets, ids))
+    ds = ctx.dataset_from(data)
+    qs = np.vstack([cent[0] + 0.01, cent[3], rng.random((6, dim), dtype=np.float32)]).astype(np.float32)
+    for nprobe in (1, 3, C):
+        for k, flags in ((1, SQRT), (10, SQRT), (100, SEQ)):
+            expect = []
+            for q in qs:
+                r, d, cand = _search_both_ways(ctx, ix, ds, q, k, nprobe, flags)
+                er, ed = O.topk_rerank_gather(q, data, cand, k, 1 if flags & SEQ else 0, bool(flags & SQRT))
+                assert r.tolist() == er.tolist() and _nbits(d).tolist() == _nbits(ed).tolist()
+                expect.append((er, ed))
+                r, d, total, scored = ix.vector_topk(ds, q, k, nprobe, flags)
+                xr, xd, xtotal, xscored = _expected_vector_topk(q, data, cent, offsets, ids, k, nprobe,
+                                                                1 if flags & SEQ else 0, bool(flags & SQRT), None, None)
+                assert (total, scored) == (xtotal, xscored)
+                assert r.tolist() == xr.tolist() and _nbits(d).tolist() == _nbits(xd).tolist()
+            br, bd, bc = ix.search_batch(ds, qs, k, nprobe, flags)
+            for i, (er, ed) in enumerate(expect):
+                assert bc[i] == er.size and br[i, :bc[i]].tolist() == er.tolist()
+                assert _nbits(bd[i, :bc[i]]).tolist() == _nbits(ed).tolist()
+    ix.drop()
+    ds.drop()
+
+
 def test_host_list_builder_equals_the_device_one(ctx):
     """PQV_CSR=host (read once per process) cannot be flipped here, so the equality is checked at the blob level: the
     device-built lists of pqv_ivf_build against lists rebuilt on the host from the same assignment (oracle)"""

@@ -23,7 +23,9 @@ def ctx(P):
 
 
 def bits(a):
-    return np.asarray(a, np.float32).view(np.uint32)
+    """bit patterns, with every NaN mapped to one pattern (the payload of a propagated NaN is hardware-specific)"""
+    a = np.asarray(a, np.float32)
+    return np.where(np.isnan(a), np.uint32(0x7FC00000), a.view(np.uint32))
 
 
 def check_topk(ds, data, q, k, flags, row_ids=None):
@@ -126,6 +128,47 @@ def test_non_finite_distances(ctx):
     q = rng.random(8, dtype=np.float32)
     for k in (10, 600):
         check_topk(ds, data, q, k, SQRT)
+    ds.drop()
+
+
+def test_nan_distances_follow_the_reference_loop(ctx):
+    """A NaN distance inside the reference heap (search.rs:119-126: `d < top` is false against a NaN root, and
+    partial_cmp -> Equal keeps a NaN wherever the sifts leave it) changes which later rows are admitted.  The GPU path
+    answers such a query by replaying the loop over every candidate; rows with a NaN coordinate sit below k, right at
+    k, and far behind it."""
+    rng = np.random.default_rng(77)
+    for n, dim, nan_rows in [(5000, 8, [3]), (5000, 8, [0, 1, 2]), (3000, 16, [9, 10, 2999]), (40_000, 4, [5, 700, 20_000]),
+                             (2000, 64, list(range(0, 2000, 97))), (300, 8, list(range(300)))]:
+        data = rng.random((n, dim), dtype=np.float32)
+        for r in nan_rows:
+            data[r, rng.integers(0, dim)] = np.nan
+        ds = ctx.dataset_from(data)
+        q = rng.random(dim, dtype=np.float32)
+        for k in (1, 4, 10, 100):
+            for flags in (SQRT, SEQ, 0):
+                check_topk(ds, data, q, k, flags)
+        ids = rng.permutation(n)[: n // 2].astype(np.uint32)
+        ids[:3] = nan_rows[0]                                 # the NaN row among the first candidates (and repeated)
+        for k in (2, 10, 64):
+            check_topk(ds, data, q, k, SQRT, row_ids=ids)
+            check_topk(ds, data, q, k, SEQ, row_ids=ids)
+        # the streaming form (VectorTopKExec heap, exec.rs:467-482), NaN rows spread over several pushes
+        for k in (3, 10, 100):
+            st = ctx.topk_stream(q, k, SEQ)
+            for a in range(0, n, 1111):
+                st.push(data[a:a + 1111])
+            r, d = st.finish()
+            er, ed = O.topk_rerank(q, data, None, k, 1, False)
+            assert r.tolist() == er.tolist() and bits(d).tolist() == bits(ed).tolist()
+        ds.drop()
+    # a NaN in the query: every distance is NaN, the heap keeps the first k rows it was given
+    data = rng.random((500, 8), dtype=np.float32)
+    ds = ctx.dataset_from(data)
+    q = rng.random(8, dtype=np.float32)
+    q[2] = np.nan
+    for k in (1, 10, 600):
+        check_topk(ds, data, q, k, SQRT)
+        check_topk(ds, data, q, k, SEQ)
     ds.drop()
 
 
