@@ -376,7 +376,8 @@ struct DeviceState {
     DevBuf<float2> tc_stats;
     DevBuf<uint2> tc_pairs;
     DevBuf<u64> tc_best;
-    DevBuf<uint32_t> tc_u32, tc_amb_rows, tc_ovf_rows;
+    DevBuf<uint32_t> tc_u32, tc_amb_rows, tc_ovf_rows, tc_perm;
+    DevBuf<u64> tc_okeys;
     // batched top-k scratch
     DevBuf<float> tb_Q, tb_Qp, tb_qf, tb_U;
     DevBuf<uint32_t> tb_u32, tb_info;
@@ -1215,6 +1216,8 @@ void pqv_destroy(pqv_ctx *ctx) {
         D.tc_u32.release();
         D.tc_amb_rows.release();
         D.tc_ovf_rows.release();
+        D.tc_perm.release();
+        D.tc_okeys.release();
         D.tb_Q.release();
         D.tb_Qp.release();
         D.tb_qf.release();
@@ -2037,10 +2040,14 @@ int pqv_bench_assign(pqv_ctx *ctx, uint64_t handle, uint64_t n, const float *cen
         PQV_TRY(sweep_shadow(*D, rds, d_rows, n, &sv, &have_sv, &built));  // the table's shadow: built by the first sweep only
         PQV_TRY(assign_dispatch(*D, d_rows, n, dim, D->d_centroids.p, n_clusters, D->d_assign.p, &path, true,
                                 have_sv ? &sv : nullptr, &kind, &built2));
-        uint32_t h_counts[2] = {0, 0};
+        uint32_t h_counts[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         if (path == ASSIGN_TC)
             CU_TRY(cudaMemcpyAsync(h_counts, D->tc_u32.p + TC_COUNTS_OFFSET, sizeof h_counts, cudaMemcpyDeviceToHost, D->stream));
         CU_TRY(cudaStreamSynchronize(D->stream));
+        if (path == ASSIGN_TC && getenv("PQV_TRACE"))
+            fprintf(stderr, "[pqv trace] assign filter: %u ambiguous rows, %u rows to the exact scan (group store full %u, non-finite %u, "
+                            "empty window %u, pair buffer full %u), %u pairs\n",
+                    h_counts[0], h_counts[1], h_counts[4], h_counts[5], h_counts[6], h_counts[7], h_counts[2]);
         record_assign_timing(ctx, *D, path, n, h_counts, true, kind, built || built2);
         const pqv_assign_timing &t = ctx->last_assign;
         acc.path = t.path;

@@ -55,22 +55,21 @@ constexpr uint32_t TMEM_COLS = 512;  // two accumulator stages of BN f32 columns
 // per SM sub-partition is latency-bound (ncu: 0.23 IPC) and the MMAs end up waiting for the accumulator to be drained
 constexpr int tc_threads(int split) { return 64 + 128 * split; }
 constexpr int EPI_WARP0 = 2;
-constexpr uint32_t BAR_BYTES = 8 * (2 * STAGES + 4) + 16;
+__host__ __device__ constexpr uint32_t bar_bytes(int stages) { return 8u * (2u * (uint32_t)stages + 4u) + 16u; }
 // shared memory behind the barriers: the hand-over area of a split epilogue (Epi::EXCH_BYTES) and EPI_TAB_FLOATS floats of
 // per-column constants the epilogue reads for every tile (centroid norms / halved query thresholds), staged once per CTA
 constexpr uint32_t EPI_TAB_FLOATS = 4096;
 constexpr uint32_t EPI_TAB_BYTES = EPI_TAB_FLOATS * 4;
-constexpr size_t smem_bytes_single(uint32_t exch_bytes) {
-    return (size_t)STAGES * STAGE_BYTES + BAR_BYTES + exch_bytes + EPI_TAB_BYTES + 1024;  // +1024: manual 1 KB alignment
+constexpr size_t smem_bytes_single(int stages, uint32_t exch_bytes) {
+    return (size_t)stages * STAGE_BYTES + bar_bytes(stages) + exch_bytes + EPI_TAB_BYTES + 1024;  // +1024: manual 1 KB alignment
 }
 // CTA-pair variant (tcgen05 cta_group::2): UMMA M = 256 over two SMs, each CTA stages its own 128 rows of A and HALF of
 // the B tile (128 table rows), so a stage is 32 KB per CTA instead of 48 KB and six stages fit
 constexpr int STAGES2 = 6;
 constexpr uint32_t B2_BYTES = (BN / 2) * BK * 4;
 constexpr uint32_t STAGE2_BYTES = A_BYTES + B2_BYTES;
-constexpr uint32_t BAR2_BYTES = 8 * (2 * STAGES2 + 4) + 16;
-constexpr size_t smem_bytes_pair(uint32_t exch_bytes) {
-    return (size_t)STAGES2 * STAGE2_BYTES + BAR2_BYTES + exch_bytes + EPI_TAB_BYTES + 1024;
+constexpr size_t smem_bytes_pair(int stages, uint32_t exch_bytes) {
+    return (size_t)stages * STAGE2_BYTES + bar_bytes(stages) + exch_bytes + EPI_TAB_BYTES + 1024;
 }
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 
@@ -317,6 +316,41 @@ __device__ __forceinline__ double kappa_of(const half16::Globals *g, uint32_t di
     return (double)__uint_as_float(g->kappa_bits) * (1.0 + 2.0 * (double)(dim + 32) * ldexp(1.0, -24) + 1e-6) + 1e-30;
 }
 
+// Column order of the table inside the filter.  A row's score s_j = |c_j - mu|^2 - 2 (x - mu).(c_j - mu) + const grows with
+// |c_j - mu|^2 (clusters of few members sit far from the mean: the term ranges over 1 .. 70 for config C3 while the projection
+// term has a spread of ~1), and so does the error weight w_j.  Sorting the columns by |c_j - mu|^2 puts the likely winners into
+// the first chunks -- the running bound m is final after a few tiles and the remaining chunks fail the chunk pre-test for
+// all 32 rows of a warp -- and makes w homogeneous inside a 4-column group / 32-column chunk.  perm[pos] = original index; the
+// epilogue maps back before anything leaves the kernel, so tie-breaking (lowest ORIGINAL index, src/ivf/index.rs:251) is untouched.
+__global__ void __launch_bounds__(128) centroid_spread_kernel(const float *__restrict__ cent, uint32_t C, uint32_t dim,
+                                                              const float *__restrict__ mu, u64 *__restrict__ keys) {
+    const uint32_t j = blockIdx.x;
+    __shared__ float red[4];
+    float b2 = 0.f;
+    for (uint32_t col = threadIdx.x; col < dim; col += blockDim.x) {
+        const float d = cent[(size_t)j * dim + col] - mu[col];
+        b2 += d * d;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) b2 += __shfl_xor_sync(0xffffffffu, b2, o);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = b2;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        b2 = (red[0] + red[1]) + (red[2] + red[3]);
+        // non-negative f32 bits order as unsigned; NaN / inf sort behind every finite value (any order is valid)
+        keys[j] = ((u64)(__float_as_uint(b2) & 0x7FFFFFFFu) << 32) | j;
+    }
+}
+constexpr uint32_t ORDER_MAX_C = 8192;   // one CTA sorts the keys in shared memory (64 KB); wider tables keep their order
+__global__ void __launch_bounds__(1024) centroid_order_kernel(const u64 *__restrict__ keys, uint32_t C, uint32_t cp2,
+                                                              uint32_t *__restrict__ perm) {
+    extern __shared__ u64 okeys[];
+    for (uint32_t i = threadIdx.x; i < cp2; i += blockDim.x) okeys[i] = i < C ? keys[i] : ~0ull;
+    __syncthreads();
+    bitonic_sort_smem(okeys, cp2, threadIdx.x, blockDim.x);
+    for (uint32_t i = threadIdx.x; i < C; i += blockDim.x) perm[i] = (uint32_t)okeys[i];
+}
+
 // B^_j = rounded (c_j - mu) in the operand type of the kernel (tf32-rounded f32, or fp16 with the sub-normal range flushed),
 // cn_j = |c_j|^2, w_j, and wc[j / 32] = max of w over the 32-column chunk of j
 template <int KIND>
@@ -324,8 +358,9 @@ __global__ void __launch_bounds__(128) centroid_prep_kernel(const float *__restr
                                                             const float *__restrict__ mu, void *__restrict__ Bp_,
                                                             float *__restrict__ cn, float *__restrict__ wv,
                                                             uint32_t *__restrict__ wc, uint32_t cn_len,
-                                                            uint32_t *__restrict__ bounds, const half16::Globals *__restrict__ hg) {
-    const uint32_t j = blockIdx.x;
+                                                            uint32_t *__restrict__ bounds, const half16::Globals *__restrict__ hg,
+                                                            const uint32_t *__restrict__ perm) {
+    const uint32_t j = blockIdx.x;   // position inside the filter; row `src` of the caller's table
     __shared__ double red[3][4];
     const float sb = KIND == KIND_F16 ? __uint_as_float(bounds[5]) : 1.f;  // power of two (scale_from_absmax_kernel)
     if (j >= C) {  // padding entries of cn: +inf never passes "ŝ <= thr"
@@ -336,8 +371,9 @@ __global__ void __launch_bounds__(128) centroid_prep_kernel(const float *__restr
         return;
     }
     double r2 = 0.0, b2 = 0.0, c2 = 0.0;
+    const uint32_t src = perm ? perm[j] : j;
     for (uint32_t col = threadIdx.x; col < dim; col += blockDim.x) {
-        const float c = cent[(size_t)j * dim + col];
+        const float c = cent[(size_t)src * dim + col];
         const double cp = (double)c - (double)mu[col];
         float b;
         if (KIND == KIND_F16) {
@@ -432,9 +468,10 @@ struct AssignTcParams {
     const float *wv;        // [num_nb * BN] per-centroid error weight w_j (0 padded): |ŝ_j - s_j| <= |x| w_j + slack
     const float *wc;        // [num_nb * BN / 32] per 32-column chunk: max_j w_j (chunk pre-test)
     const uint32_t *bounds; // [8] see centroid_mean_kernel
+    const uint32_t *perm;   // [C] column of the filter -> row of the caller's table (centroid_order_kernel), nullptr = identity
     const float *scale_a;   // operand scale of the rows (half16::Globals::scale), nullptr = 1
     uint32_t *assign;       // [n] out: final for rows the filter decides
-    uint32_t *counts;       // [0] ambiguous rows, [1] overflow rows, [2] (row, candidate) pairs; zeroed by the caller
+    uint32_t *counts;       // [0] ambiguous rows, [1] overflow rows, [2] (row, candidate) pairs, [4..7] overflow reasons; zeroed by the caller
     uint32_t *amb_rows;     // [n]
     uint2 *pairs;           // [pair_cap] (row, candidate): one exact distance each (pair_exact_kernel)
     u64 *best;              // [n] per ambiguous row: min over its pairs of bits(distance) << 32 | candidate
@@ -495,6 +532,7 @@ __global__ void __launch_bounds__(tc_threads(Epi::SPLIT), 1)
 tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
                        const typename Epi::Params p) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr int STAGES = Epi::STAGES_SINGLE;   // shared-memory ring depth of this epilogue's instance (shadows the default)
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t bar0 = base + STAGES * STAGE_BYTES;
@@ -570,7 +608,7 @@ tc_rows_x_table_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_con
         __syncwarp();
     } else {
         // ===== epilogue warps: one row per thread; a warp may only touch TMEM lanes 32*(warp%4) .. +31 =====
-        uint8_t *const after_bars = smem_raw + (bar0 + BAR_BYTES - raw);
+        uint8_t *const after_bars = smem_raw + (bar0 + bar_bytes(STAGES) - raw);
         Epi::run(EpiCtx{BAR_TFULL(0), BAR_TEMPTY(0), 0u, tmem_base, warp & 3u, lane, counter, blockIdx.x, gridDim.x, g.num_mb,
                         (warp - 2u) >> 2, reinterpret_cast<uint32_t *>(after_bars),
                         reinterpret_cast<float *>(after_bars + Epi::EXCH_BYTES), threadIdx.x - 64u},
@@ -601,6 +639,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(tc_threads(Epi::SPLI
 tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmShape g,
                             const typename Epi::Params p) {
     extern __shared__ uint8_t smem_raw[];
+    constexpr int STAGES2 = Epi::STAGES_PAIR;    // shared-memory ring depth of this epilogue's instance (shadows the default)
     const uint32_t raw = smem_u32(smem_raw);
     const uint32_t base = (raw + 1023u) & ~1023u;
     const uint32_t bar0 = base + STAGES2 * STAGE2_BYTES;
@@ -687,7 +726,7 @@ tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
         __syncwarp();
     } else {
         // ===== epilogue warps of both CTAs: each drains its own 128 TMEM lanes =====
-        uint8_t *const after_bars = smem_raw + (bar0 + BAR2_BYTES - raw);
+        uint8_t *const after_bars = smem_raw + (bar0 + bar_bytes(STAGES2) - raw);
         Epi::run(EpiCtx{BAR2_TFULL(0), lead_bar0 + 8u * (uint32_t)(2 * STAGES2 + 2), 1u, tmem_base, warp & 3u, lane, counter,
                         pair * 2u + rank, num_pairs * 2u, num_mb2 * 2u, (warp - 2u) >> 2,
                         reinterpret_cast<uint32_t *>(after_bars), reinterpret_cast<float *>(after_bars + Epi::EXCH_BYTES),
@@ -710,37 +749,56 @@ tc_rows_x_table_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __gri
 }
 
 // epilogue of the k-means assignment filter (see the header of this file).
-// Two warps share a row, each scanning half of every tile's columns with its own running minimum and its own candidate
-// list in shared memory (its window is the wider one of its slice, so nothing the full-width scan keeps is lost); after the
-// last tile of the row slice 1 publishes (min, count, overflow flag) and slice 0 finalises over both lists.  The list is
-// append-only -- a few instructions per candidate instead of a search for a stale register slot -- and compacted against
-// the current threshold when its 8 entries are used up (stale entries: columns that were record minima when they passed).
+// Two warps share a row, each scanning half of every tile's columns with its own running bound m >= min_j s_j^true and its
+// own candidate store in shared memory (its window is the wider one of its slice, so nothing the full-width scan keeps is
+// lost); after the last tile of the row slice 1 publishes (m, store) and slice 0 finalises over both stores.
 //
 // Per 32-column chunk the common path is one FFMA and half a three-input minimum per column:
 //     s_j = cn_j - 2 acc_j ,  smin = min_j s_j ,  awc = a * max_{j in chunk} w_j
 //     m  <- min(m, smin + awc)              (an upper bound of min_j s_j^true: s_j^true <= ŝ_j + a w_j <= s_j + awc)
-//     a column can only matter if  s_j - awc <= thr(m)  -- tested once per chunk on smin.  Only chunks that hold such a
-//     column walk their columns, and there the decision uses the column's OWN w_j (one far-out centroid -- an empty
-//     cluster at the origin, src/ivf/index.rs:446-453 -- must not widen the window of its 31 neighbours):
-//     m <- min(m, s_j + a w_j),  candidate iff  s_j - a w_j <= thr(m).
+//     a column can only matter if  s_j - awc <= thr(m),  tested on smin for the chunk and on the 4-column minima the
+//     reduction tree already holds for its eight groups.
+// A warp holds 32 different rows, each with its own sequence of record minima, so SOME lane passes the chunk test in
+// nearly every chunk (98.7 % measured): whatever happens then is paid by the whole warp.  The scan therefore does no
+// per-column work at all: a group that passes is SAVED (its four scores as one 16-byte shared-memory store, its index
+// pushed on a register stack) with predicated straight-line code, and the columns are only looked at after the row's last
+// tile, against the final threshold and with each column's OWN w_j (one far-out centroid -- an empty cluster at the
+// origin, src/ivf/index.rs:446-453 -- must not widen the window of its 31 neighbours) -- by then most saved groups
+// (records that were overtaken) are outside the window, and every lane has the same kind of work.  The store holds
+// SAVE groups per row and slice; when it is full the groups that have left the window are dropped (thr only shrinks),
+// and a row whose live groups still do not fit is handed to the exact scan (overflow).
 struct AssignEpi {
     typedef AssignTcParams Params;
     static constexpr int SPLIT = 2;
     static constexpr int NCH = BN / 32 / SPLIT;      // chunks per warp and tile
-    static constexpr int LIST = 8;                   // candidate entries per row and slice (shared memory, append + compact)
+    static constexpr int STAGES_SINGLE = 3, STAGES_PAIR = 5;   // one stage less than the default: room for the group store
+    static constexpr int SAVE = 6;                   // saved 4-column groups per row and slice
+    static constexpr int GBITS = 10;                 // bits per group index on the register stack (6 x 10 in a u64): C <= 4096
     static constexpr int ETHREADS = 128 * SPLIT;     // epilogue threads per CTA
-    // shared memory of the epilogue: LIST x ETHREADS entries (score bits, column) + per slice-1 thread (min bits, count | ovf << 31)
-    static constexpr uint32_t LIST_BYTES = LIST * ETHREADS * 8;
-    static constexpr uint32_t EXCH_BYTES = LIST_BYTES + 128 * 8;
+    // shared memory of the epilogue: SAVE x ETHREADS float4 entries + one uint4 per row (slice 1 -> slice 0: m, stack, count)
+    static constexpr uint32_t SAVE_BYTES = SAVE * ETHREADS * 16;
+    static constexpr uint32_t EXCH_BYTES = SAVE_BYTES + 128 * 16;
     static __device__ __forceinline__ void finish(uint32_t *, const Params &) {}
 
-    // drops the entries whose score has left the window (thr only ever shrinks while a row is scanned); returns the new count
-    static __device__ __noinline__ uint32_t compact(uint2 *mine, uint32_t cnt, float thr) {
+    static __device__ __forceinline__ float min4(const float4 v) { return fminf(fminf(v.x, v.y), fminf(v.z, v.w)); }
+    // group index of entry e (0 = oldest) of a stack holding cnt entries
+    static __device__ __forceinline__ uint32_t group_of(u64 stack, uint32_t cnt, uint32_t e) {
+        return (uint32_t)(stack >> ((cnt - 1u - e) * GBITS)) & ((1u << GBITS) - 1u);
+    }
+    // drops the saved groups no column of which can still be inside the window; returns the new count
+    static __device__ __forceinline__ float max4(const float4 v) { return fmaxf(fmaxf(v.x, v.y), fmaxf(v.z, v.w)); }
+    static __device__ __noinline__ uint32_t compact(float4 *mine, uint32_t cnt, u64 *stack, float thr, float a, const float *wv) {
         uint32_t o = 0;
+        u64 ns = 0;
         for (uint32_t e = 0; e < cnt; ++e) {
-            const uint2 it = mine[e * ETHREADS];
-            if (__uint_as_float(it.x) <= thr) mine[(o++) * ETHREADS] = it;
+            const uint32_t grp = group_of(*stack, cnt, e);
+            const float4 it = mine[e * ETHREADS];
+            if (min4(it) - a * max4(*reinterpret_cast<const float4 *>(wv + (size_t)grp * 4u)) <= thr) {
+                mine[(o++) * ETHREADS] = it;
+                ns = (ns << GBITS) | grp;
+            }
         }
+        *stack = ns;
         return o;
     }
 
@@ -750,18 +808,22 @@ struct AssignEpi {
         // centroid norms and error weights for every tile of this CTA: staged once in shared memory when the table is short enough
         const uint32_t cn_len = g.num_nb * BN;
         const float *cnp = p.cn, *wvp = p.wv;
-        if (2u * cn_len <= EPI_TAB_FLOATS) {
+        const float *wgp = nullptr;   // per 4-column group: max of w (only when the table's constants fit the staging area)
+        if (2u * cn_len + cn_len / 4u <= EPI_TAB_FLOATS) {
             for (uint32_t i = c.et; i < cn_len; i += ETHREADS) {
                 c.tab[i] = p.cn[i];
                 c.tab[cn_len + i] = p.wv[i];
             }
+            for (uint32_t i = c.et; i < cn_len / 4u; i += ETHREADS)
+                c.tab[2u * cn_len + i] = max4(*reinterpret_cast<const float4 *>(p.wv + (size_t)i * 4u));
             c.sync_epilogue(ETHREADS);
             cnp = c.tab;
             wvp = c.tab + cn_len;
+            wgp = c.tab + 2u * cn_len;
         }
-        uint2 *const lists = reinterpret_cast<uint2 *>(c.exch);
-        uint2 *const mine = lists + c.et;                                   // entry e of this thread: mine[e * ETHREADS]
-        uint2 *const meta = lists + LIST * ETHREADS + row_in_tile;          // written by slice 1, read by slice 0 (same row)
+        float4 *const saves = reinterpret_cast<float4 *>(c.exch);
+        float4 *const mine = saves + c.et;                                  // entry e of this thread: mine[e * ETHREADS]
+        uint4 *const meta = reinterpret_cast<uint4 *>(saves + SAVE * ETHREADS) + row_in_tile;   // slice 1 -> slice 0 (same row)
         const float wmax = __uint_as_float(p.bounds[0]), cnmax = __uint_as_float(p.bounds[1]);
         const float bnmax = __uint_as_float(p.bounds[2]);
         // the tensor cores saw (sa x) and (sb B'): -2 / (sa sb) undoes both scales exactly (powers of two)
@@ -772,6 +834,7 @@ struct AssignEpi {
         const float gamma = (float)(p.dim + 32) * 5.9604645e-08f;       // f32 sums of the row statistics
         const float c2 = 2.2f * delta;
         const bool table_ok = (cnmax < 1e30f) && (wmax < 1e30f) && (mun < 1e30f) && (dmu < 1e30f);
+        const bool stack_ok = (cn_len >> 2) <= (1u << GBITS);   // every group index fits its stack field
         const float inf = __int_as_float(0x7f800000);
         uint32_t tile = 0;
         for (uint32_t mb = c.mb0; mb < c.mb_end; mb += c.mb_stride) {
@@ -788,12 +851,12 @@ struct AssignEpi {
             const float T2 = mag * 1.9073486e-06f + 1e-37f;                              // 2^-19: cn / fma / awc / thr roundings
             const float K2 = (x2 - 2.f * st.y) + 2.f * a * dmu + 2.02f * gamma * a * mun + (kmag + mag) * 9.5367432e-07f;
             float m = inf;
-            uint32_t cnt = 0;   // live entries of this thread's list
-            bool ovf = false;
+            uint32_t cnt = 0;   // saved groups of this thread
+            u64 stack = 0;      // their group indices (column / 4), GBITS each, newest in the low bits
+            bool ovf = !stack_ok;
             for (uint32_t nb = 0; nb < g.num_nb; ++nb, ++tile) {
                 const uint32_t taddr = c.acquire(tile);
                 const float4 *cn4 = reinterpret_cast<const float4 *>(cnp + (size_t)nb * BN);
-                const float *wv1 = wvp + (size_t)nb * BN;
                 const float *wcp = p.wc + (size_t)nb * (BN / 32);
 #pragma unroll 1
                 for (uint32_t ch = c.h * NCH; ch < (c.h + 1u) * NCH; ++ch) {
@@ -814,59 +877,97 @@ struct AssignEpi {
                     const float awc = a * __ldg(wcp + ch);
                     m = fminf(m, smin + awc);
                     float thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
-                    const float ts = thr + awc;   // s_j <= ts  <=>  s_j - awc <= thr (rounding of the two forms: inside T2)
+                    // s_j <= ts  <=>  s_j - awc <= thr (rounding of the two forms: inside T2); +inf scores (padding columns,
+                    // overflowed norms) never win in the reference and never pass, even while m is still +inf
+                    const float ts = fminf(thr + awc, 3.0e38f);
                     if (smin <= ts) {
-                        const uint32_t j0 = nb * BN + ch * 32u;
-                        const float *wj = wv1 + ch * 32u;
+                        // the groups are tested with their OWN widest w: one far-out centroid (an empty cluster at the origin)
+                        // inflates awc of its chunk tenfold, and its 7 neighbour groups must not all be saved for it
+                        const uint32_t g0 = (nb * BN + ch * 32u) >> 2;
+                        float wg[8];
+                        if (wgp) {
+                            const float4 wa = *reinterpret_cast<const float4 *>(wgp + g0);
+                            const float4 wb = *reinterpret_cast<const float4 *>(wgp + g0 + 4u);
+                            wg[0] = wa.x, wg[1] = wa.y, wg[2] = wa.z, wg[3] = wa.w, wg[4] = wb.x, wg[5] = wb.y, wg[6] = wb.z, wg[7] = wb.w;
+                        } else {
 #pragma unroll
-                        for (int i = 0; i < 32; ++i) {
-                            if (v[i] <= ts) {   // pre-test with the chunk's widest w; the column's own w decides
-                                const float aw = a * wj[i];
-                                m = fminf(m, v[i] + aw);
-                                thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
-                                const float lj = v[i] - aw;
-                                if (lj <= thr) {
-                                    if (cnt == (uint32_t)LIST) cnt = compact(mine, cnt, thr);
-                                    if (cnt < (uint32_t)LIST) mine[(cnt++) * ETHREADS] = make_uint2(__float_as_uint(lj), j0 + (uint32_t)i);
-                                    else ovf = true;
-                                }
+                            for (int g4 = 0; g4 < 8; ++g4) wg[g4] = max4(*reinterpret_cast<const float4 *>(wvp + (size_t)(g0 + g4) * 4u));
+                        }
+                        // tighten m with the groups' own bounds first (min4 + a max4(w) >= U_j of the group's best column): while
+                        // the chunk of a far-out centroid holds the record, smin + awc alone would keep the window ten times
+                        // too wide for every later chunk
+                        float ug[8];
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4) ug[g4] = __fmaf_rn(a, wg[g4], sm[g4]);
+                        m = fminf(m, fminf(fminf(fminf(ug[0], ug[1]), fminf(ug[2], ug[3])), fminf(fminf(ug[4], ug[5]), fminf(ug[6], ug[7]))));
+                        thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
+                        const float thr_c = fminf(thr, 3.0e38f);
+                        uint32_t hits = 0;
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4) hits |= (__fmaf_rn(-a, wg[g4], sm[g4]) <= thr_c) ? (1u << g4) : 0u;
+                        if (cnt + (uint32_t)__popc(hits) > (uint32_t)SAVE) {   // rare: make room, or give the row up
+                            cnt = compact(mine, cnt, &stack, thr, a, wvp);
+                            if (cnt + (uint32_t)__popc(hits) > (uint32_t)SAVE) {
+                                ovf = true;
+                                hits = 0;
+                            }
+                        }
+#pragma unroll
+                        for (int g4 = 0; g4 < 8; ++g4) {
+                            if ((hits >> g4) & 1u) {
+                                mine[cnt * ETHREADS] = make_float4(v[4 * g4], v[4 * g4 + 1], v[4 * g4 + 2], v[4 * g4 + 3]);
+                                stack = (stack << GBITS) | (u64)(g0 + (uint32_t)g4);
+                                ++cnt;
                             }
                         }
                     }
                 }
                 c.release(tile);
             }
+            // ---- after the row's last tile: every saved column's own bound U_j = s_j + a w_j tightens m (the column attaining
+            // the minimum of U is itself inside the window, hence saved -- unless the row overflowed)
+            for (uint32_t e = 0; e < cnt; ++e) {
+                const float4 it = mine[e * ETHREADS];
+                const float4 w4 = *reinterpret_cast<const float4 *>(wvp + (size_t)group_of(stack, cnt, e) * 4u);
+                m = fminf(m, fminf(fminf(it.x + a * w4.x, it.y + a * w4.y), fminf(it.z + a * w4.z, it.w + a * w4.w)));
+            }
             // ---- hand-over between the two column slices (named barrier 1 + q: the two warps that own TMEM quarter q): slice 1
-            // publishes (min, count, overflow); its entries are read in place by slice 0, which finalises the row
-            if (c.h != 0u) *meta = make_uint2(__float_as_uint(m), cnt | (ovf ? 0x80000000u : 0u));
+            // publishes (m, stack, count, overflow); its entries are read in place by slice 0, which finalises the row
+            if (c.h != 0u)
+                *meta = make_uint4(__float_as_uint(m), cnt | (ovf ? 0x80000000u : 0u), (uint32_t)stack, (uint32_t)(stack >> 32));
             asm volatile("bar.sync %0, 64;" ::"r"(1u + q) : "memory");
             if (c.h == 0u) {
-                const uint2 om = *meta;
+                const uint4 om = *meta;
                 const uint32_t ocnt = om.y & 0x7FFFFFFFu;
-                const uint2 *const other = lists + (c.et + 128u);   // the same row's thread of slice 1
+                const u64 ostack = (u64)om.z | ((u64)om.w << 32);
+                const float4 *const other = mine + 128;   // the same row's thread of slice 1
                 m = fminf(m, __uint_as_float(om.x));
                 ovf |= (om.y >> 31) != 0u;
                 const float thr = m + T2 + c2 * fmaxf(m + K2, 0.f);
-                // pass 1: how many entries of both lists are still inside the final window
+                // pass 1: which saved columns of both slices are inside the final window (bit 4 e + i of inwin)
+                static_assert(2 * SAVE * 4 <= 64, "inwin holds one bit per saved column of both slices");
                 uint32_t nv = 0, only = NONE;
-                for (uint32_t e = 0; e < cnt; ++e) {
-                    const uint2 it = mine[e * ETHREADS];
-                    if (__uint_as_float(it.x) <= thr) {
-                        ++nv;
-                        only = it.y;
-                    }
-                }
-                for (uint32_t e = 0; e < ocnt; ++e) {
-                    const uint2 it = other[e * ETHREADS];
-                    if (__uint_as_float(it.x) <= thr) {
-                        ++nv;
-                        only = it.y;
+                u64 inwin = 0;   // 2 x SAVE entries x 4 columns
+                for (uint32_t e = 0; e < cnt + ocnt; ++e) {
+                    const bool own = e < cnt;
+                    const uint32_t grp = own ? group_of(stack, cnt, e) : group_of(ostack, ocnt, e - cnt);
+                    const float4 it = own ? mine[e * ETHREADS] : other[(e - cnt) * ETHREADS];
+                    const float4 w4 = *reinterpret_cast<const float4 *>(wvp + (size_t)grp * 4u);
+                    const float lj[4] = {it.x - a * w4.x, it.y - a * w4.y, it.z - a * w4.z, it.w - a * w4.w};
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) {
+                        if (lj[i] <= thr) {
+                            ++nv;
+                            only = grp * 4u + (uint32_t)i;
+                            inwin |= 1ull << (4u * e + (uint32_t)i);
+                        }
                     }
                 }
                 const bool finite = table_ok && (x2 < 1e30f) && (m < 1e30f) && (m > -1e30f) && (kmag < 1e30f);
                 bool is_ovf = valid && (ovf || !finite || nv == 0u);
+                if (is_ovf) atomicAdd(&p.counts[ovf ? 4 : (!finite ? 5 : 6)], 1u);   // diagnostics (PQV_TRACE): why the row left the filter
                 bool is_amb = valid && !is_ovf && nv > 1u;
-                if (valid && !is_ovf && nv == 1u) p.assign[row] = only;
+                if (valid && !is_ovf && nv == 1u) p.assign[row] = p.perm ? __ldg(p.perm + only) : only;
                 // (row, candidate) pairs of the ambiguous rows: warp-aggregated reservation
                 const uint32_t want = is_amb ? nv : 0u;
                 uint32_t incl = want;
@@ -885,16 +986,18 @@ struct AssignEpi {
                 if (is_amb) {
                     // pass 2: a reservation that does not fit leaves sentinels behind and the row takes the full scan
                     uint32_t slot = pbase + incl - want;
-                    for (uint32_t e = 0; e < cnt + ocnt; ++e) {
-                        const uint2 it = e < cnt ? mine[e * ETHREADS] : other[(e - cnt) * ETHREADS];
-                        if (__uint_as_float(it.x) <= thr) {
-                            if (slot < p.pair_cap) p.pairs[slot] = fits ? make_uint2((uint32_t)row, it.y) : make_uint2(NONE, NONE);
-                            ++slot;
-                        }
+                    for (u64 bits = inwin; bits; bits &= bits - 1ull) {
+                        const uint32_t b = (uint32_t)__ffsll((long long)bits) - 1u, e = b >> 2;
+                        const uint32_t grp = e < cnt ? group_of(stack, cnt, e) : group_of(ostack, ocnt, e - cnt);
+                        const uint32_t col = grp * 4u + (b & 3u);
+                        if (slot < p.pair_cap)
+                            p.pairs[slot] = fits ? make_uint2((uint32_t)row, p.perm ? __ldg(p.perm + col) : col) : make_uint2(NONE, NONE);
+                        ++slot;
                     }
                     if (!fits) {
                         is_amb = false;
                         is_ovf = true;
+                        atomicAdd(&p.counts[7], 1u);
                     }
                 }
                 const uint32_t amb_mask = __ballot_sync(0xffffffffu, is_amb);
@@ -916,7 +1019,7 @@ struct AssignEpi {
                     p.best[row] = KEY_MAX;
                 }
             }
-            asm volatile("bar.sync %0, 64;" ::"r"(1u + q) : "memory");  // slice 1 may overwrite its list / meta for the next rows
+            asm volatile("bar.sync %0, 64;" ::"r"(1u + q) : "memory");  // slice 1 may overwrite its store / meta for the next rows
         }
     }
 };
@@ -1115,6 +1218,7 @@ struct BatchEpi {
     typedef BatchParams Params;
     static constexpr int SPLIT = 2;  // every (row, query) pair is independent: the two warps of a row just split the columns
     static constexpr uint32_t EXCH_BYTES = 0;
+    static constexpr int STAGES_SINGLE = STAGES, STAGES_PAIR = STAGES2;
     static __device__ __forceinline__ void finish(uint32_t *counter, const Params &p) {
         if (MODE == BATCH_FILTER) p.region_count[blockIdx.x] = min(*counter, p.region_cap);
     }

@@ -198,7 +198,7 @@ template <class Epi, int KIND, bool PAIR>
 int tc_launch_inst(uint32_t grid, cudaStream_t st, const CUtensorMap &tmA, const CUtensorMap &tmB, const pqv::tc::GemmShape &shape,
                    const typename Epi::Params &p) {
     namespace T = pqv::tc;
-    constexpr size_t smem = PAIR ? T::smem_bytes_pair(Epi::EXCH_BYTES) : T::smem_bytes_single(Epi::EXCH_BYTES);
+    constexpr size_t smem = PAIR ? T::smem_bytes_pair(Epi::STAGES_PAIR, Epi::EXCH_BYTES) : T::smem_bytes_single(Epi::STAGES_SINGLE, Epi::EXCH_BYTES);
     static_assert(smem <= 227 * 1024, "tensor-core kernel exceeds the shared memory of an SM");
     static std::once_flag once;
     static cudaError_t attr_err = cudaSuccess;
@@ -241,6 +241,8 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     PQV_TRY(D.tc_wc.ensure(cn_len / 32));
     if (!sv) PQV_TRY(D.tc_stats.ensure(n));
     PQV_TRY(D.tc_u32.ensure(16));
+    PQV_TRY(D.tc_perm.ensure(C));
+    PQV_TRY(D.tc_okeys.ensure(C));
     PQV_TRY(D.tc_amb_rows.ensure(n));
     PQV_TRY(D.tc_pairs.ensure(pair_cap64));
     PQV_TRY(D.tc_best.ensure(n));
@@ -259,12 +261,28 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     // operand scale of the centred table: bounds[5] = max |c - mu| (fp16 only), then the power of two derived from it (1 for tf32)
     if (sv) T::centroid_absmax_kernel<<<(uint32_t)D.sm_count, 256, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, bounds + 5);
     pqv::half16::scale_from_absmax_kernel<<<1, 32, 0, D.stream>>>(bounds + 5, reinterpret_cast<float *>(bounds + 5));
+    // column order of the filter: ascending |c - mu|^2 (pqv_tc.cuh, centroid_order_kernel)
+    const uint32_t *perm = nullptr;
+    static const bool order_off = getenv("PQV_ASSIGN_ORDER") && !strcmp(getenv("PQV_ASSIGN_ORDER"), "off");
+    if (C <= T::ORDER_MAX_C && C > 1 && !order_off) {
+        uint32_t cp2 = 2;
+        while (cp2 < C) cp2 <<= 1;
+        static std::once_flag order_once;
+        static cudaError_t order_err = cudaSuccess;
+        std::call_once(order_once, [] {
+            order_err = cudaFuncSetAttribute(T::centroid_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T::ORDER_MAX_C * 8));
+        });
+        CU_TRY(order_err);
+        T::centroid_spread_kernel<<<C, 128, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, D.tc_okeys.p);
+        T::centroid_order_kernel<<<1, 1024, (size_t)cp2 * 8, D.stream>>>(D.tc_okeys.p, C, cp2, D.tc_perm.p);
+        perm = D.tc_perm.p;
+    }
     if (sv) {
         T::centroid_prep_kernel<T::KIND_F16><<<cn_len, 128, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, D.tc_bp.p, D.tc_cn.p,
-                                                                          D.tc_cn.p + cn_len, D.tc_wc.p, cn_len, bounds, sv->g);
+                                                                          D.tc_cn.p + cn_len, D.tc_wc.p, cn_len, bounds, sv->g, perm);
     } else {
         T::centroid_prep_kernel<T::KIND_TF32><<<cn_len, 128, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, D.tc_bp.p, D.tc_cn.p,
-                                                                           D.tc_cn.p + cn_len, D.tc_wc.p, cn_len, bounds, nullptr);
+                                                                           D.tc_cn.p + cn_len, D.tc_wc.p, cn_len, bounds, nullptr, perm);
         T::row_stats_kernel<<<(uint32_t)D.sm_count * 8, 256, 0, D.stream>>>(d_rows, n, dim, D.tc_mu.p, D.tc_stats.p);
     }
     CU_TRY(cudaGetLastError());
@@ -275,6 +293,7 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     p.wv = D.tc_cn.p + cn_len;
     p.wc = reinterpret_cast<const float *>(D.tc_wc.p);
     p.bounds = bounds;
+    p.perm = perm;
     p.scale_a = sv ? &sv->g->scale : nullptr;
     p.assign = d_out;
     p.counts = counts;
