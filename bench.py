@@ -383,9 +383,9 @@ def scan_leg(env, P, ctx, n, dim, k, steps, warmup, exchange_pref, peaks, sample
         res = search(queries[warmup + i])
         t = ctx.last_timing()
         e2e_launches += int(t["launches"])
-        if exchange == "p2p":   # query in; the exchanged block of all ranks out
+        if exchange == "p2p":   # query in; header + the live candidate keys of all ranks, written to pinned host memory by the pack kernel
             h2d += dim * 4
-            d2h += world * (sharded.cap + 1) * 8
+            d2h += (2 + world + int(t["entrants"])) * 8
         else:
             h2d += dim * 4 + (sharded.cap + 1) * 8 * (world > 1)
             d2h += 8 * (1 + max(t["entrants"], 8192)) + (sharded.last_gather_bytes if world > 1 else 0)
@@ -425,8 +425,8 @@ def scan_leg(env, P, ctx, n, dim, k, steps, warmup, exchange_pref, peaks, sample
                     "d2h_bytes_per_step": d2h // steps, "ms_per_step": e2e_s * 1e3, "global_qps": 1.0 / e2e_s,
                     "gpu_launches": e2e_launches, "exchange": exchange,
                     "path": ("pqv_l2_topk: host query in, host (row_idx, distance) out" if world == 1 else
-                             ("pqv_l2_topk_candidates_p2p (host query in, union of all ranks' candidate keys out) + "
-                              "pqv_replay_candidates" if exchange == "p2p" else
+                             ("pqv_l2_topk_p2p: host query in, host (row_idx, distance) out; scan + NVLink peer-write "
+                              "candidate exchange + heap replay in one native call" if exchange == "p2p" else
                               "pqv_l2_topk_candidates (host query in, host candidate keys out) + one all-gather + "
                               "pqv_replay_candidates"))},
             "gpu_launches": dev_launches,

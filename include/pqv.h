@@ -203,8 +203,8 @@ PQV_API int pqv_replay_candidates(const uint64_t *keys, uint64_t n_keys, const u
  * (pqv_peer_exchange_create -> a 64-byte CUDA IPC handle), the handles travel once through whatever channel the host
  * side has (torch.distributed here), pqv_peer_exchange_open maps the peers' buffers.  pqv_l2_topk_candidates_p2p then
  * runs scan -> filter -> a tail kernel that WRITES this rank's candidates into every peer's buffer and publishes a
- * sequence flag -> a kernel that waits for the peers' flags -> one read-back of the union: no collective launch and no
- * extra host round trip per query.  All ranks must call it the same number of times, in the same order.
+ * sequence flag -> a kernel that waits for the peers' flags and packs the union of the live keys into page-locked host
+ * memory: no collective launch, no copy call and no extra host round trip per query.  All ranks must call it the same number of times, in the same order.
  * out_keys[0 .. *out_count) = the union in rank order; *out_overflow = 1 (nothing written) when some rank had more than
  * cap_keys candidates -- every rank sees the same counts, so all of them fall back to pqv_l2_topk_candidates together. */
 PQV_API int pqv_peer_exchange_create(pqv_ctx *ctx, uint32_t world, uint32_t rank, uint32_t cap_keys, uint8_t *out_handle64);
@@ -212,6 +212,12 @@ PQV_API int pqv_peer_exchange_open(pqv_ctx *ctx, const uint8_t *handles /* world
 PQV_API int pqv_l2_topk_candidates_p2p(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags,
                                        uint32_t pos_base, uint64_t *out_keys, uint64_t cap_total, uint64_t *out_count,
                                        uint32_t *out_overflow);
+/* One rank's whole sharded search in one call: the exchange above followed by the reference heap replay over the union
+ * (= pqv_l2_topk_candidates_p2p + pqv_replay_candidates; TopkBuilder::search's re-rank, src/ivf/search.rs:112-141, with the
+ * rows spread over the ranks).  Every rank passes the same query and receives the same bit-exact (row_idx, distance) list;
+ * row_idx = pos_base + local row.  *out_overflow = 1 (nothing else written) as above. */
+PQV_API int pqv_l2_topk_p2p(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t pos_base,
+                            uint32_t *out_row_idx, float *out_dist, uint32_t *out_count, uint32_t *out_overflow);
 
 /* Batched variant (config C5: many queries, rows sharded over the ranks).  pqv_l2_topk_batch_keys answers the batch
  * over this rank's slice in one tensor-core pass and returns, per query, the k + 1 smallest

@@ -339,6 +339,19 @@ class Dataset:
                                                _ptr(keys, C.c_uint64), cap_total, C.byref(cnt), C.byref(ovf)))
         return None if ovf.value else keys[:cnt.value]
 
+    def l2_topk_p2p(self, query, k: int, flags: int = N.PQV_SQRT, pos_base: int = 0):
+        """This rank's whole sharded search in one call (pqv_l2_topk_p2p): scan, NVLink candidate exchange, heap replay.
+        Returns (row_idx, dist) -- identical on every rank -- or None when a rank overflowed its slot."""
+        q = _f32(query)
+        if q.size != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.size}")
+        rows = np.zeros(max(k, 1), dtype=np.uint32)
+        dist = np.zeros(max(k, 1), dtype=np.float32)
+        cnt, ovf = C.c_uint32(), C.c_uint32()
+        _check(_lib.pqv_l2_topk_p2p(self.ctx._h, self.handle, _ptr(q, C.c_float), k, flags, pos_base, _ptr(rows, C.c_uint32),
+                                    _ptr(dist, C.c_float), C.byref(cnt), C.byref(ovf)))
+        return None if ovf.value else (rows[:cnt.value], dist[:cnt.value])
+
     def l2_topk_batch_keys(self, queries, k: int, flags: int = N.PQV_SQRT, pos_base: int = 0):
         """Per-rank half of a sharded batched search: (keys [nq, k+1] u64, counts [nq] u32), see pqv.h."""
         q = _f32(queries)

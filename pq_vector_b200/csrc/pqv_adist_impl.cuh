@@ -33,10 +33,9 @@ int adist_launch(DeviceState &D, const float *d_data, u64 n, uint32_t dim, const
         auto *fn = pqv::array_distance_kernel<METRIC, VEC2, QS>;                                                             \
         static int occ = 0;  /* CTAs per SM at this shared-memory size; the grid is persistent */                           \
         static size_t occ_smem = 0;                                                                                          \
+        PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(fn), smem));                                                  \
         if (!occ || occ_smem != smem) {                                                                                      \
-            attr_err = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);                     \
-            if (attr_err == cudaSuccess)                                                                                     \
-                attr_err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pqv::ADIST_WARPS * 32, smem);             \
+            attr_err = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, fn, pqv::ADIST_WARPS * 32, smem);                 \
             if (attr_err != cudaSuccess) break;                                                                              \
             if (occ < 1) occ = 1;                                                                                            \
             occ_smem = smem;                                                                                                 \

@@ -632,6 +632,24 @@ struct pqv_ctx {
 
 namespace {
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is per DEVICE and sticky per kernel: remember the largest size set for
+// (current device, kernel) and only ever raise it.  Every launch that needs more than 48 KB of dynamic shared memory goes
+// through here (a context may drive several devices, and the same kernel is then launched on each of them).
+static int ensure_dyn_smem(const void *kern, size_t smem) {
+    static std::mutex mu;
+    static std::map<std::pair<int, const void *>, size_t> raised;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::mutex> lk(mu);
+    size_t &cur = raised[{dev, kern}];
+    if (smem > cur) {
+        const cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return fail(PQV_ECUDA, "cudaFuncSetAttribute(%zu bytes of dynamic shared memory): %s", smem, cudaGetErrorString(e));
+        cur = smem;
+    }
+    return PQV_OK;
+}
+
 struct DevGuard {
     int prev = -1;
     explicit DevGuard(int dev) {
@@ -665,15 +683,8 @@ struct ScanGeom {
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is sticky per kernel: only ever raise it
 template <int ORDER, bool VEC4, bool GATHER>
 int scan_ensure_smem_attr(size_t smem) {
-    static std::mutex mu;
-    static size_t attr_smem = 0;
-    std::lock_guard<std::mutex> lk(mu);
-    if (smem > attr_smem) {
-        auto kern = pqv::l2_scan_topk_kernel<ORDER, VEC4, GATHER, SCAN_WARPS>;
-        CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_smem = smem;
-    }
-    return PQV_OK;
+    auto kern = pqv::l2_scan_topk_kernel<ORDER, VEC4, GATHER, SCAN_WARPS>;
+    return ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem);
 }
 
 template <int ORDER, bool VEC4, bool GATHER>
@@ -713,7 +724,7 @@ static const ScanVariant kVariants[] = {{8, 1, 2}, {16, 1, 2}, {4, 1, 3}, {4, 2,
 template <int RB, int CBV, int MINB>
 int scan_variant_go(const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStream_t st, int *occ_out) {
     auto kern = pqv::l2_scan_topk_kernel<0, true, false, SCAN_WARPS, RB, CBV, MINB>;
-    CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
     if (occ_out) {
         CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, SCAN_WARPS * 32, smem));
         return PQV_OK;
@@ -918,19 +929,42 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
         const float *d_data;
         const uint32_t *d_ids;
         uint32_t pos_base;
+        const std::vector<uint32_t> *gpos;  // multi-shard gather: position in the caller's candidate sequence of local candidate i
     };
     std::vector<Launched> launched;
 
-    // gathered search runs on the shard that owns the table; multi-shard gather splits ids by owner
+    // A gathered search over a table spread over several devices: every shard scans the candidates it owns (local row
+    // indices, in sequence order) and their keys are moved back to the positions of the caller's sequence, so the replay
+    // below sees exactly what a single device would have produced.
+    const bool split = gather && ds.shards.size() > 1;
+    std::vector<std::vector<uint32_t>> loc, gpos;
+    if (split) {
+        if (d_cand) return fail(PQV_EINVAL, "device-resident candidate lists need a single-device dataset");
+        loc.resize(ds.shards.size());
+        gpos.resize(ds.shards.size());
+        for (u64 i = 0; i < n_ids; ++i) {
+            const uint32_t r = row_ids[i];
+            size_t si = 0;
+            while (si + 1 < ds.shards.size() && r >= ds.shards[si].first_row + ds.shards[si].n_rows) ++si;
+            loc[si].push_back((uint32_t)(r - ds.shards[si].first_row));
+            gpos[si].push_back((uint32_t)i);
+        }
+    }
+
     for (size_t si = 0; si < ds.shards.size(); ++si) {
         Shard &sh = ds.shards[si];
         DeviceState &D = ctx->devs[sh.di];
         DevGuard guard(D.dev);
         u64 n = 0;
         const uint32_t *d_ids = nullptr;
-        if (gather) {
-            if (ds.shards.size() != 1)
-                return fail(PQV_EINVAL, "pqv_l2_topk_gather needs a single-device dataset (got %zu shards)", ds.shards.size());
+        if (split) {
+            n = loc[si].size();
+            if (n) {
+                PQV_TRY(D.d_row_ids.ensure(n));
+                CU_TRY(cudaMemcpyAsync(D.d_row_ids.p, loc[si].data(), n * 4, cudaMemcpyHostToDevice, D.stream));
+                d_ids = D.d_row_ids.p;
+            }
+        } else if (gather) {
             n = n_ids;
             if (n && d_cand) {
                 d_ids = d_cand;
@@ -958,9 +992,15 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
         ScanGeom g;
         const uint32_t pos_base = gather ? 0u : (uint32_t)sh.first_row + pos_offset;
         PQV_TRY(enqueue_scan(ctx, D, sh.d_data, d_ids, n, ds.dim, D.d_query.p, k, order, pos_base, nullptr, D.final_topk.p,
-                             D.ent_out.p, cap, si == 0, &g));
-        launched.push_back({&D, g, cap, n, sh.d_data, d_ids, pos_base});
+                             D.ent_out.p, cap, launched.empty(), &g));  // the first launch carries the timing events
+        launched.push_back({&D, g, cap, n, sh.d_data, d_ids, pos_base, split ? &gpos[si] : nullptr});
     }
+    // keys of one launch: local candidate index -> position in the caller's sequence
+    auto to_sequence = [](u64 *keys, size_t n_keys, const std::vector<uint32_t> *map) {
+        if (!map) return;
+        for (size_t i = 0; i < n_keys; ++i)
+            if (keys[i] != pqv::KEY_MAX) keys[i] = (keys[i] & 0xFFFFFFFF00000000ull) | (*map)[key_pos(keys[i])];
+    };
     if (trace) tt[1] = trace_now_ms();
     // collect
     for (auto &L : launched) {
@@ -970,8 +1010,10 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
             PQV_TRY(D.h_final.ensure(PQV_MAX_K));
             CU_TRY(cudaMemcpyAsync(D.h_final.p, D.final_topk.p, (size_t)L.g.kcap * 8, cudaMemcpyDeviceToHost, D.stream));
             CU_TRY(cudaStreamSynchronize(D.stream));
+            to_sequence(D.h_final.p, L.g.kcap, L.gpos);
             finals.insert(finals.end(), D.h_final.p, D.h_final.p + L.g.kcap);
         } else {
+            const size_t e0 = entrants.size();
             bool overflow = false;
             PQV_TRY(fetch_entrants(D, D.ent_out.p, L.cap, entrants, &overflow));
             if (overflow) {
@@ -988,6 +1030,7 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
                 PQV_TRY(fetch_entrants(D, D.ent_out.p, cap2, entrants, &overflow));
                 if (overflow) return fail(PQV_ECUDA, "entrant buffer overflow after regrow");
             }
+            to_sequence(entrants.data() + e0, entrants.size() - e0, L.gpos);
         }
     }
     if (trace) tt[2] = trace_now_ms();
@@ -1022,7 +1065,18 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
             dist.resize(base + L.n);
             CU_TRY(cudaMemcpyAsync(dist.data() + base, D.d_dist.p, L.n * 4, cudaMemcpyDeviceToHost, D.stream));
             CU_TRY(cudaStreamSynchronize(D.stream));
-            for (u64 i = 0; i < L.n; ++i) poses.push_back(L.pos_base + (uint32_t)i);
+            for (u64 i = 0; i < L.n; ++i) poses.push_back(L.gpos ? (*L.gpos)[i] : L.pos_base + (uint32_t)i);
+        }
+        if (split) {  // the reference loop walks the caller's sequence: back into that order
+            std::vector<u64> ord(poses.size());
+            for (size_t i = 0; i < poses.size(); ++i) ord[i] = ((u64)poses[i] << 32) | i;
+            std::sort(ord.begin(), ord.end());
+            std::vector<float> d2(dist.size());
+            for (size_t i = 0; i < ord.size(); ++i) {
+                d2[i] = dist[(uint32_t)ord[i]];
+                poses[i] = (uint32_t)(ord[i] >> 32);
+            }
+            dist.swap(d2);
         }
         tm.entrants = (uint32_t)dist.size();
         ctx->last = tm;
@@ -1066,6 +1120,139 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
 #include "pqv_tc_host.cuh"
 
 static void pqv_free_all_indexes(pqv_ctx *ctx);
+
+// Rows `ids` (global, any order) of a table spread over several devices, as one dense n x dim block on device D0 (d_out):
+// every shard gathers the rows it owns on its own device, the pieces travel to D0 (peer copy) and are put in the caller's
+// order there.  The k-means sample of pqv_ivf_build (src/ivf/index.rs:222-242) over a multi-device table.
+static int gather_rows_multi(pqv_ctx *ctx, Dataset &ds, const uint32_t *ids, u64 n_ids, DeviceState &D0, float *d_out) {
+    const uint32_t dim = ds.dim;
+    const size_t ns = ds.shards.size();
+    std::vector<std::vector<uint32_t>> loc(ns);
+    std::vector<uint32_t> inv(n_ids);  // d_out[j] = staging[inv[j]]
+    std::vector<u64> cnt(ns, 0), off(ns + 1, 0);
+    std::vector<uint8_t> owner(n_ids);
+    for (u64 i = 0; i < n_ids; ++i) {
+        size_t si = 0;
+        while (si + 1 < ns && ids[i] >= ds.shards[si].first_row + ds.shards[si].n_rows) ++si;
+        owner[i] = (uint8_t)si;
+        ++cnt[si];
+    }
+    for (size_t si = 0; si < ns; ++si) off[si + 1] = off[si] + cnt[si];
+    for (size_t si = 0; si < ns; ++si) loc[si].reserve(cnt[si]);
+    for (u64 i = 0; i < n_ids; ++i) {
+        const size_t si = owner[i];
+        inv[i] = (uint32_t)(off[si] + loc[si].size());
+        loc[si].push_back((uint32_t)(ids[i] - ds.shards[si].first_row));
+    }
+    DevBuf<float> staging;
+    DevBuf<uint32_t> d_inv;
+    {
+        DevGuard g0(D0.dev);
+        PQV_TRY(staging.ensure((size_t)n_ids * dim));
+        PQV_TRY(d_inv.ensure(n_ids));
+    }
+    int rc = PQV_OK;
+    for (size_t si = 0; si < ns && rc == PQV_OK; ++si) {
+        if (!cnt[si]) continue;
+        Shard &sh = ds.shards[si];
+        DeviceState &D = ctx->devs[sh.di];
+        DevGuard guard(D.dev);
+        rc = D.d_row_ids.ensure(cnt[si]);
+        if (!rc) rc = D.d_tmp_rows.ensure((size_t)cnt[si] * dim);
+        if (rc) break;
+        cudaError_t e = cudaMemcpyAsync(D.d_row_ids.p, loc[si].data(), cnt[si] * 4, cudaMemcpyHostToDevice, D.stream);
+        if (e == cudaSuccess) {
+            pqv::gather_rows_kernel<<<D.sm_count * 8, 256, 0, D.stream>>>(sh.d_data, D.d_row_ids.p, cnt[si], dim, D.d_tmp_rows.p);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess)
+            e = cudaMemcpyPeerAsync(staging.p + off[si] * dim, D0.dev, D.d_tmp_rows.p, D.dev, (size_t)cnt[si] * dim * 4, D.stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D.stream);
+        if (e != cudaSuccess) rc = fail(PQV_ECUDA, "gathering rows of shard %zu failed: %s", si, cudaGetErrorString(e));
+    }
+    if (rc == PQV_OK) {
+        DevGuard g0(D0.dev);
+        cudaError_t e = cudaMemcpyAsync(d_inv.p, inv.data(), n_ids * 4, cudaMemcpyHostToDevice, D0.stream);
+        if (e == cudaSuccess) {
+            pqv::gather_rows_kernel<<<D0.sm_count * 8, 256, 0, D0.stream>>>(staging.p, d_inv.p, n_ids, dim, d_out);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(D0.stream);
+        if (e != cudaSuccess) rc = fail(PQV_ECUDA, "placing the gathered rows failed: %s", cudaGetErrorString(e));
+    }
+    {
+        DevGuard g0(D0.dev);
+        staging.release();
+        d_inv.release();
+    }
+    return rc;
+}
+
+// A batch over a table spread over several devices of ONE context (one process driving all GPUs): every shard answers the
+// whole batch over its own rows in one tensor-core pass (batch_topk in raw mode: the k + 1 smallest exact keys per query,
+// positions = global rows), each from its own host thread so the passes overlap, and the per-shard lists are merged as the
+// per-rank lists of the process-per-GPU form are (pqv_merge_batch_keys).  Queries the merge cannot decide (exact ties, a
+// shard that declined) stay unhandled: the caller runs them through the multi-shard single-query scan.
+static int batch_topk_sharded(pqv_ctx *ctx, Dataset &ds, const float *queries, uint32_t n_queries, uint32_t k, uint32_t flags,
+                              uint32_t *out_row_idx, float *out_dist, uint32_t *out_count, std::vector<uint8_t> &handled) {
+    const size_t ns = ds.shards.size();
+    const size_t kp = (size_t)k + 1;
+    pqv_batch_timing total{};
+    for (uint32_t q0 = 0; q0 < n_queries; q0 += BATCH_MAX_QUERIES) {
+        const uint32_t nq = std::min(BATCH_MAX_QUERIES, n_queries - q0);
+        if (nq < BATCH_MIN_QUERIES) break;
+        std::vector<u64> keys(ns * nq * kp, pqv::KEY_MAX);
+        std::vector<uint32_t> counts(ns * nq, 0xFFFFFFFFu);
+        std::vector<pqv_batch_timing> bts(ns);
+        std::vector<int> rcs(ns, PQV_OK);
+        std::vector<std::string> errs(ns);
+        auto run = [&](size_t si) {
+            Shard &sh = ds.shards[si];
+            if (sh.n_rows == 0) {
+                for (uint32_t q = 0; q < nq; ++q) counts[si * nq + q] = 0;
+                return;
+            }
+            DeviceState &D = ctx->devs[sh.di];
+            DevGuard guard(D.dev);
+            std::vector<uint8_t> part;
+            if ((reinterpret_cast<uintptr_t>(sh.d_data) & 15) != 0) return;  // counts stay "undecided"
+            rcs[si] = batch_topk(ctx, D, ds, sh.n_rows, ds.dim, queries + (size_t)q0 * ds.dim, nq, k, flags, nullptr, nullptr, nullptr,
+                                 part, keys.data() + si * nq * kp, counts.data() + si * nq, (uint32_t)sh.first_row, nullptr, &sh,
+                                 &bts[si]);
+            if (rcs[si] != PQV_OK) errs[si] = g_err;
+        };
+        std::vector<std::thread> th;
+        for (size_t si = 1; si < ns; ++si) th.emplace_back(run, si);
+        run(0);
+        for (auto &t : th) t.join();
+        for (size_t si = 0; si < ns; ++si)
+            if (rcs[si] != PQV_OK) {
+                g_err = errs[si];
+                return rcs[si];
+            }
+        std::vector<uint8_t> need(nq, 0);
+        PQV_TRY(pqv_merge_batch_keys(reinterpret_cast<const uint64_t *>(keys.data()), counts.data(), (uint32_t)ns, nq, k, flags, out_row_idx + (size_t)q0 * k,
+                                     out_dist + (size_t)q0 * k, out_count + q0, need.data()));
+        for (uint32_t q = 0; q < nq; ++q) handled[q0 + q] = need[q] ? 0 : 1;
+        total.queries += nq;
+        total.rows = ds.n_rows;
+        for (size_t si = 0; si < ns; ++si) {  // device times: the slowest shard of each phase (the shards run side by side)
+            const pqv_batch_timing &b = bts[si];
+            total.declined |= b.declined;
+            total.candidates += b.candidates;
+            total.sample_rows = std::max(total.sample_rows, b.sample_rows);
+        }
+        double pm = 0, sm = 0, fm = 0, rm = 0, tmx = 0;
+        for (const auto &b : bts) {
+            pm = std::max(pm, b.prep_ms), sm = std::max(sm, b.sample_ms), fm = std::max(fm, b.filter_ms);
+            rm = std::max(rm, b.rerank_ms), tmx = std::max(tmx, b.total_ms);
+        }
+        total.prep_ms += pm, total.sample_ms += sm, total.filter_ms += fm, total.rerank_ms += rm, total.total_ms += tmx;
+        for (uint32_t q = 0; q < nq; ++q) total.tie_queries += need[q] ? 1u : 0u;
+    }
+    ctx->last_batch = total;
+    return PQV_OK;
+}
 
 // ================================================================================================
 // C ABI
@@ -1479,7 +1666,6 @@ int pqv_dataset_read_rows(pqv_ctx *ctx, uint64_t handle, const uint32_t *row_ids
     std::lock_guard<std::mutex> lk(ctx->mu);
     Dataset *ds = find_dataset(ctx, handle);
     if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
-    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_dataset_read_rows needs a single-device dataset");
     if (n_ids == 0) return PQV_OK;
     for (u64 i = 0; i < n_ids; ++i)
         if (row_ids[i] >= ds->n_rows) return fail(PQV_EINVAL, "row %u out of range (%llu rows)", row_ids[i], (unsigned long long)ds->n_rows);
@@ -1488,6 +1674,12 @@ int pqv_dataset_read_rows(pqv_ctx *ctx, uint64_t handle, const uint32_t *row_ids
     DevGuard guard(D.dev);
     PQV_TRY(D.d_row_ids.ensure(n_ids));
     PQV_TRY(D.d_tmp_rows.ensure((size_t)n_ids * ds->dim));
+    if (ds->shards.size() > 1) {  // rows spread over several devices: collected on the first one
+        PQV_TRY(gather_rows_multi(ctx, *ds, row_ids, n_ids, D, D.d_tmp_rows.p));
+        CU_TRY(cudaMemcpyAsync(out, D.d_tmp_rows.p, (size_t)n_ids * ds->dim * 4, cudaMemcpyDeviceToHost, D.stream));
+        CU_TRY(cudaStreamSynchronize(D.stream));
+        return PQV_OK;
+    }
     CU_TRY(cudaMemcpyAsync(D.d_row_ids.p, row_ids, n_ids * 4, cudaMemcpyHostToDevice, D.stream));
     pqv::gather_rows_kernel<<<D.sm_count * 8, 256, 0, D.stream>>>(sh.d_data, D.d_row_ids.p, n_ids, ds->dim, D.d_tmp_rows.p);
     CU_TRY(cudaGetLastError());
@@ -1538,6 +1730,9 @@ int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_
         }
         ctx->last_batch = total;
     }
+    if (n_queries && ds->n_rows && ds->shards.size() > 1 && !(flags & PQV_TIES_BY_POSITION) &&
+        batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k, true))
+        PQV_TRY(batch_topk_sharded(ctx, *ds, queries, n_queries, k, flags, out_row_idx, out_dist, out_count, handled));
     for (uint32_t q = 0; q < n_queries; ++q)
         if (!handled[q])
             PQV_TRY(topk_one(ctx, *ds, queries + (size_t)q * ds->dim, nullptr, 0, k, flags, out_row_idx + (size_t)q * k,
@@ -1715,7 +1910,7 @@ int pqv_peer_exchange_create(pqv_ctx *ctx, uint32_t world, uint32_t rank, uint32
     CU_TRY(cudaMemset(px.local, 0, px.words() * 8));  // flags 0: sequence numbers start at 1
     CU_TRY(cudaMalloc((void **)&px.d_peers, (size_t)world * sizeof(u64 *)));
     CU_TRY(cudaMalloc((void **)&px.d_timeout, 4));
-    PQV_TRY(px.h_block.ensure((size_t)world * (1 + (size_t)cap_keys) + 1));
+    PQV_TRY(px.h_block.ensure((size_t)world * (1 + (size_t)cap_keys) + 2));  // flags, total, counts[world], keys
     cudaIpcMemHandle_t h;
     CU_TRY(cudaIpcGetMemHandle(&h, px.local));
     memcpy(out_handle64, &h, 64);
@@ -1747,12 +1942,13 @@ int pqv_peer_exchange_open(pqv_ctx *ctx, const uint8_t *handles) {
     return PQV_OK;
 }
 
-int pqv_l2_topk_candidates_p2p(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t pos_base,
-                               uint64_t *out_keys, uint64_t cap_total, uint64_t *out_count, uint32_t *out_overflow) {
-    if (!ctx || !query || !out_keys || !out_count || !out_overflow) return fail(PQV_EINVAL, "null argument");
-    std::lock_guard<std::mutex> lk(ctx->mu);
+// scan -> filter -> publish to every peer -> wait + pack: leaves [flags, total, counts[world], keys...] in px.h_block
+// (page-locked, written by the pack kernel itself); ctx->mu held
+static int p2p_collect(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t pos_base,
+                       u64 *out_total, uint32_t *out_overflow) {
     PeerExchange &px = ctx->peer;
     if (!px.ready) return fail(PQV_EINVAL, "the peer exchange is not set up (pqv_peer_exchange_create / _open)");
+    if (px.world > 64) return fail(PQV_ELIMIT, "at most 64 ranks per peer exchange");
     Dataset *ds = find_dataset(ctx, handle);
     if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
     PQV_TRY(check_topk_args(k, ds->dim, flags));
@@ -1772,7 +1968,6 @@ int pqv_l2_topk_candidates_p2p(pqv_ctx *ctx, uint64_t handle, const float *query
     memcpy(D.h_query.p, query, (size_t)ds->dim * 4);
     CU_TRY(cudaMemcpyAsync(D.d_query.p, D.h_query.p, (size_t)ds->dim * 4, cudaMemcpyHostToDevice, D.stream));
     CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
-    CU_TRY(cudaMemsetAsync(px.d_timeout, 0, 4, D.stream));
     ScanGeom g;
     if (ds->n_rows) {
         PQV_TRY(enqueue_scan(ctx, D, sh.d_data, nullptr, ds->n_rows, ds->dim, D.d_query.p, k, order, pos_base, nullptr,
@@ -1784,21 +1979,13 @@ int pqv_l2_topk_candidates_p2p(pqv_ctx *ctx, uint64_t handle, const float *query
         g.grid = 0;
     }
     pqv::peer_publish_kernel<<<px.world, 256, 0, D.stream>>>(D.ent_out.p, px.cap, px.d_peers, px.rank, px.world, seq);
-    pqv::peer_wait_kernel<<<1, 32, 0, D.stream>>>(px.local, px.cap, px.world, seq, px.d_timeout);
+    pqv::peer_wait_pack_kernel<<<1, 256, 0, D.stream>>>(px.local, px.cap, px.world, seq, px.h_block.p);
     CU_TRY(cudaGetLastError());
-    const size_t block_words = (size_t)px.world * (1 + (size_t)px.cap);
-    CU_TRY(cudaMemcpyAsync(px.h_block.p, px.local + (seq & 1ull) * block_words, block_words * 8, cudaMemcpyDeviceToHost, D.stream));
-    CU_TRY(cudaMemcpyAsync(px.h_block.p + block_words, px.d_timeout, 4, cudaMemcpyDeviceToHost, D.stream));
     CU_TRY(cudaStreamSynchronize(D.stream));
-    if ((uint32_t)px.h_block.p[block_words] != 0) return fail(PQV_ECUDA, "peer exchange timed out waiting for the other ranks (sequence %llu)", (unsigned long long)seq);
-    u64 total = 0;
-    *out_overflow = 0;
-    for (uint32_t r = 0; r < px.world; ++r) {
-        const u64 c = px.h_block.p[(size_t)r * (1 + px.cap)];
-        if (c > px.cap) *out_overflow = 1;  // some rank had more candidates than a slot holds: every rank sees it
-        total += std::min<u64>(c, px.cap);
-    }
-    *out_count = total;
+    const u64 *hb = px.h_block.p;
+    if (hb[0] & 1ull) return fail(PQV_ECUDA, "peer exchange timed out waiting for the other ranks (sequence %llu)", (unsigned long long)seq);
+    *out_overflow = (hb[0] & 2ull) ? 1u : 0u;  // some rank had more candidates than a slot holds: every rank sees it
+    *out_total = hb[1];
     pqv_timing tm{};
     float a = 0, b = 0;
     cudaEventElapsedTime(&a, D.ev[0], D.ev[1]);
@@ -1809,16 +1996,38 @@ int pqv_l2_topk_candidates_p2p(pqv_ctx *ctx, uint64_t handle, const float *query
     tm.scan_bytes = ds->n_rows * (u64)ds->dim * 4;
     tm.launches = 6;
     tm.grid = g.grid;
-    tm.entrants = (uint32_t)total;
+    tm.entrants = (uint32_t)hb[1];
     ctx->last = tm;
+    return PQV_OK;
+}
+
+int pqv_l2_topk_candidates_p2p(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t pos_base,
+                               uint64_t *out_keys, uint64_t cap_total, uint64_t *out_count, uint32_t *out_overflow) {
+    if (!ctx || !query || !out_keys || !out_count || !out_overflow) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    u64 total = 0;
+    PQV_TRY(p2p_collect(ctx, handle, query, k, flags, pos_base, &total, out_overflow));
+    *out_count = total;
     if (*out_overflow) return PQV_OK;
     if (total > cap_total) return fail(PQV_ELIMIT, "%llu candidate keys do not fit the caller's buffer of %llu", (unsigned long long)total, (unsigned long long)cap_total);
-    u64 o = 0;
-    for (uint32_t r = 0; r < px.world; ++r) {
-        const u64 *slot = px.h_block.p + (size_t)r * (1 + px.cap);
-        memcpy(out_keys + o, slot + 1, slot[0] * 8);
-        o += slot[0];
-    }
+    memcpy(out_keys, ctx->peer.h_block.p + 2 + ctx->peer.world, total * 8);
+    return PQV_OK;
+}
+
+// The whole sharded search of one rank in one call: pqv_l2_topk_candidates_p2p + pqv_replay_candidates.  Every rank calls
+// it with the same query and gets the same, bit-exact (row_idx, distance) list.  *out_overflow = 1 (nothing else written):
+// a rank had more candidates than a slot holds -- all ranks see it and take the collective path for this query.
+int pqv_l2_topk_p2p(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t pos_base,
+                    uint32_t *out_row_idx, float *out_dist, uint32_t *out_count, uint32_t *out_overflow) {
+    if (!ctx || !query || !out_row_idx || !out_dist || !out_count || !out_overflow) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    u64 total = 0;
+    *out_count = 0;
+    PQV_TRY(p2p_collect(ctx, handle, query, k, flags, pos_base, &total, out_overflow));
+    if (*out_overflow) return PQV_OK;
+    const u64 *keys = ctx->peer.h_block.p + 2 + ctx->peer.world;
+    std::vector<u64> ent(keys, keys + total);
+    *out_count = (uint32_t)replay_reference_heap(ent, RowMap{}, k, flags, out_row_idx, out_dist);
     return PQV_OK;
 }
 
@@ -1897,15 +2106,9 @@ static int dist_launch(DeviceState &D, const float *d_data, const uint32_t *d_id
         // short table (centroid ranking): one CTA per 32 rows instead of one warp (l2_dist_wide_kernel)
         uint32_t ts = ((dim >> 2) + 3u) & ~3u;
         if (((ts >> 2) & 1u) == 0) ts += 4;
-        static std::once_flag once;
-        static cudaError_t attr_err = cudaSuccess;
-        std::call_once(once, [] {
-            uint32_t tmax = ((WIDE_MAX_DIM >> 2) + 3u) & ~3u;
-            if (((tmax >> 2) & 1u) == 0) tmax += 4;
-            attr_err = cudaFuncSetAttribute(pqv::l2_dist_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)(32u * tmax * 4u));
-        });
-        if (attr_err != cudaSuccess) return fail(PQV_ECUDA, "l2_dist_wide_kernel attribute: %s", cudaGetErrorString(attr_err));
+        uint32_t tmax = ((WIDE_MAX_DIM >> 2) + 3u) & ~3u;
+        if (((tmax >> 2) & 1u) == 0) tmax += 4;
+        PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(pqv::l2_dist_wide_kernel), (size_t)32u * tmax * 4u));
         pqv::l2_dist_wide_kernel<<<(uint32_t)NG, 256, (size_t)32 * ts * 4, D.stream>>>(d_data, d_ids, n, dim, ts, d_vec, d_out,
                                                                                      min_update);
         CU_TRY(cudaGetLastError());
@@ -1915,11 +2118,7 @@ static int dist_launch(DeviceState &D, const float *d_data, const uint32_t *d_id
 #define DIST_GO(V, G)                                                                                        \
     do {                                                                                                     \
         auto kern = pqv::l2_dist_kernel<V, G, SCAN_WARPS>;                                                   \
-        static size_t attr_smem = 0; /* sticky per kernel: only ever raise it */                             \
-        if (smem > attr_smem) {                                                                              \
-            CU_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));      \
-            attr_smem = smem;                                                                                \
-        }                                                                                                    \
+        PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));                                \
         kern<<<grid, SCAN_WARPS * 32, smem, D.stream>>>(d_data, d_ids, n, dim, d_vec, d_out, min_update, h_mirror); \
     } while (0)
     if (vec4) {
@@ -1959,11 +2158,12 @@ static int resolve_rows(pqv_ctx *ctx, uint64_t handle, const float *rows, u64 n,
 }
 
 // the 16-bit shadow of a resident table for an assignment sweep over its first n rows (null view: none -- layout, memory)
-static int sweep_shadow(DeviceState &D, Dataset *ds, const float *d_rows, u64 n, ShadowView *sv, bool *have, bool *built) {
+static int sweep_shadow(DeviceState &D, Dataset *ds, const float *d_rows, u64 n, ShadowView *sv, bool *have, bool *built,
+                        Shard *sh = nullptr) {
     *have = false;
     *built = false;
     if (!ds || n < 2048 || !shadow_layout_ok(ds->dim, d_rows)) return PQV_OK;  // small sweeps take the SIMT kernel anyway
-    const int rc = shard_shadow(D, *ds, ds->shards[0], sv, built);
+    const int rc = shard_shadow(D, *ds, sh ? *sh : ds->shards[0], sv, built);
     if (rc == PQV_OK) *have = true;
     else if (rc != PQV_ENOMEM) return rc;
     return PQV_OK;
@@ -1977,6 +2177,57 @@ int pqv_kmeans_assign(pqv_ctx *ctx, uint64_t handle, const float *rows, uint64_t
     std::lock_guard<std::mutex> lk(ctx->mu);
     if (out_sizes) memset(out_sizes, 0, sizeof(uint64_t) * n_clusters);
     if (n == 0) return PQV_OK;
+    if (!rows) {
+        // a resident table spread over several devices: every shard sweeps its own rows against its own copy of the
+        // centroids; all sweeps are enqueued before the first one is waited for
+        Dataset *mds = find_dataset(ctx, handle);
+        if (mds && mds->shards.size() > 1) {
+            if (mds->dim != dim) return fail(PQV_EINVAL, "dimension mismatch: dataset has %u, call has %u", mds->dim, dim);
+            if (n > mds->n_rows) return fail(PQV_EINVAL, "n = %llu exceeds the dataset's %llu rows", (unsigned long long)n, (unsigned long long)mds->n_rows);
+            struct Piece {
+                DeviceState *D;
+                u64 off, cnt;
+                int path, kind;
+                bool built;
+                uint32_t h_counts[8];
+            };
+            std::vector<Piece> pieces;
+            pieces.reserve(mds->shards.size());
+            for (Shard &sh : mds->shards) {
+                if (sh.first_row >= n || sh.n_rows == 0) continue;
+                const u64 cnt = std::min<u64>(sh.n_rows, n - sh.first_row);
+                DeviceState &D = ctx->devs[sh.di];
+                DevGuard guard(D.dev);
+                PQV_TRY(D.d_centroids.ensure((size_t)n_clusters * dim));
+                CU_TRY(cudaMemcpyAsync(D.d_centroids.p, centroids, (size_t)n_clusters * dim * 4, cudaMemcpyHostToDevice, D.stream));
+                PQV_TRY(D.d_assign.ensure(cnt));
+                pieces.push_back(Piece{&D, sh.first_row, cnt, 0, 0, false, {0, 0, 0, 0, 0, 0, 0, 0}});
+                Piece &P = pieces.back();
+                ShadowView sv;
+                bool have_sv = false, built = false, built2 = false;
+                if (cnt == sh.n_rows) PQV_TRY(sweep_shadow(D, mds, sh.d_data, cnt, &sv, &have_sv, &built, &sh));
+                PQV_TRY(assign_dispatch(D, sh.d_data, cnt, dim, D.d_centroids.p, n_clusters, D.d_assign.p, &P.path, true,
+                                        have_sv ? &sv : nullptr, &P.kind, &built2));
+                P.built = built || built2;
+            }
+            // read-backs only now: a copy into pageable memory holds the host until it is done, and the other shards' sweeps
+            // should be running by then
+            bool first = true;
+            for (Piece &P : pieces) {
+                DeviceState &D = *P.D;
+                DevGuard guard(D.dev);
+                if (P.path == ASSIGN_TC)
+                    CU_TRY(cudaMemcpyAsync(P.h_counts, D.tc_u32.p + TC_COUNTS_OFFSET, sizeof P.h_counts, cudaMemcpyDeviceToHost, D.stream));
+                CU_TRY(cudaMemcpyAsync(out_assign + P.off, D.d_assign.p, P.cnt * 4, cudaMemcpyDeviceToHost, D.stream));
+                CU_TRY(cudaStreamSynchronize(P.D->stream));
+                record_assign_timing(ctx, *P.D, P.path, P.cnt, P.h_counts, first, P.kind, P.built);
+                first = false;
+            }
+            if (out_sizes)
+                for (u64 i = 0; i < n; ++i) out_sizes[out_assign[i]]++;
+            return PQV_OK;
+        }
+    }
     // host rows are streamed in bounded pieces so scratch stays small
     const u64 piece = rows ? std::max<u64>(1, (u64)(256u << 20) / ((u64)dim * 4)) : n;
     for (u64 off = 0; off < n; off += piece) {
@@ -2146,19 +2397,10 @@ int pqv_centroid_rank(pqv_ctx *ctx, const float *centroids, uint32_t n_clusters,
     const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(D.d_centroids.p) & 15) == 0);
     const size_t smem = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)SCAN_WARPS * pqv::TileCfg<0, true>::TILE_FLOATS * 4;
     const u64 NG = ((u64)n_clusters + 31) / 32;
-    static size_t attr_dist[2] = {0, 0};
-    static size_t attr_rank = 0;
     auto *k_vec = pqv::l2_dist_batch_kernel<true, SCAN_WARPS>;
     auto *k_sca = pqv::l2_dist_batch_kernel<false, SCAN_WARPS>;
-    if (smem > attr_dist[vec4]) {
-        if (vec4) CU_TRY(cudaFuncSetAttribute(k_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else CU_TRY(cudaFuncSetAttribute(k_sca, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        attr_dist[vec4] = smem;
-    }
-    if ((size_t)cp2 * 8 > attr_rank) {
-        CU_TRY(cudaFuncSetAttribute(pqv::rank_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cp2 * 8)));
-        attr_rank = (size_t)cp2 * 8;
-    }
+    PQV_TRY(ensure_dyn_smem(vec4 ? reinterpret_cast<const void *>(k_vec) : reinterpret_cast<const void *>(k_sca), smem));
+    PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(pqv::rank_batch_kernel), (size_t)cp2 * 8));
     constexpr uint32_t CHUNK = 16384;  // queries per launch (gridDim.y limit, scratch size)
     const uint32_t chunk_max = std::min(n_queries, CHUNK);
     PQV_TRY(D.d_tmp_rows.ensure((size_t)chunk_max * dim));

@@ -132,15 +132,9 @@ int csr_device(DeviceState &D, const uint32_t *d_assign, u64 n, uint32_t C, u64 
     PQV_TRY(D.csr_counts.ensure((size_t)C * NB));
     PQV_TRY(D.csr_totals.ensure(C));
     const size_t smem = (size_t)C * 4;
-    static std::mutex mu;
-    static size_t attr_smem = 48 * 1024;
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        if (smem > attr_smem) {
-            CU_TRY(cudaFuncSetAttribute(pqv::csr_count_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            CU_TRY(cudaFuncSetAttribute(pqv::csr_scatter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            attr_smem = smem;
-        }
+    if (smem > 48 * 1024) {
+        PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(pqv::csr_count_kernel), smem));
+        PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(pqv::csr_scatter_kernel), smem));
     }
     pqv::csr_count_kernel<<<NB, 256, smem, D.stream>>>(d_assign, n, (uint32_t)R, C, NB, D.csr_counts.p);
     pqv::csr_scan_kernel<<<C, 256, 0, D.stream>>>(D.csr_counts.p, NB, D.csr_totals.p);
@@ -282,13 +276,7 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
     const uint32_t C = ix.n_clusters, np = std::min(nprobe, C), cp2 = pow2ceil(C);
     const u64 n_bound = ro ? std::min<u64>(ix.n_ids, ro->max_candidates) : ix.n_ids;
     const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
-    static std::once_flag attr_once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(attr_once, [] {
-        attr_err = cudaFuncSetAttribute(pqv::ivf_rank_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(IVF_RANK_MAX_C * 8));
-    });
-    if (attr_err != cudaSuccess) return fail(PQV_ECUDA, "ivf_rank_kernel attribute: %s", cudaGetErrorString(attr_err));
+    PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(pqv::ivf_rank_kernel), (size_t)IVF_RANK_MAX_C * 8));
     PQV_TRY(D.d_query.ensure(ix.dim));
     PQV_TRY(D.h_query.ensure(ix.dim));
     PQV_TRY(D.final_topk.ensure(PQV_MAX_K));
@@ -639,7 +627,7 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
     std::lock_guard<std::mutex> lk(ctx->mu);
     Dataset *ds = find_dataset(ctx, handle);
     if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
-    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_build needs a single-device dataset");
+    const bool multi = ds->shards.size() > 1;  // table spread over several devices of this context
     const u64 n = ds->n_rows;
     const uint32_t dim = ds->dim;
     if (n == 0) return fail(PQV_EINVAL, "Cannot build IVF index with zero vectors");  // index.rs:157-159
@@ -675,7 +663,20 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
     // ---- training sample (index.rs:182-187, 222-242)
     const float *d_sample = sh.d_data;
     const u64 ns = sample_size;
-    if (sample_size != n) {
+    if (multi) {
+        // the sample (or, for a tiny table, every row) is collected on the first device; training runs there
+        std::vector<uint32_t> sidx;
+        if (sample_size != n) {
+            SplitMix64 rng_s(seed);
+            sidx = sample_indices(rng_s, n, sample_size);
+        } else {
+            sidx.resize(n);
+            for (u64 i = 0; i < n; ++i) sidx[i] = (uint32_t)i;
+        }
+        IVF_TRY(D.d_tmp_rows.ensure((size_t)ns * dim));
+        IVF_TRY(gather_rows_multi(ctx, *ds, sidx.data(), ns, D, D.d_tmp_rows.p));
+        d_sample = D.d_tmp_rows.p;
+    } else if (sample_size != n) {
         SplitMix64 rng_s(seed);
         std::vector<uint32_t> sidx = sample_indices(rng_s, n, sample_size);
         IVF_TRY(D.d_row_ids.ensure(ns));
@@ -699,7 +700,33 @@ int pqv_ivf_build(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters_or_0, uint3
     static const bool trace = getenv("PQV_TRACE") != nullptr;
     double tf[4] = {now_ms(), 0, 0, 0};
     IVF_TRY(D.d_assign.ensure(n));
-    {
+    if (multi) {
+        // every shard assigns its own rows against its own copy of the centroids (all sweeps enqueued before the first wait);
+        // the assignments meet on the first device, where the lists are built
+        IVF_CU(cudaStreamSynchronize(D.stream));  // centroids final
+        for (Shard &s2 : ds->shards) {
+            if (!s2.n_rows) continue;
+            DeviceState &D2 = ctx->devs[s2.di];
+            DevGuard g2(D2.dev);
+            if (&D2 != &D) {
+                IVF_TRY(D2.d_centroids.ensure((size_t)C * dim));
+                IVF_CU(cudaMemcpyPeerAsync(D2.d_centroids.p, D2.dev, D.d_centroids.p, D.dev, (size_t)C * dim * 4, D2.stream));
+                IVF_TRY(D2.d_assign.ensure(s2.n_rows));
+            }
+            ShadowView fsv;
+            bool have_fsv = false, built = false;
+            IVF_TRY(sweep_shadow(D2, ds, s2.d_data, s2.n_rows, &fsv, &have_fsv, &built, &s2));
+            uint32_t *dst = (&D2 == &D) ? D.d_assign.p + s2.first_row : D2.d_assign.p;
+            IVF_TRY(assign_device(D2, s2.d_data, s2.n_rows, dim, D2.d_centroids.p, C, dst, have_fsv ? &fsv : nullptr));
+            if (&D2 != &D)
+                IVF_CU(cudaMemcpyPeerAsync(D.d_assign.p + s2.first_row, D.dev, D2.d_assign.p, D2.dev, s2.n_rows * 4, D2.stream));
+        }
+        for (Shard &s2 : ds->shards) {
+            DeviceState &D2 = ctx->devs[s2.di];
+            DevGuard g2(D2.dev);
+            IVF_CU(cudaStreamSynchronize(D2.stream));
+        }
+    } else {
         // the table's own shadow: stays with the shard for later sweeps and batched searches
         ShadowView fsv;
         bool have_fsv = false, built = false;
@@ -930,7 +957,8 @@ int pqv_ivf_candidate_rows(pqv_ctx *ctx, uint64_t index, const float *query, uin
 static int ivf_search_one(pqv_ctx *ctx, Dataset *ds, DeviceState &D, IvfIndex *ix, const float *query, uint32_t k,
                           uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
     PQV_TRY(index_make_resident(D, *ix));
-    if (ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids) {
+    const bool multi = ds->shards.size() > 1;  // table spread over several devices: ranking here, candidates split by owner (topk_one)
+    if (!multi && ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids) {
         bool done = false;
         PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, query, k, nprobe, flags, out_row_idx, out_dist, out_count, &done));
         if (done) return PQV_OK;  // otherwise: NaN distance or entrant overflow -> host-ranked path below
@@ -938,6 +966,13 @@ static int ivf_search_one(pqv_ctx *ctx, Dataset *ds, DeviceState &D, IvfIndex *i
     PQV_TRY(index_host_ids(D, *ix));
     std::vector<uint32_t> ranked;
     PQV_TRY(rank_clusters(D, *ix, query, nprobe, ranked));
+    if (multi) {
+        std::vector<uint32_t> rows;
+        for (uint32_t c : ranked) rows.insert(rows.end(), ix->ids.begin() + ix->offsets[c], ix->ids.begin() + ix->offsets[c + 1]);
+        *out_count = 0;
+        if (rows.empty()) return PQV_OK;
+        return topk_one(ctx, *ds, query, rows.data(), rows.size(), k, flags, out_row_idx, out_dist, out_count);
+    }
     const uint32_t np = (uint32_t)ranked.size();
     std::vector<u64> prefix((size_t)np + 1, 0);
     for (uint32_t r = 0; r < np; ++r) prefix[r + 1] = prefix[r] + (ix->offsets[ranked[r] + 1] - ix->offsets[ranked[r]]);
@@ -971,7 +1006,6 @@ int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *q
     if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
     PQV_TRY(check_topk_args(k, ds->dim, flags));
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
-    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search needs a single-device dataset");
     PQV_TRY(check_index_fits(*ix, *ds));
     DeviceState &D = ctx->devs[ds->shards[0].di];
     DevGuard guard(D.dev);
@@ -1009,9 +1043,8 @@ static int ivf_batch_masked(pqv_ctx *ctx, Dataset *ds, DeviceState &D, IvfIndex 
         const size_t smem = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)SCAN_WARPS * pqv::TileCfg<0, true>::TILE_FLOATS * 4;
         auto *k_vec = pqv::l2_dist_batch_kernel<true, SCAN_WARPS>;
         auto *k_sca = pqv::l2_dist_batch_kernel<false, SCAN_WARPS>;
-        if (vec4) CU_TRY(cudaFuncSetAttribute(k_vec, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        else CU_TRY(cudaFuncSetAttribute(k_sca, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CU_TRY(cudaFuncSetAttribute(pqv::rank_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(cp2 * 8)));
+        PQV_TRY(ensure_dyn_smem(vec4 ? reinterpret_cast<const void *>(k_vec) : reinterpret_cast<const void *>(k_sca), smem));
+        PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(pqv::rank_batch_kernel), (size_t)cp2 * 8));
         PQV_TRY(D.d_tmp_rows.ensure((size_t)nq * dim));
         PQV_TRY(D.d_dist.ensure((size_t)nq * C));
         PQV_TRY(D.d_assign.ensure((size_t)nq * np));
@@ -1072,14 +1105,14 @@ int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const fl
     if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
     PQV_TRY(check_topk_args(k, ds->dim, flags));
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
-    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_ivf_search_batch needs a single-device dataset");
     PQV_TRY(check_index_fits(*ix, *ds));
     DeviceState &D = ctx->devs[ds->shards[0].di];
     DevGuard guard(D.dev);
     PQV_TRY(index_make_resident(D, *ix));
     const uint32_t C = ix->n_clusters, dim = ds->dim;
+    const bool multi = ds->shards.size() > 1;  // several devices: every query through the split single-query pipeline
     std::vector<uint8_t> handled(n_queries, 0), part;
-    for (uint32_t q0 = 0; q0 < n_queries; q0 += BATCH_MAX_QUERIES) {  // the pass' scratch grows with the batch
+    for (uint32_t q0 = 0; q0 < n_queries && !multi; q0 += BATCH_MAX_QUERIES) {  // the pass' scratch grows with the batch
         const uint32_t nq = std::min(BATCH_MAX_QUERIES, n_queries - q0);
         PQV_TRY(ivf_batch_masked(ctx, ds, D, ix, queries + (size_t)q0 * dim, nq, k, nprobe, flags, out_row_idx + (size_t)q0 * k,
                                  out_dist + (size_t)q0 * k, out_count + q0, part, nullptr, nullptr, 0));
@@ -1096,7 +1129,7 @@ int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const fl
             RowOrder ro;
             bool done = false;
             out_count[q] = 0;
-            if (ivf_fused_enabled() && C <= IVF_RANK_MAX_C && ix->n_ids)
+            if (!multi && ivf_fused_enabled() && C <= IVF_RANK_MAX_C && ix->n_ids)
                 PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, qv, k, nprobe, flags, orow, odist, out_count + q, &done, &ro));
             if (!done) {  // host-ranked selection in row order (as pqv_vector_topk_indexed)
                 PQV_TRY(index_host_ids(D, *ix));
@@ -1217,14 +1250,14 @@ int pqv_vector_topk_indexed_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index,
     if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
     PQV_TRY(check_topk_args(k, ds->dim, flags));
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
-    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_vector_topk_indexed_batch needs a single-device dataset");
     PQV_TRY(check_index_fits(*ix, *ds));
     DeviceState &D = ctx->devs[ds->shards[0].di];
     DevGuard guard(D.dev);
     PQV_TRY(index_make_resident(D, *ix));
     const uint32_t dim = ds->dim;
+    const bool multi = ds->shards.size() > 1;
     std::vector<uint8_t> handled(n_queries, 0), part;
-    for (uint32_t q0 = 0; q0 < n_queries; q0 += BATCH_MAX_QUERIES) {
+    for (uint32_t q0 = 0; q0 < n_queries && !multi; q0 += BATCH_MAX_QUERIES) {
         const uint32_t nq = std::min(BATCH_MAX_QUERIES, n_queries - q0);
         PQV_TRY(ivf_batch_masked(ctx, ds, D, ix, queries + (size_t)q0 * dim, nq, k, nprobe, flags, out_row_idx + (size_t)q0 * k,
                                  out_dist + (size_t)q0 * k, out_count + q0, part, nullptr, nullptr, 0, row_mask));
@@ -1239,7 +1272,7 @@ int pqv_vector_topk_indexed_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index,
         ro.h_mask = row_mask;
         bool done = false;
         out_count[q] = 0;
-        if (ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids)
+        if (!multi && ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids)
             PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, qv, k, nprobe, flags, orow, odist, out_count + q, &done, &ro));
         if (!done) {
             PQV_TRY(index_host_ids(D, *ix));
@@ -1271,7 +1304,7 @@ int pqv_vector_topk_indexed(pqv_ctx *ctx, uint64_t handle, uint64_t index, const
     if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
     PQV_TRY(check_topk_args(k, ds->dim, flags));
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);  // index_exec.rs:152-158
-    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_vector_topk_indexed needs a single-device dataset");
+    const bool multi = ds->shards.size() > 1;  // several devices: host-side selection, candidates split by owner (topk_one)
     PQV_TRY(check_index_fits(*ix, *ds));
     DeviceState &D = ctx->devs[ds->shards[0].di];
     DevGuard guard(D.dev);
@@ -1291,7 +1324,7 @@ int pqv_vector_topk_indexed(pqv_ctx *ctx, uint64_t handle, uint64_t index, const
         if (out_rows_scored) *out_rows_scored = 0;
         return PQV_OK;
     }
-    if (ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids) {
+    if (!multi && ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids) {
         bool done = false;
         PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, query, k, nprobe, flags, out_row_idx, out_dist, out_count, &done, &ro));
         if (done) {

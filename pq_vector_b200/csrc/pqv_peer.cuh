@@ -5,7 +5,8 @@
 // launch; here the ranks map one another's exchange buffer once (CUDA IPC) and the scan's tail kernel WRITES the rank's
 // candidates straight into every peer's buffer over NVLink, publishes a sequence flag, and waits for the peers' flags:
 //
-//   l2_scan_topk_kernel -> merge -> entrant_filter_kernel -> peer_publish_kernel -> peer_wait_kernel -> one D2H
+//   l2_scan_topk_kernel -> merge -> entrant_filter_kernel -> peer_publish_kernel -> peer_wait_pack_kernel (writes the
+//   union of all ranks' live keys into page-locked host memory)
 //
 // Buffer of a rank (device memory, local):   2 parities x [ world slots x (1 + cap) u64 ]  +  2 x world u64 flags.
 // Slot r of parity p holds rank r's (count, keys) of the search with sequence number s, s % 2 == p; flag[p][r] == s once
@@ -50,6 +51,55 @@ __global__ void __launch_bounds__(32) peer_wait_kernel(const u64 *__restrict__ l
             __nanosleep(200);
         } while (++spins < (1ull << 27));  // ~ half a minute: ranks may be skewed by first-call allocations
         if (v != seq) atomicOr(timed_out, 1u);
+    }
+}
+
+// The same wait, followed by the read-back itself: once every flag carries `seq`, the CTA packs the live keys of all slots
+// (rank order) straight into page-locked HOST memory -- out[0] = timed-out | any slot over capacity << 1, out[1] = total,
+// out[2 + r] = count of rank r, keys from out[2 + world] on.  A search reads back a few KB instead of the whole
+// world x (1 + cap) block, and needs no separate copy after the kernel.
+__global__ void __launch_bounds__(256) peer_wait_pack_kernel(const u64 *__restrict__ local_base, const uint32_t cap,
+                                                             const uint32_t world, const u64 seq, u64 *__restrict__ out) {
+    __shared__ uint32_t s_timed_out;
+    __shared__ u64 s_off[65];
+    const u64 par = seq & 1ull;
+    const u64 slot_words = 1ull + cap;
+    const u64 *slots = local_base + par * world * slot_words;
+    const u64 *flags = local_base + 2ull * world * slot_words + par * world;
+    if (threadIdx.x == 0) s_timed_out = 0u;
+    __syncthreads();
+    if (threadIdx.x < 32) {
+        for (uint32_t r = threadIdx.x; r < world; r += 32) {
+            u64 v = 0;
+            uint64_t spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + r) : "memory");
+                if (v == seq) break;
+                __nanosleep(200);
+            } while (++spins < (1ull << 27));
+            if (v != seq) atomicOr(&s_timed_out, 1u);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        u64 total = 0, over = 0;
+        for (uint32_t r = 0; r < world; ++r) {
+            const u64 c = __ldcg(slots + r * slot_words);
+            if (c > cap) over = 1;
+            s_off[r] = total;
+            total += c < (u64)cap ? c : (u64)cap;
+            out[2 + r] = c;
+        }
+        s_off[world] = total;
+        out[0] = (u64)s_timed_out | (over << 1);
+        out[1] = total;
+    }
+    __syncthreads();
+    for (uint32_t r = 0; r < world; ++r) {
+        const u64 n = s_off[r + 1] - s_off[r];
+        const u64 *src = slots + r * slot_words + 1;
+        u64 *dst = out + 2 + world + s_off[r];
+        for (u64 i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcg(src + i);
     }
 }
 

@@ -200,13 +200,8 @@ int tc_launch_inst(uint32_t grid, cudaStream_t st, const CUtensorMap &tmA, const
     namespace T = pqv::tc;
     constexpr size_t smem = PAIR ? T::smem_bytes_pair(Epi::STAGES_PAIR, Epi::EXCH_BYTES) : T::smem_bytes_single(Epi::STAGES_SINGLE, Epi::EXCH_BYTES);
     static_assert(smem <= 227 * 1024, "tensor-core kernel exceeds the shared memory of an SM");
-    static std::once_flag once;
-    static cudaError_t attr_err = cudaSuccess;
-    std::call_once(once, [] {
-        if (PAIR) attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_pair_kernel<Epi, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        else attr_err = cudaFuncSetAttribute(T::tc_rows_x_table_kernel<Epi, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    });
-    CU_TRY(attr_err);
+    if (PAIR) PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(T::tc_rows_x_table_pair_kernel<Epi, KIND>), smem));
+    else PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(T::tc_rows_x_table_kernel<Epi, KIND>), smem));
     if (PAIR) T::tc_rows_x_table_pair_kernel<Epi, KIND><<<grid, T::tc_threads(Epi::SPLIT), smem, st>>>(tmA, tmB, shape, p);
     else T::tc_rows_x_table_kernel<Epi, KIND><<<grid, T::tc_threads(Epi::SPLIT), smem, st>>>(tmA, tmB, shape, p);
     CU_TRY(cudaGetLastError());
@@ -267,12 +262,7 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     if (C <= T::ORDER_MAX_C && C > 1 && !order_off) {
         uint32_t cp2 = 2;
         while (cp2 < C) cp2 <<= 1;
-        static std::once_flag order_once;
-        static cudaError_t order_err = cudaSuccess;
-        std::call_once(order_once, [] {
-            order_err = cudaFuncSetAttribute(T::centroid_order_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(T::ORDER_MAX_C * 8));
-        });
-        CU_TRY(order_err);
+        PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(T::centroid_order_kernel), (size_t)T::ORDER_MAX_C * 8));
         T::centroid_spread_kernel<<<C, 128, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, D.tc_okeys.p);
         T::centroid_order_kernel<<<1, 1024, (size_t)cp2 * 8, D.stream>>>(D.tc_okeys.p, C, cp2, D.tc_perm.p);
         perm = D.tc_perm.p;
@@ -399,10 +389,10 @@ struct BatchMask {
     const uint32_t *row_mask;     // device, [ceil(n / 32)] or null
 };
 
-bool batch_path_applies(const Dataset &ds, const float *d_rows, uint32_t nq, uint32_t k) {
+bool batch_path_applies(const Dataset &ds, const float *d_rows, uint32_t nq, uint32_t k, bool any_shards = false) {
     const char *e = getenv("PQV_BATCH");
     if (e && !strcmp(e, "off")) return false;
-    return ds.shards.size() == 1 && nq >= BATCH_MIN_QUERIES && (ds.dim % 4 == 0) && ds.dim >= (uint32_t)pqv::tc::BK &&
+    return (any_shards || ds.shards.size() == 1) && nq >= BATCH_MIN_QUERIES && (ds.dim % 4 == 0) && ds.dim >= (uint32_t)pqv::tc::BK &&
            ((reinterpret_cast<uintptr_t>(d_rows) & 15) == 0) && ds.n_rows < 0xFFFFFFFFull && ds.n_rows >= 1 &&
            k + 1 <= (uint32_t)pqv::tc::SEL_MAX && tmap_encoder() != nullptr;
 }
@@ -528,17 +518,19 @@ int resolve_ties_together(DeviceState &D, const float *d_rows, u64 S, uint32_t d
 int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, const float *queries, uint32_t nq,
                uint32_t k, uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
                std::vector<uint8_t> &handled, u64 *raw_keys = nullptr, uint32_t *raw_count = nullptr, uint32_t pos_base = 0,
-               const BatchMask *bmask = nullptr) {
+               const BatchMask *bmask = nullptr, Shard *shard_in = nullptr, pqv_batch_timing *bt_io = nullptr) {
+    // shard_in + bt_io (raw mode only): one shard of a table spread over several devices, driven from its own host thread
+    // -- nothing of the context is written (timing goes to *bt_io, no tie state is kept)
     // bmask != null (batched IVF search): only (row, query) pairs whose row lies in a cluster the query probes count;
     // tie queries are left unhandled (their order follows the IVF candidate sequence, which the caller replays)
     // raw mode (raw_keys != null, the per-rank half of a sharded search): per query the k + 1 smallest exact keys of
     // this slice go to raw_keys[q*(k+1) ..] with pos_base added to the positions, raw_count[q] = how many are valid, or
     // 0xFFFFFFFF when this slice could not decide the query (the caller falls back to the single-query exchange)
     namespace T = pqv::tc;
-    Shard &sh = ds.shards[0];
+    Shard &sh = shard_in ? *shard_in : ds.shards[0];
     const float *d_rows = sh.d_data;
     handled.assign(nq, 0);
-    pqv_batch_timing &bt = ctx->last_batch;
+    pqv_batch_timing &bt = bt_io ? *bt_io : ctx->last_batch;
     bt = pqv_batch_timing{};
     bt.queries = nq;
     bt.rows = n;
@@ -645,12 +637,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     const float delta = (float)(order == 1 ? dim + 8 : dim / 4 + 12) * 5.9604645e-08f;
     {
         const uint32_t M = k <= 128 ? 2048u : 16384u;  // chunk minima kept per query (>= 16 k)
-        static std::once_flag sel_once;
-        static cudaError_t sel_err = cudaSuccess;
-        std::call_once(sel_once, [] {
-            sel_err = cudaFuncSetAttribute(T::theta_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16384 * 4);
-        });
-        CU_TRY(sel_err);
+        PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(T::theta_select_kernel), (size_t)16384 * 4));
         T::theta_select_kernel<<<nq_pad, 256, M * sizeof(float), st>>>(D.tb_U.p, ldU, (uint32_t)S, k, nq, q2, delta, M, qtheta);
     }
     CU_TRY(cudaGetLastError());
@@ -704,6 +691,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
             raw_count[q] = cnt;
             handled[q] = 1;
         }
+        if (shard_in) return PQV_OK;
         pqv_ctx::BatchState &bs = ctx->batch_state;  // the per-query candidate segments stay on the device for tie queries
         bs.valid = true;
         bs.S = S;

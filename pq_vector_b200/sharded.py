@@ -74,10 +74,10 @@ class ShardedTopk:
 
     def search(self, query, k: int, flags: int):
         if self._p2p is not None:
-            union = self._p2p.l2_topk_candidates_p2p(query, k, flags, self.pos_base)
+            got = self._p2p.l2_topk_p2p(query, k, flags, self.pos_base)   # scan + exchange + replay in one native call
             self.last_gather_bytes = 0
-            if union is not None:
-                return replay_candidates(union, k, flags)
+            if got is not None:
+                return got
             # a rank had more candidates than a slot holds -- every rank saw it: all take the collective path below
         keys = np.ascontiguousarray(self.scan_fn(query, k, flags, self.pos_base), dtype=np.uint64)
         if self.world == 1:  # nothing to exchange
