@@ -59,7 +59,17 @@ extern "C" {
 typedef struct pqv_ctx pqv_ctx;
 
 /* Lifetime.  device_ids == NULL && n_devices == 0 selects the current device.  With n_devices > 1
- * a dataset's rows are split into contiguous ranges, one per device. */
+ * a dataset's rows are split into contiguous ranges, one per device, and ONE host
+ * process drives all of them through the calls below: pqv_l2_topk (single queries: every shard scans
+ * its rows; batches: one tensor-core pass per shard, each from its own host thread, keys merged),
+ * pqv_l2_topk_gather / pqv_ivf_search(_batch) / pqv_vector_topk_indexed(_batch) (candidates split by
+ * owning shard, keys moved back to the caller's sequence positions before the heap replay),
+ * pqv_kmeans_assign over the resident table, pqv_ivf_build (sample gathered to the first device,
+ * rows assigned where they live) and pqv_dataset_read(_rows) -- all with the results of a single
+ * device, bit for bit (tests/test_gpu_multi_device.py).  The per-rank entry points further down
+ * (*_candidates, *_keys, *_p2p) are the other form: one process per GPU, each with its own context.
+ * Still single-device only: pqv_array_distance*, pqv_kmeans_train, pqv_min_dist_update over a
+ * resident table. */
 PQV_API int  pqv_init(pqv_ctx **out, const int *device_ids, int n_devices);
 PQV_API void pqv_destroy(pqv_ctx *ctx);
 PQV_API const char *pqv_last_error(void);
@@ -94,8 +104,8 @@ PQV_API int pqv_dataset_read_rows(pqv_ctx *ctx, uint64_t handle, const uint32_t 
  * Output i of query q is at out_*[q*k + i]; out_count[q] <= k results are valid, ascending. */
 PQV_API int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k,
                 uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count);
-/* With n_queries >= 4 (single-device dataset, dim % 4 == 0) pqv_l2_topk answers the whole batch in one tensor-core pass
- * over the table (tcgen05 tf32 filter + exact re-rank of the survivors); every query's output is
+/* With n_queries >= 4 (dim % 4 == 0) pqv_l2_topk answers the whole batch in one tensor-core pass
+ * over the table (per shard, when the table is spread over several devices) (tcgen05 tf32 filter + exact re-rank of the survivors); every query's output is
  * still identical to its own single-query call.  PQV_BATCH=off in the environment disables the batched pass. */
 typedef struct {
     uint32_t queries;      /* batch size of the last pqv_l2_topk call (0: batched pass not used)                        */

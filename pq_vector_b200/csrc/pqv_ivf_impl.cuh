@@ -100,6 +100,9 @@ struct IvfIndex {
     u64 row_cluster_rows = 0;
     uint32_t build_iters = 0;   // Lloyd iterations the build ran
     double build_ms[4] = {0, 0, 0, 0};  // sample+init, lloyd, final assign, total
+    // host maps row -> (cluster, index inside the cluster's list), for the tie replay of batched searches; built on first use
+    std::vector<uint32_t> h_row_cluster, h_row_listpos;
+    u64 h_row_maps_rows = 0;
 };
 
 void csr_from_assign(const uint32_t *assign, u64 n, uint32_t n_clusters, std::vector<u64> &offsets,
@@ -268,13 +271,14 @@ struct EntrantsOut {
 
 int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, const float *query, uint32_t k,
                      uint32_t nprobe, uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
-                     bool *done, RowOrder *ro = nullptr, EntrantsOut *eo = nullptr) {
+                     bool *done, RowOrder *ro = nullptr, EntrantsOut *eo = nullptr, u64 seq_limit = ~0ull) {
+    // seq_limit (rank-order form only): scan just the first seq_limit candidates of the sequence
     *done = false;
     static const bool trace = getenv("PQV_TRACE") != nullptr;
     double tt[8] = {0};
     if (trace) tt[0] = now_ms();
     const uint32_t C = ix.n_clusters, np = std::min(nprobe, C), cp2 = pow2ceil(C);
-    const u64 n_bound = ro ? std::min<u64>(ix.n_ids, ro->max_candidates) : ix.n_ids;
+    const u64 n_bound = ro ? std::min<u64>(ix.n_ids, ro->max_candidates) : std::min<u64>(ix.n_ids, seq_limit);
     const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
     PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(pqv::ivf_rank_kernel), (size_t)IVF_RANK_MAX_C * 8));
     PQV_TRY(D.d_query.ensure(ix.dim));
@@ -311,6 +315,7 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
     if (!ro) {
         pqv::ivf_expand_kernel<<<dim3(np, 8), 256, 0, D.stream>>>(ix.d_ids.p, ix.d_offsets.p, ix.d_probe_cluster.p,
                                                                   ix.d_probe_prefix.p, ix.d_cand.p);
+        if (seq_limit != ~0ull) pqv::clamp_count_kernel<<<1, 1, 0, D.stream>>>(D.ivf_info.p, seq_limit);
     } else {
         const uint32_t *d_mask = ro->h_mask ? D.vt_mask.p : nullptr;
         pqv::ivf_mark_kernel<<<dim3(np, 8), 256, 0, D.stream>>>(ix.d_ids.p, ix.d_offsets.p, ix.d_probe_cluster.p,
@@ -1017,7 +1022,7 @@ int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *q
 static int ivf_batch_masked(pqv_ctx *ctx, Dataset *ds, DeviceState &D, IvfIndex *ix, const float *queries, uint32_t n_queries,
                             uint32_t k, uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist,
                             uint32_t *out_count, std::vector<uint8_t> &handled, u64 *raw_keys, uint32_t *raw_count,
-                            uint32_t pos_base, const uint8_t *h_row_mask = nullptr) {
+                            uint32_t pos_base, const uint8_t *h_row_mask = nullptr, BatchTieOut *tie_out = nullptr) {
     const uint32_t C = ix->n_clusters, dim = ds->dim, np = std::min(nprobe, C);
     handled.assign(n_queries, 0);
     ctx->last_batch = pqv_batch_timing{};
@@ -1075,12 +1080,166 @@ static int ivf_batch_masked(pqv_ctx *ctx, Dataset *ds, DeviceState &D, IvfIndex 
         }
         BatchMask bm{ix->d_row_cluster.p, D.vt_mask.p, qwords, d_row_mask};
         PQV_TRY(batch_topk(ctx, D, *ds, ds->n_rows, dim, queries, nq, k, flags, out_row_idx, out_dist, out_count, handled, raw_keys,
-                           raw_count, pos_base, &bm));
+                           raw_count, pos_base, &bm, nullptr, nullptr, tie_out));
         ctx->batch_state.valid = false;  // the candidate segments left on the device are masked: not for the dense tie API
         CU_TRY(cudaStreamSynchronize(D.stream));  // nan_flags is in (batch_topk may have returned before its own sync)
         for (uint32_t q = 0; q < nq; ++q)
             if (nan_flags[q]) handled[q] = 0;
+        if (tie_out) {  // a NaN ranking has no usable candidate sequence on the device
+            size_t o = 0;
+            for (size_t t = 0; t < tie_out->queries.size(); ++t)
+                if (!nan_flags[tie_out->queries[t]]) {
+                    tie_out->queries[o] = tie_out->queries[t];
+                    tie_out->cnt[o] = tie_out->cnt[t];
+                    tie_out->T[o] = tie_out->T[t];
+                    ++o;
+                }
+            tie_out->queries.resize(o);
+            tie_out->cnt.resize(o);
+            tie_out->T.resize(o);
+        }
     }
+    return PQV_OK;
+}
+
+// Tie queries of a batched IVF search (rank-order form), replayed from a SHORT prefix of their candidate sequences.
+// The reference heap (src/ivf/search.rs:115-127) walks the query's sequence -- probed lists in rank order -- and admits a
+// row iff it beats the current k-th smallest.  Let T = qT (theta_select_kernel): every row with d <= T is among the query's
+// candidates of the batched pass, and at least k of them exist.  Let P be the sequence position of the k-th candidate
+// (in sequence order) with d <= T.  From P on the heap's threshold is <= T, so whatever it admits behind P is a candidate the
+// pass already holds with its exact distance; only the rows at positions <= P can enter with d > T, and those are scanned
+// exactly (ivf_search_fused limited to P + 1 candidates: ~2 % of the sequence at k = 100).  The union, in sequence order,
+// replays to the reference's answer, layout ties included.  Queries this cannot place (candidates outside the lists' maps,
+// fewer than k candidates under T, a declined fused scan) stay unhandled for the full single-query pipeline.
+static int index_host_row_maps(DeviceState &D, IvfIndex &ix, u64 n_rows) {
+    if (ix.h_row_maps_rows == n_rows && !ix.h_row_cluster.empty()) return PQV_OK;
+    PQV_TRY(index_host_ids(D, ix));
+    ix.h_row_cluster.assign(n_rows, 0xFFFFFFFFu);
+    ix.h_row_listpos.assign(n_rows, 0u);
+    for (uint32_t c = 0; c < ix.n_clusters; ++c)
+        for (u64 i = ix.offsets[c]; i < ix.offsets[c + 1]; ++i) {
+            const uint32_t r = ix.ids[i];
+            if (r < n_rows) {
+                ix.h_row_cluster[r] = c;
+                ix.h_row_listpos[r] = (uint32_t)(i - ix.offsets[c]);
+            }
+        }
+    ix.h_row_maps_rows = n_rows;
+    return PQV_OK;
+}
+
+static int ivf_ties_short_prefix(pqv_ctx *ctx, Dataset *ds, DeviceState &D, IvfIndex *ix, const float *queries, uint32_t nq,
+                                 uint32_t k, uint32_t nprobe, uint32_t flags, const BatchTieOut &ties, uint32_t *out_row_idx,
+                                 float *out_dist, uint32_t *out_count, std::vector<uint8_t> &handled, uint32_t *n_resolved) {
+    *n_resolved = 0;
+    const size_t nt = ties.queries.size();
+    if (!nt || !ivf_fused_enabled() || ix->n_clusters > IVF_RANK_MAX_C) return PQV_OK;
+    const uint32_t C = ix->n_clusters, np = std::min(nprobe, C), dim = ds->dim;
+    PQV_TRY(index_host_row_maps(D, *ix, ds->n_rows));
+    // the pass' rankings (D.d_assign: [nq][np] cluster ids in rank order) and the tie queries' candidate segments
+    std::vector<uint32_t> ranked((size_t)nq * np);
+    CU_TRY(cudaMemcpyAsync(ranked.data(), D.d_assign.p, ranked.size() * 4, cudaMemcpyDeviceToHost, D.stream));
+    std::vector<size_t> seg_off(nt + 1, 0);
+    for (size_t t = 0; t < nt; ++t) seg_off[t + 1] = seg_off[t] + ties.cnt[t];
+    std::vector<u64> segs(seg_off[nt]);
+    for (size_t t = 0; t < nt; ++t)
+        if (ties.cnt[t])
+            CU_TRY(cudaMemcpyAsync(segs.data() + seg_off[t], D.tb_seg.p + (size_t)ties.queries[t] * ties.cap_q, (size_t)ties.cnt[t] * 8,
+                                   cudaMemcpyDeviceToHost, D.stream));
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    struct Item {
+        uint32_t pos, row;
+        float d;
+    };
+    struct Tie {
+        std::vector<Item> items;  // the pass' candidates with their sequence positions, ascending
+        u64 P = ~0ull;            // sequence position of the k-th candidate with d <= T (~0: cannot be placed)
+        EntrantsOut eo;
+        bool scanned = false;
+    };
+    std::vector<Tie> work(nt);
+    const size_t nth = std::max<size_t>(1, std::min<size_t>(tie_threads(), (nt + 1) / 2));
+    auto parallel = [&](auto &&fn) {  // fn(t) for every tie query, independent of one another
+        if (nth <= 1) {
+            for (size_t t = 0; t < nt; ++t) fn(t);
+            return;
+        }
+        std::vector<std::thread> th;
+        for (size_t w = 1; w < nth; ++w)
+            th.emplace_back([&, w] {
+                for (size_t t = w; t < nt; t += nth) fn(t);
+            });
+        for (size_t t = 0; t < nt; t += nth) fn(t);
+        for (auto &x : th) x.join();
+    };
+    // phase A (host threads): place every candidate in its query's sequence, find P
+    parallel([&](size_t t) {
+        Tie &W = work[t];
+        const uint32_t q = ties.queries[t];
+        const uint32_t *rk = ranked.data() + (size_t)q * np;
+        std::vector<int32_t> rank_of(C, -1);
+        std::vector<u64> prefix((size_t)np + 1);
+        prefix[0] = 0;
+        for (uint32_t r = 0; r < np; ++r) {
+            rank_of[rk[r]] = (int32_t)r;
+            prefix[r + 1] = prefix[r] + (ix->offsets[rk[r] + 1] - ix->offsets[rk[r]]);
+        }
+        const float T = ties.T[t];
+        if (prefix[np] > 0xFFFFFFFFull || !(T >= 0.f)) return;
+        const size_t b0 = seg_off[t], b1 = seg_off[t + 1];
+        W.items.reserve(b1 - b0);
+        for (size_t i = b0; i < b1; ++i) {
+            if (i + 16 < b1) {  // the two maps are tens of MB: hide the misses
+                const uint32_t ahead = key_pos(segs[i + 16]);
+                if (ahead < ds->n_rows) {
+                    __builtin_prefetch(&ix->h_row_cluster[ahead]);
+                    __builtin_prefetch(&ix->h_row_listpos[ahead]);
+                }
+            }
+            const uint32_t row = key_pos(segs[i]);
+            const uint32_t c = row < ds->n_rows ? ix->h_row_cluster[row] : 0xFFFFFFFFu;
+            if (c == 0xFFFFFFFFu || rank_of[c] < 0) {
+                W.items.clear();
+                return;
+            }
+            W.items.push_back(Item{(uint32_t)(prefix[rank_of[c]] + ix->h_row_listpos[row]), row, key_dist(segs[i])});
+        }
+        std::sort(W.items.begin(), W.items.end(), [](const Item &x, const Item &y) { return x.pos < y.pos; });
+        uint32_t under = 0;
+        for (const Item &it : W.items)
+            if (it.d <= T && ++under == k) {
+                W.P = it.pos;
+                break;
+            }
+    });
+    // phase B (one stream): exact scans of the sequence prefixes [0, P]
+    for (size_t t = 0; t < nt; ++t) {
+        Tie &W = work[t];
+        if (W.P == ~0ull) continue;
+        bool done = false;
+        uint32_t dummy_rows[1], dummy_cnt = 0;
+        float dummy_dist[1];
+        PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, queries + (size_t)ties.queries[t] * dim, k, nprobe, flags, dummy_rows, dummy_dist,
+                                 &dummy_cnt, &done, nullptr, &W.eo, W.P + 1));
+        W.scanned = done;
+    }
+    // phase C (host threads): union in sequence order, reference loop
+    parallel([&](size_t t) {
+        Tie &W = work[t];
+        if (!W.scanned) return;
+        const uint32_t q = ties.queries[t];
+        std::vector<Item> merged;
+        merged.reserve(W.eo.keys.size() + W.items.size());
+        for (size_t i = 0; i < W.eo.keys.size(); ++i) merged.push_back(Item{key_pos(W.eo.keys[i]), W.eo.rows[i], key_dist(W.eo.keys[i])});
+        for (const Item &it : W.items)
+            if (it.pos > W.P) merged.push_back(it);
+        std::sort(merged.begin(), merged.end(), [](const Item &x, const Item &y) { return x.pos < y.pos; });
+        out_count[q] = (uint32_t)replay_ordered(
+            merged.size(), [&](size_t i) { return ReplayItem{merged[i].d, merged[i].row}; }, k, flags, out_row_idx + (size_t)q * k,
+            out_dist + (size_t)q * k);
+        handled[q] = 1;
+    });
+    for (size_t t = 0; t < nt; ++t) *n_resolved += work[t].scanned ? 1u : 0u;
     return PQV_OK;
 }
 
@@ -1114,9 +1273,28 @@ int pqv_ivf_search_batch(pqv_ctx *ctx, uint64_t handle, uint64_t index, const fl
     std::vector<uint8_t> handled(n_queries, 0), part;
     for (uint32_t q0 = 0; q0 < n_queries && !multi; q0 += BATCH_MAX_QUERIES) {  // the pass' scratch grows with the batch
         const uint32_t nq = std::min(BATCH_MAX_QUERIES, n_queries - q0);
+        BatchTieOut tie_out;
+        static const bool short_prefix = !(getenv("PQV_IVF_TIE_PREFIX") && !strcmp(getenv("PQV_IVF_TIE_PREFIX"), "off"));
+        const bool want_ties = !row_order && short_prefix;  // the row-order form walks another sequence (ascending rows)
         PQV_TRY(ivf_batch_masked(ctx, ds, D, ix, queries + (size_t)q0 * dim, nq, k, nprobe, flags, out_row_idx + (size_t)q0 * k,
-                                 out_dist + (size_t)q0 * k, out_count + q0, part, nullptr, nullptr, 0));
+                                 out_dist + (size_t)q0 * k, out_count + q0, part, nullptr, nullptr, 0, nullptr,
+                                 want_ties ? &tie_out : nullptr));
+        if (want_ties && !tie_out.queries.empty()) {
+            const pqv_batch_timing keep = ctx->last_batch;  // the prefix scans below overwrite the single-query timing only
+            uint32_t resolved = 0;
+            PQV_TRY(ivf_ties_short_prefix(ctx, ds, D, ix, queries + (size_t)q0 * dim, nq, k, nprobe, flags, tie_out,
+                                          out_row_idx + (size_t)q0 * k, out_dist + (size_t)q0 * k, out_count + q0, part, &resolved));
+            ctx->last_batch = keep;
+            ctx->last_batch.tie_queries += (uint32_t)tie_out.queries.size();
+            ctx->last_batch.tie_batched += resolved;
+        }
         for (uint32_t i = 0; i < nq; ++i) handled[q0 + i] = part[i];
+    }
+    if (getenv("PQV_TRACE")) {
+        uint32_t left = 0;
+        for (uint32_t q = 0; q < n_queries; ++q) left += handled[q] ? 0u : 1u;
+        fprintf(stderr, "[pqv trace] ivf_search_batch: %u queries, %u tie queries (%u replayed from a short prefix), %u left for the "
+                        "single-query pipeline\n", n_queries, ctx->last_batch.tie_queries, ctx->last_batch.tie_batched, left);
     }
     for (uint32_t q = 0; q < n_queries; ++q) {
         if (handled[q]) continue;

@@ -1144,6 +1144,11 @@ __global__ void __launch_bounds__(1024) ivf_rank_kernel(const float *__restrict_
     }
 }
 
+// info[0] = min(info[0], limit): a search over a prefix of the candidate sequence only (tie replay of a batched IVF search)
+__global__ void clamp_count_kernel(u64 *__restrict__ info, const u64 limit) {
+    if (info[0] > limit) info[0] = limit;
+}
+
 // row ids of the surviving entrant keys of a gathered scan: rows_out[i] = cand[position of key i]
 // (keys = entrant_filter_kernel's out: [0] = count, keys from [1]).
 __global__ void __launch_bounds__(256) ent_rows_kernel(const u64 *__restrict__ ent_out, const uint32_t cap,

@@ -1361,15 +1361,24 @@ __device__ __forceinline__ float f32_unordered(uint32_t o) {
 // queries >= nq (padding) get -inf so that they never produce candidates.  S < k: +inf (every row is a candidate).
 __global__ void __launch_bounds__(256) theta_select_kernel(const float *__restrict__ U, uint32_t ldU, uint32_t S, uint32_t k,
                                                            uint32_t nq, const float *__restrict__ q2, float delta, uint32_t M,
-                                                           float *__restrict__ qtheta) {
+                                                           float *__restrict__ qtheta, float *__restrict__ qT) {
+    // qT[q] (reference-distance units): at least k rows of the sample have d_ref <= qT, and EVERY row of the table with
+    // d_ref <= qT passes the filter -- d_true <= qT / (1 - delta) <= (th + |q|^2)(1 + 2.01 delta + 2^-23) stays below theta_q.
+    // The IVF tie replay uses it to bound the sequence prefix that needs exact distances (pqv_ivf_impl.cuh).
     extern __shared__ float mins[];  // [M]
     const uint32_t q = blockIdx.x;
     if (q >= nq) {
-        if (threadIdx.x == 0) qtheta[q] = __int_as_float(0xff800000);
+        if (threadIdx.x == 0) {
+            qtheta[q] = __int_as_float(0xff800000);
+            qT[q] = __int_as_float(0xff800000);
+        }
         return;
     }
     if (S < k) {
-        if (threadIdx.x == 0) qtheta[q] = __int_as_float(0x7f800000);
+        if (threadIdx.x == 0) {
+            qtheta[q] = __int_as_float(0x7f800000);
+            qT[q] = __int_as_float(0xff800000);   // no bound from the sample: the replay takes the whole sequence
+        }
         return;
     }
     __shared__ uint32_t hist[256];
@@ -1422,6 +1431,7 @@ __global__ void __launch_bounds__(256) theta_select_kernel(const float *__restri
         const float qq = q2[q];
         const float d = fmaxf(th + qq, 0.f);
         qtheta[q] = th + (9.5367432e-07f + 2.2f * delta) * d + (fabsf(th) + qq) * 9.5367432e-07f + 1e-37f;
+        qT[q] = d * (1.f + delta + 1.2e-07f);
     }
 }
 

@@ -389,6 +389,14 @@ struct BatchMask {
     const uint32_t *row_mask;     // device, [ceil(n / 32)] or null
 };
 
+// masked (IVF) batches: what the caller needs to replay its tie queries from a short prefix of their candidate sequences
+struct BatchTieOut {
+    std::vector<uint32_t> queries;  // tie queries of the pass (index into the batch)
+    std::vector<uint32_t> cnt;      // candidates of each in its device segment (D.tb_seg + q * cap_q)
+    std::vector<float> T;           // qT of each (theta_select_kernel)
+    uint32_t cap_q = 0;
+};
+
 bool batch_path_applies(const Dataset &ds, const float *d_rows, uint32_t nq, uint32_t k, bool any_shards = false) {
     const char *e = getenv("PQV_BATCH");
     if (e && !strcmp(e, "off")) return false;
@@ -518,7 +526,8 @@ int resolve_ties_together(DeviceState &D, const float *d_rows, u64 S, uint32_t d
 int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, const float *queries, uint32_t nq,
                uint32_t k, uint32_t flags, uint32_t *out_rows, float *out_dist, uint32_t *out_count,
                std::vector<uint8_t> &handled, u64 *raw_keys = nullptr, uint32_t *raw_count = nullptr, uint32_t pos_base = 0,
-               const BatchMask *bmask = nullptr, Shard *shard_in = nullptr, pqv_batch_timing *bt_io = nullptr) {
+               const BatchMask *bmask = nullptr, Shard *shard_in = nullptr, pqv_batch_timing *bt_io = nullptr,
+               BatchTieOut *tie_out = nullptr) {
     // shard_in + bt_io (raw mode only): one shard of a table spread over several devices, driven from its own host thread
     // -- nothing of the context is written (timing goes to *bt_io, no tie state is kept)
     // bmask != null (batched IVF search): only (row, query) pairs whose row lies in a cluster the query probes count;
@@ -566,7 +575,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
 
     PQV_TRY(D.tb_Q.ensure((size_t)nq * dim));
     PQV_TRY(D.tb_Qp.ensure((size_t)nq * dim));
-    PQV_TRY(D.tb_qf.ensure(3 * (size_t)nq_pad));
+    PQV_TRY(D.tb_qf.ensure(4 * (size_t)nq_pad));
     PQV_TRY(D.tc_wc.ensure(nq_pad / 32));
     PQV_TRY(D.tb_u32.ensure(4 + (size_t)nq + grid));
     PQV_TRY(D.tb_U.ensure((size_t)nq_pad * ldU));
@@ -582,7 +591,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
         sh.norms_cap = n;
     }
     PQV_TRY(D.h_batch_keys.ensure((size_t)nq * kout + nq + 2));
-    float *qw = D.tb_qf.p, *q2 = D.tb_qf.p + nq_pad, *qtheta = D.tb_qf.p + 2 * (size_t)nq_pad;
+    float *qw = D.tb_qf.p, *q2 = D.tb_qf.p + nq_pad, *qtheta = D.tb_qf.p + 2 * (size_t)nq_pad, *qT = D.tb_qf.p + 3 * (size_t)nq_pad;
     uint32_t *qbounds = D.tb_u32.p, *dflags = D.tb_u32.p + 1, *cntq = D.tb_u32.p + 4, *region_count = D.tb_u32.p + 4 + nq;
     PQV_TRY(D.tb_info.ensure(nq));
 
@@ -638,7 +647,7 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     {
         const uint32_t M = k <= 128 ? 2048u : 16384u;  // chunk minima kept per query (>= 16 k)
         PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(T::theta_select_kernel), (size_t)16384 * 4));
-        T::theta_select_kernel<<<nq_pad, 256, M * sizeof(float), st>>>(D.tb_U.p, ldU, (uint32_t)S, k, nq, q2, delta, M, qtheta);
+        T::theta_select_kernel<<<nq_pad, 256, M * sizeof(float), st>>>(D.tb_U.p, ldU, (uint32_t)S, k, nq, q2, delta, M, qtheta, qT);
     }
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaEventRecord(D.ev[2], st));
@@ -665,6 +674,11 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
     CU_TRY(cudaMemcpyAsync(h_flags, dflags, 4, cudaMemcpyDeviceToHost, st));
     std::vector<uint32_t> h_cnt(nq);
     CU_TRY(cudaMemcpyAsync(h_cnt.data(), cntq, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    std::vector<float> h_qT;
+    if (tie_out) {
+        h_qT.resize(nq);
+        CU_TRY(cudaMemcpyAsync(h_qT.data(), qT, (size_t)nq * 4, cudaMemcpyDeviceToHost, st));
+    }
     CU_TRY(cudaStreamSynchronize(st));
     float ms[4] = {0, 0, 0, 0};
     for (int i = 0; i < 4; ++i) cudaEventElapsedTime(&ms[i], D.ev[i], D.ev[i + 1]);
@@ -709,7 +723,14 @@ int batch_topk(pqv_ctx *ctx, DeviceState &D, Dataset &ds, u64 n, uint32_t dim, c
         const uint32_t info = h_info[q];
         if (info & T::SEL_OVERFLOW) continue;  // candidate list incomplete: the caller runs the full single-query scan
         if ((info & T::SEL_TIE) && !by_pos) {
-            if (!bmask) ties.push_back(q);
+            if (!bmask) {
+                ties.push_back(q);
+            } else if (tie_out && h_cnt[q] <= cap_q) {
+                tie_out->queries.push_back(q);
+                tie_out->cnt.push_back(h_cnt[q]);
+                tie_out->T.push_back(h_qT[q]);
+                tie_out->cap_q = cap_q;
+            }
             continue;
         }
         const uint32_t cnt = info & 0xFFFFu;
