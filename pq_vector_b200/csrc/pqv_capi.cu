@@ -1117,6 +1117,7 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
 
 }  // namespace
 
+#include "pqv_kmeanspp.cuh"
 #include "pqv_tc_host.cuh"
 
 static void pqv_free_all_indexes(pqv_ctx *ctx);

@@ -470,9 +470,8 @@ int kmeans_train_device(DeviceState &D, const float *d_sample, u64 ns, uint32_t 
         return fail(PQV_ECUDA, "k-means init failed: %s", cudaGetErrorString(ce));
     }
     int rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p, d_md.p, 0);  // index.rs:344-352
-    ScopedPin<float> h_md;  // pinned: the sweep result comes back 1023 times
-    if (!rc) rc = h_md.ensure(init_n);
-    float *md = h_md.p;
+    ScopedPin<float> h_md;  // pinned: the sweep result comes back 1023 times (host loop only, allocated there)
+    float *md = nullptr;
     unsigned hw = std::thread::hardware_concurrency();
     const u64 workers = std::max<u64>(1, std::min<u64>(sum_workers ? sum_workers : (hw ? hw : 1), init_n));  // index.rs:259-265
     const u64 chunk = (init_n + workers - 1) / workers;
@@ -480,7 +479,62 @@ int kmeans_train_device(DeviceState &D, const float *d_sample, u64 ns, uint32_t 
     std::vector<float> local(n_chunks);
     static const bool trace_pp = getenv("PQV_TRACE") != nullptr;
     double tp[4] = {0, 0, 0, 0}, t_a = 0, t_b = 0, t_c = 0;
-    for (uint32_t i = 1; i < C && !rc; ++i) {
+    // The picks on the device (pqv_kmeanspp.cuh): sweep and pick kernels alternate on the stream, the random stream lives in
+    // device memory, nothing comes back to the host until the last centroid is set.  PQV_KMEANSPP=host keeps the host loop
+    // below (also taken by init sets that do not fit one CTA's shared memory: more than 50 000 clusters).
+    static const bool pp_host = getenv("PQV_KMEANSPP") && !strcmp(getenv("PQV_KMEANSPP"), "host");
+    bool on_device = false;
+    if (!rc && !pp_host && init_n <= pqv::kpp::MAX_ROWS && C > 1) {
+        ScopedDev<unsigned long long> d_rng;
+        ScopedDev<uint32_t> d_dbg;
+        rc = d_rng.ensure(1);
+        if (!rc && trace_pp) rc = d_dbg.ensure(8 * (size_t)C);
+        if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void *>(pqv::kpp::kmeanspp_pick_kernel), (size_t)init_n * 4);
+        const unsigned long long state = rng.s;
+        if (!rc) {
+            ce = cudaMemcpyAsync(d_rng.p, &state, 8, cudaMemcpyHostToDevice, D.stream);
+            if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "k-means++ random state upload failed: %s", cudaGetErrorString(ce));
+        }
+        if (trace_pp) t_a = now_ms();
+        for (uint32_t i = 1; i < C && !rc; ++i) {
+            rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p + (size_t)(i - 1) * dim, d_md.p, 1);
+            if (rc) break;
+            pqv::kpp::kmeanspp_pick_kernel<<<1, pqv::kpp::THREADS, (size_t)init_n * 4, D.stream>>>(
+                d_md.p, (uint32_t)init_n, (uint32_t)chunk, (uint32_t)n_chunks, d_rng.p, d_init.p, d_sample, dim,
+                D.d_centroids.p + (size_t)i * dim, trace_pp ? d_dbg.p + 8 * (size_t)i : nullptr);
+            ce = cudaGetLastError();
+            if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "k-means++ pick launch failed: %s", cudaGetErrorString(ce));
+        }
+        if (!rc) {
+            ce = cudaStreamSynchronize(D.stream);
+            if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "k-means++ on the device failed: %s", cudaGetErrorString(ce));
+        }
+        if (trace_pp) {
+            fprintf(stderr, "[pqv trace] k-means++ on the device (%u picks over %llu rows, %llu chunk sums): %.1f ms\n", C - 1,
+                    (unsigned long long)init_n, (unsigned long long)n_chunks, now_ms() - t_a);
+            std::vector<uint32_t> dbg(8 * (size_t)C, 0);
+            if (!rc && cudaMemcpy(dbg.data(), d_dbg.p, dbg.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess) {
+                double ph[6] = {0, 0, 0, 0, 0, 0}, iters = 0, pos = 0;
+                for (uint32_t i = 1; i < C; ++i) {
+                    for (int j = 1; j <= 5; ++j) ph[j] += dbg[8 * (size_t)i + j];
+                    iters += dbg[8 * (size_t)i + 6];
+                    pos += dbg[8 * (size_t)i] == 0xFFFFFFFFu ? 0 : dbg[8 * (size_t)i];
+                }
+                const double inv = 1.0 / (C - 1);
+                fprintf(stderr, "[pqv trace] pick kernel, mean cycles: load %.0f, chunk sums %.0f, draw + prologue %.0f, walk %.0f (%.1f blocks, "
+                                "mean pick position %.0f), row copy %.0f\n", ph[1] * inv, (ph[2] - ph[1]) * inv, (ph[3] - ph[2]) * inv,
+                        (ph[4] - ph[3]) * inv, iters * inv, pos * inv, (ph[5] - ph[4]) * inv);
+            }
+            d_dbg.release();
+        }
+        d_rng.release();
+        on_device = true;
+    }
+    if (!rc && !on_device && C > 1) {
+        rc = h_md.ensure(init_n);
+        md = h_md.p;
+    }
+    for (uint32_t i = 1; i < C && !rc && !on_device; ++i) {
         if (trace_pp) t_a = now_ms();
         // the sweep writes its result to d_md and, in the same pass, to the page-locked host buffer md
         rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p + (size_t)(i - 1) * dim, d_md.p, 1, md);
@@ -525,7 +579,7 @@ int kmeans_train_device(DeviceState &D, const float *d_sample, u64 ns, uint32_t 
             tp[2] += t_d - t_c;
         }
     }
-    if (trace_pp)
+    if (trace_pp && !on_device)
         fprintf(stderr, "[pqv trace] k-means++ (%u picks over %llu rows): sweep+readback %.1f ms, chunk sums %.1f ms, cumsum pick %.1f ms\n",
                 C - 1, (unsigned long long)init_n, tp[0], tp[1], tp[2]);
     h_md.release();

@@ -130,6 +130,41 @@ def test_build_matches_oracle_pipeline(ctx, n, dim, C, iters):
     ix.drop(); ix2.drop(); ds.drop()
 
 
+@pytest.mark.parametrize("case", ["identical", "two-points", "tiny", "huge", "grid", "big-init", "nan-row", "one-worker"])
+def test_kmeanspp_on_the_device_handles_awkward_tables(ctx, case):
+    """the device-side k-means++ pick (pqv_kmeanspp.cuh: chunk sums, draw, block-parallel exact walk) against the oracle's
+    literal chains on tables that leave its integer model: zero totals (uniform draws), tiny / huge distances, distances on a
+    coarse grid (rounding ties all along the walk), an init set of the full 50 000 rows, non-finite distances"""
+    rng = np.random.default_rng(len(case))
+    workers, iters = 4, 2
+    if case == "identical":
+        data, C = np.tile(rng.random((1, 8), dtype=np.float32), (400, 1)), 9
+    elif case == "two-points":
+        data, C = np.repeat(rng.random((2, 8), dtype=np.float32), 300, axis=0), 6
+    elif case == "tiny":
+        data, C = (rng.random((3000, 8)) * 1e-19).astype(np.float32), 12
+    elif case == "huge":
+        data, C = (rng.random((3000, 8)) * 3e17).astype(np.float32), 12
+    elif case == "grid":
+        data, C = (rng.integers(0, 5, (20000, 4)) * 1024.5).astype(np.float32), 30
+    elif case == "big-init":
+        data, C, workers = rng.random((60000, 8), dtype=np.float32) * 7, 40, 3
+    elif case == "nan-row":
+        data, C = rng.random((2500, 8), dtype=np.float32), 10
+        data[7, 3] = np.nan
+        data[900, 0] = np.inf
+    else:
+        data, C, workers = rng.random((9000, 16), dtype=np.float32), 25, 1
+    ds = ctx.dataset_from(data)
+    ix = ctx.ivf_build(ds, n_clusters=C, max_iters=iters, seed=7, sum_workers=workers)
+    _, cent, offsets, ids = O.index_from_bytes(ix.to_bytes())
+    ecent, eoff, eids, _ = oracle_build(data, C, iters, 7, workers)
+    assert np.array_equal(np.isnan(cent), np.isnan(ecent))
+    assert np.array_equal(np.nan_to_num(cent, nan=-1.0).view(np.uint32), np.nan_to_num(ecent, nan=-1.0).view(np.uint32))
+    assert np.array_equal(offsets, eoff) and np.array_equal(ids, eids)
+    ix.drop(); ds.drop()
+
+
 def test_reference_index_kat_blob(ctx):
     # src/ivf/index.rs:495-511
     blob = (np.array([3, 2], "<u4").tobytes() + np.arange(1, 7, dtype="<f4").tobytes()
