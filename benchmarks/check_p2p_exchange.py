@@ -64,7 +64,26 @@ tiny = ShardedTopk(scan, pos_base, dev, cap=64)
 tiny.enable_p2p(ctx, ds)
 r_tiny, _ = run(tiny)
 same_tiny = all(x[0].tolist() == y[0].tolist() for x, y in zip(r_nccl, r_tiny))
-flag = torch.tensor([float(same and same_tiny)], device=dev)
+# grid data: thousands of bit-equal distances across the ranks (the threshold that drops later ranks' entrants is strict),
+# plus a slice holding a NaN row (every rank must fall back together and agree with the collective path)
+same_grid = True
+for trial, (gn, gd, with_nan) in enumerate([(150_000, 16, False), (40_000, 8, True)]):
+    g = np.random.default_rng(1000 + rank + 17 * trial).integers(0, 3, (gn, gd)).astype(np.float32)
+    if with_nan and rank == world - 1:
+        g[5, 1] = np.nan
+    gds = ctx.dataset_from(g)
+    gscan = lambda q, k_, f_, pb, _d=gds: _d.l2_topk_candidates(q, k_, f_, pb)  # noqa: E731
+    g_nccl = ShardedTopk(gscan, rank * gn, dev)
+    g_p2p = ShardedTopk(gscan, rank * gn, dev)
+    g_p2p.enable_p2p(ctx, gds)
+    gq = np.random.default_rng(5 + trial).integers(0, 3, (12, gd)).astype(np.float32)
+    for k_ in (1, 10, 100):
+        for q in gq:
+            x, y = g_nccl.search(q, k_, P.PQV_SQRT), g_p2p.search(q, k_, P.PQV_SQRT)
+            xn, yn = np.nan_to_num(x[1], nan=-1.0), np.nan_to_num(y[1], nan=-1.0)
+            same_grid &= x[0].tolist() == y[0].tolist() and xn.view(np.uint32).tolist() == yn.view(np.uint32).tolist()
+    gds.drop()
+flag = torch.tensor([float(same and same_tiny and same_grid)], device=dev)
 if world > 1:
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
 if rank == 0:

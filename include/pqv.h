@@ -215,8 +215,10 @@ PQV_API int pqv_replay_candidates(const uint64_t *keys, uint64_t n_keys, const u
  * runs scan -> filter -> a tail kernel that WRITES this rank's candidates into every peer's buffer and publishes a
  * sequence flag -> a kernel that waits for the peers' flags and packs the union of the live keys into page-locked host
  * memory: no collective launch, no copy call and no extra host round trip per query.  All ranks must call it the same number of times, in the same order.
- * out_keys[0 .. *out_count) = the union in rank order; *out_overflow = 1 (nothing written) when some rank had more than
- * cap_keys candidates -- every rank sees the same counts, so all of them fall back to pqv_l2_topk_candidates together. */
+ * out_keys[0 .. *out_count) = the union (no particular order; entrants of later ranks that the global heap cannot admit --
+ * distance not below the smallest final k-th distance of the ranks before them -- are already dropped); *out_overflow = 1
+ * (nothing written) when some rank had more than cap_keys candidates or a NaN distance showed up -- every rank sees the same
+ * data, so all of them fall back to pqv_l2_topk_candidates together. */
 PQV_API int pqv_peer_exchange_create(pqv_ctx *ctx, uint32_t world, uint32_t rank, uint32_t cap_keys, uint8_t *out_handle64);
 PQV_API int pqv_peer_exchange_open(pqv_ctx *ctx, const uint8_t *handles /* world x 64 bytes, rank order */);
 PQV_API int pqv_l2_topk_candidates_p2p(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags,

@@ -1979,7 +1979,8 @@ static int p2p_collect(pqv_ctx *ctx, uint64_t handle, const float *query, uint32
         CU_TRY(cudaEventRecord(D.ev[2], D.stream));
         g.grid = 0;
     }
-    pqv::peer_publish_kernel<<<px.world, 256, 0, D.stream>>>(D.ent_out.p, px.cap, px.d_peers, px.rank, px.world, seq);
+    pqv::peer_publish_kernel<<<px.world, 256, 0, D.stream>>>(D.ent_out.p, px.cap, px.d_peers, px.rank, px.world, seq,
+                                                             ds->n_rows ? D.final_topk.p : nullptr, k);
     pqv::peer_wait_pack_kernel<<<1, 256, 0, D.stream>>>(px.local, px.cap, px.world, seq, px.h_block.p);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(D.stream));
@@ -2010,6 +2011,10 @@ int pqv_l2_topk_candidates_p2p(pqv_ctx *ctx, uint64_t handle, const float *query
     PQV_TRY(p2p_collect(ctx, handle, query, k, flags, pos_base, &total, out_overflow));
     *out_count = total;
     if (*out_overflow) return PQV_OK;
+    if (any_nan_key(ctx->peer.h_block.p + 2 + ctx->peer.world, total)) {  // NaN distance: the collective path replays every row
+        *out_overflow = 1;
+        return PQV_OK;
+    }
     if (total > cap_total) return fail(PQV_ELIMIT, "%llu candidate keys do not fit the caller's buffer of %llu", (unsigned long long)total, (unsigned long long)cap_total);
     memcpy(out_keys, ctx->peer.h_block.p + 2 + ctx->peer.world, total * 8);
     return PQV_OK;
@@ -2027,6 +2032,10 @@ int pqv_l2_topk_p2p(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t 
     PQV_TRY(p2p_collect(ctx, handle, query, k, flags, pos_base, &total, out_overflow));
     if (*out_overflow) return PQV_OK;
     const u64 *keys = ctx->peer.h_block.p + 2 + ctx->peer.world;
+    if (any_nan_key(keys, total)) {  // a NaN distance: only the loop over every row answers that -- the collective path does it
+        *out_overflow = 1;
+        return PQV_OK;
+    }
     std::vector<u64> ent(keys, keys + total);
     *out_count = (uint32_t)replay_reference_heap(ent, RowMap{}, k, flags, out_row_idx, out_dist);
     return PQV_OK;

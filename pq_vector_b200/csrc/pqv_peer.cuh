@@ -18,9 +18,12 @@ namespace pqv {
 
 // CTA d copies this rank's candidate block (count + min(count, cap) keys) into slot `rank` of peer d's buffer, makes it
 // visible system-wide and then releases the flag.
+// The count word also carries, in its upper half, the distance bits of this rank's final k-th smallest key (0xFFFFFFFF: the
+// slice holds fewer than k rows): the reader uses it to drop the later ranks' entrants that the global heap cannot admit.
 __global__ void __launch_bounds__(256) peer_publish_kernel(const u64 *__restrict__ ent_out, const uint32_t cap,
                                                            u64 *const *__restrict__ peer_base, const uint32_t rank,
-                                                           const uint32_t world, const u64 seq) {
+                                                           const uint32_t world, const u64 seq,
+                                                           const u64 *__restrict__ final_topk, const uint32_t k) {
     const uint32_t d = blockIdx.x;
     const u64 par = seq & 1ull;
     const u64 slot_words = 1ull + cap;
@@ -29,7 +32,10 @@ __global__ void __launch_bounds__(256) peer_publish_kernel(const u64 *__restrict
     const u64 count = ent_out[0];
     const u64 n = count < (u64)cap ? count : (u64)cap;
     for (u64 i = threadIdx.x; i < n; i += blockDim.x) slot[1 + i] = ent_out[1 + i];
-    if (threadIdx.x == 0) slot[0] = count;
+    if (threadIdx.x == 0) {
+        const u64 kth = final_topk ? final_topk[k - 1] : ~0ull;
+        slot[0] = (count & 0xFFFFFFFFull) | ((kth == ~0ull ? 0xFFFFFFFFull : (kth >> 32)) << 32);
+    }
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -61,7 +67,6 @@ __global__ void __launch_bounds__(32) peer_wait_kernel(const u64 *__restrict__ l
 __global__ void __launch_bounds__(256) peer_wait_pack_kernel(const u64 *__restrict__ local_base, const uint32_t cap,
                                                              const uint32_t world, const u64 seq, u64 *__restrict__ out) {
     __shared__ uint32_t s_timed_out;
-    __shared__ u64 s_off[65];
     const u64 par = seq & 1ull;
     const u64 slot_words = 1ull + cap;
     const u64 *slots = local_base + par * world * slot_words;
@@ -81,25 +86,52 @@ __global__ void __launch_bounds__(256) peer_wait_pack_kernel(const u64 *__restri
         }
     }
     __syncthreads();
+    // Rows are numbered rank by rank, so when the global heap reaches rank r's rows it already holds the k best of ranks
+    // < r: its threshold is at most T_r = min_{j<r} (rank j's final k-th distance).  An entrant of rank r with d >= T_r is
+    // never admitted (admission needs d < threshold) and is dropped here; NaN keys always travel (the host decides).
+    // out[2 + r] keeps the RAW count (overflow detection), out[1] = keys actually packed, in no particular order.
+    __shared__ uint32_t s_thr[64], s_raw[64];
+    __shared__ uint32_t s_total, s_over;
     if (threadIdx.x == 0) {
-        u64 total = 0, over = 0;
+        uint32_t T = 0xFFFFFFFFu, over = 0;
         for (uint32_t r = 0; r < world; ++r) {
-            const u64 c = __ldcg(slots + r * slot_words);
+            const u64 head = __ldcg(slots + r * slot_words);
+            const uint32_t c = (uint32_t)head;
             if (c > cap) over = 1;
-            s_off[r] = total;
-            total += c < (u64)cap ? c : (u64)cap;
+            s_thr[r] = T;
+            s_raw[r] = c < cap ? c : cap;
             out[2 + r] = c;
+            const uint32_t kth = (uint32_t)(head >> 32);
+            if (kth < T) T = kth;
         }
-        s_off[world] = total;
-        out[0] = (u64)s_timed_out | (over << 1);
-        out[1] = total;
+        s_total = 0;
+        s_over = over;
     }
     __syncthreads();
+    u64 *dst = out + 2 + world;
     for (uint32_t r = 0; r < world; ++r) {
-        const u64 n = s_off[r + 1] - s_off[r];
+        const uint32_t n = s_raw[r], T = s_thr[r];
         const u64 *src = slots + r * slot_words + 1;
-        u64 *dst = out + 2 + world + s_off[r];
-        for (u64 i = threadIdx.x; i < n; i += blockDim.x) dst[i] = __ldcg(src + i);
+        for (uint32_t i0 = 0; i0 < n; i0 += blockDim.x) {
+            const uint32_t i = i0 + threadIdx.x;
+            u64 key = 0;
+            bool keep = false;
+            if (i < n) {
+                key = __ldcg(src + i);
+                const uint32_t b = (uint32_t)(key >> 32);
+                keep = b < T || (b & 0x7FFFFFFFu) > 0x7F800000u;
+            }
+            const uint32_t m = __ballot_sync(0xffffffffu, keep);
+            uint32_t base = 0;
+            if ((threadIdx.x & 31u) == 0u && m) base = atomicAdd(&s_total, (uint32_t)__popc(m));
+            base = __shfl_sync(0xffffffffu, base, 0);
+            if (keep) dst[base + (uint32_t)__popc(m & ((1u << (threadIdx.x & 31u)) - 1u))] = key;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        out[0] = (u64)s_timed_out | ((u64)s_over << 1);
+        out[1] = s_total;
     }
 }
 
