@@ -95,6 +95,16 @@ def _file_key(path) -> tuple:
     return (os.path.realpath(path), st.st_size, st.st_mtime_ns)
 
 
+def _evict_stale(cache: dict, key: tuple):
+    """a file that was rewritten leaves entries of its old (size, mtime) behind: release their HBM when the path comes back"""
+    for old in [k for k in cache if k[0] == key[0] and k[1:3] != key[1:3]]:
+        obj = cache.pop(old)[0]
+        try:
+            obj.drop()
+        except PqvError:
+            pass
+
+
 # ---------------------------------------------------------------------------------------------------------------
 # Parquet side (host I/O; format as the reference's)
 # ---------------------------------------------------------------------------------------------------------------
@@ -388,7 +398,9 @@ class IndexBuilder:
 
     def _register(self, path, ds, ix, column, shape):
         key = _file_key(path)
-        _tables[key] = (ds, shape[0], shape[1])
+        _evict_stale(_tables, key)
+        _evict_stale(_indexes, key)
+        _tables[key + (column,)] = (ds, shape[0], shape[1])
         _indexes[key] = (ix, column)
 
     def build_inplace(self) -> None:
@@ -420,6 +432,7 @@ def _resident_index(path) -> "tuple[IvfIndex, str]":
     key = _file_key(path)
     hit = _indexes.get(key)
     if hit is None:
+        _evict_stale(_indexes, key)
         blob, column = read_index_payload(path)
         try:
             hit = (context().ivf_from_bytes(blob), column)
@@ -430,9 +443,10 @@ def _resident_index(path) -> "tuple[IvfIndex, str]":
 
 
 def _resident_table(path, column) -> "tuple[Dataset, int, int]":
-    key = _file_key(path)
+    key = _file_key(path) + (column,)   # one resident block per (file state, vector column)
     hit = _tables.get(key)
     if hit is None:
+        _evict_stale(_tables, key)
         _, emb = read_parquet_with_embeddings(path, column)
         hit = (context().dataset_from(emb), emb.shape[0], emb.shape[1])
         _tables[key] = hit

@@ -126,3 +126,25 @@ def test_vector_topk_matches_the_oracle_on_every_list_flavour(B, flavour):
     assert few.num_rows == 12 - len(skip)
     none = B.vector_topk([], "embedding", q, 3, schema=out.schema)
     assert none.num_rows == 0 and none.schema == out.schema
+
+
+def test_resident_tables_are_per_column_and_follow_rewrites(B, tmp_path):
+    """the residency cache: one HBM block per (file state, vector column) -- a second vector column of the same file must
+    not be answered from the first one's rows -- and a rewritten file releases the blocks of its old state"""
+    rng = np.random.default_rng(3)
+    a, b = rng.random((300, 8), dtype=np.float32), rng.random((300, 8), dtype=np.float32) + 5
+    path = str(tmp_path / "two.parquet")
+    _write(path, a.tolist(), other=pa.array(b.tolist(), pa.list_(pa.float32())))
+    da, _, _ = B._resident_table(path, "embedding")
+    db, _, _ = B._resident_table(path, "other")
+    assert da.handle != db.handle
+    assert np.array_equal(da.read(0, 300), a) and np.array_equal(db.read(0, 300), b)
+    assert B._resident_table(path, "embedding")[0].handle == da.handle          # a hit, not a reload
+    n_before = len(B._tables)
+    c = rng.random((400, 8), dtype=np.float32)
+    _write(path, c.tolist(), other=pa.array((c + 1).tolist(), pa.list_(pa.float32())))   # new size / mtime
+    dc, rows, _ = B._resident_table(path, "embedding")
+    assert rows == 400 and np.array_equal(dc.read(0, 400), c)
+    assert len(B._tables) == n_before - 1                                        # both old blocks gone, one new
+    with pytest.raises(Exception):
+        da.read(0, 1)                                                           # the stale block was dropped on the device
