@@ -79,8 +79,31 @@ struct ResidentIndex {
     std::string column;
 };
 std::mutex g_cache_mu;
-std::map<FileKey, ResidentTable> g_tables;
+using TableKey = std::pair<FileKey, std::string>;  // one resident block per (file state, vector column)
+std::map<TableKey, ResidentTable> g_tables;
 std::map<FileKey, ResidentIndex> g_indexes;
+
+// a file that was rewritten leaves entries of its old (size, mtime) behind: release their HBM when the path comes back
+// (g_cache_mu held)
+void evict_stale(const FileKey &key) {
+    pqv_ctx *ctx = gpu();
+    for (auto it = g_tables.begin(); it != g_tables.end();) {
+        if (std::get<0>(it->first.first) == std::get<0>(key) && it->first.first != key) {
+            pqv_dataset_drop(ctx, it->second.handle);
+            it = g_tables.erase(it);
+        } else {
+            ++it;
+        }
+    }
+    for (auto it = g_indexes.begin(); it != g_indexes.end();) {
+        if (std::get<0>(it->first) == std::get<0>(key) && it->first != key) {
+            pqv_ivf_drop(ctx, it->second.handle);
+            it = g_indexes.erase(it);
+        } else {
+            ++it;
+        }
+    }
+}
 
 ResidentTable load_table(const std::string &path, const std::string &column) {
     pqv_ctx *ctx = gpu();
@@ -102,11 +125,12 @@ ResidentTable load_table(const std::string &path, const std::string &column) {
 }
 
 ResidentTable resident_table(const std::string &path, const std::string &column) {
-    const FileKey key = file_key(path);
+    const TableKey key{file_key(path), column};
     {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto it = g_tables.find(key);
         if (it != g_tables.end()) return it->second;
+        evict_stale(key.first);
     }
     ResidentTable t = load_table(path, column);
     std::lock_guard<std::mutex> lk(g_cache_mu);
@@ -121,6 +145,7 @@ ResidentIndex resident_index(const std::string &path) {
         std::lock_guard<std::mutex> lk(g_cache_mu);
         auto it = g_indexes.find(key);
         if (it != g_indexes.end()) return it->second;
+        evict_stale(key);
     }
     auto payload = detail::read_index_payload(path);
     ResidentIndex ix;
@@ -401,7 +426,8 @@ void keep_resident(const std::string &path, const Built &b) {
     uint64_t ids = 0;
     gpu_check(pqv_ivf_info(gpu(), b.index, &dim, &clusters, &ids));
     std::lock_guard<std::mutex> lk(g_cache_mu);
-    g_tables[key] = b.table;
+    evict_stale(key);
+    g_tables[TableKey{key, b.column}] = b.table;
     g_indexes[key] = ResidentIndex{b.index, dim, b.column};
 }
 }  // namespace
