@@ -86,10 +86,10 @@ std::map<FileKey, ResidentIndex> g_indexes;
 // a file that was rewritten leaves entries of its old (size, mtime) behind: release their HBM when the path comes back
 // (g_cache_mu held)
 void evict_stale(const FileKey &key) {
-    pqv_ctx *ctx = gpu();
+    // (an entry can only exist once a context does: nothing here touches the GPU on a cold cache)
     for (auto it = g_tables.begin(); it != g_tables.end();) {
         if (std::get<0>(it->first.first) == std::get<0>(key) && it->first.first != key) {
-            pqv_dataset_drop(ctx, it->second.handle);
+            pqv_dataset_drop(gpu(), it->second.handle);
             it = g_tables.erase(it);
         } else {
             ++it;
@@ -97,7 +97,7 @@ void evict_stale(const FileKey &key) {
     }
     for (auto it = g_indexes.begin(); it != g_indexes.end();) {
         if (std::get<0>(it->first) == std::get<0>(key) && it->first != key) {
-            pqv_ivf_drop(ctx, it->second.handle);
+            pqv_ivf_drop(gpu(), it->second.handle);
             it = g_indexes.erase(it);
         } else {
             ++it;
