@@ -134,3 +134,39 @@ def test_short_prefix_plus_thresholded_candidates_replay_to_the_reference_answer
     rows, d = P.replay_candidates(_keys(dist[sel], sel), k, P.PQV_SQRT if do_sqrt else 0)
     assert rows.tolist() == er.tolist()
     assert d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+
+
+@pytest.mark.parametrize("levels", [0, 3, 40])
+@pytest.mark.parametrize("k", [1, 10, 100])
+@pytest.mark.parametrize("world", [2, 8])
+def test_rank_threshold_prefilter_keeps_the_reference_answer(levels, k, world):
+    """Model of peer_wait_pack_kernel (pqv_peer.cuh): rows are numbered rank by rank, every rank publishes the rows its LOCAL
+    heap admits plus its final k-th smallest distance, and the reader drops rank r's entrants with
+    d >= T_r = min over ranks j < r of (rank j's k-th smallest distance) -- when the global heap reaches rank r's rows it
+    already holds the k best of the earlier ranks, and admission needs d < threshold.  The replay over what is left must be
+    the reference loop over the whole table, ties included (levels: coarse grids -> thousands of bit-equal distances)."""
+    rng = np.random.default_rng(100 * levels + 10 * k + world)
+    per = 4000
+    n = per * world
+    dist = rng.random(n).astype(np.float32) * 4 + 0.5
+    if levels:
+        dist = (np.floor(dist * levels) / levels).astype(np.float32)
+    dist[rng.integers(0, n, 5)] = np.float32(0.25)                     # a few global winners scattered over the ranks
+    kept, T, raw = [], np.float32(np.inf), 0
+    for r in range(world):
+        lo = r * per
+        local = dist[lo:lo + per]
+        ent = lo + _entrants(local, k)                                  # what rank r's scan emits (global positions)
+        raw += ent.size
+        kept.append(ent[dist[ent] < T])                                 # the reader's filter
+        kth = np.partition(local, k - 1)[k - 1] if per >= k else np.float32(np.inf)
+        T = min(T, kth)
+    sel = np.concatenate(kept)
+    assert np.isin(_entrants(dist, k), sel).all()                       # nothing the global heap admits was dropped
+    if levels == 0 and world == 8 and k == 100:
+        assert sel.size < raw // 3                                      # and most of the later ranks' entrants are gone
+    for do_sqrt in (False, True):
+        er, ed = O.heap_topk(dist, None, k, do_sqrt)
+        rows, d = P.replay_candidates(_keys(dist[sel], sel), k, P.PQV_SQRT if do_sqrt else 0)
+        assert rows.tolist() == er.tolist()
+        assert d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
