@@ -216,7 +216,10 @@ __global__ void __launch_bounds__(THREADS) kmeanspp_pick_kernel(const float *__r
     }
     __syncthreads();
     // ---- (c) the walk
-    if (s_mode != 2u) {
+    const bool do_walk = s_mode != 2u;
+    __syncthreads();  // every thread has read the mode before the prologue test below may set it (racecheck: read / write race,
+                      // and a thread that saw the new value would have skipped the barriers inside the block)
+    if (do_walk) {
         const float thr = s_thr;
         if (pro_side && !s_weird) {
             // the prologue's running sums are there: the first one that reaches the threshold, if any (they never decrease)
