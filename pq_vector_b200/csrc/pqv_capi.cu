@@ -370,7 +370,7 @@ struct DeviceState {
     // 16-bit shadow of rows that do not belong to a resident table (host rows streamed through, the k-means training sample)
     DevBuf<__half> ts_half;
     DevBuf<float2> ts_stats;
-    DevBuf<float> ts_mu;
+    DevBuf<float> ts_mu, ts_mean_part;
     DevBuf<pqv::half16::Globals> ts_g;
     cudaEvent_t ev_shadow[2] = {nullptr, nullptr};
     DevBuf<float2> tc_stats;
@@ -1405,6 +1405,7 @@ void pqv_destroy(pqv_ctx *ctx) {
         D.tc_amb_rows.release();
         D.tc_ovf_rows.release();
         D.tc_perm.release();
+        D.ts_mean_part.release();
         D.tc_okeys.release();
         D.tb_Q.release();
         D.tb_Qp.release();

@@ -1297,20 +1297,41 @@ __global__ void __launch_bounds__(256) centroid_update_kernel(const float *__res
                                                               float *__restrict__ centroids) {
     const uint32_t j = blockIdx.x;
     const u64 b = member_offsets[j], e = member_offsets[j + 1];
-    for (uint32_t d = threadIdx.x; d < dim; d += blockDim.x) {
-        float acc = 0.f;
+    // a thread owns up to four columns (d, d + blockDim, ...: coalesced across the CTA) and walks the members once for all of
+    // them: the additions form one serial chain per (cluster, column), the loads do not depend on it -- 8 members x 4
+    // columns in flight (the kernel is pure load latency: one cluster's rows are scattered over the sample)
+    for (uint32_t d0 = threadIdx.x; d0 < dim; d0 += 4u * blockDim.x) {
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+        bool on[4];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) on[c] = d0 + (uint32_t)c * blockDim.x < dim;
         u64 m = b;
-        // the additions form one serial chain per (cluster, column); the loads do not depend on it: 8 in flight
         for (; m + 8 <= e; m += 8) {
-            float v[8];
+            float v[4][8];
 #pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __ldg(data + (u64)__ldg(member_ids + m + i) * dim + d);
+            for (int i = 0; i < 8; ++i) {
+                const float *row = data + (u64)__ldg(member_ids + m + i) * dim + d0;
 #pragma unroll
-            for (int i = 0; i < 8; ++i) acc = __fadd_rn(acc, v[i]);
+                for (int c = 0; c < 4; ++c) v[c][i] = on[c] ? __ldg(row + (size_t)c * blockDim.x) : 0.f;
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) acc[c] = __fadd_rn(acc[c], v[c][i]);
         }
-        for (; m < e; ++m) acc = __fadd_rn(acc, __ldg(data + (u64)__ldg(member_ids + m) * dim + d));
-        if (e > b) acc = __fdiv_rn(acc, (float)(e - b));
-        centroids[(u64)j * dim + d] = acc;
+        for (; m < e; ++m) {
+            const float *row = data + (u64)__ldg(member_ids + m) * dim + d0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                if (on[c]) acc[c] = __fadd_rn(acc[c], __ldg(row + (size_t)c * blockDim.x));
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            if (on[c]) {
+                float a = acc[c];
+                if (e > b) a = __fdiv_rn(a, (float)(e - b));
+                centroids[(u64)j * dim + d0 + (size_t)c * blockDim.x] = a;
+            }
     }
 }
 

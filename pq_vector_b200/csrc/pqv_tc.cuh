@@ -273,12 +273,24 @@ __device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
 // mu = column mean of the centroids (the vector the table is centred on); mu_d = the vector the per-row statistic x.mu_d
 // was computed against: the same mu (mu_data == nullptr: row_stats_kernel ran for this sweep) or the table's cached data
 // mean (pqv_half.cuh).  The consumer needs x.mu only inside a bound: x.mu = x.mu_d + x.(mu - mu_d), |x.(mu - mu_d)| <= |x| |mu - mu_d|.
-__global__ void centroid_mean_kernel(const float *__restrict__ cent, uint32_t C, uint32_t dim, const float *__restrict__ mu_data,
+// column sums of the table in CMEAN_SLICES row slices (blockIdx.y), added in slice order by centroid_mean_kernel: one thread
+// per column walking all C rows cost 46 us per sweep, more than the centroid preparation itself
+constexpr uint32_t CMEAN_SLICES = 16;
+__global__ void centroid_mean_partial_kernel(const float *__restrict__ cent, uint32_t C, uint32_t dim, float *__restrict__ part) {
+    const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
+    if (col >= dim) return;
+    const uint32_t per = (C + CMEAN_SLICES - 1) / CMEAN_SLICES;
+    const uint32_t b = blockIdx.y * per, e = min(C, b + per);
+    float s = 0.f;
+    for (uint32_t j = b; j < e; ++j) s += cent[(size_t)j * dim + col];
+    part[(size_t)blockIdx.y * dim + col] = s;
+}
+__global__ void centroid_mean_kernel(const float *__restrict__ part, uint32_t C, uint32_t dim, const float *__restrict__ mu_data,
                                      float *__restrict__ mu, uint32_t *__restrict__ bounds) {
     const uint32_t col = blockIdx.x * blockDim.x + threadIdx.x;
     if (col >= dim) return;
     float s = 0.f;
-    for (uint32_t j = 0; j < C; ++j) s += cent[(size_t)j * dim + col];
+    for (uint32_t i = 0; i < CMEAN_SLICES; ++i) s += part[(size_t)i * dim + col];
     const float m = s / (float)C;  // any vector is valid here; the mean just keeps |c - mu| small
     mu[col] = m;
     const float md = mu_data ? mu_data[col] : m;

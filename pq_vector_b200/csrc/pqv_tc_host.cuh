@@ -69,7 +69,10 @@ constexpr u64 SHADOW_MEAN_ROWS = 65536;  // rows the data mean is taken over
 int shadow_begin(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, float *mu, pqv::half16::Globals *g) {
     const u64 ns = std::min<u64>(n, SHADOW_MEAN_ROWS);
     CU_TRY(cudaMemsetAsync(g, 0, sizeof(pqv::half16::Globals), D.stream));
-    pqv::half16::column_mean_kernel<<<(dim + 127) / 128, 128, 0, D.stream>>>(d_rows, ns, dim, mu);
+    PQV_TRY(D.ts_mean_part.ensure((size_t)pqv::half16::MEAN_SLICES * dim));
+    pqv::half16::column_mean_partial_kernel<<<dim3((dim + 127) / 128, pqv::half16::MEAN_SLICES), 128, 0, D.stream>>>(
+        d_rows, ns, dim, D.ts_mean_part.p);
+    pqv::half16::column_mean_kernel<<<(dim + 127) / 128, 128, 0, D.stream>>>(D.ts_mean_part.p, ns, dim, mu);
     // absmax of the sample lands (as bits) in the `reserved-for-scale` word, then becomes the power-of-two scale in place
     uint32_t *word = reinterpret_cast<uint32_t *>(&g->scale);
     pqv::half16::absmax_kernel<<<(uint32_t)D.sm_count * 4, 256, 0, D.stream>>>(d_rows, ns * dim, word);
@@ -252,7 +255,9 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
     if (time_it) CU_TRY(cudaEventRecord(D.ev[0], D.stream));
     CU_TRY(cudaMemsetAsync(D.tc_u32.p, 0, 16 * sizeof(uint32_t), D.stream));
     CU_TRY(cudaMemsetAsync(D.tc_wc.p, 0, (size_t)(cn_len / 32) * sizeof(uint32_t), D.stream));
-    T::centroid_mean_kernel<<<(dim + 127) / 128, 128, 0, D.stream>>>(d_cent, C, dim, sv ? sv->mu : nullptr, D.tc_mu.p, bounds);
+    PQV_TRY(D.ts_mean_part.ensure((size_t)pqv::half16::MEAN_SLICES * dim));
+    T::centroid_mean_partial_kernel<<<dim3((dim + 127) / 128, T::CMEAN_SLICES), 128, 0, D.stream>>>(d_cent, C, dim, D.ts_mean_part.p);
+    T::centroid_mean_kernel<<<(dim + 127) / 128, 128, 0, D.stream>>>(D.ts_mean_part.p, C, dim, sv ? sv->mu : nullptr, D.tc_mu.p, bounds);
     // operand scale of the centred table: bounds[5] = max |c - mu| (fp16 only), then the power of two derived from it (1 for tf32)
     if (sv) T::centroid_absmax_kernel<<<(uint32_t)D.sm_count, 256, 0, D.stream>>>(d_cent, C, dim, D.tc_mu.p, bounds + 5);
     pqv::half16::scale_from_absmax_kernel<<<1, 32, 0, D.stream>>>(bounds + 5, reinterpret_cast<float *>(bounds + 5));
