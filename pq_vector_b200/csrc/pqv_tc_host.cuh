@@ -309,7 +309,7 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
                                                                                      D.tc_pairs.p, D.tc_best.p);
     if (time_it) CU_TRY(cudaEventRecord(D.ev[4], D.stream));
     {
-        const uint32_t slice_len = 2 * pqv::AS_BN;
+        const uint32_t slice_len = pqv::AS_BN;  // one centroid tile per CTA: a handful of rows is spread over C / 64 CTAs
         dim3 grid_ovf((uint32_t)std::min<u64>((n + pqv::AS_BM - 1) / pqv::AS_BM, (u64)D.sm_count * 2), (C + slice_len - 1) / slice_len);
         pqv::kmeans_assign_kernel<true, true><<<grid_ovf, 256, 0, D.stream>>>(d_rows, 0, dim, d_cent, C, nullptr, D.tc_ovf_rows.p,
                                                                               counts + 1, D.tc_best.p, slice_len);
