@@ -23,7 +23,8 @@ namespace kpp {
 
 constexpr uint32_t THREADS = 1024, EPT = 4, BLOCK = THREADS * EPT;
 constexpr uint32_t SAT = 1u << 25, TOP = 1u << 24;
-constexpr uint32_t PROLOGUE = 1024;      // plain adds before the first block (the first binades hold a handful of elements each)
+constexpr uint32_t PROLOGUE = 2048;      // plain adds before the first block: the first binades hold a handful of elements each, and
+                                         // about this many dependent adds (with their stores) fit beside the worker-chunk chains (3125 elements each at 16 workers)
 constexpr uint32_t SERIAL_BURST = 256;   // plain adds when the state is zero / tiny or a block made almost no progress
 constexpr uint32_t NONE = 0xFFFFFFFFu;
 constexpr uint32_t MAX_ROWS = 50000;     // init set of the reference (index.rs:332); 200 000 B of shared memory
@@ -161,7 +162,20 @@ __global__ void __launch_bounds__(THREADS) kmeanspp_pick_kernel(const float *__r
     const bool pro_side = n_chunks <= THREADS - 32u;
     if (pro_side && tid == THREADS - 1u && !s_weird) {
         float y = 0.f;
-        for (uint32_t i = 0; i < pro_n; ++i) {
+        uint32_t i = 0;
+        for (; i + 8 <= pro_n; i += 8) {  // loads first, then the dependent adds, then the stores
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = smd[i + j];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                y = __fadd_rn(y, v[j]);
+                v[j] = y;
+            }
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s_pre[i + j] = v[j];
+        }
+        for (; i < pro_n; ++i) {
             y = __fadd_rn(y, smd[i]);
             s_pre[i] = y;
         }
@@ -223,10 +237,11 @@ __global__ void __launch_bounds__(THREADS) kmeanspp_pick_kernel(const float *__r
         const float thr = s_thr;
         if (pro_side && !s_weird) {
             // the prologue's running sums are there: the first one that reaches the threshold, if any (they never decrease)
-            if (tid < pro_n && s_pre[tid] >= thr && (tid == 0u || !(s_pre[tid - 1u] >= thr))) {
-                s_pick = tid;
-                s_mode = 2u;
-            }
+            for (uint32_t i = tid; i < pro_n; i += THREADS)
+                if (s_pre[i] >= thr && (i == 0u || !(s_pre[i - 1u] >= thr))) {
+                    s_pick = i;
+                    s_mode = 2u;
+                }
             if (tid == 0) {
                 s_x = s_pre[pro_n - 1u];
                 s_base = pro_n;
