@@ -199,3 +199,28 @@ def test_default_path_selection(ctx):
     assert ctx.last_assign_timing()["path"] == 0
     ctx.kmeans_assign(np.ascontiguousarray(data[:, :63]), np.ascontiguousarray(cent[:, :63]))  # dim % 4 != 0
     assert ctx.last_assign_timing()["path"] == 0
+
+
+@pytest.mark.parametrize("n,dim,c", [(12000, 64, 2048), (9000, 128, 3000), (6000, 32, 4096)])
+def test_wide_tables_take_the_unstaged_constants(ctx, n, dim, c):
+    """more centroids than the epilogue stages in shared memory (norms / weights / group maxima then come from global
+    memory, and the 60-bit group stack runs at its widest indices)"""
+    rng = np.random.default_rng(n + c)
+    data = rng.random((n, dim), dtype=np.float32)
+    cent = kmeans_like_centroids(data, c, rng, per=3)
+    check(ctx, data, cent)
+
+
+def test_heavy_tailed_centroid_spread(ctx):
+    """a table as k-means++ + a few Lloyd rounds leave it: most centroids near the data mean, some single-member clusters
+    (raw rows, |c - mu| ten times larger), an empty cluster at the origin (index.rs:446-453) -- the far-out columns inflate
+    the error weight of their chunk, and used to keep the window of 31 neighbours open (group store overflow)"""
+    rng = np.random.default_rng(99)
+    n, dim, c = 40000, 256, 1024
+    data = rng.random((n, dim), dtype=np.float32)
+    cent = kmeans_like_centroids(data, c, rng, per=64)
+    far = rng.choice(c, 120, replace=False)
+    cent[far] = data[rng.choice(n, 120, replace=False)]          # single-member clusters
+    cent[far[:3]] = 0.0                                           # empty clusters
+    t = check(ctx, data, cent)
+    assert t["overflow_rows"] < n // 100, t                       # the store copes: almost nothing goes to the exact scan
