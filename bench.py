@@ -668,7 +668,8 @@ def leg_c5(env, P, ctx, n, dim, peaks, cpu=True):
                              "pqv_l2_topk_batch_keys per rank + one all-gather + pqv_merge_batch_keys (+ candidate exchange for tie queries)")},
             "rank0_batch_timing": tm, "replayed_queries": sb.last_replayed if world > 1 else tm["tie_queries"],
             "tflops_aggregate_e2e": 2.0 * n_glob * nq * dim / e2e / 1e12,
-            "identical_to_single_query_search_on": 4 if ok else -1}
+            "identical_to_single_query_search_on": 4 if ok else -1,
+            "rank0_e2e_phases_ms": (getattr(sb, "last_phase_ms", None) if world > 1 else None)}
         if cpu and world == 1:
             import oracle as O
             samp, sq = min(250_000, n), 8

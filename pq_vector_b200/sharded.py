@@ -112,6 +112,7 @@ class ShardedBatchTopk:
         self.single = ShardedTopk(scan_fn, pos_base, device, group)
         self.last_gather_bytes = 0
         self.last_replayed = 0
+        self.last_phase_ms = {}
 
     def _all_gather(self, arr: np.ndarray) -> np.ndarray:
         """[world, len(arr)] int64, same on every rank"""
@@ -124,18 +125,25 @@ class ShardedBatchTopk:
         return recv.cpu().numpy().reshape(self.world, send.numel())
 
     def search(self, queries, k: int, flags: int):
+        import time
         queries = np.ascontiguousarray(queries, dtype=np.float32)
         nq = queries.shape[0]
         self.last_gather_bytes = 0
+        t0 = time.perf_counter()
         keys, counts = self.batch_fn(queries, k, flags, self.pos_base)
+        t1 = time.perf_counter()
         # one payload per rank: [nq, k+1] keys followed by the nq counts (widened to 64 bit)
         got = self._all_gather(np.concatenate([keys.reshape(-1).view(np.int64), counts.astype(np.int64)]))
+        t2 = time.perf_counter()
         all_keys = got[:, :nq * (k + 1)].view(np.uint64).reshape(self.world, nq, k + 1)
         all_counts = got[:, nq * (k + 1):].astype(np.uint32)
         rows, dd, cnt, need = merge_batch_keys(all_keys, all_counts, k, flags)
+        t3 = time.perf_counter()
         # deterministic on identical gathered data -> every rank sees the same flagged queries, in the same order
         ties = np.nonzero(need)[0]
         self.last_replayed = int(ties.size)
+        # where a call's wall time went on this rank (ms): the per-rank pass, the all-gather, the merge; "ties" is added below
+        self.last_phase_ms = {"pass": (t1 - t0) * 1e3, "all_gather": (t2 - t1) * 1e3, "merge": (t3 - t2) * 1e3, "ties": 0.0}
         if ties.size == 0:
             return rows, dd, cnt
         # candidates of ALL flagged queries travel together: one all-gather of their lengths, one of the padded keys
@@ -155,6 +163,7 @@ class ShardedBatchTopk:
             cnt[q] = r_.size
             rows[q, :r_.size] = r_
             dd[q, :r_.size] = d_
+        self.last_phase_ms["ties"] = (time.perf_counter() - t3) * 1e3
         return rows, dd, cnt
 
 
