@@ -611,7 +611,7 @@ def leg_c3(env, P, ctx, ds, n, dim, peaks, cpu=True):
     return out
 
 
-def leg_c5(env, P, ctx, n, dim, peaks, cpu=True):
+def leg_c5(env, P, ctx, n, dim, peaks, cpu=True, exchange_pref="p2p"):
     """BASELINE configs[4] shape: rows sharded over the ranks (6.25M x 768 per GPU = 50M at N = 8), 1024 queries per batch,
     k = 10, VectorTopKExec arithmetic (PQV_SUM_SEQ).  Every rank answers the batch over its slice in one tensor-core pass,
     ONE all-gather, host merge, tie queries through the candidate exchange."""
@@ -625,6 +625,19 @@ def leg_c5(env, P, ctx, n, dim, peaks, cpu=True):
     sb = ShardedBatchTopk(lambda q, k_, f_, pb: ds.l2_topk_batch_keys(q, k_, f_, pb),
                           lambda q, k_, f_, pb: ds.l2_topk_candidates(q, k_, f_, pb), pos_base, dev,
                           tie_fn=lambda qi, q: ds.l2_topk_batch_tie_candidates(qi, q))
+    exchange = "none" if world == 1 else "nccl"
+    if world > 1 and exchange_pref == "p2p":
+        try:
+            sb.enable_p2p(ctx, ds, nq, k)
+            ok = True
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] rank {rank}: peer exchange set-up failed ({e}); using the NCCL all-gather", file=sys.stderr)
+            ok = False
+        if env.all_ok(ok):
+            exchange = "p2p"
+        else:
+            sb._p2p = None
+            sb.single._p2p = None
     search = (lambda: ds.l2_topk(queries, k, flags)) if world == 1 else (lambda: sb.search(queries, k, flags))
     for _ in range(3):
         search()   # warm-up: allocations, row statistics / shadow, NCCL channels
@@ -663,9 +676,13 @@ def leg_c5(env, P, ctx, n, dim, peaks, cpu=True):
                          "algorithmic_flops_per_launch": flops, "kernel_ms": tm["filter_ms"],
                          "hbm_gbs_of_the_pass": n * dim * 4 / (tm["filter_ms"] * 1e-3) / 1e9},
             "e2e": {"value": nq / e2e, "unit": UNIT, "ms_per_step": e2e * 1e3,
-                    "h2d_bytes_per_step": nq * dim * 4, "d2h_bytes_per_step": nq * (k + 1) * 8 + nq * 8 + (sb.last_gather_bytes if world > 1 else 0),
+                    "h2d_bytes_per_step": nq * dim * 4,
+                    "d2h_bytes_per_step": (nq * (k + 1) * 8 + nq * 8) * (world if exchange == "p2p" else 1) + (sb.last_gather_bytes if world > 1 else 0),
+                    "exchange": exchange,
                     "path": ("pqv_l2_topk(n_queries = 1024): host queries in, host results out" if world == 1 else
-                             "pqv_l2_topk_batch_keys per rank + one all-gather + pqv_merge_batch_keys (+ candidate exchange for tie queries)")},
+                             ("pqv_l2_topk_batch_p2p: host queries in, host results out; per-rank tensor-core pass + NVLink peer-write "
+                              "exchange of the key lists + host merge + tie replays in one native call" if exchange == "p2p" else
+                              "pqv_l2_topk_batch_keys per rank + one all-gather + pqv_merge_batch_keys (+ candidate exchange for tie queries)"))},
             "rank0_batch_timing": tm, "replayed_queries": sb.last_replayed if world > 1 else tm["tie_queries"],
             "tflops_aggregate_e2e": 2.0 * n_glob * nq * dim / e2e / 1e12,
             "identical_to_single_query_search_on": 4 if ok else -1,
@@ -723,7 +740,7 @@ def run_ours(args):
             rec["value_definition"] = "queries/s over the whole table (compare with the N=1 headline: same table, one GPU)"
             configs["strong"] = rec
     if "c5" in args.legs:
-        rec = leg_c5(env, P, ctx, int(6_250_000 * scale), dim, peaks, cpu)
+        rec = leg_c5(env, P, ctx, int(6_250_000 * scale), dim, peaks, cpu, args.exchange)
         if rank == 0:
             configs["c5"] = rec
     if "c4" in args.legs:

@@ -230,6 +230,16 @@ PQV_API int pqv_l2_topk_candidates_p2p(pqv_ctx *ctx, uint64_t handle, const floa
  * row_idx = pos_base + local row.  *out_overflow = 1 (nothing else written) as above. */
 PQV_API int pqv_l2_topk_p2p(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t pos_base,
                             uint32_t *out_row_idx, float *out_dist, uint32_t *out_count, uint32_t *out_overflow);
+/* The batched form (config C5 with one process per GPU): this rank's tensor-core pass over its slice (pqv_l2_topk_batch_keys
+ * below), the per-query key lists of all ranks exchanged over the same peer buffers, merged on the host
+ * (pqv_merge_batch_keys), and the queries the merge cannot decide replayed from their candidates
+ * (pqv_l2_topk_batch_tie_candidates + the exchange + pqv_replay_candidates) -- one call, the same bit-exact results on every
+ * rank (out_*[q*k + i], out_count[q]; *out_replayed = queries that needed the heap replay).  The exchange slots must hold
+ * n_queries * (k + 2) words (pqv_peer_exchange_create's cap_keys); *out_overflow = 1 otherwise, or when a rank's slice
+ * declined the batch / a NaN distance showed up -- all ranks see it and take the collective path together. */
+PQV_API int pqv_l2_topk_batch_p2p(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k,
+                                  uint32_t flags, uint32_t pos_base, uint32_t *out_row_idx, float *out_dist,
+                                  uint32_t *out_count, uint32_t *out_replayed, uint32_t *out_overflow);
 
 /* Batched variant (config C5: many queries, rows sharded over the ranks).  pqv_l2_topk_batch_keys answers the batch
  * over this rank's slice in one tensor-core pass and returns, per query, the k + 1 smallest

@@ -81,6 +81,8 @@ SIGNATURES = {
     "pqv_l2_topk_candidates_p2p": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u64p, C.c_uint64,
                                              u64p, u32p]),
     "pqv_l2_topk_p2p": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p, u32p, u32p]),
+    "pqv_l2_topk_batch_p2p": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u32p, f32p,
+                                        u32p, u32p, u32p]),
     "pqv_l2_topk_batch_keys": (C.c_int, [ctxp, C.c_uint64, f32p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, u64p,
                                          u32p]),
     "pqv_l2_topk_batch_tie_candidates": (C.c_int, [ctxp, C.c_uint64, C.c_uint32, f32p, u64p, C.c_uint64, u64p]),

@@ -352,6 +352,23 @@ class Dataset:
                                     _ptr(dist, C.c_float), C.byref(cnt), C.byref(ovf)))
         return None if ovf.value else (rows[:cnt.value], dist[:cnt.value])
 
+    def l2_topk_batch_p2p(self, queries, k: int, flags: int = N.PQV_SQRT, pos_base: int = 0):
+        """This rank's whole sharded batch in one call (pqv_l2_topk_batch_p2p): tensor-core pass over the slice, key lists
+        exchanged over NVLink peer memory, host merge, tie queries replayed.  Returns (row_idx [nq,k], dist [nq,k], count [nq],
+        replayed) -- identical on every rank -- or None when the exchange slots are too small / a slice declined the batch."""
+        q = np.atleast_2d(_f32(queries))
+        if q.shape[1] != self.dim:
+            raise PqvError(N.PQV_EINVAL, f"Query dimension mismatch: expected {self.dim}, got {q.shape[1]}")
+        nq, kk = q.shape[0], max(k, 1)
+        rows = np.zeros((nq, kk), dtype=np.uint32)
+        dist = np.zeros((nq, kk), dtype=np.float32)
+        cnt = np.zeros(nq, dtype=np.uint32)
+        rep, ovf = C.c_uint32(), C.c_uint32()
+        _check(_lib.pqv_l2_topk_batch_p2p(self.ctx._h, self.handle, _ptr(q, C.c_float), nq, k, flags, pos_base,
+                                          _ptr(rows, C.c_uint32), _ptr(dist, C.c_float), _ptr(cnt, C.c_uint32), C.byref(rep),
+                                          C.byref(ovf)))
+        return None if ovf.value else (rows, dist, cnt, rep.value)
+
     def l2_topk_batch_keys(self, queries, k: int, flags: int = N.PQV_SQRT, pos_base: int = 0):
         """Per-rank half of a sharded batched search: (keys [nq, k+1] u64, counts [nq] u32), see pqv.h."""
         q = _f32(queries)

@@ -1796,11 +1796,17 @@ int pqv_replay_candidates(const uint64_t *keys, uint64_t n_keys, const uint32_t 
     return PQV_OK;
 }
 
+static int batch_keys_locked(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k, uint32_t flags,
+                             uint32_t pos_base, uint64_t *out_keys, uint32_t *out_count);
 int pqv_l2_topk_batch_keys(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k,
                            uint32_t flags, uint32_t pos_base, uint64_t *out_keys, uint32_t *out_count) {
     if (!ctx) return fail(PQV_EINVAL, "null ctx");
     if (n_queries && (!queries || !out_keys || !out_count)) return fail(PQV_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    return batch_keys_locked(ctx, handle, queries, n_queries, k, flags, pos_base, out_keys, out_count);
+}
+static int batch_keys_locked(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k, uint32_t flags,
+                             uint32_t pos_base, uint64_t *out_keys, uint32_t *out_count) {
     Dataset *ds = find_dataset(ctx, handle);
     if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
     PQV_TRY(check_topk_args(k, ds->dim, flags));
@@ -1826,10 +1832,19 @@ int pqv_l2_topk_batch_keys(pqv_ctx *ctx, uint64_t handle, const float *queries, 
     return PQV_OK;
 }
 
+static int tie_candidates_locked(pqv_ctx *ctx, uint64_t handle, uint32_t q_index, const float *query, std::vector<u64> &ent);
 int pqv_l2_topk_batch_tie_candidates(pqv_ctx *ctx, uint64_t handle, uint32_t q_index, const float *query, uint64_t *out_keys,
                                      uint64_t cap, uint64_t *out_count) {
     if (!ctx || !query || !out_count || (cap && !out_keys)) return fail(PQV_EINVAL, "null argument");
     std::lock_guard<std::mutex> lk(ctx->mu);
+    std::vector<u64> ent;
+    PQV_TRY(tie_candidates_locked(ctx, handle, q_index, query, ent));
+    *out_count = ent.size();
+    if (ent.size() > cap) return fail(PQV_ELIMIT, "%zu candidate keys do not fit the caller's buffer of %llu", ent.size(), (unsigned long long)cap);
+    if (!ent.empty()) memcpy(out_keys, ent.data(), ent.size() * 8);
+    return PQV_OK;
+}
+static int tie_candidates_locked(pqv_ctx *ctx, uint64_t handle, uint32_t q_index, const float *query, std::vector<u64> &ent) {
     pqv_ctx::BatchState &bs = ctx->batch_state;
     if (!bs.valid || bs.handle != handle) return fail(PQV_EINVAL, "no batched pass of this dataset is pending (call pqv_l2_topk_batch_keys first)");
     if (q_index >= bs.nq) return fail(PQV_EINVAL, "query index %u out of range (batch of %u)", q_index, bs.nq);
@@ -1837,7 +1852,7 @@ int pqv_l2_topk_batch_tie_candidates(pqv_ctx *ctx, uint64_t handle, uint32_t q_i
     if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
     // admissions of the reference heap inside this slice: positions < S from the exact scan of that prefix alone,
     // positions >= S are all among the query's candidates of the batched pass
-    std::vector<u64> ent;
+    ent.clear();
     uint32_t dummy = 0;
     PQV_TRY(topk_one(ctx, *ds, query, nullptr, 0, bs.k, bs.flags, nullptr, nullptr, &dummy, &ent, bs.pos_base, nullptr, nullptr, bs.S));
     DeviceState &D = ctx->devs[bs.dev_index];
@@ -1847,9 +1862,6 @@ int pqv_l2_topk_batch_tie_candidates(pqv_ctx *ctx, uint64_t handle, uint32_t q_i
     if (cq) CU_TRY(cudaMemcpy(seg.data(), D.tb_seg.p + (size_t)q_index * bs.cap_q, (size_t)cq * 8, cudaMemcpyDeviceToHost));
     for (u64 key : seg)
         if (key_pos(key) >= bs.S) ent.push_back(key + bs.pos_base);
-    *out_count = ent.size();
-    if (ent.size() > cap) return fail(PQV_ELIMIT, "%zu candidate keys do not fit the caller's buffer of %llu", ent.size(), (unsigned long long)cap);
-    if (!ent.empty()) memcpy(out_keys, ent.data(), ent.size() * 8);
     return PQV_OK;
 }
 
@@ -1860,8 +1872,8 @@ int pqv_merge_batch_keys(const uint64_t *keys, const uint32_t *counts, uint32_t 
     if (n_queries && (!out_row_idx || !out_dist || !out_count || !out_needs_replay)) return fail(PQV_EINVAL, "null argument");
     if (k == 0) return fail(PQV_EINVAL, "k must be > 0");
     const size_t kp = (size_t)k + 1;
-    // queries are independent: large batches are merged by a few host threads (1024 queries x 8 ranks: 0.75 -> ~0.1 ms)
-    const uint32_t n_thr = n_queries >= 256 ? (uint32_t)std::min<size_t>(tie_threads(), n_queries / 64) : 1u;
+    // queries are independent: large batches are merged by up to four host threads
+    const uint32_t n_thr = n_queries >= 512 ? (uint32_t)std::min<size_t>(std::min<size_t>(tie_threads(), 4), n_queries / 256) : 1u;  // spawning costs ~25 us each
     auto merge_range = [&](uint32_t q_begin, uint32_t q_end) {
     std::vector<u64> all;
     for (uint32_t q = q_begin; q < q_end; ++q) {
@@ -1995,7 +2007,7 @@ static int p2p_collect(pqv_ctx *ctx, uint64_t handle, const float *query, uint32
     }
     pqv::peer_publish_kernel<<<px.world, 256, 0, D.stream>>>(D.ent_out.p, px.cap, px.d_peers, px.rank, px.world, seq,
                                                              ds->n_rows ? D.final_topk.p : nullptr, k);
-    pqv::peer_wait_pack_kernel<<<1, 256, 0, D.stream>>>(px.local, px.cap, px.world, seq, px.h_block.p);
+    pqv::peer_wait_pack_kernel<<<1, 256, 0, D.stream>>>(px.local, px.cap, px.world, seq, px.h_block.p, 0u);
     CU_TRY(cudaGetLastError());
     CU_TRY(cudaStreamSynchronize(D.stream));
     const u64 *hb = px.h_block.p;
@@ -2052,6 +2064,125 @@ int pqv_l2_topk_p2p(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t 
     }
     std::vector<u64> ent(keys, keys + total);
     *out_count = (uint32_t)replay_reference_heap(ent, RowMap{}, k, flags, out_row_idx, out_dist);
+    return PQV_OK;
+}
+
+// `n_words` host words of this rank travel to every peer and come back as [rank][n_words] (same order on every rank) in
+// px.h_block behind the header; raw = 1 keeps every word in place (a structured payload), raw = 0 packs candidate keys.
+// ctx->mu held.  *out_overflow = 1: the payload does not fit a slot (nothing sent: every rank passes the same size).
+static int p2p_exchange_words(pqv_ctx *ctx, DeviceState &D, const u64 *words, u64 n_words, uint32_t raw, u64 *out_total,
+                              uint32_t *out_overflow) {
+    PeerExchange &px = ctx->peer;
+    *out_overflow = 0;
+    *out_total = 0;
+    if (n_words > px.cap) {
+        *out_overflow = 1;
+        return PQV_OK;
+    }
+    DevGuard guard(D.dev);
+    const u64 seq = ++px.seq;
+    PQV_TRY(D.ent_out.ensure((size_t)std::max<u64>(n_words, 1u << 16) + 1));
+    PQV_TRY(D.h_ent_out.ensure((size_t)std::max<u64>(n_words, ENT_FIRST_CHUNK) + 1));
+    D.h_ent_out.p[0] = n_words;
+    if (n_words) memcpy(D.h_ent_out.p + 1, words, n_words * 8);
+    CU_TRY(cudaMemcpyAsync(D.ent_out.p, D.h_ent_out.p, (n_words + 1) * 8, cudaMemcpyHostToDevice, D.stream));
+    pqv::peer_publish_kernel<<<px.world, 256, 0, D.stream>>>(D.ent_out.p, px.cap, px.d_peers, px.rank, px.world, seq, nullptr, 1u);
+    pqv::peer_wait_pack_kernel<<<1, 256, 0, D.stream>>>(px.local, px.cap, px.world, seq, px.h_block.p, raw);
+    CU_TRY(cudaGetLastError());
+    CU_TRY(cudaStreamSynchronize(D.stream));
+    const u64 *hb = px.h_block.p;
+    if (hb[0] & 1ull) return fail(PQV_ECUDA, "peer exchange timed out waiting for the other ranks (sequence %llu)", (unsigned long long)seq);
+    if (hb[0] & 2ull) *out_overflow = 1;
+    *out_total = hb[1];
+    return PQV_OK;
+}
+
+// A rank's whole sharded BATCH in one call (config C5 from one process per GPU): the tensor-core pass over this rank's slice
+// (pqv_l2_topk_batch_keys), the per-query key lists of all ranks exchanged over NVLink peer memory, merged on the host
+// (pqv_merge_batch_keys), and the queries the merge cannot decide (exact ties) replayed from their candidates
+// (pqv_l2_topk_batch_tie_candidates + the same exchange + pqv_replay_candidates).  Every rank passes the same queries and
+// receives the same bit-exact results.  *out_overflow = 1: the payload does not fit the exchange slots (create them with
+// cap_keys >= n_queries * (k + 2)) or a rank's slice declined the batch -- all ranks see it and take the collective path.
+int pqv_l2_topk_batch_p2p(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_queries, uint32_t k, uint32_t flags,
+                          uint32_t pos_base, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count, uint32_t *out_replayed,
+                          uint32_t *out_overflow) {
+    if (!ctx || !out_overflow) return fail(PQV_EINVAL, "null argument");
+    if (n_queries && (!queries || !out_row_idx || !out_dist || !out_count)) return fail(PQV_EINVAL, "null argument");
+    std::lock_guard<std::mutex> lk(ctx->mu);
+    PeerExchange &px = ctx->peer;
+    if (!px.ready) return fail(PQV_EINVAL, "the peer exchange is not set up (pqv_peer_exchange_create / _open)");
+    *out_overflow = 0;
+    if (out_replayed) *out_replayed = 0;
+    if (n_queries == 0) return PQV_OK;
+    Dataset *ds = find_dataset(ctx, handle);
+    if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
+    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "single-device dataset expected");
+    DeviceState &D = ctx->devs[ds->shards[0].di];
+    const size_t kp = (size_t)k + 1, nq = n_queries;
+    const u64 n_words = nq * kp + nq;
+    static const bool trace = getenv("PQV_TRACE") != nullptr;
+    double tt[5] = {trace_now_ms(), 0, 0, 0, 0};
+    // this rank's pass: k + 1 keys per query + the counts (widened to one word each) behind them
+    std::vector<u64> mine(n_words, pqv::KEY_MAX);
+    std::vector<uint32_t> cnt32(nq);
+    PQV_TRY(batch_keys_locked(ctx, handle, queries, n_queries, k, flags, pos_base, reinterpret_cast<uint64_t *>(mine.data()), cnt32.data()));
+    for (size_t q = 0; q < nq; ++q) mine[nq * kp + q] = cnt32[q];
+    u64 total = 0;
+    tt[1] = trace_now_ms();
+    PQV_TRY(p2p_exchange_words(ctx, D, mine.data(), n_words, 1u, &total, out_overflow));
+    tt[2] = trace_now_ms();
+    if (*out_overflow) return PQV_OK;
+    if (total != n_words * px.world) {  // the ranks did not send the same shape: nothing to merge
+        *out_overflow = 1;
+        return PQV_OK;
+    }
+    const u64 *un = px.h_block.p + 2 + px.world;
+    std::vector<u64> all_keys((size_t)px.world * nq * kp);
+    std::vector<uint32_t> all_cnt((size_t)px.world * nq);
+    uint32_t undecided = 0;
+    for (uint32_t r = 0; r < px.world; ++r) {
+        memcpy(all_keys.data() + (size_t)r * nq * kp, un + (size_t)r * n_words, nq * kp * 8);
+        for (size_t q = 0; q < nq; ++q) {
+            all_cnt[(size_t)r * nq + q] = (uint32_t)un[(size_t)r * n_words + nq * kp + q];
+            undecided += all_cnt[(size_t)r * nq + q] == 0xFFFFFFFFu ? 1u : 0u;
+        }
+    }
+    if (undecided > 64) {  // some slice declined the batch: hundreds of single scans belong to the caller's collective path
+        *out_overflow = 1;
+        return PQV_OK;
+    }
+    std::vector<uint8_t> need(nq, 0);
+    PQV_TRY(pqv_merge_batch_keys(reinterpret_cast<const uint64_t *>(all_keys.data()), all_cnt.data(), px.world, n_queries, k, flags,
+                                 out_row_idx, out_dist, out_count, need.data()));
+    tt[3] = trace_now_ms();
+    // flagged queries: deterministic on identical data, so every rank walks the same list in the same order
+    const bool pending = ctx->batch_state.valid && ctx->batch_state.handle == handle;
+    std::vector<u64> cand;
+    for (uint32_t q = 0; q < n_queries; ++q) {
+        if (!need[q]) continue;
+        const float *qv = queries + (size_t)q * ds->dim;
+        if (pending) {
+            PQV_TRY(tie_candidates_locked(ctx, handle, q, qv, cand));
+        } else {  // no batched pass on this rank (tiny / unaligned slice): candidates of the full single-query scan
+            cand.clear();
+            uint32_t dummy = 0;
+            PQV_TRY(topk_one(ctx, *ds, qv, nullptr, 0, k, flags, nullptr, nullptr, &dummy, &cand, pos_base));
+        }
+        PQV_TRY(p2p_exchange_words(ctx, D, cand.data(), cand.size(), 0u, &total, out_overflow));
+        if (*out_overflow) return PQV_OK;
+        const u64 *keys = px.h_block.p + 2 + px.world;
+        if (any_nan_key(keys, total)) {
+            *out_overflow = 1;
+            return PQV_OK;
+        }
+        std::vector<u64> ent(keys, keys + total);
+        out_count[q] = (uint32_t)replay_reference_heap(ent, RowMap{}, k, flags, out_row_idx + (size_t)q * k, out_dist + (size_t)q * k);
+        if (out_replayed) ++*out_replayed;
+    }
+    if (trace)
+        fprintf(stderr, "[pqv trace] batch_p2p rank %u: pass %.2f ms (device %.2f), exchange (incl. waiting for the peers) %.2f, merge %.2f, "
+                        "tie replays %.2f\n", px.rank, tt[1] - tt[0], ctx->last_batch.total_ms, tt[2] - tt[1], tt[3] - tt[2],
+                trace_now_ms() - tt[3]);
     return PQV_OK;
 }
 

@@ -65,7 +65,9 @@ __global__ void __launch_bounds__(32) peer_wait_kernel(const u64 *__restrict__ l
 // out[2 + r] = count of rank r, keys from out[2 + world] on.  A search reads back a few KB instead of the whole
 // world x (1 + cap) block, and needs no separate copy after the kernel.
 __global__ void __launch_bounds__(256) peer_wait_pack_kernel(const u64 *__restrict__ local_base, const uint32_t cap,
-                                                             const uint32_t world, const u64 seq, u64 *__restrict__ out) {
+                                                             const uint32_t world, const u64 seq, u64 *__restrict__ out,
+                                                             const uint32_t raw) {
+    // raw != 0: a structured payload (batch key lists): every word of every slot, in place and in rank order, no filter
     __shared__ uint32_t s_timed_out;
     const u64 par = seq & 1ull;
     const u64 slot_words = 1ull + cap;
@@ -102,13 +104,28 @@ __global__ void __launch_bounds__(256) peer_wait_pack_kernel(const u64 *__restri
             s_raw[r] = c < cap ? c : cap;
             out[2 + r] = c;
             const uint32_t kth = (uint32_t)(head >> 32);
-            if (kth < T) T = kth;
+            if (kth < T && !raw) T = kth;
         }
         s_total = 0;
         s_over = over;
     }
     __syncthreads();
     u64 *dst = out + 2 + world;
+    if (raw) {
+        uint32_t off = 0;
+        for (uint32_t r = 0; r < world; ++r) {
+            const uint32_t n = s_raw[r];
+            const u64 *src = slots + r * slot_words + 1;
+            for (uint32_t i = threadIdx.x; i < n; i += blockDim.x) dst[off + i] = __ldcg(src + i);
+            off += n;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            out[0] = (u64)s_timed_out | ((u64)s_over << 1);
+            out[1] = off;
+        }
+        return;
+    }
     for (uint32_t r = 0; r < world; ++r) {
         const uint32_t n = s_raw[r], T = s_thr[r];
         const u64 *src = slots + r * slot_words + 1;

@@ -113,6 +113,15 @@ class ShardedBatchTopk:
         self.last_gather_bytes = 0
         self.last_replayed = 0
         self.last_phase_ms = {}
+        self._p2p = None
+
+    def enable_p2p(self, ctx, dataset, nq: int, k: int):
+        """Answer batches with ONE native call per rank (pqv_l2_topk_batch_p2p): the key lists travel over NVLink peer memory
+        instead of an all-gather, merge and tie replays stay in the library.  The exchange slots are sized for nq x (k + 2)
+        words; a batch that does not fit (or that a slice declines) takes the collective path below on every rank."""
+        self.single.cap = max(self.single.cap, nq * (k + 2))
+        self.single.enable_p2p(ctx, dataset)
+        self._p2p = dataset
 
     def _all_gather(self, arr: np.ndarray) -> np.ndarray:
         """[world, len(arr)] int64, same on every rank"""
@@ -130,6 +139,12 @@ class ShardedBatchTopk:
         nq = queries.shape[0]
         self.last_gather_bytes = 0
         t0 = time.perf_counter()
+        if self._p2p is not None:
+            got = self._p2p.l2_topk_batch_p2p(queries, k, flags, self.pos_base)
+            if got is not None:
+                rows, dd, cnt, self.last_replayed = got
+                self.last_phase_ms = {"native_call": (time.perf_counter() - t0) * 1e3}
+                return rows, dd, cnt
         keys, counts = self.batch_fn(queries, k, flags, self.pos_base)
         t1 = time.perf_counter()
         # one payload per rank: [nq, k+1] keys followed by the nq counts (widened to 64 bit)
