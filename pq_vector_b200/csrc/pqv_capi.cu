@@ -2251,8 +2251,12 @@ int pqv_bench_scan(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k
 }
 
 // ---- k-means pieces ------------------------------------------------------------------------------
+struct SweepTune {
+    bool repeated = false;  // the same rows are swept again and again: the one-group-per-warp shape with L2 eviction hints
+    u64 keep_groups = 0;    // groups [0, keep_groups) are loaded evict_last (kept in L2 for the next sweep), the rest evict_first
+};
 static int dist_launch(DeviceState &D, const float *d_data, const uint32_t *d_ids, u64 n, uint32_t dim, const float *d_vec,
-                       float *d_out, int min_update, float *h_mirror = nullptr) {
+                       float *d_out, int min_update, float *h_mirror = nullptr, const SweepTune *tune = nullptr) {
     const bool vec4 = (dim % 4 == 0) && ((reinterpret_cast<uintptr_t>(d_data) & 15) == 0);
     const size_t smem = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)SCAN_WARPS * pqv::TileCfg<0, true>::TILE_FLOATS * 4;
     const u64 NG = (n + 31) / 32;
@@ -2269,12 +2273,24 @@ static int dist_launch(DeviceState &D, const float *d_data, const uint32_t *d_id
         CU_TRY(cudaGetLastError());
         return PQV_OK;
     }
+    if (tune && tune->repeated && vec4 && d_ids && !h_mirror) {
+        // repeated sweeps of one gathered set (k-means++: 1023 sweeps of a 154 MB init set): one group per warp, one warp per
+        // CTA (the block scheduler evens out the SMs), 16 rows x 2 float4 per lane in flight, and the first keep_groups groups
+        // loaded evict_last so that they are still in L2 for the next sweep (profiles/r02_kpp_probe_v*.jsonl: 27 -> 20 us per
+        // sweep at 45 % of the set kept; the shape alone changed nothing, 60 % and more thrashes)
+        auto kern = pqv::l2_dist_kernel<true, true, 1, 16, 2, true>;
+        const size_t sm = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)pqv::TileCfg<0, true, 2>::TILE_FLOATS * 4;
+        PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), sm));
+        kern<<<(uint32_t)NG, 32, sm, D.stream>>>(d_data, d_ids, n, dim, d_vec, d_out, min_update, nullptr, tune->keep_groups);
+        CU_TRY(cudaGetLastError());
+        return PQV_OK;
+    }
     const uint32_t grid = (uint32_t)std::min<u64>((NG + SCAN_WARPS - 1) / SCAN_WARPS, (u64)D.sm_count * 4);
 #define DIST_GO(V, G)                                                                                        \
     do {                                                                                                     \
         auto kern = pqv::l2_dist_kernel<V, G, SCAN_WARPS>;                                                   \
         PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));                                \
-        kern<<<grid, SCAN_WARPS * 32, smem, D.stream>>>(d_data, d_ids, n, dim, d_vec, d_out, min_update, h_mirror); \
+        kern<<<grid, SCAN_WARPS * 32, smem, D.stream>>>(d_data, d_ids, n, dim, d_vec, d_out, min_update, h_mirror, 0); \
     } while (0)
     if (vec4) {
         if (d_ids) DIST_GO(true, true);

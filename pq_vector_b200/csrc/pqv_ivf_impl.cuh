@@ -488,20 +488,36 @@ int kmeans_train_device(DeviceState &D, const float *d_sample, u64 ns, uint32_t 
         ScopedDev<unsigned long long> d_rng;
         ScopedDev<uint32_t> d_dbg;
         rc = d_rng.ensure(1);
-        if (!rc && trace_pp) rc = d_dbg.ensure(8 * (size_t)C);
-        if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void *>(pqv::kpp::kmeanspp_pick_kernel), (size_t)init_n * 4);
+        if (!rc && trace_pp) rc = d_dbg.ensure(10 * (size_t)C);
+        const size_t pick_smem = (size_t)((init_n + 3) & ~(u64)3) * 4;
+        auto pick_kern = pqv::kpp::kmeanspp_pick_kernel<4>;
+        if (!rc) rc = ensure_dyn_smem(reinterpret_cast<const void *>(pick_kern), pick_smem);
         const unsigned long long state = rng.s;
         if (!rc) {
             ce = cudaMemcpyAsync(d_rng.p, &state, 8, cudaMemcpyHostToDevice, D.stream);
             if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "k-means++ random state upload failed: %s", cudaGetErrorString(ce));
         }
         if (trace_pp) t_a = now_ms();
+        // the init set is swept C - 1 times: keep as much of it in L2 as stays there (measured: ~55 % of the L2 size; PQV_SWEEP_KEEP
+        // = percent of the set overrides, PQV_SWEEP_KEEP=off takes the general sweep kernel)
+        SweepTune tune;
+        tune.repeated = true;
+        {
+            int l2_bytes = 0;
+            cudaDeviceGetAttribute(&l2_bytes, cudaDevAttrL2CacheSize, D.dev);
+            const u64 n_groups = (init_n + 31) / 32, group_bytes = (u64)32 * dim * 4;
+            tune.keep_groups = std::min<u64>(n_groups, (u64)(0.55 * (double)l2_bytes) / group_bytes);
+            if (const char *e = getenv("PQV_SWEEP_KEEP")) {
+                if (!strcmp(e, "off")) tune.repeated = false;
+                else tune.keep_groups = std::min<u64>(n_groups, (u64)(atof(e) * 0.01 * (double)n_groups));
+            }
+        }
         for (uint32_t i = 1; i < C && !rc; ++i) {
-            rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p + (size_t)(i - 1) * dim, d_md.p, 1);
+            rc = dist_launch(D, d_sample, d_init.p, init_n, dim, D.d_centroids.p + (size_t)(i - 1) * dim, d_md.p, 1, nullptr, &tune);
             if (rc) break;
-            pqv::kpp::kmeanspp_pick_kernel<<<1, pqv::kpp::THREADS, (size_t)init_n * 4, D.stream>>>(
+            pick_kern<<<1, pqv::kpp::THREADS, pick_smem, D.stream>>>(
                 d_md.p, (uint32_t)init_n, (uint32_t)chunk, (uint32_t)n_chunks, d_rng.p, d_init.p, d_sample, dim,
-                D.d_centroids.p + (size_t)i * dim, trace_pp ? d_dbg.p + 8 * (size_t)i : nullptr);
+                D.d_centroids.p + (size_t)i * dim, trace_pp ? d_dbg.p + 10 * (size_t)i : nullptr, 1.0f);
             ce = cudaGetLastError();
             if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "k-means++ pick launch failed: %s", cudaGetErrorString(ce));
         }
@@ -512,17 +528,20 @@ int kmeans_train_device(DeviceState &D, const float *d_sample, u64 ns, uint32_t 
         if (trace_pp) {
             fprintf(stderr, "[pqv trace] k-means++ on the device (%u picks over %llu rows, %llu chunk sums): %.1f ms\n", C - 1,
                     (unsigned long long)init_n, (unsigned long long)n_chunks, now_ms() - t_a);
-            std::vector<uint32_t> dbg(8 * (size_t)C, 0);
+            std::vector<uint32_t> dbg(10 * (size_t)C, 0);
             if (!rc && cudaMemcpy(dbg.data(), d_dbg.p, dbg.size() * 4, cudaMemcpyDeviceToHost) == cudaSuccess) {
-                double ph[6] = {0, 0, 0, 0, 0, 0}, iters = 0, pos = 0;
+                double ph[6] = {0, 0, 0, 0, 0, 0}, iters = 0, pos = 0, chain = 0, pro = 0;
                 for (uint32_t i = 1; i < C; ++i) {
-                    for (int j = 1; j <= 5; ++j) ph[j] += dbg[8 * (size_t)i + j];
-                    iters += dbg[8 * (size_t)i + 6];
-                    pos += dbg[8 * (size_t)i] == 0xFFFFFFFFu ? 0 : dbg[8 * (size_t)i];
+                    for (int j = 1; j <= 5; ++j) ph[j] += dbg[10 * (size_t)i + j];
+                    iters += dbg[10 * (size_t)i + 6];
+                    chain += dbg[10 * (size_t)i + 7];
+                    pro += dbg[10 * (size_t)i + 8];
+                    pos += dbg[10 * (size_t)i] == 0xFFFFFFFFu ? 0 : dbg[10 * (size_t)i];
                 }
                 const double inv = 1.0 / (C - 1);
-                fprintf(stderr, "[pqv trace] pick kernel, mean cycles: load %.0f, chunk sums %.0f, draw + prologue %.0f, walk %.0f (%.1f blocks, "
-                                "mean pick position %.0f), row copy %.0f\n", ph[1] * inv, (ph[2] - ph[1]) * inv, (ph[3] - ph[2]) * inv,
+                fprintf(stderr, "[pqv trace] pick kernel, mean cycles: load %.0f, chunk sums %.0f (first chain %.0f, prologue sums %.0f), "
+                                "draw + prologue %.0f, walk %.0f (%.1f blocks, mean pick position %.0f), row copy %.0f\n", ph[1] * inv,
+                        (ph[2] - ph[1]) * inv, (chain - ph[1]) * inv, (pro - ph[1]) * inv, (ph[3] - ph[2]) * inv,
                         (ph[4] - ph[3]) * inv, iters * inv, pos * inv, (ph[5] - ph[4]) * inv);
             }
             d_dbg.release();

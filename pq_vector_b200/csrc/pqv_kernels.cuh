@@ -28,6 +28,25 @@ __device__ __forceinline__ float4 ld_stream_v4(const float *p) {
                  : "l"(p));
     return r;
 }
+// same load with an L2 eviction policy word (createpolicy): rows a kernel is going to read again in the next launch are
+// kept (evict_last), the rest of an over-sized working set is let go first (evict_first)
+__device__ __forceinline__ float4 ld_policy_v4(const float *p, const unsigned long long policy) {
+    float4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.f32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+                 : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ float2 ld_stream_v2(const float *p) {
     float2 r;
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
@@ -79,11 +98,11 @@ struct ScanDefaults {
     static constexpr int RB = (GATHER && CBV == 2) ? 4 : 8;  // the gather variant spills at 8 x 2 under 128 regs
 };
 
-template <int ORDER, bool VEC4, bool GATHER, int RB = 8, int CBV = 1>
+template <int ORDER, bool VEC4, bool GATHER, int RB = 8, int CBV = 1, bool HINT = false>
 __device__ __forceinline__ float group_distance(const float *__restrict__ data,
                                                 const uint32_t *__restrict__ row_ids, const u64 n,
                                                 const uint32_t dim, const u64 g, const float *s_vec,
-                                                float *tile, const uint32_t lane) {
+                                                float *tile, const uint32_t lane, const unsigned long long policy = 0ull) {
     constexpr int TSTRIDE = TileCfg<ORDER, VEC4, CBV>::TSTRIDE;
     static_assert(CBV == 1 || (ORDER == 0 && VEC4), "CBV > 1 only for the unroll-4 vector path");
     const u64 pos = g * 32 + lane;
@@ -176,7 +195,10 @@ __device__ __forceinline__ float group_distance(const float *__restrict__ data,
 #pragma unroll
                     for (int v = 0; v < CBV; ++v) {
                         v4[j][v] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (inb[v]) v4[j][v] = ld_stream_v4(rp + 128 * v);
+                        if (inb[v]) {
+                            if constexpr (HINT) v4[j][v] = ld_policy_v4(rp + 128 * v, policy);
+                            else v4[j][v] = ld_stream_v4(rp + 128 * v);
+                        }
                     }
                 }
 #pragma unroll
@@ -560,16 +582,18 @@ __global__ void __launch_bounds__(256) entrant_filter_kernel(const u64 *__restri
 // `squared_l2_distance(vec, centroid)`), optional row selection, store or k-means++ min-update
 // (index.rs:363-365: if dist < slot { slot = dist }).
 // ------------------------------------------------------------------------------------------------
-template <bool VEC4, bool GATHER, int WARPS>
+template <bool VEC4, bool GATHER, int WARPS, int RB = 8, int CBV = 1, bool HINT = false>
 __global__ void __launch_bounds__(WARPS * 32, 2) l2_dist_kernel(const float *__restrict__ data,
                                                              const uint32_t *__restrict__ row_ids, const u64 n,
                                                              const uint32_t dim, const float *__restrict__ vec,
                                                              float *__restrict__ out, const int min_update,
-                                                             float *__restrict__ mirror = nullptr) {
+                                                             float *__restrict__ mirror = nullptr, const u64 keep_groups = 0) {
     // mirror (may be null): page-locked host memory that receives the same final values while the kernel runs, so the
     // k-means++ loop (1023 dependent sweeps, each followed by a host-side pick) needs no separate read-back copy
+    // HINT: the rows of groups < keep_groups are loaded evict_last, the others evict_first -- a caller that sweeps the same
+    // rows again and again (k-means++: 1023 sweeps of a 154 MB init set) keeps the part of them that fits in L2 resident
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int TILE_FLOATS = TileCfg<0, VEC4>::TILE_FLOATS;
+    constexpr int TILE_FLOATS = TileCfg<0, VEC4, VEC4 ? CBV : 1>::TILE_FLOATS;
     const uint32_t dim_pad = (dim + 3u) & ~3u;
     float *s_vec = reinterpret_cast<float *>(smem_raw);
     float *s_tiles = s_vec + dim_pad;
@@ -578,8 +602,14 @@ __global__ void __launch_bounds__(WARPS * 32, 2) l2_dist_kernel(const float *__r
     __syncthreads();
     float *tile = s_tiles + warp * TILE_FLOATS;
     const u64 NG = (n + 31) >> 5;
+    unsigned long long pol_keep = 0ull, pol_go = 0ull;
+    if constexpr (HINT) {
+        pol_keep = l2_policy_evict_last();
+        pol_go = l2_policy_evict_first();
+    }
     for (u64 g = (u64)blockIdx.x * WARPS + warp; g < NG; g += (u64)gridDim.x * WARPS) {
-        const float d = group_distance<0, VEC4, GATHER>(data, row_ids, n, dim, g, s_vec, tile, lane);
+        const float d = group_distance<0, VEC4, GATHER, RB, VEC4 ? CBV : 1, HINT>(data, row_ids, n, dim, g, s_vec, tile, lane,
+                                                                                  g < keep_groups ? pol_keep : pol_go);
         const u64 pos = g * 32 + lane;
         if (pos < n) {
             float keep = d;

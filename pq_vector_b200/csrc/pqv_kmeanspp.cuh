@@ -21,7 +21,7 @@
 namespace pqv {
 namespace kpp {
 
-constexpr uint32_t THREADS = 1024, EPT = 4, BLOCK = THREADS * EPT;
+constexpr uint32_t THREADS = 1024;
 constexpr uint32_t SAT = 1u << 25, TOP = 1u << 24;
 constexpr uint32_t PROLOGUE = 2048;      // plain adds before the first block: the first binades hold a handful of elements each, and
                                          // about this many dependent adds (with their stores) fit beside the worker-chunk chains (3125 elements each at 16 workers)
@@ -121,30 +121,105 @@ struct SplitMix64Dev {
     __device__ float unit_f32() { return (float)(next() >> 40) * (1.0f / 16777216.0f); }
 };
 
-// one CTA of THREADS threads; dynamic shared memory: n floats
+// sixteen chain adds, in element order
+// PQV_KPP_ACC(s, v) = s + v, rounded once.  Written as fma(v, one, s) with `one` = 1.0f arriving as a kernel argument (so
+// that it stays an FFMA): the product v * 1 is exact, hence the result is the f32 sum bit for bit, and a chain of dependent
+// FFMAs advances every 4 cycles where the measured chain of FADDs took 5.8.
+#define PQV_KPP_ACC(S, V) __fmaf_rn((V), one, (S))
+#define PQV_KPP_ADD16(S, A0, A1, A2, A3)                                                                           \
+    do {                                                                                                           \
+        S = PQV_KPP_ACC(S, A0.x); S = PQV_KPP_ACC(S, A0.y); S = PQV_KPP_ACC(S, A0.z); S = PQV_KPP_ACC(S, A0.w);    \
+        S = PQV_KPP_ACC(S, A1.x); S = PQV_KPP_ACC(S, A1.y); S = PQV_KPP_ACC(S, A1.z); S = PQV_KPP_ACC(S, A1.w);    \
+        S = PQV_KPP_ACC(S, A2.x); S = PQV_KPP_ACC(S, A2.y); S = PQV_KPP_ACC(S, A2.z); S = PQV_KPP_ACC(S, A2.w);    \
+        S = PQV_KPP_ACC(S, A3.x); S = PQV_KPP_ACC(S, A3.y); S = PQV_KPP_ACC(S, A3.z); S = PQV_KPP_ACC(S, A3.w);    \
+    } while (0)
+
+// sixteen running sums in element order, left in place of the elements
+#define PQV_KPP_SCAN4(S, A)          \
+    do {                             \
+        A.x = S = PQV_KPP_ACC(S, A.x); \
+        A.y = S = PQV_KPP_ACC(S, A.y); \
+        A.z = S = PQV_KPP_ACC(S, A.z); \
+        A.w = S = PQV_KPP_ACC(S, A.w); \
+    } while (0)
+#define PQV_KPP_SCAN16(S, A0, A1, A2, A3) \
+    do {                                  \
+        PQV_KPP_SCAN4(S, A0);             \
+        PQV_KPP_SCAN4(S, A1);             \
+        PQV_KPP_SCAN4(S, A2);             \
+        PQV_KPP_SCAN4(S, A3);             \
+    } while (0)
+
+// s + smd[i] + smd[i + 1] + ... + smd[e - 1], one rounding per add, in this order (a worker chunk's chain, index.rs:358-368).
+// The chain's adds are all that may sit on the critical path: plain adds up to a 16-byte boundary, then 32 elements at a time
+// from two register sets that are refilled (LDS.128) behind the adds that consumed them.
+__device__ __forceinline__ float chain_sum(float s, const float *smd, uint32_t i, const uint32_t e, const float one) {
+    for (; i < e && (i & 3u); ++i) s = __fadd_rn(s, smd[i]);
+    if (i + 32 <= e) {
+        const float4 *p = reinterpret_cast<const float4 *>(smd + i);
+        float4 a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
+        float4 b0 = p[4], b1 = p[5], b2 = p[6], b3 = p[7];
+        for (i += 32, p += 8; i + 32 <= e; i += 32, p += 8) {
+            PQV_KPP_ADD16(s, a0, a1, a2, a3);
+            a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
+            PQV_KPP_ADD16(s, b0, b1, b2, b3);
+            b0 = p[4], b1 = p[5], b2 = p[6], b3 = p[7];
+        }
+        PQV_KPP_ADD16(s, a0, a1, a2, a3);
+        PQV_KPP_ADD16(s, b0, b1, b2, b3);
+    }
+    for (; i < e; ++i) s = __fadd_rn(s, smd[i]);
+    return s;
+}
+
+// one CTA of THREADS threads; dynamic shared memory: n floats.  EPT = elements per thread of one walk block: a block round
+// costs a fixed ~3 000 cycles of barriers and shuffles, so wider blocks mean fewer rounds (the rounds a binade crossing
+// forces stay: ~log2(n / PROLOGUE) of them)
+template <uint32_t EPT>
 __global__ void __launch_bounds__(THREADS) kmeanspp_pick_kernel(const float *__restrict__ md, const uint32_t n, const uint32_t chunk,
                                                                  const uint32_t n_chunks, unsigned long long *__restrict__ rng_state,
                                                                  const uint32_t *__restrict__ init_idx,
                                                                  const float *__restrict__ sample, const uint32_t dim,
-                                                                 float *__restrict__ centroid_out, uint32_t *__restrict__ picked_out) {
-    extern __shared__ float smd[];
+                                                                 float *__restrict__ centroid_out, uint32_t *__restrict__ picked_out,
+                                                                 const float one_arg) {
+    constexpr uint32_t BLOCK = THREADS * EPT;
+    static_assert(EPT % 4u == 0u, "a thread's elements are loaded as float4");
+    const uint32_t n_pad = (n + 3u) & ~3u;  // the dynamic shared array is allocated up to the next multiple of four
+    extern __shared__ __align__(16) float smd[];
     __shared__ float s_local[THREADS];
-    __shared__ float s_pre[PROLOGUE];  // running sums of the first PROLOGUE elements (computed beside the chunk sums)
+    __shared__ __align__(16) float s_pre[PROLOGUE];  // running sums of the first PROLOGUE elements (computed beside the chunk sums)
     __shared__ uint32_t s_wt_e[32], s_wt_o[32];
-    __shared__ unsigned long long s_event;  // (position << 1 | kind) << 32 | m before the element; ~0: no event in this block
-    __shared__ uint32_t s_mend, s_base, s_pick, s_mode, s_weird;
+    __shared__ uint32_t s_base, s_pick, s_mode, s_weird;
     __shared__ float s_x, s_thr;
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const long long t_start = picked_out ? clock64() : 0;  // picked_out != null (PQV_TRACE): [0] = pick, [1..5] = cycles per phase
-    if (tid == 0) s_weird = 0u;
+    const long long t_start = picked_out ? clock64() : 0;  // picked_out != null (PQV_TRACE): [0] = pick, [1..5], [7], [8] = cycles at the end of a phase, [6] = walk rounds
+    __shared__ float s_one;
+    if (tid == 0) {
+        s_weird = 0u;
+        s_one = one_arg;
+    }
     __syncthreads();
+    // 1.0f for the chains' FFMAs, read back from shared memory so that it sits in a vector register of each thread (as a
+    // uniform-register operand the dependent FFMAs measured no faster than FADDs)
+    const float one = *reinterpret_cast<volatile float *>(&s_one);
     bool weird = false;
     const uint32_t n4 = ((reinterpret_cast<uintptr_t>(md) & 15u) == 0u) ? (n >> 2) : 0u;
-    for (uint32_t i = tid; i < n4; i += THREADS) {
-        const float4 v = __ldcg(reinterpret_cast<const float4 *>(md) + i);
-        reinterpret_cast<float4 *>(smd)[i] = v;
-        // NaN, inf, negative: the integer model does not apply -> plain chains
-        weird |= !(v.x >= 0.f && v.x < 3.0e38f) || !(v.y >= 0.f && v.y < 3.0e38f) || !(v.z >= 0.f && v.z < 3.0e38f) || !(v.w >= 0.f && v.w < 3.0e38f);
+    for (uint32_t i0 = 0; i0 < n4; i0 += 4u * THREADS) {  // four loads of a thread in flight (one SM pulls the whole array)
+        float4 v[4];
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t i = i0 + j * THREADS + tid;
+            v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (i < n4) v[j] = __ldcg(reinterpret_cast<const float4 *>(md) + i);
+        }
+#pragma unroll
+        for (uint32_t j = 0; j < 4; ++j) {
+            const uint32_t i = i0 + j * THREADS + tid;
+            if (i < n4) reinterpret_cast<float4 *>(smd)[i] = v[j];
+            // NaN, inf, negative: the integer model does not apply -> plain chains
+            weird |= !(v[j].x >= 0.f && v[j].x < 3.0e38f) || !(v[j].y >= 0.f && v[j].y < 3.0e38f) ||
+                     !(v[j].z >= 0.f && v[j].z < 3.0e38f) || !(v[j].w >= 0.f && v[j].w < 3.0e38f);
+        }
     }
     for (uint32_t i = (n4 << 2) + tid; i < n; i += THREADS) {
         const float v = md[i];
@@ -156,54 +231,43 @@ __global__ void __launch_bounds__(THREADS) kmeanspp_pick_kernel(const float *__r
     if (tid == 0 && picked_out) picked_out[1] = (uint32_t)(clock64() - t_start);
     // ---- (a) chunk sums (index.rs:356-370): one serial chain per worker chunk, then the chunk sums in chunk order
     float total = 0.f;
-    // meanwhile the walk's first PROLOGUE running sums, which need no threshold yet: a lane of the LAST warp takes them when
-    // the chunk chains leave it free (the usual 16 workers sit in warp 0), so they cost nothing on the critical path
     const uint32_t pro_n = min(PROLOGUE, n);
     const bool pro_side = n_chunks <= THREADS - 32u;
+    // meanwhile the walk's first PROLOGUE running sums, which need no threshold yet: a lane of the LAST warp takes them when
+    // the chunk chains leave it free (the usual 16 workers sit in warp 0), so they cost nothing on the critical path
     if (pro_side && tid == THREADS - 1u && !s_weird) {
         float y = 0.f;
         uint32_t i = 0;
-        for (; i + 8 <= pro_n; i += 8) {  // loads first, then the dependent adds, then the stores
-            float v[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = smd[i + j];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                y = __fadd_rn(y, v[j]);
-                v[j] = y;
+        if (pro_n >= 32u) {  // two register sets of 16: one is being summed and stored while the other one's loads are in flight
+            const float4 *p = reinterpret_cast<const float4 *>(smd);
+            float4 *q = reinterpret_cast<float4 *>(s_pre);
+            float4 a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
+            float4 b0 = p[4], b1 = p[5], b2 = p[6], b3 = p[7];
+            for (i = 32, p += 8; i + 32 <= pro_n; i += 32, p += 8, q += 8) {
+                PQV_KPP_SCAN16(y, a0, a1, a2, a3);
+                q[0] = a0, q[1] = a1, q[2] = a2, q[3] = a3;
+                a0 = p[0], a1 = p[1], a2 = p[2], a3 = p[3];
+                PQV_KPP_SCAN16(y, b0, b1, b2, b3);
+                q[4] = b0, q[5] = b1, q[6] = b2, q[7] = b3;
+                b0 = p[4], b1 = p[5], b2 = p[6], b3 = p[7];
             }
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s_pre[i + j] = v[j];
+            PQV_KPP_SCAN16(y, a0, a1, a2, a3);
+            q[0] = a0, q[1] = a1, q[2] = a2, q[3] = a3;
+            PQV_KPP_SCAN16(y, b0, b1, b2, b3);
+            q[4] = b0, q[5] = b1, q[6] = b2, q[7] = b3;
         }
         for (; i < pro_n; ++i) {
             y = __fadd_rn(y, smd[i]);
             s_pre[i] = y;
         }
+        if (picked_out) picked_out[8] = (uint32_t)(clock64() - t_start);  // end of the prologue's running sums
     }
     for (uint32_t c0 = 0; c0 < n_chunks; c0 += THREADS) {
         const uint32_t c = c0 + tid;
         if (c < n_chunks) {
             const uint32_t b = c * chunk, e = min(n, b + chunk);
-            float s = 0.f;
-            uint32_t i = b;
-            if (i + 16 <= e) {  // sixteen elements in registers ahead of the chain: the dependent adds are all that is left on it
-                float v[16];
-#pragma unroll
-                for (int j = 0; j < 16; ++j) v[j] = smd[i + j];
-                for (i += 16; i + 16 <= e; i += 16) {
-                    float w[16];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) w[j] = smd[i + j];
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) s = __fadd_rn(s, v[j]);
-#pragma unroll
-                    for (int j = 0; j < 16; ++j) v[j] = w[j];
-                }
-#pragma unroll
-                for (int j = 0; j < 16; ++j) s = __fadd_rn(s, v[j]);
-            }
-            for (; i < e; ++i) s = __fadd_rn(s, smd[i]);
-            s_local[tid] = s;
+            s_local[tid] = chain_sum(0.f, smd, b, e, one);
+            if (picked_out && c == 0u) picked_out[7] = (uint32_t)(clock64() - t_start);  // end of the first chunk's chain
         }
         __syncthreads();
         if (tid == 0) {
@@ -293,25 +357,42 @@ __global__ void __launch_bounds__(THREADS) kmeanspp_pick_kernel(const float *__r
             const float half_u = __uint_as_float((uint32_t)(E - 24) << 23);
             const float inv_u = __uint_as_float((uint32_t)(277 - E) << 23);
             const float big = __uint_as_float(((uint32_t)E << 23) | 0x400000u);   // 1.5 x 2^(E - 127): same ulp, even mantissa
+            const uint32_t big_bits = ((uint32_t)E << 23) | 0x400000u;
             const float dmax = __uint_as_float((uint32_t)(E - 1) << 23);          // big + d stays inside big's binade below this
-            // element -> (a, tie) with three f32 adds: r = (big + d) - big is d rounded to a multiple of u (ties to even), the
-            // residual d - r is exact, and |residual| == u / 2 marks the tie; a = the round-DOWN choice of a tie, so that the
-            // parity rule of the running sum (not of big) decides it below
+            // the threshold in units of u: m u >= thr  <=>  m >= ceil(thr / u) (the scaling is exact; a quotient that
+            // underflows compares true for every m >= 2^23 like thr itself, one that overflows or is NaN never does)
+            const float tq = __fmul_rn(thr, inv_u);
+            const uint32_t thr_m = (tq < 33554432.f) ? (uint32_t)ceilf(tq) : SAT;
+            const uint32_t lim = min(TOP, thr_m);  // the first m >= lim is the block's event: pick (m < TOP) or binade exit
+            // element -> (a, tie): t = big + d is d rounded to a multiple of u (ties to even) on top of big, so a is the
+            // DIFFERENCE OF THE BIT PATTERNS of t and big; the residual d - (t - big) is exact, and |residual| == u / 2 marks
+            // the tie; a = the round-DOWN choice of a tie, so that the parity rule of the running sum (not of big) decides it
             uint32_t a[EPT];
             bool tie[EPT], any_tie = false;
             uint32_t sum_a = 0u;
+            // the block starts at the 16-byte boundary at or below base (elements before base count as zeros), so that a
+            // thread's EPT consecutive elements come in as LDS.128 -- with EPT = 12 the eight lanes of a quarter warp are
+            // 48 bytes apart and hit eight different 16-byte bank groups (scalar loads at stride EPT were 4- to 16-way conflicts)
+            const uint32_t base_al = base & ~3u;
+            const uint32_t j0 = base_al + tid * EPT;
 #pragma unroll
-            for (uint32_t e = 0; e < EPT; ++e) {
-                const uint32_t j = base + tid * EPT + e;
-                const float d = j < n ? smd[j] : 0.f;
-                const float r = __fadd_rn(__fadd_rn(big, d), -big);
-                const float res = __fadd_rn(d, -r);
-                const bool big_d = d >= dmax;  // at least a quarter of the binade: leaves it for sure (and would overflow big's)
-                tie[e] = !big_d && fabsf(res) == half_u;
-                const float af = (res == -half_u) ? __fadd_rn(r, -u) : r;
-                a[e] = big_d ? SAT : __float2uint_rn(__fmul_rn(af, inv_u));
-                any_tie |= tie[e];
-                sum_a = min(sum_a + a[e], SAT);
+            for (uint32_t e4 = 0; e4 < EPT; e4 += 4) {
+                float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j0 + e4 < n_pad) v4 = *reinterpret_cast<const float4 *>(smd + j0 + e4);
+                const float dv[4] = {v4.x, v4.y, v4.z, v4.w};
+#pragma unroll
+                for (uint32_t q = 0; q < 4; ++q) {
+                    const uint32_t e = e4 + q, j = j0 + e;
+                    const float d = (j >= base && j < n) ? dv[q] : 0.f;
+                    const float t = __fadd_rn(big, d);
+                    const float res = __fadd_rn(d, -__fadd_rn(t, -big));
+                    const bool big_d = d >= dmax;  // at least a quarter of the binade: leaves it for sure (and would overflow big's)
+                    tie[e] = !big_d && fabsf(res) == half_u;
+                    const uint32_t ai = __float_as_uint(t) - big_bits - ((res == -half_u) ? 1u : 0u);
+                    a[e] = big_d ? SAT : ai;
+                    any_tie |= tie[e];
+                    sum_a = min(sum_a + a[e], SAT);
+                }
             }
             // inclusive scan inside the warp: plain saturating sums unless some lane of the warp holds a tie
             Fn inc;
@@ -336,7 +417,6 @@ __global__ void __launch_bounds__(THREADS) kmeanspp_pick_kernel(const float *__r
                     if (lane >= o) inc = fn_compose(g, inc);
                 }
             }
-            if (tid == 0) s_event = ~0ull;
             if (lane == 31) {
                 s_wt_e[warp] = inc.e;
                 s_wt_o[warp] = inc.o;
@@ -355,68 +435,59 @@ __global__ void __launch_bounds__(THREADS) kmeanspp_pick_kernel(const float *__r
                 s_wt_o[lane] = w.o;
             }
             __syncthreads();
-            Fn excl;  // everything before this thread's first element
-            excl.e = __shfl_up_sync(0xffffffffu, inc.e, 1);
-            excl.o = __shfl_up_sync(0xffffffffu, inc.o, 1);
-            if (lane == 0) excl = fn_identity();
-            if (warp > 0) excl = fn_compose(Fn{s_wt_e[warp - 1], s_wt_o[warp - 1]}, excl);
-            uint32_t m = m0 + ((m0 & 1u) ? excl.o : excl.e);
-            // The running sum never decreases, so exactly ONE thread sees the block's first event: the one that starts inside
-            // the binade and below the threshold and does not end that way.  It alone writes s_event (no atomics).
-            uint32_t my_event = NONE, my_before = 0u;
-            if (m < TOP && !(__fmul_rn(__uint2float_rn(m), u) >= thr)) {
+            // The running sum never decreases, so the state behind a thread's LAST element tells whether the block's first
+            // event lies at or before it: exactly ONE thread starts below lim and does not end below it.  It alone walks its
+            // elements and leaves the next round's state (no atomics); without an event the last thread does.  Everybody else
+            // is done after two integer compares.
+            const uint32_t m_warp = warp > 0 ? m0 + ((m0 & 1u) ? s_wt_o[warp - 1] : s_wt_e[warp - 1]) : m0;  // before the warp
+            const Fn incl = warp > 0 ? fn_compose(Fn{s_wt_e[warp - 1], s_wt_o[warp - 1]}, inc) : inc;
+            const uint32_t m_end = m0 + ((m0 & 1u) ? incl.o : incl.e);
+            uint32_t m = __shfl_up_sync(0xffffffffu, m_end, 1);
+            if (lane == 0) m = m_warp;
+            if (m < lim && m_end >= lim) {
+                uint32_t ev_e = 0u, mn = 0u;
+                bool found = false;
 #pragma unroll
                 for (uint32_t e = 0; e < EPT; ++e) {
-                    if (my_event != NONE) break;
-                    const uint32_t mn = m + a[e] + (tie[e] ? ((m + a[e]) & 1u) : 0u);
-                    const uint32_t j = base + tid * EPT + e;
-                    if (mn >= TOP) {
-                        my_event = ((tid * EPT + e) << 1);
-                        my_before = m;
-                    } else if (j < n && __fmul_rn(__uint2float_rn(mn), u) >= thr) {
-                        my_event = ((tid * EPT + e) << 1) | 1u;
-                        my_before = m;
-                    } else {
-                        m = mn;
-                    }
-                }
-            }
-            if (my_event != NONE) s_event = ((unsigned long long)my_event << 32) | my_before;
-            if (tid == THREADS - 1) s_mend = m;
-            __syncthreads();
-            if (tid == 0) {
-                const unsigned long long ev64 = s_event;
-                const uint32_t ev = (uint32_t)(ev64 >> 32), m_before = (uint32_t)ev64;
-                if (ev64 == ~0ull) {
-                    s_x = __fmul_rn(__uint2float_rn(s_mend), u);
-                    s_base = base + BLOCK;
-                } else {
-                    const uint32_t pos = ev >> 1;
-                    if (ev & 1u) {
-                        s_pick = base + pos;
-                        s_mode = 2u;
-                    } else {  // the add that leaves the binade: a real f32 add from the exact state before it
-                        float y = __fadd_rn(__fmul_rn(__uint2float_rn(m_before), u), smd[base + pos]);
-                        uint32_t i = base + pos;
-                        if (y >= thr) {
-                            s_pick = i;
-                            s_mode = 2u;
+                    if (!found) {
+                        mn = m + a[e] + (tie[e] ? ((m + a[e]) & 1u) : 0u);
+                        if (mn >= lim) {
+                            found = true;
+                            ev_e = e;
                         } else {
-                            ++i;
-                            if (pos < 16u) {  // hardly any progress (alternating magnitudes): plain adds for a while
-                                const uint32_t end = min(n, i + SERIAL_BURST);
-                                const uint32_t hit = serial_walk(smd, i, end, &y, thr, true);
-                                if (hit != NONE) {
-                                    s_pick = hit;
-                                    s_mode = 2u;
-                                }
-                                i = end;
-                            }
-                            s_x = y;
-                            s_base = i;
+                            m = mn;
                         }
                     }
                 }
+                // m = the exact state before element ev_e, mn behind it: it reaches the threshold inside the binade or leaves it
+                const uint32_t i_ev = j0 + ev_e;
+                if (mn < TOP) {
+                    s_pick = i_ev;
+                    s_mode = 2u;
+                } else {  // the add that leaves the binade: a real f32 add from the exact state before it
+                    float y = __fadd_rn(__fmul_rn(__uint2float_rn(m), u), smd[i_ev]);
+                    uint32_t i = i_ev;
+                    if (y >= thr) {
+                        s_pick = i;
+                        s_mode = 2u;
+                    } else {
+                        ++i;
+                        if (i_ev - base < 16u) {  // hardly any progress (alternating magnitudes): plain adds for a while
+                            const uint32_t end = min(n, i + SERIAL_BURST);
+                            const uint32_t hit = serial_walk(smd, i, end, &y, thr, true);
+                            if (hit != NONE) {
+                                s_pick = hit;
+                                s_mode = 2u;
+                            }
+                            i = end;
+                        }
+                        s_x = y;
+                        s_base = i;
+                    }
+                }
+            } else if (tid == THREADS - 1u && m_end < lim) {  // no event in this block
+                s_x = __fmul_rn(__uint2float_rn(m_end), u);
+                s_base = base_al + BLOCK;
             }
             __syncthreads();
         }

@@ -130,7 +130,8 @@ def test_build_matches_oracle_pipeline(ctx, n, dim, C, iters):
     ix.drop(); ix2.drop(); ds.drop()
 
 
-@pytest.mark.parametrize("case", ["identical", "two-points", "tiny", "huge", "grid", "big-init", "nan-row", "one-worker"])
+@pytest.mark.parametrize("case", ["identical", "two-points", "tiny", "huge", "grid", "big-init", "nan-row", "one-worker",
+                                  "forty-workers", "six-hundred-workers", "odd-rows", "short-chunks"])
 def test_kmeanspp_on_the_device_handles_awkward_tables(ctx, case):
     """the device-side k-means++ pick (pqv_kmeanspp.cuh: chunk sums, draw, block-parallel exact walk) against the oracle's
     literal chains on tables that leave its integer model: zero totals (uniform draws), tiny / huge distances, distances on a
@@ -153,6 +154,14 @@ def test_kmeanspp_on_the_device_handles_awkward_tables(ctx, case):
         data, C = rng.random((2500, 8), dtype=np.float32), 10
         data[7, 3] = np.nan
         data[900, 0] = np.inf
+    elif case == "forty-workers":     # chunk chains in two warps; chunk boundaries off the 16-byte grid of the bulk copy
+        data, C, workers = rng.random((9001, 8), dtype=np.float32), 20, 40
+    elif case == "six-hundred-workers":  # more chain warps than the two-wave copy serves: plain loads
+        data, C, workers = rng.random((7003, 8), dtype=np.float32), 15, 600
+    elif case == "odd-rows":          # row count % 4 != 0: the array's tail comes by plain loads
+        data, C, workers = rng.random((2999, 8), dtype=np.float32), 14, 5
+    elif case == "short-chunks":      # chunks shorter than the first wave of the copy
+        data, C, workers = rng.random((1000, 8), dtype=np.float32), 10, 16
     else:
         data, C, workers = rng.random((9000, 16), dtype=np.float32), 25, 1
     ds = ctx.dataset_from(data)
