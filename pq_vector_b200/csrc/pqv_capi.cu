@@ -604,6 +604,7 @@ struct pqv_ctx {
     } batch_state;
     int occ_override = 0;
     int scan_variant = 0;
+    int gather_variant = 0;
     PeerExchange peer;
     // coalescing front door for concurrent single-query callers (pqv_l2_topk_coalesced)
     struct CoalesceReq {
@@ -678,6 +679,7 @@ struct ScanGeom {
     uint32_t kcap, sort_n, flush_at, grid;
     size_t smem;
     bool vec4;
+    bool gather = false;
 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is sticky per kernel: only ever raise it
@@ -752,6 +754,36 @@ static int scan_variant_dispatch(int v, const pqv::ScanParams &p, uint32_t grid,
     }
 }
 
+// Tuning variants of the GATHERED unroll-4 vector kernel (PQV_GATHER_VARIANT=n; 0 = the shipped default).  The default
+// <4, 2, 2> keeps 4 KB per warp in flight (8 x 2 spills under the 128-register cap of two CTAs per SM); one CTA per SM lifts
+// the cap.
+static const ScanVariant kGatherVariants[] = {{4, 2, 2}, {8, 2, 1}, {16, 1, 1}, {16, 2, 1}, {8, 1, 2}, {8, 2, 2}, {8, 3, 1}};
+
+template <int RB, int CBV, int MINB>
+int gather_variant_go(const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStream_t st, int *occ_out) {
+    auto kern = pqv::l2_scan_topk_kernel<0, true, true, SCAN_WARPS, RB, CBV, MINB>;
+    PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
+    if (occ_out) {
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, SCAN_WARPS * 32, smem));
+        return PQV_OK;
+    }
+    kern<<<grid, SCAN_WARPS * 32, smem, st>>>(p);
+    CU_TRY(cudaGetLastError());
+    return PQV_OK;
+}
+
+static int gather_variant_dispatch(int v, const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStream_t st, int *occ_out) {
+    switch (v) {
+        case 1: return gather_variant_go<8, 2, 1>(p, grid, smem, st, occ_out);
+        case 2: return gather_variant_go<16, 1, 1>(p, grid, smem, st, occ_out);
+        case 3: return gather_variant_go<16, 2, 1>(p, grid, smem, st, occ_out);
+        case 4: return gather_variant_go<8, 1, 2>(p, grid, smem, st, occ_out);
+        case 5: return gather_variant_go<8, 2, 2>(p, grid, smem, st, occ_out);
+        case 6: return gather_variant_go<8, 3, 1>(p, grid, smem, st, occ_out);
+        default: return fail(PQV_EINVAL, "unknown PQV_GATHER_VARIANT %d", v);
+    }
+}
+
 #define SCAN_DISPATCH(FN, order, vec4, gather, ...)                                                 \
     ((order) == 0 ? ((vec4) ? ((gather) ? FN<0, true, true>(__VA_ARGS__) : FN<0, true, false>(__VA_ARGS__))      \
                             : ((gather) ? FN<0, false, true>(__VA_ARGS__) : FN<0, false, false>(__VA_ARGS__)))   \
@@ -773,13 +805,15 @@ int scan_geometry(pqv_ctx *ctx, DeviceState &D, const float *d_data, u64 n, uint
     g->flush_at = std::max<uint32_t>(1, g->kcap / 2);
     g->sort_n = pow2ceil(g->kcap + g->flush_at + SCAN_WARPS * 32);
     g->smem = scan_smem_bytes(order, g->vec4, dim, g->sort_n);
-    g->variant = (order == 0 && g->vec4 && !gather) ? ctx->scan_variant : 0;
+    g->variant = (order == 0 && g->vec4) ? (gather ? ctx->gather_variant : ctx->scan_variant) : 0;
+    g->gather = gather;
     if (g->variant > 0) {
-        const ScanVariant &sv = kVariants[g->variant];
+        const ScanVariant &sv = gather ? kGatherVariants[g->variant] : kVariants[g->variant];
         g->smem = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)SCAN_WARPS * 32 * (32 * sv.cbv + 4) * 4 + (size_t)g->sort_n * 8;
         int occ = 0;
         pqv::ScanParams dummy{};
-        PQV_TRY(scan_variant_dispatch(g->variant, dummy, 0, g->smem, nullptr, &occ));
+        if (gather) PQV_TRY(gather_variant_dispatch(g->variant, dummy, 0, g->smem, nullptr, &occ));
+        else PQV_TRY(scan_variant_dispatch(g->variant, dummy, 0, g->smem, nullptr, &occ));
         if (occ < 1) return fail(PQV_ELIMIT, "scan variant does not fit");
         occ = std::min(occ, ctx->occ_override > 0 ? ctx->occ_override : sv.minb);
         const u64 NGv = (n + 31) / 32;
@@ -828,7 +862,8 @@ int enqueue_scan(pqv_ctx *ctx, DeviceState &D, const float *d_data, const uint32
     p.ent_count = D.ent_count.p;
     p.dist_out = dist_out;
     if (time_it) CU_TRY(cudaEventRecord(D.ev[0], D.stream));
-    if (g.variant > 0) PQV_TRY(scan_variant_dispatch(g.variant, p, g.grid, g.smem, D.stream, nullptr));
+    if (g.variant > 0 && g.gather) PQV_TRY(gather_variant_dispatch(g.variant, p, g.grid, g.smem, D.stream, nullptr));
+    else if (g.variant > 0) PQV_TRY(scan_variant_dispatch(g.variant, p, g.grid, g.smem, D.stream, nullptr));
     else PQV_TRY(SCAN_DISPATCH(scan_launch_t, order, g.vec4, d_row_ids != nullptr, p, g.grid, g.smem, D.stream));
     if (time_it) CU_TRY(cudaEventRecord(D.ev[1], D.stream));
     // two-level exclusive "top-k scan" over the per-CTA lists, then per-CTA threshold + entrant filter
@@ -1285,6 +1320,7 @@ int pqv_init(pqv_ctx **out, const int *device_ids, int n_devices) {
     pqv_ctx *ctx = new pqv_ctx();
     if (const char *s = getenv("PQV_SCAN_CTAS_PER_SM")) ctx->occ_override = atoi(s);
     if (const char *s = getenv("PQV_SCAN_VARIANT")) ctx->scan_variant = std::max(0, std::min(12, atoi(s)));
+    if (const char *s = getenv("PQV_GATHER_VARIANT")) ctx->gather_variant = std::max(0, std::min(6, atoi(s)));
     for (int id : ids) {
         DeviceState D;
         D.dev = id;

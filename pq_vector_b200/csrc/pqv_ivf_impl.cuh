@@ -313,7 +313,7 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
                                                                  reinterpret_cast<uint32_t *>(D.ivf_info.p + 1));
     CU_TRY(cudaGetLastError());
     if (!ro) {
-        pqv::ivf_expand_kernel<<<dim3(np, 8), 256, 0, D.stream>>>(ix.d_ids.p, ix.d_offsets.p, ix.d_probe_cluster.p,
+        pqv::ivf_expand_kernel<<<dim3(np, 32), 256, 0, D.stream>>>(ix.d_ids.p, ix.d_offsets.p, ix.d_probe_cluster.p,
                                                                   ix.d_probe_prefix.p, ix.d_cand.p);
         if (seq_limit != ~0ull) pqv::clamp_count_kernel<<<1, 1, 0, D.stream>>>(D.ivf_info.p, seq_limit);
     } else {
@@ -329,12 +329,11 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
     ScanGeom g;
     PQV_TRY(enqueue_scan(ctx, D, ds.shards[0].d_data, ix.d_cand.p, n_bound, ds.dim, D.d_query.p, k, order, 0u, nullptr,
                          D.final_topk.p, D.ent_out.p, cap, true, &g, D.ivf_info.p));
-    pqv::ent_rows_kernel<<<32, 256, 0, D.stream>>>(D.ent_out.p, cap, ix.d_cand.p, D.ent_rows.p);
-    CU_TRY(cudaGetLastError());
+    // the kernel leaves count, first keys, their row ids and the info words in page-locked host memory itself
     const uint32_t first = std::min<uint32_t>(ENT_FIRST_CHUNK, cap);
-    CU_TRY(cudaMemcpyAsync(D.h_ent_out.p, D.ent_out.p, ((size_t)first + 1) * 8, cudaMemcpyDeviceToHost, D.stream));
-    CU_TRY(cudaMemcpyAsync(D.h_ent_rows.p, D.ent_rows.p, (size_t)first * 4, cudaMemcpyDeviceToHost, D.stream));
-    CU_TRY(cudaMemcpyAsync(D.h_ivf_info.p, D.ivf_info.p, 32, cudaMemcpyDeviceToHost, D.stream));
+    pqv::ent_rows_kernel<<<32, 256, 0, D.stream>>>(D.ent_out.p, cap, ix.d_cand.p, D.ent_rows.p, D.h_ent_out.p, D.h_ent_rows.p, first,
+                                                   D.ivf_info.p, D.h_ivf_info.p);
+    CU_TRY(cudaGetLastError());
     if (eo) {
         eo->probe.resize(np);
         CU_TRY(cudaMemcpyAsync(eo->probe.data(), ix.d_probe_cluster.p, (size_t)np * 4, cudaMemcpyDeviceToHost, D.stream));

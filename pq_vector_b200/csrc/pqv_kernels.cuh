@@ -465,41 +465,45 @@ __global__ void __launch_bounds__(1024) topk_seq_merge_kernel(const u64 *__restr
                                                               u64 *__restrict__ excl_prefix_out,
                                                               u64 *__restrict__ total_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *s = reinterpret_cast<u64 *>(smem_raw);  // 2*kcap keys: [P ascending | incoming list descending]
+    u64 *s = reinterpret_cast<u64 *>(smem_raw);  // 2*kcap keys: two exchange buffers for the strides that cross warps
     constexpr int PF = 4;
-    const uint32_t tid = threadIdx.x;  // blockDim.x == kcap
+    const uint32_t tid = threadIdx.x;  // blockDim.x == kcap (a power of two >= 32)
     const uint32_t b0 = blockIdx.x * lists_per_cta;
     const uint32_t b1 = min(n_lists, b0 + lists_per_cta);
-    s[tid] = carry ? carry[tid] : KEY_MAX;
+    // Thread t keeps P[t] in a register.  One step: the incoming list arrives REVERSED (thread t holds its (kcap-1-t)-th
+    // key), so [P | incoming reversed] is bitonic and x[t] = min(P[t], incoming[kcap-1-t]) is the half-cleaner's lower half:
+    // the kcap smallest keys of the union as a bitonic sequence.  It is sorted with compare-exchanges at strides kcap/2 .. 1;
+    // strides >= 32 go through shared memory (alternating buffers: one barrier each), strides < 32 through shuffles.
+    u64 P = carry ? carry[tid] : KEY_MAX;
     u64 nxt[PF];
 #pragma unroll
     for (int i = 0; i < PF; ++i) nxt[i] = (b0 + i < b1) ? lists[(u64)(b0 + i) * kcap + (kcap - 1 - tid)] : KEY_MAX;
-    __syncthreads();
+    uint32_t buf = 0;
     for (uint32_t b = b0; b < b1; b += PF) {
 #pragma unroll
         for (int i = 0; i < PF; ++i) {
             if (b + i >= b1) break;  // uniform
-            if (excl_prefix_out) excl_prefix_out[(u64)(b + i) * kcap + tid] = s[tid];
-            s[kcap + tid] = nxt[i];
+            if (excl_prefix_out) excl_prefix_out[(u64)(b + i) * kcap + tid] = P;
+            u64 x = min(P, nxt[i]);
             const uint32_t bn = b + i + PF;
             nxt[i] = (bn < b1) ? lists[(u64)bn * kcap + (kcap - 1 - tid)] : KEY_MAX;
-            __syncthreads();
-            // bitonic merge of the 2*kcap bitonic sequence, ascending; one compare-exchange per thread per step
-            for (uint32_t stride = kcap; stride > 0; stride >>= 1) {
-                const uint32_t lo = ((tid & ~(stride - 1)) << 1) | (tid & (stride - 1));
-                const uint32_t hi = lo + stride;
-                const u64 a = s[lo], c = s[hi];
-                if (a > c) {
-                    s[lo] = c;
-                    s[hi] = a;
-                }
+            for (uint32_t stride = kcap >> 1; stride >= 32; stride >>= 1) {
+                u64 *sb = s + buf * kcap;
+                sb[tid] = x;
                 __syncthreads();
+                const u64 y = sb[tid ^ stride];
+                x = (tid & stride) ? max(x, y) : min(x, y);
+                buf ^= 1u;
             }
-            if (tid >= k) s[tid] = KEY_MAX;
-            __syncthreads();
+#pragma unroll
+            for (uint32_t stride = 16; stride > 0; stride >>= 1) {
+                const u64 y = __shfl_xor_sync(0xffffffffu, x, stride);
+                x = (tid & stride) ? max(x, y) : min(x, y);
+            }
+            P = tid < k ? x : KEY_MAX;
         }
     }
-    total_out[(u64)blockIdx.x * kcap + tid] = s[tid];
+    total_out[(u64)blockIdx.x * kcap + tid] = P;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -1181,12 +1185,29 @@ __global__ void clamp_count_kernel(u64 *__restrict__ info, const u64 limit) {
 
 // row ids of the surviving entrant keys of a gathered scan: rows_out[i] = cand[position of key i]
 // (keys = entrant_filter_kernel's out: [0] = count, keys from [1]).
+// h_keys / h_rows / h_info (may be null): page-locked host memory that receives the count ([0] of h_keys), the first
+// h_first keys and row ids and the four info words while the kernel runs, so that a search needs no device-to-host copy
+// behind it (three small copies cost ~25 us of DMA set-up; these are a few KB of posted writes).
 __global__ void __launch_bounds__(256) ent_rows_kernel(const u64 *__restrict__ ent_out, const uint32_t cap,
                                                        const uint32_t *__restrict__ cand,
-                                                       uint32_t *__restrict__ rows_out) {
-    const u64 cnt = min(ent_out[0], (u64)cap);
-    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (u64)gridDim.x * blockDim.x)
-        rows_out[i] = cand[(uint32_t)ent_out[1 + i]];
+                                                       uint32_t *__restrict__ rows_out, u64 *__restrict__ h_keys = nullptr,
+                                                       uint32_t *__restrict__ h_rows = nullptr, const uint32_t h_first = 0,
+                                                       const u64 *__restrict__ info = nullptr, u64 *__restrict__ h_info = nullptr) {
+    const u64 total = ent_out[0];
+    const u64 cnt = min(total, (u64)cap);
+    for (u64 i = (u64)blockIdx.x * blockDim.x + threadIdx.x; i < cnt; i += (u64)gridDim.x * blockDim.x) {
+        const u64 key = ent_out[1 + i];
+        const uint32_t row = cand[(uint32_t)key];
+        rows_out[i] = row;
+        if (h_keys && i < h_first) {
+            h_keys[1 + i] = key;
+            h_rows[i] = row;
+        }
+    }
+    if (h_keys && blockIdx.x == 0) {
+        if (threadIdx.x == 0) h_keys[0] = total;
+        if (info && threadIdx.x < 4) h_info[threadIdx.x] = info[threadIdx.x];
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
