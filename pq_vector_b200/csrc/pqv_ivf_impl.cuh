@@ -294,8 +294,7 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
     if (trace) tt[1] = now_ms();
     memcpy(D.h_query.p, query, (size_t)ix.dim * 4);
     CU_TRY(cudaMemcpyAsync(D.d_query.p, D.h_query.p, (size_t)ix.dim * 4, cudaMemcpyHostToDevice, D.stream));
-    CU_TRY(cudaMemsetAsync(D.ivf_info.p, 0, 32, D.stream));
-    CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
+    // (the info words and the entrant counter are zeroed by ivf_rank_kernel)
     const u64 n_words = (ds.n_rows + 31) / 32;
     const uint32_t bm_blocks = (uint32_t)((n_words + pqv::BM_WORDS_PER_BLOCK - 1) / pqv::BM_WORDS_PER_BLOCK);
     if (ro) {
@@ -309,8 +308,7 @@ int ivf_search_fused(pqv_ctx *ctx, Dataset &ds, DeviceState &D, IvfIndex &ix, co
     }
     PQV_TRY(dist_launch(D, ix.d_centroids.p, nullptr, C, ix.dim, D.d_query.p, ix.d_cdist.p, 0));
     pqv::ivf_rank_kernel<<<1, 1024, (size_t)cp2 * 8, D.stream>>>(ix.d_cdist.p, C, cp2, np, ix.d_offsets.p, ix.d_probe_cluster.p,
-                                                                 ix.d_probe_prefix.p, D.ivf_info.p,
-                                                                 reinterpret_cast<uint32_t *>(D.ivf_info.p + 1));
+                                                                 ix.d_probe_prefix.p, D.ivf_info.p, D.ent_out.p);
     CU_TRY(cudaGetLastError());
     if (!ro) {
         pqv::ivf_expand_kernel<<<dim3(np, 32), 256, 0, D.stream>>>(ix.d_ids.p, ix.d_offsets.p, ix.d_probe_cluster.p,

@@ -1120,8 +1120,10 @@ __global__ void __launch_bounds__(1024) ivf_rank_kernel(const float *__restrict_
                                                         const uint32_t cp2, const uint32_t nprobe,
                                                         const u64 *__restrict__ list_offsets,
                                                         uint32_t *__restrict__ probe_cluster,
-                                                        u64 *__restrict__ probe_prefix, u64 *__restrict__ n_cand_out,
-                                                        uint32_t *__restrict__ nan_flag) {
+                                                        u64 *__restrict__ probe_prefix, u64 *__restrict__ info,
+                                                        u64 *__restrict__ zero_word) {
+    // info[0] = candidate count, info[1] = 1 when a centroid distance is NaN, info[2], info[3] = 0; *zero_word = 0 (the
+    // entrant counter of the scan that follows): the search needs no memset launches in front of this kernel
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s = reinterpret_cast<u64 *>(smem_raw);
     __shared__ u64 s_part[1024];
@@ -1136,8 +1138,13 @@ __global__ void __launch_bounds__(1024) ivf_rank_kernel(const float *__restrict_
         }
         s[i] = key;
     }
-    if (bad) atomicOr(nan_flag, 1u);
-    __syncthreads();
+    const int any_bad = __syncthreads_or(bad);
+    if (tid == 0) {
+        info[1] = any_bad ? 1u : 0u;
+        info[2] = 0;
+        info[3] = 0;
+        if (zero_word) *zero_word = 0;
+    }
     bitonic_sort_smem(s, cp2, tid, 1024);
     __syncthreads();
     const uint32_t per = (nprobe + 1023) / 1024;
@@ -1165,7 +1172,7 @@ __global__ void __launch_bounds__(1024) ivf_rank_kernel(const float *__restrict_
         }
         if (tid == 31) {
             probe_prefix[nprobe] = incl;
-            *n_cand_out = incl;
+            info[0] = incl;
         }
     }
     __syncthreads();
