@@ -575,6 +575,7 @@ struct PeerExchange {
     u64 **d_peers = nullptr;   // device copy of `peers`
     uint32_t *d_timeout = nullptr;
     PinBuf<u64> h_block;       // world x (1 + cap) words + 1 (timeout flag)
+    double t_enqueued = 0;     // PQV_TRACE: when the last exchange's launches were all enqueued
     size_t words() const { return 2ull * world * (1ull + cap) + 2ull * world; }
 };
 
@@ -2045,6 +2046,7 @@ static int p2p_collect(pqv_ctx *ctx, uint64_t handle, const float *query, uint32
                                                              ds->n_rows ? D.final_topk.p : nullptr, k);
     pqv::peer_wait_pack_kernel<<<1, 256, 0, D.stream>>>(px.local, px.cap, px.world, seq, px.h_block.p, 0u);
     CU_TRY(cudaGetLastError());
+    px.t_enqueued = trace_now_ms();
     CU_TRY(cudaStreamSynchronize(D.stream));
     const u64 *hb = px.h_block.p;
     if (hb[0] & 1ull) return fail(PQV_ECUDA, "peer exchange timed out waiting for the other ranks (sequence %llu)", (unsigned long long)seq);
@@ -2088,10 +2090,24 @@ int pqv_l2_topk_candidates_p2p(pqv_ctx *ctx, uint64_t handle, const float *query
 int pqv_l2_topk_p2p(pqv_ctx *ctx, uint64_t handle, const float *query, uint32_t k, uint32_t flags, uint32_t pos_base,
                     uint32_t *out_row_idx, float *out_dist, uint32_t *out_count, uint32_t *out_overflow) {
     if (!ctx || !query || !out_row_idx || !out_dist || !out_count || !out_overflow) return fail(PQV_EINVAL, "null argument");
+    static const bool trace = getenv("PQV_TRACE") != nullptr;
+    const double t_in = trace ? trace_now_ms() : 0;
     std::lock_guard<std::mutex> lk(ctx->mu);
     u64 total = 0;
     *out_count = 0;
     PQV_TRY(p2p_collect(ctx, handle, query, k, flags, pos_base, &total, out_overflow));
+    const double t_sync = trace ? trace_now_ms() : 0;
+    struct TraceOut {
+        bool on;
+        double t_in, t_sync;
+        pqv_ctx *ctx;
+        ~TraceOut() {
+            if (on)
+                fprintf(stderr, "[pqv trace] l2_topk_p2p rank %u: enqueue %.1f us, wait for the device %.1f us (scan %.1f + post %.1f on the device), replay %.1f us\n",
+                        ctx->peer.rank, (ctx->peer.t_enqueued - t_in) * 1e3, (t_sync - ctx->peer.t_enqueued) * 1e3, ctx->last.scan_ms * 1e3,
+                        ctx->last.post_ms * 1e3, (trace_now_ms() - t_sync) * 1e3);
+        }
+    } trace_out{trace, t_in, t_sync, ctx};
     if (*out_overflow) return PQV_OK;
     const u64 *keys = ctx->peer.h_block.p + 2 + ctx->peer.world;
     if (any_nan_key(keys, total)) {  // a NaN distance: only the loop over every row answers that -- the collective path does it
