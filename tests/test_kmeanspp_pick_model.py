@@ -243,3 +243,75 @@ def test_float_classification_equals_the_integer_one():
                 assert a2 == SAT and a1 >= (1 << 22)     # both lead to "leaves the binade" or a huge step; the kernel re-adds it
             else:
                 assert (a1, t1) == (a2, t2), (E, float(d))
+
+
+# ---- the kernel's element classification and threshold, as it computes them (round 2: no float -> int conversions) ----------
+def kernel_classify(d, E):
+    """pqv_kmeanspp.cuh: t = big + d is d rounded to a multiple of u on top of big = 1.5 * 2^(E-127); a is read off the BIT
+    PATTERNS (bits(t) - bits(big)), the residual d - (t - big) is exact and marks the tie; a = the round-down choice of a tie"""
+    d = np.float32(d)
+    big_bits = np.uint32((E << 23) | 0x400000)
+    big = big_bits.view(np.float32)
+    half_u = np.uint32((E - 24) << 23).view(np.float32)
+    dmax = np.uint32((E - 1) << 23).view(np.float32)
+    if d >= dmax:
+        return SAT, 0
+    t = np.float32(big + d)
+    res = np.float32(d - np.float32(t - big))
+    tie = int(abs(res) == half_u)
+    a = int(t.view(np.uint32)) - int(big_bits) - (1 if res == -half_u else 0)
+    return a, tie
+
+
+def test_bit_pattern_classification_equals_the_integer_model():
+    rng = np.random.default_rng(11)
+    n_checked = 0
+    for E in [25, 26, 40, 100, 127, 128, 150, 200, 253]:
+        u_exp = E - 150
+        cases = []
+        # random elements over 40 binades below the state's, exact half-way cases, multiples of u, sub-normals, zero
+        for sh in range(1, 40):
+            Ed = E - sh
+            if Ed < 1:
+                break
+            for _ in range(40):
+                cases.append(np.uint32((Ed << 23) | int(rng.integers(0, 1 << 23))).view(np.float32))
+            if sh <= 23:
+                half = 1 << (sh - 1)
+                for q in (0, 1, 2, 3, 12345):  # mantissa = q * 2^sh + half: a rounding tie in the state's units
+                    Md = ((q << sh) | half) & 0x7FFFFF
+                    cases.append(np.uint32((Ed << 23) | Md).view(np.float32))
+                    cases.append(np.uint32((Ed << 23) | ((q << sh) & 0x7FFFFF)).view(np.float32))
+        cases += [np.float32(0.0), np.uint32(1).view(np.float32), np.uint32(0x7FFFFF).view(np.float32)]
+        for d in cases:
+            if not (d >= 0):
+                continue
+            a_ref, tie_ref = classify(np.float32(d).view(np.uint32), E)
+            a, tie = kernel_classify(d, E)
+            if a_ref >= (1 << 22):  # a quarter of the binade or more: the kernel sends it to the real add (SAT) -- allowed
+                assert a == SAT or (a, tie) == (a_ref, tie_ref)
+                continue
+            assert (a, tie) == (a_ref, tie_ref), (E, u_exp, float(d), a, tie, a_ref, tie_ref)
+            n_checked += 1
+    assert n_checked > 5000
+
+
+def test_integer_threshold_equals_the_float_compare():
+    """m u >= thr  <=>  m >= ceil(thr / u), with thr / u computed as an f32 multiply by the power of two 1 / u"""
+    rng = np.random.default_rng(12)
+    for E in [25, 60, 127, 150, 230, 253]:
+        u = np.uint32((E - 23) << 23).view(np.float32)
+        inv_u = np.uint32((277 - E) << 23).view(np.float32)
+        ms = [1 << 23, (1 << 23) + 1, (1 << 24) - 1] + [int(v) for v in rng.integers(1 << 23, 1 << 24, 200)]
+        with np.errstate(over="ignore", under="ignore"):
+            thrs = [np.float32(0.0), np.float32(np.inf)]
+            for m in ms[:40]:
+                x = np.float32(np.float32(m) * u)
+                thrs += [x, np.nextafter(x, np.float32(np.inf)), np.nextafter(x, np.float32(0))]
+            thrs += [np.float32(float(u) * 0.3), np.float32(float(u) * 2 ** 30) if E < 200 else np.float32(3e38)]
+            for thr in thrs:
+                tq = np.float32(thr * inv_u)
+                thr_m = int(np.ceil(tq)) if tq < np.float32(33554432.0) else SAT
+                for m in ms:
+                    lhs = bool(np.float32(np.float32(m) * u) >= thr)
+                    assert lhs == (m >= thr_m), (E, m, float(thr), thr_m)
