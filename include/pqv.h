@@ -41,7 +41,10 @@ extern "C" {
 #define PQV_EHANDLE   5  /* unknown dataset / stream handle                                    */
 #define PQV_ELIMIT    6  /* over an implementation limit (k > PQV_MAX_K, dim > PQV_MAX_DIM)    */
 
-#define PQV_MAX_K    1024u   /* per-query k handled by the in-kernel selection               */
+#define PQV_MAX_K    1024u   /* per-query k handled by the in-kernel selection; pqv_l2_topk,
+                                 pqv_l2_topk_gather and pqv_ivf_search also take larger k (every
+                                 candidate's distance is logged and the reference loop replayed on
+                                 the host: exact, slower), the other entry points return PQV_ELIMIT */
 #define PQV_MAX_DIM  16384u  /* query staged in shared memory                                 */
 
 /* flags for the top-k calls */

@@ -915,9 +915,11 @@ Dataset *find_dataset(pqv_ctx *ctx, u64 h) {
     return it == ctx->datasets.end() ? nullptr : &it->second;
 }
 
-int check_topk_args(uint32_t k, uint32_t dim, uint32_t flags) {
+// any_k: the entry point answers k > PQV_MAX_K as well (topk_one's full-replay path: every candidate's distance comes back
+// and the reference loop runs on the host -- slow, but the reference accepts any k)
+int check_topk_args(uint32_t k, uint32_t dim, uint32_t flags, bool any_k = false) {
     if (k == 0) return fail(PQV_EINVAL, "k must be > 0");  // src/ivf/search.rs:67
-    if (k > PQV_MAX_K) return fail(PQV_ELIMIT, "k = %u exceeds PQV_MAX_K = %u", k, PQV_MAX_K);
+    if (k > PQV_MAX_K && !any_k) return fail(PQV_ELIMIT, "k = %u exceeds PQV_MAX_K = %u", k, PQV_MAX_K);
     if (dim == 0) return fail(PQV_EINVAL, "Embedding dimension must be > 0");  // src/ivf/mod.rs:61
     if (dim > PQV_MAX_DIM) return fail(PQV_ELIMIT, "dim = %u exceeds PQV_MAX_DIM = %u", dim, PQV_MAX_DIM);
     if (flags & ~(PQV_SUM_SEQ | PQV_SQRT | PQV_TIES_BY_POSITION)) return fail(PQV_EINVAL, "unknown flags 0x%x", flags);
@@ -948,6 +950,11 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
              const std::function<uint32_t(uint32_t)> *row_fn = nullptr, u64 limit_rows = 0) {
     const int order = (flags & PQV_SUM_SEQ) ? 1 : 0;
     const bool gather = row_ids != nullptr || d_cand != nullptr;
+    // k above what the in-kernel selection holds: the scan runs with k = PQV_MAX_K only to produce the per-candidate distance
+    // log, and the reference loop (any k) is replayed over every candidate on the host -- the path NaN distances take
+    const bool big_k = k > PQV_MAX_K;
+    const uint32_t k_user = k;
+    if (big_k) k = PQV_MAX_K;
     static const bool trace = getenv("PQV_TRACE") != nullptr;
     double tt[4] = {0, 0, 0, 0};
     if (trace) tt[0] = trace_now_ms();
@@ -1027,8 +1034,10 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
         CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
         ScanGeom g;
         const uint32_t pos_base = gather ? 0u : (uint32_t)sh.first_row + pos_offset;
+        if (big_k) PQV_TRY(D.d_dist.ensure(n));
         PQV_TRY(enqueue_scan(ctx, D, sh.d_data, d_ids, n, ds.dim, D.d_query.p, k, order, pos_base, nullptr, D.final_topk.p,
-                             D.ent_out.p, cap, launched.empty(), &g));  // the first launch carries the timing events
+                             D.ent_out.p, cap, launched.empty(), &g, nullptr,  // the first launch carries the timing events
+                             big_k ? D.d_dist.p : nullptr));
         launched.push_back({&D, g, cap, n, sh.d_data, d_ids, pos_base, split ? &gpos[si] : nullptr});
     }
     // keys of one launch: local candidate index -> position in the caller's sequence
@@ -1042,7 +1051,9 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
     for (auto &L : launched) {
         DeviceState &D = *L.D;
         DevGuard guard(D.dev);
-        if (flags & PQV_TIES_BY_POSITION) {
+        if (big_k) {
+            CU_TRY(cudaStreamSynchronize(D.stream));  // the distance log is read below
+        } else if (flags & PQV_TIES_BY_POSITION) {
             PQV_TRY(D.h_final.ensure(PQV_MAX_K));
             CU_TRY(cudaMemcpyAsync(D.h_final.p, D.final_topk.p, (size_t)L.g.kcap * 8, cudaMemcpyDeviceToHost, D.stream));
             CU_TRY(cudaStreamSynchronize(D.stream));
@@ -1087,16 +1098,18 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
     // with `partial_cmp -> Equal`), so nothing short of its own loop over EVERY candidate, in order, reproduces it.  The scan is
     // repeated with a per-candidate distance log and the loop is replayed literally on the host (or, for a rank's half of a
     // sharded search, every row of the slice becomes a candidate).
-    if (!(flags & PQV_TIES_BY_POSITION) && any_nan_key(entrants.data(), entrants.size())) {
+    if (big_k || (!(flags & PQV_TIES_BY_POSITION) && any_nan_key(entrants.data(), entrants.size()))) {
         std::vector<float> dist;
         std::vector<uint32_t> poses;
         for (auto &L : launched) {
             DeviceState &D = *L.D;
             DevGuard guard(D.dev);
-            PQV_TRY(D.d_dist.ensure(L.n));
-            CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
-            PQV_TRY(enqueue_scan(ctx, D, L.d_data, L.d_ids, L.n, ds.dim, D.d_query.p, k, order, L.pos_base, nullptr, D.final_topk.p,
-                                 D.ent_out.p, L.cap, false, nullptr, nullptr, D.d_dist.p));
+            if (!big_k) {  // (big k: the first scan already wrote the log)
+                PQV_TRY(D.d_dist.ensure(L.n));
+                CU_TRY(cudaMemsetAsync(D.ent_out.p, 0, 8, D.stream));
+                PQV_TRY(enqueue_scan(ctx, D, L.d_data, L.d_ids, L.n, ds.dim, D.d_query.p, k, order, L.pos_base, nullptr, D.final_topk.p,
+                                     D.ent_out.p, L.cap, false, nullptr, nullptr, D.d_dist.p));
+            }
             const size_t base = dist.size();
             dist.resize(base + L.n);
             CU_TRY(cudaMemcpyAsync(dist.data() + base, D.d_dist.p, L.n * 4, cudaMemcpyDeviceToHost, D.stream));
@@ -1125,8 +1138,18 @@ int topk_one(pqv_ctx *ctx, Dataset &ds, const float *query, const uint32_t *row_
             }
             return PQV_OK;
         }
+        if (flags & PQV_TIES_BY_POSITION) {  // (big k only) the k smallest by (distance, position)
+            std::vector<u64> keys(dist.size());
+            for (size_t i = 0; i < dist.size(); ++i) {
+                uint32_t b;
+                memcpy(&b, &dist[i], 4);
+                keys[i] = ((u64)b << 32) | poses[i];
+            }
+            *out_count = (uint32_t)emit_by_position(keys, row_of, k_user, flags, out_rows, out_dist);
+            return PQV_OK;
+        }
         *out_count = (uint32_t)replay_ordered(
-            dist.size(), [&](size_t i) { return ReplayItem{dist[i], row_of(poses[i])}; }, k, flags, out_rows, out_dist);
+            dist.size(), [&](size_t i) { return ReplayItem{dist[i], row_of(poses[i])}; }, k_user, flags, out_rows, out_dist);
         return PQV_OK;
     }
     if (entrants_out) {
@@ -1735,13 +1758,14 @@ int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_
     std::lock_guard<std::mutex> lk(ctx->mu);
     Dataset *ds = find_dataset(ctx, handle);
     if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
-    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    PQV_TRY(check_topk_args(k, ds->dim, flags, true));
+    const bool big_k = k > PQV_MAX_K;  // answered query by query through topk_one's full replay
     // several queries: one tensor-core pass over the table answers every query whose result does not hinge on the
     // reference heap's layout (pqv_tc.cuh); the rest -- and small batches -- take the single-query scan
     std::vector<uint8_t> handled(n_queries, 0);
     ctx->last_batch = pqv_batch_timing{};
     ctx->batch_state.valid = false;
-    if (n_queries && ds->n_rows && batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k)) {
+    if (!big_k && n_queries && ds->n_rows && batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k)) {
         DeviceState &D = ctx->devs[ds->shards[0].di];
         DevGuard guard(D.dev);
         // at most BATCH_MAX_QUERIES queries per pass over the table (the pass' scratch grows with the batch)
@@ -1769,7 +1793,7 @@ int pqv_l2_topk(pqv_ctx *ctx, uint64_t handle, const float *queries, uint32_t n_
         }
         ctx->last_batch = total;
     }
-    if (n_queries && ds->n_rows && ds->shards.size() > 1 && !(flags & PQV_TIES_BY_POSITION) &&
+    if (!big_k && n_queries && ds->n_rows && ds->shards.size() > 1 && !(flags & PQV_TIES_BY_POSITION) &&
         batch_path_applies(*ds, ds->shards[0].d_data, n_queries, k, true))
         PQV_TRY(batch_topk_sharded(ctx, *ds, queries, n_queries, k, flags, out_row_idx, out_dist, out_count, handled));
     for (uint32_t q = 0; q < n_queries; ++q)
@@ -1792,7 +1816,7 @@ int pqv_l2_topk_gather(pqv_ctx *ctx, uint64_t handle, const float *query, const 
     std::lock_guard<std::mutex> lk(ctx->mu);
     Dataset *ds = find_dataset(ctx, handle);
     if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
-    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    PQV_TRY(check_topk_args(k, ds->dim, flags, true));
     if (n_ids > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "candidate positions are u32");
     for (u64 i = 0; i < n_ids; ++i)
         if (row_ids[i] >= ds->n_rows) return fail(PQV_EINVAL, "row id %u at position %llu is out of range (%llu rows)", row_ids[i], (unsigned long long)i, (unsigned long long)ds->n_rows);

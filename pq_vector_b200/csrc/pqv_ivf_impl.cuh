@@ -1033,7 +1033,7 @@ static int ivf_search_one(pqv_ctx *ctx, Dataset *ds, DeviceState &D, IvfIndex *i
                           uint32_t nprobe, uint32_t flags, uint32_t *out_row_idx, float *out_dist, uint32_t *out_count) {
     PQV_TRY(index_make_resident(D, *ix));
     const bool multi = ds->shards.size() > 1;  // table spread over several devices: ranking here, candidates split by owner (topk_one)
-    if (!multi && ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids) {
+    if (!multi && ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids && k <= PQV_MAX_K) {  // (larger k: topk_one's full replay)
         bool done = false;
         PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, query, k, nprobe, flags, out_row_idx, out_dist, out_count, &done));
         if (done) return PQV_OK;  // otherwise: NaN distance or entrant overflow -> host-ranked path below
@@ -1079,7 +1079,7 @@ int pqv_ivf_search(pqv_ctx *ctx, uint64_t handle, uint64_t index, const float *q
     if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
     IvfIndex *ix = find_index(ctx, index);
     if (!ix) return fail(PQV_EHANDLE, "unknown index handle %llu", (unsigned long long)index);
-    PQV_TRY(check_topk_args(k, ds->dim, flags));
+    PQV_TRY(check_topk_args(k, ds->dim, flags, true));
     if (ix->dim != ds->dim) return fail(PQV_EINVAL, "Query dimension mismatch: expected %u, got %u", ix->dim, ds->dim);
     PQV_TRY(check_index_fits(*ix, *ds));
     DeviceState &D = ctx->devs[ds->shards[0].di];
@@ -1572,7 +1572,7 @@ int pqv_vector_topk_indexed(pqv_ctx *ctx, uint64_t handle, uint64_t index, const
         if (out_rows_scored) *out_rows_scored = 0;
         return PQV_OK;
     }
-    if (!multi && ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids) {
+    if (!multi && ivf_fused_enabled() && ix->n_clusters <= IVF_RANK_MAX_C && ix->n_ids && k <= PQV_MAX_K) {  // (larger k: topk_one's full replay)
         bool done = false;
         PQV_TRY(ivf_search_fused(ctx, *ds, D, *ix, query, k, nprobe, flags, out_row_idx, out_dist, out_count, &done, &ro));
         if (done) {

@@ -277,6 +277,13 @@ def test_search_with_empty_lists_ties_and_duplicates(ctx):
                     assert cand.tolist() == O.candidate_rows(q, cent, offsets, ids, nprobe).tolist()
                     er, ed = O.topk_rerank_gather(q, data, cand, k, 1 if flags & SEQ else 0, bool(flags & SQRT))
                     assert r.tolist() == er.tolist() and d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
+    # k above the in-kernel selection (PQV_MAX_K = 1024): distance log + reference loop on the host
+    for k in (1025, 3000):
+        for flags in (SQRT, SEQ):
+            r, d = ix.search(ds, data[150], k, 5, flags)
+            cand = O.candidate_rows(data[150], cent, offsets, ids, 5)
+            er, ed = O.topk_rerank_gather(data[150], data, cand, k, 1 if flags & SEQ else 0, bool(flags & SQRT))
+            assert r.tolist() == er.tolist() and d.view(np.uint32).tolist() == ed.view(np.uint32).tolist()
     # an index whose probed lists are all empty
     off2 = np.zeros(13, np.uint64)
     off2[12:] = 0

@@ -189,6 +189,38 @@ def test_gather_matches_oracle(ctx):
     ds.drop()
 
 
+def test_k_above_the_in_kernel_selection(ctx):
+    """the reference takes any k (search.rs:112-141); above PQV_MAX_K = 1024 the library logs every candidate's distance and
+    replays the reference loop on the host: dense, gathered, quantised data (ties), both summation orders, both tie modes"""
+    rng = np.random.default_rng(77)
+    data = rng.random((6000, 24), dtype=np.float32)
+    ds = ctx.dataset_from(data)
+    q = rng.random(24, dtype=np.float32)
+    for k in (1025, 2000, 5999, 6000, 9000):
+        check_topk(ds, data, q, k, SQRT)
+        check_topk(ds, data, q, k, SEQ)
+    ids = rng.permutation(6000)[:3000].astype(np.uint32)
+    check_topk(ds, data, q, 1500, SQRT, ids)
+    check_topk(ds, data, q, 4000, SEQ | SQRT, ids)
+    ds.drop()
+    grid = rng.integers(0, 3, (20_000, 4)).astype(np.float32)   # thousands of bit-equal distances
+    ds = ctx.dataset_from(grid)
+    q0 = np.zeros(4, np.float32)
+    check_topk(ds, grid, q0, 3000, SQRT)
+    check_topk(ds, grid, q0, 1100, SEQ)
+    r, d = ds.l2_topk(q0, 2500, BYPOS)
+    dist = O.distances(grid, q0, 0)
+    order = np.lexsort((np.arange(20_000), dist))[:2500]
+    assert r.tolist() == order.tolist() and bits(d).tolist() == bits(dist[order]).tolist()
+    # several queries per call take the same path one by one
+    qs = rng.integers(0, 3, (5, 4)).astype(np.float32)
+    rows, dd, cnt = ds.l2_topk(qs, 1200, SQRT)
+    for i in range(5):
+        er, ed = O.topk_rerank(qs[i], grid, None, 1200, 0, True)
+        assert rows[i, :cnt[i]].tolist() == er.tolist() and bits(dd[i, :cnt[i]]).tolist() == bits(ed).tolist()
+    ds.drop()
+
+
 def test_ties_by_position_mode(ctx):
     rng = np.random.default_rng(12)
     data = rng.integers(0, 3, (10_000, 4)).astype(np.float32)
@@ -346,8 +378,10 @@ def test_errors(ctx, P):
         ds.l2_topk(np.zeros(4, np.float32), 0)
     with pytest.raises(P.PqvError, match="Query dimension mismatch: expected 4, got 5"):
         ds.l2_topk(np.zeros(5, np.float32), 1)
-    with pytest.raises(P.PqvError) as ei:
-        ds.l2_topk(np.zeros(4, np.float32), 5000)
+    r, d = ds.l2_topk(np.zeros(4, np.float32), 5000)   # k above the in-kernel selection: answered by the full replay (10 rows)
+    assert r.size == 10
+    with pytest.raises(P.PqvError) as ei:               # the streaming form keeps the limit
+        ctx.topk_stream(np.zeros(4, np.float32), 5000)
     assert ei.value.code == 6
     with pytest.raises(P.PqvError, match="out of range"):
         ds.l2_topk_gather(np.zeros(4, np.float32), np.array([10], np.uint32), 1)
