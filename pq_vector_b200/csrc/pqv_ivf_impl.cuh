@@ -522,6 +522,7 @@ int kmeans_train_device(DeviceState &D, const float *d_sample, u64 ns, uint32_t 
             ce = cudaStreamSynchronize(D.stream);
             if (ce != cudaSuccess) rc = fail(PQV_ECUDA, "k-means++ on the device failed: %s", cudaGetErrorString(ce));
         }
+        if (tune.repeated) cudaCtxResetPersistingL2Cache();  // the init set's evict_last lines have no claim on the L2 any more
         if (trace_pp) {
             fprintf(stderr, "[pqv trace] k-means++ on the device (%u picks over %llu rows, %llu chunk sums): %.1f ms\n", C - 1,
                     (unsigned long long)init_n, (unsigned long long)n_chunks, now_ms() - t_a);
