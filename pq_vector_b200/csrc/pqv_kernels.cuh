@@ -753,6 +753,7 @@ __global__ void __launch_bounds__(256) l2_dist_wide_kernel(const float *__restri
 // Ties: lowest centroid index (strict '<' while scanning centroids upwards); NaN/inf never win.
 // ------------------------------------------------------------------------------------------------
 constexpr int AS_BM = 64, AS_BN = 64, AS_BK = 32, AS_LD = AS_BK + 4;
+constexpr uint32_t FEW_ROWS_MAX = 256;  // device-side row lists up to this length take few_rows_assign_kernel
 
 // GATHER: the tile's rows are row_ids[0 .. *n_dev) (a device-side list: the rows the tensor-core filter could not
 // decide).  The grid covers the worst case in x and surplus CTAs exit at once; blockIdx.y selects a slice of slice_len
@@ -774,6 +775,7 @@ __global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__re
     const uint32_t tid = threadIdx.x;
     const uint32_t tx = tid & 15, ty = tid >> 4;
     const u64 n = GATHER ? (u64)*n_dev : n_arg;
+    if (GATHER && n <= FEW_ROWS_MAX) return;            // short lists: few_rows_assign_kernel
     const uint32_t n4 = dim >> 2;                       // full 4-chunks (chain terms)
     const uint32_t nkb = (n4 + 7) >> 3;                 // blocks of 8 chunks = 32 columns
     const uint32_t tail0 = n4 << 2, ntail = dim - tail0;  // scalar tail terms (dim % 4)
@@ -909,6 +911,51 @@ __global__ void __launch_bounds__(256, 2) kmeans_assign_kernel(const float *__re
         }
     }
     }  // row tiles
+}
+
+// ------------------------------------------------------------------------------------------------
+// few_rows_assign_kernel: the same exact argmin pieces for a SHORT device-side list of rows (the rows the tensor-core filter
+// hands to the full scan: a few per million).  The 64-row tiles of kmeans_assign_kernel<.., GATHER> spend ~70 us of
+// barriers and k-blocks on four rows; here one warp takes (row, 32 centroids): the row sits in the warp's shared-memory
+// slot as the "query", the 32 centroids are the "rows" of group_distance<0> (squared_l2_distance(row, centroid): the
+// difference's sign does not reach the square), lane j holds centroid j's exact chain, the warp's finite minimum folds into
+// best[row] = min(bits(distance) << 32 | centroid) like the tiled kernel's.  Lists longer than FEW_ROWS_MAX are left to the
+// tiled kernel (which re-uses its operand tiles); both kernels are launched and the device-side count picks one.
+// Dynamic shared memory: warps * (dim_pad + TileCfg<0, VEC4>::TILE_FLOATS) floats.
+// ------------------------------------------------------------------------------------------------
+template <bool VEC4>
+__global__ void __launch_bounds__(256) few_rows_assign_kernel(const float *__restrict__ rows, const uint32_t dim,
+                                                              const float *__restrict__ centroids, const uint32_t n_clusters,
+                                                              const uint32_t *__restrict__ row_ids,
+                                                              const uint32_t *__restrict__ n_dev, u64 *__restrict__ best) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int TILE_FLOATS = TileCfg<0, VEC4>::TILE_FLOATS;
+    const uint32_t n = *n_dev;
+    if (n == 0 || n > FEW_ROWS_MAX) return;
+    const uint32_t dim_pad = (dim + 3u) & ~3u;
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5, warps = blockDim.x >> 5;
+    float *s_vec = reinterpret_cast<float *>(smem_raw) + (size_t)warp * (dim_pad + TILE_FLOATS);
+    float *tile = s_vec + dim_pad;
+    const uint32_t nslices = (n_clusters + 31u) >> 5;
+    const uint32_t items = n * nslices;
+    uint32_t have_row = 0xFFFFFFFFu;
+    for (uint32_t item = blockIdx.x * warps + warp; item < items; item += gridDim.x * warps) {
+        const uint32_t r = item / nslices, sl = item - r * nslices;
+        const uint32_t row = row_ids[r];
+        if (row != have_row) {
+            __syncwarp();
+            for (uint32_t i = lane; i < dim; i += 32) s_vec[i] = rows[(u64)row * dim + i];
+            have_row = row;
+            __syncwarp();
+        }
+        const float d = group_distance<0, VEC4, false>(centroids, nullptr, (u64)n_clusters, dim, (u64)sl, s_vec, tile, lane);
+        const uint32_t c = (sl << 5) + lane;
+        u64 key = KEY_MAX;
+        if (c < n_clusters && d < __int_as_float(0x7f800000)) key = ((u64)__float_as_uint(d) << 32) | (u64)c;  // NaN / inf never win
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) key = min(key, (u64)__shfl_xor_sync(0xffffffffu, key, off));
+        if (lane == 0 && key != KEY_MAX) atomicMin(reinterpret_cast<unsigned long long *>(&best[row]), key);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------

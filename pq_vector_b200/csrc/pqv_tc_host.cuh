@@ -313,6 +313,13 @@ int assign_tc(DeviceState &D, const float *d_rows, u64 n, uint32_t dim, const fl
         dim3 grid_ovf((uint32_t)std::min<u64>((n + pqv::AS_BM - 1) / pqv::AS_BM, (u64)D.sm_count * 2), (C + slice_len - 1) / slice_len);
         pqv::kmeans_assign_kernel<true, true><<<grid_ovf, 256, 0, D.stream>>>(d_rows, 0, dim, d_cent, C, nullptr, D.tc_ovf_rows.p,
                                                                               counts + 1, D.tc_best.p, slice_len);
+        // ... which leaves lists of up to FEW_ROWS_MAX rows (the usual handful) to the warp-per-(row, 32 centroids) kernel
+        const size_t per_warp = ((size_t)((dim + 3u) & ~3u) + pqv::TileCfg<0, true>::TILE_FLOATS) * 4;
+        const uint32_t fw = (uint32_t)std::max<size_t>(1, std::min<size_t>(8, (200 * 1024) / per_warp));
+        auto few = pqv::few_rows_assign_kernel<true>;
+        PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(few), per_warp * fw));
+        few<<<(uint32_t)D.sm_count * 2, fw * 32, per_warp * fw, D.stream>>>(d_rows, dim, d_cent, C, D.tc_ovf_rows.p, counts + 1,
+                                                                             D.tc_best.p);
     }
     T::best_finalize_kernel<<<(uint32_t)D.sm_count * 2, 256, 0, D.stream>>>(counts, D.tc_amb_rows.p, D.tc_ovf_rows.p, D.tc_best.p,
                                                                             d_out);
