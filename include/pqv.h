@@ -68,11 +68,12 @@ typedef struct pqv_ctx pqv_ctx;
  * pqv_l2_topk_gather / pqv_ivf_search(_batch) / pqv_vector_topk_indexed(_batch) (candidates split by
  * owning shard, keys moved back to the caller's sequence positions before the heap replay),
  * pqv_kmeans_assign over the resident table, pqv_ivf_build (sample gathered to the first device,
- * rows assigned where they live) and pqv_dataset_read(_rows) -- all with the results of a single
- * device, bit for bit (tests/test_gpu_multi_device.py).  The per-rank entry points further down
+ * rows assigned where they live), pqv_array_distance(_topk,_topk_filtered) (every shard fills its
+ * slice of the column / selects its own k smallest, merged by (distance, row)) and
+ * pqv_dataset_read(_rows) -- all with the results of a single device, bit for bit
+ * (tests/test_gpu_multi_device.py).  The per-rank entry points further down
  * (*_candidates, *_keys, *_p2p) are the other form: one process per GPU, each with its own context.
- * Still single-device only: pqv_array_distance*, pqv_kmeans_train, pqv_min_dist_update over a
- * resident table. */
+ * Still single-device only: pqv_kmeans_train and pqv_min_dist_update over a resident table. */
 PQV_API int  pqv_init(pqv_ctx **out, const int *device_ids, int n_devices);
 PQV_API void pqv_destroy(pqv_ctx *ctx);
 PQV_API const char *pqv_last_error(void);

@@ -68,7 +68,6 @@ int adist_resolve(pqv_ctx *ctx, uint64_t handle, const double *query, uint32_t q
     // upstream: exec_err!("Both arrays must have the same length") per row
     if (query_len != ds->dim) return fail(PQV_EINVAL, "Both arrays must have the same length (row %u, literal %u)", ds->dim, query_len);
     if (metric != PQV_METRIC_L2 && metric != PQV_METRIC_COSINE) return fail(PQV_EINVAL, "unknown metric %u", metric);
-    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "array_distance needs a single-device dataset");
     *ds_out = ds;
     return PQV_OK;
 }
@@ -84,13 +83,22 @@ int pqv_array_distance(pqv_ctx *ctx, uint64_t handle, const double *query, uint3
     PQV_TRY(adist_resolve(ctx, handle, query, query_len, metric, &ds));
     if (ds->n_rows == 0) return PQV_OK;
     if (!out) return fail(PQV_EINVAL, "out is null");
-    Shard &sh = ds->shards[0];
-    DeviceState &D = ctx->devs[sh.di];
-    DevGuard guard(D.dev);
-    PQV_TRY(D.ad_col.ensure(ds->n_rows));
-    PQV_TRY(adist_launch(D, sh.d_data, ds->n_rows, ds->dim, query, metric, D.ad_col.p));
-    CU_TRY(cudaMemcpyAsync(out, D.ad_col.p, (size_t)ds->n_rows * 8, cudaMemcpyDeviceToHost, D.stream));
-    CU_TRY(cudaStreamSynchronize(D.stream));
+    // a table spread over several devices: every shard (its own device state, stream and scratch) fills its slice of the
+    // column; all passes are enqueued before the first one is waited for
+    for (Shard &sh : ds->shards) {
+        if (sh.n_rows == 0) continue;
+        DeviceState &D = ctx->devs[sh.di];
+        DevGuard guard(D.dev);
+        PQV_TRY(D.ad_col.ensure(sh.n_rows));
+        PQV_TRY(adist_launch(D, sh.d_data, sh.n_rows, ds->dim, query, metric, D.ad_col.p));
+        CU_TRY(cudaMemcpyAsync(out + sh.first_row, D.ad_col.p, (size_t)sh.n_rows * 8, cudaMemcpyDeviceToHost, D.stream));
+    }
+    for (Shard &sh : ds->shards) {
+        if (sh.n_rows == 0) continue;
+        DeviceState &D = ctx->devs[sh.di];
+        DevGuard guard(D.dev);
+        CU_TRY(cudaStreamSynchronize(D.stream));
+    }
     return PQV_OK;
 }
 
@@ -104,62 +112,94 @@ static int adist_topk_impl(pqv_ctx *ctx, uint64_t handle, const double *query, u
     if (!out_row_idx || !out_dist) return fail(PQV_EINVAL, "null argument");
     *out_count = 0;
     if (ds->n_rows == 0) return PQV_OK;
-    const u64 n = ds->n_rows;
-    Shard &sh = ds->shards[0];
-    DeviceState &D = ctx->devs[sh.di];
-    DevGuard guard(D.dev);
-    // the scan subtree's filter: rows whose bit is clear never reach the sort (FilterExec below SortExec)
-    const uint32_t *d_mask = nullptr;
-    u64 live = n;
-    if (row_mask) {
-        const u64 n_words = (n + 31) / 32;
-        PQV_TRY(D.vt_bitmap.ensure(n_words));
-        CU_TRY(cudaMemsetAsync(D.vt_bitmap.p + (n_words - 1), 0, 4, D.stream));
-        CU_TRY(cudaMemcpyAsync(D.vt_bitmap.p, row_mask, (size_t)((n + 7) / 8), cudaMemcpyHostToDevice, D.stream));
-        d_mask = D.vt_bitmap.p;
-        live = 0;
-        for (u64 i = 0; i < n / 8; ++i) live += (u64)__builtin_popcount(row_mask[i]);
-        for (u64 r = n / 8 * 8; r < n; ++r) live += (row_mask[r >> 3] >> (r & 7)) & 1u;
-        if (live == 0) {
-            CU_TRY(cudaStreamSynchronize(D.stream));
-            return PQV_OK;
+    // Every shard (one per device of the context) selects its own k smallest; the host merges them by (distance, row).  All
+    // passes are enqueued before the first one is waited for.
+    struct Part {
+        DeviceState *D;
+        u64 first_row;
+        uint32_t k_eff;
+    };
+    std::vector<Part> parts;
+    const u64 total_mask_bytes = (ds->n_rows + 7) / 8;
+    for (Shard &sh : ds->shards) {
+        const u64 n = sh.n_rows;
+        if (n == 0) continue;
+        DeviceState &D = ctx->devs[sh.di];
+        DevGuard guard(D.dev);
+        // the scan subtree's filter: rows whose bit is clear never reach the sort (FilterExec below SortExec)
+        const uint32_t *d_mask = nullptr;
+        u64 live = n;
+        if (row_mask) {
+            // this shard's bits [first_row, first_row + n) of the caller's bitmap, moved down to bit 0
+            const u64 nb = (n + 7) / 8, b0 = sh.first_row >> 3;
+            const unsigned shft = (unsigned)(sh.first_row & 7);
+            std::vector<uint8_t> m(nb);
+            for (u64 j = 0; j < nb; ++j) {
+                unsigned v = row_mask[b0 + j] >> shft;
+                if (shft && b0 + j + 1 < total_mask_bytes) v |= (unsigned)row_mask[b0 + j + 1] << (8 - shft);
+                m[j] = (uint8_t)v;
+            }
+            if (n & 7) m[nb - 1] &= (uint8_t)((1u << (n & 7)) - 1u);
+            live = 0;
+            for (u64 j = 0; j < nb; ++j) live += (u64)__builtin_popcount(m[j]);
+            if (live == 0) continue;
+            const u64 n_words = (n + 31) / 32;
+            PQV_TRY(D.vt_bitmap.ensure(n_words));
+            CU_TRY(cudaMemsetAsync(D.vt_bitmap.p + (n_words - 1), 0, 4, D.stream));
+            CU_TRY(cudaMemcpyAsync(D.vt_bitmap.p, m.data(), (size_t)nb, cudaMemcpyHostToDevice, D.stream));
+            CU_TRY(cudaStreamSynchronize(D.stream));  // `m` goes out of scope
+            d_mask = D.vt_bitmap.p;
+        }
+        const uint32_t k_eff = (uint32_t)std::min<u64>(k, live);
+        PQV_TRY(D.ad_col.ensure(n));
+        PQV_TRY(D.ad_state.ensure(1));
+        PQV_TRY(D.ad_out_dist.ensure(k_eff));
+        PQV_TRY(D.ad_out_row.ensure(k_eff));
+        PQV_TRY(D.h_ad_dist.ensure(PQV_MAX_K));
+        PQV_TRY(D.h_ad_row.ensure(PQV_MAX_K));
+        PQV_TRY(D.h_ad_state.ensure(1));
+        CU_TRY(cudaEventRecord(D.ev[0], D.stream));
+        PQV_TRY(adist_launch(D, sh.d_data, n, ds->dim, query, metric, D.ad_col.p));
+        CU_TRY(cudaEventRecord(D.ev[1], D.stream));
+        const uint32_t hgrid = (uint32_t)std::max<u64>(1, std::min<u64>((u64)D.sm_count * 8, (n + 255) / 256));
+        pqv::sel_init_kernel<<<1, 256, 0, D.stream>>>(D.ad_state.p, k_eff);
+        for (int pass = 0; pass < 12; ++pass) {
+            pqv::sel_hist_kernel<<<hgrid, 256, 0, D.stream>>>(D.ad_col.p, n, pass, D.ad_state.p, d_mask);
+            pqv::sel_pick_kernel<<<1, 256, 0, D.stream>>>(pass, D.ad_state.p);
+        }
+        pqv::sel_collect_kernel<<<hgrid, 256, 0, D.stream>>>(D.ad_col.p, n, D.ad_state.p, k_eff, D.ad_out_dist.p, D.ad_out_row.p, d_mask);
+        CU_TRY(cudaGetLastError());
+        CU_TRY(cudaEventRecord(D.ev[2], D.stream));
+        CU_TRY(cudaMemcpyAsync(D.h_ad_dist.p, D.ad_out_dist.p, (size_t)k_eff * 8, cudaMemcpyDeviceToHost, D.stream));
+        CU_TRY(cudaMemcpyAsync(D.h_ad_row.p, D.ad_out_row.p, (size_t)k_eff * 4, cudaMemcpyDeviceToHost, D.stream));
+        CU_TRY(cudaMemcpyAsync(D.h_ad_state.p, D.ad_state.p, sizeof(pqv::SelState), cudaMemcpyDeviceToHost, D.stream));
+        parts.push_back(Part{&D, sh.first_row, k_eff});
+    }
+    std::vector<double> hd;
+    std::vector<uint32_t> hr;
+    ctx->last = pqv_timing{};
+    for (Part &P : parts) {
+        DeviceState &D = *P.D;
+        DevGuard guard(D.dev);
+        CU_TRY(cudaStreamSynchronize(D.stream));
+        if (D.h_ad_state.p->out_count != P.k_eff)
+            return fail(PQV_ECUDA, "array_distance top-k: selected %u keys, expected %u", D.h_ad_state.p->out_count, P.k_eff);
+        float ms_scan = 0.f, ms_sel = 0.f;
+        cudaEventElapsedTime(&ms_scan, D.ev[0], D.ev[1]);
+        cudaEventElapsedTime(&ms_sel, D.ev[1], D.ev[2]);
+        // the slowest shard is the call's device time
+        if (ms_scan + ms_sel > ctx->last.total_ms) {
+            ctx->last.scan_ms = ms_scan;
+            ctx->last.post_ms = ms_sel;
+            ctx->last.total_ms = ms_scan + ms_sel;
+        }
+        for (uint32_t i = 0; i < P.k_eff; ++i) {
+            hd.push_back(D.h_ad_dist.p[i]);
+            hr.push_back((uint32_t)(D.h_ad_row.p[i] + P.first_row));
         }
     }
-    const uint32_t k_eff = (uint32_t)std::min<u64>(k, live);
-    PQV_TRY(D.ad_col.ensure(n));
-    PQV_TRY(D.ad_state.ensure(1));
-    PQV_TRY(D.ad_out_dist.ensure(k_eff));
-    PQV_TRY(D.ad_out_row.ensure(k_eff));
-    PQV_TRY(D.h_ad_dist.ensure(PQV_MAX_K));
-    PQV_TRY(D.h_ad_row.ensure(PQV_MAX_K));
-    PQV_TRY(D.h_ad_state.ensure(1));
-    CU_TRY(cudaEventRecord(D.ev[0], D.stream));
-    PQV_TRY(adist_launch(D, sh.d_data, n, ds->dim, query, metric, D.ad_col.p));
-    CU_TRY(cudaEventRecord(D.ev[1], D.stream));
-    const uint32_t hgrid = (uint32_t)std::max<u64>(1, std::min<u64>((u64)D.sm_count * 8, (n + 255) / 256));
-    pqv::sel_init_kernel<<<1, 256, 0, D.stream>>>(D.ad_state.p, k_eff);
-    for (int pass = 0; pass < 12; ++pass) {
-        pqv::sel_hist_kernel<<<hgrid, 256, 0, D.stream>>>(D.ad_col.p, n, pass, D.ad_state.p, d_mask);
-        pqv::sel_pick_kernel<<<1, 256, 0, D.stream>>>(pass, D.ad_state.p);
-    }
-    pqv::sel_collect_kernel<<<hgrid, 256, 0, D.stream>>>(D.ad_col.p, n, D.ad_state.p, k_eff, D.ad_out_dist.p, D.ad_out_row.p, d_mask);
-    CU_TRY(cudaGetLastError());
-    CU_TRY(cudaEventRecord(D.ev[2], D.stream));
-    CU_TRY(cudaMemcpyAsync(D.h_ad_dist.p, D.ad_out_dist.p, (size_t)k_eff * 8, cudaMemcpyDeviceToHost, D.stream));
-    CU_TRY(cudaMemcpyAsync(D.h_ad_row.p, D.ad_out_row.p, (size_t)k_eff * 4, cudaMemcpyDeviceToHost, D.stream));
-    CU_TRY(cudaMemcpyAsync(D.h_ad_state.p, D.ad_state.p, sizeof(pqv::SelState), cudaMemcpyDeviceToHost, D.stream));
-    CU_TRY(cudaStreamSynchronize(D.stream));
-    if (D.h_ad_state.p->out_count != k_eff)
-        return fail(PQV_ECUDA, "array_distance top-k: selected %u keys, expected %u", D.h_ad_state.p->out_count, k_eff);
-    float ms_scan = 0.f, ms_sel = 0.f;
-    cudaEventElapsedTime(&ms_scan, D.ev[0], D.ev[1]);
-    cudaEventElapsedTime(&ms_sel, D.ev[1], D.ev[2]);
-    ctx->last = pqv_timing{};
-    ctx->last.scan_ms = ms_scan;
-    ctx->last.post_ms = ms_sel;
-    ctx->last.total_ms = ms_scan + ms_sel;
-    ctx->last.scan_bytes = n * (u64)ds->dim * 4;
-    ctx->last.launches = 27;
+    ctx->last.scan_bytes = ds->n_rows * (u64)ds->dim * 4;
+    ctx->last.launches = 27 * (uint32_t)parts.size();
     // ascending by (f64 total order with NaN last, row)
     auto ordered = [](double d) {
         u64 b;
@@ -167,19 +207,18 @@ static int adist_topk_impl(pqv_ctx *ctx, uint64_t handle, const double *query, u
         if ((b & 0x7FFFFFFFFFFFFFFFull) > 0x7FF0000000000000ull) b = 0x7FF8000000000000ull;
         return (b >> 63) ? ~b : (b | 0x8000000000000000ull);
     };
-    std::vector<uint32_t> idx(k_eff);
-    for (uint32_t i = 0; i < k_eff; ++i) idx[i] = i;
-    const double *hd = D.h_ad_dist.p;
-    const uint32_t *hr = D.h_ad_row.p;
+    std::vector<uint32_t> idx(hd.size());
+    for (uint32_t i = 0; i < idx.size(); ++i) idx[i] = i;
     std::sort(idx.begin(), idx.end(), [&](uint32_t a, uint32_t b) {
         const u64 ua = ordered(hd[a]), ub = ordered(hd[b]);
         return ua != ub ? ua < ub : hr[a] < hr[b];
     });
-    for (uint32_t i = 0; i < k_eff; ++i) {
+    const uint32_t n_out = (uint32_t)std::min<size_t>(k, idx.size());
+    for (uint32_t i = 0; i < n_out; ++i) {
         out_row_idx[i] = hr[idx[i]];
         out_dist[i] = hd[idx[i]];
     }
-    *out_count = k_eff;
+    *out_count = n_out;
     return PQV_OK;
 }
 

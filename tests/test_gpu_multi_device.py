@@ -154,3 +154,33 @@ def test_assignment_and_index_build_equal_the_single_device_ones(mctx, sctx):
     assert mi.to_bytes() == si.to_bytes()
     for d_ in (mds, sds, mt, stn):
         d_.drop()
+
+
+def test_array_distance_arm_over_several_shards(mctx):
+    """the un-indexed arm (pqv_array_distance, _topk, _topk_filtered) over a table spread over several device states: the
+    Float64 column and the exact (distance, row) top-k against the oracle, with a filter whose bits cross the shard
+    boundaries (row counts that are no multiples of 8, quantised data with ties across shards)"""
+    rng = np.random.default_rng(31)
+    for n, dim, grid in [(10_007, 48, False), (5_003, 16, True), (3, 8, False)]:
+        data = (rng.integers(0, 3, (n, dim)).astype(np.float32) if grid else rng.random((n, dim), dtype=np.float32))
+        q = (np.zeros(dim) if grid else rng.random(dim) + 1e-9)
+        ds = mctx.dataset_from(data)
+        for metric in (0, 1):
+            got = ds.array_distance(q, metric)
+            exp = O.array_distance_column(data, q, metric)
+            assert np.asarray(got).view(np.uint64).tolist() == np.asarray(exp).view(np.uint64).tolist()
+        for k in (1, 7, 100, 1024):
+            rows, dist = ds.array_distance_topk(q, k)
+            er, ed = O.array_distance_topk(data, q, k)
+            assert rows.tolist() == er.tolist() and np.asarray(dist).view(np.uint64).tolist() == np.asarray(ed).view(np.uint64).tolist()
+        for share in (0.5, 0.01, 0.0):
+            mask = rng.random(n) < share
+            rows, dist = ds.array_distance_topk(q, 50, row_mask=mask)
+            keep = np.nonzero(mask)[0]
+            if keep.size == 0:
+                assert rows.size == 0
+                continue
+            er, ed = O.array_distance_topk(data[keep], q, 50)
+            assert rows.tolist() == keep[er].tolist()
+            assert np.asarray(dist).view(np.uint64).tolist() == np.asarray(ed).view(np.uint64).tolist()
+        ds.drop()
