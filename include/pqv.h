@@ -73,7 +73,8 @@ typedef struct pqv_ctx pqv_ctx;
  * pqv_dataset_read(_rows) -- all with the results of a single device, bit for bit
  * (tests/test_gpu_multi_device.py).  The per-rank entry points further down
  * (*_candidates, *_keys, *_p2p) are the other form: one process per GPU, each with its own context.
- * Still single-device only: pqv_kmeans_train and pqv_min_dist_update over a resident table. */
+ * pqv_kmeans_train and pqv_min_dist_update over a resident table collect the rows they need on the
+ * first device and run there. */
 PQV_API int  pqv_init(pqv_ctx **out, const int *device_ids, int n_devices);
 PQV_API void pqv_destroy(pqv_ctx *ctx);
 PQV_API const char *pqv_last_error(void);

@@ -2583,10 +2583,29 @@ int pqv_min_dist_update(pqv_ctx *ctx, uint64_t handle, const float *rows, const 
     }
     DeviceState *D = nullptr;
     const float *d_rows = nullptr;
-    PQV_TRY(resolve_rows(ctx, handle, rows, n_table, dim, &D, &d_rows));
+    bool gathered = false;
+    if (!rows) {
+        // a resident table spread over several devices: the selected rows are collected on the first device, in selection
+        // order, and swept there as a dense block
+        Dataset *mds = find_dataset(ctx, handle);
+        if (mds && mds->shards.size() > 1) {
+            if (mds->dim != dim) return fail(PQV_EINVAL, "dimension mismatch: dataset has %u, call has %u", mds->dim, dim);
+            if (n_table > mds->n_rows) return fail(PQV_EINVAL, "n = %llu exceeds the dataset's %llu rows", (unsigned long long)n_table, (unsigned long long)mds->n_rows);
+            if (n_sel > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "row ids are u32");
+            std::vector<uint32_t> ids32(n_sel);
+            for (u64 i = 0; i < n_sel; ++i) ids32[i] = row_sel ? (uint32_t)row_sel[i] : (uint32_t)i;
+            D = &ctx->devs[mds->shards[0].di];
+            DevGuard g0(D->dev);
+            PQV_TRY(D->d_tmp_rows.ensure((size_t)n_sel * dim));
+            PQV_TRY(gather_rows_multi(ctx, *mds, ids32.data(), n_sel, *D, D->d_tmp_rows.p));
+            d_rows = D->d_tmp_rows.p;
+            gathered = true;
+        }
+    }
+    if (!gathered) PQV_TRY(resolve_rows(ctx, handle, rows, n_table, dim, &D, &d_rows));
     DevGuard guard(D->dev);
     const uint32_t *d_ids = nullptr;
-    if (row_sel) {
+    if (row_sel && !gathered) {
         std::vector<uint32_t> ids32(n_sel);
         for (u64 i = 0; i < n_sel; ++i) ids32[i] = (uint32_t)row_sel[i];
         PQV_TRY(D->d_row_ids.ensure(n_sel));

@@ -858,14 +858,24 @@ int pqv_kmeans_train(pqv_ctx *ctx, uint64_t handle, uint32_t n_clusters, uint32_
     std::lock_guard<std::mutex> lk(ctx->mu);
     Dataset *ds = find_dataset(ctx, handle);
     if (!ds) return fail(PQV_EHANDLE, "unknown dataset handle %llu", (unsigned long long)handle);
-    if (ds->shards.size() != 1) return fail(PQV_EINVAL, "pqv_kmeans_train needs a single-device dataset");
     if (ds->n_rows == 0) return fail(PQV_EINVAL, "Cannot build IVF index with zero vectors");
     if (n_clusters > ds->n_rows) return fail(PQV_EINVAL, "n_clusters cannot exceed number of vectors");
     Shard &sh = ds->shards[0];
     DeviceState &D = ctx->devs[sh.di];
     DevGuard guard(D.dev);
     uint32_t iters = 0;
-    PQV_TRY(kmeans_train_device(D, sh.d_data, ds->n_rows, ds->dim, n_clusters, max_iters, seed, sum_workers, &iters, nullptr));
+    const float *d_rows = sh.d_data;
+    if (ds->shards.size() > 1) {
+        // a table spread over several devices: k_means sees ALL rows in table order -- they are collected on the first device
+        // (this entry point is the reference's k_means over a training set, which pqv_ivf_build keeps to <= 100 000 rows)
+        if (ds->n_rows > 0xFFFFFFFFull) return fail(PQV_ELIMIT, "row ids are u32");
+        std::vector<uint32_t> all(ds->n_rows);
+        for (u64 i = 0; i < ds->n_rows; ++i) all[i] = (uint32_t)i;
+        PQV_TRY(D.d_tmp_rows.ensure((size_t)ds->n_rows * ds->dim));
+        PQV_TRY(gather_rows_multi(ctx, *ds, all.data(), ds->n_rows, D, D.d_tmp_rows.p));
+        d_rows = D.d_tmp_rows.p;
+    }
+    PQV_TRY(kmeans_train_device(D, d_rows, ds->n_rows, ds->dim, n_clusters, max_iters, seed, sum_workers, &iters, nullptr));
     CU_TRY(cudaMemcpyAsync(out_centroids, D.d_centroids.p, (size_t)n_clusters * ds->dim * 4, cudaMemcpyDeviceToHost, D.stream));
     CU_TRY(cudaStreamSynchronize(D.stream));
     if (out_iters) *out_iters = iters;

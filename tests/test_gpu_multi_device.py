@@ -184,3 +184,25 @@ def test_array_distance_arm_over_several_shards(mctx):
             assert rows.tolist() == keep[er].tolist()
             assert np.asarray(dist).view(np.uint64).tolist() == np.asarray(ed).view(np.uint64).tolist()
         ds.drop()
+
+
+def test_kmeans_train_and_min_dist_update_over_several_shards(mctx, sctx):
+    """the two k_means helpers that need rows from everywhere (pqv_kmeans_train: every row in table order;
+    pqv_min_dist_update: a selection of rows) collect them on the first device: same bits as over one device / the oracle"""
+    rng = np.random.default_rng(41)
+    n, dim, C = 9_001, 24, 17
+    data = rng.random((n, dim), dtype=np.float32)
+    mds, sds = mctx.dataset_from(data), sctx.dataset_from(data)
+    mc = mctx.kmeans_train(mds, C, max_iters=3, seed=5, sum_workers=4)
+    sc = sctx.kmeans_train(sds, C, max_iters=3, seed=5, sum_workers=4)
+    assert mc.view(np.uint32).tolist() == sc.view(np.uint32).tolist()
+    sel = rng.permutation(n)[:4000].astype(np.uint64)
+    c0, c1 = data[17], data[4242]
+    md = mctx.min_dist_update(mds, sel, c0)
+    assert md.view(np.uint32).tolist() == O.distances(data[sel.astype(np.int64)], c0, 0).view(np.uint32).tolist()
+    mctx.min_dist_update(mds, sel, c1, md)
+    exp = np.minimum(O.distances(data[sel.astype(np.int64)], c0, 0), O.distances(data[sel.astype(np.int64)], c1, 0))
+    assert md.view(np.uint32).tolist() == exp.view(np.uint32).tolist()
+    full = mctx.min_dist_update(mds, None, c0)          # no selection: every row, in table order
+    assert full.view(np.uint32).tolist() == O.distances(data, c0, 0).view(np.uint32).tolist()
+    mds.drop(); sds.drop()
