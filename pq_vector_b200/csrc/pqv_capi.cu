@@ -606,6 +606,7 @@ struct pqv_ctx {
     int occ_override = 0;
     int scan_variant = 0;
     int gather_variant = 0;
+    int seq_gather_variant = 0;
     PeerExchange peer;
     // coalescing front door for concurrent single-query callers (pqv_l2_topk_coalesced)
     struct CoalesceReq {
@@ -681,6 +682,7 @@ struct ScanGeom {
     size_t smem;
     bool vec4;
     bool gather = false;
+    int seq_variant = 0;
 };
 
 // cudaFuncSetAttribute(MaxDynamicSharedMemorySize) is sticky per kernel: only ever raise it
@@ -785,6 +787,31 @@ static int gather_variant_dispatch(int v, const pqv::ScanParams &p, uint32_t gri
     }
 }
 
+// ... and of the gathered SEQUENTIAL-order kernel (PQV_SEQ_GATHER_VARIANT=n; 0 = the shipped <8 row pairs, two CTAs per SM>)
+template <int RB, int MINB>
+int seq_gather_variant_go(const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStream_t st, int *occ_out) {
+    auto kern = pqv::l2_scan_topk_kernel<1, true, true, SCAN_WARPS, RB, 1, MINB>;
+    PQV_TRY(ensure_dyn_smem(reinterpret_cast<const void *>(kern), smem));
+    if (occ_out) {
+        CU_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(occ_out, kern, SCAN_WARPS * 32, smem));
+        return PQV_OK;
+    }
+    kern<<<grid, SCAN_WARPS * 32, smem, st>>>(p);
+    CU_TRY(cudaGetLastError());
+    return PQV_OK;
+}
+static const ScanVariant kSeqGatherVariants[] = {{8, 1, 2}, {16, 1, 2}, {16, 1, 1}, {4, 1, 2}, {4, 1, 3}, {8, 1, 1}};
+static int seq_gather_variant_dispatch(int v, const pqv::ScanParams &p, uint32_t grid, size_t smem, cudaStream_t st, int *occ_out) {
+    switch (v) {
+        case 1: return seq_gather_variant_go<16, 2>(p, grid, smem, st, occ_out);
+        case 2: return seq_gather_variant_go<16, 1>(p, grid, smem, st, occ_out);
+        case 3: return seq_gather_variant_go<4, 2>(p, grid, smem, st, occ_out);
+        case 4: return seq_gather_variant_go<4, 3>(p, grid, smem, st, occ_out);
+        case 5: return seq_gather_variant_go<8, 1>(p, grid, smem, st, occ_out);
+        default: return fail(PQV_EINVAL, "unknown PQV_SEQ_GATHER_VARIANT %d", v);
+    }
+}
+
 #define SCAN_DISPATCH(FN, order, vec4, gather, ...)                                                 \
     ((order) == 0 ? ((vec4) ? ((gather) ? FN<0, true, true>(__VA_ARGS__) : FN<0, true, false>(__VA_ARGS__))      \
                             : ((gather) ? FN<0, false, true>(__VA_ARGS__) : FN<0, false, false>(__VA_ARGS__)))   \
@@ -808,6 +835,18 @@ int scan_geometry(pqv_ctx *ctx, DeviceState &D, const float *d_data, u64 n, uint
     g->smem = scan_smem_bytes(order, g->vec4, dim, g->sort_n);
     g->variant = (order == 0 && g->vec4) ? (gather ? ctx->gather_variant : ctx->scan_variant) : 0;
     g->gather = gather;
+    g->seq_variant = (order == 1 && g->vec4 && gather) ? ctx->seq_gather_variant : 0;
+    if (g->seq_variant > 0) {
+        const ScanVariant &sv = kSeqGatherVariants[g->seq_variant];
+        int occ = 0;
+        pqv::ScanParams dummy{};
+        PQV_TRY(seq_gather_variant_dispatch(g->seq_variant, dummy, 0, g->smem, nullptr, &occ));
+        if (occ < 1) return fail(PQV_ELIMIT, "scan variant does not fit");
+        occ = std::min(occ, ctx->occ_override > 0 ? ctx->occ_override : sv.minb);
+        const u64 NGv = (n + 31) / 32;
+        g->grid = (uint32_t)std::min<u64>((u64)D.sm_count * occ, std::max<u64>(NGv, 1));
+        return PQV_OK;
+    }
     if (g->variant > 0) {
         const ScanVariant &sv = gather ? kGatherVariants[g->variant] : kVariants[g->variant];
         g->smem = (size_t)((dim + 3u) & ~3u) * 4 + (size_t)SCAN_WARPS * 32 * (32 * sv.cbv + 4) * 4 + (size_t)g->sort_n * 8;
@@ -863,7 +902,8 @@ int enqueue_scan(pqv_ctx *ctx, DeviceState &D, const float *d_data, const uint32
     p.ent_count = D.ent_count.p;
     p.dist_out = dist_out;
     if (time_it) CU_TRY(cudaEventRecord(D.ev[0], D.stream));
-    if (g.variant > 0 && g.gather) PQV_TRY(gather_variant_dispatch(g.variant, p, g.grid, g.smem, D.stream, nullptr));
+    if (g.seq_variant > 0) PQV_TRY(seq_gather_variant_dispatch(g.seq_variant, p, g.grid, g.smem, D.stream, nullptr));
+    else if (g.variant > 0 && g.gather) PQV_TRY(gather_variant_dispatch(g.variant, p, g.grid, g.smem, D.stream, nullptr));
     else if (g.variant > 0) PQV_TRY(scan_variant_dispatch(g.variant, p, g.grid, g.smem, D.stream, nullptr));
     else PQV_TRY(SCAN_DISPATCH(scan_launch_t, order, g.vec4, d_row_ids != nullptr, p, g.grid, g.smem, D.stream));
     if (time_it) CU_TRY(cudaEventRecord(D.ev[1], D.stream));
@@ -1345,6 +1385,7 @@ int pqv_init(pqv_ctx **out, const int *device_ids, int n_devices) {
     if (const char *s = getenv("PQV_SCAN_CTAS_PER_SM")) ctx->occ_override = atoi(s);
     if (const char *s = getenv("PQV_SCAN_VARIANT")) ctx->scan_variant = std::max(0, std::min(12, atoi(s)));
     if (const char *s = getenv("PQV_GATHER_VARIANT")) ctx->gather_variant = std::max(0, std::min(6, atoi(s)));
+    if (const char *s = getenv("PQV_SEQ_GATHER_VARIANT")) ctx->seq_gather_variant = std::max(0, std::min(5, atoi(s)));
     for (int id : ids) {
         DeviceState D;
         D.dev = id;
