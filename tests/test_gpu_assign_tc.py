@@ -135,6 +135,21 @@ def test_non_finite_and_huge_rows_take_the_exact_scan(ctx):
     assert t["overflow_rows"] >= 6
 
 
+@pytest.mark.parametrize("m", [1, 7, 255, 256, 257, 1500])
+def test_overflow_list_lengths_around_the_few_rows_switch(ctx, m):
+    """rows the filter hands to the full exact scan: lists of up to 256 rows take few_rows_assign_kernel (one warp per row and
+    32 centroids), longer ones the 64-row tiles -- the device-side count picks, both must give the reference's argmin"""
+    rng = np.random.default_rng(100 + m)
+    n, dim, C = 6000, 96, 70
+    data = rng.random((n, dim), dtype=np.float32)
+    cent = kmeans_like_centroids(data, C, rng)
+    bad = rng.permutation(n)[:m]
+    data[bad, rng.integers(0, dim, m)] = 1e20           # huge norm: the window is meaningless, the row goes to the scan
+    data[bad[: max(1, m // 3)], 0] = np.inf              # ... and some with no finite distance at all (default cluster 0)
+    t = check(ctx, data, cent)
+    assert t["overflow_rows"] >= m
+
+
 def test_non_finite_centroid_table(ctx):
     rng = np.random.default_rng(9)
     data = rng.random((2500, 48), dtype=np.float32)
